@@ -1,0 +1,227 @@
+/*
+ * vce.h -- C-ABI of the B200-native vcfeval matching engine ("vce").
+ *
+ * This is the drop-in boundary for the ONE hot path this repository rebuilds:
+ * the body of rtg-tools' SequenceEvaluator.run() between "variants + template
+ * loaded" and "mSynchronize.write(...)"
+ *   (reference: src/com/rtg/vcf/eval/SequenceEvaluator.java:87-155),
+ * i.e. PathFinder.bestPath() (PathFinder.java:129-214) with its Orientor /
+ * Path / HalfPath / HaplotypePlayback state, the MaxSumBoth tie-breaks,
+ * Path.calculateWeights (Path.java:424-453), the status merge
+ * (SequenceEvaluator.java:170-209), PhasingEvaluator.countMisphasings, and the
+ * RocContainer accumulate / sort / cumulative-sum (RocContainer.java:225-318).
+ *
+ * The reference has no FFI; a maintainer adds the JNI stub shown in
+ * INTEGRATION.md.  Everything here is plain C: pointers + sizes, caller owns
+ * every buffer, no exceptions cross the boundary, return 0 == OK.
+ *
+ * Coordinates: 0-based, end-exclusive.  Bases: N=0 A=1 C=2 G=3 T=4
+ * (reference: src/com/rtg/mode/DnaUtils.java:225-252); 5 = explicit unknown
+ * allele token (Allele.java:50-52).
+ */
+#ifndef VCE_H_
+#define VCE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status bits: identical to VariantId.java:40-50 ---- */
+#define VCE_STATUS_SKIPPED       0x01
+#define VCE_STATUS_GT_MATCH      0x02
+#define VCE_STATUS_ALLELE_MATCH  0x04
+#define VCE_STATUS_NO_MATCH      0x08
+#define VCE_STATUS_OUTSIDE_EVAL  0x10
+#define VCE_STATUS_ANY_MATCH     0x20
+
+/* ---- orientor kinds: Orientor.java ---- */
+enum {
+  VCE_ORIENT_UNPHASED      = 0, /* Orientor.UnphasedOrientor      :60-99   */
+  VCE_ORIENT_PHASED        = 1, /* Orientor.PhasedOrientor(false) :107-148 */
+  VCE_ORIENT_PHASED_INVERT = 2, /* Orientor.PhasedOrientor(true)           */
+  VCE_ORIENT_SQUASH_GT     = 3, /* Orientor.SQUASH_GT             :156-188 */
+  VCE_ORIENT_ALLELE_GT     = 4, /* Orientor.ALLELE_GT             :196-233 */
+  VCE_ORIENT_HAPLOID_POP   = 5, /* Orientor.HAPLOID_POP           :240-257 */
+  VCE_ORIENT_DIPLOID_POP   = 6, /* Orientor.DIPLOID_POP           :264-290 */
+  VCE_ORIENT_ALT           = 7  /* Orientor.AltOrientor           :297-338 */
+};
+
+/* ---- path preference: PathFinder.java:86-100 ---- */
+enum {
+  VCE_PREFER_SUM            = 0, /* MaxSumBoth.java:43-82           */
+  VCE_PREFER_CALLS_MIN_BASE = 1  /* MaxCallsMinBaseline.java:42-61  */
+};
+
+/* ---- error codes ---- */
+enum {
+  VCE_OK                  = 0,
+  VCE_ERR_NOT_INITIALISED = 1,
+  VCE_ERR_BAD_ARGUMENT    = 2,
+  VCE_ERR_CUDA            = 3,  /* CUDA runtime failure, see vce_last_error() */
+  VCE_ERR_NO_DEVICE       = 4,  /* no CUDA device: there is NO CPU fallback   */
+  VCE_ERR_CAPACITY        = 5,  /* a caller-provided output buffer was too small */
+  VCE_ERR_BEST_PATH_NULL  = 6,  /* SequenceEvaluator.java:105-116 (NullPointerException) */
+  VCE_ERR_MOVE_IN_VARIANT = 7,  /* HaplotypePlayback.java:260 IllegalStateException during a too-complex skip */
+  VCE_ERR_UNSUPPORTED     = 8
+};
+
+#define VCE_MAX_PLOIDY 4
+
+/*
+ * One side (baseline or calls) of one reference sequence, exactly the data a
+ * List<Variant> holds after loading (Variant.java / GtIdVariant.java /
+ * Allele.java), in load order (ascending id).  Structure-of-arrays.
+ *
+ * Allele slots: variant i owns slots [allele_off[i], allele_off[i+1]); slot k
+ * within the variant is allele id k-1, i.e. the array is indexed by GT+1 like
+ * Variant.mAlleles (Variant.java:241): slot 0 = missing (-1), slot 1 = REF.
+ * A slot with allele_null[s] != 0 is a Java null Allele ("play nothing").
+ * Allele bases are nt[allele_nt_off[s] .. allele_nt_off[s+1]).
+ * The variant locus (start,end) is derived by the engine as the bounds of the
+ * non-null alleles (Allele.getAlleleBounds, Allele.java:195-206).
+ */
+typedef struct vce_variants {
+  int32_t        n;             /* number of variants                              */
+  int32_t        gt_ploidy;     /* entries per variant in gt[]; 0 = no GT (AllAlts factory) */
+  const int32_t* id;            /* [n] VariantId.getId(): 1-based record ordinal, strictly ascending */
+  const uint8_t* phased;        /* [n] Variant.isPhased()                          */
+  const uint8_t* status_in;     /* [n] pre-set status bits (only OUTSIDE_EVAL is meaningful) or NULL */
+  const int8_t*  gt;            /* [n*gt_ploidy] GtIdVariant.alleleIds(), -1 = missing */
+  const int32_t* allele_off;    /* [n+1]                                           */
+  int32_t        n_slots;       /* == allele_off[n]                                */
+  const int32_t* allele_start;  /* [n_slots]                                       */
+  const int32_t* allele_end;    /* [n_slots]                                       */
+  const uint8_t* allele_null;   /* [n_slots]                                       */
+  const int32_t* allele_nt_off; /* [n_slots+1]                                     */
+  const uint8_t* nt;            /* [allele_nt_off[n_slots]] packed allele bases    */
+} vce_variants;
+
+typedef struct vce_sequence {
+  const char*    name;          /* sequence name (only used in warning text)       */
+  const uint8_t* template_bases;/* [template_len] 0..4, what SequencesReader.read() returns */
+  int32_t        template_len;
+  vce_variants   baseline;
+  vce_variants   calls;
+} vce_sequence;
+
+/* PathFinder.Config (PathFinder.java:51-101) + the orientor pairs VcfEvalTask builds (:122-128,195-208). */
+typedef struct vce_config {
+  int32_t n_passes;             /* 1, or 2 for two-pass (diploid then allele matching on FN/FP) */
+  int32_t baseline_orientor[2]; /* per pass                                        */
+  int32_t calls_orientor[2];
+  int32_t ploidy[2];            /* Orientor.haplotypes() per pass                  */
+  int32_t max_paths;            /* ToolsGlobalFlags VCFEVAL_MAX_PATHS, default 50000      */
+  int32_t max_iterations;       /* VCFEVAL_MAX_ITERATIONS, default 10000000               */
+  int32_t prune_no_ops;         /* VCFEVAL_PRUNE_NO_OPS, default 1                        */
+  int32_t flag_alternates;      /* VCFEVAL_FLAG_ALTERNATES, default 0                     */
+  int32_t preference;           /* VCE_PREFER_*                                           */
+} vce_config;
+
+/* One "Evaluation too complex" event, PathFinder.java:162-169. */
+typedef struct vce_warning {
+  int32_t pass;                 /* 0 or 1                                          */
+  int32_t paths;                /* sortedPaths.size()                              */
+  int32_t iterations;           /* currentIterations                               */
+  int32_t start1;               /* lastSyncPos + 1                                 */
+  int32_t end1;                 /* mCurrentMaxPos + 2                              */
+} vce_warning;
+
+/* Per-side results, indexed like the input arrays (load order). Caller-allocated. */
+typedef struct vce_side_result {
+  uint8_t* status;              /* [n] VariantId status bits after SequenceEvaluator.mergeVariants */
+  int8_t*  allele_ids;          /* [n*VCE_MAX_PLOIDY] OrientedVariant.alleleIds() of the chosen orientation
+                                   (valid when GT_MATCH or ALLELE_MATCH), unused entries = -2 */
+  uint8_t* original;            /* [n] OrientedVariant.isOriginal()                */
+  double*  weight;              /* [n] OrientedVariant.getWeight() (calls side; 0 on baseline) */
+  int32_t* sync_id;             /* [n] optional (may be NULL): index into sync_points[pass] of the sync
+                                   region holding the variant (InterleavingEvalSynchronizer.floorSyncPos :71-83),
+                                   pass 0 for GT_MATCH, pass 1 when a pass-2 list exists and the variant was not GT-matched */
+} vce_side_result;
+
+typedef struct vce_sequence_result {
+  vce_side_result baseline;
+  vce_side_result calls;
+  int32_t*     sync_points[2];  /* Path.getSyncPoints() per pass; caller-allocated        */
+  int32_t      sync_cap[2];     /* capacity; (n_baseline + n_calls + 2) always suffices   */
+  int32_t      n_sync[2];       /* out                                                    */
+  int32_t      phasing[3];      /* out: misPhasings, correctPhasings, unphaseable (PhasingEvaluator.java:55-142) */
+  vce_warning* warnings;        /* caller-allocated                                       */
+  int32_t      warn_cap;
+  int32_t      n_warnings;      /* out (may exceed warn_cap: then only warn_cap are written) */
+  int32_t      error;           /* out: VCE_OK or a per-sequence VCE_ERR_*                */
+  int64_t      n_regions;       /* out: independent search regions the engine ran (diagnostic) */
+  int64_t      n_iterations;    /* out: total best-first iterations (diagnostic)          */
+} vce_sequence_result;
+
+/* ---- ROC (RocContainer) ---- */
+typedef struct vce_roc_in {
+  int64_t        n;             /* number of addRocLine calls, in arrival order (RocContainer.java:225) */
+  const double*  score;         /* [n] RocSortValueExtractor value; NaN/Inf -> "None" bucket (:232-237) */
+  const double*  tp;            /* [n] tpWeight                                            */
+  const double*  fp;            /* [n] fpWeight                                            */
+  const double*  tp_raw;        /* [n] tpRaw                                               */
+  const uint32_t* filter_mask;  /* [n] bit f set = RocFilter f accepts the record (or NULL = all) */
+  int32_t        n_filters;     /* <= 32                                                   */
+  int32_t        ascending;     /* RocSortOrder: 0 = DESCENDING (default), 1 = ASCENDING   */
+} vce_roc_in;
+
+/*
+ * Output: for every filter, the TreeMap iteration of RocContainer.writeRocs
+ * (:296-309): distinct score buckets in comparator order with the CUMULATIVE
+ * tp / fp / tpRaw sums after adding that bucket (plain sequential double +=,
+ * bucket sums first accumulated in arrival order :251-258).
+ * Row formatting / the 3-dp merge (:298-312) stays with the caller.
+ */
+typedef struct vce_roc_out {
+  int64_t  cap;                 /* rows available per filter in the arrays below     */
+  int64_t* n_rows;              /* [n_filters] out                                   */
+  double*  threshold;           /* [n_filters*cap] bucket score (NaN for the None bucket) */
+  double*  cum_tp;              /* [n_filters*cap]                                   */
+  double*  cum_fp;              /* [n_filters*cap]                                   */
+  double*  cum_tp_raw;          /* [n_filters*cap]                                   */
+  int64_t* no_score;            /* out: mNoScoreVariants (one per addRocLine with NaN/Inf score) */
+} vce_roc_out;
+
+/* ---- life cycle ---- */
+int         vce_init(int device);               /* selects the CUDA device; fails with VCE_ERR_NO_DEVICE when none */
+void        vce_shutdown(void);
+const char* vce_last_error(void);               /* thread-local message for the last non-zero return */
+const char* vce_version(void);
+
+/* Default configuration = `rtg vcfeval` defaults (diploid, unphased orientors, split mode single pass). */
+void        vce_default_config(vce_config* cfg);
+
+/*
+ * Synchronous whole-batch evaluation with HOST buffers (what the JNI shim
+ * calls): replaces SequenceEvaluator.run() for every sequence in the batch.
+ * Thread-safe; one CUDA stream per call.
+ */
+int vce_submit(const vce_config* cfg, int32_t n_seq, const vce_sequence* seqs,
+               vce_sequence_result* results);
+
+/*
+ * Staged variant used to time the device path with inputs already resident in
+ * HBM: create = host packing + H2D, run = all kernels (may be called
+ * repeatedly), fetch = D2H + result assembly into caller buffers.
+ */
+typedef struct vce_job vce_job;
+int  vce_job_create(const vce_config* cfg, int32_t n_seq, const vce_sequence* seqs, vce_job** job);
+int  vce_job_run(vce_job* job);
+int  vce_job_fetch(vce_job* job, vce_sequence_result* results);
+void vce_job_destroy(vce_job* job);
+/* Diagnostics of the last vce_job_run: kernel launches, device milliseconds (CUDA events on the job's stream). */
+int  vce_job_stats(const vce_job* job, int64_t* n_launches, double* device_ms, double* search_kernel_ms,
+                   int64_t* n_regions, int64_t* n_escalated);
+
+/* RocContainer accumulate + sort + cumulative scan on the device. */
+int vce_roc(const vce_roc_in* in, vce_roc_out* out);
+
+/* Formats the reference's warning text (PathFinder.java:163). Returns bytes written (excluding NUL). */
+int vce_format_warning(const vce_warning* w, const char* seq_name, char* buf, int32_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VCE_H_ */

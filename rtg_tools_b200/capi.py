@@ -1,0 +1,406 @@
+"""ctypes view of include/vce.h plus numpy containers for the flat batch format.
+
+This is plumbing: it owns no algorithm.  `Library` wraps a shared object that
+exports the vce C-ABI (`vce_submit`, `vce_roc`, ...).  The product library is
+rtg_tools_b200/csrc/libvce.so; tests and bench.py's cpu_baseline leg also point
+it at the oracle (oracle/liboracle.so, symbol prefix `oracle_`) so that both are
+driven through byte-identical buffers.
+"""
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence as Seq
+
+import numpy as np
+
+MAX_PLOIDY = 4
+
+STATUS_SKIPPED = 0x01
+STATUS_GT_MATCH = 0x02
+STATUS_ALLELE_MATCH = 0x04
+STATUS_NO_MATCH = 0x08
+STATUS_OUTSIDE_EVAL = 0x10
+STATUS_ANY_MATCH = 0x20
+
+ORIENT_UNPHASED = 0
+ORIENT_PHASED = 1
+ORIENT_PHASED_INVERT = 2
+ORIENT_SQUASH_GT = 3
+ORIENT_ALLELE_GT = 4
+ORIENT_HAPLOID_POP = 5
+ORIENT_DIPLOID_POP = 6
+ORIENT_ALT = 7
+
+PREFER_SUM = 0
+PREFER_CALLS_MIN_BASE = 1
+
+ERR_NAMES = {
+    0: "VCE_OK", 1: "VCE_ERR_NOT_INITIALISED", 2: "VCE_ERR_BAD_ARGUMENT", 3: "VCE_ERR_CUDA", 4: "VCE_ERR_NO_DEVICE",
+    5: "VCE_ERR_CAPACITY", 6: "VCE_ERR_BEST_PATH_NULL", 7: "VCE_ERR_MOVE_IN_VARIANT", 8: "VCE_ERR_UNSUPPORTED",
+}
+
+_i32p = C.POINTER(C.c_int32)
+_u8p = C.POINTER(C.c_uint8)
+_i8p = C.POINTER(C.c_int8)
+_f64p = C.POINTER(C.c_double)
+_i64p = C.POINTER(C.c_int64)
+_u32p = C.POINTER(C.c_uint32)
+
+
+class CVariants(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32), ("gt_ploidy", C.c_int32),
+        ("id", _i32p), ("phased", _u8p), ("status_in", _u8p), ("gt", _i8p),
+        ("allele_off", _i32p), ("n_slots", C.c_int32),
+        ("allele_start", _i32p), ("allele_end", _i32p), ("allele_null", _u8p),
+        ("allele_nt_off", _i32p), ("nt", _u8p),
+    ]
+
+
+class CSequence(C.Structure):
+    _fields_ = [
+        ("name", C.c_char_p), ("template_bases", _u8p), ("template_len", C.c_int32),
+        ("baseline", CVariants), ("calls", CVariants),
+    ]
+
+
+class CConfig(C.Structure):
+    _fields_ = [
+        ("n_passes", C.c_int32), ("baseline_orientor", C.c_int32 * 2), ("calls_orientor", C.c_int32 * 2),
+        ("ploidy", C.c_int32 * 2), ("max_paths", C.c_int32), ("max_iterations", C.c_int32),
+        ("prune_no_ops", C.c_int32), ("flag_alternates", C.c_int32), ("preference", C.c_int32),
+    ]
+
+
+class CWarning(C.Structure):
+    _fields_ = [("pass_", C.c_int32), ("paths", C.c_int32), ("iterations", C.c_int32),
+                ("start1", C.c_int32), ("end1", C.c_int32)]
+
+
+class CSideResult(C.Structure):
+    _fields_ = [("status", _u8p), ("allele_ids", _i8p), ("original", _u8p), ("weight", _f64p), ("sync_id", _i32p)]
+
+
+class CSequenceResult(C.Structure):
+    _fields_ = [
+        ("baseline", CSideResult), ("calls", CSideResult),
+        ("sync_points", _i32p * 2), ("sync_cap", C.c_int32 * 2), ("n_sync", C.c_int32 * 2),
+        ("phasing", C.c_int32 * 3),
+        ("warnings", C.POINTER(CWarning)), ("warn_cap", C.c_int32), ("n_warnings", C.c_int32),
+        ("error", C.c_int32), ("n_regions", C.c_int64), ("n_iterations", C.c_int64),
+    ]
+
+
+class CRocIn(C.Structure):
+    _fields_ = [("n", C.c_int64), ("score", _f64p), ("tp", _f64p), ("fp", _f64p), ("tp_raw", _f64p),
+                ("filter_mask", _u32p), ("n_filters", C.c_int32), ("ascending", C.c_int32)]
+
+
+class CRocOut(C.Structure):
+    _fields_ = [("cap", C.c_int64), ("n_rows", _i64p), ("threshold", _f64p), ("cum_tp", _f64p), ("cum_fp", _f64p),
+                ("cum_tp_raw", _f64p), ("no_score", _i64p)]
+
+
+def _ptr(a: Optional[np.ndarray], typ):
+    if a is None:
+        return C.cast(None, typ)
+    return a.ctypes.data_as(typ)
+
+
+# --------------------------------------------------------------------------- containers
+@dataclass
+class VariantSide:
+    """One side of one sequence in load order: the SoA image of List<Variant> (vce_variants)."""
+    id: np.ndarray
+    phased: np.ndarray
+    status_in: np.ndarray
+    gt: np.ndarray            # (n, gt_ploidy) int8
+    allele_off: np.ndarray    # n+1
+    allele_start: np.ndarray
+    allele_end: np.ndarray
+    allele_null: np.ndarray
+    allele_nt_off: np.ndarray
+    nt: np.ndarray
+
+    @property
+    def n(self) -> int:
+        return int(self.id.shape[0])
+
+    @property
+    def gt_ploidy(self) -> int:
+        return int(self.gt.shape[1]) if self.gt.ndim == 2 else 0
+
+    @staticmethod
+    def empty(gt_ploidy: int = 2) -> "VariantSide":
+        return VariantSide.from_variants([], gt_ploidy)
+
+    @staticmethod
+    def from_variants(variants, gt_ploidy: int = 2) -> "VariantSide":
+        """variants: iterable of dicts {id, phased, status, gt (list or None), alleles: [None | (start, end, bytes)]}
+        where alleles[k] is allele id k-1 (slot 0 = missing, slot 1 = REF), cf. Variant.java:241."""
+        variants = list(variants)
+        n = len(variants)
+        ids = np.zeros(n, np.int32)
+        phased = np.zeros(n, np.uint8)
+        status = np.zeros(n, np.uint8)
+        gt = np.full((n, gt_ploidy), -2, np.int8)
+        off = np.zeros(n + 1, np.int32)
+        a_start, a_end, a_null, nt_off, nts = [], [], [], [0], []
+        total = 0
+        for i, v in enumerate(variants):
+            ids[i] = v["id"]
+            phased[i] = 1 if v.get("phased") else 0
+            status[i] = v.get("status", 0)
+            if v.get("gt") is not None and gt_ploidy:
+                g = list(v["gt"])
+                assert len(g) == gt_ploidy, (g, gt_ploidy)
+                gt[i, :] = g
+            for a in v["alleles"]:
+                if a is None:
+                    a_start.append(0)
+                    a_end.append(0)
+                    a_null.append(1)
+                else:
+                    a_start.append(a[0])
+                    a_end.append(a[1])
+                    a_null.append(0)
+                    nts.append(bytes(a[2]))
+                    total += len(a[2])
+                nt_off.append(total)
+            off[i + 1] = len(a_null)
+        nt = np.frombuffer(b"".join(nts), np.uint8).copy() if nts else np.zeros(0, np.uint8)
+        return VariantSide(ids, phased, status, gt, off, np.asarray(a_start, np.int32), np.asarray(a_end, np.int32),
+                           np.asarray(a_null, np.uint8), np.asarray(nt_off, np.int32), nt)
+
+    def to_c(self) -> CVariants:
+        cv = CVariants()
+        cv.n = self.n
+        cv.gt_ploidy = self.gt_ploidy
+        self.gt = np.ascontiguousarray(self.gt, np.int8)
+        cv.id = _ptr(self.id, _i32p)
+        cv.phased = _ptr(self.phased, _u8p)
+        cv.status_in = _ptr(self.status_in, _u8p)
+        cv.gt = _ptr(self.gt, _i8p)
+        cv.allele_off = _ptr(self.allele_off, _i32p)
+        cv.n_slots = int(self.allele_off[-1])
+        cv.allele_start = _ptr(self.allele_start, _i32p)
+        cv.allele_end = _ptr(self.allele_end, _i32p)
+        cv.allele_null = _ptr(self.allele_null, _u8p)
+        cv.allele_nt_off = _ptr(self.allele_nt_off, _i32p)
+        cv.nt = _ptr(self.nt, _u8p)
+        return cv
+
+
+@dataclass
+class Sequence:
+    name: str
+    template: np.ndarray  # uint8 0..4
+    baseline: VariantSide
+    calls: VariantSide
+
+    def to_c(self) -> CSequence:
+        cs = CSequence()
+        self._name_b = self.name.encode()
+        cs.name = self._name_b
+        self.template = np.ascontiguousarray(self.template, np.uint8)
+        cs.template_bases = _ptr(self.template, _u8p)
+        cs.template_len = int(self.template.shape[0])
+        cs.baseline = self.baseline.to_c()
+        cs.calls = self.calls.to_c()
+        return cs
+
+
+@dataclass
+class Config:
+    """PathFinder.Config (PathFinder.java:51-101) + the orientor pairs of VcfEvalTask.java:122-128."""
+    n_passes: int = 1
+    baseline_orientor: Seq[int] = (ORIENT_UNPHASED, ORIENT_SQUASH_GT)
+    calls_orientor: Seq[int] = (ORIENT_UNPHASED, ORIENT_SQUASH_GT)
+    ploidy: Seq[int] = (2, 1)
+    max_paths: int = 50000
+    max_iterations: int = 10000000
+    prune_no_ops: bool = True
+    flag_alternates: bool = False
+    preference: int = PREFER_SUM
+
+    def to_c(self) -> CConfig:
+        c = CConfig()
+        c.n_passes = self.n_passes
+        for i in range(2):
+            c.baseline_orientor[i] = self.baseline_orientor[i]
+            c.calls_orientor[i] = self.calls_orientor[i]
+            c.ploidy[i] = self.ploidy[i]
+        c.max_paths = self.max_paths
+        c.max_iterations = self.max_iterations
+        c.prune_no_ops = int(self.prune_no_ops)
+        c.flag_alternates = int(self.flag_alternates)
+        c.preference = self.preference
+        return c
+
+
+@dataclass
+class SideResult:
+    status: np.ndarray
+    allele_ids: np.ndarray  # (n, MAX_PLOIDY) int8
+    original: np.ndarray
+    weight: np.ndarray
+    sync_id: np.ndarray
+
+    @staticmethod
+    def alloc(n: int) -> "SideResult":
+        return SideResult(np.zeros(n, np.uint8), np.full((n, MAX_PLOIDY), -2, np.int8), np.zeros(n, np.uint8),
+                          np.zeros(n, np.float64), np.zeros(n, np.int32))
+
+    def to_c(self) -> CSideResult:
+        r = CSideResult()
+        r.status = _ptr(self.status, _u8p)
+        r.allele_ids = _ptr(self.allele_ids, _i8p)
+        r.original = _ptr(self.original, _u8p)
+        r.weight = _ptr(self.weight, _f64p)
+        r.sync_id = _ptr(self.sync_id, _i32p)
+        return r
+
+
+@dataclass
+class SequenceResult:
+    baseline: SideResult
+    calls: SideResult
+    sync_points: List[np.ndarray]
+    phasing: List[int] = field(default_factory=lambda: [0, 0, 0])
+    warnings: List[dict] = field(default_factory=list)
+    error: int = 0
+    n_regions: int = 0
+    n_iterations: int = 0
+
+
+WARN_CAP = 64
+
+
+class Library:
+    """A shared object exporting the vce C-ABI, optionally under a symbol prefix."""
+
+    def __init__(self, path: str, prefix: str = "vce_"):
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                "%s is missing: build it first (python -c 'import __graft_entry__ as g; g.build()')" % path)
+        self.path = path
+        self.prefix = prefix
+        self.lib = C.CDLL(path)
+        self._submit = self._sym("submit" if prefix == "vce_" else "vce_submit")
+        self._submit.restype = C.c_int
+        self._submit.argtypes = [C.POINTER(CConfig), C.c_int32, C.POINTER(CSequence), C.POINTER(CSequenceResult)]
+        self._roc = self._sym("roc" if prefix == "vce_" else "vce_roc")
+        self._roc.restype = C.c_int
+        self._roc.argtypes = [C.POINTER(CRocIn), C.POINTER(CRocOut)]
+
+    def _sym(self, name):
+        return getattr(self.lib, self.prefix + name)
+
+    def has(self, name) -> bool:
+        return hasattr(self.lib, self.prefix + name)
+
+    def last_error(self) -> str:
+        if self.prefix == "vce_":
+            f = self.lib.vce_last_error
+            f.restype = C.c_char_p
+            s = f()
+            return s.decode() if s else ""
+        return ""
+
+    # ---- batch packing shared by submit() and the staged job API
+    @staticmethod
+    def pack(cfg: Config, seqs: List[Sequence]):
+        ccfg = cfg.to_c()
+        n = len(seqs)
+        cseqs = (CSequence * max(n, 1))()
+        cres = (CSequenceResult * max(n, 1))()
+        results = []
+        keep = []
+        for i, s in enumerate(seqs):
+            cseqs[i] = s.to_c()
+            r = SequenceResult(SideResult.alloc(s.baseline.n), SideResult.alloc(s.calls.n),
+                               [np.zeros(s.baseline.n + s.calls.n + 2, np.int32) for _ in range(2)])
+            warn = (CWarning * WARN_CAP)()
+            cr = cres[i]
+            cr.baseline = r.baseline.to_c()
+            cr.calls = r.calls.to_c()
+            for p in range(2):
+                cr.sync_points[p] = _ptr(r.sync_points[p], _i32p)
+                cr.sync_cap[p] = int(r.sync_points[p].shape[0])
+            cr.warnings = warn
+            cr.warn_cap = WARN_CAP
+            keep.append(warn)
+            results.append(r)
+        return ccfg, cseqs, cres, results, keep
+
+    @staticmethod
+    def unpack(cres, results, keep):
+        for i, r in enumerate(results):
+            cr = cres[i]
+            for p in range(2):
+                r.sync_points[p] = r.sync_points[p][: cr.n_sync[p]].copy()
+            r.phasing = [cr.phasing[0], cr.phasing[1], cr.phasing[2]]
+            r.warnings = [dict(pass_=keep[i][k].pass_, paths=keep[i][k].paths, iterations=keep[i][k].iterations,
+                               start1=keep[i][k].start1, end1=keep[i][k].end1)
+                          for k in range(min(cr.n_warnings, WARN_CAP))]
+            r.error = cr.error
+            r.n_regions = cr.n_regions
+            r.n_iterations = cr.n_iterations
+        return results
+
+    def submit(self, cfg: Config, seqs: List[Sequence], threads: int = 0) -> List[SequenceResult]:
+        ccfg, cseqs, cres, results, keep = self.pack(cfg, seqs)
+        if threads > 1 and self.has("vce_submit_mt"):
+            f = self._sym("vce_submit_mt")
+            f.restype = C.c_int
+            f.argtypes = [C.POINTER(CConfig), C.c_int32, C.POINTER(CSequence), C.POINTER(CSequenceResult), C.c_int32]
+            rc = f(C.byref(ccfg), len(seqs), cseqs, cres, threads)
+        else:
+            rc = self._submit(C.byref(ccfg), len(seqs), cseqs, cres)
+        self.unpack(cres, results, keep)
+        if rc != 0 and all(r.error == 0 for r in results):
+            raise RuntimeError("%ssubmit failed: %s %s" % (self.prefix, ERR_NAMES.get(rc, rc), self.last_error()))
+        return results
+
+    def roc(self, score, tp, fp, tp_raw, filter_mask=None, n_filters=1, ascending=False):
+        """Returns (rows per filter: list of (threshold, cum_tp, cum_fp, cum_tp_raw) arrays, no_score count)."""
+        score = np.ascontiguousarray(score, np.float64)
+        tp = np.ascontiguousarray(tp, np.float64)
+        fp = np.ascontiguousarray(fp, np.float64)
+        tp_raw = np.ascontiguousarray(tp_raw, np.float64)
+        n = int(score.shape[0])
+        cin = CRocIn()
+        cin.n = n
+        cin.score = _ptr(score, _f64p)
+        cin.tp = _ptr(tp, _f64p)
+        cin.fp = _ptr(fp, _f64p)
+        cin.tp_raw = _ptr(tp_raw, _f64p)
+        if filter_mask is not None:
+            filter_mask = np.ascontiguousarray(filter_mask, np.uint32)
+        cin.filter_mask = _ptr(filter_mask, _u32p)
+        cin.n_filters = n_filters
+        cin.ascending = int(ascending)
+        cap = max(n, 1)
+        n_rows = np.zeros(n_filters, np.int64)
+        thr = np.zeros(n_filters * cap, np.float64)
+        ctp = np.zeros(n_filters * cap, np.float64)
+        cfp = np.zeros(n_filters * cap, np.float64)
+        craw = np.zeros(n_filters * cap, np.float64)
+        no_score = np.zeros(1, np.int64)
+        cout = CRocOut()
+        cout.cap = cap
+        cout.n_rows = _ptr(n_rows, _i64p)
+        cout.threshold = _ptr(thr, _f64p)
+        cout.cum_tp = _ptr(ctp, _f64p)
+        cout.cum_fp = _ptr(cfp, _f64p)
+        cout.cum_tp_raw = _ptr(craw, _f64p)
+        cout.no_score = _ptr(no_score, _i64p)
+        rc = self._roc(C.byref(cin), C.byref(cout))
+        if rc != 0:
+            raise RuntimeError("%sroc failed: %s %s" % (self.prefix, ERR_NAMES.get(rc, rc), self.last_error()))
+        rows = []
+        for f in range(n_filters):
+            k = int(n_rows[f])
+            s = f * cap
+            rows.append((thr[s:s + k].copy(), ctp[s:s + k].copy(), cfp[s:s + k].copy(), craw[s:s + k].copy()))
+        return rows, int(no_score[0])

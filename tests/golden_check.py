@@ -1,0 +1,102 @@
+"""Shared checker: replay one reference fixture through an engine and compare with the golden outputs."""
+import ref_host
+
+
+def _body(text):
+    return [l for l in text.splitlines() if l and not l.startswith("#")]
+
+
+def _info(line):
+    out = {}
+    for kv in line.split("\t")[7].split(";"):
+        p = kv.split("=", 1)
+        out[p[0]] = p[1] if len(p) == 2 else True
+    return out
+
+
+def _key(line):
+    f = line.split("\t")
+    return (f[0], f[1], f[3], f[4])
+
+
+def _weight_str(w):
+    # WithInfoEvalSynchronizer.java:137 String.format("%.3g", w) when |w - 1| > 0.001
+    return None if abs(w - 1.0) <= 0.001 else format(w, "#.3g")
+
+
+def check_scenario(engine, sc, cfg_over=None):
+    """Returns the list of output names that were compared."""
+    rr = ref_host.run_vcfeval(engine, sc["template_fa"], sc["baseline_vcf"], sc["calls_vcf"], sc["args"], cfg_over)
+    exp = sc["expected"]
+    checked = []
+    p = rr.params
+    if "weighted_roc.tsv" in exp:
+        assert rr.roc_tsv == exp["weighted_roc.tsv"], "weighted_roc.tsv differs"
+        checked.append("weighted_roc.tsv")
+    if p.output_mode == "split":
+        sets = {"tp.vcf": [], "fp.vcf": [], "tp-baseline.vcf": [], "fn.vcf": []}
+        for rec, cls, w, sync, st in rr.call_class:
+            if cls == "TP":
+                sets["tp.vcf"].append(_key(rec.line))
+            elif cls in ("FP", "FP_CA"):
+                sets["fp.vcf"].append(_key(rec.line))
+        for rec, cls, sync, st in rr.base_class:
+            if cls == "TP":
+                sets["tp-baseline.vcf"].append(_key(rec.line))
+            elif cls in ("FN", "FN_CA"):
+                sets["fn.vcf"].append(_key(rec.line))
+        for name, got in sets.items():
+            if name in exp:
+                want = [_key(l) for l in _body(exp[name])]
+                assert got == want, "%s differs: %s vs %s" % (name, got, want)
+                checked.append(name)
+    if p.output_mode == "annotate":
+        for side, fname, classes in (("calls", "calls.vcf", rr.call_class), ("baseline", "baseline.vcf", rr.base_class)):
+            if fname not in exp:
+                continue
+            tag = "CALL" if side == "calls" else "BASE"
+            known = {}
+            for item in classes:
+                rec = item[0]
+                known[id(rec)] = item
+            text = sc["calls_vcf"] if side == "calls" else sc["baseline_vcf"]
+            _, recs = ref_host.parse_vcf(text)
+            order = {}
+            for r in recs:
+                order.setdefault(r.chrom, []).append(r)
+            got = []
+            # known records are found through the loaded variants (same VcfRecord objects are not shared between
+            # the two parses), so match by (chrom, refined ordinal)
+            per_chrom = {}
+            for item in classes:
+                per_chrom.setdefault(item[0].chrom, {})[item[0].line] = item
+            seq_names = [n for n, _ in ref_host.parse_fasta(sc["template_fa"])]
+            for chrom in seq_names:
+                for r in ref_host.sort_refine(order.get(chrom, [])):
+                    item = per_chrom.get(chrom, {}).get(r.line)
+                    if item is None:
+                        got.append((_key(r.line), "IGN", None, None))
+                    elif side == "calls":
+                        _, cls, w, sync, st = item
+                        wt = _weight_str(w) if cls in ("TP", "FP_CA") else None
+                        got.append((_key(r.line), cls, str(sync) if sync is not None else None, wt))
+                    else:
+                        _, cls, sync, st = item
+                        got.append((_key(r.line), cls, str(sync) if sync is not None else None, None))
+            want = []
+            for l in _body(exp[fname]):
+                info = _info(l)
+                want.append((_key(l), info.get(tag), info.get("SYNC"), info.get("CALL_WEIGHT")))
+            assert got == want, "%s differs:\n got %s\nwant %s" % (fname, got, want)
+            checked.append(fname)
+    if "summary.txt" in exp and p.output_mode == "split":
+        assert rr.summary == exp["summary.txt"], "summary differs:\n%s\n%s" % (rr.summary, exp["summary.txt"])
+        checked.append("summary.txt")
+    if "phasing.txt" in exp:
+        assert rr.phasing_txt == exp["phasing.txt"]
+        checked.append("phasing.txt")
+    if "expected_stderr" in sc and "too complex" in sc["expected_stderr"]:
+        want = [l for l in sc["expected_stderr"].splitlines() if l.startswith("Evaluation too complex")]
+        assert rr.warnings == want, "warnings differ: %s vs %s" % (rr.warnings, want)
+        checked.append("stderr")
+    return checked

@@ -1,0 +1,15 @@
+"""Pins the CPU oracle on the reference's own end-to-end fixtures."""
+import pytest
+
+from golden_check import check_scenario
+
+# scenarios whose checked outputs this harness regenerates (split / annotate / roc-only modes)
+SCENARIOS = ["small", "small_squash", "small_alt", "tricky", "tricky2", "tricky3", "tricky4", "obeyphasing",
+             "small_region", "small_samples", "too_complex", "too_complex_end", "updel", "updel2", "updel3", "updel4",
+             "updel5", "trickysquash", "tetraploid", "annotate", "roc_only", "split", "split_no_roc"]
+
+
+@pytest.mark.parametrize("name", SCENARIOS)
+def test_oracle_matches_reference_golden(oracle, fixtures, name):
+    checked = check_scenario(oracle, fixtures[name])
+    assert checked, "nothing was compared for " + name
