@@ -1,0 +1,145 @@
+// vce_pipeline.h -- host side of the engine: packs a batch of sequences into flat arrays, splits every
+// sequence into independent search regions, drives the search kernels (re-running the few regions that
+// report SPILL / OVERFLOW / prefix-dependent tie-breaks) and assembles the per-variant results the
+// reference's SequenceEvaluator.run() would hand to EvalSynchronizer.write
+// (src/com/rtg/vcf/eval/SequenceEvaluator.java:87-155).
+//
+// The device work is behind `Backend`.  The product library links exactly one backend, the CUDA one
+// (vce_cuda.cu).  tests/emul builds a 1-lane host instantiation of the same search source to exercise this
+// host logic where no GPU exists; it is never linked into the product.
+#ifndef VCE_PIPELINE_H_
+#define VCE_PIPELINE_H_
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/vce.h"
+#include "vce_device.h"
+#include "vce_search.h"
+
+namespace vce {
+
+struct AlleleTable {  // one side, whole batch
+  std::vector<int32_t> aStart, aEnd, aNtOff;
+  std::vector<uint8_t> aNull, nt;
+};
+
+struct HostSide {  // one side of one pass, whole batch, sorted by (sequence, start, end) -- stable
+  int gtPloidy = 0;
+  std::vector<int32_t> vStart, vEnd, slot0, nSl;
+  std::vector<uint8_t> vFlags;      // bit0 phased, bit4 outside-eval (== VCE_STATUS_OUTSIDE_EVAL)
+  std::vector<int8_t> gt;           // n * 4
+  std::vector<int32_t> inputIdx;    // index in the caller's arrays of that sequence
+  std::vector<int32_t> seqFirst;    // [nSeq + 1]
+  // K1 output (host copy)
+  std::vector<int32_t> oOff;
+  std::vector<int8_t> oIds;
+  std::vector<uint8_t> oOrig;
+  // K2/K3 output
+  std::vector<uint8_t> decision;
+  std::vector<double> weight;
+  size_t n() const { return vStart.size(); }
+};
+
+struct PassData {
+  int pass = 0;
+  int H = 2;
+  int kind[2] = {0, 0};  // [0] = calls orientor, [1] = baseline orientor
+  HostSide side[2];      // [0] = calls, [1] = baseline
+  int maxOrient[2] = {0, 0};
+};
+
+struct SearchStats {
+  int64_t launches = 0;
+  double searchMs = 0;   // device time of the search kernels
+  double deviceMs = 0;   // device time of everything launched
+  int64_t regions = 0, escalated = 0, spilled = 0, prefixReruns = 0;
+  int64_t searchAlgBytes = 0;
+};
+
+class Backend {
+ public:
+  virtual ~Backend() {}
+  virtual int setAlleles(int side, const AlleleTable& t) = 0;
+  // Uploads the pass's variant arrays and runs K1 (orientation expansion); fills oOff/oIds/oOrig and maxOrient.
+  virtual int beginPass(PassData& pd) = 0;
+  // Runs the region search (K2 + K3 epilogue) over `regs`.  general=false: shared-memory kernel with fixed small
+  // capacities (reports kRegionOverflow beyond them); general=true: large-capacity kernel with per-region arenas.
+  virtual int search(PassData& pd, const SearchConfig& sc, const std::vector<RegionDesc>& regs,
+                     const std::vector<uint8_t>& windows, bool general, std::vector<RegionResult>& out,
+                     const std::vector<int32_t>& syncOff, std::vector<int32_t>& syncOut, std::vector<WarnRec>& warns) = 0;
+  // Copies decision / weight arrays of the pass back to the host.
+  virtual int fetchPass(PassData& pd) = 0;
+  virtual const char* lastError() const = 0;
+  SearchStats stats;
+};
+
+// Fixed capacities of the shared-memory ("fast") search kernel.
+struct FastLimits {
+  static constexpr int kMaxVarPerSide = 8;   // 4-bit decisions in one word per side
+  static constexpr int kQ = 2;               // pending alleles per haplotype
+  static constexpr int kSMax = 8;            // sync points per region
+  static constexpr int kCap = 24;            // frontier capacity
+  static constexpr int kMaxChildren = 7;     // exclude + up to 6 orientations (ALLELE_GT)
+  static constexpr int kSlots = kCap + 1 + kMaxChildren;
+  static constexpr int kOrdCap = 2 * kCap;
+};
+
+struct PipelineOptions {
+  int gap = 1;        // split when next.start >= maxEnd + gap  (gap >= 1)
+  int margin = 24;    // reference bases kept beyond the last variant end of a region
+  bool wantSyncId = true;
+};
+
+class Pipeline {
+ public:
+  Pipeline(Backend* b, const PipelineOptions& o) : be_(b), opt_(o) {}
+  int run(const vce_config& cfg, int32_t nSeq, const vce_sequence* seqs, vce_sequence_result* results);
+  // staged variant (bench): prepare = pack + split + upload, execute = kernels + re-run loops, finish = assembly
+  int prepare(const vce_config& cfg, int32_t nSeq, const vce_sequence* seqs);
+  int execute();
+  int finish(vce_sequence_result* results);
+  const std::string& error() const { return err_; }
+  Backend* backend() { return be_; }
+
+ private:
+  struct Region {
+    RegionDesc d;
+    RegionResult r;
+    int syncOff = 0;
+    bool alive = true;
+    bool general = false;
+    int assumedPrefix = 0;
+    int extraMargin = 0;   // reference bases added to the window after a window miss (< 0: rest of the template)
+  };
+  struct PassState {
+    PassData pd;
+    std::vector<Region> regions;          // sequence order
+    std::vector<int32_t> seqRegionFirst;  // [nSeq+1]
+    std::vector<int32_t> syncBuf;
+    std::vector<WarnRec> warns;
+    std::vector<uint8_t> shortCircuit;    // per sequence
+  };
+  int buildPass0();
+  int buildPass1();
+  void splitRegions(PassState& ps);
+  bool fastEligible(const PassState& ps, const RegionDesc& d) const;
+  int runPass(PassState& ps);
+  int launch(PassState& ps, const std::vector<int>& ids, bool general);
+  void assemble(int k, vce_sequence_result& res);
+  void phasing(int k, int32_t out[3]) const;
+
+  Backend* be_;
+  PipelineOptions opt_;
+  vce_config cfg_{};
+  int32_t nSeq_ = 0;
+  const vce_sequence* seqs_ = nullptr;
+  AlleleTable alleles_[2];
+  std::vector<int32_t> slotBase_[2];  // per sequence
+  PassState pass_[2];
+  std::string err_;
+};
+
+}  // namespace vce
+#endif

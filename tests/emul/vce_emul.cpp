@@ -1,0 +1,157 @@
+// vce_emul.cpp -- TEST-ONLY host instantiation of the engine's host pipeline.
+//
+// There is no GPU in the build container.  To exercise the HOST logic of the product (packing, region
+// splitting, SPILL merging, overflow escalation, prefix re-runs, result assembly) in `-m "not gpu"` tests,
+// this file plugs a 1-lane CPU instantiation of the very same search source (vce_search.h, HostLane policy)
+// behind the pipeline's Backend interface.  It is built into tests/emul/libvce_emul.so, exported under the
+// `emul_` prefix, and is never linked into or loaded by the product library (rtg_tools_b200/csrc/libvce.so),
+// which fails loudly without a CUDA device.
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../rtg_tools_b200/csrc/vce_orient.h"
+#include "../../rtg_tools_b200/csrc/vce_pipeline.h"
+
+namespace {
+using namespace vce;
+
+class EmulBackend : public Backend {
+ public:
+  bool forceGeneral = false;
+  int setAlleles(int side, const AlleleTable& t) override { al_[side] = &t; return 0; }
+
+  int beginPass(PassData& pd) override {
+    for (int side = 0; side < 2; ++side) {
+      HostSide& hs = pd.side[side];
+      const size_t n = hs.n();
+      hs.oOff.assign(n + 1, 0);
+      int mo = 0;
+      for (size_t v = 0; v < n; ++v) {
+        VariantGt g = gtOf(hs, side, v);
+        OrientCount cnt;
+        orientVariant(pd.kind[side], pd.H, g, cnt);
+        hs.oOff[v + 1] = hs.oOff[v] + cnt.n;
+        mo = std::max(mo, cnt.n);
+      }
+      pd.maxOrient[side] = mo;
+      const size_t rows = hs.oOff[n];
+      oSlot_[side].assign(rows * pd.H + 1, -1);
+      hs.oIds.assign(rows * 4 + 4, -2);
+      hs.oOrig.assign(rows + 1, 0);
+      for (size_t v = 0; v < n; ++v) {
+        VariantGt g = gtOf(hs, side, v);
+        OrientFill f{hs.oOff[v], pd.H, g.slot0, g.nSlots, g.aNull, oSlot_[side].data(), hs.oIds.data(), hs.oOrig.data()};
+        orientVariant(pd.kind[side], pd.H, g, f);
+      }
+      hs.decision.assign(n, 0);
+      hs.weight.assign(n, 0.0);
+    }
+    return 0;
+  }
+
+  int search(PassData& pd, const SearchConfig& sc, const std::vector<RegionDesc>& regs, const std::vector<uint8_t>& windows,
+             bool general, std::vector<RegionResult>& out, const std::vector<int32_t>& syncOff, std::vector<int32_t>& syncOut,
+             std::vector<WarnRec>& warns) override {
+    ++stats.launches;
+    for (size_t q = 0; q < regs.size(); ++q) {
+      RegionSearch<HostLane> rs;
+      rs.R = regs[q];
+      rs.cfg = sc;
+      for (int side = 0; side < 2; ++side) {
+        HostSide& hs = pd.side[side];
+        SideArrays& S = rs.S[side];
+        S.vStart = hs.vStart.data(); S.vEnd = hs.vEnd.data(); S.oOff = hs.oOff.data(); S.oSlot = oSlot_[side].data();
+        S.oIds = hs.oIds.data(); S.oOrig = hs.oOrig.data();
+        S.aStart = al_[side]->aStart.data(); S.aEnd = al_[side]->aEnd.data(); S.aNtOff = al_[side]->aNtOff.data();
+        S.nt = al_[side]->nt.data(); S.vFlags = hs.vFlags.data();
+        S.outDecision = hs.decision.data(); S.outWeight = hs.weight.data();
+      }
+      rs.win = windows.data() + regs[q].winOff;
+      const int mo = std::max(pd.maxOrient[0], pd.maxOrient[1]);
+      if (general || forceGeneral) {
+        rs.L.init(pd.H, regs[q].qMax > 0 ? regs[q].qMax : 1, std::max(1, std::max(regs[q].cCount, regs[q].bCount)),
+                  regs[q].cCount + regs[q].bCount + 2, regs[q].decBits ? regs[q].decBits : 4);
+        rs.maxChildren = 1 + mo;
+        rs.cap = sc.maxPaths + 1 + rs.maxChildren;
+        // grow the arena lazily in the emulation: start small, retry bigger on overflow
+      } else {
+        rs.L.init(pd.H, FastLimits::kQ, FastLimits::kMaxVarPerSide, FastLimits::kSMax, 4);
+        rs.maxChildren = FastLimits::kMaxChildren;
+        rs.cap = FastLimits::kCap;
+      }
+      int capTry = general ? std::min(rs.cap, 256) : rs.cap;
+      const int capFull = rs.cap;
+      RegionResult rr;
+      while (true) {
+        rs.cap = capTry;
+        rs.nSlots = rs.cap + 1 + rs.maxChildren;
+        rs.ordCap = 2 * rs.cap + 2;
+        std::vector<int32_t> slots((size_t) (rs.nSlots + 2) * rs.L.W), order(rs.ordCap), freeList(rs.nSlots), ctl(16 + 2 * rs.maxChildren);
+        rs.slots = slots.data(); rs.order = order.data(); rs.freeList = freeList.data(); rs.ctl = ctl.data();
+        std::vector<WarnRec> lw(64);
+        rs.warnOut = lw.data(); rs.warnCap = 64; rs.regionId = (int) q;
+        int resultSlot = -1;
+        const int st = rs.run(resultSlot);
+        if (st == kRegionOverflow && general && capTry < capFull) { capTry = std::min(capFull, capTry * 8); continue; }
+        std::memset(&rr, 0, sizeof(rr));
+        rr.status = st;
+        rr.usedPrefix = rs.usedPrefix;
+        rr.nWarn = rs.nWarn;
+        rr.maxFrontier = rs.maxFrontier;
+        rr.iterations = rs.totalIters;
+        rr.lastBaseAlleleId = kPrefixEmpty;
+        if (st == kRegionClean || st == kRegionFinished) {
+          rs.writeResults(resultSlot, syncOut.data() + syncOff[q], &rr);
+          for (int i = 0; i < rs.nWarn && i < 64; ++i) warns.push_back(lw[i]);
+        }
+        break;
+      }
+      out[q] = rr;
+    }
+    return 0;
+  }
+  int fetchPass(PassData&) override { return 0; }
+  const char* lastError() const override { return err_.c_str(); }
+
+ private:
+  VariantGt gtOf(const HostSide& hs, int side, size_t v) const {
+    VariantGt g;
+    g.gtPloidy = hs.gtPloidy;
+    for (int h = 0; h < 4; ++h) g.gt[h] = hs.gt[v * 4 + h];
+    g.phased = hs.vFlags[v] & 1;
+    g.slot0 = hs.slot0[v];
+    g.nSlots = hs.nSl[v];
+    g.aNull = al_[side]->aNull.data();
+    return g;
+  }
+  const AlleleTable* al_[2] = {nullptr, nullptr};
+  std::vector<int32_t> oSlot_[2];
+  std::string err_;
+};
+
+int g_gap = 1, g_margin = 24, g_forceGeneral = 0;
+int64_t g_stats[8];
+}  // namespace
+
+extern "C" {
+void emul_set_options(int gap, int margin, int forceGeneral) { g_gap = gap; g_margin = margin; g_forceGeneral = forceGeneral; }
+// regions, escalated, spilled, prefixReruns, launches of the last emul_vce_submit
+void emul_get_stats(int64_t* out) { for (int i = 0; i < 5; ++i) out[i] = g_stats[i]; }
+
+int emul_vce_submit(const vce_config* cfg, int32_t n_seq, const vce_sequence* seqs, vce_sequence_result* results) {
+  EmulBackend be;
+  be.forceGeneral = g_forceGeneral != 0;
+  PipelineOptions opt;
+  opt.gap = g_gap;
+  opt.margin = g_margin;
+  Pipeline pl(&be, opt);
+  const int rc = pl.run(*cfg, n_seq, seqs, results);
+  g_stats[0] = be.stats.regions; g_stats[1] = be.stats.escalated; g_stats[2] = be.stats.spilled;
+  g_stats[3] = be.stats.prefixReruns; g_stats[4] = be.stats.launches;
+  if (rc && !pl.error().empty()) fprintf(stderr, "emul: %s\n", pl.error().c_str());
+  return rc;
+}
+int emul_vce_roc(const vce_roc_in*, vce_roc_out*) { return VCE_ERR_UNSUPPORTED; }
+}
