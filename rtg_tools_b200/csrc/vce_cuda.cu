@@ -1,0 +1,594 @@
+// vce_cuda.cu -- the CUDA backend: device buffers, K1 (orientation expansion), K2/K3 (region search with the
+// tie-break / weight epilogue) for sm_100a.  Compiled with
+//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo
+//
+// Kernels
+//   k_orient_count / k_orient_fill : one thread per variant, Orientor.orientations (vce_orient.h)
+//   k_search<false>                : one warp per region, path records + frontier in shared memory, the region's
+//                                    reference window staged into shared memory, fixed small capacities
+//   k_search<true>                 : one warp per region, per-warp arena in HBM, capacities up to the reference's
+//                                    own search budget (max-paths / max-iterations)
+// Both search kernels pull regions from a global atomic work counter so that long clusters do not stall a block.
+#include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "vce_cuda.h"
+#include "vce_orient.h"
+#include "vce_search.h"
+
+namespace vce {
+
+// ------------------------------------------------------------------------------------------------ K1
+struct OrientParams {
+  int n, kind, H, gtPloidy;
+  const int8_t* gt;
+  const uint8_t* vFlags;
+  const int32_t* slot0;
+  const int32_t* nSl;
+  const uint8_t* aNull;
+};
+
+__device__ __forceinline__ VariantGt loadGt(const OrientParams& p, int v) {
+  VariantGt g;
+  g.gtPloidy = p.gtPloidy;
+  const char4 q = reinterpret_cast<const char4*>(p.gt)[v];
+  g.gt[0] = q.x; g.gt[1] = q.y; g.gt[2] = q.z; g.gt[3] = q.w;
+  g.phased = p.vFlags[v] & 1;
+  g.slot0 = p.slot0[v];
+  g.nSlots = p.nSl[v];
+  g.aNull = p.aNull;
+  return g;
+}
+
+__global__ void k_orient_count(const OrientParams p, int32_t* __restrict__ cnt, int32_t* __restrict__ maxOut) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  int c = 0;
+  if (v < p.n) {
+    const VariantGt g = loadGt(p, v);
+    OrientCount oc;
+    orientVariant(p.kind, p.H, g, oc);
+    c = oc.n;
+    cnt[v] = c;
+  } else if (v == p.n) {
+    cnt[v] = 0;
+  }
+  // block max -> one atomic per warp
+  for (int o = 16; o > 0; o >>= 1) c = max(c, __shfl_xor_sync(0xffffffffu, c, o));
+  if ((threadIdx.x & 31) == 0 && c > 0) atomicMax(maxOut, c);
+}
+
+__global__ void k_orient_fill(const OrientParams p, const int32_t* __restrict__ oOff, int32_t* __restrict__ oSlot,
+                              int8_t* __restrict__ oIds, uint8_t* __restrict__ oOrig) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= p.n) return;
+  const VariantGt g = loadGt(p, v);
+  OrientFill f{oOff[v], p.H, g.slot0, g.nSlots, g.aNull, oSlot, oIds, oOrig};
+  orientVariant(p.kind, p.H, g, f);
+}
+
+// ------------------------------------------------------------------------------------------------ K2 / K3
+struct SearchParams {
+  const RegionDesc* regs;
+  int nRegs;
+  SideArrays S[2];
+  const uint8_t* windows;
+  SearchConfig cfg;
+  RegionResult* out;
+  const int32_t* syncOff;
+  int32_t* syncOut;
+  WarnRec* warns;        // global list
+  int* warnCount;
+  int warnCap;
+  WarnRec* warnScratch;  // kWarnPerRegion per warp of the grid
+  int* counter;          // work queue
+  int H;
+  int maxChildren;
+  int32_t* arena;        // general kernel only
+  long long arenaWordsPerWarp;
+  int winSmemBytes;      // fast kernel: bytes of shared memory per warp for the reference window
+};
+
+constexpr int kWarnPerRegion = 64;
+constexpr int kFastWarps = 8;
+
+template <bool GENERAL>
+__global__ void __launch_bounds__(kFastWarps * 32) k_search(const __grid_constant__ SearchParams p) {
+  extern __shared__ __align__(16) int32_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int gwarp = blockIdx.x * (blockDim.x >> 5) + warp;
+
+  RegionSearch<DeviceWarp> rs;
+  rs.cfg = p.cfg;
+  rs.S[0] = p.S[0];
+  rs.S[1] = p.S[1];
+  rs.warnOut = p.warnScratch + (size_t) gwarp * kWarnPerRegion;
+  rs.warnCap = kWarnPerRegion;
+  uint8_t* winS = nullptr;
+  if (!GENERAL) {
+    rs.L.init(p.H, FastLimits::kQ, FastLimits::kMaxVarPerSide, FastLimits::kSMax, 4);
+    rs.maxChildren = FastLimits::kMaxChildren;
+    rs.cap = FastLimits::kCap;
+    rs.nSlots = FastLimits::kSlots;
+    rs.ordCap = FastLimits::kOrdCap;
+    PathLayout LM;
+    LM.init(2, FastLimits::kQ, FastLimits::kMaxVarPerSide, FastLimits::kSMax, 4);
+    // ctl is padded so that the window that follows it (and the next warp's block) stays 16-byte aligned
+    const int preWords = (FastLimits::kSlots + 2) * LM.W + FastLimits::kOrdCap + FastLimits::kSlots;
+    const int ctlWords = ((preWords + 16 + 2 * FastLimits::kMaxChildren + 3) & ~3) - preWords;
+    const int wordsPerWarp = preWords + ctlWords + p.winSmemBytes / 4;
+    int32_t* base = smem + (size_t) warp * wordsPerWarp;
+    rs.slots = base;
+    rs.order = base + (FastLimits::kSlots + 2) * LM.W;
+    rs.freeList = rs.order + FastLimits::kOrdCap;
+    rs.ctl = rs.freeList + FastLimits::kSlots;
+    winS = reinterpret_cast<uint8_t*>(rs.ctl + ctlWords);
+  }
+
+  while (true) {
+    int r = 0;
+    if (lane == 0) r = atomicAdd(p.counter, 1);
+    r = __shfl_sync(0xffffffffu, r, 0);
+    if (r >= p.nRegs) break;
+    rs.R = p.regs[r];
+    rs.regionId = r;
+    if (GENERAL) {
+      rs.L.init(p.H, rs.R.qMax, max(1, max(rs.R.cCount, rs.R.bCount)), rs.R.cCount + rs.R.bCount + 2, rs.R.decBits);
+      rs.maxChildren = p.maxChildren;
+      const long long ctlWords = 16 + 2 * p.maxChildren;
+      // capacity that fits this warp's arena:  (nSlots+2)*W + ordCap + nSlots + ctl <= arenaWords,
+      // nSlots = cap + 1 + MC, ordCap = 2*cap + 2
+      long long cap = p.cfg.maxPaths + 1 + p.maxChildren;
+      const long long fixed = (long long) (3 + p.maxChildren) * rs.L.W + 2 + (1 + p.maxChildren) + ctlWords;
+      const long long fit = (p.arenaWordsPerWarp - fixed) / (rs.L.W + 3);
+      if (cap > fit) cap = fit;
+      if (cap < 1) cap = 1;
+      rs.cap = (int) cap;
+      rs.nSlots = rs.cap + 1 + p.maxChildren;
+      rs.ordCap = 2 * rs.cap + 2;
+      int32_t* base = p.arena + (size_t) gwarp * p.arenaWordsPerWarp;
+      rs.slots = base;
+      rs.order = base + (size_t) (rs.nSlots + 2) * rs.L.W;
+      rs.freeList = rs.order + rs.ordCap;
+      rs.ctl = rs.freeList + rs.nSlots;
+      rs.win = p.windows + rs.R.winOff;
+    } else {
+      // stage the reference window in shared memory (16-byte vector loads; the window buffer is 16 B aligned and padded)
+      const uint8_t* gw = p.windows + rs.R.winOff;
+      if (rs.R.winLen <= p.winSmemBytes) {
+        const int nvec = (rs.R.winLen + 15) >> 4;
+        const uint4* src = reinterpret_cast<const uint4*>(gw);
+        uint4* dst = reinterpret_cast<uint4*>(winS);
+        for (int i = lane; i < nvec; i += 32) dst[i] = __ldg(src + i);
+        rs.win = winS;
+      } else {
+        rs.win = gw;
+      }
+      __syncwarp();
+    }
+    int resultSlot = -1;
+    const int st = rs.run(resultSlot);
+    RegionResult rr;
+    rr.status = st;
+    rr.usedPrefix = rs.usedPrefix;
+    rr.nSync = 0;
+    rr.nWarn = rs.nWarn;
+    rr.lastBaseAlleleId = kPrefixEmpty;
+    rr.maxFrontier = rs.maxFrontier;
+    rr.iterations = rs.totalIters;
+    rr.pad = 0;
+    __syncwarp();
+    if (st == kRegionClean || st == kRegionFinished) {
+      rs.writeResults(resultSlot, p.syncOut + p.syncOff[r], &rr);
+      if (lane == 0 && rs.nWarn > 0) {
+        const int nw = min(rs.nWarn, kWarnPerRegion);
+        const int at = atomicAdd(p.warnCount, nw);
+        for (int i = 0; i < nw; ++i) if (at + i < p.warnCap) p.warns[at + i] = rs.warnOut[i];
+      }
+    }
+    if (lane == 0) p.out[r] = rr;
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backend
+#define CUDA_TRY(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t e_ = (expr);                                                                 \
+    if (e_ != cudaSuccess) {                                                                 \
+      char b_[512];                                                                          \
+      snprintf(b_, sizeof(b_), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      err_ = b_;                                                                             \
+      return VCE_ERR_CUDA;                                                                   \
+    }                                                                                        \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = n + n / 8 + 64;
+    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct AlleleDev {
+  DevBuf<int32_t> aStart, aEnd, aNtOff;
+  DevBuf<uint8_t> aNull, nt;
+  void release() { aStart.release(); aEnd.release(); aNtOff.release(); aNull.release(); nt.release(); }
+};
+
+struct SideDev {  // one side of one pass
+  DevBuf<int32_t> vStart, vEnd, slot0, nSl, oCnt, oOff, oSlot;
+  DevBuf<uint8_t> vFlags, oOrig, decision;
+  DevBuf<int8_t> gt, oIds;
+  DevBuf<double> weight;
+  size_t nVar = 0, nRows = 0;
+  void release() {
+    vStart.release(); vEnd.release(); slot0.release(); nSl.release(); oCnt.release(); oOff.release(); oSlot.release();
+    vFlags.release(); oOrig.release(); decision.release(); gt.release(); oIds.release(); weight.release();
+  }
+};
+
+class CudaBackend : public Backend {
+ public:
+  explicit CudaBackend(int device) : device_(device) {}
+  ~CudaBackend() override { destroy(); }
+
+  int init() {
+    CUDA_TRY(cudaSetDevice(device_));
+    CUDA_TRY(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&ev0_));
+    CUDA_TRY(cudaEventCreate(&ev1_));
+    CUDA_TRY(cudaDeviceGetAttribute(&smCount_, cudaDevAttrMultiProcessorCount, device_));
+    int maxSmem = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_));
+    maxSmemOptin_ = maxSmem;
+    CUDA_TRY(cudaFuncSetAttribute(k_search<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+    ready_ = true;
+    return VCE_OK;
+  }
+  void destroy() {
+    if (!ready_) return;
+    cudaSetDevice(device_);
+    for (int s = 0; s < 2; ++s) { al_[s].release(); pdev_[0][s].release(); pdev_[1][s].release(); }
+    sRegs_.release(); sSyncOff_.release(); sWindows_.release();
+    regs_.release(); rres_.release(); syncOff_.release(); syncBuf_.release(); windows_.release(); warns_.release();
+    warnScratch_.release(); ints_.release(); arena_.release(); scanTmp_.release();
+    cudaEventDestroy(ev0_);
+    cudaEventDestroy(ev1_);
+    cudaStreamDestroy(stream_);
+    ready_ = false;
+  }
+
+  int setAlleles(int side, const AlleleTable& t) override {
+    CUDA_TRY(cudaSetDevice(device_));
+    AlleleDev& d = al_[side];
+    CUDA_TRY(d.aStart.ensure(t.aStart.size() + 1));
+    CUDA_TRY(d.aEnd.ensure(t.aEnd.size() + 1));
+    CUDA_TRY(d.aNtOff.ensure(t.aNtOff.size() + 1));
+    CUDA_TRY(d.aNull.ensure(t.aNull.size() + 1));
+    CUDA_TRY(d.nt.ensure(t.nt.size() + 16));
+    CUDA_TRY(cudaMemcpyAsync(d.aStart.p, t.aStart.data(), t.aStart.size() * 4, cudaMemcpyHostToDevice, stream_));
+    CUDA_TRY(cudaMemcpyAsync(d.aEnd.p, t.aEnd.data(), t.aEnd.size() * 4, cudaMemcpyHostToDevice, stream_));
+    CUDA_TRY(cudaMemcpyAsync(d.aNtOff.p, t.aNtOff.data(), t.aNtOff.size() * 4, cudaMemcpyHostToDevice, stream_));
+    CUDA_TRY(cudaMemcpyAsync(d.aNull.p, t.aNull.data(), t.aNull.size(), cudaMemcpyHostToDevice, stream_));
+    CUDA_TRY(cudaMemcpyAsync(d.nt.p, t.nt.data(), t.nt.size(), cudaMemcpyHostToDevice, stream_));
+    stats.h2dBytes += (int64_t) (t.aStart.size() * 4 + t.aEnd.size() * 4 + t.aNtOff.size() * 4 + t.aNull.size() + t.nt.size());
+    return VCE_OK;
+  }
+
+  int uploadPass(PassData& pd) override {
+    CUDA_TRY(cudaSetDevice(device_));
+    CUDA_TRY(ints_.ensure(16));
+    for (int side = 0; side < 2; ++side) {
+      HostSide& hs = pd.side[side];
+      SideDev& d = pdev_[pd.pass][side];
+      const size_t n = hs.n();
+      d.nVar = n;
+      CUDA_TRY(d.vStart.ensure(n + 1)); CUDA_TRY(d.vEnd.ensure(n + 1)); CUDA_TRY(d.slot0.ensure(n + 1));
+      CUDA_TRY(d.nSl.ensure(n + 1)); CUDA_TRY(d.vFlags.ensure(n + 1)); CUDA_TRY(d.gt.ensure(4 * n + 4));
+      CUDA_TRY(d.oCnt.ensure(n + 1)); CUDA_TRY(d.oOff.ensure(n + 1)); CUDA_TRY(d.decision.ensure(n + 1));
+      CUDA_TRY(d.weight.ensure(n + 1));
+      if (n) {
+        CUDA_TRY(cudaMemcpyAsync(d.vStart.p, hs.vStart.data(), n * 4, cudaMemcpyHostToDevice, stream_));
+        CUDA_TRY(cudaMemcpyAsync(d.vEnd.p, hs.vEnd.data(), n * 4, cudaMemcpyHostToDevice, stream_));
+        CUDA_TRY(cudaMemcpyAsync(d.slot0.p, hs.slot0.data(), n * 4, cudaMemcpyHostToDevice, stream_));
+        CUDA_TRY(cudaMemcpyAsync(d.nSl.p, hs.nSl.data(), n * 4, cudaMemcpyHostToDevice, stream_));
+        CUDA_TRY(cudaMemcpyAsync(d.vFlags.p, hs.vFlags.data(), n, cudaMemcpyHostToDevice, stream_));
+        CUDA_TRY(cudaMemcpyAsync(d.gt.p, hs.gt.data(), n * 4, cudaMemcpyHostToDevice, stream_));
+        stats.h2dBytes += (int64_t) (n * 21);
+      }
+    }
+    return resetPass(pd);
+  }
+
+  int resetPass(PassData& pd) override {
+    CUDA_TRY(cudaSetDevice(device_));
+    for (int side = 0; side < 2; ++side) {
+      SideDev& d = pdev_[pd.pass][side];
+      CUDA_TRY(cudaMemsetAsync(d.decision.p, 0, d.nVar + 1, stream_));
+      CUDA_TRY(cudaMemsetAsync(d.weight.p, 0, (d.nVar + 1) * sizeof(double), stream_));
+    }
+    return VCE_OK;
+  }
+
+  int orient(PassData& pd) override {
+    CUDA_TRY(cudaSetDevice(device_));
+    curPass_ = pd.pass;
+    // K1: count -> exclusive scan -> fill
+    for (int side = 0; side < 2; ++side) {
+      HostSide& hs = pd.side[side];
+      SideDev& d = pdev_[pd.pass][side];
+      const size_t n = d.nVar;
+      OrientParams op{(int) n, pd.kind[side], pd.H, hs.gtPloidy, d.gt.p, d.vFlags.p, d.slot0.p, d.nSl.p, al_[side].aNull.p};
+      const int tb = 256;
+      const int nb = (int) ((n + 1 + tb - 1) / tb);
+      CUDA_TRY(cudaMemsetAsync(ints_.p + side, 0, sizeof(int), stream_));
+      k_orient_count<<<nb, tb, 0, stream_>>>(op, d.oCnt.p, ints_.p + side);
+      ++stats.launches;
+      size_t tmpBytes = 0;
+      CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, d.oCnt.p, d.oOff.p, (int) (n + 1), stream_));
+      CUDA_TRY(scanTmp_.ensure(tmpBytes + 16));
+      CUDA_TRY(cub::DeviceScan::ExclusiveSum(scanTmp_.p, tmpBytes, d.oCnt.p, d.oOff.p, (int) (n + 1), stream_));
+      ++stats.launches;
+      // the row total is bounded on the host so that no round trip is needed before the fill
+      const size_t rowBound = n * (size_t) std::max(1, pd.maxOrient[side]);
+      CUDA_TRY(d.oSlot.ensure(rowBound * pd.H + 4));
+      CUDA_TRY(d.oIds.ensure(rowBound * 4 + 4));
+      CUDA_TRY(d.oOrig.ensure(rowBound + 4));
+      if (n) {
+        k_orient_fill<<<(int) ((n + tb - 1) / tb), tb, 0, stream_>>>(op, d.oOff.p, d.oSlot.p, d.oIds.p, d.oOrig.p);
+        ++stats.launches;
+      }
+      CUDA_TRY(cudaGetLastError());
+    }
+    return VCE_OK;
+  }
+
+  int stage(const std::vector<RegionDesc>& regs, const std::vector<uint8_t>& windows, const std::vector<int32_t>& syncOff,
+            size_t syncTotal) override {
+    CUDA_TRY(cudaSetDevice(device_));
+    const size_t nr = regs.size();
+    CUDA_TRY(sRegs_.ensure(nr + 1)); CUDA_TRY(sSyncOff_.ensure(nr + 1)); CUDA_TRY(sWindows_.ensure(windows.size() + 64));
+    CUDA_TRY(ensureSync(syncTotal));
+    CUDA_TRY(cudaMemcpyAsync(sRegs_.p, regs.data(), nr * sizeof(RegionDesc), cudaMemcpyHostToDevice, stream_));
+    CUDA_TRY(cudaMemcpyAsync(sSyncOff_.p, syncOff.data(), nr * 4, cudaMemcpyHostToDevice, stream_));
+    CUDA_TRY(cudaMemcpyAsync(sWindows_.p, windows.data(), windows.size(), cudaMemcpyHostToDevice, stream_));
+    CUDA_TRY(cudaStreamSynchronize(stream_));
+    stats.h2dBytes += (int64_t) (nr * (sizeof(RegionDesc) + 4) + windows.size());
+    return VCE_OK;
+  }
+
+  cudaError_t ensureSync(size_t total) {
+    // the device sync buffer mirrors the host one (which grows when regions are merged)
+    if (total > syncBuf_.cap) {
+      DevBuf<int32_t> nb;
+      cudaError_t e = nb.ensure(total * 2 + 1024);
+      if (e != cudaSuccess) return e;
+      if (syncBuf_.p && syncBufUsed_) {
+        e = cudaMemcpyAsync(nb.p, syncBuf_.p, syncBufUsed_ * 4, cudaMemcpyDeviceToDevice, stream_);
+        if (e != cudaSuccess) return e;
+      }
+      e = cudaStreamSynchronize(stream_);
+      if (e != cudaSuccess) return e;
+      syncBuf_.release();
+      syncBuf_ = nb;
+    }
+    syncBufUsed_ = total;
+    return cudaSuccess;
+  }
+
+  SideArrays sideArrays(int side) const {
+    const SideDev& d = pdev_[curPass_][side];
+    const AlleleDev& a = al_[side];
+    SideArrays S;
+    S.vStart = d.vStart.p; S.vEnd = d.vEnd.p; S.oOff = d.oOff.p; S.oSlot = d.oSlot.p; S.oIds = d.oIds.p; S.oOrig = d.oOrig.p;
+    S.aStart = a.aStart.p; S.aEnd = a.aEnd.p; S.aNtOff = a.aNtOff.p; S.nt = a.nt.p; S.vFlags = d.vFlags.p;
+    S.outDecision = d.decision.p; S.outWeight = d.weight.p;
+    return S;
+  }
+
+  int search(PassData& pd, const SearchConfig& sc, const std::vector<RegionDesc>& regs, const std::vector<uint8_t>& windows,
+             bool general, bool staged, std::vector<RegionResult>& out, const std::vector<int32_t>& syncOff, size_t syncTotal,
+             std::vector<WarnRec>& warns) override {
+    CUDA_TRY(cudaSetDevice(device_));
+    curPass_ = pd.pass;
+    const size_t nr = regs.size();
+    if (nr == 0) return VCE_OK;
+    CUDA_TRY(rres_.ensure(nr));
+    CUDA_TRY(ints_.ensure(16));
+    CUDA_TRY(ensureSync(syncTotal));
+    const int warnCap = 1 << 16;
+    CUDA_TRY(warns_.ensure(warnCap));
+    const RegionDesc* dRegs;
+    const int32_t* dSyncOff;
+    const uint8_t* dWindows;
+    if (staged) {
+      dRegs = sRegs_.p; dSyncOff = sSyncOff_.p; dWindows = sWindows_.p;
+    } else {
+      CUDA_TRY(regs_.ensure(nr)); CUDA_TRY(syncOff_.ensure(nr)); CUDA_TRY(windows_.ensure(windows.size() + 64));
+      CUDA_TRY(cudaMemcpyAsync(regs_.p, regs.data(), nr * sizeof(RegionDesc), cudaMemcpyHostToDevice, stream_));
+      CUDA_TRY(cudaMemcpyAsync(syncOff_.p, syncOff.data(), nr * 4, cudaMemcpyHostToDevice, stream_));
+      CUDA_TRY(cudaMemcpyAsync(windows_.p, windows.data(), windows.size(), cudaMemcpyHostToDevice, stream_));
+      stats.h2dBytes += (int64_t) (nr * (sizeof(RegionDesc) + 4) + windows.size());
+      dRegs = regs_.p; dSyncOff = syncOff_.p; dWindows = windows_.p;
+    }
+    CUDA_TRY(cudaMemsetAsync(ints_.p + 4, 0, 2 * sizeof(int), stream_));  // [4] work counter, [5] warning count
+
+    SearchParams sp;
+    std::memset(&sp, 0, sizeof(sp));
+    sp.regs = dRegs; sp.nRegs = (int) nr;
+    sp.S[0] = sideArrays(0); sp.S[1] = sideArrays(1);
+    sp.windows = dWindows; sp.cfg = sc; sp.out = rres_.p; sp.syncOff = dSyncOff; sp.syncOut = syncBuf_.p;
+    sp.warns = warns_.p; sp.warnCount = ints_.p + 5; sp.warnCap = warnCap; sp.counter = ints_.p + 4;
+    sp.H = pd.H;
+    sp.maxChildren = 1 + std::max(pd.maxOrient[0], pd.maxOrient[1]);
+
+    int blocks = 0, threads = kFastWarps * 32;
+    size_t smemBytes = 0;
+    if (!general) {
+      PathLayout LM;
+      LM.init(2, FastLimits::kQ, FastLimits::kMaxVarPerSide, FastLimits::kSMax, 4);
+      const int preWords = (FastLimits::kSlots + 2) * LM.W + FastLimits::kOrdCap + FastLimits::kSlots;
+      const int ctlWords = ((preWords + 16 + 2 * FastLimits::kMaxChildren + 3) & ~3) - preWords;
+      sp.winSmemBytes = 256;
+      const size_t wordsPerWarp = (size_t) preWords + ctlWords + sp.winSmemBytes / 4;
+      smemBytes = wordsPerWarp * 4 * kFastWarps;
+      if ((int) smemBytes > maxSmemOptin_) { err_ = "fast kernel shared memory exceeds the device limit"; return VCE_ERR_CUDA; }
+      int perSm = 0;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_search<false>, threads, smemBytes));
+      if (perSm < 1) perSm = 1;
+      blocks = smCount_ * perSm;
+      const int need = (int) ((nr + kFastWarps - 1) / kFastWarps);
+      if (blocks > need) blocks = need;
+    } else {
+      // per-warp arena sized for the largest record layout in this launch at the full search budget
+      long long maxW = 0;
+      for (const RegionDesc& d : regs) maxW = std::max(maxW, (long long) d.layoutW);
+      const long long mc = sp.maxChildren;
+      const long long capFull = (long long) sc.maxPaths + 1 + mc;
+      long long words = (capFull + 1 + mc + 2) * maxW + (2 * capFull + 2) + (capFull + 1 + mc) + 16 + 2 * mc + 64;
+      const long long budgetWords = (long long) (48ull << 30) / 4;  // 48 GB of HBM for search arenas
+      long long warpsWanted = std::min<long long>((long long) nr, (long long) smCount_ * kFastWarps);
+      if (words > budgetWords) words = budgetWords;  // a single region larger than the budget runs with reduced capacity
+      long long warpsFit = std::max<long long>(1, budgetWords / words);
+      long long nw = std::min(warpsWanted, warpsFit);
+      blocks = (int) ((nw + kFastWarps - 1) / kFastWarps);
+      const size_t totalWords = (size_t) blocks * kFastWarps * (size_t) words;
+      CUDA_TRY(arena_.ensure(totalWords));
+      sp.arena = arena_.p;
+      sp.arenaWordsPerWarp = words;
+    }
+    CUDA_TRY(warnScratch_.ensure((size_t) blocks * kFastWarps * kWarnPerRegion));
+    sp.warnScratch = warnScratch_.p;
+
+    CUDA_TRY(cudaEventRecord(ev0_, stream_));
+    if (general) k_search<true><<<blocks, threads, 0, stream_>>>(sp);
+    else k_search<false><<<blocks, threads, smemBytes, stream_>>>(sp);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(ev1_, stream_));
+    ++stats.launches;
+    out.resize(nr);
+    int nWarn = 0;
+    CUDA_TRY(cudaMemcpyAsync(out.data(), rres_.p, nr * sizeof(RegionResult), cudaMemcpyDeviceToHost, stream_));
+    CUDA_TRY(cudaMemcpyAsync(&nWarn, ints_.p + 5, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    CUDA_TRY(cudaStreamSynchronize(stream_));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    stats.searchMs += ms;
+    stats.d2hBytes += (int64_t) (nr * sizeof(RegionResult));
+    if (!general && (long long) nr >= lastFastRegions_) { lastFastMs_ = ms; lastFastRegions_ = (long long) nr; }
+    if (nWarn > 0) {
+      nWarn = std::min(nWarn, warnCap);
+      const size_t at = warns.size();
+      warns.resize(at + nWarn);
+      CUDA_TRY(cudaMemcpy(warns.data() + at, warns_.p, (size_t) nWarn * sizeof(WarnRec), cudaMemcpyDeviceToHost));
+      // keep each region's warnings in emission order
+      std::stable_sort(warns.begin() + at, warns.end(), [](const WarnRec& a, const WarnRec& b) { return a.region < b.region; });
+    }
+    return VCE_OK;
+  }
+
+  int fetchPass(PassData& pd, std::vector<int32_t>& syncBuf) override {
+    CUDA_TRY(cudaSetDevice(device_));
+    for (int side = 0; side < 2; ++side) {
+      HostSide& hs = pd.side[side];
+      SideDev& d = pdev_[pd.pass][side];
+      const size_t n = hs.n();
+      int32_t rows = 0;
+      CUDA_TRY(cudaMemcpyAsync(&rows, d.oOff.p + n, 4, cudaMemcpyDeviceToHost, stream_));
+      CUDA_TRY(cudaStreamSynchronize(stream_));
+      d.nRows = (size_t) rows;
+      hs.decision.resize(n);
+      hs.weight.resize(n);
+      hs.oOff.resize(n + 1);
+      hs.oIds.resize(d.nRows * 4 + 4);
+      hs.oOrig.resize(d.nRows + 4);
+      if (n) {
+        CUDA_TRY(cudaMemcpyAsync(hs.decision.data(), d.decision.p, n, cudaMemcpyDeviceToHost, stream_));
+        CUDA_TRY(cudaMemcpyAsync(hs.weight.data(), d.weight.p, n * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+      }
+      CUDA_TRY(cudaMemcpyAsync(hs.oOff.data(), d.oOff.p, (n + 1) * 4, cudaMemcpyDeviceToHost, stream_));
+      if (d.nRows) {
+        CUDA_TRY(cudaMemcpyAsync(hs.oIds.data(), d.oIds.p, d.nRows * 4, cudaMemcpyDeviceToHost, stream_));
+        CUDA_TRY(cudaMemcpyAsync(hs.oOrig.data(), d.oOrig.p, d.nRows, cudaMemcpyDeviceToHost, stream_));
+      }
+    }
+    if (!syncBuf.empty()) CUDA_TRY(cudaMemcpyAsync(syncBuf.data(), syncBuf_.p, syncBuf.size() * 4, cudaMemcpyDeviceToHost, stream_));
+    CUDA_TRY(cudaStreamSynchronize(stream_));
+    for (int side = 0; side < 2; ++side) {
+      const size_t n = pd.side[side].n();
+      stats.d2hBytes += (int64_t) (n * 9 + (n + 1) * 4 + pdev_[pd.pass][side].nRows * 5);
+    }
+    stats.d2hBytes += (int64_t) syncBuf.size() * 4;
+    return VCE_OK;
+  }
+
+  const char* lastError() const override { return err_.c_str(); }
+  cudaStream_t stream() const { return stream_; }
+  int device() const { return device_; }
+  double lastFastMs_ = 0;
+  long long lastFastRegions_ = 0;
+
+ private:
+  int device_;
+  bool ready_ = false;
+  cudaStream_t stream_ = nullptr;
+  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+  int smCount_ = 148;
+  int maxSmemOptin_ = 0;
+  AlleleDev al_[2];
+  SideDev pdev_[2][2];   // [pass][side]
+  int curPass_ = 0;
+  DevBuf<RegionDesc> regs_, sRegs_;         // transient / staged launch inputs
+  DevBuf<int32_t> sSyncOff_;
+  DevBuf<uint8_t> sWindows_;
+  DevBuf<RegionResult> rres_;
+  DevBuf<int32_t> syncOff_, syncBuf_;
+  size_t syncBufUsed_ = 0;
+  DevBuf<uint8_t> windows_;
+  DevBuf<WarnRec> warns_, warnScratch_;
+  DevBuf<int> ints_;
+  DevBuf<int32_t> arena_;
+  DevBuf<uint8_t> scanTmp_;
+  std::string err_;
+};
+
+Backend* createCudaBackend(int device, std::string& err) {
+  CudaBackend* b = new CudaBackend(device);
+  if (b->init() != VCE_OK) {
+    err = b->lastError();
+    delete b;
+    return nullptr;
+  }
+  return b;
+}
+
+int cudaDeviceCount() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+void cudaBackendFastStats(Backend* b, double* ms, long long* regions) {
+  CudaBackend* c = static_cast<CudaBackend*>(b);
+  *ms = c->lastFastMs_;
+  *regions = c->lastFastRegions_;
+}
+
+}  // namespace vce

@@ -53,7 +53,10 @@ int Pipeline::prepare(const vce_config& cfg, int32_t nSeq, const vce_sequence* s
     const int rc = be_->setAlleles(side, t);
     if (rc) { err_ = be_->lastError(); return rc; }
   }
-  return buildPass0();
+  executed_ = false;
+  int rc = buildPass0();
+  if (rc) return rc;
+  return setupPass(pass_[0], true);
 }
 
 int Pipeline::buildPass0() {
@@ -200,92 +203,150 @@ bool Pipeline::fastEligible(const PassState& ps, const RegionDesc& d) const {
   return true;
 }
 
-int Pipeline::launch(PassState& ps, const std::vector<int>& ids, bool general) {
-  if (ids.empty()) return VCE_OK;
-  std::vector<RegionDesc> descs;
-  std::vector<uint8_t> windows;
-  std::vector<int32_t> syncOff;
-  descs.reserve(ids.size());
-  syncOff.reserve(ids.size());
+// Upper bound on the number of orientations any variant of a pass can have (Orientor.java), used to size child
+// slots and decision fields before K1 has run.
+int Pipeline::orientBound(int kind, int H, int gtPloidy, int maxSlots) {
+  const int nA = std::max(1, maxSlots - 1);  // numAlleles()
+  static const int fact[5] = {1, 1, 2, 6, 24};
+  switch (kind) {
+    case VCE_ORIENT_UNPHASED:
+    case VCE_ORIENT_PHASED:
+    case VCE_ORIENT_PHASED_INVERT: return H == 2 ? 2 : fact[std::min(4, std::max(gtPloidy, H))];
+    case VCE_ORIENT_SQUASH_GT: return std::max(1, gtPloidy);
+    case VCE_ORIENT_ALLELE_GT: return 6;
+    case VCE_ORIENT_HAPLOID_POP: return std::max(1, nA - 1);
+    case VCE_ORIENT_DIPLOID_POP: return std::max(1, (nA - 1) * (2 * nA + 1));
+    case VCE_ORIENT_ALT: {
+      long b = nA - 1;
+      for (int h = 1; h < H; ++h) b *= (nA + 1);
+      b *= fact[std::min(4, H)];
+      return (int) std::min<long>(std::max<long>(1, b), 1 << 20);
+    }
+  }
+  return 1;
+}
+
+void Pipeline::buildLaunch(PassState& ps, const std::vector<int>& ids, bool general, Launch& L) {
+  L.ids = ids;
+  L.descs.clear();
+  L.windows.clear();
+  L.syncOff.clear();
+  L.descs.reserve(ids.size());
+  L.syncOff.reserve(ids.size());
   const int mo = std::max(ps.pd.maxOrient[0], ps.pd.maxOrient[1]);
+  const HostSide& C = ps.pd.side[0];
+  const HostSide& B = ps.pd.side[1];
+  size_t winBytes = 0;
   for (int id : ids) {
     Region& rg = ps.regions[id];
+    RegionDesc& d = rg.d;
     if (general) {
-      rg.d.qMax = std::max(1, std::max(rg.d.cCount, rg.d.bCount));
-      rg.d.decBits = (mo + 2 <= 15) ? 4 : 8;
-      PathLayout L;
-      L.init(ps.pd.H, rg.d.qMax, std::max(1, std::max(rg.d.cCount, rg.d.bCount)), rg.d.cCount + rg.d.bCount + 2, rg.d.decBits);
-      rg.d.layoutW = L.W;
+      d.qMax = std::max(1, std::max(d.cCount, d.bCount));
+      d.decBits = (mo + 2 <= 15) ? 4 : 8;
+      PathLayout PL;
+      PL.init(ps.pd.H, d.qMax, std::max(1, std::max(d.cCount, d.bCount)), d.cCount + d.bCount + 2, d.decBits);
+      d.layoutW = PL.W;
     }
-    descs.push_back(rg.d);
-    syncOff.push_back(rg.syncOff);
-  }
-  for (size_t q = 0; q < ids.size(); ++q) {
-    // Reference window of a region: from just before its first variant to `margin` bases beyond the furthest
+    // Reference window of the region: from just before its first variant to `margin` bases beyond the furthest
     // variant end (the whole remainder of the template when extraMargin < 0).
-    Region& rg = ps.regions[ids[q]];
-    RegionDesc& d = descs[q];
-    const HostSide& C = ps.pd.side[0];
-    const HostSide& B = ps.pd.side[1];
     int lo = INT_MAX;
     long hi = 0;
     for (int v = d.cFirst; v < d.cFirst + d.cCount; ++v) { lo = std::min(lo, C.vStart[v]); hi = std::max(hi, (long) C.vEnd[v]); }
     for (int v = d.bFirst; v < d.bFirst + d.bCount; ++v) { lo = std::min(lo, B.vStart[v]); hi = std::max(hi, (long) B.vEnd[v]); }
     if (lo == INT_MAX) lo = 0;
-    const int extra = rg.extraMargin;  // 0, or grown after a window miss; < 0 = rest of the template
-    int ws = std::max(0, std::min(lo, d.startPos < 0 ? 0 : d.startPos) - 1);
+    const int extra = rg.extraMargin;
+    const int ws = std::max(0, std::min(lo, d.startPos < 0 ? 0 : d.startPos) - 1);
     long we = extra < 0 ? (long) d.tmplLen : hi + opt_.margin + extra;
     we = std::min(we, (long) d.tmplLen);
     if (we < ws) we = ws;
     d.winStart = ws;
     d.winLen = (int32_t) (we - ws);
-    const size_t off = (windows.size() + 15) & ~(size_t) 15;
-    windows.resize(off + (size_t) d.winLen + 16, 0);
-    d.winOff = (uint32_t) off;
-    if (d.winLen > 0) std::memcpy(windows.data() + off, seqs_[d.seq].template_bases + ws, (size_t) d.winLen);
+    d.winOff = (uint32_t) winBytes;
+    winBytes += ((size_t) d.winLen + 15 + 16) & ~(size_t) 15;  // 16-byte aligned and padded: vector / bulk loads
+    L.descs.push_back(d);
+    L.syncOff.push_back(rg.syncOff);
   }
+  L.windows.assign(winBytes + 16, 0);
+  for (const RegionDesc& d : L.descs) {
+    if (d.winLen > 0) std::memcpy(L.windows.data() + d.winOff, seqs_[d.seq].template_bases + d.winStart, (size_t) d.winLen);
+  }
+}
+
+int Pipeline::runLaunch(PassState& ps, Launch& L, bool general, bool staged) {
+  if (L.ids.empty()) return VCE_OK;
   // a re-run region reports its warnings afresh
   if (!ps.warns.empty()) {
     std::vector<uint8_t> redo(ps.regions.size(), 0);
-    for (int id : ids) redo[id] = 1;
+    for (int id : L.ids) redo[id] = 1;
     std::vector<WarnRec> keep;
     for (const WarnRec& wr : ps.warns) if (!redo[wr.region]) keep.push_back(wr);
     ps.warns.swap(keep);
   }
-  std::vector<RegionResult> out(ids.size());
+  std::vector<RegionResult> out(L.ids.size());
   const SearchConfig sc{cfg_.max_paths, cfg_.max_iterations, cfg_.prune_no_ops, cfg_.preference};
   const size_t warn0 = ps.warns.size();
-  const int rc = be_->search(ps.pd, sc, descs, windows, general, out, syncOff, ps.syncBuf, ps.warns);
+  const int rc = be_->search(ps.pd, sc, L.descs, L.windows, general, staged, out, L.syncOff, ps.syncBuf.size(), ps.warns);
   if (rc) { err_ = be_->lastError(); return rc; }
-  for (size_t q = 0; q < ids.size(); ++q) {
-    Region& rg = ps.regions[ids[q]];
+  for (size_t q = 0; q < L.ids.size(); ++q) {
+    Region& rg = ps.regions[L.ids[q]];
     rg.r = out[q];
     rg.general = general;
   }
   // warnings carry the launch-local region index: translate to the pass's region id
-  for (size_t wi = warn0; wi < ps.warns.size(); ++wi) ps.warns[wi].region = ids[ps.warns[wi].region];
+  for (size_t wi = warn0; wi < ps.warns.size(); ++wi) ps.warns[wi].region = L.ids[ps.warns[wi].region];
   return VCE_OK;
 }
 
-int Pipeline::runPass(PassState& ps) {
-  int rc = be_->beginPass(ps.pd);
+int Pipeline::launch(PassState& ps, const std::vector<int>& ids, bool general) {
+  if (ids.empty()) return VCE_OK;
+  Launch L;
+  buildLaunch(ps, ids, general, L);
+  return runLaunch(ps, L, general, false);
+}
+
+// Upload the pass, split it into regions and (optionally) stage the main shared-memory launch on the device.
+int Pipeline::setupPass(PassState& ps, bool stageMain) {
+  for (int side = 0; side < 2; ++side) {
+    const HostSide& hs = ps.pd.side[side];
+    int maxSl = 2;
+    for (int x : hs.nSl) maxSl = std::max(maxSl, x);
+    ps.pd.maxOrient[side] = orientBound(ps.pd.kind[side], ps.pd.H, hs.gtPloidy, maxSl);
+    if (ps.pd.maxOrient[side] + 2 > 255) { err_ = "too many orientations per variant for this engine"; return VCE_ERR_UNSUPPORTED; }
+  }
+  int rc = be_->uploadPass(ps.pd);
   if (rc) { err_ = be_->lastError(); return rc; }
   splitRegions(ps);
-  // sync-point output space: cCount + bCount + 2 per region
-  size_t so = 0;
+  size_t so = 0;  // sync-point output space: cCount + bCount + 2 per region
   for (Region& rg : ps.regions) {
     rg.syncOff = (int) so;
     so += (size_t) rg.d.cCount + rg.d.bCount + 2;
     rg.r = RegionResult();
   }
   ps.syncBuf.assign(so, 0);
-  be_->stats.regions += (int64_t) ps.regions.size();
+  ps.initSyncSize = so;
+  std::vector<int> fast;
+  ps.mainGen.clear();
+  for (int id = 0; id < (int) ps.regions.size(); ++id) (fastEligible(ps, ps.regions[id].d) ? fast : ps.mainGen).push_back(id);
+  buildLaunch(ps, fast, false, ps.mainFast);
+  ps.initRegions = ps.regions;
+  if (stageMain && !ps.mainFast.ids.empty()) {
+    rc = be_->stage(ps.mainFast.descs, ps.mainFast.windows, ps.mainFast.syncOff, ps.syncBuf.size());
+    if (rc) { err_ = be_->lastError(); return rc; }
+  }
+  return VCE_OK;
+}
 
-  std::vector<int> fast, gen;
-  for (int id = 0; id < (int) ps.regions.size(); ++id) (fastEligible(ps, ps.regions[id].d) ? fast : gen).push_back(id);
-  be_->stats.escalated += (int64_t) gen.size();
-  if ((rc = launch(ps, fast, false))) return rc;
-  if ((rc = launch(ps, gen, true))) return rc;
+int Pipeline::runPass(PassState& ps, bool staged) {
+  int rc;
+  ps.regions = ps.initRegions;
+  ps.syncBuf.assign(ps.initSyncSize, 0);
+  ps.warns.clear();
+  ps.fetched = false;
+  if ((rc = be_->orient(ps.pd))) { err_ = be_->lastError(); return rc; }
+  be_->stats.regions += (int64_t) ps.regions.size();
+  be_->stats.escalated += (int64_t) ps.mainGen.size();
+  if ((rc = runLaunch(ps, ps.mainFast, false, staged))) return rc;
+  if ((rc = launch(ps, ps.mainGen, true))) return rc;
 
   // ---- settle SPILL / OVERFLOW, then prefix-dependent tie-breaks
   std::vector<int> pending;  // regions whose latest run must be inspected
@@ -365,17 +426,27 @@ int Pipeline::runPass(PassState& ps) {
     pending.insert(pending.end(), redoFast.begin(), redoFast.end());
     pending.insert(pending.end(), redoGen.begin(), redoGen.end());
   }
-  rc = be_->fetchPass(ps.pd);
-  if (rc) { err_ = be_->lastError(); return rc; }
+  for (const Region& rg : ps.regions) if (rg.alive) be_->stats.iterations += rg.r.iterations;
   return VCE_OK;
 }
 
 int Pipeline::execute() {
-  int rc = runPass(pass_[0]);
-  if (rc) return rc;
+  int rc;
+  if (executed_) {  // repeated execution of a staged job: only the device-side outputs of pass 0 are cleared
+    if ((rc = be_->resetPass(pass_[0].pd))) { err_ = be_->lastError(); return rc; }
+  }
+  executed_ = true;
+  if ((rc = runPass(pass_[0], true))) return rc;
   if (cfg_.n_passes == 2) {
+    PassState& p0 = pass_[0];
+    if ((rc = be_->fetchPass(p0.pd, p0.syncBuf))) { err_ = be_->lastError(); return rc; }
+    p0.fetched = true;
+    // the second pass needs the device for itself: its arrays replace the first pass's
     if ((rc = buildPass1())) return rc;
-    if ((rc = runPass(pass_[1]))) return rc;
+    if ((rc = setupPass(pass_[1], false))) return rc;
+    if ((rc = runPass(pass_[1], false))) return rc;
+    if ((rc = be_->fetchPass(pass_[1].pd, pass_[1].syncBuf))) { err_ = be_->lastError(); return rc; }
+    pass_[1].fetched = true;
   }
   return VCE_OK;
 }
@@ -612,6 +683,10 @@ void Pipeline::assemble(int k, vce_sequence_result& res) {
 
 int Pipeline::finish(vce_sequence_result* results) {
   int rc = VCE_OK;
+  if (!pass_[0].fetched) {
+    if ((rc = be_->fetchPass(pass_[0].pd, pass_[0].syncBuf))) { err_ = be_->lastError(); return rc; }
+    pass_[0].fetched = true;
+  }
   for (int k = 0; k < nSeq_; ++k) {
     assemble(k, results[k]);
     if (results[k].error != VCE_OK && rc == VCE_OK) rc = results[k].error;

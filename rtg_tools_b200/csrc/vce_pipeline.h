@@ -55,22 +55,32 @@ struct SearchStats {
   double searchMs = 0;   // device time of the search kernels
   double deviceMs = 0;   // device time of everything launched
   int64_t regions = 0, escalated = 0, spilled = 0, prefixReruns = 0;
-  int64_t searchAlgBytes = 0;
+  int64_t h2dBytes = 0, d2hBytes = 0;
+  int64_t iterations = 0;
 };
 
 class Backend {
  public:
   virtual ~Backend() {}
   virtual int setAlleles(int side, const AlleleTable& t) = 0;
-  // Uploads the pass's variant arrays and runs K1 (orientation expansion); fills oOff/oIds/oOrig and maxOrient.
-  virtual int beginPass(PassData& pd) = 0;
+  // Host -> device copy of the pass's variant arrays; clears the per-variant outputs.
+  virtual int uploadPass(PassData& pd) = 0;
+  // Clears the per-variant outputs again (a staged job may be executed repeatedly).
+  virtual int resetPass(PassData& pd) = 0;
+  // K1: orientation expansion on the device (fills the device-side orientation table).
+  virtual int orient(PassData& pd) = 0;
+  // Host -> device copy of one search launch's inputs (region descriptors, reference windows, sync offsets) ahead of
+  // time, so that a following search(..., staged = true) starts with everything resident in HBM.
+  virtual int stage(const std::vector<RegionDesc>& regs, const std::vector<uint8_t>& windows,
+                    const std::vector<int32_t>& syncOff, size_t syncTotal) = 0;
   // Runs the region search (K2 + K3 epilogue) over `regs`.  general=false: shared-memory kernel with fixed small
   // capacities (reports kRegionOverflow beyond them); general=true: large-capacity kernel with per-region arenas.
+  // staged=true: the launch inputs were already copied by stage(); regs/windows/syncOff are then only read for sizes.
   virtual int search(PassData& pd, const SearchConfig& sc, const std::vector<RegionDesc>& regs,
-                     const std::vector<uint8_t>& windows, bool general, std::vector<RegionResult>& out,
-                     const std::vector<int32_t>& syncOff, std::vector<int32_t>& syncOut, std::vector<WarnRec>& warns) = 0;
-  // Copies decision / weight arrays of the pass back to the host.
-  virtual int fetchPass(PassData& pd) = 0;
+                     const std::vector<uint8_t>& windows, bool general, bool staged, std::vector<RegionResult>& out,
+                     const std::vector<int32_t>& syncOff, size_t syncTotal, std::vector<WarnRec>& warns) = 0;
+  // Copies decision / weight / orientation-id arrays of the pass and the sync-point buffer back to the host.
+  virtual int fetchPass(PassData& pd, std::vector<int32_t>& syncBuf) = 0;
   virtual const char* lastError() const = 0;
   SearchStats stats;
 };
@@ -113,9 +123,20 @@ class Pipeline {
     int assumedPrefix = 0;
     int extraMargin = 0;   // reference bases added to the window after a window miss (< 0: rest of the template)
   };
+  struct Launch {  // one search launch, ready to go
+    std::vector<int> ids;
+    std::vector<RegionDesc> descs;
+    std::vector<uint8_t> windows;
+    std::vector<int32_t> syncOff;
+  };
   struct PassState {
     PassData pd;
+    bool fetched = false;
     std::vector<Region> regions;          // sequence order
+    std::vector<Region> initRegions;      // as split, before any merge (a staged job can be executed repeatedly)
+    size_t initSyncSize = 0;
+    Launch mainFast;                      // staged in prepare() for pass 0
+    std::vector<int> mainGen;
     std::vector<int32_t> seqRegionFirst;  // [nSeq+1]
     std::vector<int32_t> syncBuf;
     std::vector<WarnRec> warns;
@@ -125,8 +146,12 @@ class Pipeline {
   int buildPass1();
   void splitRegions(PassState& ps);
   bool fastEligible(const PassState& ps, const RegionDesc& d) const;
-  int runPass(PassState& ps);
+  int setupPass(PassState& ps, bool stageMain);
+  int runPass(PassState& ps, bool staged);
+  void buildLaunch(PassState& ps, const std::vector<int>& ids, bool general, Launch& L);
+  int runLaunch(PassState& ps, Launch& L, bool general, bool staged);
   int launch(PassState& ps, const std::vector<int>& ids, bool general);
+  static int orientBound(int kind, int H, int gtPloidy, int maxSlots);
   void assemble(int k, vce_sequence_result& res);
   void phasing(int k, int32_t out[3]) const;
 
@@ -138,6 +163,7 @@ class Pipeline {
   AlleleTable alleles_[2];
   std::vector<int32_t> slotBase_[2];  // per sequence
   PassState pass_[2];
+  bool executed_ = false;
   std::string err_;
 };
 

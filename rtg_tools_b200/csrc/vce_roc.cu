@@ -1,0 +1,252 @@
+// vce_roc.cu -- K4: RocContainer accumulate + sort + cumulative sums on the device.
+//
+// Reference behaviour (src/com/rtg/vcf/eval/RocContainer.java):
+//   addRocLine :225-258  per filter, a TreeMap<score, RocPoint>; equal scores are summed with sequential
+//                        double += in ARRIVAL order (RocPoint.add, RocPoint.java:70-74); NaN / Inf scores go
+//                        to one NaN bucket that sorts last (:232-237, :447-457)
+//   writeRocs  :296-309  buckets visited in comparator order, cumulative = sequential double += per bucket
+// Floating-point addition is not associative, so both levels are reproduced as the same sequential chains:
+//   1. scores -> order-preserving 64-bit keys, one stable radix sort of (key, arrival index) shared by all filters
+//   2. bucket sums: one thread per (bucket, filter) adds its members in arrival order
+//   3. cumulative sums: one warp per filter walks the buckets in key order; lanes fetch 32 bucket sums with one
+//      coalesced load, the 3 dependent add chains (tp, fp, tpRaw) run through warp shuffles, lane j keeps the
+//      value after step j, rows of non-empty buckets are written compacted.
+// The radix sort and the prefix sums are CUB (plumbing); the ROC-specific kernels are below.
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <cmath>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/vce.h"
+#include "vce_cuda.h"
+
+namespace vce {
+
+__device__ __forceinline__ unsigned long long rocKey(double s, int ascending) {
+  if (isnan(s) || isinf(s)) return ~0ull;  // the "None" bucket is last in both orders
+  unsigned long long b = (unsigned long long) __double_as_longlong(s);
+  b = (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);  // ascending total order, -0.0 < +0.0 (Double.compareTo)
+  if (!ascending) b = ~b;
+  if (b == ~0ull) b = ~0ull - 1;  // keep the NaN key unique (only reachable by -NaN patterns, already excluded)
+  return b;
+}
+
+__global__ void k_roc_keys(long long n, const double* __restrict__ score, int ascending, unsigned long long* __restrict__ key,
+                           unsigned int* __restrict__ idx, unsigned long long* __restrict__ noScore) {
+  const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  int bad = 0;
+  if (i < n) {
+    const double s = score[i];
+    bad = (isnan(s) || isinf(s)) ? 1 : 0;
+    key[i] = rocKey(s, ascending);
+    idx[i] = (unsigned int) i;
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(noScore, (unsigned long long) __popc(m));
+}
+
+__global__ void k_roc_heads(long long n, const unsigned long long* __restrict__ key, int* __restrict__ head) {
+  const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) head[i] = (i == 0 || key[i] != key[i - 1]) ? 1 : 0;
+}
+
+// bucketStart[b] = first sorted position of bucket b; bucketOf = inclusive scan of head - 1
+__global__ void k_roc_starts(long long n, const int* __restrict__ head, const int* __restrict__ scan, int* __restrict__ bucketStart,
+                             int nBuckets) {
+  const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && head[i]) bucketStart[scan[i] - 1] = (int) i;
+  if (i == 0) bucketStart[nBuckets] = (int) n;
+}
+
+// One thread per (bucket, filter): sequential sums in arrival order.
+__global__ void k_roc_bucket_sums(int nBuckets, int nFilters, const int* __restrict__ bucketStart, const unsigned int* __restrict__ idx,
+                                  const double* __restrict__ tp, const double* __restrict__ fp, const double* __restrict__ raw,
+                                  const unsigned int* __restrict__ mask, double* __restrict__ sTp, double* __restrict__ sFp,
+                                  double* __restrict__ sRaw, int* __restrict__ nonEmpty) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int f = blockIdx.y;
+  if (b >= nBuckets) return;
+  const int s = bucketStart[b], e = bucketStart[b + 1];
+  double a = 0, c = 0, d = 0;
+  int cnt = 0;
+  for (int j = s; j < e; ++j) {
+    const unsigned int i = idx[j];
+    const unsigned int m = mask ? mask[i] : 0xffffffffu;
+    if ((m >> f) & 1u) {
+      if (cnt == 0) { a = tp[i]; c = fp[i]; d = raw[i]; }  // new RocPoint<>(point), RocContainer.java:256
+      else { a += tp[i]; c += fp[i]; d += raw[i]; }          // RocPoint.add
+      ++cnt;
+    }
+  }
+  const size_t o = (size_t) f * nBuckets + b;
+  sTp[o] = a; sFp[o] = c; sRaw[o] = d;
+  nonEmpty[o] = cnt > 0 ? 1 : 0;
+}
+
+// One warp per filter: cumulative sums over the buckets in key order, rows compacted to non-empty buckets.
+__global__ void k_roc_chain(int nBuckets, const int* __restrict__ bucketStart, const unsigned int* __restrict__ idx,
+                            const double* __restrict__ score, const double* __restrict__ sTp, const double* __restrict__ sFp,
+                            const double* __restrict__ sRaw, const int* __restrict__ nonEmpty, long long cap,
+                            double* __restrict__ oThr, double* __restrict__ oTp, double* __restrict__ oFp, double* __restrict__ oRaw,
+                            long long* __restrict__ nRows) {
+  const int f = blockIdx.x;
+  const int lane = threadIdx.x;
+  double ct = 0, cf = 0, cr = 0;   // new RocPoint<>() : zeros, RocContainer.java:297
+  long long row = 0;
+  const size_t fo = (size_t) f * nBuckets;
+  for (int base = 0; base < nBuckets; base += 32) {
+    const int b = base + lane;
+    double vt = 0, vf = 0, vr = 0;
+    int ne = 0;
+    if (b < nBuckets) {
+      ne = nonEmpty[fo + b];
+      vt = sTp[fo + b]; vf = sFp[fo + b]; vr = sRaw[fo + b];
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, ne);
+    double mt = 0, mf = 0, mr = 0;
+    // every lane replays the same dependent chain; lane j keeps the value after step j
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const double xt = __shfl_sync(0xffffffffu, vt, j);
+      const double xf = __shfl_sync(0xffffffffu, vf, j);
+      const double xr = __shfl_sync(0xffffffffu, vr, j);
+      if ((m >> j) & 1u) { ct += xt; cf += xf; cr += xr; }
+      if (j == lane) { mt = ct; mf = cf; mr = cr; }
+    }
+    if (ne) {
+      const long long r = row + __popc(m & ((1u << lane) - 1u));
+      if (r < cap) {
+        const size_t o = (size_t) f * cap + r;
+        double s = score[idx[bucketStart[b]]];
+        if (isnan(s) || isinf(s)) s = nan("");
+        oThr[o] = s; oTp[o] = mt; oFp[o] = mf; oRaw[o] = mr;
+      }
+    }
+    row += __popc(m);
+  }
+  if (lane == 0) nRows[f] = row;
+}
+
+#define ROC_TRY(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t e_ = (expr);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      char b_[512];                                                                           \
+      snprintf(b_, sizeof(b_), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      err = b_;                                                                               \
+      cleanup();                                                                              \
+      return VCE_ERR_CUDA;                                                                    \
+    }                                                                                         \
+  } while (0)
+
+int rocRun(int device, const vce_roc_in* in, vce_roc_out* out, std::string& err, RocTiming* timing) {
+  const long long n = in->n;
+  const int nF = in->n_filters;
+  if (n < 0 || nF < 1 || nF > 32 || n > 0x7fffffffLL - 64) { err = "bad ROC arguments"; return VCE_ERR_BAD_ARGUMENT; }
+  for (int f = 0; f < nF; ++f) out->n_rows[f] = 0;
+  *out->no_score = 0;
+  if (n == 0) return VCE_OK;
+  std::vector<void*> allocs;
+  cudaStream_t st = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+  auto cleanup = [&]() {
+    for (void* p : allocs) cudaFree(p);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (e2) cudaEventDestroy(e2);
+    if (st) cudaStreamDestroy(st);
+  };
+  auto alloc = [&](size_t bytes, void** p) -> cudaError_t {
+    cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
+    if (e == cudaSuccess) allocs.push_back(*p);
+    return e;
+  };
+  ROC_TRY(cudaSetDevice(device));
+  ROC_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  ROC_TRY(cudaEventCreate(&e0));
+  ROC_TRY(cudaEventCreate(&e1));
+  ROC_TRY(cudaEventCreate(&e2));
+  double *dScore, *dTp, *dFp, *dRaw;
+  unsigned int* dMask = nullptr;
+  unsigned long long *dKey, *dKey2, *dNoScore;
+  unsigned int *dIdx, *dIdx2;
+  int *dHead, *dScan, *dStart;
+  ROC_TRY(cudaEventRecord(e0, st));
+  ROC_TRY(alloc(n * 8, (void**) &dScore)); ROC_TRY(alloc(n * 8, (void**) &dTp)); ROC_TRY(alloc(n * 8, (void**) &dFp));
+  ROC_TRY(alloc(n * 8, (void**) &dRaw));
+  if (in->filter_mask) ROC_TRY(alloc(n * 4, (void**) &dMask));
+  ROC_TRY(alloc(n * 8, (void**) &dKey)); ROC_TRY(alloc(n * 8, (void**) &dKey2)); ROC_TRY(alloc(8, (void**) &dNoScore));
+  ROC_TRY(alloc(n * 4, (void**) &dIdx)); ROC_TRY(alloc(n * 4, (void**) &dIdx2));
+  ROC_TRY(alloc(n * 4, (void**) &dHead)); ROC_TRY(alloc(n * 4, (void**) &dScan)); ROC_TRY(alloc((n + 1) * 4, (void**) &dStart));
+  ROC_TRY(cudaMemcpyAsync(dScore, in->score, n * 8, cudaMemcpyHostToDevice, st));
+  ROC_TRY(cudaMemcpyAsync(dTp, in->tp, n * 8, cudaMemcpyHostToDevice, st));
+  ROC_TRY(cudaMemcpyAsync(dFp, in->fp, n * 8, cudaMemcpyHostToDevice, st));
+  ROC_TRY(cudaMemcpyAsync(dRaw, in->tp_raw, n * 8, cudaMemcpyHostToDevice, st));
+  if (dMask) ROC_TRY(cudaMemcpyAsync(dMask, in->filter_mask, n * 4, cudaMemcpyHostToDevice, st));
+  ROC_TRY(cudaMemsetAsync(dNoScore, 0, 8, st));
+  ROC_TRY(cudaEventRecord(e1, st));
+  const int tb = 256;
+  const int nb = (int) ((n + tb - 1) / tb);
+  k_roc_keys<<<nb, tb, 0, st>>>(n, dScore, in->ascending, dKey, dIdx, dNoScore);
+  size_t tmpBytes = 0, tmp2 = 0;
+  ROC_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, dKey, dKey2, dIdx, dIdx2, (int) n, 0, 64, st));
+  ROC_TRY(cub::DeviceScan::InclusiveSum(nullptr, tmp2, dHead, dScan, (int) n, st));
+  void* dTmp;
+  ROC_TRY(alloc(std::max(tmpBytes, tmp2) + 64, &dTmp));
+  ROC_TRY(cub::DeviceRadixSort::SortPairs(dTmp, tmpBytes, dKey, dKey2, dIdx, dIdx2, (int) n, 0, 64, st));
+  k_roc_heads<<<nb, tb, 0, st>>>(n, dKey2, dHead);
+  ROC_TRY(cub::DeviceScan::InclusiveSum(dTmp, tmp2, dHead, dScan, (int) n, st));
+  int nBuckets = 0;
+  ROC_TRY(cudaMemcpyAsync(&nBuckets, dScan + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+  ROC_TRY(cudaStreamSynchronize(st));
+  k_roc_starts<<<nb, tb, 0, st>>>(n, dHead, dScan, dStart, nBuckets);
+  double *sTp, *sFp, *sRaw, *oThr, *oTp, *oFp, *oRaw;
+  int* dNe;
+  long long* dRows;
+  const size_t fb = (size_t) nF * nBuckets;
+  const long long cap = nBuckets;
+  ROC_TRY(alloc(fb * 8, (void**) &sTp)); ROC_TRY(alloc(fb * 8, (void**) &sFp)); ROC_TRY(alloc(fb * 8, (void**) &sRaw));
+  ROC_TRY(alloc(fb * 4, (void**) &dNe)); ROC_TRY(alloc(nF * 8, (void**) &dRows));
+  ROC_TRY(alloc(fb * 8, (void**) &oThr)); ROC_TRY(alloc(fb * 8, (void**) &oTp)); ROC_TRY(alloc(fb * 8, (void**) &oFp));
+  ROC_TRY(alloc(fb * 8, (void**) &oRaw));
+  dim3 g((nBuckets + tb - 1) / tb, nF);
+  k_roc_bucket_sums<<<g, tb, 0, st>>>(nBuckets, nF, dStart, dIdx2, dTp, dFp, dRaw, dMask, sTp, sFp, sRaw, dNe);
+  k_roc_chain<<<nF, 32, 0, st>>>(nBuckets, dStart, dIdx2, dScore, sTp, sFp, sRaw, dNe, cap, oThr, oTp, oFp, oRaw, dRows);
+  ROC_TRY(cudaGetLastError());
+  ROC_TRY(cudaEventRecord(e2, st));
+  std::vector<long long> rows(nF);
+  unsigned long long noScore = 0;
+  ROC_TRY(cudaMemcpyAsync(rows.data(), dRows, nF * 8, cudaMemcpyDeviceToHost, st));
+  ROC_TRY(cudaMemcpyAsync(&noScore, dNoScore, 8, cudaMemcpyDeviceToHost, st));
+  ROC_TRY(cudaStreamSynchronize(st));
+  int rc = VCE_OK;
+  for (int f = 0; f < nF; ++f) {
+    out->n_rows[f] = rows[f];
+    long long k = rows[f];
+    if (k > out->cap) { k = out->cap; rc = VCE_ERR_CAPACITY; err = "ROC output capacity too small"; }
+    if (k > 0) {
+      ROC_TRY(cudaMemcpyAsync(out->threshold + (size_t) f * out->cap, oThr + (size_t) f * cap, k * 8, cudaMemcpyDeviceToHost, st));
+      ROC_TRY(cudaMemcpyAsync(out->cum_tp + (size_t) f * out->cap, oTp + (size_t) f * cap, k * 8, cudaMemcpyDeviceToHost, st));
+      ROC_TRY(cudaMemcpyAsync(out->cum_fp + (size_t) f * out->cap, oFp + (size_t) f * cap, k * 8, cudaMemcpyDeviceToHost, st));
+      ROC_TRY(cudaMemcpyAsync(out->cum_tp_raw + (size_t) f * out->cap, oRaw + (size_t) f * cap, k * 8, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  ROC_TRY(cudaStreamSynchronize(st));
+  *out->no_score = (int64_t) noScore;
+  if (timing) {
+    float a = 0, b = 0;
+    cudaEventElapsedTime(&a, e0, e1);
+    cudaEventElapsedTime(&b, e1, e2);
+    timing->h2dMs = a;
+    timing->kernelMs = b;
+    timing->launches = 9;
+  }
+  cleanup();
+  return rc;
+}
+
+}  // namespace vce

@@ -1,0 +1,197 @@
+"""Host-side mirror of the reference's interface for the vcfeval matching path, on top of the CUDA library.
+
+Reference classes mirrored (src/com/rtg/vcf/eval/ of RealTimeGenomics/rtg-tools):
+  SequenceEvaluator.run()      -> Engine.submit() / SequenceEvaluator.evaluate()   (SequenceEvaluator.java:76-158)
+  PathFinder(...).bestPath()   -> PathFinder(...).best_path()                      (PathFinder.java:106-214)
+  PathFinder.Config            -> capi.Config                                      (PathFinder.java:51-101)
+  RocContainer                 -> RocContainer.add_roc_line / rows                 (RocContainer.java:225-318)
+
+There is no CPU implementation behind these classes: constructing an Engine without a visible CUDA device
+(or without the built csrc/libvce.so) raises.
+"""
+import ctypes as C
+import os
+from typing import List, Optional
+
+import numpy as np
+
+from . import capi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libvce.so")
+
+
+class EngineUnavailable(RuntimeError):
+    pass
+
+
+class Job:
+    """Staged evaluation (vce_job_*): create = pack + H2D, run = device pipeline, fetch = D2H + assembly."""
+
+    def __init__(self, engine, cfg, seqs):
+        self.engine = engine
+        self.ccfg, self.cseqs, self.cres, self.results, self.keep = capi.Library.pack(cfg, seqs)
+        self.seqs = seqs
+        self.handle = C.c_void_p()
+        lib = engine.lib.lib
+        rc = lib.vce_job_create(C.byref(self.ccfg), len(seqs), self.cseqs, C.byref(self.handle))
+        if rc != 0:
+            raise RuntimeError("vce_job_create: %s %s" % (capi.ERR_NAMES.get(rc, rc), engine.lib.last_error()))
+
+    def run(self):
+        rc = self.engine.lib.lib.vce_job_run(self.handle)
+        if rc != 0:
+            raise RuntimeError("vce_job_run: %s %s" % (capi.ERR_NAMES.get(rc, rc), self.engine.lib.last_error()))
+
+    def fetch(self) -> List[capi.SequenceResult]:
+        rc = self.engine.lib.lib.vce_job_fetch(self.handle, self.cres)
+        capi.Library.unpack(self.cres, self.results, self.keep)
+        if rc != 0 and all(r.error == 0 for r in self.results):
+            raise RuntimeError("vce_job_fetch: %s %s" % (capi.ERR_NAMES.get(rc, rc), self.engine.lib.last_error()))
+        return self.results
+
+    def stats(self):
+        n_launch = C.c_int64()
+        dev_ms = C.c_double()
+        fast_ms = C.c_double()
+        n_reg = C.c_int64()
+        n_esc = C.c_int64()
+        self.engine.lib.lib.vce_job_stats(self.handle, C.byref(n_launch), C.byref(dev_ms), C.byref(fast_ms), C.byref(n_reg),
+                                          C.byref(n_esc))
+        return dict(launches=n_launch.value, search_ms=dev_ms.value, fast_kernel_ms=fast_ms.value, regions=n_reg.value,
+                    escalated=n_esc.value)
+
+    def close(self):
+        if self.handle:
+            self.engine.lib.lib.vce_job_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Engine:
+    """The CUDA vcfeval engine on one device."""
+
+    def __init__(self, device: int = 0):
+        if not os.path.exists(LIB_PATH):
+            raise EngineUnavailable("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'`" % LIB_PATH)
+        self.lib = capi.Library(LIB_PATH, prefix="vce_")
+        lib = self.lib.lib
+        lib.vce_init.restype = C.c_int
+        lib.vce_init.argtypes = [C.c_int]
+        lib.vce_job_create.restype = C.c_int
+        lib.vce_job_create.argtypes = [C.POINTER(capi.CConfig), C.c_int32, C.POINTER(capi.CSequence), C.POINTER(C.c_void_p)]
+        lib.vce_job_run.restype = C.c_int
+        lib.vce_job_run.argtypes = [C.c_void_p]
+        lib.vce_job_fetch.restype = C.c_int
+        lib.vce_job_fetch.argtypes = [C.c_void_p, C.POINTER(capi.CSequenceResult)]
+        lib.vce_job_destroy.restype = None
+        lib.vce_job_destroy.argtypes = [C.c_void_p]
+        lib.vce_job_stats.restype = C.c_int
+        lib.vce_job_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                      C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        rc = lib.vce_init(device)
+        if rc != 0:
+            raise EngineUnavailable("vce_init(%d) failed: %s %s" % (device, capi.ERR_NAMES.get(rc, rc), self.lib.last_error()))
+        self.device = device
+
+    def submit(self, cfg: capi.Config, seqs: List[capi.Sequence]) -> List[capi.SequenceResult]:
+        return self.lib.submit(cfg, seqs)
+
+    def job(self, cfg, seqs) -> Job:
+        return Job(self, cfg, seqs)
+
+    def roc(self, *a, **k):
+        return self.lib.roc(*a, **k)
+
+
+# ----------------------------------------------------------------------------------------------- reference-style API
+class Path:
+    """What PathFinder.bestPath() returns (Path.java): included / excluded lists per side + sync points."""
+
+    def __init__(self, seq: capi.Sequence, res: capi.SequenceResult):
+        S = capi
+        self.sync_points = [int(x) for x in res.sync_points[0]]
+
+        def split(side_res, side):
+            inc, exc, skipped = [], [], []
+            for i in range(side.n):
+                st = int(side_res.status[i])
+                if st & S.STATUS_GT_MATCH:
+                    inc.append((int(side.id[i]), tuple(int(a) for a in side_res.allele_ids[i] if a != -2), bool(side_res.original[i]),
+                                float(side_res.weight[i])))
+                elif st & S.STATUS_NO_MATCH:
+                    exc.append(int(side.id[i]))
+                else:
+                    skipped.append(int(side.id[i]))
+            return inc, exc, skipped
+        self.called_included, self.called_excluded, self.called_skipped = split(res.calls, seq.calls)
+        self.baseline_included, self.baseline_excluded, self.baseline_skipped = split(res.baseline, seq.baseline)
+
+
+class PathFinder:
+    """PathFinder(template, templateName, baseLineVariants, calledVariants, baselineOrientor, callOrientor, config)
+    (PathFinder.java:106-127).  Variants are capi.VariantSide images; orientors are capi.ORIENT_* codes."""
+
+    def __init__(self, engine: Engine, template, template_name, baseline: capi.VariantSide, calls: capi.VariantSide,
+                 baseline_orientor=capi.ORIENT_UNPHASED, call_orientor=capi.ORIENT_UNPHASED, haplotypes=2,
+                 config: Optional[capi.Config] = None):
+        self.engine = engine
+        self.seq = capi.Sequence(template_name, np.asarray(template, np.uint8), baseline, calls)
+        cfg = config or capi.Config()
+        self.cfg = capi.Config(n_passes=1, baseline_orientor=(baseline_orientor, baseline_orientor),
+                               calls_orientor=(call_orientor, call_orientor), ploidy=(haplotypes, haplotypes),
+                               max_paths=cfg.max_paths, max_iterations=cfg.max_iterations, prune_no_ops=cfg.prune_no_ops,
+                               flag_alternates=cfg.flag_alternates, preference=cfg.preference)
+
+    def best_path(self) -> Path:
+        # note: SequenceEvaluator short-circuits when a side is empty (SequenceEvaluator.java:94-97); so does this
+        res = self.engine.submit(self.cfg, [self.seq])[0]
+        if res.error:
+            raise RuntimeError(capi.ERR_NAMES.get(res.error, str(res.error)))
+        self.result = res
+        return Path(self.seq, res)
+
+
+class SequenceEvaluator:
+    """SequenceEvaluator (SequenceEvaluator.java:56-158) for a batch of sequences."""
+
+    def __init__(self, engine: Engine, config: Optional[capi.Config] = None):
+        self.engine = engine
+        self.config = config or capi.Config()
+
+    def evaluate(self, seqs: List[capi.Sequence]) -> List[capi.SequenceResult]:
+        return self.engine.submit(self.config, seqs)
+
+
+class RocContainer:
+    """RocContainer accumulate / sorted cumulative scan (RocContainer.java:204-318); formatting stays with the caller."""
+
+    def __init__(self, engine: Engine, n_filters: int = 1, ascending: bool = False):
+        self.engine = engine
+        self.n_filters = n_filters
+        self.ascending = ascending
+        self._score, self._tp, self._fp, self._raw, self._mask = [], [], [], [], []
+
+    def add_roc_line(self, score, tp_weight, fp_weight, tp_raw, filter_mask=0xffffffff):
+        self._score.append(score)
+        self._tp.append(tp_weight)
+        self._fp.append(fp_weight)
+        self._raw.append(tp_raw)
+        self._mask.append(filter_mask)
+
+    def add_roc_lines(self, score, tp, fp, raw, mask=None):
+        self._score.extend(np.asarray(score, np.float64).tolist())
+        self._tp.extend(np.asarray(tp, np.float64).tolist())
+        self._fp.extend(np.asarray(fp, np.float64).tolist())
+        self._raw.extend(np.asarray(raw, np.float64).tolist())
+        n = len(np.asarray(score))
+        self._mask.extend([0xffffffff] * n if mask is None else np.asarray(mask, np.uint32).tolist())
+
+    def rows(self):
+        return self.engine.roc(np.array(self._score, np.float64), np.array(self._tp, np.float64), np.array(self._fp, np.float64),
+                               np.array(self._raw, np.float64), np.array(self._mask, np.uint32), self.n_filters, self.ascending)

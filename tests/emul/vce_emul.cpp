@@ -22,7 +22,16 @@ class EmulBackend : public Backend {
   bool forceGeneral = false;
   int setAlleles(int side, const AlleleTable& t) override { al_[side] = &t; return 0; }
 
-  int beginPass(PassData& pd) override {
+  int uploadPass(PassData& pd) override { return resetPass(pd); }
+  int resetPass(PassData& pd) override {
+    for (int side = 0; side < 2; ++side) {
+      pd.side[side].decision.assign(pd.side[side].n(), 0);
+      pd.side[side].weight.assign(pd.side[side].n(), 0.0);
+    }
+    return 0;
+  }
+  int stage(const std::vector<RegionDesc>&, const std::vector<uint8_t>&, const std::vector<int32_t>&, size_t) override { return 0; }
+  int orient(PassData& pd) override {
     for (int side = 0; side < 2; ++side) {
       HostSide& hs = pd.side[side];
       const size_t n = hs.n();
@@ -35,7 +44,7 @@ class EmulBackend : public Backend {
         hs.oOff[v + 1] = hs.oOff[v] + cnt.n;
         mo = std::max(mo, cnt.n);
       }
-      pd.maxOrient[side] = mo;
+      if (mo > pd.maxOrient[side]) { err_ = "orientation bound violated"; return VCE_ERR_UNSUPPORTED; }
       const size_t rows = hs.oOff[n];
       oSlot_[side].assign(rows * pd.H + 1, -1);
       hs.oIds.assign(rows * 4 + 4, -2);
@@ -45,16 +54,16 @@ class EmulBackend : public Backend {
         OrientFill f{hs.oOff[v], pd.H, g.slot0, g.nSlots, g.aNull, oSlot_[side].data(), hs.oIds.data(), hs.oOrig.data()};
         orientVariant(pd.kind[side], pd.H, g, f);
       }
-      hs.decision.assign(n, 0);
-      hs.weight.assign(n, 0.0);
     }
     return 0;
   }
 
   int search(PassData& pd, const SearchConfig& sc, const std::vector<RegionDesc>& regs, const std::vector<uint8_t>& windows,
-             bool general, std::vector<RegionResult>& out, const std::vector<int32_t>& syncOff, std::vector<int32_t>& syncOut,
+             bool general, bool /*staged*/, std::vector<RegionResult>& out, const std::vector<int32_t>& syncOff, size_t syncTotal,
              std::vector<WarnRec>& warns) override {
     ++stats.launches;
+    std::vector<int32_t>& syncOut = sync_[pd.pass];
+    if (syncOut.size() < syncTotal) syncOut.resize(syncTotal, 0);
     for (size_t q = 0; q < regs.size(); ++q) {
       RegionSearch<HostLane> rs;
       rs.R = regs[q];
@@ -112,7 +121,11 @@ class EmulBackend : public Backend {
     }
     return 0;
   }
-  int fetchPass(PassData&) override { return 0; }
+  int fetchPass(PassData& pd, std::vector<int32_t>& syncBuf) override {
+    std::vector<int32_t>& so = sync_[pd.pass];
+    for (size_t i = 0; i < syncBuf.size() && i < so.size(); ++i) syncBuf[i] = so[i];
+    return 0;
+  }
   const char* lastError() const override { return err_.c_str(); }
 
  private:
@@ -128,6 +141,7 @@ class EmulBackend : public Backend {
   }
   const AlleleTable* al_[2] = {nullptr, nullptr};
   std::vector<int32_t> oSlot_[2];
+  std::vector<int32_t> sync_[2];
   std::string err_;
 };
 

@@ -1,0 +1,116 @@
+"""Parity tests proper: the CUDA engine, called through the C-ABI (libvce.so), against the CPU oracle and the
+reference's golden fixtures.  Bit-exact everywhere: statuses, orientations, sync points, phasing counts, warnings,
+and FP64 weights / ROC sums compared as raw bit patterns."""
+import os
+
+import numpy as np
+import pytest
+
+from compare import compare_results
+from golden_check import check_scenario
+from helpers import CONFIGS, fuzz_batch
+from rtg_tools_b200 import capi, synth
+from test_oracle_golden import SCENARIOS
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from rtg_tools_b200 import vcfeval
+    return vcfeval.Engine(0)
+
+
+@pytest.mark.parametrize("name", SCENARIOS)
+def test_cuda_reproduces_reference_golden(engine, fixtures, name):
+    assert check_scenario(engine, fixtures[name])
+
+
+@pytest.mark.parametrize("cfg_name", sorted(CONFIGS))
+def test_cuda_matches_oracle_on_fuzz(engine, oracle, cfg_name):
+    cfg = CONFIGS[cfg_name]
+    seqs = []
+    for seed in range(40):
+        seqs += fuzz_batch(seed, n_seq=4)
+    compare_results(oracle.submit(cfg, seqs), engine.submit(cfg, seqs), seqs, what=cfg_name)
+
+
+def test_cuda_c1_synthetic_pair(engine, oracle):
+    """BASELINE.json configs[0]: 10 Mbp, ~15 k variants per side, diploid."""
+    seqs = synth.make_pair(10_000_000, n_chrom=1)
+    assert 12000 < seqs[0].baseline.n < 18000
+    for name in ("default", "twopass", "squash"):
+        compare_results(oracle.submit(CONFIGS[name], seqs), engine.submit(CONFIGS[name], seqs), seqs, what=name)
+
+
+def test_cuda_multi_chromosome(engine, oracle):
+    seqs = synth.make_pair(60_000_000, n_chrom=24)
+    compare_results(oracle.submit(CONFIGS["twopass"], seqs, threads=8), engine.submit(CONFIGS["twopass"], seqs), seqs)
+
+
+def test_cuda_dense_clusters(engine, oracle):
+    """BASELINE.json configs[2]: dense overlapping clusters that exceed the (here reduced) search budget."""
+    rng = np.random.default_rng(3)
+    seqs = [synth.dense_cluster_sequence(rng, n_clusters=4, per_side=(6, 10), name="d%d" % i) for i in range(3)]
+    cfg = capi.Config(max_paths=2000, max_iterations=20000)
+    want = oracle.submit(cfg, seqs)
+    assert any(r.warnings for r in want)
+    compare_results(want, engine.submit(cfg, seqs), seqs)
+
+
+def test_cuda_staged_job_equals_submit(engine, oracle):
+    seqs = synth.make_pair(2_000_000, n_chrom=2)
+    job = engine.job(CONFIGS["twopass"], seqs)
+    job.run()
+    job.run()  # re-runnable
+    got = job.fetch()
+    st = job.stats()
+    job.close()
+    compare_results(oracle.submit(CONFIGS["twopass"], seqs), got, seqs)
+    assert st["launches"] > 0 and st["regions"] > 0
+
+
+def test_cuda_empty_inputs(engine, oracle):
+    rng = np.random.default_rng(5)
+    seqs = [synth.fuzz_sequence(rng, n_base=0, n_calls=5, name="nobase"), synth.fuzz_sequence(rng, n_base=4, n_calls=4, name="full"),
+            synth.fuzz_sequence(rng, n_base=0, n_calls=0, name="none"), synth.fuzz_sequence(rng, n_base=5, n_calls=0, name="nocalls")]
+    for name in ("default", "twopass"):
+        compare_results(oracle.submit(CONFIGS[name], seqs), engine.submit(CONFIGS[name], seqs), seqs)
+    assert engine.submit(CONFIGS["default"], []) == []
+
+
+def _roc_equal(a, b):
+    (ra, na), (rb, nb) = a, b
+    assert na == nb
+    assert len(ra) == len(rb)
+    for fa, fb in zip(ra, rb):
+        for x, y in zip(fa, fb):
+            assert x.shape == y.shape
+            assert np.array_equal(x.view(np.int64), y.view(np.int64))
+
+
+@pytest.mark.parametrize("n,asc", [(1, False), (1000, False), (1000, True), (200_000, False)])
+def test_cuda_roc_matches_oracle(engine, oracle, n, asc):
+    rng = np.random.default_rng(n)
+    score = np.round(rng.uniform(-5, 60, n), 1)
+    score[rng.random(n) < 0.02] = np.nan
+    score[rng.random(n) < 0.005] = np.inf
+    score[rng.random(n) < 0.01] = 0.0
+    score[rng.random(n) < 0.01] = -0.0
+    tp = rng.choice([1.0, 0.5, 1.0 / 3, 2.0 / 3, 0.2, 2.0, 0.0], n)
+    fp = (tp == 0).astype(np.float64)
+    raw = (tp > 0).astype(np.float64)
+    mask = rng.integers(0, 32, n).astype(np.uint32)
+    _roc_equal(engine.roc(score, tp, fp, raw, mask, 5, asc), oracle.roc(score, tp, fp, raw, mask, 5, asc))
+    _roc_equal(engine.roc(score, tp, fp, raw, None, 1, asc), oracle.roc(score, tp, fp, raw, None, 1, asc))
+
+
+def test_cuda_roc_known_answer(engine):
+    """RocContainerTest.java:45-85: accumulate + cumulative known answers."""
+    score = np.array([0.1, 0.1, 0.2, 0.2, 0.1, 0.3])
+    tp = np.array([1.0, 1.0, 1.0, 0.0, 1.0, 1.0])
+    fp = 1.0 - tp
+    rows, _ = engine.roc(score, tp, fp, tp, None, 1, False)
+    thr, ctp, cfp, craw = rows[0]
+    assert list(thr) == [0.3, 0.2, 0.1]
+    assert list(ctp) == [1.0, 2.0, 5.0] and list(cfp) == [0.0, 1.0, 1.0]

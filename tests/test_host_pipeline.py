@@ -1,0 +1,127 @@
+"""Host logic of the product (packing, region split, SPILL merge, escalation, prefix re-runs, assembly) exercised on the
+CPU through the test-only 1-lane instantiation of the search source (tests/emul), against the oracle."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from compare import compare_results
+from golden_check import check_scenario
+from helpers import CONFIGS, ROOT, Hybrid, emul_library, emul_stats, fuzz_batch
+from rtg_tools_b200 import capi, synth
+from test_oracle_golden import SCENARIOS
+
+
+@pytest.fixture(scope="module")
+def emul():
+    return emul_library()
+
+
+@pytest.mark.parametrize("name", SCENARIOS)
+def test_pipeline_reproduces_reference_golden(emul, oracle, fixtures, name):
+    assert check_scenario(Hybrid(emul, oracle), fixtures[name])
+
+
+@pytest.mark.parametrize("cfg_name", sorted(CONFIGS))
+def test_pipeline_matches_oracle_on_fuzz(emul, oracle, cfg_name):
+    cfg = CONFIGS[cfg_name]
+    tot = dict(spilled=0, escalated=0, prefix_reruns=0)
+    for seed in range(60):
+        seqs = fuzz_batch(seed)
+        compare_results(oracle.submit(cfg, seqs), emul.submit(cfg, seqs), seqs, what="%s seed %d" % (cfg_name, seed))
+        st = emul_stats(emul)
+        for k in tot:
+            tot[k] += st[k]
+    # the interesting host paths must actually have been taken
+    assert tot["spilled"] > 0
+
+
+def test_every_split_gap_and_margin_is_exact(emul, oracle):
+    """Exactness must not depend on the split heuristics: any gap / window margin gives identical results."""
+    seqs = fuzz_batch(1234, n_seq=6)
+    want = oracle.submit(CONFIGS["twopass"], seqs)
+    try:
+        for gap, margin in ((1, 0), (1, 4), (3, 24), (50, 1), (100000, 24)):
+            emul.lib.emul_set_options(gap, margin, 0)
+            compare_results(want, emul.submit(CONFIGS["twopass"], seqs), seqs, what="gap %d margin %d" % (gap, margin))
+    finally:
+        emul.lib.emul_set_options(1, 24, 0)
+
+
+def test_large_capacity_path_is_exact(emul, oracle):
+    """Force every region through the large-capacity (arena) layout."""
+    try:
+        emul.lib.emul_set_options(1, 24, 1)
+        for seed in range(20):
+            seqs = fuzz_batch(5000 + seed)
+            compare_results(oracle.submit(CONFIGS["twopass"], seqs), emul.submit(CONFIGS["twopass"], seqs), seqs)
+    finally:
+        emul.lib.emul_set_options(1, 24, 0)
+
+
+def test_synthetic_genome_pair(emul, oracle):
+    seqs = synth.make_pair(3_000_000, n_chrom=3)
+    assert sum(s.calls.n for s in seqs) > 3000
+    for name in ("default", "twopass", "squash"):
+        compare_results(oracle.submit(CONFIGS[name], seqs), emul.submit(CONFIGS[name], seqs), seqs, what=name)
+
+
+def test_dense_clusters_hit_the_budget(emul, oracle):
+    rng = np.random.default_rng(3)
+    seqs = [synth.dense_cluster_sequence(rng, n_clusters=3, per_side=(6, 10))]
+    cfg = capi.Config(max_paths=2000, max_iterations=20000)
+    want = oracle.submit(cfg, seqs)
+    assert want[0].warnings, "stress input should exceed the reduced budget"
+    compare_results(want, emul.submit(cfg, seqs), seqs)
+
+
+def test_empty_and_one_sided_sequences(emul, oracle):
+    rng = np.random.default_rng(5)
+    full = synth.fuzz_sequence(rng, n_base=5, n_calls=5, name="full")
+    nob = synth.fuzz_sequence(rng, n_base=0, n_calls=5, name="nobase")
+    noc = synth.fuzz_sequence(rng, n_base=5, n_calls=0, name="nocalls")
+    none = synth.fuzz_sequence(rng, n_base=0, n_calls=0, name="none")
+    seqs = [nob, full, none, noc]
+    for name in ("default", "twopass"):
+        compare_results(oracle.submit(CONFIGS[name], seqs), emul.submit(CONFIGS[name], seqs), seqs)
+    assert emul.submit(CONFIGS["default"], []) == []
+
+
+# ------------------------------------------------------------------------------------------- the C-ABI library itself
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "vce.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vce_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    so = os.path.join(ROOT, "rtg_tools_b200", "csrc", "libvce.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-C", os.path.dirname(so)])
+    lib = ctypes.CDLL(so)
+    names = _declared_functions()
+    assert "vce_submit" in names and "vce_roc" in names and len(names) >= 12
+    for n in names:
+        assert hasattr(lib, n), "libvce.so does not export " + n
+
+
+def test_product_fails_loudly_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from rtg_tools_b200 import vcfeval
+    with pytest.raises(vcfeval.EngineUnavailable):
+        vcfeval.Engine(0)
+    lib = ctypes.CDLL(vcfeval.LIB_PATH)
+    assert lib.vce_init(0) == 4  # VCE_ERR_NO_DEVICE
+    cfg = capi.Config().to_c()
+    assert lib.vce_submit(ctypes.byref(cfg), 0, None, None) != 0
+
+
+def test_product_library_does_not_contain_the_oracle_or_the_emulation():
+    so = os.path.join(ROOT, "rtg_tools_b200", "csrc", "libvce.so")
+    syms = subprocess.check_output(["nm", "-D", "--defined-only", so]).decode()
+    assert "oracle_" not in syms and "emul_" not in syms
