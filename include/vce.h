@@ -215,8 +215,15 @@ void vce_job_destroy(vce_job* job);
 int  vce_job_stats(const vce_job* job, int64_t* n_launches, double* device_ms, double* search_kernel_ms,
                    int64_t* n_regions, int64_t* n_escalated);
 
+/* Extended diagnostics of the last vce_job_run, out[0..n): launches, search-kernel ms, ms and region count of the largest
+   shared-memory search launch, regions, escalated, spilled, prefix re-runs, H2D bytes, D2H bytes, best-first iterations,
+   device ms of the whole run (CUDA events on the job's stream). */
+int  vce_job_stats_ex(const vce_job* job, double* out, int32_t n);
+
 /* RocContainer accumulate + sort + cumulative scan on the device. */
 int vce_roc(const vce_roc_in* in, vce_roc_out* out);
+/* Same, also reporting host->device and kernel milliseconds (CUDA events) and the number of kernel launches. */
+int vce_roc_timed(const vce_roc_in* in, vce_roc_out* out, double* h2d_ms, double* kernel_ms, int32_t* launches);
 
 /* Formats the reference's warning text (PathFinder.java:163). Returns bytes written (excluding NUL). */
 int vce_format_warning(const vce_warning* w, const char* seq_name, char* buf, int32_t cap);

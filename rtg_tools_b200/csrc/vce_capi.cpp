@@ -29,6 +29,7 @@ struct vce_job {
   int32_t nSeq = 0;
   const vce_sequence* seqs = nullptr;
   bool prepared = false;
+  double executeMs = 0;
 };
 
 extern "C" {
@@ -91,11 +92,13 @@ int vce_job_create(const vce_config* cfg, int32_t n_seq, const vce_sequence* seq
 
 int vce_job_run(vce_job* job) {
   if (!job || !job->prepared) return fail(VCE_ERR_BAD_ARGUMENT, "job not prepared");
+  // inputs are resident on the device since vce_job_create; only the device pipeline runs here
+  const int64_t h2d = job->backend->stats.h2dBytes;
   job->backend->stats = vce::SearchStats();
-  // the search is re-runnable: pass state is rebuilt from the packed inputs
-  int rc = job->pipeline->prepare(job->cfg, job->nSeq, job->seqs);
-  if (rc) return fail(rc, job->pipeline->error());
-  rc = job->pipeline->execute();
+  job->backend->stats.h2dBytes = h2d;
+  job->backend->timerStart();
+  const int rc = job->pipeline->execute();
+  job->executeMs = job->backend->timerStopMs();
   if (rc) return fail(rc, job->pipeline->error());
   return VCE_OK;
 }
@@ -123,6 +126,19 @@ int vce_job_stats(const vce_job* job, int64_t* n_launches, double* device_ms, do
     vce::cudaBackendFastStats(job->backend.get(), &ms, &regs);
     *search_kernel_ms = ms;
   }
+  return VCE_OK;
+}
+
+int vce_job_stats_ex(const vce_job* job, double* out, int32_t n) {
+  if (!job || !out) return fail(VCE_ERR_BAD_ARGUMENT, "null argument");
+  const vce::SearchStats& s = job->backend->stats;
+  double fastMs = 0;
+  long long fastRegions = 0;
+  vce::cudaBackendFastStats(job->backend.get(), &fastMs, &fastRegions);
+  const double v[12] = {(double) s.launches, s.searchMs, fastMs, (double) fastRegions, (double) s.regions, (double) s.escalated,
+                        (double) s.spilled, (double) s.prefixReruns, (double) s.h2dBytes, (double) s.d2hBytes,
+                        (double) s.iterations, job->executeMs};
+  for (int i = 0; i < n && i < 12; ++i) out[i] = v[i];
   return VCE_OK;
 }
 

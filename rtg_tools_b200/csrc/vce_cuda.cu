@@ -254,6 +254,8 @@ class CudaBackend : public Backend {
     CUDA_TRY(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&ev0_));
     CUDA_TRY(cudaEventCreate(&ev1_));
+    CUDA_TRY(cudaEventCreate(&evT0_));
+    CUDA_TRY(cudaEventCreate(&evT1_));
     CUDA_TRY(cudaDeviceGetAttribute(&smCount_, cudaDevAttrMultiProcessorCount, device_));
     int maxSmem = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_));
@@ -271,6 +273,8 @@ class CudaBackend : public Backend {
     warnScratch_.release(); ints_.release(); arena_.release(); scanTmp_.release();
     cudaEventDestroy(ev0_);
     cudaEventDestroy(ev1_);
+    cudaEventDestroy(evT0_);
+    cudaEventDestroy(evT1_);
     cudaStreamDestroy(stream_);
     ready_ = false;
   }
@@ -540,6 +544,18 @@ class CudaBackend : public Backend {
   }
 
   const char* lastError() const override { return err_.c_str(); }
+  void timerStart() override {
+    cudaSetDevice(device_);
+    cudaEventRecord(evT0_, stream_);
+  }
+  double timerStopMs() override {
+    cudaSetDevice(device_);
+    cudaEventRecord(evT1_, stream_);
+    cudaEventSynchronize(evT1_);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, evT0_, evT1_);
+    return ms;
+  }
   cudaStream_t stream() const { return stream_; }
   int device() const { return device_; }
   double lastFastMs_ = 0;
@@ -549,7 +565,7 @@ class CudaBackend : public Backend {
   int device_;
   bool ready_ = false;
   cudaStream_t stream_ = nullptr;
-  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr, evT0_ = nullptr, evT1_ = nullptr;
   int smCount_ = 148;
   int maxSmemOptin_ = 0;
   AlleleDev al_[2];

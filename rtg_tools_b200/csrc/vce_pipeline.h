@@ -82,6 +82,9 @@ class Backend {
   // Copies decision / weight / orientation-id arrays of the pass and the sync-point buffer back to the host.
   virtual int fetchPass(PassData& pd, std::vector<int32_t>& syncBuf) = 0;
   virtual const char* lastError() const = 0;
+  // Device-side stopwatch on the backend's stream (CUDA events): brackets a whole execute().
+  virtual void timerStart() {}
+  virtual double timerStopMs() { return 0.0; }
   SearchStats stats;
 };
 

@@ -239,18 +239,27 @@ def to_side(vs: VarSet, template) -> capi.VariantSide:
         allele_nt_off=nt_off, nt=nt)
 
 
-def make_pair(total_bp, n_chrom=1, genome_seed=42, sample_seed=572, perturb_seed=126, **kw) -> List[capi.Sequence]:
-    """BASELINE.md C1 (total_bp=10e6, n_chrom=1) / C2 (total_bp=3e9, n_chrom=24)."""
+def make_sequence(name, length, genome_seed, sample_seed, perturb_seed, return_qual=False, **kw):
+    """One chromosome: uniform ACGT template, baseline sample, perturbed calls (each from its own seed stream)."""
+    tmpl = np.random.default_rng(genome_seed).integers(1, 5, size=int(length), dtype=np.uint8)
+    base = simulate_sample(tmpl, np.random.default_rng(sample_seed))
+    calls = perturb(tmpl, base, np.random.default_rng(perturb_seed), **kw)
+    seq = capi.Sequence(name, tmpl, to_side(base, tmpl), to_side(calls, tmpl))
+    return (seq, calls.qual) if return_qual else seq
+
+
+def make_pair(total_bp, n_chrom=1, genome_seed=42, sample_seed=572, perturb_seed=126, only=None, return_qual=False, **kw):
+    """BASELINE.md C1 (total_bp=10e6, n_chrom=1) / C2 (total_bp=3e9, n_chrom=24).  Every chromosome draws from its own
+    (seed, chromosome) streams, so `only=[...]` builds any subset identically to the full genome."""
     lens = genome_lengths(total_bp, n_chrom) if n_chrom > 1 else [int(total_bp)]
-    genome = make_genome(lens, genome_seed)
-    rs = np.random.default_rng(sample_seed)
-    rp = np.random.default_rng(perturb_seed)
-    out = []
-    for c, tmpl in enumerate(genome):
-        base = simulate_sample(tmpl, rs)
-        calls = perturb(tmpl, base, rp, **kw)
-        out.append(capi.Sequence("chr%d" % (c + 1), tmpl, to_side(base, tmpl), to_side(calls, tmpl)))
-    return out
+    out, quals = [], []
+    for c, ln in enumerate(lens):
+        if only is not None and c not in only:
+            continue
+        seq, q = make_sequence("chr%d" % (c + 1), ln, (genome_seed, c), (sample_seed, c), (perturb_seed, c), True, **kw)
+        out.append(seq)
+        quals.append(q)
+    return (out, quals) if return_qual else out
 
 
 def qualities(seqs_calls: List[VarSet]):

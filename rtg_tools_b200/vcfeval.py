@@ -50,6 +50,13 @@ class Job:
             raise RuntimeError("vce_job_fetch: %s %s" % (capi.ERR_NAMES.get(rc, rc), self.engine.lib.last_error()))
         return self.results
 
+    def stats_ex(self):
+        out = (C.c_double * 12)()
+        self.engine.lib.lib.vce_job_stats_ex(self.handle, out, 12)
+        keys = ["launches", "search_ms", "fast_kernel_ms", "fast_regions", "regions", "escalated", "spilled", "prefix_reruns",
+                "h2d_bytes", "d2h_bytes", "iterations", "execute_ms"]
+        return {k: out[i] for i, k in enumerate(keys)}
+
     def stats(self):
         n_launch = C.c_int64()
         dev_ms = C.c_double()
@@ -94,6 +101,8 @@ class Engine:
         lib.vce_job_stats.restype = C.c_int
         lib.vce_job_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                       C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        lib.vce_job_stats_ex.restype = C.c_int
+        lib.vce_job_stats_ex.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int32]
         rc = lib.vce_init(device)
         if rc != 0:
             raise EngineUnavailable("vce_init(%d) failed: %s %s" % (device, capi.ERR_NAMES.get(rc, rc), self.lib.last_error()))
