@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- vcfeval matching throughput on B200 (BASELINE.json metric: variants evaluated/s).
+
+A "step" is one pass of the hot path (SequenceEvaluator.run() for every sequence of the workload:
+orientation expansion, region search, tie-break/weights, status merge, sync ids, phasing counts) over one
+batch of synthetic input.
+
+  value : whole-job variants/s with the batch already resident in HBM (staged job: vce_job_run), timed with CUDA
+          events on the engine's stream, max over ranks
+  e2e   : the same metric through the reference-facing C-ABI call vce_submit() with HOST buffers: packing, H2D,
+          kernels, D2H and result assembly all inside the timed region
+  roofline : the dominant kernel (shared-memory region search), 48 algorithmic bytes per variant
+  cpu_baseline : the CPU oracle (C++ restatement of the reference, "port": the reference is Java and the image
+          has no JDK) on the host cores, one worker per sequence like the reference's SimpleThreadPool
+
+`--impl reference` times that CPU path alone, on the same workload, as the reference arm.
+
+Multi-GPU (torchrun, one rank per GPU): sequences are independent units (VcfEvalTask.java:131-135), so every rank
+evaluates its own shard with no data-path collective; the only exchange is the summary-count merge (NCCL
+all-reduce).  Default scaling is weak: rank r evaluates sample pair r of the cohort (same 24-chromosome genome
+layout, different sample seeds); `--scaling strong` shards ONE pair's chromosomes over the ranks by LPT.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+ALG_BYTES_PER_VARIANT = 48  # 32 B in + 16 B out per variant
+ALG_BYTES_PER_ROC_CALL = 72
+
+WORKLOADS = {
+    # name: (total_bp, n_chrom, description)
+    "c2": (3_000_000_000, 24, "synthetic 3 Gbp 24-chromosome genome, ~4.4M baseline/call variants per side (BASELINE.json configs[1])"),
+    "c1": (10_000_000, 1, "synthetic 10 Mbp genome, ~15k variants per side (BASELINE.json configs[0])"),
+    "tiny": (2_000_000, 4, "2 Mbp smoke workload"),
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(name, rank, world, scaling, total_bp=None):
+    from rtg_tools_b200 import partition, synth
+    bp, n_chrom, desc = WORKLOADS[name]
+    if total_bp:
+        bp = int(total_bp)
+    if scaling == "strong" and world > 1:
+        lens = synth.genome_lengths(bp, n_chrom) if n_chrom > 1 else [bp]
+        mine = partition.lpt_partition(lens, world)[rank]
+        seqs, quals = synth.make_pair(bp, n_chrom=n_chrom, only=mine, return_qual=True)
+        pair = 0
+    else:
+        # weak: sample pair `rank` of the cohort (pair 0 = the canonical seeds 42 / 572 / 126)
+        pair = rank
+        seqs, quals = synth.make_pair(bp, n_chrom=n_chrom, sample_seed=572 + 1000 * pair, perturb_seed=126 + 1000 * pair,
+                                      return_qual=True)
+    return seqs, quals, desc, pair
+
+
+def n_variants(seqs):
+    return int(sum(s.baseline.n + s.calls.n for s in seqs))
+
+
+def summary_counts(seqs, results):
+    """TP-baseline / FN / TP-call / FP / skipped totals (the numbers summary.txt is made of)."""
+    from rtg_tools_b200 import capi
+    tot = np.zeros(6, np.int64)
+    for r in results:
+        b, c = r.baseline.status, r.calls.status
+        tot[0] += int(((b & capi.STATUS_GT_MATCH) != 0).sum())
+        tot[1] += int(((b & capi.STATUS_NO_MATCH) != 0).sum())
+        tot[2] += int(((c & capi.STATUS_GT_MATCH) != 0).sum())
+        tot[3] += int(((c & capi.STATUS_NO_MATCH) != 0).sum())
+        tot[4] += int(((b & capi.STATUS_SKIPPED) != 0).sum()) + int(((c & capi.STATUS_SKIPPED) != 0).sum())
+        tot[5] += sum(len(r.sync_points[0]) for _ in (0,))
+    return tot
+
+
+def run_reference(args, rank, world):
+    """The reference arm: the CPU implementation of the path (C++ restatement -- the Java reference cannot run here)
+    on all host cores, one worker per sequence as the reference's SimpleThreadPool does."""
+    if rank != 0:
+        return
+    from rtg_tools_b200 import capi
+    seqs, quals, desc, pair = build_workload(args.workload, 0, 1, "weak", args.total_bp)
+    oracle = capi.Library(os.path.join(ROOT, "oracle", "liboracle.so"), prefix="oracle_")
+    cores = os.cpu_count() or 1
+    threads = max(1, min(cores, len(seqs)))
+    cfg = capi.Config()
+    nv = n_variants(seqs)
+    for _ in range(args.warmup):
+        oracle.submit(cfg, seqs, threads=threads)
+    t0 = time.perf_counter()
+    regions = 0
+    for _ in range(args.steps):
+        res = oracle.submit(cfg, seqs, threads=threads)
+        regions = sum(len(r.sync_points[0]) for r in res)
+    dt = (time.perf_counter() - t0) / args.steps
+    v = nv / dt
+    out = {
+        "impl": "reference", "metric": "vcfeval variants evaluated/sec", "value": v, "unit": "variants/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": "%s: %s" % (args.workload, desc), "variants_per_step": nv, "sync_regions_per_step": regions},
+        "cpu_baseline": {"value": v, "unit": "variants/s", "cores": threads, "kind": "port",
+                         "sample": "the full workload per step (%d variants, %d sequences), %d worker threads of %d host cores" % (
+                             nv, len(seqs), threads, cores)},
+        "e2e": {"value": v, "unit": "variants/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "sync_regions_per_s": regions / dt,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--total-bp", type=float, default=None, help="override the genome size of the workload (testing)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roc", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from rtg_tools_b200 import capi, vcfeval
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    t_gen = time.perf_counter()
+    seqs, quals, desc, pair = build_workload(args.workload, rank, world, args.scaling, args.total_bp)
+    nv = n_variants(seqs)
+    log("[rank %d] workload %s: %d sequences, %d variants (generated in %.1fs)" % (rank, args.workload, len(seqs), nv,
+                                                                               time.perf_counter() - t_gen))
+    eng = vcfeval.Engine(local_rank)
+    cfg = capi.Config()
+
+    # ------------------------------------------------------------------ device-resident throughput (value)
+    job = eng.job(cfg, seqs)
+    for _ in range(max(args.warmup, 3)):
+        job.run()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    dev_ms = 0.0
+    launches = 0
+    search_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        job.run()
+        st = job.stats_ex()
+        dev_ms += st["execute_ms"]
+        launches += int(st["launches"])
+        search_ms += st["search_ms"]
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop()
+    results = job.fetch()
+    st = job.stats_ex()
+    regions = int(sum(len(r.sync_points[0]) for r in results))
+    job.close()
+
+    # ------------------------------------------------------------------ end to end through vce_submit (host buffers)
+    for _ in range(max(1, min(args.warmup, 3))):
+        eng.submit(cfg, seqs)
+    barrier()
+    t0 = time.perf_counter()
+    counts = None
+    for _ in range(args.steps):
+        res = eng.submit(cfg, seqs)
+        counts = summary_counts(seqs, res)
+        if world > 1:  # the summary merge: the only collective of the path
+            t = torch.from_numpy(counts).cuda()
+            dist.all_reduce(t)
+            counts = t.cpu().numpy()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+
+    # max over ranks / totals
+    def reduce_max(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_sum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    ms_per_step = reduce_max(dev_ms / args.steps)
+    wall_per_step = reduce_max(wall_ms / args.steps)
+    e2e_ms = reduce_max(e2e_ms)
+    total_variants = reduce_sum(nv)
+    total_regions = reduce_sum(regions)
+    total_launches = reduce_sum(launches)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ------------------------------------------------------------------ roofline of the dominant kernel
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    fast_ms = st["fast_kernel_ms"]
+    fast_var = st["fast_variants"]
+    achieved = (ALG_BYTES_PER_VARIANT * fast_var / (fast_ms * 1e-3) / 1e9) if fast_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("k_search_fast_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": "k_search<false> (shared-memory region search, K2+K3)", "variants_per_launch": fast_var,
+                "launch_ms": fast_ms, "algorithmic_bytes_per_variant": ALG_BYTES_PER_VARIANT, "peak_source": peak_src,
+                "search_share_of_step": (search_ms / args.steps) / (dev_ms / args.steps) if dev_ms > 0 else None}
+
+    # ------------------------------------------------------------------ CPU baseline (oracle, bounded sample)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        oracle = capi.Library(os.path.join(ROOT, "oracle", "liboracle.so"), prefix="oracle_")
+        cores = os.cpu_count() or 1
+        threads = max(1, min(cores, len(seqs)))
+        t0 = time.perf_counter()
+        want = oracle.submit(cfg, seqs, threads=threads)
+        dt = time.perf_counter() - t0
+        cpu = {"value": nv / dt, "unit": "variants/s", "cores": threads, "kind": "port",
+               "sample": "one pass over the full workload (%d variants, %d sequences) on %d worker threads of %d host cores, %.1f s" % (
+                   nv, len(seqs), threads, cores, dt)}
+        # the bench output is also a parity check at full size
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from compare import compare_results
+        compare_results(want, results, seqs, what="bench")
+        cpu["parity"] = "bit-exact vs oracle on all %d variants" % nv
+
+    # ------------------------------------------------------------------ ROC (K4) on the scored calls of the run, reported beside
+    roc = None
+    if not args.no_roc:
+        score = np.concatenate(quals) if quals else np.zeros(0)
+        wts = np.concatenate([r.calls.weight for r in results]) if results else np.zeros(0)
+        stc = np.concatenate([r.calls.status for r in results]) if results else np.zeros(0, np.uint8)
+        tp = np.where((stc & capi.STATUS_GT_MATCH) != 0, wts, 0.0)
+        raw = ((stc & capi.STATUS_GT_MATCH) != 0).astype(np.float64)
+        fp = ((stc & capi.STATUS_NO_MATCH) != 0).astype(np.float64)
+        eng.roc(score, tp, fp, raw, None, 1)
+        t0 = time.perf_counter()
+        rows, _ = eng.roc(score, tp, fp, raw, None, 1)
+        dt = time.perf_counter() - t0
+        roc = {"scored_calls": int(score.shape[0]), "rows": int(rows[0][0].shape[0]), "e2e_calls_per_s": score.shape[0] / dt}
+
+    value = total_variants / (ms_per_step * 1e-3)
+    out = {
+        "metric": "vcfeval variants evaluated/sec", "value": value, "unit": "variants/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": "%s: %s" % (args.workload, desc), "variants_per_step": int(total_variants),
+                   "sync_regions_per_step": int(total_regions), "sequences_per_rank": len(seqs),
+                   "l2": "inputs larger than L2 (per-variant arrays + reference windows > 126 MB)" if nv > 2_000_000 else "inputs smaller than L2 (small workload)",
+                   "sharding": "none (1 GPU)" if world == 1 else ("sample pair per rank" if args.scaling == "weak" else "LPT over chromosomes")},
+        "sync_regions_per_s": total_regions / (ms_per_step * 1e-3),
+        "wall_ms_per_step": wall_per_step,
+        "e2e": {"value": total_variants / (e2e_ms * 1e-3), "unit": "variants/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(st["h2d_bytes"]), "d2h_bytes_per_step": int(st["d2h_bytes"])},
+        "gpu_launches": int(total_launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "roc": roc,
+        "summary_counts": [int(x) for x in counts] if counts is not None else None,
+        "engine_stats": {k: st[k] for k in ("regions", "escalated", "spilled", "prefix_reruns", "iterations")},
+    }
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

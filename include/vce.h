@@ -217,7 +217,7 @@ int  vce_job_stats(const vce_job* job, int64_t* n_launches, double* device_ms, d
 
 /* Extended diagnostics of the last vce_job_run, out[0..n): launches, search-kernel ms, ms and region count of the largest
    shared-memory search launch, regions, escalated, spilled, prefix re-runs, H2D bytes, D2H bytes, best-first iterations,
-   device ms of the whole run (CUDA events on the job's stream). */
+   device ms of the whole run (CUDA events on the job's stream), variants searched by that largest launch. */
 int  vce_job_stats_ex(const vce_job* job, double* out, int32_t n);
 
 /* RocContainer accumulate + sort + cumulative scan on the device. */

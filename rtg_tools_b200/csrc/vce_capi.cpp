@@ -123,7 +123,7 @@ int vce_job_stats(const vce_job* job, int64_t* n_launches, double* device_ms, do
   if (search_kernel_ms) {
     double ms = 0;
     long long regs = 0;
-    vce::cudaBackendFastStats(job->backend.get(), &ms, &regs);
+    vce::cudaBackendFastStats(job->backend.get(), &ms, &regs, nullptr);
     *search_kernel_ms = ms;
   }
   return VCE_OK;
@@ -134,11 +134,12 @@ int vce_job_stats_ex(const vce_job* job, double* out, int32_t n) {
   const vce::SearchStats& s = job->backend->stats;
   double fastMs = 0;
   long long fastRegions = 0;
-  vce::cudaBackendFastStats(job->backend.get(), &fastMs, &fastRegions);
-  const double v[12] = {(double) s.launches, s.searchMs, fastMs, (double) fastRegions, (double) s.regions, (double) s.escalated,
+  long long fastVariants = 0;
+  vce::cudaBackendFastStats(job->backend.get(), &fastMs, &fastRegions, &fastVariants);
+  const double v[13] = {(double) s.launches, s.searchMs, fastMs, (double) fastRegions, (double) s.regions, (double) s.escalated,
                         (double) s.spilled, (double) s.prefixReruns, (double) s.h2dBytes, (double) s.d2hBytes,
-                        (double) s.iterations, job->executeMs};
-  for (int i = 0; i < n && i < 12; ++i) out[i] = v[i];
+                        (double) s.iterations, job->executeMs, (double) fastVariants};
+  for (int i = 0; i < n && i < 13; ++i) out[i] = v[i];
   return VCE_OK;
 }
 

@@ -496,7 +496,13 @@ class CudaBackend : public Backend {
     CUDA_TRY(cudaEventElapsedTime(&ms, ev0_, ev1_));
     stats.searchMs += ms;
     stats.d2hBytes += (int64_t) (nr * sizeof(RegionResult));
-    if (!general && (long long) nr >= lastFastRegions_) { lastFastMs_ = ms; lastFastRegions_ = (long long) nr; }
+    if (!general && (long long) nr >= lastFastRegions_) {
+      lastFastMs_ = ms;
+      lastFastRegions_ = (long long) nr;
+      long long nv = 0;
+      for (const RegionDesc& d : regs) nv += d.cCount + d.bCount;
+      lastFastVariants_ = nv;
+    }
     if (nWarn > 0) {
       nWarn = std::min(nWarn, warnCap);
       const size_t at = warns.size();
@@ -560,6 +566,7 @@ class CudaBackend : public Backend {
   int device() const { return device_; }
   double lastFastMs_ = 0;
   long long lastFastRegions_ = 0;
+  long long lastFastVariants_ = 0;
 
  private:
   int device_;
@@ -601,10 +608,11 @@ int cudaDeviceCount() {
   return n;
 }
 
-void cudaBackendFastStats(Backend* b, double* ms, long long* regions) {
+void cudaBackendFastStats(Backend* b, double* ms, long long* regions, long long* variants) {
   CudaBackend* c = static_cast<CudaBackend*>(b);
   *ms = c->lastFastMs_;
   *regions = c->lastFastRegions_;
+  if (variants) *variants = c->lastFastVariants_;
 }
 
 }  // namespace vce

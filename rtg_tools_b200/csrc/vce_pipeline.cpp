@@ -3,6 +3,8 @@
 
 #include <algorithm>
 #include <climits>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -427,6 +429,16 @@ int Pipeline::runPass(PassState& ps, bool staged) {
     pending.insert(pending.end(), redoGen.begin(), redoGen.end());
   }
   for (const Region& rg : ps.regions) if (rg.alive) be_->stats.iterations += rg.r.iterations;
+  if (const char* dump = std::getenv("VCE_DUMP_REGIONS")) {  // diagnostics: one line per settled region
+    if (FILE* f = std::fopen(dump, ps.pd.pass == 0 ? "w" : "a")) {
+      for (const Region& rg : ps.regions) {
+        if (!rg.alive) continue;
+        std::fprintf(f, "%d,%d,%d,%d,%d,%d,%d,%d\n", ps.pd.pass, rg.d.cCount, rg.d.bCount, rg.r.maxFrontier, rg.r.iterations,
+                     rg.r.nSync, rg.r.status, rg.general ? 1 : 0);
+      }
+      std::fclose(f);
+    }
+  }
   return VCE_OK;
 }
 

@@ -51,10 +51,10 @@ class Job:
         return self.results
 
     def stats_ex(self):
-        out = (C.c_double * 12)()
-        self.engine.lib.lib.vce_job_stats_ex(self.handle, out, 12)
+        out = (C.c_double * 13)()
+        self.engine.lib.lib.vce_job_stats_ex(self.handle, out, 13)
         keys = ["launches", "search_ms", "fast_kernel_ms", "fast_regions", "regions", "escalated", "spilled", "prefix_reruns",
-                "h2d_bytes", "d2h_bytes", "iterations", "execute_ms"]
+                "h2d_bytes", "d2h_bytes", "iterations", "execute_ms", "fast_variants"]
         return {k: out[i] for i, k in enumerate(keys)}
 
     def stats(self):
