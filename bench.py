@@ -9,7 +9,7 @@ batch of synthetic input.
           events on the engine's stream, max over ranks
   e2e   : the same metric through the reference-facing C-ABI call vce_submit() with HOST buffers: packing, H2D,
           kernels, D2H and result assembly all inside the timed region
-  roofline : the dominant kernel (shared-memory region search), 48 algorithmic bytes per variant
+  roofline : the dominant kernel (thread-per-region search), 48 algorithmic bytes per variant
   cpu_baseline : the CPU oracle (C++ restatement of the reference, "port": the reference is Java and the image
           has no JDK) on the host cores, one worker per sequence like the reference's SimpleThreadPool
 
@@ -294,18 +294,18 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    fast_ms = st["fast_kernel_ms"]
-    fast_var = st["fast_variants"]
+    fast_ms = st["micro_kernel_ms"]
+    fast_var = st["micro_variants"]
     achieved = (ALG_BYTES_PER_VARIANT * fast_var / (fast_ms * 1e-3) / 1e9) if fast_ms > 0 else 0.0
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("k_search_fast_dram_bytes_per_launch")
+            traffic = json.load(open(tpath)).get("k_micro_dram_bytes_per_launch")
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "k_search<false> (shared-memory region search, K2+K3)", "variants_per_launch": fast_var,
+                "kernel": "k_micro<MicroA> (thread-per-region search from region packets, K1+K2+K3)", "variants_per_launch": fast_var,
                 "launch_ms": fast_ms, "algorithmic_bytes_per_variant": ALG_BYTES_PER_VARIANT, "peak_source": peak_src,
                 "search_share_of_step": (search_ms / args.steps) / (dev_ms / args.steps) if dev_ms > 0 else None}
 

@@ -1,40 +1,79 @@
-// vce_capi.cpp -- the C-ABI of include/vce.h on top of the pipeline + CUDA backend.
+// vce_capi.cpp -- the C-ABI of include/vce.h on top of the engine + CUDA backend.
 //
 // There is NO CPU fallback: without a CUDA device every compute entry point fails with VCE_ERR_NO_DEVICE.
+//
+// Contexts (CUDA backend: streams, device arenas, page-locked staging + engine) are pooled and reused across calls,
+// so that a steady-state vce_submit() pays no allocation; concurrent callers each get their own context and share
+// the host worker pool.
 #include <cstdio>
 #include <cstring>
 #include <memory>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/vce.h"
 #include "vce_cuda.h"
-#include "vce_pipeline.h"
+#include "vce_engine.h"
 
 namespace {
 std::mutex g_mu;
 int g_device = -1;
 thread_local std::string t_err;
 
+struct Context {
+  std::unique_ptr<vce::Backend> backend;
+  std::unique_ptr<vce::Engine> engine;
+  int device = -1;
+};
+std::vector<std::unique_ptr<Context>> g_free;
+std::unique_ptr<vce::WorkerPool> g_pool;
+
 int fail(int code, const std::string& msg) {
   t_err = msg;
   return code;
 }
+
+Context* acquire(int& rc) {
+  int dev;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    dev = g_device;
+    if (dev < 0) { rc = fail(VCE_ERR_NOT_INITIALISED, "call vce_init first"); return nullptr; }
+    if (!g_pool) g_pool.reset(new vce::WorkerPool(vce::WorkerPool::defaultThreads()));
+    for (size_t i = 0; i < g_free.size(); ++i) {
+      if (g_free[i]->device == dev) {
+        Context* c = g_free[i].release();
+        g_free.erase(g_free.begin() + (long) i);
+        return c;
+      }
+    }
+  }
+  std::string err;
+  std::unique_ptr<vce::Backend> be(vce::createCudaBackend(dev, err));
+  if (!be) { rc = fail(VCE_ERR_CUDA, err); return nullptr; }
+  Context* c = new Context();
+  c->device = dev;
+  c->backend = std::move(be);
+  c->engine.reset(new vce::Engine(c->backend.get(), g_pool.get(), vce::EngineOptions()));
+  return c;
+}
+
+void release(Context* c) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_device < 0 || g_free.size() >= 4) { delete c; return; }
+  g_free.emplace_back(c);
+}
 }  // namespace
 
 struct vce_job {
-  std::unique_ptr<vce::Backend> backend;
-  std::unique_ptr<vce::Pipeline> pipeline;
-  vce_config cfg;
-  int32_t nSeq = 0;
-  const vce_sequence* seqs = nullptr;
-  bool prepared = false;
+  Context* ctx = nullptr;
   double executeMs = 0;
 };
 
 extern "C" {
 
-const char* vce_version(void) { return "rtg-tools_b200 vce 0.1.0 (sm_100a)"; }
+const char* vce_version(void) { return "rtg-tools_b200 vce 0.2.0 (sm_100a)"; }
 
 const char* vce_last_error(void) { return t_err.c_str(); }
 
@@ -63,59 +102,59 @@ int vce_init(int device) {
 
 void vce_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_mu);
+  g_free.clear();
   g_device = -1;
 }
 
 int vce_job_create(const vce_config* cfg, int32_t n_seq, const vce_sequence* seqs, vce_job** job) {
   if (!cfg || !job || n_seq < 0 || (n_seq > 0 && !seqs)) return fail(VCE_ERR_BAD_ARGUMENT, "null argument");
-  int dev;
-  {
-    std::lock_guard<std::mutex> lk(g_mu);
-    dev = g_device;
+  int rc = VCE_OK;
+  Context* c = acquire(rc);
+  if (!c) return rc;
+  c->backend->stats = vce::SearchStats();
+  rc = c->engine->prepare(*cfg, n_seq, seqs, true);
+  if (rc) {
+    const std::string msg = c->engine->error();
+    release(c);
+    return fail(rc, msg);
   }
-  if (dev < 0) return fail(VCE_ERR_NOT_INITIALISED, "call vce_init first");
-  std::string err;
-  std::unique_ptr<vce::Backend> be(vce::createCudaBackend(dev, err));
-  if (!be) return fail(VCE_ERR_CUDA, err);
-  std::unique_ptr<vce_job> j(new vce_job());
-  j->backend = std::move(be);
-  j->pipeline.reset(new vce::Pipeline(j->backend.get(), vce::PipelineOptions()));
-  j->cfg = *cfg;
-  j->nSeq = n_seq;
-  j->seqs = seqs;
-  const int rc = j->pipeline->prepare(*cfg, n_seq, seqs);
-  if (rc) return fail(rc, j->pipeline->error());
-  j->prepared = true;
-  *job = j.release();
+  vce_job* j = new vce_job();
+  j->ctx = c;
+  *job = j;
   return VCE_OK;
 }
 
 int vce_job_run(vce_job* job) {
-  if (!job || !job->prepared) return fail(VCE_ERR_BAD_ARGUMENT, "job not prepared");
+  if (!job || !job->ctx) return fail(VCE_ERR_BAD_ARGUMENT, "job not prepared");
   // inputs are resident on the device since vce_job_create; only the device pipeline runs here
-  const int64_t h2d = job->backend->stats.h2dBytes;
-  job->backend->stats = vce::SearchStats();
-  job->backend->stats.h2dBytes = h2d;
-  job->backend->timerStart();
-  const int rc = job->pipeline->execute();
-  job->executeMs = job->backend->timerStopMs();
-  if (rc) return fail(rc, job->pipeline->error());
+  vce::Backend* be = job->ctx->backend.get();
+  const int64_t h2d = be->stats.h2dBytes;
+  be->stats = vce::SearchStats();
+  be->stats.h2dBytes = h2d;
+  be->timerStart();
+  const int rc = job->ctx->engine->execute();
+  job->executeMs = be->timerStopMs();
+  if (rc) return fail(rc, job->ctx->engine->error());
   return VCE_OK;
 }
 
 int vce_job_fetch(vce_job* job, vce_sequence_result* results) {
-  if (!job || !results) return fail(VCE_ERR_BAD_ARGUMENT, "null argument");
-  const int rc = job->pipeline->finish(results);
+  if (!job || !job->ctx || !results) return fail(VCE_ERR_BAD_ARGUMENT, "null argument");
+  const int rc = job->ctx->engine->finish(results);
   if (rc) return fail(rc, "one or more sequences reported an error (see vce_sequence_result.error)");
   return VCE_OK;
 }
 
-void vce_job_destroy(vce_job* job) { delete job; }
+void vce_job_destroy(vce_job* job) {
+  if (!job) return;
+  if (job->ctx) release(job->ctx);
+  delete job;
+}
 
 int vce_job_stats(const vce_job* job, int64_t* n_launches, double* device_ms, double* search_kernel_ms, int64_t* n_regions,
                   int64_t* n_escalated) {
-  if (!job) return fail(VCE_ERR_BAD_ARGUMENT, "null job");
-  const vce::SearchStats& s = job->backend->stats;
+  if (!job || !job->ctx) return fail(VCE_ERR_BAD_ARGUMENT, "null job");
+  const vce::SearchStats& s = job->ctx->backend->stats;
   if (n_launches) *n_launches = s.launches;
   if (device_ms) *device_ms = s.searchMs;
   if (n_regions) *n_regions = s.regions;
@@ -123,40 +162,35 @@ int vce_job_stats(const vce_job* job, int64_t* n_launches, double* device_ms, do
   if (search_kernel_ms) {
     double ms = 0;
     long long regs = 0;
-    vce::cudaBackendFastStats(job->backend.get(), &ms, &regs, nullptr);
+    vce::cudaBackendMicroStats(job->ctx->backend.get(), &ms, &regs);
     *search_kernel_ms = ms;
   }
   return VCE_OK;
 }
 
 int vce_job_stats_ex(const vce_job* job, double* out, int32_t n) {
-  if (!job || !out) return fail(VCE_ERR_BAD_ARGUMENT, "null argument");
-  const vce::SearchStats& s = job->backend->stats;
-  double fastMs = 0;
-  long long fastRegions = 0;
-  long long fastVariants = 0;
-  vce::cudaBackendFastStats(job->backend.get(), &fastMs, &fastRegions, &fastVariants);
-  const double v[13] = {(double) s.launches, s.searchMs, fastMs, (double) fastRegions, (double) s.regions, (double) s.escalated,
+  if (!job || !job->ctx || !out) return fail(VCE_ERR_BAD_ARGUMENT, "null argument");
+  const vce::SearchStats& s = job->ctx->backend->stats;
+  double microMs = 0;
+  long long microRegions = 0;
+  vce::cudaBackendMicroStats(job->ctx->backend.get(), &microMs, &microRegions);
+  const double v[13] = {(double) s.launches, s.searchMs, microMs, (double) microRegions, (double) s.regions, (double) s.escalated,
                         (double) s.spilled, (double) s.prefixReruns, (double) s.h2dBytes, (double) s.d2hBytes,
-                        (double) s.iterations, job->executeMs, (double) fastVariants};
+                        (double) s.iterations, job->executeMs, (double) job->ctx->engine->microVariants};
   for (int i = 0; i < n && i < 13; ++i) out[i] = v[i];
   return VCE_OK;
 }
 
 int vce_submit(const vce_config* cfg, int32_t n_seq, const vce_sequence* seqs, vce_sequence_result* results) {
   if (!cfg || !results || n_seq < 0 || (n_seq > 0 && !seqs)) return fail(VCE_ERR_BAD_ARGUMENT, "null argument");
-  int dev;
-  {
-    std::lock_guard<std::mutex> lk(g_mu);
-    dev = g_device;
-  }
-  if (dev < 0) return fail(VCE_ERR_NOT_INITIALISED, "call vce_init first");
-  std::string err;
-  std::unique_ptr<vce::Backend> be(vce::createCudaBackend(dev, err));
-  if (!be) return fail(VCE_ERR_CUDA, err);
-  vce::Pipeline pl(be.get(), vce::PipelineOptions());
-  const int rc = pl.run(*cfg, n_seq, seqs, results);
-  if (rc) return fail(rc, pl.error().empty() ? std::string("one or more sequences reported an error") : pl.error());
+  int rc = VCE_OK;
+  Context* c = acquire(rc);
+  if (!c) return rc;
+  c->backend->stats = vce::SearchStats();
+  rc = c->engine->run(*cfg, n_seq, seqs, results);
+  const std::string msg = rc ? c->engine->error() : std::string();
+  release(c);
+  if (rc) return fail(rc, msg.empty() ? std::string("one or more sequences reported an error") : msg);
   return VCE_OK;
 }
 

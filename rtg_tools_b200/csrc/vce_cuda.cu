@@ -18,7 +18,10 @@
 #include <string>
 #include <vector>
 
+#include <mutex>
+
 #include "vce_cuda.h"
+#include "vce_micro.h"
 #include "vce_orient.h"
 #include "vce_search.h"
 
@@ -197,6 +200,77 @@ __global__ void __launch_bounds__(kFastWarps * 32) k_search(const __grid_constan
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ K1+K2+K3, one region per thread
+// Thread-per-region search (vce_micro.h).  Every lane owns a shared-memory slice; a lane that settles its region
+// takes the next one (grid-stride), so the warp keeps all lanes busy on "one search iteration" per loop trip while
+// the regions of its lanes are at different stages.
+struct MicroChunkDesc {
+  const uint8_t* packets;
+  const uint32_t* offsets;
+  uint8_t* results;
+  int n;
+  int first;   // global index of the chunk's first region within the launch
+};
+struct MicroParams {
+  MicroChunkDesc one;            // single-chunk launch
+  const MicroChunkDesc* table;   // multi-chunk launch (nullptr = use `one`)
+  int nChunks;
+  int total;
+  MicroConfig cfg;
+};
+constexpr int kMicroThreads = 64;
+
+template <class T>
+__global__ void __launch_bounds__(kMicroThreads) k_micro(const __grid_constant__ MicroParams p) {
+  extern __shared__ __align__(16) uint8_t msm[];
+  MicroSearch<T> ms;
+  ms.ws = msm + (size_t) threadIdx.x * T::WS_BYTES;
+  ms.cfg = p.cfg;
+  const int stride = gridDim.x * blockDim.x;
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  bool running = false;
+  int slot = -1;
+  uint8_t* resOut = nullptr;
+  while (true) {
+    __syncwarp();
+    if (!running && r < p.total) {
+      MicroChunkDesc c = p.one;
+      if (p.table != nullptr) {
+        int lo = 0, hi = p.nChunks - 1;  // last chunk whose first region is <= r
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (__ldg(&p.table[mid].first) <= r) lo = mid; else hi = mid - 1;
+        }
+        c = p.table[lo];
+      }
+      const int q = r - c.first;
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(c.packets) + __ldg(c.offsets + q);
+      uint32_t* dst = reinterpret_cast<uint32_t*>(ms.ws + T::OFF_PKT);
+      const uint32_t w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
+      const int nw = (int) (w2 >> 24);
+      dst[0] = w0; dst[1] = w1; dst[2] = w2;
+      for (int i = 3; i < nw; ++i) dst[i] = __ldg(src + i);
+      resOut = c.results + (size_t) q * T::RES_BYTES;
+      ms.begin();
+      running = true;
+    }
+    if (__all_sync(0xffffffffu, !running)) break;
+    if (running) {
+      const int st = ms.iterate(slot);
+      if (st != kMicroPending) {
+        uint32_t tmp[T::RES_BYTES / 4];
+        ms.writeResult(st, slot, reinterpret_cast<uint8_t*>(tmp));
+        uint32_t* o = reinterpret_cast<uint32_t*>(resOut);
+#pragma unroll
+        for (int i = 0; i < T::RES_BYTES / 4; ++i) o[i] = tmp[i];
+        running = false;
+        r += stride;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ backend
 #define CUDA_TRY(expr)                                                                       \
   do {                                                                                       \
@@ -261,6 +335,15 @@ class CudaBackend : public Backend {
     CUDA_TRY(cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_));
     maxSmemOptin_ = maxSmem;
     CUDA_TRY(cudaFuncSetAttribute(k_search<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+    CUDA_TRY(cudaFuncSetAttribute(k_micro<MicroA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMicroThreads * MicroA::WS_BYTES));
+    for (int i = 0; i < kMicroLanes; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&mStream_[i], cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&evM0_));
+    CUDA_TRY(cudaEventCreate(&evM1_));
+    {
+      int perSm = 0;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_micro<MicroA>, kMicroThreads, kMicroThreads * MicroA::WS_BYTES));
+      microBlocksPerSm_ = perSm < 1 ? 1 : perSm;
+    }
     ready_ = true;
     return VCE_OK;
   }
@@ -275,6 +358,13 @@ class CudaBackend : public Backend {
     cudaEventDestroy(ev1_);
     cudaEventDestroy(evT0_);
     cudaEventDestroy(evT1_);
+    cudaEventDestroy(evM0_);
+    cudaEventDestroy(evM1_);
+    for (cudaEvent_t e : mEvents_) cudaEventDestroy(e);
+    mEvents_.clear();
+    for (int i = 0; i < kMicroLanes; ++i) cudaStreamDestroy(mStream_[i]);
+    for (DevBlock& b : dBlocks_) cudaFree(b.p);
+    dBlocks_.clear();
     cudaStreamDestroy(stream_);
     ready_ = false;
   }
@@ -549,6 +639,140 @@ class CudaBackend : public Backend {
     return VCE_OK;
   }
 
+
+  // ---------------------------------------------------------------- thread-per-region path
+  void* hostAlloc(size_t bytes) override {
+    cudaSetDevice(device_);
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { err_ = "cudaHostAlloc failed"; return nullptr; }
+    return p;
+  }
+  void hostFree(void* p) override {
+    cudaSetDevice(device_);
+    cudaFreeHost(p);
+  }
+  int microReset() override {
+    std::lock_guard<std::mutex> lk(mMu_);
+    for (DevBlock& b : dBlocks_) b.used = 0;
+    mNextEvent_ = 0;
+    mNextLane_ = 0;
+    return VCE_OK;
+  }
+  void* devAlloc(size_t bytes) {  // caller holds mMu_
+    bytes = (bytes + 255) & ~(size_t) 255;
+    for (DevBlock& b : dBlocks_) {
+      if (b.cap - b.used >= bytes) {
+        void* p = b.p + b.used;
+        b.used += bytes;
+        return p;
+      }
+    }
+    const size_t cap = std::max(bytes, (size_t) 256 << 20);
+    void* p = nullptr;
+    if (cudaMalloc(&p, cap) != cudaSuccess) return nullptr;
+    dBlocks_.push_back(DevBlock{static_cast<uint8_t*>(p), cap, bytes});
+    return p;
+  }
+  int microUpload(MicroJob& j) override {
+    CUDA_TRY(cudaSetDevice(device_));
+    {
+      std::lock_guard<std::mutex> lk(mMu_);
+      j.dPackets = devAlloc(j.packetBytes + 16);
+      j.dOffsets = devAlloc((size_t) j.n * 4);
+      j.dResults = devAlloc((size_t) j.n * j.resBytes);
+      j.lane = mNextLane_;
+      mNextLane_ = (mNextLane_ + 1) % kMicroLanes;
+      if ((int) mEvents_.size() <= mNextEvent_) {
+        cudaEvent_t e;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { err_ = "cudaEventCreate failed"; return VCE_ERR_CUDA; }
+        mEvents_.push_back(e);
+      }
+      j.event = mNextEvent_++;
+      j.evHandle = mEvents_[j.event];
+      stats.h2dBytes += (int64_t) (j.packetBytes + (size_t) j.n * 4);
+    }
+    if (!j.dPackets || !j.dOffsets || !j.dResults) { err_ = "out of device memory for region packets"; return VCE_ERR_CUDA; }
+    cudaStream_t st = mStream_[j.lane];
+    CUDA_TRY(cudaMemcpyAsync(j.dPackets, j.packets, j.packetBytes, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(j.dOffsets, j.offsets, (size_t) j.n * 4, cudaMemcpyHostToDevice, st));
+    return VCE_OK;
+  }
+  int microGrid(int n) const {
+    const int need = (n + kMicroThreads - 1) / kMicroThreads;
+    return std::max(1, std::min(need, smCount_ * microBlocksPerSm_));
+  }
+  int microRun(MicroJob& j, const MicroConfig& mc) override {
+    CUDA_TRY(cudaSetDevice(device_));
+    cudaStream_t st = mStream_[j.lane];
+    MicroParams mp;
+    std::memset(&mp, 0, sizeof(mp));
+    mp.one = MicroChunkDesc{static_cast<const uint8_t*>(j.dPackets), static_cast<const uint32_t*>(j.dOffsets),
+                            static_cast<uint8_t*>(j.dResults), j.n, 0};
+    mp.table = nullptr;
+    mp.nChunks = 1;
+    mp.total = j.n;
+    mp.cfg = mc;
+    k_micro<MicroA><<<microGrid(j.n), kMicroThreads, kMicroThreads * MicroA::WS_BYTES, st>>>(mp);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(j.results, j.dResults, (size_t) j.n * j.resBytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(j.evHandle), st));
+    {
+      std::lock_guard<std::mutex> lk(mMu_);
+      ++stats.launches;
+      stats.d2hBytes += (int64_t) j.n * j.resBytes;
+    }
+    return VCE_OK;
+  }
+  int microRunAll(std::vector<MicroJob*>& jobs, const MicroConfig& mc) override {
+    CUDA_TRY(cudaSetDevice(device_));
+    if (jobs.empty()) return VCE_OK;
+    // every upload has to be complete before the one launch that reads them all
+    for (int i = 0; i < kMicroLanes; ++i) CUDA_TRY(cudaStreamSynchronize(mStream_[i]));
+    std::vector<MicroChunkDesc> table(jobs.size());
+    int total = 0;
+    for (size_t i = 0; i < jobs.size(); ++i) {
+      MicroJob& j = *jobs[i];
+      table[i] = MicroChunkDesc{static_cast<const uint8_t*>(j.dPackets), static_cast<const uint32_t*>(j.dOffsets),
+                                static_cast<uint8_t*>(j.dResults), j.n, total};
+      total += j.n;
+    }
+    CUDA_TRY(mTable_.ensure(table.size()));
+    cudaStream_t st = mStream_[0];
+    CUDA_TRY(cudaMemcpyAsync(mTable_.p, table.data(), table.size() * sizeof(MicroChunkDesc), cudaMemcpyHostToDevice, st));
+    MicroParams mp;
+    std::memset(&mp, 0, sizeof(mp));
+    mp.one = table[0];
+    mp.table = mTable_.p;
+    mp.nChunks = (int) table.size();
+    mp.total = total;
+    mp.cfg = mc;
+    CUDA_TRY(cudaEventRecord(evM0_, st));
+    k_micro<MicroA><<<microGrid(total), kMicroThreads, kMicroThreads * MicroA::WS_BYTES, st>>>(mp);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(evM1_, st));
+    for (MicroJob* j : jobs) {
+      CUDA_TRY(cudaMemcpyAsync(j->results, j->dResults, (size_t) j->n * j->resBytes, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(j->evHandle), st));
+      j->lane = 0;
+      stats.d2hBytes += (int64_t) j->n * j->resBytes;
+    }
+    ++stats.launches;
+    CUDA_TRY(cudaEventSynchronize(evM1_));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, evM0_, evM1_));
+    stats.searchMs += ms;
+    lastMicroMs_ = ms;
+    lastMicroRegions_ = total;
+    return VCE_OK;
+  }
+  int microWait(MicroJob& j) override {
+    CUDA_TRY(cudaSetDevice(device_));
+    CUDA_TRY(cudaEventSynchronize(static_cast<cudaEvent_t>(j.evHandle)));
+    return VCE_OK;
+  }
+  double lastMicroMs_ = 0;
+  long long lastMicroRegions_ = 0;
+
   const char* lastError() const override { return err_.c_str(); }
   void timerStart() override {
     cudaSetDevice(device_);
@@ -589,6 +813,17 @@ class CudaBackend : public Backend {
   DevBuf<int> ints_;
   DevBuf<int32_t> arena_;
   DevBuf<uint8_t> scanTmp_;
+  // thread-per-region path: device bump arena, copy/compute lanes, per-job events
+  struct DevBlock { uint8_t* p; size_t cap, used; };
+  static constexpr int kMicroLanes = 4;
+  std::mutex mMu_;
+  std::vector<DevBlock> dBlocks_;
+  cudaStream_t mStream_[kMicroLanes] = {nullptr, nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> mEvents_;
+  int mNextEvent_ = 0, mNextLane_ = 0;
+  cudaEvent_t evM0_ = nullptr, evM1_ = nullptr;
+  int microBlocksPerSm_ = 1;
+  DevBuf<MicroChunkDesc> mTable_;
   std::string err_;
 };
 
@@ -613,6 +848,12 @@ void cudaBackendFastStats(Backend* b, double* ms, long long* regions, long long*
   *ms = c->lastFastMs_;
   *regions = c->lastFastRegions_;
   if (variants) *variants = c->lastFastVariants_;
+}
+
+void cudaBackendMicroStats(Backend* b, double* ms, long long* regions) {
+  CudaBackend* c = static_cast<CudaBackend*>(b);
+  *ms = c->lastMicroMs_;
+  *regions = c->lastMicroRegions_;
 }
 
 }  // namespace vce

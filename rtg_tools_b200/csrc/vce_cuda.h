@@ -15,6 +15,9 @@ Backend* createCudaBackend(int device, std::string& err);
 // Device milliseconds and region count of the last shared-memory search launch (roofline reporting).
 void cudaBackendFastStats(Backend* b, double* ms, long long* regions, long long* variants);
 
+// Device milliseconds and region count of the last single-launch thread-per-region search (staged jobs).
+void cudaBackendMicroStats(Backend* b, double* ms, long long* regions);
+
 struct RocTiming { double h2dMs = 0, kernelMs = 0; int launches = 0; };
 int rocRun(int device, const vce_roc_in* in, vce_roc_out* out, std::string& err, RocTiming* timing);
 

@@ -1,0 +1,1242 @@
+// vce_engine.cpp -- see vce_engine.h
+#include "vce_engine.h"
+
+#include <algorithm>
+#include <atomic>
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "vce_orient.h"
+
+namespace vce {
+
+namespace {
+const int kDummyPrefix = 0;  // "some baseline variant was included earlier, allele id unknown": the common case
+
+// Upper bound on the number of orientations any variant of a pass can have (Orientor.java), used to size child
+// slots and decision fields before K1 has run.
+int orientBound(int kind, int H, int gtPloidy, int maxSlots) {
+  const int nA = std::max(1, maxSlots - 1);  // numAlleles()
+  static const int fact[5] = {1, 1, 2, 6, 24};
+  switch (kind) {
+    case VCE_ORIENT_UNPHASED:
+    case VCE_ORIENT_PHASED:
+    case VCE_ORIENT_PHASED_INVERT: return H == 2 ? 2 : fact[std::min(4, std::max(gtPloidy, H))];
+    case VCE_ORIENT_SQUASH_GT: return std::max(1, gtPloidy);
+    case VCE_ORIENT_ALLELE_GT: return 6;
+    case VCE_ORIENT_HAPLOID_POP: return std::max(1, nA - 1);
+    case VCE_ORIENT_DIPLOID_POP: return std::max(1, (nA - 1) * (2 * nA + 1));
+    case VCE_ORIENT_ALT: {
+      long b = nA - 1;
+      for (int h = 1; h < H; ++h) b *= (nA + 1);
+      b *= fact[std::min(4, H)];
+      return (int) std::min<long>(std::max<long>(1, b), 1 << 20);
+    }
+  }
+  return 1;
+}
+
+struct RowPick {  // selects one orientation row of a variant (host side of K1, for the output arrays)
+  int want, at = 0;
+  int8_t ids[4] = {-2, -2, -2, -2};
+  bool original = false;
+  void operator()(const int* p, int n, bool orig) {
+    if (at == want) {
+      for (int h = 0; h < 4; ++h) ids[h] = h < n ? (int8_t) p[h] : (int8_t) -2;
+      original = orig;
+    }
+    ++at;
+  }
+};
+}  // namespace
+
+Engine::Engine(Backend* b, WorkerPool* pool, const EngineOptions& o) : be_(b), pool_(pool), opt_(o) {
+  scratch_.resize(pool_->threads());
+  scratchOff_.resize(pool_->threads());
+}
+
+Engine::~Engine() {
+  for (HostBlock& hb : arena_) be_->hostFree(hb.p);
+}
+
+uint8_t* Engine::arenaAlloc(size_t bytes) {
+  bytes = (bytes + 63) & ~(size_t) 63;
+  std::lock_guard<std::mutex> lk(arenaMu_);
+  for (HostBlock& hb : arena_) {
+    if (hb.cap - hb.used >= bytes) {
+      uint8_t* p = hb.p + hb.used;
+      hb.used += bytes;
+      return p;
+    }
+  }
+  const size_t cap = std::max(bytes, (size_t) 64 << 20);
+  uint8_t* p = static_cast<uint8_t*>(be_->hostAlloc(cap));
+  if (!p) return nullptr;
+  arena_.push_back(HostBlock{p, cap, bytes});
+  return p;
+}
+
+void Engine::arenaReset() {
+  std::lock_guard<std::mutex> lk(arenaMu_);
+  for (HostBlock& hb : arena_) hb.used = 0;
+}
+
+// ------------------------------------------------------------------------------------------- pass set-up
+int Engine::setupPass0() {
+  PassCtx& pc = pass_[0];
+  pc = PassCtx();
+  pc.pass = 0;
+  pc.H = cfg_.ploidy[0];
+  pc.kind[0] = cfg_.calls_orientor[0];
+  pc.kind[1] = cfg_.baseline_orientor[0];
+  pc.shortCircuit.assign(nSeq_, 0);
+  for (int side = 0; side < 2; ++side) {
+    pc.ss[side].resize(nSeq_);
+    pc.idxStore[side].resize(nSeq_);
+  }
+  int32_t tot[2] = {0, 0};
+  for (int k = 0; k < nSeq_; ++k) {
+    const bool sc = seqs_[k].baseline.n == 0 || seqs_[k].calls.n == 0;  // SequenceEvaluator.java:94-97
+    pc.shortCircuit[k] = sc ? 1 : 0;
+    for (int side = 0; side < 2; ++side) {
+      const vce_variants& v = side == 0 ? seqs_[k].calls : seqs_[k].baseline;
+      if (v.n > 0) pc.gtPloidy[side] = std::max(pc.gtPloidy[side], (int) v.gt_ploidy);
+      SideSeq& s = pc.ss[side][k];
+      s.in = &v;
+      s.first = tot[side];
+      s.n = sc ? 0 : v.n;
+      s.idx = nullptr;
+      tot[side] += s.n;
+    }
+  }
+  for (int side = 0; side < 2; ++side) {
+    pc.vStart[side].resize(tot[side]);
+    pc.vEnd[side].resize(tot[side]);
+    pc.decision[side].assign(tot[side], 0);
+  }
+  pc.weight.assign(tot[0], 0.0);
+  computeBounds(pc);
+  return VCE_OK;
+}
+
+// Allele.getAlleleBounds (Allele.java:195-206) for every variant, and the stable (start, end) order PathFinder
+// establishes (PathFinder.java:122-126) when the input is not already in that order.
+void Engine::computeBounds(PassCtx& pc) {
+  struct Task { int side, seq, lo, hi; };
+  std::vector<Task> tasks;
+  const int block = 1 << 16;
+  for (int side = 0; side < 2; ++side)
+    for (int k = 0; k < nSeq_; ++k)
+      for (int lo = 0; lo < pc.ss[side][k].n; lo += block) tasks.push_back(Task{side, k, lo, std::min(pc.ss[side][k].n, lo + block)});
+  std::vector<std::atomic<int>> unsorted(2 * (size_t) std::max(1, nSeq_));
+  for (auto& u : unsorted) u.store(0);
+  pool_->parallelFor((int) tasks.size(), [&](int t, int) {
+    const Task& tk = tasks[t];
+    const SideSeq& s = pc.ss[tk.side][tk.seq];
+    const vce_variants& v = *s.in;
+    int32_t* vs = pc.vStart[tk.side].data() + s.first;
+    int32_t* ve = pc.vEnd[tk.side].data() + s.first;
+    auto bounds = [&](int i, int& st, int& en) {
+      int a = INT_MAX, b = INT_MIN;
+      for (int q = v.allele_off[i]; q < v.allele_off[i + 1]; ++q) {
+        if (!v.allele_null[q]) {
+          a = std::min(a, v.allele_start[q]);
+          b = std::max(b, v.allele_end[q]);
+        }
+      }
+      st = a;
+      en = b;
+    };
+    int ps = INT_MIN, pe = INT_MIN;
+    if (tk.lo > 0) bounds(tk.lo - 1, ps, pe);
+    bool bad = false;
+    for (int i = tk.lo; i < tk.hi; ++i) {
+      int st, en;
+      bounds(i, st, en);
+      vs[i] = st;
+      ve[i] = en;
+      if (st < ps || (st == ps && en < pe)) bad = true;
+      ps = st;
+      pe = en;
+    }
+    if (bad) unsorted[(size_t) tk.side * nSeq_ + tk.seq].store(1);
+  });
+  for (int side = 0; side < 2; ++side) {
+    for (int k = 0; k < nSeq_; ++k) {
+      if (!unsorted[(size_t) side * nSeq_ + k].load()) continue;
+      SideSeq& s = pc.ss[side][k];
+      std::vector<int32_t>& order = pc.idxStore[side][k];
+      order.resize(s.n);
+      for (int i = 0; i < s.n; ++i) order[i] = i;
+      int32_t* vs = pc.vStart[side].data() + s.first;
+      int32_t* ve = pc.vEnd[side].data() + s.first;
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        if (vs[a] != vs[b]) return vs[a] < vs[b];
+        return ve[a] < ve[b];
+      });
+      std::vector<int32_t> ts(s.n), te(s.n);
+      for (int i = 0; i < s.n; ++i) { ts[i] = vs[order[i]]; te[i] = ve[order[i]]; }
+      std::copy(ts.begin(), ts.end(), vs);
+      std::copy(te.begin(), te.end(), ve);
+      s.idx = order.data();
+    }
+  }
+}
+
+int Engine::setupPass1() {
+  const PassCtx& p0 = pass_[0];
+  PassCtx& pc = pass_[1];
+  pc = PassCtx();
+  pc.pass = 1;
+  pc.H = cfg_.ploidy[1];
+  pc.kind[0] = cfg_.calls_orientor[1];
+  pc.kind[1] = cfg_.baseline_orientor[1];
+  pc.shortCircuit = p0.shortCircuit;
+  pc.gtPloidy[0] = p0.gtPloidy[0];
+  pc.gtPloidy[1] = p0.gtPloidy[1];
+  for (int side = 0; side < 2; ++side) {
+    pc.ss[side].resize(nSeq_);
+    pc.idxStore[side].resize(nSeq_);
+    // Path.getCalledExcluded / getBaselineExcluded of the first pass, per sequence
+    pool_->parallelFor(nSeq_, [&](int k, int) {
+      const SideSeq& a = p0.ss[side][k];
+      std::vector<int32_t>& ix = pc.idxStore[side][k];
+      ix.clear();
+      const uint8_t* dec = p0.decision[side].data() + a.first;
+      for (int i = 0; i < a.n; ++i) if (dec[i] == 1) ix.push_back(i);  // position in pass 0 for now
+    });
+    int32_t tot = 0;
+    for (int k = 0; k < nSeq_; ++k) {
+      SideSeq& s = pc.ss[side][k];
+      s.in = p0.ss[side][k].in;
+      s.first = tot;
+      s.n = (int32_t) pc.idxStore[side][k].size();
+      tot += s.n;
+    }
+    pc.vStart[side].resize(tot);
+    pc.vEnd[side].resize(tot);
+    pc.decision[side].assign(tot, 0);
+    if (side == 0) pc.weight.assign(tot, 0.0);
+    pool_->parallelFor(nSeq_, [&](int k, int) {
+      const SideSeq& a = p0.ss[side][k];
+      SideSeq& s = pc.ss[side][k];
+      std::vector<int32_t>& ix = pc.idxStore[side][k];
+      const int32_t* as = p0.vStart[side].data() + a.first;
+      const int32_t* ae = p0.vEnd[side].data() + a.first;
+      int32_t* vs = pc.vStart[side].data() + s.first;
+      int32_t* ve = pc.vEnd[side].data() + s.first;
+      for (int i = 0; i < s.n; ++i) {
+        const int p = ix[i];
+        vs[i] = as[p];
+        ve[i] = ae[p];
+        ix[i] = a.idx ? a.idx[p] : p;  // now the input index
+      }
+      s.idx = ix.data();
+    });
+  }
+  return VCE_OK;
+}
+
+// ------------------------------------------------------------------------------------------- regions
+void Engine::splitSequence(PassCtx& pc, int k) {
+  std::vector<RegRange>& out = pc.rr[k];
+  out.clear();
+  if (pc.shortCircuit[k]) return;
+  const SideSeq& C = pc.ss[0][k];
+  const SideSeq& B = pc.ss[1][k];
+  const int32_t* cs = pc.vStart[0].data();
+  const int32_t* ce = pc.vEnd[0].data();
+  const int32_t* bs = pc.vStart[1].data();
+  const int32_t* bee = pc.vEnd[1].data();
+  int i = C.first, j = B.first;
+  const int ie = C.first + C.n, je = B.first + B.n;
+  const long gap = std::max(1, opt_.gap);
+  out.reserve((size_t) std::max(C.n, B.n) + 16);
+  do {
+    RegRange g{i, 0, j, 0};
+    long maxEnd = LONG_MIN;
+    while (i < ie || j < je) {
+      const bool takeC = j >= je || (i < ie && cs[i] <= bs[j]);
+      const int s = takeC ? cs[i] : bs[j];
+      const int e = takeC ? ce[i] : bee[j];
+      if (maxEnd != LONG_MIN && (long) s >= maxEnd + gap) break;
+      maxEnd = std::max(maxEnd, (long) e);
+      if (takeC) ++i; else ++j;
+    }
+    g.cCount = i - g.cFirst;
+    g.bCount = j - g.bFirst;
+    out.push_back(g);
+  } while (i < ie || j < je);
+}
+
+int Engine::regionStartPos(const PassCtx& pc, int k, int j) const {
+  if (j == 0) return -1;
+  const RegRange& g = pc.rr[k][j];
+  int first = INT_MAX;
+  for (int v = g.cFirst; v < g.cFirst + g.cCount; ++v) first = std::min(first, pc.vStart[0][v]);
+  for (int v = g.bFirst; v < g.bFirst + g.bCount; ++v) first = std::min(first, pc.vStart[1][v]);
+  return first - 1;
+}
+
+bool Engine::fastEligible(const PassCtx& pc, const RegRange& g) const {
+  if (opt_.forceGeneral) return false;
+  if (pc.H > 2) return false;
+  if (g.cCount > FastLimits::kMaxVarPerSide || g.bCount > FastLimits::kMaxVarPerSide) return false;
+  return true;
+}
+
+void Engine::planChunks(PassCtx& pc) {
+  pc.chunks.clear();
+  size_t total = 0;
+  for (int k = 0; k < nSeq_; ++k) total += pc.rr[k].size();
+  int per = opt_.chunkRegions;
+  if (per <= 0) {
+    per = (int) (total / ((size_t) pool_->threads() * 6 + 1));
+    per = std::max(8192, std::min(131072, per));
+  }
+  for (int k = 0; k < nSeq_; ++k) {
+    const int n = (int) pc.rr[k].size();
+    for (int r0 = 0; r0 < n; r0 += per) {
+      Chunk ch;
+      ch.seq = k;
+      ch.r0 = r0;
+      ch.r1 = std::min(n, r0 + per);
+      pc.chunks.push_back(std::move(ch));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- packets
+// Writes the packet of region (k, j) in the layout of vce_micro.h; returns its length in bytes (a multiple of 4) or
+// 0 when the region does not fit the thread-per-region kernel.
+template <class T>
+int Engine::buildPacket(const PassCtx& pc, int k, int j, uint8_t* out) const {
+  if (j == 0) return 0;  // the first path of a sequence starts at -1 and is not in sync (HalfPath.java:50-57)
+  const RegRange& g = pc.rr[k][j];
+  if (g.cCount > T::KV || g.bCount > T::KV) return 0;
+  const SideSeq* SS[2] = {&pc.ss[0][k], &pc.ss[1][k]};
+  const int first[2] = {g.cFirst, g.bFirst};
+  const int count[2] = {g.cCount, g.bCount};
+  int nextStart[2];
+  for (int side = 0; side < 2; ++side) {
+    const int e = first[side] + count[side];
+    nextStart[side] = e < SS[side]->first + SS[side]->n ? pc.vStart[side][e] : kNoNext;
+  }
+  if (nextStart[0] == kNoNext && nextStart[1] == kNoNext) return 0;  // the last region finishes at the template end
+  int firstStart = INT_MAX;
+  long maxEnd = LONG_MIN;
+  for (int side = 0; side < 2; ++side) {
+    for (int v = first[side]; v < first[side] + count[side]; ++v) {
+      firstStart = std::min(firstStart, pc.vStart[side][v]);
+      maxEnd = std::max(maxEnd, (long) pc.vEnd[side][v]);
+    }
+  }
+  if (firstStart == INT_MAX || firstStart < 1 || maxEnd < firstStart) return 0;
+  const int winStart = firstStart - 1;
+  const int tl = seqs_[k].template_len;
+  const long winEnd = std::min<long>(maxEnd + opt_.microMargin, tl);
+  const long winLen = winEnd - winStart;
+  if (winLen < 1 || winLen > kMicroMaxWin) return 0;
+
+  uint8_t bits[64];
+  std::memset(bits, 0, sizeof(bits));
+  int nBases = 0;
+  uint8_t alleles[4 * T::KV * MA_BYTES];
+  int nAl = 0;
+  uint8_t* vout = out + MP_VARS;
+  for (int side = 0; side < 2; ++side) {
+    const SideSeq& s = *SS[side];
+    const vce_variants& in = *s.in;
+    const int P = in.gt_ploidy;
+    if (P != pc.gtPloidy[side]) return 0;
+    if (pc.H == 2 ? P != 2 : (P < 1 || P > 2)) return 0;
+    for (int v = first[side]; v < first[side] + count[side]; ++v) {
+      const int li = v - s.first;
+      const int ii = s.idx ? s.idx[li] : li;
+      const int off0 = in.allele_off[ii];
+      const int nSl = in.allele_off[ii + 1] - off0;
+      const int gt[2] = {in.gt[(size_t) ii * P], P > 1 ? in.gt[(size_t) ii * P + 1] : in.gt[(size_t) ii * P]};
+      int al[2] = {kMicroNoAllele, kMicroNoAllele};
+      for (int h = 0; h < 2; ++h) {
+        if (h == 1 && gt[1] == gt[0]) { al[1] = al[0]; break; }
+        const int id = gt[h];
+        if (id < -1 || id + 1 >= nSl) continue;
+        const int slot = off0 + id + 1;
+        if (in.allele_null[slot]) continue;
+        const long st = (long) in.allele_start[slot] - winStart, en = (long) in.allele_end[slot] - winStart;
+        const int nb = in.allele_nt_off[slot];
+        const int len = in.allele_nt_off[slot + 1] - nb;
+        if (st < 0 || en < st || en > kMicroMaxWin || len > kMicroMaxWin || nBases + len + winLen > 255) return 0;
+        const uint8_t* nt = in.nt + nb;
+        for (int q = 0; q < len; ++q) {
+          const unsigned b = (unsigned) nt[q] - 1u;
+          if (b > 3u) return 0;  // N or the explicit-unknown token: not representable in 2 bits
+          bits[(nBases + q) >> 2] |= (uint8_t) (b << (((nBases + q) & 3) * 2));
+        }
+        uint8_t* a = alleles + nAl * MA_BYTES;
+        a[MA_START] = (uint8_t) st; a[MA_END] = (uint8_t) en; a[MA_NT] = (uint8_t) nBases; a[MA_LEN] = (uint8_t) len;
+        nBases += len;
+        al[h] = nAl++;
+      }
+      const long vs = (long) pc.vStart[side][v] - winStart, ve = (long) pc.vEnd[side][v] - winStart;
+      if (vs < 1 || ve < vs || ve > kMicroMaxWin) return 0;
+      uint8_t f = (uint8_t) ((in.phased && in.phased[ii]) ? 1 : 0);
+      f |= (uint8_t) (P << 1);
+      if (in.status_in) f |= in.status_in[ii] & VCE_STATUS_OUTSIDE_EVAL;
+      vout[MV_START] = (uint8_t) vs; vout[MV_END] = (uint8_t) ve; vout[MV_FLAGS] = f;
+      vout[MV_GT0] = (uint8_t) (int8_t) gt[0]; vout[MV_GT1] = (uint8_t) (int8_t) gt[1];
+      vout[MV_A0] = (uint8_t) al[0]; vout[MV_A1] = (uint8_t) al[1]; vout[7] = 0;
+      vout += MV_BYTES;
+    }
+  }
+  const uint8_t* tb = seqs_[k].template_bases + winStart;
+  for (int q = 0; q < (int) winLen; ++q) {
+    const unsigned b = (unsigned) tb[q] - 1u;
+    if (b > 3u) return 0;
+    bits[(nBases + q) >> 2] |= (uint8_t) (b << (((nBases + q) & 3) * 2));
+  }
+  const int winBase = nBases;
+  nBases += (int) winLen;
+  std::memcpy(vout, alleles, (size_t) nAl * MA_BYTES);
+  uint8_t* bout = vout + nAl * MA_BYTES;
+  const int nb2 = (nBases + 3) >> 2;
+  std::memcpy(bout, bits, (size_t) nb2);
+  int bytes = (int) (bout + nb2 - out);
+  while (bytes & 3) out[bytes++] = 0;
+  if (bytes > T::PKT_MAX) return 0;
+  const int32_t ws32 = winStart;
+  std::memcpy(out + MP_WINSTART, &ws32, 4);
+  out[MP_COUNTS] = (uint8_t) (g.cCount | (g.bCount << 4));
+  out[MP_WINLEN] = (uint8_t) winLen;
+  for (int side = 0; side < 2; ++side) {
+    int rel = kMicroNoNext;
+    if (nextStart[side] != kNoNext) rel = (int) std::min<long>((long) nextStart[side] - winStart, kMicroFar);
+    out[side == 0 ? MP_CNEXT : MP_BNEXT] = (uint8_t) rel;
+  }
+  out[MP_TMPLLEN] = (uint8_t) std::min<long>((long) tl - winStart, kMicroFar + 2);
+  out[MP_NALLELES] = (uint8_t) nAl;
+  out[MP_WINBASE] = (uint8_t) winBase;
+  out[MP_NWORDS] = (uint8_t) (bytes / 4);
+  return bytes;
+}
+
+int Engine::buildChunk(PassCtx& pc, Chunk& ch, int worker, bool launch) {
+  const int k = ch.seq;
+  std::vector<uint8_t>& sc = scratch_[worker];
+  std::vector<uint32_t>& so = scratchOff_[worker];
+  const int nr = ch.r1 - ch.r0;
+  sc.resize((size_t) nr * MicroA::PKT_MAX + 16);
+  so.resize(nr);
+  ch.pktRegion.clear();
+  ch.pktRegion.reserve(nr);
+  ch.variants = 0;
+  size_t at = 0;
+  uint8_t* cls = pc.rcls[k].data();
+  RegRes* rs = pc.rs[k].data();
+  int np = 0;
+  for (int j = ch.r0; j < ch.r1; ++j) {
+    int bytes = 0;
+    if (pc.microOk) bytes = buildPacket<MicroA>(pc, k, j, sc.data() + at);
+    if (bytes > 0) {
+      so[np++] = (uint32_t) (at >> 2);
+      ch.pktRegion.push_back(j);
+      at += (size_t) bytes;
+      cls[j] = 1;
+      rs[j].state = RS_PENDING;
+      ch.variants += pc.rr[k][j].cCount + pc.rr[k][j].bCount;
+    } else {
+      cls[j] = 0;
+      rs[j].state = RS_RESIDUAL;
+    }
+  }
+  MicroJob& job = ch.job;
+  job = MicroJob();
+  job.cls = 0;
+  job.n = np;
+  job.resBytes = MicroA::RES_BYTES;
+  if (np == 0) return VCE_OK;
+  uint8_t* pk = arenaAlloc(at + 16);
+  uint8_t* off = arenaAlloc((size_t) np * 4);
+  uint8_t* res = arenaAlloc((size_t) np * MicroA::RES_BYTES);
+  if (!pk || !off || !res) {
+    std::lock_guard<std::mutex> lk(errMu_);
+    err_ = "out of page-locked host memory";
+    return VCE_ERR_CUDA;
+  }
+  std::memcpy(pk, sc.data(), at);
+  std::memcpy(off, so.data(), (size_t) np * 4);
+  job.packets = pk;
+  job.packetBytes = at;
+  job.offsets = reinterpret_cast<const uint32_t*>(off);
+  job.results = res;
+  int rc = be_->microUpload(job);
+  if (rc == VCE_OK && launch) rc = be_->microRun(job, pc.mc);
+  if (rc) {
+    std::lock_guard<std::mutex> lk(errMu_);
+    err_ = be_->lastError();
+  }
+  return rc;
+}
+
+void Engine::decodeChunk(PassCtx& pc, Chunk& ch, int64_t& iterations) {
+  typedef MicroA T;
+  const int k = ch.seq;
+  const MicroJob& job = ch.job;
+  RegRes* rs = pc.rs[k].data();
+  const RegRange* rr = pc.rr[k].data();
+  uint8_t* dc = pc.decision[0].data();
+  uint8_t* db = pc.decision[1].data();
+  double* wt = pc.weight.data();
+  int64_t it = 0;
+  for (int q = 0; q < job.n; ++q) {
+    const uint8_t* rec = job.results + (size_t) q * T::RES_BYTES;
+    const int j = ch.pktRegion[q];
+    RegRes& s = rs[j];
+    it += rec[MR_ITERS] | (rec[MR_ITERS + 1] << 8);
+    if (rec[MR_STATUS] != kMicroClean) { s.state = RS_RESIDUAL; continue; }
+    const RegRange& g = rr[j];
+    s.state = RS_MICRO_DONE;
+    s.flags = rec[MR_FLAGS] & 1;
+    s.lastId = (int8_t) rec[MR_LASTID];
+    s.nSync = rec[MR_NSYNC];
+    for (int i = 0; i < T::SMAX; ++i) s.rel[i] = rec[MR_SYNC + i];
+    const uint8_t* dec = rec + MR_SYNC + T::SMAX;
+    const uint8_t* wn = dec + 2 * T::KV;
+    const uint8_t* wd = wn + T::KV;
+    for (int i = 0; i < g.cCount; ++i) {
+      dc[g.cFirst + i] = dec[i];
+      wt[g.cFirst + i] = dec[i] >= 2 ? (double) wn[i] / (double) wd[i] : 0.0;  // Path.java:450
+    }
+    for (int i = 0; i < g.bCount; ++i) db[g.bFirst + i] = dec[T::KV + i];
+  }
+  iterations += it;
+}
+
+// ------------------------------------------------------------------------------------------- life cycle
+int Engine::prepare(const vce_config& cfg, int32_t nSeq, const vce_sequence* seqs, bool staged) {
+  staged_ = false;
+  cfg_ = cfg;
+  nSeq_ = nSeq;
+  seqs_ = seqs;
+  err_.clear();
+  executed_ = false;
+  if (cfg.n_passes < 1 || cfg.n_passes > 2) { err_ = "n_passes must be 1 or 2"; return VCE_ERR_BAD_ARGUMENT; }
+  if (cfg.flag_alternates) { err_ = "flag_alternates is not supported"; return VCE_ERR_UNSUPPORTED; }
+  for (int p = 0; p < cfg.n_passes; ++p) {
+    if (cfg.ploidy[p] < 1 || cfg.ploidy[p] > VCE_MAX_PLOIDY) { err_ = "ploidy out of range"; return VCE_ERR_BAD_ARGUMENT; }
+  }
+  arenaReset();
+  int rc = be_->microReset();
+  if (rc) { err_ = be_->lastError(); return rc; }
+  if ((rc = setupPass0())) return rc;
+  if (staged) {  // digest + upload now, so that execute() starts with everything resident in HBM
+    PassCtx& pc = pass_[0];
+    if ((rc = runChunks(pc))) return rc;
+    std::atomic<int> failed(0);
+    pool_->parallelFor((int) pc.chunks.size(), [&](int t, int worker) {
+      if (failed.load()) return;
+      const int r = buildChunk(pc, pc.chunks[t], worker, false);
+      if (r) failed.store(r);
+    });
+    if (failed.load()) return failed.load();
+    staged_ = true;
+  }
+  return VCE_OK;
+}
+
+// Splits the pass into regions, builds + uploads (+ starts, when `launch`) every chunk.
+static inline bool orientorPairMicro(int kc, int kb, int H) { return microOrientorSupported(kc, H) && microOrientorSupported(kb, H); }
+
+void Engine::resetPassRun(PassCtx& pc) {
+  for (size_t i = pc.undo.size(); i-- > 0;) pc.rr[pc.undo[i].first.seq][pc.undo[i].first.j] = pc.undo[i].second;
+  pc.undo.clear();
+  pc.rare.clear();
+  pc.warns.clear();
+  pc.wideSync.clear();
+  pool_->parallelFor(nSeq_, [&](int k, int) {
+    RegRes* rs = pc.rs[k].data();
+    const uint8_t* cls = pc.rcls[k].data();
+    const size_t n = pc.rs[k].size();
+    for (size_t j = 0; j < n; ++j) {
+      std::memset(&rs[j], 0, sizeof(RegRes));
+      rs[j].state = cls[j] ? RS_PENDING : RS_RESIDUAL;
+    }
+  });
+}
+
+int Engine::runChunks(PassCtx& pc) {
+  // split (per sequence), plan, build + upload + start
+  pc.rr.assign(nSeq_, std::vector<RegRange>());
+  pc.rs.assign(nSeq_, std::vector<RegRes>());
+  pc.rcls.assign(nSeq_, std::vector<uint8_t>());
+  pc.microOk = !opt_.disableMicro && !opt_.forceGeneral && orientorPairMicro(pc.kind[0], pc.kind[1], pc.H);
+  pc.mc.H = pc.H;
+  pc.mc.kind[0] = pc.kind[0];
+  pc.mc.kind[1] = pc.kind[1];
+  pc.mc.maxPaths = cfg_.max_paths;
+  pc.mc.maxIterations = cfg_.max_iterations;
+  pc.mc.pruneNoOps = cfg_.prune_no_ops;
+  pc.mc.preference = cfg_.preference;
+  // largest sequences first
+  std::vector<int> order(nSeq_);
+  for (int k = 0; k < nSeq_; ++k) order[k] = k;
+  std::sort(order.begin(), order.end(), [&](int a, int b) {
+    const int na = pc.ss[0][a].n + pc.ss[1][a].n, nb = pc.ss[0][b].n + pc.ss[1][b].n;
+    return na != nb ? na > nb : a < b;
+  });
+  pool_->parallelFor(nSeq_, [&](int t, int) {
+    const int k = order[t];
+    splitSequence(pc, k);
+    pc.rs[k].resize(pc.rr[k].size());
+    pc.rcls[k].assign(pc.rr[k].size(), 0);
+    if (!pc.rs[k].empty()) std::memset(pc.rs[k].data(), 0, pc.rs[k].size() * sizeof(RegRes));
+  });
+  planChunks(pc);
+  return VCE_OK;
+}
+
+int Engine::execute() {
+  int rc;
+  microMs = 0;
+  microRegions = microVariants = 0;
+  for (int p = 0; p < cfg_.n_passes; ++p) {
+    PassCtx& pc = pass_[p];
+    const bool rerun = p == 0 && staged_;
+    if (p == 1) {
+      if ((rc = setupPass1())) return rc;
+    }
+    std::atomic<int> failed(0);
+    if (!rerun) {
+      if ((rc = runChunks(pc))) return rc;
+      pool_->parallelFor((int) pc.chunks.size(), [&](int t, int worker) {
+        if (failed.load()) return;
+        const int r = buildChunk(pc, pc.chunks[t], worker, true);
+        if (r) failed.store(r);
+      });
+    } else {
+      if (executed_) resetPassRun(pc);
+      std::vector<MicroJob*> jobs;
+      for (Chunk& ch : pc.chunks) if (ch.job.n > 0) jobs.push_back(&ch.job);
+      if (!jobs.empty()) {
+        const int r = be_->microRunAll(jobs, pc.mc);
+        if (r) { err_ = be_->lastError(); return r; }
+      }
+    }
+    if (failed.load()) return failed.load();
+    std::vector<int64_t> iters(pool_->threads(), 0);
+    pool_->parallelFor((int) pc.chunks.size(), [&](int t, int worker) {
+      Chunk& ch = pc.chunks[t];
+      if (ch.job.n > 0) {
+        const int r = be_->microWait(ch.job);
+        if (r) { failed.store(r); return; }
+      }
+      decodeChunk(pc, ch, iters[worker]);
+    });
+    if (failed.load()) { err_ = be_->lastError(); return failed.load(); }
+    for (int64_t v : iters) be_->stats.iterations += v;
+    for (const Chunk& ch : pc.chunks) {
+      be_->stats.regions += ch.r1 - ch.r0;
+      microRegions += ch.job.n;
+      microVariants += ch.variants;
+    }
+    if ((rc = settle(pc))) return rc;
+  }
+  executed_ = true;
+  return VCE_OK;
+}
+
+int Engine::run(const vce_config& cfg, int32_t nSeq, const vce_sequence* seqs, vce_sequence_result* results) {
+  int rc = prepare(cfg, nSeq, seqs, false);
+  if (rc) return rc;
+  if ((rc = execute())) return rc;
+  return finish(results);
+}
+
+// ------------------------------------------------------------------------------------------- warp-per-region path
+// Runs the regions `ids` through the warp-per-region kernels (vce_search.h).  The variants and alleles of just these
+// regions are packed into compact arrays, so that the cost is proportional to the residual, not to the batch.
+int Engine::wideLaunch(PassCtx& pc, const std::vector<RegKey>& ids, bool general, std::vector<int>& statusOut) {
+  statusOut.assign(ids.size(), kRegionPending);
+  if (ids.empty()) return VCE_OK;
+  PassData pd;
+  pd.pass = pc.pass;
+  pd.H = pc.H;
+  pd.kind[0] = pc.kind[0];
+  pd.kind[1] = pc.kind[1];
+  AlleleTable at[2];
+  std::vector<RegionDesc> descs(ids.size());
+  std::vector<int32_t> syncOff(ids.size());
+  size_t so = 0;
+  int maxSl[2] = {2, 2};
+  for (size_t q = 0; q < ids.size(); ++q) {
+    const int k = ids[q].seq, j = ids[q].j;
+    const RegRange& g = pc.rr[k][j];
+    RegionDesc& d = descs[q];
+    std::memset(&d, 0, sizeof(d));
+    d.seq = k;
+    d.tmplLen = seqs_[k].template_len;
+    const int first[2] = {g.cFirst, g.bFirst};
+    const int count[2] = {g.cCount, g.bCount};
+    int lo = INT_MAX;
+    long hi = 0;
+    for (int side = 0; side < 2; ++side) {
+      const SideSeq& s = pc.ss[side][k];
+      const vce_variants& in = *s.in;
+      HostSide& hs = pd.side[side];
+      hs.gtPloidy = pc.gtPloidy[side];
+      AlleleTable& t = at[side];
+      (side == 0 ? d.cFirst : d.bFirst) = (int32_t) hs.vStart.size();
+      (side == 0 ? d.cCount : d.bCount) = count[side];
+      const int e = first[side] + count[side];
+      (side == 0 ? d.cNextStart : d.bNextStart) = e < s.first + s.n ? pc.vStart[side][e] : kNoNext;
+      for (int v = first[side]; v < e; ++v) {
+        const int li = v - s.first;
+        const int ii = s.idx ? s.idx[li] : li;
+        lo = std::min(lo, pc.vStart[side][v]);
+        hi = std::max(hi, (long) pc.vEnd[side][v]);
+        hs.vStart.push_back(pc.vStart[side][v]);
+        hs.vEnd.push_back(pc.vEnd[side][v]);
+        hs.slot0.push_back((int32_t) t.aStart.size());
+        const int off0 = in.allele_off[ii], nSl = in.allele_off[ii + 1] - off0;
+        hs.nSl.push_back(nSl);
+        maxSl[side] = std::max(maxSl[side], nSl);
+        uint8_t f = (in.phased && in.phased[ii]) ? 1 : 0;
+        if (in.status_in) f |= in.status_in[ii] & VCE_STATUS_OUTSIDE_EVAL;
+        hs.vFlags.push_back(f);
+        for (int h = 0; h < 4; ++h) hs.gt.push_back(h < in.gt_ploidy ? in.gt[(size_t) ii * in.gt_ploidy + h] : (int8_t) -2);
+        hs.inputIdx.push_back(ii);
+        const int nb0 = in.allele_nt_off[off0];
+        const int base = (int) t.nt.size() - nb0;
+        for (int sl = off0; sl < off0 + nSl; ++sl) {
+          t.aStart.push_back(in.allele_start[sl]);
+          t.aEnd.push_back(in.allele_end[sl]);
+          t.aNull.push_back(in.allele_null[sl]);
+          t.aNtOff.push_back(base + in.allele_nt_off[sl]);
+        }
+        t.nt.insert(t.nt.end(), in.nt + nb0, in.nt + in.allele_nt_off[off0 + nSl]);
+      }
+    }
+    d.startPos = j == 0 ? -1 : lo - 1;
+    const auto rit = pc.rare.find(key(k, j));
+    d.prefixAlleleId = j == 0 ? kPrefixEmpty : kDummyPrefix;
+    int extra = 0;
+    if (rit != pc.rare.end()) {
+      if (rit->second.hasPrefix) d.prefixAlleleId = rit->second.assumedPrefix;
+      extra = rit->second.extraMargin;
+    }
+    if (lo == INT_MAX) lo = 0;
+    const int ws = std::max(0, std::min(lo, d.startPos < 0 ? 0 : d.startPos) - 1);
+    long we = extra < 0 ? (long) d.tmplLen : hi + opt_.margin + extra;
+    we = std::min(we, (long) d.tmplLen);
+    if (we < ws) we = ws;
+    d.winStart = ws;
+    d.winLen = (int32_t) (we - ws);
+    syncOff[q] = (int32_t) so;
+    so += (size_t) d.cCount + d.bCount + 2;
+  }
+  for (int side = 0; side < 2; ++side) {
+    at[side].aNtOff.push_back((int32_t) at[side].nt.size());
+    pd.side[side].seqFirst.assign(2, 0);
+    pd.side[side].seqFirst[1] = (int32_t) pd.side[side].n();
+    pd.maxOrient[side] = orientBound(pc.kind[side], pc.H, pc.gtPloidy[side], maxSl[side]);
+    if (pd.maxOrient[side] + 2 > 255) { err_ = "too many orientations per variant for this engine"; return VCE_ERR_UNSUPPORTED; }
+  }
+  const int mo = std::max(pd.maxOrient[0], pd.maxOrient[1]);
+  if (!general && 1 + mo > FastLimits::kMaxChildren) general = true;
+  size_t winBytes = 0;
+  for (RegionDesc& d : descs) {
+    if (general) {
+      d.qMax = std::max(1, std::max(d.cCount, d.bCount));
+      d.decBits = (mo + 2 <= 15) ? 4 : 8;
+      PathLayout PL;
+      PL.init(pc.H, d.qMax, std::max(1, std::max(d.cCount, d.bCount)), d.cCount + d.bCount + 2, d.decBits);
+      d.layoutW = PL.W;
+    }
+    d.winOff = (uint32_t) winBytes;
+    winBytes += ((size_t) d.winLen + 15 + 16) & ~(size_t) 15;
+  }
+  std::vector<uint8_t> windows(winBytes + 16, 0);
+  for (const RegionDesc& d : descs) {
+    if (d.winLen > 0) std::memcpy(windows.data() + d.winOff, seqs_[d.seq].template_bases + d.winStart, (size_t) d.winLen);
+  }
+  int rc;
+  for (int side = 0; side < 2; ++side) {
+    if ((rc = be_->setAlleles(side, at[side]))) { err_ = be_->lastError(); return rc; }
+  }
+  if ((rc = be_->uploadPass(pd))) { err_ = be_->lastError(); return rc; }
+  if ((rc = be_->orient(pd))) { err_ = be_->lastError(); return rc; }
+  std::vector<RegionResult> out(ids.size());
+  std::vector<WarnRec> warns;
+  const SearchConfig sc{cfg_.max_paths, cfg_.max_iterations, cfg_.prune_no_ops, cfg_.preference};
+  if ((rc = be_->search(pd, sc, descs, windows, general, false, out, syncOff, so, warns))) { err_ = be_->lastError(); return rc; }
+  std::vector<int32_t> syncBuf(so, 0);
+  if ((rc = be_->fetchPass(pd, syncBuf))) { err_ = be_->lastError(); return rc; }
+  // a re-run region reports its warnings afresh
+  if (!pc.warns.empty()) {
+    std::vector<WarnEntry> keep;
+    for (const WarnEntry& w : pc.warns) {
+      bool redo = false;
+      for (const RegKey& id : ids) if (id.seq == w.seq && id.j == w.j) { redo = true; break; }
+      if (!redo) keep.push_back(w);
+    }
+    pc.warns.swap(keep);
+  }
+  for (size_t q = 0; q < ids.size(); ++q) {
+    const int k = ids[q].seq, j = ids[q].j;
+    const RegRange& g = pc.rr[k][j];
+    RegRes& s = pc.rs[k][j];
+    const RegionResult& r = out[q];
+    const RegionDesc& d = descs[q];
+    statusOut[q] = r.status;
+    Rare& ra = pc.rare[key(k, j)];
+    ra.general = general;
+    ra.lastStatus = r.status;
+    be_->stats.iterations += r.iterations;
+    if (r.status == kRegionClean || r.status == kRegionFinished) {
+      s.state = RS_WIDE_DONE;
+      s.flags = (uint8_t) ((r.usedPrefix ? 1 : 0) | (r.status == kRegionFinished ? 2 : 0));
+      s.lastId = r.lastBaseAlleleId == kPrefixEmpty ? (int8_t) kMicroNoLastId : (int8_t) r.lastBaseAlleleId;
+      s.nSync = 0;
+      s.ext.idx = (int32_t) pc.wideSync.size();
+      s.ext.n = r.nSync;
+      pc.wideSync.insert(pc.wideSync.end(), syncBuf.begin() + syncOff[q], syncBuf.begin() + syncOff[q] + r.nSync);
+      for (int i = 0; i < g.cCount; ++i) {
+        pc.decision[0][g.cFirst + i] = pd.side[0].decision[d.cFirst + i];
+        pc.weight[g.cFirst + i] = pd.side[0].weight[d.cFirst + i];
+      }
+      for (int i = 0; i < g.bCount; ++i) pc.decision[1][g.bFirst + i] = pd.side[1].decision[d.bFirst + i];
+    } else if (r.status == kRegionErrNull) {
+      s.state = RS_ERR_NULL;
+    } else if (r.status == kRegionErrMove) {
+      s.state = RS_ERR_MOVE;
+    } else if (r.status == kRegionErrOrder) {
+      s.state = RS_ERR_ORDER;
+    } else {
+      s.state = RS_RESIDUAL;
+    }
+  }
+  for (const WarnRec& w : warns) {
+    if (w.region < 0 || (size_t) w.region >= ids.size()) continue;
+    const int st = statusOut[w.region];
+    if (st != kRegionClean && st != kRegionFinished) continue;
+    pc.warns.push_back(WarnEntry{ids[w.region].seq, ids[w.region].j, w});
+  }
+  return VCE_OK;
+}
+
+// Settles every region the thread-per-region kernel left open: SPILL -> merge with the following region and re-run,
+// capacity -> large-capacity kernel, then the prefix-dependent tie-breaks (MaxSumBoth.java:55,76).
+int Engine::settle(PassCtx& pc) {
+  int rc;
+  std::vector<RegKey> todoFast, todoGen;
+  {
+    std::vector<std::vector<RegKey>> per(nSeq_);
+    pool_->parallelFor(nSeq_, [&](int k, int) {
+      const RegRes* rs = pc.rs[k].data();
+      const size_t n = pc.rs[k].size();
+      for (size_t j = 0; j < n; ++j) if (rs[j].state == RS_RESIDUAL) per[k].push_back(RegKey{k, (int) j});
+    });
+    for (int k = 0; k < nSeq_; ++k) {
+      for (const RegKey& id : per[k]) (fastEligible(pc, pc.rr[k][id.j]) ? todoFast : todoGen).push_back(id);
+    }
+  }
+  be_->stats.escalated += (int64_t) (todoFast.size() + todoGen.size());
+  auto nextAlive = [&](int k, int j) {
+    const int n = (int) pc.rs[k].size();
+    int nx = j + 1;
+    while (nx < n && pc.rs[k][nx].state == RS_DEAD) ++nx;
+    return nx;
+  };
+  for (int round = 0; round < 100000; ++round) {
+    if (todoFast.empty() && todoGen.empty()) {
+      // prefix-dependent tie-breaks: re-run the first region per sequence whose assumption was wrong
+      std::vector<int> fix(nSeq_, -1);
+      std::vector<int> fixPrefix(nSeq_, 0);
+      pool_->parallelFor(nSeq_, [&](int k, int) {
+        const RegRes* rs = pc.rs[k].data();
+        const int n = (int) pc.rs[k].size();
+        int prefix = kPrefixEmpty;
+        for (int j = 0; j < n; ++j) {
+          const RegRes& s = rs[j];
+          if (s.state == RS_DEAD) continue;
+          if (s.state != RS_MICRO_DONE && s.state != RS_WIDE_DONE) continue;
+          if (s.flags & 1) {
+            int assumed = j == 0 ? kPrefixEmpty : kDummyPrefix;
+            if (s.state == RS_WIDE_DONE) {
+              const auto it = pc.rare.find(key(k, j));
+              if (it != pc.rare.end() && it->second.hasPrefix) assumed = it->second.assumedPrefix;
+            }
+            if (assumed != prefix) { fix[k] = j; fixPrefix[k] = prefix; return; }
+          }
+          if (s.lastId != (int8_t) kMicroNoLastId) prefix = s.lastId;
+        }
+      });
+      for (int k = 0; k < nSeq_; ++k) {
+        if (fix[k] < 0) continue;
+        Rare& ra = pc.rare[key(k, fix[k])];
+        ra.hasPrefix = true;
+        ra.assumedPrefix = fixPrefix[k];
+        const RegKey id{k, fix[k]};
+        ((ra.general || !fastEligible(pc, pc.rr[k][fix[k]])) ? todoGen : todoFast).push_back(id);
+        ++be_->stats.prefixReruns;
+      }
+      if (todoFast.empty() && todoGen.empty()) break;
+    }
+    std::vector<RegKey> ranF, ranG;
+    std::vector<int> stF, stG;
+    ranF.swap(todoFast);
+    ranG.swap(todoGen);
+    if ((rc = wideLaunch(pc, ranF, false, stF))) return rc;
+    if ((rc = wideLaunch(pc, ranG, true, stG))) return rc;
+    // inspect in sequence order so that chains of spilling regions merge front to back
+    std::vector<std::pair<RegKey, int>> all;
+    for (size_t q = 0; q < ranF.size(); ++q) all.push_back(std::make_pair(ranF[q], stF[q]));
+    for (size_t q = 0; q < ranG.size(); ++q) all.push_back(std::make_pair(ranG[q], stG[q]));
+    std::sort(all.begin(), all.end(), [](const std::pair<RegKey, int>& a, const std::pair<RegKey, int>& b) {
+      return a.first.seq != b.first.seq ? a.first.seq < b.first.seq : a.first.j < b.first.j;
+    });
+    for (size_t q = 0; q < all.size(); ++q) {
+      const int k = all[q].first.seq, j = all[q].first.j;
+      const int st = all[q].second;
+      if (pc.rs[k][j].state == RS_DEAD) continue;
+      Rare& ra = pc.rare[key(k, j)];
+      if (st == kRegionOverflow) {
+        if (ra.general) { err_ = "search capacity exceeded in the large-capacity kernel"; return VCE_ERR_CAPACITY; }
+        todoGen.push_back(all[q].first);
+        ++be_->stats.escalated;
+      } else if (st == kRegionSpill) {
+        ++be_->stats.spilled;
+        const int n = (int) pc.rs[k].size();
+        int nx = nextAlive(k, j);
+        RegRange& g = pc.rr[k][j];
+        if (nx >= n) {
+          // last region of its sequence ran off its reference window: widen it
+          if (ra.extraMargin < 0) { err_ = "region spilled with the whole template in its window"; return VCE_ERR_CAPACITY; }
+          ra.extraMargin = ra.extraMargin == 0 ? 256 : (ra.extraMargin >= (1 << 20) ? -1 : ra.extraMargin * 16);
+        } else {
+          // absorb the following region (and further ones while they are themselves known to spill)
+          pc.undo.push_back(std::make_pair(RegKey{k, j}, g));
+          bool more = true;
+          while (more && nx < n) {
+            RegRes& o = pc.rs[k][nx];
+            const RegRange& og = pc.rr[k][nx];
+            const auto oit = pc.rare.find(key(k, nx));
+            more = o.state == RS_RESIDUAL && oit != pc.rare.end() && oit->second.lastStatus == kRegionSpill;
+            g.cCount += og.cCount;
+            g.bCount += og.bCount;
+            o.state = RS_DEAD;
+            nx = nextAlive(k, nx);
+          }
+          ra.extraMargin = 0;
+        }
+        pc.rs[k][j].state = RS_RESIDUAL;
+        (fastEligible(pc, g) ? todoFast : todoGen).push_back(all[q].first);
+      }
+    }
+  }
+  return VCE_OK;
+}
+
+// ------------------------------------------------------------------------------------------- assembly
+// PhasingEvaluator.countMisphasings, src/com/rtg/vcf/eval/PhasingEvaluator.java:55-142, on the flat pass-0 results.
+namespace {
+struct VSum { int start; bool phased, included, phase; };
+struct CallIter {  // PhasingEvaluator.CallIterator :160-195
+  const std::vector<VSum>& inc;
+  const std::vector<VSum>& exc;
+  size_t i = 0, e = 0;
+  CallIter(const std::vector<VSum>& a, const std::vector<VSum>& b) : inc(a), exc(b) {}
+  bool hasNext() const { return i < inc.size() || e < exc.size(); }
+  VSum next() {
+    const bool haveI = i < inc.size(), haveE = e < exc.size();
+    if (!haveI || (haveE && exc[e].start < inc[i].start)) return exc[e++];
+    return inc[i++];
+  }
+};
+bool groupInPhase(const std::vector<VSum>& g) {  // :143-155
+  if (g.empty()) return true;
+  if (!g[0].phased) return false;
+  const bool ph = g[0].phase;
+  for (const VSum& v : g) if (!v.phased || v.phase != ph) return false;
+  return true;
+}
+}  // namespace
+
+void Engine::phasing(int k, const std::vector<int32_t>& sync, int32_t out[3]) const {
+  const PassCtx& pc = pass_[0];
+  std::vector<VSum> inc[2], exc[2];
+  for (int side = 0; side < 2; ++side) {
+    const SideSeq& s = pc.ss[side][k];
+    const vce_variants& in = *s.in;
+    const int P = in.gt_ploidy;
+    for (int li = 0; li < s.n; ++li) {
+      const int v = s.first + li;
+      const int dec = pc.decision[side][v];
+      if (dec == 0) continue;
+      const int ii = s.idx ? s.idx[li] : li;
+      const bool ph = in.phased && in.phased[ii];
+      if (dec == 1) {
+        exc[side].push_back(VSum{pc.vStart[side][v], ph, false, false});
+      } else {
+        VariantGt g;
+        g.gtPloidy = pc.gtPloidy[side];
+        for (int h = 0; h < 4; ++h) g.gt[h] = h < P ? in.gt[(size_t) ii * P + h] : -2;
+        g.phased = ph ? 1 : 0;
+        g.slot0 = in.allele_off[ii];
+        g.nSlots = in.allele_off[ii + 1] - in.allele_off[ii];
+        g.aNull = in.allele_null;
+        RowPick pick;
+        pick.want = dec - 2;
+        orientVariant(pc.kind[side], pc.H, g, pick);
+        inc[side].push_back(VSum{pc.vStart[side][v], ph, true, pick.original});
+      }
+    }
+  }
+  CallIter baseline(inc[1], exc[1]);
+  CallIter calls(inc[0], exc[0]);
+  int mis = 0, unph = 0, correct = 0;
+  bool baseIsPhased = false, basePhase = false, callIsPhased = false, callPhase = false;
+  bool haveCall = false, haveBase = false;
+  VSum call{0, false, false, false}, base{0, false, false, false};
+  std::vector<VSum> bsec, csec;
+  for (int point : sync) {
+    bsec.clear();
+    csec.clear();
+    do {
+      if (haveBase && base.start < point) {
+        bsec.push_back(base);
+        haveBase = baseline.hasNext();
+        if (haveBase) base = baseline.next();
+      }
+      if (!haveBase) {
+        haveBase = baseline.hasNext();
+        if (haveBase) base = baseline.next();
+      }
+    } while (haveBase && base.start < point);
+    do {
+      if (haveCall) csec.push_back(call);
+      haveCall = calls.hasNext();
+      if (haveCall) call = calls.next();
+    } while (haveCall && call.start < point);
+    if (!groupInPhase(bsec)) {
+      for (const VSum& s : csec) if (s.phased) ++unph;
+      baseIsPhased = false;
+      callIsPhased = false;
+      continue;
+    }
+    bool transition = false;
+    if (!baseIsPhased) callIsPhased = false;
+    for (const VSum& b : bsec) {
+      if (b.phased) {
+        if (basePhase != b.phase) transition = true;
+        baseIsPhased = true;
+      }
+      basePhase = b.phase;
+    }
+    for (const VSum& c : csec) {
+      if (!c.phased) {
+        callIsPhased = false;
+      } else if (!callIsPhased) {
+        callIsPhased = true;
+        callPhase = c.phase;
+      } else {
+        const bool callTransition = c.phase != callPhase;
+        if (c.included && !(callTransition == transition)) { ++mis; callPhase = c.phase; }
+        else if (c.included) { ++correct; callPhase = c.phase; }
+      }
+      transition = false;
+    }
+  }
+  out[0] = mis; out[1] = correct; out[2] = unph;
+}
+
+void Engine::assemble(int k, vce_sequence_result& res) {
+  const vce_sequence& sq = seqs_[k];
+  res.n_sync[0] = res.n_sync[1] = 0;
+  res.phasing[0] = res.phasing[1] = res.phasing[2] = 0;
+  res.n_warnings = 0;
+  res.error = VCE_OK;
+  res.n_regions = 0;
+  res.n_iterations = 0;
+  vce_side_result* sides[2] = {&res.calls, &res.baseline};
+  const vce_variants* vin[2] = {&sq.calls, &sq.baseline};
+  if (pass_[0].shortCircuit[k]) {  // SequenceEvaluator.java:94-97
+    for (int side = 0; side < 2; ++side) {
+      vce_side_result& o = *sides[side];
+      for (int i = 0; i < vin[side]->n; ++i) {
+        o.status[i] = (uint8_t) ((vin[side]->status_in ? vin[side]->status_in[i] : 0) | VCE_STATUS_NO_MATCH);
+        for (int h = 0; h < VCE_MAX_PLOIDY; ++h) o.allele_ids[(size_t) i * VCE_MAX_PLOIDY + h] = -2;
+        o.original[i] = 0;
+        o.weight[i] = 0;
+        if (o.sync_id) o.sync_id[i] = 1;
+      }
+    }
+    return;
+  }
+  // sync points per pass + per-sequence errors
+  std::vector<int32_t> sync[2];
+  for (int p = 0; p < cfg_.n_passes; ++p) {
+    const PassCtx& pc = pass_[p];
+    const int n = (int) pc.rs[k].size();
+    sync[p].reserve((size_t) n + 8);
+    for (int j = 0; j < n; ++j) {
+      const RegRes& s = pc.rs[k][j];
+      if (s.state == RS_DEAD) continue;
+      if (s.state == RS_ERR_NULL) res.error = VCE_ERR_BEST_PATH_NULL;
+      else if (s.state == RS_ERR_MOVE) res.error = VCE_ERR_MOVE_IN_VARIANT;
+      else if (s.state == RS_ERR_ORDER) res.error = VCE_ERR_UNSUPPORTED;
+      if (s.state == RS_MICRO_DONE) {
+        const int base = regionStartPos(pc, k, j);
+        for (int q = 0; q < s.nSync; ++q) {
+          const int sp = base + s.rel[q];
+          if (sync[p].empty() || sync[p].back() != sp) sync[p].push_back(sp);  // Path.java:293 de-duplication
+        }
+      } else if (s.state == RS_WIDE_DONE) {
+        for (int q = 0; q < s.ext.n; ++q) {
+          const int sp = pc.wideSync[s.ext.idx + q];
+          if (sync[p].empty() || sync[p].back() != sp) sync[p].push_back(sp);
+        }
+      }
+    }
+    // re-runs append out of order: report in region order, as the sequential reference would
+    std::vector<WarnEntry> ws;
+    for (const WarnEntry& w : pc.warns) if (w.seq == k && pc.rs[k][w.j].state != RS_DEAD) ws.push_back(w);
+    std::stable_sort(ws.begin(), ws.end(), [](const WarnEntry& a, const WarnEntry& b) { return a.j < b.j; });
+    for (const WarnEntry& w : ws) {
+      if (res.n_warnings < res.warn_cap) res.warnings[res.n_warnings] = vce_warning{p, w.w.paths, w.w.iterations, w.w.start1, w.w.end1};
+      ++res.n_warnings;
+    }
+  }
+  if (res.error != VCE_OK) {
+    for (int side = 0; side < 2; ++side) {
+      vce_side_result& o = *sides[side];
+      for (int i = 0; i < vin[side]->n; ++i) {
+        o.status[i] = vin[side]->status_in ? vin[side]->status_in[i] : 0;
+        for (int h = 0; h < VCE_MAX_PLOIDY; ++h) o.allele_ids[(size_t) i * VCE_MAX_PLOIDY + h] = -2;
+        o.original[i] = 0;
+        o.weight[i] = 0;
+        if (o.sync_id) o.sync_id[i] = 0;
+      }
+    }
+    return;
+  }
+  for (int p = 0; p < cfg_.n_passes; ++p) {
+    res.n_sync[p] = (int32_t) sync[p].size();
+    if ((int) sync[p].size() > res.sync_cap[p]) { res.error = VCE_ERR_CAPACITY; return; }
+    std::copy(sync[p].begin(), sync[p].end(), res.sync_points[p]);
+  }
+  res.n_regions = (int64_t) sync[0].size();
+  // statuses (SequenceEvaluator.mergeVariants :170-182, insertSkipped :190-209), orientation ids, weights, sync ids
+  for (int side = 0; side < 2; ++side) {
+    vce_side_result& o = *sides[side];
+    const vce_variants& in = *vin[side];
+    const PassCtx& p0 = pass_[0];
+    const SideSeq& a = p0.ss[side][k];
+    const int P = in.gt_ploidy;
+    // pass-1 decision of every input variant (0 when the variant did not enter pass 1)
+    std::vector<uint8_t> dec1;
+    std::vector<double> w1;
+    if (cfg_.n_passes == 2) {
+      const PassCtx& p1 = pass_[1];
+      const SideSeq& b = p1.ss[side][k];
+      dec1.assign(in.n, 0);
+      if (side == 0) w1.assign(in.n, 0.0);
+      for (int li = 0; li < b.n; ++li) {
+        const int ii = b.idx[li];
+        dec1[ii] = p1.decision[side][b.first + li];
+        if (side == 0) w1[ii] = p1.weight[b.first + li];
+      }
+    }
+    size_t f0 = 0, f1 = 0;  // floor cursors into sync[0] / sync[1] (variants come in ascending start order)
+    auto floorVal = [](const std::vector<int32_t>& sp, size_t& cur, int start) -> int {
+      // InterleavingEvalSynchronizer.floorSyncPos :71-83: last sync point <= start - 1 (first one if none)
+      if (sp.empty()) return 0;
+      const int vv = start - 1;
+      while (cur + 1 < sp.size() && sp[cur + 1] <= vv) ++cur;
+      return sp[cur] + 1;
+    };
+    for (int li = 0; li < a.n; ++li) {
+      const int v = a.first + li;
+      const int ii = a.idx ? a.idx[li] : li;
+      int st = in.status_in ? in.status_in[ii] : 0;
+      int d0 = p0.decision[side][v];
+      int kindSel = -1, row = 0;
+      double wgt = 0.0;
+      if (d0 >= 2) {
+        st |= VCE_STATUS_GT_MATCH;
+        kindSel = 0;
+        row = d0 - 2;
+        wgt = side == 0 ? p0.weight[v] : 0.0;
+      } else if (cfg_.n_passes == 1) {
+        if (d0 == 1) st |= VCE_STATUS_NO_MATCH;
+        else st |= VCE_STATUS_SKIPPED;
+      } else {
+        const int d1 = dec1[ii];
+        if (d1 >= 2) {
+          st |= VCE_STATUS_ALLELE_MATCH;
+          kindSel = 1;
+          row = d1 - 2;
+          wgt = side == 0 ? w1[ii] : 0.0;
+        } else if (d1 == 1) {
+          st |= VCE_STATUS_NO_MATCH;
+        } else {
+          st |= VCE_STATUS_SKIPPED;
+        }
+      }
+      o.status[ii] = (uint8_t) st;
+      int8_t* ids = o.allele_ids + (size_t) ii * VCE_MAX_PLOIDY;
+      if (kindSel >= 0) {
+        const PassCtx& pp = pass_[kindSel];
+        VariantGt g;
+        g.gtPloidy = pp.gtPloidy[side];
+        for (int h = 0; h < 4; ++h) g.gt[h] = h < P ? in.gt[(size_t) ii * P + h] : -2;
+        g.phased = (in.phased && in.phased[ii]) ? 1 : 0;
+        g.slot0 = in.allele_off[ii];
+        g.nSlots = in.allele_off[ii + 1] - in.allele_off[ii];
+        g.aNull = in.allele_null;
+        RowPick pick;
+        pick.want = row;
+        orientVariant(pp.kind[side], pp.H, g, pick);
+        for (int h = 0; h < 4; ++h) ids[h] = pick.ids[h];
+        o.original[ii] = pick.original ? 1 : 0;
+      } else {
+        ids[0] = ids[1] = ids[2] = ids[3] = -2;
+        o.original[ii] = 0;
+      }
+      o.weight[ii] = wgt;
+      if (o.sync_id) {
+        // SYNC annotation value (InterleavingEvalSynchronizer.floorSyncPos :71-83 + WithInfoEvalSynchronizer :121-222)
+        const int s1 = floorVal(sync[0], f0, p0.vStart[side][v]);
+        const int s2 = floorVal(sync[1], f1, p0.vStart[side][v]);
+        int val = 0;
+        if (st & VCE_STATUS_SKIPPED) val = 0;
+        else if (st & VCE_STATUS_GT_MATCH) val = s1 + 1;
+        else if (st & VCE_STATUS_ALLELE_MATCH) val = s2 + 1;
+        else if (st & VCE_STATUS_NO_MATCH) val = s2 > 0 ? s2 + 1 : s1 + 1;
+        o.sync_id[ii] = val;
+      }
+    }
+  }
+  phasing(k, sync[0], res.phasing);
+}
+
+int Engine::finish(vce_sequence_result* results) {
+  // largest sequences first
+  std::vector<int> order(nSeq_);
+  for (int k = 0; k < nSeq_; ++k) order[k] = k;
+  std::sort(order.begin(), order.end(), [&](int a, int b) {
+    const int na = seqs_[a].calls.n + seqs_[a].baseline.n, nb = seqs_[b].calls.n + seqs_[b].baseline.n;
+    return na != nb ? na > nb : a < b;
+  });
+  pool_->parallelFor(nSeq_, [&](int t, int) { assemble(order[t], results[order[t]]); });
+  int rc = VCE_OK;
+  for (int k = 0; k < nSeq_; ++k) {
+    // per-sequence diagnostics
+    if (results[k].error != VCE_OK && rc == VCE_OK) rc = results[k].error;
+  }
+  return rc;
+}
+
+}  // namespace vce

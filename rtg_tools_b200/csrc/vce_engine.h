@@ -1,0 +1,149 @@
+// vce_engine.h -- host side of the engine.  Replaces SequenceEvaluator.run() for a batch of sequences
+// (src/com/rtg/vcf/eval/SequenceEvaluator.java:87-155):
+//
+//   digest   (worker pool)  variant bounds, (start,end) order check, split of every sequence into independent search
+//                           regions, one self-contained PACKET per small region written into page-locked memory
+//   device   (CUDA streams) per chunk of regions: H2D of the packets, thread-per-region search kernel (vce_micro.h),
+//                           D2H of the fixed-size result records -- overlapped with the digest of later chunks
+//   decode   (worker pool)  result records -> per-variant decisions / weights, per-region sync points
+//   residual                regions the small kernel cannot take or did not settle (first / last region of a
+//                           sequence, large or N-containing regions, SPILL, capacity, prefix-dependent tie-breaks) are
+//                           merged / re-run with the warp-per-region kernels (vce_search.h) until every region is exact
+//   assemble (worker pool)  status merge, orientation ids, sync ids, phasing counts into the caller's arrays
+//
+// The device work is behind `Backend` (vce_pipeline.h).  The product library links the CUDA backend only.
+#ifndef VCE_ENGINE_H_
+#define VCE_ENGINE_H_
+
+#include <cstdint>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "vce_pipeline.h"
+#include "vce_pool.h"
+
+namespace vce {
+
+struct EngineOptions {
+  int gap = 1;            // split when next.start >= maxEnd + gap (gap >= 1)
+  int margin = 24;        // reference bases beyond the last variant end of a region (warp-per-region kernels)
+  int microMargin = 12;   // same, thread-per-region kernel
+  bool forceGeneral = false;   // tests: every region through the large-capacity kernel
+  bool disableMicro = false;   // tests: no thread-per-region kernel
+  int chunkRegions = 0;        // regions per chunk, 0 = automatic
+};
+
+class Engine {
+ public:
+  Engine(Backend* b, WorkerPool* pool, const EngineOptions& o);
+  ~Engine();
+  int run(const vce_config& cfg, int32_t nSeq, const vce_sequence* seqs, vce_sequence_result* results);
+  // staged variant: prepare = digest + upload of pass 0, execute = device work and settling (repeatable),
+  // finish = assembly into the caller's arrays
+  int prepare(const vce_config& cfg, int32_t nSeq, const vce_sequence* seqs, bool staged);
+  int execute();
+  int finish(vce_sequence_result* results);
+  const std::string& error() const { return err_; }
+  Backend* backend() { return be_; }
+  // diagnostics of the last execute(): milliseconds of the largest thread-per-region launch, its regions and variants
+  double microMs = 0;
+  int64_t microRegions = 0, microVariants = 0;
+
+ private:
+  struct SideSeq {            // one side of one sequence in one pass
+    const vce_variants* in = nullptr;
+    int32_t first = 0, n = 0; // slice of the pass-wide arrays
+    const int32_t* idx = nullptr;  // (start,end)-sorted position -> input index, nullptr = identity
+  };
+  struct RegRange { int32_t cFirst, cCount, bFirst, bCount; };  // pass-wide sorted indices
+  struct RegRes {
+    uint8_t state, flags;     // RS_*, bit0 usedPrefix, bit1 finished (last region of the sequence)
+    int8_t lastId;            // alleleId() of the last baseline variant included in the region, -128 = none
+    uint8_t nSync;            // thread-per-region results: sync points relative to the region start position
+    union {
+      uint8_t rel[8];
+      struct { int32_t idx, n; } ext;   // warp-per-region results: slice of PassCtx::wideSync
+    };
+  };
+  enum : uint8_t { RS_PENDING = 0, RS_MICRO_DONE = 1, RS_WIDE_DONE = 2, RS_DEAD = 3, RS_RESIDUAL = 4, RS_ERR_NULL = 5,
+                   RS_ERR_MOVE = 6, RS_ERR_ORDER = 7 };
+  struct RegKey { int32_t seq, j; };
+  struct Rare {               // state only re-run regions carry
+    int extraMargin = 0;      // reference bases added after a window miss (< 0: rest of the template)
+    int assumedPrefix = 0;
+    bool hasPrefix = false;   // an explicit prefix was set (otherwise the default assumption)
+    bool general = false;     // last ran in the large-capacity kernel
+    int lastStatus = 0;       // kRegion* of the last wide run
+  };
+  struct Chunk {
+    int seq = 0, r0 = 0, r1 = 0;
+    MicroJob job;
+    std::vector<int32_t> pktRegion;   // packet -> region index within the sequence
+    int64_t variants = 0;
+  };
+  struct WarnEntry { int32_t seq, j; WarnRec w; };
+  struct PassCtx {
+    int pass = 0, H = 2, kind[2] = {0, 0};
+    int gtPloidy[2] = {0, 0};
+    bool microOk = false;
+    MicroConfig mc{};
+    std::vector<SideSeq> ss[2];                  // [side][seq]; side 0 = calls, 1 = baseline
+    std::vector<int32_t> vStart[2], vEnd[2];
+    std::vector<uint8_t> decision[2];
+    std::vector<double> weight;                  // calls
+    std::vector<std::vector<int32_t>> idxStore[2];
+    std::vector<std::vector<RegRange>> rr;       // per sequence
+    std::vector<std::vector<RegRes>> rs;
+    std::vector<std::vector<uint8_t>> rcls;      // 0 = warp-per-region path, 1 = MicroA, 2 = MicroB
+    std::vector<Chunk> chunks;
+    std::vector<int32_t> wideSync;
+    std::vector<WarnEntry> warns;
+    std::unordered_map<uint64_t, Rare> rare;
+    std::vector<std::pair<RegKey, RegRange>> undo;   // ranges changed by merges (a staged job can be executed repeatedly)
+    std::vector<uint8_t> shortCircuit;
+    bool launched = false;                       // chunks were started during prepare()
+  };
+  struct HostBlock { uint8_t* p; size_t cap, used; };
+
+  static uint64_t key(int seq, int j) { return ((uint64_t) (uint32_t) seq << 32) | (uint32_t) j; }
+  uint8_t* arenaAlloc(size_t bytes);
+  void arenaReset();
+
+  int setupPass0();
+  int setupPass1();
+  void computeBounds(PassCtx& pc);
+  void splitSequence(PassCtx& pc, int k);
+  void planChunks(PassCtx& pc);
+  template <class T> int buildPacket(const PassCtx& pc, int k, int j, uint8_t* out) const;
+  int buildChunk(PassCtx& pc, Chunk& ch, int worker, bool launch);
+  int runChunks(PassCtx& pc);
+  void decodeChunk(PassCtx& pc, Chunk& ch, int64_t& iterations);
+  int settle(PassCtx& pc);
+  int wideLaunch(PassCtx& pc, const std::vector<RegKey>& ids, bool general, std::vector<int>& statusOut);
+  bool fastEligible(const PassCtx& pc, const RegRange& g) const;
+  int regionStartPos(const PassCtx& pc, int k, int j) const;
+  void assemble(int k, vce_sequence_result& res);
+  void phasing(int k, const std::vector<int32_t>& sync, int32_t out[3]) const;
+  void resetPassRun(PassCtx& pc);
+
+  Backend* be_;
+  WorkerPool* pool_;
+  EngineOptions opt_;
+  vce_config cfg_{};
+  int32_t nSeq_ = 0;
+  const vce_sequence* seqs_ = nullptr;
+  PassCtx pass_[2];
+  bool executed_ = false;
+  bool staged_ = false;
+  std::string err_;
+  std::mutex errMu_;
+  std::mutex arenaMu_;
+  std::vector<HostBlock> arena_;
+  std::vector<std::vector<uint8_t>> scratch_;   // per worker
+  std::vector<std::vector<uint32_t>> scratchOff_;
+};
+
+}  // namespace vce
+#endif

@@ -1,12 +1,9 @@
-// vce_pipeline.h -- host side of the engine: packs a batch of sequences into flat arrays, splits every
-// sequence into independent search regions, drives the search kernels (re-running the few regions that
-// report SPILL / OVERFLOW / prefix-dependent tie-breaks) and assembles the per-variant results the
-// reference's SequenceEvaluator.run() would hand to EvalSynchronizer.write
-// (src/com/rtg/vcf/eval/SequenceEvaluator.java:87-155).
+// vce_pipeline.h -- the interface between the host engine (vce_engine.h) and the device work: flat host-side arrays
+// of a batch of regions, launch descriptors, and `Backend`.
 //
-// The device work is behind `Backend`.  The product library links exactly one backend, the CUDA one
-// (vce_cuda.cu).  tests/emul builds a 1-lane host instantiation of the same search source to exercise this
-// host logic where no GPU exists; it is never linked into the product.
+// The product library links exactly one backend, the CUDA one (vce_cuda.cu).  tests/emul builds a host
+// instantiation of the same search sources to exercise the host logic where no GPU exists; it is never linked
+// into the product.
 #ifndef VCE_PIPELINE_H_
 #define VCE_PIPELINE_H_
 
@@ -16,6 +13,7 @@
 
 #include "../../include/vce.h"
 #include "vce_device.h"
+#include "vce_micro.h"
 #include "vce_search.h"
 
 namespace vce {
@@ -59,9 +57,36 @@ struct SearchStats {
   int64_t iterations = 0;
 };
 
+// One chunk of thread-per-region work (vce_micro.h): packets in, fixed-size result records out.
+struct MicroJob {
+  int cls = 0;                        // 0 = MicroA, 1 = MicroB
+  int n = 0;                          // regions in the chunk
+  const uint8_t* packets = nullptr;   // host buffer (from Backend::hostAlloc), packetBytes long
+  size_t packetBytes = 0;
+  const uint32_t* offsets = nullptr;  // [n] offset of each packet in 4-byte words (host, from hostAlloc)
+  uint8_t* results = nullptr;         // [n * resBytes] host (from hostAlloc)
+  int resBytes = 0;
+  // backend-private
+  void* dPackets = nullptr;
+  void* dOffsets = nullptr;
+  void* dResults = nullptr;
+  int lane = 0;
+  int event = -1;
+  void* evHandle = nullptr;
+};
+
 class Backend {
  public:
   virtual ~Backend() {}
+  // ---- thread-per-region path.  Calls for different jobs may come from different host threads.
+  virtual void* hostAlloc(size_t bytes) = 0;   // page-locked on the CUDA backend
+  virtual void hostFree(void* p) = 0;
+  virtual int microReset() = 0;                               // forgets the device buffers of earlier jobs
+  virtual int microUpload(MicroJob& j) = 0;                   // async host -> device copy of packets and offsets
+  virtual int microRun(MicroJob& j, const MicroConfig& mc) = 0;  // async kernel + device -> host copy of the results
+  // one kernel launch over all (uploaded) jobs + one async result copy per job: the staged / HBM-resident path
+  virtual int microRunAll(std::vector<MicroJob*>& jobs, const MicroConfig& mc) = 0;
+  virtual int microWait(MicroJob& j) = 0;                     // blocks until the results of j are on the host
   virtual int setAlleles(int side, const AlleleTable& t) = 0;
   // Host -> device copy of the pass's variant arrays; clears the per-variant outputs.
   virtual int uploadPass(PassData& pd) = 0;
@@ -97,77 +122,6 @@ struct FastLimits {
   static constexpr int kMaxChildren = 7;     // exclude + up to 6 orientations (ALLELE_GT)
   static constexpr int kSlots = kCap + 1 + kMaxChildren;
   static constexpr int kOrdCap = 2 * kCap;
-};
-
-struct PipelineOptions {
-  int gap = 1;        // split when next.start >= maxEnd + gap  (gap >= 1)
-  int margin = 24;    // reference bases kept beyond the last variant end of a region
-  bool wantSyncId = true;
-};
-
-class Pipeline {
- public:
-  Pipeline(Backend* b, const PipelineOptions& o) : be_(b), opt_(o) {}
-  int run(const vce_config& cfg, int32_t nSeq, const vce_sequence* seqs, vce_sequence_result* results);
-  // staged variant (bench): prepare = pack + split + upload, execute = kernels + re-run loops, finish = assembly
-  int prepare(const vce_config& cfg, int32_t nSeq, const vce_sequence* seqs);
-  int execute();
-  int finish(vce_sequence_result* results);
-  const std::string& error() const { return err_; }
-  Backend* backend() { return be_; }
-
- private:
-  struct Region {
-    RegionDesc d;
-    RegionResult r;
-    int syncOff = 0;
-    bool alive = true;
-    bool general = false;
-    int assumedPrefix = 0;
-    int extraMargin = 0;   // reference bases added to the window after a window miss (< 0: rest of the template)
-  };
-  struct Launch {  // one search launch, ready to go
-    std::vector<int> ids;
-    std::vector<RegionDesc> descs;
-    std::vector<uint8_t> windows;
-    std::vector<int32_t> syncOff;
-  };
-  struct PassState {
-    PassData pd;
-    bool fetched = false;
-    std::vector<Region> regions;          // sequence order
-    std::vector<Region> initRegions;      // as split, before any merge (a staged job can be executed repeatedly)
-    size_t initSyncSize = 0;
-    Launch mainFast;                      // staged in prepare() for pass 0
-    std::vector<int> mainGen;
-    std::vector<int32_t> seqRegionFirst;  // [nSeq+1]
-    std::vector<int32_t> syncBuf;
-    std::vector<WarnRec> warns;
-    std::vector<uint8_t> shortCircuit;    // per sequence
-  };
-  int buildPass0();
-  int buildPass1();
-  void splitRegions(PassState& ps);
-  bool fastEligible(const PassState& ps, const RegionDesc& d) const;
-  int setupPass(PassState& ps, bool stageMain);
-  int runPass(PassState& ps, bool staged);
-  void buildLaunch(PassState& ps, const std::vector<int>& ids, bool general, Launch& L);
-  int runLaunch(PassState& ps, Launch& L, bool general, bool staged);
-  int launch(PassState& ps, const std::vector<int>& ids, bool general);
-  static int orientBound(int kind, int H, int gtPloidy, int maxSlots);
-  void assemble(int k, vce_sequence_result& res);
-  void phasing(int k, int32_t out[3]) const;
-
-  Backend* be_;
-  PipelineOptions opt_;
-  vce_config cfg_{};
-  int32_t nSeq_ = 0;
-  const vce_sequence* seqs_ = nullptr;
-  AlleleTable alleles_[2];
-  std::vector<int32_t> slotBase_[2];  // per sequence
-  PassState pass_[2];
-  bool executed_ = false;
-  std::string err_;
 };
 
 }  // namespace vce

@@ -200,10 +200,11 @@ def perturb(template, base: VarSet, rng, drop=0.05, novel=0.05, rerep=0.10, zyg=
     extra = simulate_sample(template, rng, snp_rate=1.24e-3 * novel, mnp_rate=9.2e-5 * novel, indel_rate=1.5e-4 * novel)
     extra.phased = (rng.random(extra.n) >= unphase).astype(np.uint8)
     allv = VarSet.concat([cur, extra]).sorted()
-    # drop novel variants that collide with an existing one (keeps the sample free of self-overlaps)
+    # drop novel variants that collide with an existing one (keeps the sample free of self-overlaps; directly
+    # adjacent records, e.g. the SNPs of a split MNP, are kept)
     end = allv.start + np.maximum(allv.ref_len, 1)
     prev_end = np.concatenate([[-1], np.maximum.accumulate(end)[:-1]])
-    ok = allv.start > prev_end
+    ok = allv.start >= prev_end
     return allv.take(np.nonzero(ok)[0])
 
 

@@ -53,8 +53,8 @@ class Job:
     def stats_ex(self):
         out = (C.c_double * 13)()
         self.engine.lib.lib.vce_job_stats_ex(self.handle, out, 13)
-        keys = ["launches", "search_ms", "fast_kernel_ms", "fast_regions", "regions", "escalated", "spilled", "prefix_reruns",
-                "h2d_bytes", "d2h_bytes", "iterations", "execute_ms", "fast_variants"]
+        keys = ["launches", "search_ms", "micro_kernel_ms", "micro_regions", "regions", "escalated", "spilled", "prefix_reruns",
+                "h2d_bytes", "d2h_bytes", "iterations", "execute_ms", "micro_variants"]
         return {k: out[i] for i, k in enumerate(keys)}
 
     def stats(self):
@@ -65,7 +65,7 @@ class Job:
         n_esc = C.c_int64()
         self.engine.lib.lib.vce_job_stats(self.handle, C.byref(n_launch), C.byref(dev_ms), C.byref(fast_ms), C.byref(n_reg),
                                           C.byref(n_esc))
-        return dict(launches=n_launch.value, search_ms=dev_ms.value, fast_kernel_ms=fast_ms.value, regions=n_reg.value,
+        return dict(launches=n_launch.value, search_ms=dev_ms.value, micro_kernel_ms=fast_ms.value, regions=n_reg.value,
                     escalated=n_esc.value)
 
     def close(self):

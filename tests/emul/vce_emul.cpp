@@ -11,6 +11,10 @@
 #include <string>
 #include <vector>
 
+#include <atomic>
+#include <cstdlib>
+
+#include "../../rtg_tools_b200/csrc/vce_engine.h"
 #include "../../rtg_tools_b200/csrc/vce_orient.h"
 #include "../../rtg_tools_b200/csrc/vce_pipeline.h"
 
@@ -20,7 +24,34 @@ using namespace vce;
 class EmulBackend : public Backend {
  public:
   bool forceGeneral = false;
-  int setAlleles(int side, const AlleleTable& t) override { al_[side] = &t; return 0; }
+  std::atomic<int64_t> microRegions{0}, microClean{0};
+  // ---- thread-per-region path: the same MicroSearch source, one region after the other
+  void* hostAlloc(size_t bytes) override { return std::malloc(bytes); }
+  void hostFree(void* p) override { std::free(p); }
+  int microReset() override { return 0; }
+  int microUpload(MicroJob&) override { return 0; }
+  int microRun(MicroJob& j, const MicroConfig& mc) override {
+    std::vector<uint8_t> ws(MicroA::WS_BYTES + 16);
+    for (int q = 0; q < j.n; ++q) {
+      MicroSearch<MicroA> ms;
+      ms.ws = ws.data();
+      ms.cfg = mc;
+      const uint8_t* src = j.packets + (size_t) j.offsets[q] * 4;
+      std::memcpy(ws.data() + MicroA::OFF_PKT, src, (size_t) src[MP_NWORDS] * 4);
+      ms.runRegion(j.results + (size_t) q * j.resBytes);
+      if (j.results[(size_t) q * j.resBytes + MR_STATUS] == kMicroClean) ++microClean;
+    }
+    microRegions += j.n;
+    ++stats.launches;
+    return 0;
+  }
+  int microRunAll(std::vector<MicroJob*>& jobs, const MicroConfig& mc) override {
+    for (MicroJob* j : jobs) microRun(*j, mc);
+    return 0;
+  }
+  int microWait(MicroJob&) override { return 0; }
+
+  int setAlleles(int side, const AlleleTable& t) override { al_copy_[side] = t; al_[side] = &al_copy_[side]; return 0; }
 
   int uploadPass(PassData& pd) override { return resetPass(pd); }
   int resetPass(PassData& pd) override {
@@ -139,32 +170,59 @@ class EmulBackend : public Backend {
     g.aNull = al_[side]->aNull.data();
     return g;
   }
+  AlleleTable al_copy_[2];
   const AlleleTable* al_[2] = {nullptr, nullptr};
   std::vector<int32_t> oSlot_[2];
   std::vector<int32_t> sync_[2];
   std::string err_;
 };
 
-int g_gap = 1, g_margin = 24, g_forceGeneral = 0;
+int g_gap = 1, g_margin = 24, g_forceGeneral = 0, g_disableMicro = 0, g_threads = 3, g_chunk = 0;
 int64_t g_stats[8];
 }  // namespace
 
 extern "C" {
 void emul_set_options(int gap, int margin, int forceGeneral) { g_gap = gap; g_margin = margin; g_forceGeneral = forceGeneral; }
 // regions, escalated, spilled, prefixReruns, launches of the last emul_vce_submit
-void emul_get_stats(int64_t* out) { for (int i = 0; i < 5; ++i) out[i] = g_stats[i]; }
+void emul_get_stats(int64_t* out) { for (int i = 0; i < 7; ++i) out[i] = g_stats[i]; }
+
+// disableMicro: no thread-per-region kernel; threads: host worker threads; chunk: regions per chunk (0 = automatic)
+void emul_set_engine(int disableMicro, int threads, int chunk) { g_disableMicro = disableMicro; g_threads = threads; g_chunk = chunk; }
 
 int emul_vce_submit(const vce_config* cfg, int32_t n_seq, const vce_sequence* seqs, vce_sequence_result* results) {
   EmulBackend be;
   be.forceGeneral = g_forceGeneral != 0;
-  PipelineOptions opt;
+  WorkerPool pool(g_threads);
+  EngineOptions opt;
   opt.gap = g_gap;
   opt.margin = g_margin;
-  Pipeline pl(&be, opt);
-  const int rc = pl.run(*cfg, n_seq, seqs, results);
+  opt.forceGeneral = g_forceGeneral != 0;
+  opt.disableMicro = g_disableMicro != 0;
+  opt.chunkRegions = g_chunk;
+  int rc;
+  {
+    Engine en(&be, &pool, opt);
+    rc = en.run(*cfg, n_seq, seqs, results);
+    if (rc && !en.error().empty()) fprintf(stderr, "emul: %s\n", en.error().c_str());
+  }
   g_stats[0] = be.stats.regions; g_stats[1] = be.stats.escalated; g_stats[2] = be.stats.spilled;
-  g_stats[3] = be.stats.prefixReruns; g_stats[4] = be.stats.launches;
-  if (rc && !pl.error().empty()) fprintf(stderr, "emul: %s\n", pl.error().c_str());
+  g_stats[3] = be.stats.prefixReruns; g_stats[4] = be.stats.launches; g_stats[5] = be.microRegions.load(); g_stats[6] = be.microClean.load();
+  return rc;
+}
+
+// staged job on the emulation: prepare once, execute `runs` times, finish (exercises the re-runnable path)
+int emul_vce_job(const vce_config* cfg, int32_t n_seq, const vce_sequence* seqs, vce_sequence_result* results, int32_t runs) {
+  EmulBackend be;
+  WorkerPool pool(g_threads);
+  EngineOptions opt;
+  opt.gap = g_gap;
+  opt.margin = g_margin;
+  opt.chunkRegions = g_chunk;
+  Engine en(&be, &pool, opt);
+  int rc = en.prepare(*cfg, n_seq, seqs, true);
+  for (int i = 0; i < runs && !rc; ++i) rc = en.execute();
+  if (!rc) rc = en.finish(results);
+  if (rc && !en.error().empty()) fprintf(stderr, "emul: %s\n", en.error().c_str());
   return rc;
 }
 int emul_vce_roc(const vce_roc_in*, vce_roc_out*) { return VCE_ERR_UNSUPPORTED; }

@@ -50,4 +50,5 @@ class Hybrid:
 def emul_stats(emul):
     st = (ctypes.c_int64 * 8)()
     emul.lib.emul_get_stats(st)
-    return dict(regions=st[0], escalated=st[1], spilled=st[2], prefix_reruns=st[3], launches=st[4])
+    return dict(regions=st[0], escalated=st[1], spilled=st[2], prefix_reruns=st[3], launches=st[4], micro_regions=st[5],
+                micro_clean=st[6])

@@ -125,3 +125,48 @@ def test_product_library_does_not_contain_the_oracle_or_the_emulation():
     so = os.path.join(ROOT, "rtg_tools_b200", "csrc", "libvce.so")
     syms = subprocess.check_output(["nm", "-D", "--defined-only", so]).decode()
     assert "oracle_" not in syms and "emul_" not in syms
+
+
+# ------------------------------------------------------------------------------------------- thread-per-region path
+def test_thread_per_region_path_carries_the_bulk(emul, oracle):
+    """On a genome-like pair nearly every region must settle in the thread-per-region kernel (vce_micro.h)."""
+    seqs = synth.make_pair(4_000_000, n_chrom=2)
+    for name in ("default", "twopass", "squash", "phased", "calls_min_base", "no_prune"):
+        compare_results(oracle.submit(CONFIGS[name], seqs), emul.submit(CONFIGS[name], seqs), seqs, what=name)
+        st = emul_stats(emul)
+        assert st["micro_regions"] > 0.97 * st["regions"] / (2 if name == "twopass" else 1) * (1 if name != "twopass" else 1)
+        assert st["micro_clean"] > 0.95 * st["micro_regions"]
+
+
+def test_results_do_not_depend_on_threads_chunks_or_the_small_kernel(emul, oracle):
+    seqs = synth.make_pair(1_500_000, n_chrom=3) + fuzz_batch(77, n_seq=5)
+    want = oracle.submit(CONFIGS["twopass"], seqs)
+    try:
+        for disable, threads, chunk in ((0, 1, 0), (0, 4, 64), (0, 7, 1000), (1, 2, 0), (0, 2, 1)):
+            emul.lib.emul_set_engine(disable, threads, chunk)
+            compare_results(want, emul.submit(CONFIGS["twopass"], seqs), seqs, what="disable %d threads %d chunk %d" % (disable, threads, chunk))
+    finally:
+        emul.lib.emul_set_engine(0, 3, 0)
+
+
+def test_staged_job_is_rerunnable(emul, oracle):
+    """vce_job_*: prepare once (digest + upload), execute repeatedly (merges are undone between runs), finish."""
+    seqs = synth.make_pair(1_000_000, n_chrom=2) + fuzz_batch(5, n_seq=4)
+    f = emul.lib.emul_vce_job
+    f.restype = ctypes.c_int
+    for name in ("default", "twopass"):
+        cfg = CONFIGS[name]
+        want = oracle.submit(cfg, seqs)
+        for runs in (1, 3):
+            ccfg, cseqs, cres, results, keep = capi.Library.pack(cfg, seqs)
+            rc = f(ctypes.byref(ccfg), len(seqs), cseqs, cres, runs)
+            capi.Library.unpack(cres, results, keep)
+            assert rc == 0
+            compare_results(want, results, seqs, what="%s runs %d" % (name, runs))
+
+
+def test_split_mnps_give_multi_variant_regions():
+    seqs = synth.make_pair(3_000_000, n_chrom=1)
+    c = seqs[0].calls
+    starts = c.allele_start[1::3]
+    assert (np.diff(starts) == 1).sum() > 5, "adjacent SNPs of split MNPs should survive the generator"
