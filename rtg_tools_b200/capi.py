@@ -362,6 +362,12 @@ class Library:
             raise RuntimeError("%ssubmit failed: %s %s" % (self.prefix, ERR_NAMES.get(rc, rc), self.last_error()))
         return results
 
+    def submit_packed(self, packed) -> int:
+        """vce_submit on buffers packed once with Library.pack (the caller owns and reuses every input / output array,
+        as a JNI host would); returns the C return code.  Call Library.unpack(cres, results, keep) when done."""
+        ccfg, cseqs, cres, results, keep = packed
+        return self._submit(C.byref(ccfg), len(results), cseqs, cres)
+
     def roc(self, score, tp, fp, tp_raw, filter_mask=None, n_filters=1, ascending=False):
         """Returns (rows per filter: list of (threshold, cum_tp, cum_fp, cum_tp_raw) arrays, no_score count)."""
         score = np.ascontiguousarray(score, np.float64)

@@ -6,6 +6,7 @@
 // so that a steady-state vce_submit() pays no allocation; concurrent callers each get their own context and share
 // the host worker pool.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -55,7 +56,10 @@ Context* acquire(int& rc) {
   Context* c = new Context();
   c->device = dev;
   c->backend = std::move(be);
-  c->engine.reset(new vce::Engine(c->backend.get(), g_pool.get(), vce::EngineOptions()));
+  vce::EngineOptions opt;
+  if (const char* e = std::getenv("VCE_DISABLE_MICRO")) opt.disableMicro = std::atoi(e) != 0;   // diagnostics
+  if (const char* e = std::getenv("VCE_CHUNK_REGIONS")) opt.chunkRegions = std::atoi(e);
+  c->engine.reset(new vce::Engine(c->backend.get(), g_pool.get(), opt));
   return c;
 }
 

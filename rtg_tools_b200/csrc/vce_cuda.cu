@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -94,11 +95,64 @@ struct SearchParams {
   int maxChildren;
   int32_t* arena;        // general kernel only
   long long arenaWordsPerWarp;
-  int winSmemBytes;      // fast kernel: bytes of shared memory per warp for the reference window
+  int winSmemBytes;      // shared memory per warp for the reference window
+  FastShape fs;          // shared-memory kernel: capacities of the tier
+  int wordsPerWarp;      // shared-memory words per warp (whole layout)
+  int tabBytes;          // shared memory per warp for the region's tables
 };
 
 constexpr int kWarnPerRegion = 64;
 constexpr int kFastWarps = 8;
+
+// Copies the region's slices of the variant / orientation / allele tables into shared memory and points the search at
+// them (the pointers are re-based so that the search keeps indexing with the batch-wide indices).  The serial part of
+// the search is a chain of dependent table reads: from HBM each costs ~700 cycles, from shared memory ~30.
+// Returns false (nothing changed) when the slices do not fit `cap` bytes.
+__device__ bool stageTables(RegionSearch<DeviceWarp>& rs, const SideArrays* G, int H, uint8_t* buf, int cap, int lane) {
+  const RegionDesc& R = rs.R;
+  int need = 0;
+  int rows0[2], rowsN[2], nt0[2], ntN[2];
+  for (int side = 0; side < 2; ++side) {
+    const int first = side == 0 ? R.cFirst : R.bFirst, cnt = side == 0 ? R.cCount : R.bCount;
+    const int sl0 = side == 0 ? R.cSlot0 : R.bSlot0, slN = side == 0 ? R.cSlotN : R.bSlotN;
+    rows0[side] = cnt > 0 ? G[side].oOff[first] : 0;
+    rowsN[side] = cnt > 0 ? G[side].oOff[first + cnt] - rows0[side] : 0;
+    nt0[side] = slN > 0 ? G[side].aNtOff[sl0] : 0;
+    ntN[side] = slN > 0 ? G[side].aNtOff[sl0 + slN] - nt0[side] : 0;
+    need += cnt * 8 + (cnt + 1) * 4 + ((cnt + 3) & ~3);            // vStart, vEnd, oOff, vFlags
+    need += rowsN[side] * H * 4 + rowsN[side] * 4;                   // oSlot, oIds
+    need += slN * 8 + (slN + 1) * 4 + ((ntN[side] + 3) & ~3);        // aStart, aEnd, aNtOff, nt
+  }
+  if (need > cap) return false;
+  uint8_t* at = buf;
+  for (int side = 0; side < 2; ++side) {
+    const int first = side == 0 ? R.cFirst : R.bFirst, cnt = side == 0 ? R.cCount : R.bCount;
+    const int sl0 = side == 0 ? R.cSlot0 : R.bSlot0, slN = side == 0 ? R.cSlotN : R.bSlotN;
+    const SideArrays& g = G[side];
+    SideArrays& S = rs.S[side];
+    int32_t* vS = reinterpret_cast<int32_t*>(at); at += cnt * 4;
+    int32_t* vE = reinterpret_cast<int32_t*>(at); at += cnt * 4;
+    int32_t* oO = reinterpret_cast<int32_t*>(at); at += (cnt + 1) * 4;
+    int32_t* oS = reinterpret_cast<int32_t*>(at); at += rowsN[side] * H * 4;
+    int32_t* aS = reinterpret_cast<int32_t*>(at); at += slN * 4;
+    int32_t* aE = reinterpret_cast<int32_t*>(at); at += slN * 4;
+    int32_t* aN = reinterpret_cast<int32_t*>(at); at += (slN + 1) * 4;
+    int8_t* oI = reinterpret_cast<int8_t*>(at); at += rowsN[side] * 4;
+    uint8_t* vF = at; at += (cnt + 3) & ~3;
+    uint8_t* nt = at; at += (ntN[side] + 3) & ~3;
+    for (int i = lane; i < cnt; i += 32) { vS[i] = g.vStart[first + i]; vE[i] = g.vEnd[first + i]; vF[i] = g.vFlags[first + i]; }
+    for (int i = lane; i <= cnt; i += 32) oO[i] = cnt > 0 ? g.oOff[first + i] : 0;
+    for (int i = lane; i < rowsN[side] * H; i += 32) oS[i] = g.oSlot[(size_t) rows0[side] * H + i];
+    for (int i = lane; i < rowsN[side] * 4; i += 32) oI[i] = g.oIds[(size_t) rows0[side] * 4 + i];
+    for (int i = lane; i < slN; i += 32) { aS[i] = g.aStart[sl0 + i]; aE[i] = g.aEnd[sl0 + i]; }
+    for (int i = lane; i <= slN; i += 32) aN[i] = slN > 0 ? g.aNtOff[sl0 + i] : 0;
+    for (int i = lane; i < ntN[side]; i += 32) nt[i] = g.nt[nt0[side] + i];
+    S.vStart = vS - first; S.vEnd = vE - first; S.vFlags = vF - first; S.oOff = oO - first;
+    S.oSlot = oS - (ptrdiff_t) rows0[side] * H; S.oIds = oI - (ptrdiff_t) rows0[side] * 4;
+    S.aStart = aS - sl0; S.aEnd = aE - sl0; S.aNtOff = aN - sl0; S.nt = nt - nt0[side];
+  }
+  return true;
+}
 
 template <bool GENERAL>
 __global__ void __launch_bounds__(kFastWarps * 32) k_search(const __grid_constant__ SearchParams p) {
@@ -109,29 +163,30 @@ __global__ void __launch_bounds__(kFastWarps * 32) k_search(const __grid_constan
 
   RegionSearch<DeviceWarp> rs;
   rs.cfg = p.cfg;
-  rs.S[0] = p.S[0];
-  rs.S[1] = p.S[1];
   rs.warnOut = p.warnScratch + (size_t) gwarp * kWarnPerRegion;
   rs.warnCap = kWarnPerRegion;
   uint8_t* winS = nullptr;
+  uint8_t* tabS = nullptr;
   if (!GENERAL) {
-    rs.L.init(p.H, FastLimits::kQ, FastLimits::kMaxVarPerSide, FastLimits::kSMax, 4);
-    rs.maxChildren = FastLimits::kMaxChildren;
-    rs.cap = FastLimits::kCap;
-    rs.nSlots = FastLimits::kSlots;
-    rs.ordCap = FastLimits::kOrdCap;
+    rs.L.init(p.H, p.fs.q, p.fs.kv, p.fs.smax, 4);
+    rs.maxChildren = p.fs.maxChildren;
+    rs.cap = p.fs.cap;
+    rs.nSlots = p.fs.slots();
+    rs.ordCap = p.fs.ordCap();
     PathLayout LM;
-    LM.init(2, FastLimits::kQ, FastLimits::kMaxVarPerSide, FastLimits::kSMax, 4);
-    // ctl is padded so that the window that follows it (and the next warp's block) stays 16-byte aligned
-    const int preWords = (FastLimits::kSlots + 2) * LM.W + FastLimits::kOrdCap + FastLimits::kSlots;
-    const int ctlWords = ((preWords + 16 + 2 * FastLimits::kMaxChildren + 3) & ~3) - preWords;
-    const int wordsPerWarp = preWords + ctlWords + p.winSmemBytes / 4;
-    int32_t* base = smem + (size_t) warp * wordsPerWarp;
+    LM.init(2, p.fs.q, p.fs.kv, p.fs.smax, 4);
+    // ctl is padded so that what follows it (tables, window, the next warp's block) stays 16-byte aligned
+    const int preWords = (rs.nSlots + 2) * LM.W + rs.ordCap + rs.nSlots;
+    const int ctlWords = ((preWords + 16 + 2 * p.fs.maxChildren + 3) & ~3) - preWords;
+    int32_t* base = smem + (size_t) warp * p.wordsPerWarp;
     rs.slots = base;
-    rs.order = base + (FastLimits::kSlots + 2) * LM.W;
-    rs.freeList = rs.order + FastLimits::kOrdCap;
-    rs.ctl = rs.freeList + FastLimits::kSlots;
-    winS = reinterpret_cast<uint8_t*>(rs.ctl + ctlWords);
+    rs.order = base + (rs.nSlots + 2) * LM.W;
+    rs.freeList = rs.order + rs.ordCap;
+    rs.ctl = rs.freeList + rs.nSlots;
+    tabS = reinterpret_cast<uint8_t*>(rs.ctl + ctlWords);
+    winS = tabS + p.tabBytes;
+  } else {
+    tabS = reinterpret_cast<uint8_t*>(smem) + (size_t) warp * p.tabBytes;
   }
 
   while (true) {
@@ -141,6 +196,10 @@ __global__ void __launch_bounds__(kFastWarps * 32) k_search(const __grid_constan
     if (r >= p.nRegs) break;
     rs.R = p.regs[r];
     rs.regionId = r;
+    rs.S[0] = p.S[0];
+    rs.S[1] = p.S[1];
+    __syncwarp();
+    stageTables(rs, p.S, p.H, tabS, p.tabBytes, lane);
     if (GENERAL) {
       rs.L.init(p.H, rs.R.qMax, max(1, max(rs.R.cCount, rs.R.bCount)), rs.R.cCount + rs.R.bCount + 2, rs.R.decBits);
       rs.maxChildren = p.maxChildren;
@@ -173,8 +232,8 @@ __global__ void __launch_bounds__(kFastWarps * 32) k_search(const __grid_constan
       } else {
         rs.win = gw;
       }
-      __syncwarp();
     }
+    __syncwarp();
     int resultSlot = -1;
     const int st = rs.run(resultSlot);
     RegionResult rr;
@@ -188,6 +247,9 @@ __global__ void __launch_bounds__(kFastWarps * 32) k_search(const __grid_constan
     rr.pad = 0;
     __syncwarp();
     if (st == kRegionClean || st == kRegionFinished) {
+      // results go to the batch-wide output arrays: restore the un-staged output pointers
+      rs.S[0].outDecision = p.S[0].outDecision; rs.S[0].outWeight = p.S[0].outWeight;
+      rs.S[1].outDecision = p.S[1].outDecision; rs.S[1].outWeight = p.S[1].outWeight;
       rs.writeResults(resultSlot, p.syncOut + p.syncOff[r], &rr);
       if (lane == 0 && rs.nWarn > 0) {
         const int nw = min(rs.nWarn, kWarnPerRegion);
@@ -199,7 +261,6 @@ __global__ void __launch_bounds__(kFastWarps * 32) k_search(const __grid_constan
     __syncwarp();
   }
 }
-
 
 // ------------------------------------------------------------------------------------------------ K1+K2+K3, one region per thread
 // Thread-per-region search (vce_micro.h).  Every lane owns a shared-memory slice; a lane that settles its region
@@ -335,6 +396,7 @@ class CudaBackend : public Backend {
     CUDA_TRY(cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_));
     maxSmemOptin_ = maxSmem;
     CUDA_TRY(cudaFuncSetAttribute(k_search<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+    CUDA_TRY(cudaFuncSetAttribute(k_search<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * kFastWarps));
     CUDA_TRY(cudaFuncSetAttribute(k_micro<MicroA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMicroThreads * MicroA::WS_BYTES));
     for (int i = 0; i < kMicroLanes; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&mStream_[i], cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&evM0_));
@@ -498,8 +560,9 @@ class CudaBackend : public Backend {
   }
 
   int search(PassData& pd, const SearchConfig& sc, const std::vector<RegionDesc>& regs, const std::vector<uint8_t>& windows,
-             bool general, bool staged, std::vector<RegionResult>& out, const std::vector<int32_t>& syncOff, size_t syncTotal,
+             int tier, bool staged, std::vector<RegionResult>& out, const std::vector<int32_t>& syncOff, size_t syncTotal,
              std::vector<WarnRec>& warns) override {
+    const bool general = tier >= kTierGeneral;
     CUDA_TRY(cudaSetDevice(device_));
     curPass_ = pd.pass;
     const size_t nr = regs.size();
@@ -536,19 +599,27 @@ class CudaBackend : public Backend {
     int blocks = 0, threads = kFastWarps * 32;
     size_t smemBytes = 0;
     if (!general) {
+      const FastShape fs = fastShape(tier);
+      sp.fs = fs;
       PathLayout LM;
-      LM.init(2, FastLimits::kQ, FastLimits::kMaxVarPerSide, FastLimits::kSMax, 4);
-      const int preWords = (FastLimits::kSlots + 2) * LM.W + FastLimits::kOrdCap + FastLimits::kSlots;
-      const int ctlWords = ((preWords + 16 + 2 * FastLimits::kMaxChildren + 3) & ~3) - preWords;
+      LM.init(2, fs.q, fs.kv, fs.smax, 4);
+      const int preWords = (fs.slots() + 2) * LM.W + fs.ordCap() + fs.slots();
+      const int ctlWords = ((preWords + 16 + 2 * fs.maxChildren + 3) & ~3) - preWords;
       sp.winSmemBytes = 256;
-      const size_t wordsPerWarp = (size_t) preWords + ctlWords + sp.winSmemBytes / 4;
-      smemBytes = wordsPerWarp * 4 * kFastWarps;
-      if ((int) smemBytes > maxSmemOptin_) { err_ = "fast kernel shared memory exceeds the device limit"; return VCE_ERR_CUDA; }
+      sp.tabBytes = fs.tabBytes;
+      sp.wordsPerWarp = preWords + ctlWords + (sp.tabBytes + sp.winSmemBytes) / 4;
+      const size_t bytesPerWarp = (size_t) sp.wordsPerWarp * 4;
+      int warpsPerBlock = (int) std::min<size_t>(kFastWarps, (size_t) maxSmemOptin_ / bytesPerWarp);
+      if (warpsPerBlock < 1) { err_ = "fast kernel shared memory exceeds the device limit"; return VCE_ERR_CUDA; }
+      // prefer several smaller blocks per SM over one large one
+      if (warpsPerBlock < kFastWarps) warpsPerBlock = std::max(1, (int) ((size_t) maxSmemOptin_ / bytesPerWarp) / 2);
+      threads = warpsPerBlock * 32;
+      smemBytes = bytesPerWarp * warpsPerBlock;
       int perSm = 0;
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_search<false>, threads, smemBytes));
       if (perSm < 1) perSm = 1;
       blocks = smCount_ * perSm;
-      const int need = (int) ((nr + kFastWarps - 1) / kFastWarps);
+      const int need = (int) ((nr + warpsPerBlock - 1) / warpsPerBlock);
       if (blocks > need) blocks = need;
     } else {
       // per-warp arena sized for the largest record layout in this launch at the full search budget
@@ -567,12 +638,14 @@ class CudaBackend : public Backend {
       CUDA_TRY(arena_.ensure(totalWords));
       sp.arena = arena_.p;
       sp.arenaWordsPerWarp = words;
+      sp.tabBytes = 4096;
+      smemBytes = (size_t) sp.tabBytes * kFastWarps;
     }
     CUDA_TRY(warnScratch_.ensure((size_t) blocks * kFastWarps * kWarnPerRegion));
     sp.warnScratch = warnScratch_.p;
 
     CUDA_TRY(cudaEventRecord(ev0_, stream_));
-    if (general) k_search<true><<<blocks, threads, 0, stream_>>>(sp);
+    if (general) k_search<true><<<blocks, threads, smemBytes, stream_>>>(sp);
     else k_search<false><<<blocks, threads, smemBytes, stream_>>>(sp);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(ev1_, stream_));
@@ -586,6 +659,9 @@ class CudaBackend : public Backend {
     CUDA_TRY(cudaEventElapsedTime(&ms, ev0_, ev1_));
     stats.searchMs += ms;
     stats.d2hBytes += (int64_t) (nr * sizeof(RegionResult));
+    if (std::getenv("VCE_TIMING")) {
+      fprintf(stderr, "[vce]     k_search tier %d: %d blocks x %d threads, %zu B shared memory per block\n", tier, blocks, threads, smemBytes);
+    }
     if (!general && (long long) nr >= lastFastRegions_) {
       lastFastMs_ = ms;
       lastFastRegions_ = (long long) nr;

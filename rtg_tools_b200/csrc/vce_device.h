@@ -47,6 +47,8 @@ struct RegionDesc {
   int32_t layoutW;        // words per path state (general kernel) -- see PathLayout
   int32_t qMax;           // pending-allele queue capacity per haplotype
   int32_t decBits;        // bits per include/exclude decision (4 or 8)
+  int32_t cSlot0, cSlotN; // allele slots [cSlot0, cSlot0 + cSlotN) of the call side hold every allele of the region's calls
+  int32_t bSlot0, bSlotN; // same for baseline (the kernels stage these ranges into shared memory)
 };
 
 // Per-region result header.

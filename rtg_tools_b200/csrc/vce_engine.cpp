@@ -10,9 +10,24 @@
 
 #include "vce_orient.h"
 
+#include <chrono>
+
 namespace vce {
 
 namespace {
+// VCE_TIMING=1: stage durations on stderr
+struct StageTimer {
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  StageTimer() : on(std::getenv("VCE_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+  void lap(const char* what) {
+    if (!on) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[vce] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
 const int kDummyPrefix = 0;  // "some baseline variant was included earlier, allele id unknown": the common case
 
 // Upper bound on the number of orientations any variant of a pass can have (Orientor.java), used to size child
@@ -84,17 +99,35 @@ void Engine::arenaReset() {
 }
 
 // ------------------------------------------------------------------------------------------- pass set-up
+namespace {
+template <class V> void ensureSize(V& v, size_t n) { if (v.size() < n) v.resize(n); }
+}  // namespace
+
+void Engine::resetPass(PassCtx& pc) {  // forget the contents, keep the memory
+  pc.chunks.clear();
+  pc.wideSync.clear();
+  pc.warns.clear();
+  pc.rare.clear();
+  pc.undo.clear();
+  pc.launched = false;
+  pc.gtPloidy[0] = pc.gtPloidy[1] = 0;
+  for (int side = 0; side < 2; ++side) {
+    pc.ss[side].clear();
+    for (auto& v : pc.idxStore[side]) v.clear();
+  }
+}
+
 int Engine::setupPass0() {
   PassCtx& pc = pass_[0];
-  pc = PassCtx();
+  resetPass(pc);
   pc.pass = 0;
   pc.H = cfg_.ploidy[0];
   pc.kind[0] = cfg_.calls_orientor[0];
   pc.kind[1] = cfg_.baseline_orientor[0];
   pc.shortCircuit.assign(nSeq_, 0);
   for (int side = 0; side < 2; ++side) {
-    pc.ss[side].resize(nSeq_);
-    pc.idxStore[side].resize(nSeq_);
+    pc.ss[side].assign(nSeq_, SideSeq());
+    ensureSize(pc.idxStore[side], (size_t) nSeq_);
   }
   int32_t tot[2] = {0, 0};
   for (int k = 0; k < nSeq_; ++k) {
@@ -112,11 +145,12 @@ int Engine::setupPass0() {
     }
   }
   for (int side = 0; side < 2; ++side) {
-    pc.vStart[side].resize(tot[side]);
-    pc.vEnd[side].resize(tot[side]);
-    pc.decision[side].assign(tot[side], 0);
+    // every variant belongs to exactly one settled region, whose results overwrite these: no clearing needed
+    ensureSize(pc.vStart[side], (size_t) tot[side]);
+    ensureSize(pc.vEnd[side], (size_t) tot[side]);
+    ensureSize(pc.decision[side], (size_t) tot[side]);
   }
-  pc.weight.assign(tot[0], 0.0);
+  ensureSize(pc.weight, (size_t) tot[0]);
   computeBounds(pc);
   return VCE_OK;
 }
@@ -188,7 +222,7 @@ void Engine::computeBounds(PassCtx& pc) {
 int Engine::setupPass1() {
   const PassCtx& p0 = pass_[0];
   PassCtx& pc = pass_[1];
-  pc = PassCtx();
+  resetPass(pc);
   pc.pass = 1;
   pc.H = cfg_.ploidy[1];
   pc.kind[0] = cfg_.calls_orientor[1];
@@ -197,8 +231,8 @@ int Engine::setupPass1() {
   pc.gtPloidy[0] = p0.gtPloidy[0];
   pc.gtPloidy[1] = p0.gtPloidy[1];
   for (int side = 0; side < 2; ++side) {
-    pc.ss[side].resize(nSeq_);
-    pc.idxStore[side].resize(nSeq_);
+    pc.ss[side].assign(nSeq_, SideSeq());
+    ensureSize(pc.idxStore[side], (size_t) nSeq_);
     // Path.getCalledExcluded / getBaselineExcluded of the first pass, per sequence
     pool_->parallelFor(nSeq_, [&](int k, int) {
       const SideSeq& a = p0.ss[side][k];
@@ -215,10 +249,10 @@ int Engine::setupPass1() {
       s.n = (int32_t) pc.idxStore[side][k].size();
       tot += s.n;
     }
-    pc.vStart[side].resize(tot);
-    pc.vEnd[side].resize(tot);
-    pc.decision[side].assign(tot, 0);
-    if (side == 0) pc.weight.assign(tot, 0.0);
+    ensureSize(pc.vStart[side], (size_t) tot);
+    ensureSize(pc.vEnd[side], (size_t) tot);
+    ensureSize(pc.decision[side], (size_t) tot);
+    if (side == 0) ensureSize(pc.weight, (size_t) tot);
     pool_->parallelFor(nSeq_, [&](int k, int) {
       const SideSeq& a = p0.ss[side][k];
       SideSeq& s = pc.ss[side][k];
@@ -240,35 +274,127 @@ int Engine::setupPass1() {
 }
 
 // ------------------------------------------------------------------------------------------- regions
-void Engine::splitSequence(PassCtx& pc, int k) {
-  std::vector<RegRange>& out = pc.rr[k];
-  out.clear();
-  if (pc.shortCircuit[k]) return;
-  const SideSeq& C = pc.ss[0][k];
-  const SideSeq& B = pc.ss[1][k];
+// Splits calls [i, ie) and baseline [j, je) (pass-wide indices, merged by start, calls first on ties) into runs
+// separated by a gap; `maxEnd` carries the largest variant end seen before the slice (LONG_MIN = nothing).
+// *continues is set when the first run of the slice is not separated from what came before.
+void Engine::splitSlice(const PassCtx& pc, int i, int ie, int j, int je, long maxEnd, std::vector<RegRange>& out, bool* continues) const {
   const int32_t* cs = pc.vStart[0].data();
   const int32_t* ce = pc.vEnd[0].data();
   const int32_t* bs = pc.vStart[1].data();
   const int32_t* bee = pc.vEnd[1].data();
-  int i = C.first, j = B.first;
-  const int ie = C.first + C.n, je = B.first + B.n;
   const long gap = std::max(1, opt_.gap);
-  out.reserve((size_t) std::max(C.n, B.n) + 16);
+  bool firstRun = true;
   do {
     RegRange g{i, 0, j, 0};
-    long maxEnd = LONG_MIN;
+    bool any = false;
+    if (!firstRun) maxEnd = LONG_MIN;  // a new run starts after a gap
     while (i < ie || j < je) {
       const bool takeC = j >= je || (i < ie && cs[i] <= bs[j]);
       const int s = takeC ? cs[i] : bs[j];
       const int e = takeC ? ce[i] : bee[j];
-      if (maxEnd != LONG_MIN && (long) s >= maxEnd + gap) break;
+      if (maxEnd != LONG_MIN && (long) s >= maxEnd + gap) {
+        if (any) break;
+        maxEnd = LONG_MIN;  // the slice itself starts with a gap: its first run is a fresh region
+      } else if (!any && firstRun && maxEnd != LONG_MIN && continues) {
+        *continues = true;
+      }
+      any = true;
       maxEnd = std::max(maxEnd, (long) e);
       if (takeC) ++i; else ++j;
     }
     g.cCount = i - g.cFirst;
     g.bCount = j - g.bFirst;
     out.push_back(g);
+    firstRun = false;
   } while (i < ie || j < je);
+}
+
+void Engine::splitAll(PassCtx& pc) {
+  ensureSize(pc.rr, (size_t) nSeq_);
+  ensureSize(pc.rs, (size_t) nSeq_);
+  ensureSize(pc.rcls, (size_t) nSeq_);
+  struct Seg { int seq, i, ie, j, je; long maxEndLocal, carry; bool continues; std::vector<RegRange> out; };
+  std::vector<Seg> segs;
+  std::vector<int> segFirst(nSeq_ + 1, 0);
+  const int per = std::max(1, opt_.splitSegment);
+  for (int k = 0; k < nSeq_; ++k) {
+    segFirst[k] = (int) segs.size();
+    if (pc.shortCircuit[k]) continue;
+    const SideSeq& C = pc.ss[0][k];
+    const SideSeq& B = pc.ss[1][k];
+    const int total = C.n + B.n;
+    const int nSeg = std::max(1, std::min(4096, total / per));
+    // cut by template position: quantiles of the larger side
+    const int side = C.n >= B.n ? 0 : 1;
+    const SideSeq& big = side == 0 ? C : B;
+    const int32_t* cs = pc.vStart[0].data() + C.first;
+    const int32_t* bs = pc.vStart[1].data() + B.first;
+    int pi = 0, pj = 0;
+    for (int sgi = 1; sgi <= nSeg; ++sgi) {
+      int ni = C.n, nj = B.n;
+      if (sgi < nSeg) {
+        const int32_t cut = pc.vStart[side][big.first + (int) ((int64_t) big.n * sgi / nSeg)];
+        ni = (int) (std::lower_bound(cs, cs + C.n, cut) - cs);
+        nj = (int) (std::lower_bound(bs, bs + B.n, cut) - bs);
+        ni = std::max(ni, pi);
+        nj = std::max(nj, pj);
+      }
+      if (sgi == nSeg || ni > pi || nj > pj) {
+        Seg sg{k, C.first + pi, C.first + ni, B.first + pj, B.first + nj, LONG_MIN, LONG_MIN, false, {}};
+        segs.push_back(std::move(sg));
+        pi = ni;
+        pj = nj;
+      }
+    }
+  }
+  segFirst[nSeq_] = (int) segs.size();
+  // phase 1: largest variant end per segment
+  pool_->parallelFor((int) segs.size(), [&](int t, int) {
+    Seg& sg = segs[t];
+    long m = LONG_MIN;
+    const int32_t* ce = pc.vEnd[0].data();
+    const int32_t* be2 = pc.vEnd[1].data();
+    for (int v = sg.i; v < sg.ie; ++v) m = std::max(m, (long) ce[v]);
+    for (int v = sg.j; v < sg.je; ++v) m = std::max(m, (long) be2[v]);
+    sg.maxEndLocal = m;
+  });
+  for (int k = 0; k < nSeq_; ++k) {
+    long carry = LONG_MIN;
+    for (int t = segFirst[k]; t < segFirst[k + 1]; ++t) {
+      segs[t].carry = carry;
+      carry = std::max(carry, segs[t].maxEndLocal);
+    }
+  }
+  // phase 2: split every segment with the carried maximum end
+  pool_->parallelFor((int) segs.size(), [&](int t, int) {
+    Seg& sg = segs[t];
+    sg.out.reserve((size_t) std::max(sg.ie - sg.i, sg.je - sg.j) + 16);
+    const bool firstOfSeq = t == segFirst[sg.seq];
+    splitSlice(pc, sg.i, sg.ie, sg.j, sg.je, sg.carry, sg.out, firstOfSeq ? nullptr : &sg.continues);
+  });
+  // phase 3: stitch per sequence
+  pool_->parallelFor(nSeq_, [&](int k, int) {
+    std::vector<RegRange>& out = pc.rr[k];
+    out.clear();
+    if (!pc.shortCircuit[k]) {
+      size_t total = 0;
+      for (int t = segFirst[k]; t < segFirst[k + 1]; ++t) total += segs[t].out.size();
+      out.reserve(total + 1);
+      for (int t = segFirst[k]; t < segFirst[k + 1]; ++t) {
+        const Seg& sg = segs[t];
+        size_t from = 0;
+        if (sg.continues && !out.empty() && !sg.out.empty()) {
+          out.back().cCount += sg.out[0].cCount;
+          out.back().bCount += sg.out[0].bCount;
+          from = 1;
+        }
+        out.insert(out.end(), sg.out.begin() + (long) from, sg.out.end());
+      }
+    }
+    pc.rs[k].resize(out.size());
+    pc.rcls[k].assign(out.size(), 0);
+    if (!out.empty()) std::memset(pc.rs[k].data(), 0, out.size() * sizeof(RegRes));
+  });
 }
 
 int Engine::regionStartPos(const PassCtx& pc, int k, int j) const {
@@ -340,8 +466,7 @@ int Engine::buildPacket(const PassCtx& pc, int k, int j, uint8_t* out) const {
   const long winLen = winEnd - winStart;
   if (winLen < 1 || winLen > kMicroMaxWin) return 0;
 
-  uint8_t bits[64];
-  std::memset(bits, 0, sizeof(bits));
+  uint8_t raw[256 + 8];   // allele bases then window bases, one per byte; packed to 2 bits at the end
   int nBases = 0;
   uint8_t alleles[4 * T::KV * MA_BYTES];
   int nAl = 0;
@@ -370,11 +495,7 @@ int Engine::buildPacket(const PassCtx& pc, int k, int j, uint8_t* out) const {
         const int len = in.allele_nt_off[slot + 1] - nb;
         if (st < 0 || en < st || en > kMicroMaxWin || len > kMicroMaxWin || nBases + len + winLen > 255) return 0;
         const uint8_t* nt = in.nt + nb;
-        for (int q = 0; q < len; ++q) {
-          const unsigned b = (unsigned) nt[q] - 1u;
-          if (b > 3u) return 0;  // N or the explicit-unknown token: not representable in 2 bits
-          bits[(nBases + q) >> 2] |= (uint8_t) (b << (((nBases + q) & 3) * 2));
-        }
+        for (int q = 0; q < len; ++q) raw[nBases + q] = nt[q];
         uint8_t* a = alleles + nAl * MA_BYTES;
         a[MA_START] = (uint8_t) st; a[MA_END] = (uint8_t) en; a[MA_NT] = (uint8_t) nBases; a[MA_LEN] = (uint8_t) len;
         nBases += len;
@@ -391,18 +512,20 @@ int Engine::buildPacket(const PassCtx& pc, int k, int j, uint8_t* out) const {
       vout += MV_BYTES;
     }
   }
-  const uint8_t* tb = seqs_[k].template_bases + winStart;
-  for (int q = 0; q < (int) winLen; ++q) {
-    const unsigned b = (unsigned) tb[q] - 1u;
-    if (b > 3u) return 0;
-    bits[(nBases + q) >> 2] |= (uint8_t) (b << (((nBases + q) & 3) * 2));
-  }
   const int winBase = nBases;
+  std::memcpy(raw + nBases, seqs_[k].template_bases + winStart, (size_t) winLen);
   nBases += (int) winLen;
+  raw[nBases] = raw[nBases + 1] = raw[nBases + 2] = 1;  // padding of the last 2-bit byte
   std::memcpy(vout, alleles, (size_t) nAl * MA_BYTES);
   uint8_t* bout = vout + nAl * MA_BYTES;
   const int nb2 = (nBases + 3) >> 2;
-  std::memcpy(bout, bits, (size_t) nb2);
+  unsigned bad = 0;
+  for (int q = 0; q < nb2; ++q) {
+    const unsigned b0 = raw[4 * q] - 1u, b1 = raw[4 * q + 1] - 1u, b2 = raw[4 * q + 2] - 1u, b3 = raw[4 * q + 3] - 1u;
+    bad |= b0 | b1 | b2 | b3;  // N (0) wraps to 0xffffffff, the explicit-unknown token 5 gives 4: neither fits 2 bits
+    bout[q] = (uint8_t) ((b0 & 3u) | ((b1 & 3u) << 2) | ((b2 & 3u) << 4) | ((b3 & 3u) << 6));
+  }
+  if (bad > 3u) return 0;
   int bytes = (int) (bout + nb2 - out);
   while (bytes & 3) out[bytes++] = 0;
   if (bytes > T::PKT_MAX) return 0;
@@ -422,7 +545,13 @@ int Engine::buildPacket(const PassCtx& pc, int k, int j, uint8_t* out) const {
   return bytes;
 }
 
+static std::atomic<long long> g_tBuild(0), g_tCopy(0), g_tUpload(0);
+static inline long long nowNs() {
+  return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 int Engine::buildChunk(PassCtx& pc, Chunk& ch, int worker, bool launch) {
+  const long long tA = nowNs();
   const int k = ch.seq;
   std::vector<uint8_t>& sc = scratch_[worker];
   std::vector<uint32_t>& so = scratchOff_[worker];
@@ -436,7 +565,17 @@ int Engine::buildChunk(PassCtx& pc, Chunk& ch, int worker, bool launch) {
   uint8_t* cls = pc.rcls[k].data();
   RegRes* rs = pc.rs[k].data();
   int np = 0;
+  const RegRange* rrk = pc.rr[k].data();
+  const uint8_t* tmpl = seqs_[k].template_bases;
+  const int nReg = (int) pc.rr[k].size();
+  const int32_t* cs = pc.vStart[0].data();
+  const int32_t* bs = pc.vStart[1].data();
   for (int j = ch.r0; j < ch.r1; ++j) {
+    if (j + 12 < nReg) {  // the reference window of a region is a cache miss: request it well ahead
+      const RegRange& f = rrk[j + 12];
+      const int32_t pos = f.cCount > 0 ? cs[f.cFirst] : (f.bCount > 0 ? bs[f.bFirst] : 0);
+      __builtin_prefetch(tmpl + (pos > 0 ? pos - 1 : 0));
+    }
     int bytes = 0;
     if (pc.microOk) bytes = buildPacket<MicroA>(pc, k, j, sc.data() + at);
     if (bytes > 0) {
@@ -451,6 +590,8 @@ int Engine::buildChunk(PassCtx& pc, Chunk& ch, int worker, bool launch) {
       rs[j].state = RS_RESIDUAL;
     }
   }
+  const long long tB = nowNs();
+  g_tBuild += tB - tA;
   MicroJob& job = ch.job;
   job = MicroJob();
   job.cls = 0;
@@ -471,8 +612,11 @@ int Engine::buildChunk(PassCtx& pc, Chunk& ch, int worker, bool launch) {
   job.packetBytes = at;
   job.offsets = reinterpret_cast<const uint32_t*>(off);
   job.results = res;
+  const long long tC = nowNs();
+  g_tCopy += tC - tB;
   int rc = be_->microUpload(job);
   if (rc == VCE_OK && launch) rc = be_->microRun(job, pc.mc);
+  g_tUpload += nowNs() - tC;
   if (rc) {
     std::lock_guard<std::mutex> lk(errMu_);
     err_ = be_->lastError();
@@ -527,13 +671,16 @@ int Engine::prepare(const vce_config& cfg, int32_t nSeq, const vce_sequence* seq
   for (int p = 0; p < cfg.n_passes; ++p) {
     if (cfg.ploidy[p] < 1 || cfg.ploidy[p] > VCE_MAX_PLOIDY) { err_ = "ploidy out of range"; return VCE_ERR_BAD_ARGUMENT; }
   }
+  StageTimer tm;
   arenaReset();
   int rc = be_->microReset();
   if (rc) { err_ = be_->lastError(); return rc; }
   if ((rc = setupPass0())) return rc;
+  tm.lap("bounds + order check");
   if (staged) {  // digest + upload now, so that execute() starts with everything resident in HBM
     PassCtx& pc = pass_[0];
     if ((rc = runChunks(pc))) return rc;
+    tm.lap("split into regions");
     std::atomic<int> failed(0);
     pool_->parallelFor((int) pc.chunks.size(), [&](int t, int worker) {
       if (failed.load()) return;
@@ -541,6 +688,11 @@ int Engine::prepare(const vce_config& cfg, int32_t nSeq, const vce_sequence* seq
       if (r) failed.store(r);
     });
     if (failed.load()) return failed.load();
+    tm.lap("packets + upload");
+    if (tm.on) {
+      std::fprintf(stderr, "[vce]   summed over workers: build %.1f ms, copy to page-locked %.1f ms, upload calls %.1f ms\n",
+                   g_tBuild.exchange(0) / 1e6, g_tCopy.exchange(0) / 1e6, g_tUpload.exchange(0) / 1e6);
+    }
     staged_ = true;
   }
   return VCE_OK;
@@ -568,9 +720,6 @@ void Engine::resetPassRun(PassCtx& pc) {
 
 int Engine::runChunks(PassCtx& pc) {
   // split (per sequence), plan, build + upload + start
-  pc.rr.assign(nSeq_, std::vector<RegRange>());
-  pc.rs.assign(nSeq_, std::vector<RegRes>());
-  pc.rcls.assign(nSeq_, std::vector<uint8_t>());
   pc.microOk = !opt_.disableMicro && !opt_.forceGeneral && orientorPairMicro(pc.kind[0], pc.kind[1], pc.H);
   pc.mc.H = pc.H;
   pc.mc.kind[0] = pc.kind[0];
@@ -579,26 +728,14 @@ int Engine::runChunks(PassCtx& pc) {
   pc.mc.maxIterations = cfg_.max_iterations;
   pc.mc.pruneNoOps = cfg_.prune_no_ops;
   pc.mc.preference = cfg_.preference;
-  // largest sequences first
-  std::vector<int> order(nSeq_);
-  for (int k = 0; k < nSeq_; ++k) order[k] = k;
-  std::sort(order.begin(), order.end(), [&](int a, int b) {
-    const int na = pc.ss[0][a].n + pc.ss[1][a].n, nb = pc.ss[0][b].n + pc.ss[1][b].n;
-    return na != nb ? na > nb : a < b;
-  });
-  pool_->parallelFor(nSeq_, [&](int t, int) {
-    const int k = order[t];
-    splitSequence(pc, k);
-    pc.rs[k].resize(pc.rr[k].size());
-    pc.rcls[k].assign(pc.rr[k].size(), 0);
-    if (!pc.rs[k].empty()) std::memset(pc.rs[k].data(), 0, pc.rs[k].size() * sizeof(RegRes));
-  });
+  splitAll(pc);
   planChunks(pc);
   return VCE_OK;
 }
 
 int Engine::execute() {
   int rc;
+  StageTimer tm;
   microMs = 0;
   microRegions = microVariants = 0;
   for (int p = 0; p < cfg_.n_passes; ++p) {
@@ -606,15 +743,22 @@ int Engine::execute() {
     const bool rerun = p == 0 && staged_;
     if (p == 1) {
       if ((rc = setupPass1())) return rc;
+      tm.lap("pass 2 set-up");
     }
     std::atomic<int> failed(0);
     if (!rerun) {
       if ((rc = runChunks(pc))) return rc;
+      tm.lap("split into regions");
       pool_->parallelFor((int) pc.chunks.size(), [&](int t, int worker) {
         if (failed.load()) return;
         const int r = buildChunk(pc, pc.chunks[t], worker, true);
         if (r) failed.store(r);
       });
+      tm.lap("packets + upload + launch");
+      if (tm.on) {
+        std::fprintf(stderr, "[vce]   summed over workers: build %.1f ms, copy to page-locked %.1f ms, upload+launch calls %.1f ms\n",
+                     g_tBuild.exchange(0) / 1e6, g_tCopy.exchange(0) / 1e6, g_tUpload.exchange(0) / 1e6);
+      }
     } else {
       if (executed_) resetPassRun(pc);
       std::vector<MicroJob*> jobs;
@@ -635,6 +779,7 @@ int Engine::execute() {
       decodeChunk(pc, ch, iters[worker]);
     });
     if (failed.load()) { err_ = be_->lastError(); return failed.load(); }
+    tm.lap("wait + decode");
     for (int64_t v : iters) be_->stats.iterations += v;
     for (const Chunk& ch : pc.chunks) {
       be_->stats.regions += ch.r1 - ch.r0;
@@ -642,6 +787,7 @@ int Engine::execute() {
       microVariants += ch.variants;
     }
     if ((rc = settle(pc))) return rc;
+    tm.lap("settle residual");
   }
   executed_ = true;
   return VCE_OK;
@@ -657,9 +803,13 @@ int Engine::run(const vce_config& cfg, int32_t nSeq, const vce_sequence* seqs, v
 // ------------------------------------------------------------------------------------------- warp-per-region path
 // Runs the regions `ids` through the warp-per-region kernels (vce_search.h).  The variants and alleles of just these
 // regions are packed into compact arrays, so that the cost is proportional to the residual, not to the batch.
-int Engine::wideLaunch(PassCtx& pc, const std::vector<RegKey>& ids, bool general, std::vector<int>& statusOut) {
+int Engine::startTier(const PassCtx& pc, const RegRange& g) const { return fastEligible(pc, g) ? 0 : kTierGeneral; }
+
+int Engine::wideLaunch(PassCtx& pc, const std::vector<RegKey>& ids, int tier, std::vector<int>& statusOut) {
   statusOut.assign(ids.size(), kRegionPending);
   if (ids.empty()) return VCE_OK;
+  StageTimer tmw;
+  bool general = tier >= kTierGeneral;
   PassData pd;
   pd.pass = pc.pass;
   pd.H = pc.H;
@@ -670,6 +820,18 @@ int Engine::wideLaunch(PassCtx& pc, const std::vector<RegKey>& ids, bool general
   std::vector<int32_t> syncOff(ids.size());
   size_t so = 0;
   int maxSl[2] = {2, 2};
+  {
+    size_t nvar[2] = {0, 0};
+    for (const RegKey& id : ids) { nvar[0] += pc.rr[id.seq][id.j].cCount; nvar[1] += pc.rr[id.seq][id.j].bCount; }
+    for (int side = 0; side < 2; ++side) {
+      HostSide& hs = pd.side[side];
+      hs.vStart.reserve(nvar[side]); hs.vEnd.reserve(nvar[side]); hs.slot0.reserve(nvar[side]); hs.nSl.reserve(nvar[side]);
+      hs.vFlags.reserve(nvar[side]); hs.gt.reserve(nvar[side] * 4); hs.inputIdx.reserve(nvar[side]);
+      at[side].aStart.reserve(nvar[side] * 3 + 8); at[side].aEnd.reserve(nvar[side] * 3 + 8);
+      at[side].aNull.reserve(nvar[side] * 3 + 8); at[side].aNtOff.reserve(nvar[side] * 3 + 8);
+      at[side].nt.reserve(nvar[side] * 4 + 64);
+    }
+  }
   for (size_t q = 0; q < ids.size(); ++q) {
     const int k = ids[q].seq, j = ids[q].j;
     const RegRange& g = pc.rr[k][j];
@@ -689,6 +851,7 @@ int Engine::wideLaunch(PassCtx& pc, const std::vector<RegKey>& ids, bool general
       AlleleTable& t = at[side];
       (side == 0 ? d.cFirst : d.bFirst) = (int32_t) hs.vStart.size();
       (side == 0 ? d.cCount : d.bCount) = count[side];
+      (side == 0 ? d.cSlot0 : d.bSlot0) = (int32_t) t.aStart.size();
       const int e = first[side] + count[side];
       (side == 0 ? d.cNextStart : d.bNextStart) = e < s.first + s.n ? pc.vStart[side][e] : kNoNext;
       for (int v = first[side]; v < e; ++v) {
@@ -717,6 +880,7 @@ int Engine::wideLaunch(PassCtx& pc, const std::vector<RegKey>& ids, bool general
         }
         t.nt.insert(t.nt.end(), in.nt + nb0, in.nt + in.allele_nt_off[off0 + nSl]);
       }
+      (side == 0 ? d.cSlotN : d.bSlotN) = (int32_t) t.aStart.size() - (side == 0 ? d.cSlot0 : d.bSlot0);
     }
     d.startPos = j == 0 ? -1 : lo - 1;
     const auto rit = pc.rare.find(key(k, j));
@@ -744,7 +908,7 @@ int Engine::wideLaunch(PassCtx& pc, const std::vector<RegKey>& ids, bool general
     if (pd.maxOrient[side] + 2 > 255) { err_ = "too many orientations per variant for this engine"; return VCE_ERR_UNSUPPORTED; }
   }
   const int mo = std::max(pd.maxOrient[0], pd.maxOrient[1]);
-  if (!general && 1 + mo > FastLimits::kMaxChildren) general = true;
+  if (!general && 1 + mo > FastLimits::kMaxChildren) { general = true; tier = kTierGeneral; }
   size_t winBytes = 0;
   for (RegionDesc& d : descs) {
     if (general) {
@@ -770,9 +934,19 @@ int Engine::wideLaunch(PassCtx& pc, const std::vector<RegKey>& ids, bool general
   std::vector<RegionResult> out(ids.size());
   std::vector<WarnRec> warns;
   const SearchConfig sc{cfg_.max_paths, cfg_.max_iterations, cfg_.prune_no_ops, cfg_.preference};
-  if ((rc = be_->search(pd, sc, descs, windows, general, false, out, syncOff, so, warns))) { err_ = be_->lastError(); return rc; }
+  const double searchBefore = be_->stats.searchMs;
+  tmw.lap("  wide: pack");
+  if ((rc = be_->search(pd, sc, descs, windows, tier, false, out, syncOff, so, warns))) { err_ = be_->lastError(); return rc; }
+  if (std::getenv("VCE_TIMING")) {
+    long long it = 0, nv = 0;
+    for (size_t q = 0; q < out.size(); ++q) { it += out[q].iterations; nv += descs[q].cCount + descs[q].bCount; }
+    std::fprintf(stderr, "[vce]   wide launch: %zu regions, %lld variants, tier %d, %lld iterations, kernel %.2f ms\n", ids.size(), nv,
+                 tier, it, be_->stats.searchMs - searchBefore);
+  }
+  tmw.lap("  wide: upload + search");
   std::vector<int32_t> syncBuf(so, 0);
   if ((rc = be_->fetchPass(pd, syncBuf))) { err_ = be_->lastError(); return rc; }
+  tmw.lap("  wide: fetch");
   // a re-run region reports its warnings afresh
   if (!pc.warns.empty()) {
     std::vector<WarnEntry> keep;
@@ -790,13 +964,15 @@ int Engine::wideLaunch(PassCtx& pc, const std::vector<RegKey>& ids, bool general
     const RegionResult& r = out[q];
     const RegionDesc& d = descs[q];
     statusOut[q] = r.status;
-    Rare& ra = pc.rare[key(k, j)];
-    ra.general = general;
-    ra.lastStatus = r.status;
     be_->stats.iterations += r.iterations;
+    if (r.status != kRegionClean && r.status != kRegionFinished) {
+      Rare& ra = pc.rare[key(k, j)];
+      ra.tier = tier;
+      ra.lastStatus = r.status;
+    }
     if (r.status == kRegionClean || r.status == kRegionFinished) {
       s.state = RS_WIDE_DONE;
-      s.flags = (uint8_t) ((r.usedPrefix ? 1 : 0) | (r.status == kRegionFinished ? 2 : 0));
+      s.flags = (uint8_t) ((r.usedPrefix ? 1 : 0) | (r.status == kRegionFinished ? 2 : 0) | (tier << 2));
       s.lastId = r.lastBaseAlleleId == kPrefixEmpty ? (int8_t) kMicroNoLastId : (int8_t) r.lastBaseAlleleId;
       s.nSync = 0;
       s.ext.idx = (int32_t) pc.wideSync.size();
@@ -823,6 +999,7 @@ int Engine::wideLaunch(PassCtx& pc, const std::vector<RegKey>& ids, bool general
     if (st != kRegionClean && st != kRegionFinished) continue;
     pc.warns.push_back(WarnEntry{ids[w.region].seq, ids[w.region].j, w});
   }
+  tmw.lap("  wide: extract");
   return VCE_OK;
 }
 
@@ -830,7 +1007,7 @@ int Engine::wideLaunch(PassCtx& pc, const std::vector<RegKey>& ids, bool general
 // capacity -> large-capacity kernel, then the prefix-dependent tie-breaks (MaxSumBoth.java:55,76).
 int Engine::settle(PassCtx& pc) {
   int rc;
-  std::vector<RegKey> todoFast, todoGen;
+  std::vector<RegKey> todo[kTierGeneral + 1];
   {
     std::vector<std::vector<RegKey>> per(nSeq_);
     pool_->parallelFor(nSeq_, [&](int k, int) {
@@ -839,18 +1016,22 @@ int Engine::settle(PassCtx& pc) {
       for (size_t j = 0; j < n; ++j) if (rs[j].state == RS_RESIDUAL) per[k].push_back(RegKey{k, (int) j});
     });
     for (int k = 0; k < nSeq_; ++k) {
-      for (const RegKey& id : per[k]) (fastEligible(pc, pc.rr[k][id.j]) ? todoFast : todoGen).push_back(id);
+      for (const RegKey& id : per[k]) todo[startTier(pc, pc.rr[k][id.j])].push_back(id);
     }
   }
-  be_->stats.escalated += (int64_t) (todoFast.size() + todoGen.size());
+  for (int t = 0; t <= kTierGeneral; ++t) be_->stats.escalated += (int64_t) todo[t].size();
   auto nextAlive = [&](int k, int j) {
     const int n = (int) pc.rs[k].size();
     int nx = j + 1;
     while (nx < n && pc.rs[k][nx].state == RS_DEAD) ++nx;
     return nx;
   };
+  auto pending = [&]() {
+    for (int t = 0; t <= kTierGeneral; ++t) if (!todo[t].empty()) return true;
+    return false;
+  };
   for (int round = 0; round < 100000; ++round) {
-    if (todoFast.empty() && todoGen.empty()) {
+    if (!pending()) {
       // prefix-dependent tie-breaks: re-run the first region per sequence whose assumption was wrong
       std::vector<int> fix(nSeq_, -1);
       std::vector<int> fixPrefix(nSeq_, 0);
@@ -860,7 +1041,6 @@ int Engine::settle(PassCtx& pc) {
         int prefix = kPrefixEmpty;
         for (int j = 0; j < n; ++j) {
           const RegRes& s = rs[j];
-          if (s.state == RS_DEAD) continue;
           if (s.state != RS_MICRO_DONE && s.state != RS_WIDE_DONE) continue;
           if (s.flags & 1) {
             int assumed = j == 0 ? kPrefixEmpty : kDummyPrefix;
@@ -875,38 +1055,44 @@ int Engine::settle(PassCtx& pc) {
       });
       for (int k = 0; k < nSeq_; ++k) {
         if (fix[k] < 0) continue;
+        const RegRes& s = pc.rs[k][fix[k]];
         Rare& ra = pc.rare[key(k, fix[k])];
         ra.hasPrefix = true;
         ra.assumedPrefix = fixPrefix[k];
-        const RegKey id{k, fix[k]};
-        ((ra.general || !fastEligible(pc, pc.rr[k][fix[k]])) ? todoGen : todoFast).push_back(id);
+        int tier = startTier(pc, pc.rr[k][fix[k]]);
+        if (s.state == RS_WIDE_DONE) tier = std::max(tier, (int) (s.flags >> 2) & 3);  // the tier that settled it before
+        todo[tier].push_back(RegKey{k, fix[k]});
         ++be_->stats.prefixReruns;
       }
-      if (todoFast.empty() && todoGen.empty()) break;
+      if (!pending()) break;
     }
-    std::vector<RegKey> ranF, ranG;
-    std::vector<int> stF, stG;
-    ranF.swap(todoFast);
-    ranG.swap(todoGen);
-    if ((rc = wideLaunch(pc, ranF, false, stF))) return rc;
-    if ((rc = wideLaunch(pc, ranG, true, stG))) return rc;
-    // inspect in sequence order so that chains of spilling regions merge front to back
+    // run every tier's list, then inspect in sequence order so that chains of spilling regions merge front to back
     std::vector<std::pair<RegKey, int>> all;
-    for (size_t q = 0; q < ranF.size(); ++q) all.push_back(std::make_pair(ranF[q], stF[q]));
-    for (size_t q = 0; q < ranG.size(); ++q) all.push_back(std::make_pair(ranG[q], stG[q]));
-    std::sort(all.begin(), all.end(), [](const std::pair<RegKey, int>& a, const std::pair<RegKey, int>& b) {
-      return a.first.seq != b.first.seq ? a.first.seq < b.first.seq : a.first.j < b.first.j;
+    std::vector<int> allTier;
+    for (int t = 0; t <= kTierGeneral; ++t) {
+      std::vector<RegKey> ran;
+      std::vector<int> st;
+      ran.swap(todo[t]);
+      if ((rc = wideLaunch(pc, ran, t, st))) return rc;
+      for (size_t q = 0; q < ran.size(); ++q) { all.push_back(std::make_pair(ran[q], st[q])); allTier.push_back(t); }
+    }
+    std::vector<size_t> ord(all.size());
+    for (size_t q = 0; q < ord.size(); ++q) ord[q] = q;
+    std::sort(ord.begin(), ord.end(), [&](size_t a, size_t b) {
+      return all[a].first.seq != all[b].first.seq ? all[a].first.seq < all[b].first.seq : all[a].first.j < all[b].first.j;
     });
-    for (size_t q = 0; q < all.size(); ++q) {
+    for (size_t oq = 0; oq < ord.size(); ++oq) {
+      const size_t q = ord[oq];
       const int k = all[q].first.seq, j = all[q].first.j;
       const int st = all[q].second;
       if (pc.rs[k][j].state == RS_DEAD) continue;
-      Rare& ra = pc.rare[key(k, j)];
       if (st == kRegionOverflow) {
-        if (ra.general) { err_ = "search capacity exceeded in the large-capacity kernel"; return VCE_ERR_CAPACITY; }
-        todoGen.push_back(all[q].first);
+        Rare& ra = pc.rare[key(k, j)];
+        if (ra.tier >= kTierGeneral) { err_ = "search capacity exceeded in the large-capacity kernel"; return VCE_ERR_CAPACITY; }
+        todo[ra.tier + 1].push_back(all[q].first);
         ++be_->stats.escalated;
       } else if (st == kRegionSpill) {
+        Rare& ra = pc.rare[key(k, j)];
         ++be_->stats.spilled;
         const int n = (int) pc.rs[k].size();
         int nx = nextAlive(k, j);
@@ -915,6 +1101,7 @@ int Engine::settle(PassCtx& pc) {
           // last region of its sequence ran off its reference window: widen it
           if (ra.extraMargin < 0) { err_ = "region spilled with the whole template in its window"; return VCE_ERR_CAPACITY; }
           ra.extraMargin = ra.extraMargin == 0 ? 256 : (ra.extraMargin >= (1 << 20) ? -1 : ra.extraMargin * 16);
+          todo[std::max(ra.tier, startTier(pc, g))].push_back(all[q].first);
         } else {
           // absorb the following region (and further ones while they are themselves known to spill)
           pc.undo.push_back(std::make_pair(RegKey{k, j}, g));
@@ -930,9 +1117,9 @@ int Engine::settle(PassCtx& pc) {
             nx = nextAlive(k, nx);
           }
           ra.extraMargin = 0;
+          todo[startTier(pc, g)].push_back(all[q].first);
         }
         pc.rs[k][j].state = RS_RESIDUAL;
-        (fastEligible(pc, g) ? todoFast : todoGen).push_back(all[q].first);
       }
     }
   }
@@ -964,13 +1151,15 @@ bool groupInPhase(const std::vector<VSum>& g) {  // :143-155
 }
 }  // namespace
 
+static inline void pickRow(int kind, int H, int gtPloidy, const vce_variants& in, int ii, int row, int8_t* ids, uint8_t* original);
+
 void Engine::phasing(int k, const std::vector<int32_t>& sync, int32_t out[3]) const {
   const PassCtx& pc = pass_[0];
   std::vector<VSum> inc[2], exc[2];
   for (int side = 0; side < 2; ++side) {
     const SideSeq& s = pc.ss[side][k];
     const vce_variants& in = *s.in;
-    const int P = in.gt_ploidy;
+    inc[side].reserve((size_t) s.n);
     for (int li = 0; li < s.n; ++li) {
       const int v = s.first + li;
       const int dec = pc.decision[side][v];
@@ -980,17 +1169,10 @@ void Engine::phasing(int k, const std::vector<int32_t>& sync, int32_t out[3]) co
       if (dec == 1) {
         exc[side].push_back(VSum{pc.vStart[side][v], ph, false, false});
       } else {
-        VariantGt g;
-        g.gtPloidy = pc.gtPloidy[side];
-        for (int h = 0; h < 4; ++h) g.gt[h] = h < P ? in.gt[(size_t) ii * P + h] : -2;
-        g.phased = ph ? 1 : 0;
-        g.slot0 = in.allele_off[ii];
-        g.nSlots = in.allele_off[ii + 1] - in.allele_off[ii];
-        g.aNull = in.allele_null;
-        RowPick pick;
-        pick.want = dec - 2;
-        orientVariant(pc.kind[side], pc.H, g, pick);
-        inc[side].push_back(VSum{pc.vStart[side][v], ph, true, pick.original});
+        int8_t ids[4];
+        uint8_t orig = 0;
+        pickRow(pc.kind[side], pc.H, pc.gtPloidy[side], in, ii, dec - 2, ids, &orig);
+        inc[side].push_back(VSum{pc.vStart[side][v], ph, true, orig != 0});
       }
     }
   }
@@ -1052,7 +1234,37 @@ void Engine::phasing(int k, const std::vector<int32_t>& sync, int32_t out[3]) co
   out[0] = mis; out[1] = correct; out[2] = unph;
 }
 
-void Engine::assemble(int k, vce_sequence_result& res) {
+// Orientation row `row` of a variant (host side of K1 for the output arrays): allele ids + isOriginal.
+// Fast paths for the orientors of the default / squash configurations, Orientor.orientations otherwise.
+static inline void pickRow(int kind, int H, int gtPloidy, const vce_variants& in, int ii, int row, int8_t* ids, uint8_t* original) {
+  const int P = in.gt_ploidy;
+  const bool phased = in.phased && in.phased[ii];
+  if (H == 2 && P == 2 && gtPloidy == 2 && (kind == VCE_ORIENT_UNPHASED || ((kind == VCE_ORIENT_PHASED || kind == VCE_ORIENT_PHASED_INVERT) && !phased))) {
+    const int8_t g0 = in.gt[(size_t) ii * 2], g1 = in.gt[(size_t) ii * 2 + 1];  // UnphasedOrientor :77-89
+    ids[0] = row == 0 ? g0 : g1;
+    ids[1] = row == 0 ? g1 : g0;
+    ids[2] = ids[3] = -2;
+    *original = row == 0 ? 1 : 0;
+    return;
+  }
+  VariantGt g;
+  g.gtPloidy = gtPloidy;
+  for (int h = 0; h < 4; ++h) g.gt[h] = h < P ? in.gt[(size_t) ii * P + h] : -2;
+  g.phased = phased ? 1 : 0;
+  g.slot0 = in.allele_off[ii];
+  g.nSlots = in.allele_off[ii + 1] - in.allele_off[ii];
+  g.aNull = in.allele_null;
+  RowPick pick;
+  pick.want = row;
+  orientVariant(kind, H, g, pick);
+  for (int h = 0; h < 4; ++h) ids[h] = pick.ids[h];
+  *original = pick.original ? 1 : 0;
+}
+
+// Per sequence: sync points of every pass (Path.getSyncPoints with the Path.java:293 de-duplication), errors,
+// warnings, and the pass-2 decisions by input index.  Returns false when the sequence needs no per-variant pass
+// (short-circuit or error: its outputs are complete).
+bool Engine::assembleHeader(int k, vce_sequence_result& res) {
   const vce_sequence& sq = seqs_[k];
   res.n_sync[0] = res.n_sync[1] = 0;
   res.phasing[0] = res.phasing[1] = res.phasing[2] = 0;
@@ -1062,42 +1274,48 @@ void Engine::assemble(int k, vce_sequence_result& res) {
   res.n_iterations = 0;
   vce_side_result* sides[2] = {&res.calls, &res.baseline};
   const vce_variants* vin[2] = {&sq.calls, &sq.baseline};
-  if (pass_[0].shortCircuit[k]) {  // SequenceEvaluator.java:94-97
+  auto blank = [&](int extraStatus, int syncId) {
     for (int side = 0; side < 2; ++side) {
       vce_side_result& o = *sides[side];
       for (int i = 0; i < vin[side]->n; ++i) {
-        o.status[i] = (uint8_t) ((vin[side]->status_in ? vin[side]->status_in[i] : 0) | VCE_STATUS_NO_MATCH);
+        o.status[i] = (uint8_t) ((vin[side]->status_in ? vin[side]->status_in[i] : 0) | extraStatus);
         for (int h = 0; h < VCE_MAX_PLOIDY; ++h) o.allele_ids[(size_t) i * VCE_MAX_PLOIDY + h] = -2;
         o.original[i] = 0;
         o.weight[i] = 0;
-        if (o.sync_id) o.sync_id[i] = 1;
+        if (o.sync_id) o.sync_id[i] = syncId;
       }
     }
-    return;
+  };
+  if (pass_[0].shortCircuit[k]) {  // SequenceEvaluator.java:94-97
+    blank(VCE_STATUS_NO_MATCH, 1);
+    return false;
   }
-  // sync points per pass + per-sequence errors
-  std::vector<int32_t> sync[2];
+  for (int p = 0; p < 2; ++p) seqSync_[p][k].clear();
   for (int p = 0; p < cfg_.n_passes; ++p) {
     const PassCtx& pc = pass_[p];
+    std::vector<int32_t>& sync = seqSync_[p][k];
     const int n = (int) pc.rs[k].size();
-    sync[p].reserve((size_t) n + 8);
+    sync.reserve((size_t) n + 8);
+    const RegRes* rs = pc.rs[k].data();
     for (int j = 0; j < n; ++j) {
-      const RegRes& s = pc.rs[k][j];
-      if (s.state == RS_DEAD) continue;
-      if (s.state == RS_ERR_NULL) res.error = VCE_ERR_BEST_PATH_NULL;
-      else if (s.state == RS_ERR_MOVE) res.error = VCE_ERR_MOVE_IN_VARIANT;
-      else if (s.state == RS_ERR_ORDER) res.error = VCE_ERR_UNSUPPORTED;
+      const RegRes& s = rs[j];
       if (s.state == RS_MICRO_DONE) {
         const int base = regionStartPos(pc, k, j);
         for (int q = 0; q < s.nSync; ++q) {
           const int sp = base + s.rel[q];
-          if (sync[p].empty() || sync[p].back() != sp) sync[p].push_back(sp);  // Path.java:293 de-duplication
+          if (sync.empty() || sync.back() != sp) sync.push_back(sp);  // Path.java:293 de-duplication
         }
       } else if (s.state == RS_WIDE_DONE) {
         for (int q = 0; q < s.ext.n; ++q) {
           const int sp = pc.wideSync[s.ext.idx + q];
-          if (sync[p].empty() || sync[p].back() != sp) sync[p].push_back(sp);
+          if (sync.empty() || sync.back() != sp) sync.push_back(sp);
         }
+      } else if (s.state == RS_ERR_NULL) {
+        res.error = VCE_ERR_BEST_PATH_NULL;
+      } else if (s.state == RS_ERR_MOVE) {
+        res.error = VCE_ERR_MOVE_IN_VARIANT;
+      } else if (s.state == RS_ERR_ORDER) {
+        res.error = VCE_ERR_UNSUPPORTED;
       }
     }
     // re-runs append out of order: report in region order, as the sequential reference would
@@ -1110,119 +1328,119 @@ void Engine::assemble(int k, vce_sequence_result& res) {
     }
   }
   if (res.error != VCE_OK) {
-    for (int side = 0; side < 2; ++side) {
-      vce_side_result& o = *sides[side];
-      for (int i = 0; i < vin[side]->n; ++i) {
-        o.status[i] = vin[side]->status_in ? vin[side]->status_in[i] : 0;
-        for (int h = 0; h < VCE_MAX_PLOIDY; ++h) o.allele_ids[(size_t) i * VCE_MAX_PLOIDY + h] = -2;
-        o.original[i] = 0;
-        o.weight[i] = 0;
-        if (o.sync_id) o.sync_id[i] = 0;
-      }
-    }
-    return;
+    blank(0, 0);
+    return false;
   }
   for (int p = 0; p < cfg_.n_passes; ++p) {
-    res.n_sync[p] = (int32_t) sync[p].size();
-    if ((int) sync[p].size() > res.sync_cap[p]) { res.error = VCE_ERR_CAPACITY; return; }
-    std::copy(sync[p].begin(), sync[p].end(), res.sync_points[p]);
+    const std::vector<int32_t>& sync = seqSync_[p][k];
+    res.n_sync[p] = (int32_t) sync.size();
+    if ((int) sync.size() > res.sync_cap[p]) { res.error = VCE_ERR_CAPACITY; blank(0, 0); return false; }
+    std::copy(sync.begin(), sync.end(), res.sync_points[p]);
   }
-  res.n_regions = (int64_t) sync[0].size();
-  // statuses (SequenceEvaluator.mergeVariants :170-182, insertSkipped :190-209), orientation ids, weights, sync ids
-  for (int side = 0; side < 2; ++side) {
-    vce_side_result& o = *sides[side];
-    const vce_variants& in = *vin[side];
-    const PassCtx& p0 = pass_[0];
-    const SideSeq& a = p0.ss[side][k];
-    const int P = in.gt_ploidy;
-    // pass-1 decision of every input variant (0 when the variant did not enter pass 1)
-    std::vector<uint8_t> dec1;
-    std::vector<double> w1;
-    if (cfg_.n_passes == 2) {
-      const PassCtx& p1 = pass_[1];
+  res.n_regions = (int64_t) seqSync_[0][k].size();
+  if (cfg_.n_passes == 2) {  // pass-2 decision / weight of every input variant (0 when the variant did not enter pass 2)
+    const PassCtx& p1 = pass_[1];
+    for (int side = 0; side < 2; ++side) {
       const SideSeq& b = p1.ss[side][k];
-      dec1.assign(in.n, 0);
-      if (side == 0) w1.assign(in.n, 0.0);
+      std::vector<uint8_t>& d1 = seqDec1_[side][k];
+      d1.assign((size_t) vin[side]->n, 0);
+      std::vector<double>& w1 = seqW1_[k];
+      if (side == 0) w1.assign((size_t) vin[side]->n, 0.0);
       for (int li = 0; li < b.n; ++li) {
         const int ii = b.idx[li];
-        dec1[ii] = p1.decision[side][b.first + li];
+        d1[ii] = p1.decision[side][b.first + li];
         if (side == 0) w1[ii] = p1.weight[b.first + li];
       }
     }
-    size_t f0 = 0, f1 = 0;  // floor cursors into sync[0] / sync[1] (variants come in ascending start order)
-    auto floorVal = [](const std::vector<int32_t>& sp, size_t& cur, int start) -> int {
-      // InterleavingEvalSynchronizer.floorSyncPos :71-83: last sync point <= start - 1 (first one if none)
-      if (sp.empty()) return 0;
-      const int vv = start - 1;
-      while (cur + 1 < sp.size() && sp[cur + 1] <= vv) ++cur;
-      return sp[cur] + 1;
-    };
-    for (int li = 0; li < a.n; ++li) {
-      const int v = a.first + li;
-      const int ii = a.idx ? a.idx[li] : li;
-      int st = in.status_in ? in.status_in[ii] : 0;
-      int d0 = p0.decision[side][v];
-      int kindSel = -1, row = 0;
-      double wgt = 0.0;
-      if (d0 >= 2) {
-        st |= VCE_STATUS_GT_MATCH;
-        kindSel = 0;
-        row = d0 - 2;
-        wgt = side == 0 ? p0.weight[v] : 0.0;
-      } else if (cfg_.n_passes == 1) {
-        if (d0 == 1) st |= VCE_STATUS_NO_MATCH;
-        else st |= VCE_STATUS_SKIPPED;
+  }
+  return true;
+}
+
+// Statuses (SequenceEvaluator.mergeVariants :170-182, insertSkipped :190-209), orientation ids, weights and sync ids
+// of the variants [lo, hi) (sorted positions of pass 1) of one side of sequence k.
+void Engine::assembleBlock(int k, int side, int lo, int hi, vce_sequence_result& res) const {
+  const vce_sequence& sq = seqs_[k];
+  vce_side_result& o = side == 0 ? res.calls : res.baseline;
+  const vce_variants& in = side == 0 ? sq.calls : sq.baseline;
+  const PassCtx& p0 = pass_[0];
+  const SideSeq& a = p0.ss[side][k];
+  const bool two = cfg_.n_passes == 2;
+  const uint8_t* dec1 = two ? seqDec1_[side][k].data() : nullptr;
+  const double* w1 = two && side == 0 ? seqW1_[k].data() : nullptr;
+  const std::vector<int32_t>& s0 = seqSync_[0][k];
+  const std::vector<int32_t>& s1 = seqSync_[1][k];
+  // InterleavingEvalSynchronizer.floorSyncPos :71-83: last sync point <= start - 1 (the first one if none); variants
+  // come in ascending start order, so the floor index only moves forward
+  auto floorInit = [](const std::vector<int32_t>& sp, int start) -> size_t {
+    if (sp.empty()) return 0;
+    const size_t u = (size_t) (std::upper_bound(sp.begin(), sp.end(), start - 1) - sp.begin());
+    return u == 0 ? 0 : u - 1;
+  };
+  size_t f0 = 0, f1 = 0;
+  if (lo < hi) {
+    f0 = floorInit(s0, p0.vStart[side][a.first + lo]);
+    f1 = floorInit(s1, p0.vStart[side][a.first + lo]);
+  }
+  auto floorVal = [](const std::vector<int32_t>& sp, size_t& cur, int start) -> int {
+    if (sp.empty()) return 0;
+    const int vv = start - 1;
+    while (cur + 1 < sp.size() && sp[cur + 1] <= vv) ++cur;
+    return sp[cur] + 1;
+  };
+  for (int li = lo; li < hi; ++li) {
+    const int v = a.first + li;
+    const int ii = a.idx ? a.idx[li] : li;
+    int st = in.status_in ? in.status_in[ii] : 0;
+    const int d0 = p0.decision[side][v];
+    int passSel = -1, row = 0;
+    double wgt = 0.0;
+    if (d0 >= 2) {
+      st |= VCE_STATUS_GT_MATCH;
+      passSel = 0;
+      row = d0 - 2;
+      wgt = side == 0 ? p0.weight[v] : 0.0;
+    } else if (!two) {
+      st |= d0 == 1 ? VCE_STATUS_NO_MATCH : VCE_STATUS_SKIPPED;
+    } else {
+      const int d1 = dec1[ii];
+      if (d1 >= 2) {
+        st |= VCE_STATUS_ALLELE_MATCH;
+        passSel = 1;
+        row = d1 - 2;
+        wgt = side == 0 ? w1[ii] : 0.0;
       } else {
-        const int d1 = dec1[ii];
-        if (d1 >= 2) {
-          st |= VCE_STATUS_ALLELE_MATCH;
-          kindSel = 1;
-          row = d1 - 2;
-          wgt = side == 0 ? w1[ii] : 0.0;
-        } else if (d1 == 1) {
-          st |= VCE_STATUS_NO_MATCH;
-        } else {
-          st |= VCE_STATUS_SKIPPED;
-        }
-      }
-      o.status[ii] = (uint8_t) st;
-      int8_t* ids = o.allele_ids + (size_t) ii * VCE_MAX_PLOIDY;
-      if (kindSel >= 0) {
-        const PassCtx& pp = pass_[kindSel];
-        VariantGt g;
-        g.gtPloidy = pp.gtPloidy[side];
-        for (int h = 0; h < 4; ++h) g.gt[h] = h < P ? in.gt[(size_t) ii * P + h] : -2;
-        g.phased = (in.phased && in.phased[ii]) ? 1 : 0;
-        g.slot0 = in.allele_off[ii];
-        g.nSlots = in.allele_off[ii + 1] - in.allele_off[ii];
-        g.aNull = in.allele_null;
-        RowPick pick;
-        pick.want = row;
-        orientVariant(pp.kind[side], pp.H, g, pick);
-        for (int h = 0; h < 4; ++h) ids[h] = pick.ids[h];
-        o.original[ii] = pick.original ? 1 : 0;
-      } else {
-        ids[0] = ids[1] = ids[2] = ids[3] = -2;
-        o.original[ii] = 0;
-      }
-      o.weight[ii] = wgt;
-      if (o.sync_id) {
-        // SYNC annotation value (InterleavingEvalSynchronizer.floorSyncPos :71-83 + WithInfoEvalSynchronizer :121-222)
-        const int s1 = floorVal(sync[0], f0, p0.vStart[side][v]);
-        const int s2 = floorVal(sync[1], f1, p0.vStart[side][v]);
-        int val = 0;
-        if (st & VCE_STATUS_SKIPPED) val = 0;
-        else if (st & VCE_STATUS_GT_MATCH) val = s1 + 1;
-        else if (st & VCE_STATUS_ALLELE_MATCH) val = s2 + 1;
-        else if (st & VCE_STATUS_NO_MATCH) val = s2 > 0 ? s2 + 1 : s1 + 1;
-        o.sync_id[ii] = val;
+        st |= d1 == 1 ? VCE_STATUS_NO_MATCH : VCE_STATUS_SKIPPED;
       }
     }
+    o.status[ii] = (uint8_t) st;
+    int8_t* ids = o.allele_ids + (size_t) ii * VCE_MAX_PLOIDY;
+    if (passSel >= 0) {
+      const PassCtx& pp = pass_[passSel];
+      pickRow(pp.kind[side], pp.H, pp.gtPloidy[side], in, ii, row, ids, &o.original[ii]);
+    } else {
+      ids[0] = ids[1] = ids[2] = ids[3] = -2;
+      o.original[ii] = 0;
+    }
+    o.weight[ii] = wgt;
+    if (o.sync_id) {
+      // SYNC annotation value (InterleavingEvalSynchronizer.floorSyncPos :71-83 + WithInfoEvalSynchronizer :121-222)
+      const int sv1 = floorVal(s0, f0, p0.vStart[side][v]);
+      const int sv2 = floorVal(s1, f1, p0.vStart[side][v]);
+      int val = 0;
+      if (st & VCE_STATUS_SKIPPED) val = 0;
+      else if (st & VCE_STATUS_GT_MATCH) val = sv1 + 1;
+      else if (st & VCE_STATUS_ALLELE_MATCH) val = sv2 + 1;
+      else if (st & VCE_STATUS_NO_MATCH) val = sv2 > 0 ? sv2 + 1 : sv1 + 1;
+      o.sync_id[ii] = val;
+    }
   }
-  phasing(k, sync[0], res.phasing);
 }
 
 int Engine::finish(vce_sequence_result* results) {
+  StageTimer tm;
+  for (int p = 0; p < 2; ++p) ensureSize(seqSync_[p], (size_t) nSeq_);
+  for (int side = 0; side < 2; ++side) ensureSize(seqDec1_[side], (size_t) nSeq_);
+  ensureSize(seqW1_, (size_t) nSeq_);
   // largest sequences first
   std::vector<int> order(nSeq_);
   for (int k = 0; k < nSeq_; ++k) order[k] = k;
@@ -1230,10 +1448,32 @@ int Engine::finish(vce_sequence_result* results) {
     const int na = seqs_[a].calls.n + seqs_[a].baseline.n, nb = seqs_[b].calls.n + seqs_[b].baseline.n;
     return na != nb ? na > nb : a < b;
   });
-  pool_->parallelFor(nSeq_, [&](int t, int) { assemble(order[t], results[order[t]]); });
+  std::vector<uint8_t> live(nSeq_, 0);
+  pool_->parallelFor(nSeq_, [&](int t, int) {
+    const int k = order[t];
+    live[k] = assembleHeader(k, results[k]) ? 1 : 0;
+  });
+  tm.lap("assemble: sync points");
+  struct Task { int seq, side, lo, hi; };  // side < 0: phasing counts of the sequence
+  std::vector<Task> tasks;
+  for (int t = 0; t < nSeq_; ++t) if (live[order[t]]) tasks.push_back(Task{order[t], -1, 0, 0});
+  const int block = 1 << 15;
+  for (int t = 0; t < nSeq_; ++t) {
+    const int k = order[t];
+    if (!live[k]) continue;
+    for (int side = 0; side < 2; ++side) {
+      const int n = pass_[0].ss[side][k].n;
+      for (int lo = 0; lo < n; lo += block) tasks.push_back(Task{k, side, lo, std::min(n, lo + block)});
+    }
+  }
+  pool_->parallelFor((int) tasks.size(), [&](int t, int) {
+    const Task& tk = tasks[t];
+    if (tk.side < 0) phasing(tk.seq, seqSync_[0][tk.seq], results[tk.seq].phasing);
+    else assembleBlock(tk.seq, tk.side, tk.lo, tk.hi, results[tk.seq]);
+  });
+  tm.lap("assemble: variants + phasing");
   int rc = VCE_OK;
   for (int k = 0; k < nSeq_; ++k) {
-    // per-sequence diagnostics
     if (results[k].error != VCE_OK && rc == VCE_OK) rc = results[k].error;
   }
   return rc;

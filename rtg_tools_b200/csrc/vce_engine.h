@@ -33,6 +33,7 @@ struct EngineOptions {
   bool forceGeneral = false;   // tests: every region through the large-capacity kernel
   bool disableMicro = false;   // tests: no thread-per-region kernel
   int chunkRegions = 0;        // regions per chunk, 0 = automatic
+  int splitSegment = 1 << 16;  // variants per segment of the parallel region split
 };
 
 class Engine {
@@ -74,7 +75,7 @@ class Engine {
     int extraMargin = 0;      // reference bases added after a window miss (< 0: rest of the template)
     int assumedPrefix = 0;
     bool hasPrefix = false;   // an explicit prefix was set (otherwise the default assumption)
-    bool general = false;     // last ran in the large-capacity kernel
+    int tier = 0;             // warp-per-region tier of the last run (kTierGeneral = large-capacity kernel)
     int lastStatus = 0;       // kRegion* of the last wide run
   };
   struct Chunk {
@@ -114,17 +115,21 @@ class Engine {
   int setupPass0();
   int setupPass1();
   void computeBounds(PassCtx& pc);
-  void splitSequence(PassCtx& pc, int k);
+  void resetPass(PassCtx& pc);
+  void splitSlice(const PassCtx& pc, int i, int ie, int j, int je, long maxEnd, std::vector<RegRange>& out, bool* continues) const;
+  void splitAll(PassCtx& pc);
   void planChunks(PassCtx& pc);
   template <class T> int buildPacket(const PassCtx& pc, int k, int j, uint8_t* out) const;
   int buildChunk(PassCtx& pc, Chunk& ch, int worker, bool launch);
   int runChunks(PassCtx& pc);
   void decodeChunk(PassCtx& pc, Chunk& ch, int64_t& iterations);
   int settle(PassCtx& pc);
-  int wideLaunch(PassCtx& pc, const std::vector<RegKey>& ids, bool general, std::vector<int>& statusOut);
+  int wideLaunch(PassCtx& pc, const std::vector<RegKey>& ids, int tier, std::vector<int>& statusOut);
+  int startTier(const PassCtx& pc, const RegRange& g) const;
   bool fastEligible(const PassCtx& pc, const RegRange& g) const;
   int regionStartPos(const PassCtx& pc, int k, int j) const;
-  void assemble(int k, vce_sequence_result& res);
+  bool assembleHeader(int k, vce_sequence_result& res);
+  void assembleBlock(int k, int side, int lo, int hi, vce_sequence_result& res) const;
   void phasing(int k, const std::vector<int32_t>& sync, int32_t out[3]) const;
   void resetPassRun(PassCtx& pc);
 
@@ -141,6 +146,9 @@ class Engine {
   std::mutex errMu_;
   std::mutex arenaMu_;
   std::vector<HostBlock> arena_;
+  std::vector<std::vector<int32_t>> seqSync_[2];   // [pass][seq] sync points (assembly)
+  std::vector<std::vector<uint8_t>> seqDec1_[2];   // [side][seq] pass-2 decision by input index
+  std::vector<std::vector<double>> seqW1_;         // [seq] pass-2 call weight by input index
   std::vector<std::vector<uint8_t>> scratch_;   // per worker
   std::vector<std::vector<uint32_t>> scratchOff_;
 };

@@ -98,11 +98,12 @@ class Backend {
   // time, so that a following search(..., staged = true) starts with everything resident in HBM.
   virtual int stage(const std::vector<RegionDesc>& regs, const std::vector<uint8_t>& windows,
                     const std::vector<int32_t>& syncOff, size_t syncTotal) = 0;
-  // Runs the region search (K2 + K3 epilogue) over `regs`.  general=false: shared-memory kernel with fixed small
-  // capacities (reports kRegionOverflow beyond them); general=true: large-capacity kernel with per-region arenas.
+  // Runs the warp-per-region search (K2 + K3 epilogue) over `regs`.  tier 0 / 1: shared-memory kernel with the fixed
+  // capacities of fastShape(tier) (reports kRegionOverflow beyond them); tier kTierGeneral: large-capacity kernel with
+  // per-region arenas in HBM.
   // staged=true: the launch inputs were already copied by stage(); regs/windows/syncOff are then only read for sizes.
   virtual int search(PassData& pd, const SearchConfig& sc, const std::vector<RegionDesc>& regs,
-                     const std::vector<uint8_t>& windows, bool general, bool staged, std::vector<RegionResult>& out,
+                     const std::vector<uint8_t>& windows, int tier, bool staged, std::vector<RegionResult>& out,
                      const std::vector<int32_t>& syncOff, size_t syncTotal, std::vector<WarnRec>& warns) = 0;
   // Copies decision / weight / orientation-id arrays of the pass and the sync-point buffer back to the host.
   virtual int fetchPass(PassData& pd, std::vector<int32_t>& syncBuf) = 0;
@@ -113,15 +114,25 @@ class Backend {
   SearchStats stats;
 };
 
-// Fixed capacities of the shared-memory ("fast") search kernel.
+// Fixed capacities of the shared-memory warp-per-region kernel, two tiers: small frontier / many resident warps, and
+// larger frontier + pending-allele queue / fewer resident warps.
+struct FastShape {
+  int kv;            // variants per side (4-bit decisions in one word per side)
+  int q;             // pending alleles per haplotype
+  int smax;          // sync points per region
+  int cap;           // frontier capacity
+  int maxChildren;   // exclude + up to 6 orientations (ALLELE_GT)
+  int tabBytes;      // shared memory per warp for the region's variant / orientation / allele tables
+  VCE_HD int slots() const { return cap + 1 + maxChildren; }
+  VCE_HD int ordCap() const { return 2 * cap; }
+};
+constexpr int kTierGeneral = 2;
+inline FastShape fastShape(int tier) {
+  return tier == 0 ? FastShape{8, 2, 8, 24, 7, 1536} : FastShape{8, 8, 12, 112, 7, 3072};
+}
 struct FastLimits {
-  static constexpr int kMaxVarPerSide = 8;   // 4-bit decisions in one word per side
-  static constexpr int kQ = 2;               // pending alleles per haplotype
-  static constexpr int kSMax = 8;            // sync points per region
-  static constexpr int kCap = 24;            // frontier capacity
-  static constexpr int kMaxChildren = 7;     // exclude + up to 6 orientations (ALLELE_GT)
-  static constexpr int kSlots = kCap + 1 + kMaxChildren;
-  static constexpr int kOrdCap = 2 * kCap;
+  static constexpr int kMaxVarPerSide = 8;
+  static constexpr int kMaxChildren = 7;
 };
 
 }  // namespace vce

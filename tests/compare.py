@@ -24,7 +24,12 @@ def compare_results(a, b, seqs, what="result"):
             assert np.array_equal(sa.weight.view(np.int64), sb.weight.view(np.int64)), "%s %s weights differ" % (tag, side)
             assert np.array_equal(sa.sync_id, sb.sync_id), "%s %s sync ids differ" % (tag, side)
         for p in range(2):
-            assert np.array_equal(ra.sync_points[p], rb.sync_points[p]), "%s sync points pass %d differ:\n%s\n%s" % (
-                tag, p, ra.sync_points[p][:20], rb.sync_points[p][:20])
+            sa, sb = ra.sync_points[p], rb.sync_points[p]
+            if not np.array_equal(sa, sb):
+                n = min(len(sa), len(sb))
+                d = np.nonzero(sa[:n] != sb[:n])[0]
+                i = int(d[0]) if len(d) else n
+                raise AssertionError("%s sync points pass %d differ at index %d (lengths %d / %d):\n%s\n%s" % (
+                    tag, p, i, len(sa), len(sb), sa[max(0, i - 3):i + 4], sb[max(0, i - 3):i + 4]))
         assert ra.phasing == rb.phasing, "%s phasing %s vs %s" % (tag, ra.phasing, rb.phasing)
         assert ra.warnings == rb.warnings, "%s warnings %s vs %s" % (tag, ra.warnings, rb.warnings)

@@ -90,8 +90,10 @@ class EmulBackend : public Backend {
   }
 
   int search(PassData& pd, const SearchConfig& sc, const std::vector<RegionDesc>& regs, const std::vector<uint8_t>& windows,
-             bool general, bool /*staged*/, std::vector<RegionResult>& out, const std::vector<int32_t>& syncOff, size_t syncTotal,
+             int tier, bool /*staged*/, std::vector<RegionResult>& out, const std::vector<int32_t>& syncOff, size_t syncTotal,
              std::vector<WarnRec>& warns) override {
+    const bool general = tier >= kTierGeneral;
+    const FastShape fs = fastShape(general ? 0 : tier);
     ++stats.launches;
     std::vector<int32_t>& syncOut = sync_[pd.pass];
     if (syncOut.size() < syncTotal) syncOut.resize(syncTotal, 0);
@@ -117,9 +119,9 @@ class EmulBackend : public Backend {
         rs.cap = sc.maxPaths + 1 + rs.maxChildren;
         // grow the arena lazily in the emulation: start small, retry bigger on overflow
       } else {
-        rs.L.init(pd.H, FastLimits::kQ, FastLimits::kMaxVarPerSide, FastLimits::kSMax, 4);
-        rs.maxChildren = FastLimits::kMaxChildren;
-        rs.cap = FastLimits::kCap;
+        rs.L.init(pd.H, fs.q, fs.kv, fs.smax, 4);
+        rs.maxChildren = fs.maxChildren;
+        rs.cap = fs.cap;
       }
       int capTry = general ? std::min(rs.cap, 256) : rs.cap;
       const int capFull = rs.cap;
@@ -177,7 +179,7 @@ class EmulBackend : public Backend {
   std::string err_;
 };
 
-int g_gap = 1, g_margin = 24, g_forceGeneral = 0, g_disableMicro = 0, g_threads = 3, g_chunk = 0;
+int g_gap = 1, g_margin = 24, g_forceGeneral = 0, g_disableMicro = 0, g_threads = 3, g_chunk = 0, g_split = 1 << 16;
 int64_t g_stats[8];
 }  // namespace
 
@@ -188,6 +190,7 @@ void emul_get_stats(int64_t* out) { for (int i = 0; i < 7; ++i) out[i] = g_stats
 
 // disableMicro: no thread-per-region kernel; threads: host worker threads; chunk: regions per chunk (0 = automatic)
 void emul_set_engine(int disableMicro, int threads, int chunk) { g_disableMicro = disableMicro; g_threads = threads; g_chunk = chunk; }
+void emul_set_split(int variantsPerSegment) { g_split = variantsPerSegment; }
 
 int emul_vce_submit(const vce_config* cfg, int32_t n_seq, const vce_sequence* seqs, vce_sequence_result* results) {
   EmulBackend be;
@@ -199,6 +202,7 @@ int emul_vce_submit(const vce_config* cfg, int32_t n_seq, const vce_sequence* se
   opt.forceGeneral = g_forceGeneral != 0;
   opt.disableMicro = g_disableMicro != 0;
   opt.chunkRegions = g_chunk;
+  opt.splitSegment = g_split;
   int rc;
   {
     Engine en(&be, &pool, opt);
@@ -218,11 +222,24 @@ int emul_vce_job(const vce_config* cfg, int32_t n_seq, const vce_sequence* seqs,
   opt.gap = g_gap;
   opt.margin = g_margin;
   opt.chunkRegions = g_chunk;
+  opt.splitSegment = g_split;
   Engine en(&be, &pool, opt);
   int rc = en.prepare(*cfg, n_seq, seqs, true);
   for (int i = 0; i < runs && !rc; ++i) rc = en.execute();
   if (!rc) rc = en.finish(results);
   if (rc && !en.error().empty()) fprintf(stderr, "emul: %s\n", en.error().c_str());
+  return rc;
+}
+// host-side micro-benchmark: `reps` staged prepare() calls on one engine (warm arenas); stage times with VCE_TIMING=1
+int emul_bench_prepare(const vce_config* cfg, int32_t n_seq, const vce_sequence* seqs, int32_t reps) {
+  EmulBackend be;
+  WorkerPool pool(g_threads);
+  EngineOptions opt;
+  opt.chunkRegions = g_chunk;
+  opt.splitSegment = g_split;
+  Engine en(&be, &pool, opt);
+  int rc = 0;
+  for (int i = 0; i < reps && !rc; ++i) rc = en.prepare(*cfg, n_seq, seqs, true);
   return rc;
 }
 int emul_vce_roc(const vce_roc_in*, vce_roc_out*) { return VCE_ERR_UNSUPPORTED; }

@@ -149,6 +149,21 @@ def test_results_do_not_depend_on_threads_chunks_or_the_small_kernel(emul, oracl
         emul.lib.emul_set_engine(0, 3, 0)
 
 
+def test_parallel_region_split_is_exact(emul, oracle):
+    """The region split runs in position-cut segments that are stitched afterwards (runs may continue across a cut)."""
+    seqs = synth.make_pair(1_000_000, n_chrom=2) + fuzz_batch(91, n_seq=6)
+    rng = np.random.default_rng(17)
+    seqs += [synth.dense_cluster_sequence(rng, n_clusters=3, per_side=(5, 8), name="dense")]
+    cfg = capi.Config(n_passes=2, max_paths=2000, max_iterations=20000)
+    want = oracle.submit(cfg, seqs)
+    try:
+        for per in (1, 2, 3, 7, 50, 1000):
+            emul.lib.emul_set_split(per)
+            compare_results(want, emul.submit(cfg, seqs), seqs, what="segment %d" % per)
+    finally:
+        emul.lib.emul_set_split(1 << 16)
+
+
 def test_staged_job_is_rerunnable(emul, oracle):
     """vce_job_*: prepare once (digest + upload), execute repeatedly (merges are undone between runs), finish."""
     seqs = synth.make_pair(1_000_000, n_chrom=2) + fuzz_batch(5, n_seq=4)
