@@ -147,10 +147,13 @@ __device__ bool stageTables(RegionSearch<DeviceWarp>& rs, const SideArrays* G, i
     for (int i = lane; i < slN; i += 32) { aS[i] = g.aStart[sl0 + i]; aE[i] = g.aEnd[sl0 + i]; }
     for (int i = lane; i <= slN; i += 32) aN[i] = slN > 0 ? g.aNtOff[sl0 + i] : 0;
     for (int i = lane; i < ntN[side]; i += 32) nt[i] = g.nt[nt0[side] + i];
-    S.vStart = vS - first; S.vEnd = vE - first; S.vFlags = vF - first; S.oOff = oO - first;
-    S.oSlot = oS - (ptrdiff_t) rows0[side] * H; S.oIds = oI - (ptrdiff_t) rows0[side] * 4;
-    S.aStart = aS - sl0; S.aEnd = aE - sl0; S.aNtOff = aN - sl0; S.nt = nt - nt0[side];
+    if (lane == 0) {
+      S.vStart = vS - first; S.vEnd = vE - first; S.vFlags = vF - first; S.oOff = oO - first;
+      S.oSlot = oS - (ptrdiff_t) rows0[side] * H; S.oIds = oI - (ptrdiff_t) rows0[side] * 4;
+      S.aStart = aS - sl0; S.aEnd = aE - sl0; S.aNtOff = aN - sl0; S.nt = nt - nt0[side];
+    }
   }
+  __syncwarp();
   return true;
 }
 
@@ -161,14 +164,19 @@ __global__ void __launch_bounds__(kFastWarps * 32) k_search(const __grid_constan
   const int lane = threadIdx.x & 31;
   const int gwarp = blockIdx.x * (blockDim.x >> 5) + warp;
 
-  RegionSearch<DeviceWarp> rs;
-  rs.cfg = p.cfg;
+  // per-warp shared memory: [RegionConst | tier layout ...] (fast tiers) or [RegionConst | tables] (general)
+  const int kcWords = (int) ((sizeof(RegionConst) + 15) / 16) * 4;
+  int32_t* warpBase = GENERAL ? smem + (size_t) warp * (kcWords + p.tabBytes / 4) : smem + (size_t) warp * p.wordsPerWarp;
+  RegionConst* kc = reinterpret_cast<RegionConst*>(warpBase);
+  RegionSearch<DeviceWarp> rs(kc);
+  if (lane == 0) kc->cfg = p.cfg;
   rs.warnOut = p.warnScratch + (size_t) gwarp * kWarnPerRegion;
   rs.warnCap = kWarnPerRegion;
   uint8_t* winS = nullptr;
   uint8_t* tabS = nullptr;
   if (!GENERAL) {
-    rs.L.init(p.H, p.fs.q, p.fs.kv, p.fs.smax, 4);
+    if (lane == 0) kc->L.init(p.H, p.fs.q, p.fs.kv, p.fs.smax, 4);
+    __syncwarp();
     rs.maxChildren = p.fs.maxChildren;
     rs.cap = p.fs.cap;
     rs.nSlots = p.fs.slots();
@@ -178,7 +186,7 @@ __global__ void __launch_bounds__(kFastWarps * 32) k_search(const __grid_constan
     // ctl is padded so that what follows it (tables, window, the next warp's block) stays 16-byte aligned
     const int preWords = (rs.nSlots + 2) * LM.W + rs.ordCap + rs.nSlots;
     const int ctlWords = ((preWords + 16 + 2 * p.fs.maxChildren + 3) & ~3) - preWords;
-    int32_t* base = smem + (size_t) warp * p.wordsPerWarp;
+    int32_t* base = warpBase + kcWords;
     rs.slots = base;
     rs.order = base + (rs.nSlots + 2) * LM.W;
     rs.freeList = rs.order + rs.ordCap;
@@ -186,7 +194,7 @@ __global__ void __launch_bounds__(kFastWarps * 32) k_search(const __grid_constan
     tabS = reinterpret_cast<uint8_t*>(rs.ctl + ctlWords);
     winS = tabS + p.tabBytes;
   } else {
-    tabS = reinterpret_cast<uint8_t*>(smem) + (size_t) warp * p.tabBytes;
+    tabS = reinterpret_cast<uint8_t*>(warpBase + kcWords);
   }
 
   while (true) {
@@ -194,14 +202,17 @@ __global__ void __launch_bounds__(kFastWarps * 32) k_search(const __grid_constan
     if (lane == 0) r = atomicAdd(p.counter, 1);
     r = __shfl_sync(0xffffffffu, r, 0);
     if (r >= p.nRegs) break;
-    rs.R = p.regs[r];
+    __syncwarp();
+    if (lane == 0) {
+      kc->R = p.regs[r];
+      kc->S[0] = p.S[0];
+      kc->S[1] = p.S[1];
+      if (GENERAL) kc->L.init(p.H, kc->R.qMax, max(1, max(kc->R.cCount, kc->R.bCount)), kc->R.cCount + kc->R.bCount + 2, kc->R.decBits);
+    }
     rs.regionId = r;
-    rs.S[0] = p.S[0];
-    rs.S[1] = p.S[1];
     __syncwarp();
     stageTables(rs, p.S, p.H, tabS, p.tabBytes, lane);
     if (GENERAL) {
-      rs.L.init(p.H, rs.R.qMax, max(1, max(rs.R.cCount, rs.R.bCount)), rs.R.cCount + rs.R.bCount + 2, rs.R.decBits);
       rs.maxChildren = p.maxChildren;
       const long long ctlWords = 16 + 2 * p.maxChildren;
       // capacity that fits this warp's arena:  (nSlots+2)*W + ordCap + nSlots + ctl <= arenaWords,
@@ -247,9 +258,6 @@ __global__ void __launch_bounds__(kFastWarps * 32) k_search(const __grid_constan
     rr.pad = 0;
     __syncwarp();
     if (st == kRegionClean || st == kRegionFinished) {
-      // results go to the batch-wide output arrays: restore the un-staged output pointers
-      rs.S[0].outDecision = p.S[0].outDecision; rs.S[0].outWeight = p.S[0].outWeight;
-      rs.S[1].outDecision = p.S[1].outDecision; rs.S[1].outWeight = p.S[1].outWeight;
       rs.writeResults(resultSlot, p.syncOut + p.syncOff[r], &rr);
       if (lane == 0 && rs.nWarn > 0) {
         const int nw = min(rs.nWarn, kWarnPerRegion);
@@ -396,15 +404,18 @@ class CudaBackend : public Backend {
     CUDA_TRY(cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_));
     maxSmemOptin_ = maxSmem;
     CUDA_TRY(cudaFuncSetAttribute(k_search<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
-    CUDA_TRY(cudaFuncSetAttribute(k_search<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * kFastWarps));
+    CUDA_TRY(cudaFuncSetAttribute(k_search<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (4096 + 1024) * kFastWarps));
     CUDA_TRY(cudaFuncSetAttribute(k_micro<MicroA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMicroThreads * MicroA::WS_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(k_micro<MicroB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMicroThreads * MicroB::WS_BYTES));
     for (int i = 0; i < kMicroLanes; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&mStream_[i], cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&evM0_));
     CUDA_TRY(cudaEventCreate(&evM1_));
     {
       int perSm = 0;
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_micro<MicroA>, kMicroThreads, kMicroThreads * MicroA::WS_BYTES));
-      microBlocksPerSm_ = perSm < 1 ? 1 : perSm;
+      microBlocksPerSm_[0] = perSm < 1 ? 1 : perSm;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_micro<MicroB>, kMicroThreads, kMicroThreads * MicroB::WS_BYTES));
+      microBlocksPerSm_[1] = perSm < 1 ? 1 : perSm;
     }
     ready_ = true;
     return VCE_OK;
@@ -607,7 +618,8 @@ class CudaBackend : public Backend {
       const int ctlWords = ((preWords + 16 + 2 * fs.maxChildren + 3) & ~3) - preWords;
       sp.winSmemBytes = 256;
       sp.tabBytes = fs.tabBytes;
-      sp.wordsPerWarp = preWords + ctlWords + (sp.tabBytes + sp.winSmemBytes) / 4;
+      const int kcWords = (int) ((sizeof(RegionConst) + 15) / 16) * 4;
+      sp.wordsPerWarp = kcWords + preWords + ctlWords + (sp.tabBytes + sp.winSmemBytes) / 4;
       const size_t bytesPerWarp = (size_t) sp.wordsPerWarp * 4;
       int warpsPerBlock = (int) std::min<size_t>(kFastWarps, (size_t) maxSmemOptin_ / bytesPerWarp);
       if (warpsPerBlock < 1) { err_ = "fast kernel shared memory exceeds the device limit"; return VCE_ERR_CUDA; }
@@ -639,7 +651,8 @@ class CudaBackend : public Backend {
       sp.arena = arena_.p;
       sp.arenaWordsPerWarp = words;
       sp.tabBytes = 4096;
-      smemBytes = (size_t) sp.tabBytes * kFastWarps;
+      const int kcWords = (int) ((sizeof(RegionConst) + 15) / 16) * 4;
+      smemBytes = ((size_t) sp.tabBytes + (size_t) kcWords * 4) * kFastWarps;
     }
     CUDA_TRY(warnScratch_.ensure((size_t) blocks * kFastWarps * kWarnPerRegion));
     sp.warnScratch = warnScratch_.p;
@@ -734,6 +747,17 @@ class CudaBackend : public Backend {
     mNextLane_ = 0;
     return VCE_OK;
   }
+  void microMark() override {
+    std::lock_guard<std::mutex> lk(mMu_);
+    dMarks_.clear();
+    for (DevBlock& b : dBlocks_) dMarks_.push_back(b.used);
+    mMarkEvent_ = mNextEvent_;
+  }
+  void microRewind() override {
+    std::lock_guard<std::mutex> lk(mMu_);
+    for (size_t i = 0; i < dBlocks_.size(); ++i) dBlocks_[i].used = i < dMarks_.size() ? dMarks_[i] : 0;
+    mNextEvent_ = mMarkEvent_;
+  }
   void* devAlloc(size_t bytes) {  // caller holds mMu_
     bytes = (bytes + 255) & ~(size_t) 255;
     for (DevBlock& b : dBlocks_) {
@@ -773,9 +797,13 @@ class CudaBackend : public Backend {
     CUDA_TRY(cudaMemcpyAsync(j.dOffsets, j.offsets, (size_t) j.n * 4, cudaMemcpyHostToDevice, st));
     return VCE_OK;
   }
-  int microGrid(int n) const {
+  int microGrid(int n, int cls) const {
     const int need = (n + kMicroThreads - 1) / kMicroThreads;
-    return std::max(1, std::min(need, smCount_ * microBlocksPerSm_));
+    return std::max(1, std::min(need, smCount_ * microBlocksPerSm_[cls]));
+  }
+  void microLaunch(const MicroParams& mp, int cls, cudaStream_t st) {
+    if (cls == 0) k_micro<MicroA><<<microGrid(mp.total, 0), kMicroThreads, kMicroThreads * MicroA::WS_BYTES, st>>>(mp);
+    else k_micro<MicroB><<<microGrid(mp.total, 1), kMicroThreads, kMicroThreads * MicroB::WS_BYTES, st>>>(mp);
   }
   int microRun(MicroJob& j, const MicroConfig& mc) override {
     CUDA_TRY(cudaSetDevice(device_));
@@ -788,7 +816,7 @@ class CudaBackend : public Backend {
     mp.nChunks = 1;
     mp.total = j.n;
     mp.cfg = mc;
-    k_micro<MicroA><<<microGrid(j.n), kMicroThreads, kMicroThreads * MicroA::WS_BYTES, st>>>(mp);
+    microLaunch(mp, j.cls, st);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(j.results, j.dResults, (size_t) j.n * j.resBytes, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(j.evHandle), st));
@@ -823,7 +851,7 @@ class CudaBackend : public Backend {
     mp.total = total;
     mp.cfg = mc;
     CUDA_TRY(cudaEventRecord(evM0_, st));
-    k_micro<MicroA><<<microGrid(total), kMicroThreads, kMicroThreads * MicroA::WS_BYTES, st>>>(mp);
+    microLaunch(mp, jobs[0]->cls, st);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(evM1_, st));
     for (MicroJob* j : jobs) {
@@ -837,8 +865,10 @@ class CudaBackend : public Backend {
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, evM0_, evM1_));
     stats.searchMs += ms;
-    lastMicroMs_ = ms;
-    lastMicroRegions_ = total;
+    if (total >= lastMicroRegions_ || jobs[0]->cls == 0) {
+      lastMicroMs_ = ms;
+      lastMicroRegions_ = total;
+    }
     return VCE_OK;
   }
   int microWait(MicroJob& j) override {
@@ -894,11 +924,13 @@ class CudaBackend : public Backend {
   static constexpr int kMicroLanes = 4;
   std::mutex mMu_;
   std::vector<DevBlock> dBlocks_;
+  std::vector<size_t> dMarks_;
+  int mMarkEvent_ = 0;
   cudaStream_t mStream_[kMicroLanes] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> mEvents_;
   int mNextEvent_ = 0, mNextLane_ = 0;
   cudaEvent_t evM0_ = nullptr, evM1_ = nullptr;
-  int microBlocksPerSm_ = 1;
+  int microBlocksPerSm_[2] = {1, 1};
   DevBuf<MicroChunkDesc> mTable_;
   std::string err_;
 };

@@ -68,11 +68,13 @@ struct RowPick {  // selects one orientation row of a variant (host side of K1, 
 }  // namespace
 
 Engine::Engine(Backend* b, WorkerPool* pool, const EngineOptions& o) : be_(b), pool_(pool), opt_(o) {
-  scratch_.resize(pool_->threads());
-  scratchOff_.resize(pool_->threads());
+  scratch_ = new std::vector<uint8_t>[pool_->threads()][2];
+  scratchOff_ = new std::vector<uint32_t>[pool_->threads()][2];
 }
 
 Engine::~Engine() {
+  delete[] scratch_;
+  delete[] scratchOff_;
   for (HostBlock& hb : arena_) be_->hostFree(hb.p);
 }
 
@@ -96,6 +98,16 @@ uint8_t* Engine::arenaAlloc(size_t bytes) {
 void Engine::arenaReset() {
   std::lock_guard<std::mutex> lk(arenaMu_);
   for (HostBlock& hb : arena_) hb.used = 0;
+  arenaMarks_.clear();
+}
+void Engine::arenaMark() {
+  std::lock_guard<std::mutex> lk(arenaMu_);
+  arenaMarks_.clear();
+  for (HostBlock& hb : arena_) arenaMarks_.push_back(hb.used);
+}
+void Engine::arenaRewind() {
+  std::lock_guard<std::mutex> lk(arenaMu_);
+  for (size_t i = 0; i < arena_.size(); ++i) arena_[i].used = i < arenaMarks_.size() ? arenaMarks_[i] : 0;
 }
 
 // ------------------------------------------------------------------------------------------- pass set-up
@@ -550,73 +562,92 @@ static inline long long nowNs() {
   return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// Builds the packets of a chunk -- the regions [r0, r1) of its sequence, or the explicit list ch.list -- one job per
+// packet class, copies them to page-locked memory and starts the upload (and the kernel when `launch`).
 int Engine::buildChunk(PassCtx& pc, Chunk& ch, int worker, bool launch) {
   const long long tA = nowNs();
   const int k = ch.seq;
-  std::vector<uint8_t>& sc = scratch_[worker];
-  std::vector<uint32_t>& so = scratchOff_[worker];
-  const int nr = ch.r1 - ch.r0;
-  sc.resize((size_t) nr * MicroA::PKT_MAX + 16);
-  so.resize(nr);
-  ch.pktRegion.clear();
-  ch.pktRegion.reserve(nr);
+  const bool listed = !ch.list.empty();
+  const int nr = listed ? (int) ch.list.size() : ch.r1 - ch.r0;
+  std::vector<uint8_t>* sc = scratch_[worker];
+  std::vector<uint32_t>* so = scratchOff_[worker];
+  sc[0].resize((size_t) nr * MicroA::PKT_MAX + 16);
+  so[0].resize(nr);
+  size_t at[2] = {0, 0};
+  int np[2] = {0, 0};
+  for (int c = 0; c < 2; ++c) {
+    ch.pktRegion[c].clear();
+    ch.job[c] = MicroJob();
+    ch.job[c].cls = c;
+  }
+  ch.pktRegion[0].reserve(nr);
   ch.variants = 0;
-  size_t at = 0;
   uint8_t* cls = pc.rcls[k].data();
   RegRes* rs = pc.rs[k].data();
-  int np = 0;
   const RegRange* rrk = pc.rr[k].data();
   const uint8_t* tmpl = seqs_[k].template_bases;
   const int nReg = (int) pc.rr[k].size();
   const int32_t* cs = pc.vStart[0].data();
   const int32_t* bs = pc.vStart[1].data();
-  for (int j = ch.r0; j < ch.r1; ++j) {
-    if (j + 12 < nReg) {  // the reference window of a region is a cache miss: request it well ahead
+  for (int q = 0; q < nr; ++q) {
+    const int j = listed ? ch.list[q] : ch.r0 + q;
+    if (!listed && j + 12 < nReg) {  // the reference window of a region is a cache miss: request it well ahead
       const RegRange& f = rrk[j + 12];
       const int32_t pos = f.cCount > 0 ? cs[f.cFirst] : (f.bCount > 0 ? bs[f.bFirst] : 0);
       __builtin_prefetch(tmpl + (pos > 0 ? pos - 1 : 0));
     }
-    int bytes = 0;
-    if (pc.microOk) bytes = buildPacket<MicroA>(pc, k, j, sc.data() + at);
+    int bytes = 0, c = 0;
+    if (pc.microOk) {
+      const RegRange& g = rrk[j];
+      if (g.cCount <= MicroA::KV && g.bCount <= MicroA::KV) {
+        bytes = buildPacket<MicroA>(pc, k, j, sc[0].data() + at[0]);
+      } else if (g.cCount <= MicroB::KV && g.bCount <= MicroB::KV) {
+        c = 1;
+        if (sc[1].size() < at[1] + MicroB::PKT_MAX + 16) sc[1].resize(std::max(sc[1].size() * 2, at[1] + (size_t) 64 * MicroB::PKT_MAX));
+        bytes = buildPacket<MicroB>(pc, k, j, sc[1].data() + at[1]);
+      }
+    }
     if (bytes > 0) {
-      so[np++] = (uint32_t) (at >> 2);
-      ch.pktRegion.push_back(j);
-      at += (size_t) bytes;
-      cls[j] = 1;
+      if (c == 1 && (int) so[1].size() <= np[1]) so[1].resize(std::max<size_t>(so[1].size() * 2, 64));
+      so[c][np[c]++] = (uint32_t) (at[c] >> 2);
+      ch.pktRegion[c].push_back(j);
+      at[c] += (size_t) bytes;
+      if (!ch.transient) cls[j] = (uint8_t) (1 + c);
       rs[j].state = RS_PENDING;
-      ch.variants += pc.rr[k][j].cCount + pc.rr[k][j].bCount;
+      ch.variants += rrk[j].cCount + rrk[j].bCount;
     } else {
-      cls[j] = 0;
+      if (!ch.transient) cls[j] = 0;
       rs[j].state = RS_RESIDUAL;
     }
   }
   const long long tB = nowNs();
   g_tBuild += tB - tA;
-  MicroJob& job = ch.job;
-  job = MicroJob();
-  job.cls = 0;
-  job.n = np;
-  job.resBytes = MicroA::RES_BYTES;
-  if (np == 0) return VCE_OK;
-  uint8_t* pk = arenaAlloc(at + 16);
-  uint8_t* off = arenaAlloc((size_t) np * 4);
-  uint8_t* res = arenaAlloc((size_t) np * MicroA::RES_BYTES);
-  if (!pk || !off || !res) {
-    std::lock_guard<std::mutex> lk(errMu_);
-    err_ = "out of page-locked host memory";
-    return VCE_ERR_CUDA;
+  int rc = VCE_OK;
+  for (int c = 0; c < 2 && rc == VCE_OK; ++c) {
+    MicroJob& job = ch.job[c];
+    job.n = np[c];
+    job.resBytes = c == 0 ? MicroA::RES_BYTES : MicroB::RES_BYTES;
+    if (np[c] == 0) continue;
+    uint8_t* pk = arenaAlloc(at[c] + 16);
+    uint8_t* off = arenaAlloc((size_t) np[c] * 4);
+    uint8_t* res = arenaAlloc((size_t) np[c] * job.resBytes);
+    if (!pk || !off || !res) {
+      std::lock_guard<std::mutex> lk(errMu_);
+      err_ = "out of page-locked host memory";
+      return VCE_ERR_CUDA;
+    }
+    std::memcpy(pk, sc[c].data(), at[c]);
+    std::memcpy(off, so[c].data(), (size_t) np[c] * 4);
+    job.packets = pk;
+    job.packetBytes = at[c];
+    job.offsets = reinterpret_cast<const uint32_t*>(off);
+    job.results = res;
+    const long long tC = nowNs();
+    rc = be_->microUpload(job);
+    if (rc == VCE_OK && launch) rc = be_->microRun(job, pc.mc);
+    g_tUpload += nowNs() - tC;
   }
-  std::memcpy(pk, sc.data(), at);
-  std::memcpy(off, so.data(), (size_t) np * 4);
-  job.packets = pk;
-  job.packetBytes = at;
-  job.offsets = reinterpret_cast<const uint32_t*>(off);
-  job.results = res;
-  const long long tC = nowNs();
-  g_tCopy += tC - tB;
-  int rc = be_->microUpload(job);
-  if (rc == VCE_OK && launch) rc = be_->microRun(job, pc.mc);
-  g_tUpload += nowNs() - tC;
+  g_tCopy += nowNs() - tB;
   if (rc) {
     std::lock_guard<std::mutex> lk(errMu_);
     err_ = be_->lastError();
@@ -624,10 +655,8 @@ int Engine::buildChunk(PassCtx& pc, Chunk& ch, int worker, bool launch) {
   return rc;
 }
 
-void Engine::decodeChunk(PassCtx& pc, Chunk& ch, int64_t& iterations) {
-  typedef MicroA T;
-  const int k = ch.seq;
-  const MicroJob& job = ch.job;
+template <class T>
+void Engine::decodeJob(PassCtx& pc, int k, const MicroJob& job, const std::vector<int32_t>& pktRegion, int64_t& iterations) {
   RegRes* rs = pc.rs[k].data();
   const RegRange* rr = pc.rr[k].data();
   uint8_t* dc = pc.decision[0].data();
@@ -636,7 +665,7 @@ void Engine::decodeChunk(PassCtx& pc, Chunk& ch, int64_t& iterations) {
   int64_t it = 0;
   for (int q = 0; q < job.n; ++q) {
     const uint8_t* rec = job.results + (size_t) q * T::RES_BYTES;
-    const int j = ch.pktRegion[q];
+    const int j = pktRegion[q];
     RegRes& s = rs[j];
     it += rec[MR_ITERS] | (rec[MR_ITERS + 1] << 8);
     if (rec[MR_STATUS] != kMicroClean) { s.state = RS_RESIDUAL; continue; }
@@ -656,6 +685,11 @@ void Engine::decodeChunk(PassCtx& pc, Chunk& ch, int64_t& iterations) {
     for (int i = 0; i < g.bCount; ++i) db[g.bFirst + i] = dec[T::KV + i];
   }
   iterations += it;
+}
+
+void Engine::decodeChunk(PassCtx& pc, Chunk& ch, int64_t& iterations) {
+  decodeJob<MicroA>(pc, ch.seq, ch.job[0], ch.pktRegion[0], iterations);
+  decodeJob<MicroB>(pc, ch.seq, ch.job[1], ch.pktRegion[1], iterations);
 }
 
 // ------------------------------------------------------------------------------------------- life cycle
@@ -688,6 +722,8 @@ int Engine::prepare(const vce_config& cfg, int32_t nSeq, const vce_sequence* seq
       if (r) failed.store(r);
     });
     if (failed.load()) return failed.load();
+    arenaMark();
+    be_->microMark();
     tm.lap("packets + upload");
     if (tm.on) {
       std::fprintf(stderr, "[vce]   summed over workers: build %.1f ms, copy to page-locked %.1f ms, upload calls %.1f ms\n",
@@ -760,21 +796,29 @@ int Engine::execute() {
                      g_tBuild.exchange(0) / 1e6, g_tCopy.exchange(0) / 1e6, g_tUpload.exchange(0) / 1e6);
       }
     } else {
-      if (executed_) resetPassRun(pc);
-      std::vector<MicroJob*> jobs;
-      for (Chunk& ch : pc.chunks) if (ch.job.n > 0) jobs.push_back(&ch.job);
-      if (!jobs.empty()) {
-        const int r = be_->microRunAll(jobs, pc.mc);
-        if (r) { err_ = be_->lastError(); return r; }
+      if (executed_) {
+        resetPassRun(pc);
+        arenaRewind();
+        be_->microRewind();
+      }
+      for (int c = 0; c < 2; ++c) {
+        std::vector<MicroJob*> jobs;
+        for (Chunk& ch : pc.chunks) if (ch.job[c].n > 0) jobs.push_back(&ch.job[c]);
+        if (!jobs.empty()) {
+          const int r = be_->microRunAll(jobs, pc.mc);
+          if (r) { err_ = be_->lastError(); return r; }
+        }
       }
     }
     if (failed.load()) return failed.load();
     std::vector<int64_t> iters(pool_->threads(), 0);
     pool_->parallelFor((int) pc.chunks.size(), [&](int t, int worker) {
       Chunk& ch = pc.chunks[t];
-      if (ch.job.n > 0) {
-        const int r = be_->microWait(ch.job);
-        if (r) { failed.store(r); return; }
+      for (int c = 0; c < 2; ++c) {
+        if (ch.job[c].n > 0) {
+          const int r = be_->microWait(ch.job[c]);
+          if (r) { failed.store(r); return; }
+        }
       }
       decodeChunk(pc, ch, iters[worker]);
     });
@@ -783,7 +827,7 @@ int Engine::execute() {
     for (int64_t v : iters) be_->stats.iterations += v;
     for (const Chunk& ch : pc.chunks) {
       be_->stats.regions += ch.r1 - ch.r0;
-      microRegions += ch.job.n;
+      microRegions += ch.job[0].n + ch.job[1].n;
       microVariants += ch.variants;
     }
     if ((rc = settle(pc))) return rc;
@@ -939,7 +983,14 @@ int Engine::wideLaunch(PassCtx& pc, const std::vector<RegKey>& ids, int tier, st
   if ((rc = be_->search(pd, sc, descs, windows, tier, false, out, syncOff, so, warns))) { err_ = be_->lastError(); return rc; }
   if (std::getenv("VCE_TIMING")) {
     long long it = 0, nv = 0;
-    for (size_t q = 0; q < out.size(); ++q) { it += out[q].iterations; nv += descs[q].cCount + descs[q].bCount; }
+    int maxIt = 0, maxItVars = 0, maxF = 0;
+    for (size_t q = 0; q < out.size(); ++q) {
+      it += out[q].iterations;
+      nv += descs[q].cCount + descs[q].bCount;
+      if (out[q].iterations > maxIt) { maxIt = out[q].iterations; maxItVars = descs[q].cCount + descs[q].bCount; }
+      maxF = std::max(maxF, out[q].maxFrontier);
+    }
+    std::fprintf(stderr, "[vce]   longest region: %d iterations (%d variants), largest frontier %d\n", maxIt, maxItVars, maxF);
     std::fprintf(stderr, "[vce]   wide launch: %zu regions, %lld variants, tier %d, %lld iterations, kernel %.2f ms\n", ids.size(), nv,
                  tier, it, be_->stats.searchMs - searchBefore);
   }
@@ -1030,7 +1081,31 @@ int Engine::settle(PassCtx& pc) {
     for (int t = 0; t <= kTierGeneral; ++t) if (!todo[t].empty()) return true;
     return false;
   };
+  std::vector<RegKey> retry;  // merged regions: their new shape may fit the thread-per-region kernel
   for (int round = 0; round < 100000; ++round) {
+    if (!retry.empty()) {
+      std::sort(retry.begin(), retry.end(), [](const RegKey& a, const RegKey& b) { return a.seq != b.seq ? a.seq < b.seq : a.j < b.j; });
+      std::vector<Chunk> rch;
+      for (const RegKey& id : retry) {
+        if (rch.empty() || rch.back().seq != id.seq) {
+          rch.emplace_back();
+          rch.back().seq = id.seq;
+          rch.back().transient = true;
+        }
+        rch.back().list.push_back(id.j);
+      }
+      for (Chunk& ch : rch) if ((rc = buildChunk(pc, ch, 0, true))) return rc;
+      int64_t it = 0;
+      for (Chunk& ch : rch) {
+        for (int c = 0; c < 2; ++c) if (ch.job[c].n > 0 && (rc = be_->microWait(ch.job[c]))) { err_ = be_->lastError(); return rc; }
+        decodeChunk(pc, ch, it);
+      }
+      be_->stats.iterations += it;
+      for (const RegKey& id : retry) {
+        if (pc.rs[id.seq][id.j].state == RS_RESIDUAL) todo[startTier(pc, pc.rr[id.seq][id.j])].push_back(id);
+      }
+      retry.clear();
+    }
     if (!pending()) {
       // prefix-dependent tie-breaks: re-run the first region per sequence whose assumption was wrong
       std::vector<int> fix(nSeq_, -1);
@@ -1066,6 +1141,7 @@ int Engine::settle(PassCtx& pc) {
       }
       if (!pending()) break;
     }
+    if (!pending() && !retry.empty()) continue;
     // run every tier's list, then inspect in sequence order so that chains of spilling regions merge front to back
     std::vector<std::pair<RegKey, int>> all;
     std::vector<int> allTier;
@@ -1117,7 +1193,12 @@ int Engine::settle(PassCtx& pc) {
             nx = nextAlive(k, nx);
           }
           ra.extraMargin = 0;
-          todo[startTier(pc, g)].push_back(all[q].first);
+          if (pc.microOk && !ra.microTried && !ra.hasPrefix) {
+            ra.microTried = true;
+            retry.push_back(all[q].first);
+          } else {
+            todo[startTier(pc, g)].push_back(all[q].first);
+          }
         }
         pc.rs[k][j].state = RS_RESIDUAL;
       }

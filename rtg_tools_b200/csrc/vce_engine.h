@@ -75,13 +75,16 @@ class Engine {
     int extraMargin = 0;      // reference bases added after a window miss (< 0: rest of the template)
     int assumedPrefix = 0;
     bool hasPrefix = false;   // an explicit prefix was set (otherwise the default assumption)
+    bool microTried = false;  // the (merged) region already went through the thread-per-region kernel
     int tier = 0;             // warp-per-region tier of the last run (kTierGeneral = large-capacity kernel)
     int lastStatus = 0;       // kRegion* of the last wide run
   };
   struct Chunk {
     int seq = 0, r0 = 0, r1 = 0;
-    MicroJob job;
-    std::vector<int32_t> pktRegion;   // packet -> region index within the sequence
+    std::vector<int32_t> list;           // explicit region indices (settling), empty = the range [r0, r1)
+    bool transient = false;              // settling: leaves the per-region packet class of the main chunks alone
+    MicroJob job[2];                     // one job per packet class (MicroA, MicroB)
+    std::vector<int32_t> pktRegion[2];   // packet -> region index within the sequence
     int64_t variants = 0;
   };
   struct WarnEntry { int32_t seq, j; WarnRec w; };
@@ -111,6 +114,8 @@ class Engine {
   static uint64_t key(int seq, int j) { return ((uint64_t) (uint32_t) seq << 32) | (uint32_t) j; }
   uint8_t* arenaAlloc(size_t bytes);
   void arenaReset();
+  void arenaMark();
+  void arenaRewind();
 
   int setupPass0();
   int setupPass1();
@@ -123,6 +128,7 @@ class Engine {
   int buildChunk(PassCtx& pc, Chunk& ch, int worker, bool launch);
   int runChunks(PassCtx& pc);
   void decodeChunk(PassCtx& pc, Chunk& ch, int64_t& iterations);
+  template <class T> void decodeJob(PassCtx& pc, int k, const MicroJob& job, const std::vector<int32_t>& pktRegion, int64_t& iterations);
   int settle(PassCtx& pc);
   int wideLaunch(PassCtx& pc, const std::vector<RegKey>& ids, int tier, std::vector<int>& statusOut);
   int startTier(const PassCtx& pc, const RegRange& g) const;
@@ -146,11 +152,12 @@ class Engine {
   std::mutex errMu_;
   std::mutex arenaMu_;
   std::vector<HostBlock> arena_;
+  std::vector<size_t> arenaMarks_;
   std::vector<std::vector<int32_t>> seqSync_[2];   // [pass][seq] sync points (assembly)
   std::vector<std::vector<uint8_t>> seqDec1_[2];   // [side][seq] pass-2 decision by input index
   std::vector<std::vector<double>> seqW1_;         // [seq] pass-2 call weight by input index
-  std::vector<std::vector<uint8_t>> scratch_;   // per worker
-  std::vector<std::vector<uint32_t>> scratchOff_;
+  std::vector<uint8_t> (*scratch_)[2] = nullptr;     // [worker][class] packet staging
+  std::vector<uint32_t> (*scratchOff_)[2] = nullptr;
 };
 
 }  // namespace vce

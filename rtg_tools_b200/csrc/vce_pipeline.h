@@ -82,6 +82,8 @@ class Backend {
   virtual void* hostAlloc(size_t bytes) = 0;   // page-locked on the CUDA backend
   virtual void hostFree(void* p) = 0;
   virtual int microReset() = 0;                               // forgets the device buffers of earlier jobs
+  virtual void microMark() {}                                 // remembers the device buffers allocated so far ...
+  virtual void microRewind() {}                               // ... and forgets everything allocated after the mark
   virtual int microUpload(MicroJob& j) = 0;                   // async host -> device copy of packets and offsets
   virtual int microRun(MicroJob& j, const MicroConfig& mc) = 0;  // async kernel + device -> host copy of the results
   // one kernel launch over all (uploaded) jobs + one async result copy per job: the staged / HBM-resident path

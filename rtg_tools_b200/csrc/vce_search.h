@@ -89,14 +89,26 @@ VCE_HD int vffs(unsigned x) {  // index of lowest set bit, x != 0
 }
 
 // ---- the search -------------------------------------------------------------------------------------
+// Warp-uniform, read-only state of one region's search.  On the device it lives in SHARED memory (one copy per warp,
+// broadcast reads): kept in the thread-local frame it would be spilled to local memory, and with the L1 carve-out
+// given to shared memory every access of the serial part would then go to L2.
+struct RegionConst {
+  RegionDesc R;
+  SearchConfig cfg;
+  PathLayout L;
+  SideArrays S[2];       // 0 = calls, 1 = baseline
+};
+
 template <class WP>
 struct RegionSearch {
   WP w;
-  RegionDesc R;
-  SearchConfig cfg;
-  SideArrays S[2];       // 0 = calls, 1 = baseline
+  RegionConst* K;        // see RegionConst
+  RegionDesc& R;
+  SearchConfig& cfg;
+  SideArrays* S;         // [2]
+  PathLayout& L;
   const uint8_t* win;    // reference window bases for this region (0..4 per byte)
-  PathLayout L;
+  VCE_HD explicit RegionSearch(RegionConst* k) : K(k), R(k->R), cfg(k->cfg), S(k->S), L(k->L) {}
   int32_t* slots;        // (nSlots + 2) path records: [nSlots] = last-sync path, [nSlots+1] = best finished path
   int32_t* order;        // sorted frontier as a deque: logical element i lives at order[oh + i]; [0] is the least path
   int32_t* freeList;     // stack of free slot ids

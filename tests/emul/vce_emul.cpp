@@ -30,17 +30,21 @@ class EmulBackend : public Backend {
   void hostFree(void* p) override { std::free(p); }
   int microReset() override { return 0; }
   int microUpload(MicroJob&) override { return 0; }
-  int microRun(MicroJob& j, const MicroConfig& mc) override {
-    std::vector<uint8_t> ws(MicroA::WS_BYTES + 16);
+  template <class T>
+  void microRunT(MicroJob& j, const MicroConfig& mc) {
+    std::vector<uint8_t> ws(T::WS_BYTES + 16);
     for (int q = 0; q < j.n; ++q) {
-      MicroSearch<MicroA> ms;
+      MicroSearch<T> ms;
       ms.ws = ws.data();
       ms.cfg = mc;
       const uint8_t* src = j.packets + (size_t) j.offsets[q] * 4;
-      std::memcpy(ws.data() + MicroA::OFF_PKT, src, (size_t) src[MP_NWORDS] * 4);
+      std::memcpy(ws.data() + T::OFF_PKT, src, (size_t) src[MP_NWORDS] * 4);
       ms.runRegion(j.results + (size_t) q * j.resBytes);
       if (j.results[(size_t) q * j.resBytes + MR_STATUS] == kMicroClean) ++microClean;
     }
+  }
+  int microRun(MicroJob& j, const MicroConfig& mc) override {
+    if (j.cls == 0) microRunT<MicroA>(j, mc); else microRunT<MicroB>(j, mc);
     microRegions += j.n;
     ++stats.launches;
     return 0;
@@ -98,7 +102,8 @@ class EmulBackend : public Backend {
     std::vector<int32_t>& syncOut = sync_[pd.pass];
     if (syncOut.size() < syncTotal) syncOut.resize(syncTotal, 0);
     for (size_t q = 0; q < regs.size(); ++q) {
-      RegionSearch<HostLane> rs;
+      RegionConst rk;
+      RegionSearch<HostLane> rs(&rk);
       rs.R = regs[q];
       rs.cfg = sc;
       for (int side = 0; side < 2; ++side) {
