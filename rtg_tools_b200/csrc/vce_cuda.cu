@@ -99,6 +99,7 @@ struct SearchParams {
   FastShape fs;          // shared-memory kernel: capacities of the tier
   int wordsPerWarp;      // shared-memory words per warp (whole layout)
   int tabBytes;          // shared memory per warp for the region's tables
+  int regionBase;        // index of regs[0] within the batch (warnings carry batch-wide region indices)
 };
 
 constexpr int kWarnPerRegion = 64;
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(kFastWarps * 32) k_search(const __grid_constan
       kc->S[1] = p.S[1];
       if (GENERAL) kc->L.init(p.H, kc->R.qMax, max(1, max(kc->R.cCount, kc->R.bCount)), kc->R.cCount + kc->R.bCount + 2, kc->R.decBits);
     }
-    rs.regionId = r;
+    rs.regionId = p.regionBase + r;
     __syncwarp();
     stageTables(rs, p.S, p.H, tabS, p.tabBytes, lane);
     if (GENERAL) {
@@ -286,6 +287,7 @@ struct MicroParams {
   const MicroChunkDesc* table;   // multi-chunk launch (nullptr = use `one`)
   int nChunks;
   int total;
+  int refill;                    // idle lanes of a warp take new regions once at least this many lanes are idle
   MicroConfig cfg;
 };
 constexpr int kMicroThreads = 64;
@@ -303,7 +305,11 @@ __global__ void __launch_bounds__(kMicroThreads) k_micro(const __grid_constant__
   uint8_t* resOut = nullptr;
   while (true) {
     __syncwarp();
-    if (!running && r < p.total) {
+    // Lanes that start their regions together run in lock step as long as the regions behave alike (most regions of a
+    // genome are alike), so idle lanes wait until a group of them can start together.
+    const unsigned idle = __ballot_sync(0xffffffffu, !running);
+    const bool take = __popc(idle) >= p.refill || idle == 0xffffffffu;
+    if (take && !running && r < p.total) {
       MicroChunkDesc c = p.one;
       if (p.table != nullptr) {
         int lo = 0, hi = p.nChunks - 1;  // last chunk whose first region is <= r
@@ -324,7 +330,7 @@ __global__ void __launch_bounds__(kMicroThreads) k_micro(const __grid_constant__
       ms.begin();
       running = true;
     }
-    if (__all_sync(0xffffffffu, !running)) break;
+    if (__all_sync(0xffffffffu, !running)) break;  // nothing left for any lane
     if (running) {
       const int st = ms.iterate(slot);
       if (st != kMicroPending) {
@@ -416,6 +422,7 @@ class CudaBackend : public Backend {
       microBlocksPerSm_[0] = perSm < 1 ? 1 : perSm;
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_micro<MicroB>, kMicroThreads, kMicroThreads * MicroB::WS_BYTES));
       microBlocksPerSm_[1] = perSm < 1 ? 1 : perSm;
+      if (const char* e = std::getenv("VCE_MICRO_REFILL")) microRefill_ = std::max(1, std::min(32, std::atoi(e)));
     }
     ready_ = true;
     return VCE_OK;
@@ -571,117 +578,137 @@ class CudaBackend : public Backend {
   }
 
   int search(PassData& pd, const SearchConfig& sc, const std::vector<RegionDesc>& regs, const std::vector<uint8_t>& windows,
-             int tier, bool staged, std::vector<RegionResult>& out, const std::vector<int32_t>& syncOff, size_t syncTotal,
+             int tier, bool /*staged*/, std::vector<RegionResult>& out, const std::vector<int32_t>& syncOff, size_t syncTotal,
              std::vector<WarnRec>& warns) override {
-    const bool general = tier >= kTierGeneral;
+    int tierFirst[kTierGeneral + 2];
+    for (int t = 0; t <= kTierGeneral + 1; ++t) tierFirst[t] = t <= tier ? 0 : (int) regs.size();
+    const int rc = searchStart(pd, sc, regs, windows, tierFirst, syncOff, syncTotal);
+    if (rc) return rc;
+    return searchFinish(out, warns);
+  }
+
+  int searchStart(PassData& pd, const SearchConfig& sc, const std::vector<RegionDesc>& regs, const std::vector<uint8_t>& windows,
+                  const int* tierFirst, const std::vector<int32_t>& syncOff, size_t syncTotal) override {
     CUDA_TRY(cudaSetDevice(device_));
     curPass_ = pd.pass;
     const size_t nr = regs.size();
+    inFlight_ = nr;
+    inFlightLaunches_ = 0;
     if (nr == 0) return VCE_OK;
     CUDA_TRY(rres_.ensure(nr));
     CUDA_TRY(ints_.ensure(16));
     CUDA_TRY(ensureSync(syncTotal));
     const int warnCap = 1 << 16;
     CUDA_TRY(warns_.ensure(warnCap));
-    const RegionDesc* dRegs;
-    const int32_t* dSyncOff;
-    const uint8_t* dWindows;
-    if (staged) {
-      dRegs = sRegs_.p; dSyncOff = sSyncOff_.p; dWindows = sWindows_.p;
-    } else {
-      CUDA_TRY(regs_.ensure(nr)); CUDA_TRY(syncOff_.ensure(nr)); CUDA_TRY(windows_.ensure(windows.size() + 64));
-      CUDA_TRY(cudaMemcpyAsync(regs_.p, regs.data(), nr * sizeof(RegionDesc), cudaMemcpyHostToDevice, stream_));
-      CUDA_TRY(cudaMemcpyAsync(syncOff_.p, syncOff.data(), nr * 4, cudaMemcpyHostToDevice, stream_));
-      CUDA_TRY(cudaMemcpyAsync(windows_.p, windows.data(), windows.size(), cudaMemcpyHostToDevice, stream_));
-      stats.h2dBytes += (int64_t) (nr * (sizeof(RegionDesc) + 4) + windows.size());
-      dRegs = regs_.p; dSyncOff = syncOff_.p; dWindows = windows_.p;
+    CUDA_TRY(regs_.ensure(nr)); CUDA_TRY(syncOff_.ensure(nr)); CUDA_TRY(windows_.ensure(windows.size() + 64));
+    CUDA_TRY(cudaMemcpyAsync(regs_.p, regs.data(), nr * sizeof(RegionDesc), cudaMemcpyHostToDevice, stream_));
+    CUDA_TRY(cudaMemcpyAsync(syncOff_.p, syncOff.data(), nr * 4, cudaMemcpyHostToDevice, stream_));
+    CUDA_TRY(cudaMemcpyAsync(windows_.p, windows.data(), windows.size(), cudaMemcpyHostToDevice, stream_));
+    stats.h2dBytes += (int64_t) (nr * (sizeof(RegionDesc) + 4) + windows.size());
+    CUDA_TRY(cudaMemsetAsync(ints_.p + 4, 0, 8 * sizeof(int), stream_));  // [4..6] work counters per tier, [7] warning count
+
+    // arena / scratch sizes over all tiers first (buffers must not move between the launches)
+    int blocksT[kTierGeneral + 1] = {0, 0, 0}, threadsT[kTierGeneral + 1] = {0, 0, 0};
+    size_t smemT[kTierGeneral + 1] = {0, 0, 0};
+    SearchParams spT[kTierGeneral + 1];
+    int maxWarps = 0;
+    for (int tier = 0; tier <= kTierGeneral; ++tier) {
+      const int r0 = tierFirst[tier], r1 = tierFirst[tier + 1];
+      if (r1 <= r0) continue;
+      const bool general = tier >= kTierGeneral;
+      const size_t nt = (size_t) (r1 - r0);
+      SearchParams& sp = spT[tier];
+      std::memset(&sp, 0, sizeof(sp));
+      sp.regs = regs_.p + r0; sp.nRegs = (int) nt;
+      sp.S[0] = sideArrays(0); sp.S[1] = sideArrays(1);
+      sp.windows = windows_.p; sp.cfg = sc; sp.out = rres_.p + r0; sp.syncOff = syncOff_.p + r0; sp.syncOut = syncBuf_.p;
+      sp.warns = warns_.p; sp.warnCount = ints_.p + 7; sp.warnCap = warnCap; sp.counter = ints_.p + 4 + tier;
+      sp.H = pd.H;
+      sp.maxChildren = 1 + std::max(pd.maxOrient[0], pd.maxOrient[1]);
+      sp.regionBase = r0;
+      int blocks = 0, threads = kFastWarps * 32;
+      size_t smemBytes = 0;
+      if (!general) {
+        const FastShape fs = fastShape(tier);
+        sp.fs = fs;
+        PathLayout LM;
+        LM.init(2, fs.q, fs.kv, fs.smax, 4);
+        const int preWords = (fs.slots() + 2) * LM.W + fs.ordCap() + fs.slots();
+        const int ctlWords = ((preWords + 16 + 2 * fs.maxChildren + 3) & ~3) - preWords;
+        sp.winSmemBytes = 256;
+        sp.tabBytes = fs.tabBytes;
+        const int kcWords = (int) ((sizeof(RegionConst) + 15) / 16) * 4;
+        sp.wordsPerWarp = kcWords + preWords + ctlWords + (sp.tabBytes + sp.winSmemBytes) / 4;
+        const size_t bytesPerWarp = (size_t) sp.wordsPerWarp * 4;
+        int warpsPerBlock = (int) std::min<size_t>(kFastWarps, (size_t) maxSmemOptin_ / bytesPerWarp);
+        if (warpsPerBlock < 1) { err_ = "fast kernel shared memory exceeds the device limit"; return VCE_ERR_CUDA; }
+        // prefer several smaller blocks per SM over one large one
+        if (warpsPerBlock < kFastWarps) warpsPerBlock = std::max(1, (int) ((size_t) maxSmemOptin_ / bytesPerWarp) / 2);
+        threads = warpsPerBlock * 32;
+        smemBytes = bytesPerWarp * warpsPerBlock;
+        int perSm = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_search<false>, threads, smemBytes));
+        if (perSm < 1) perSm = 1;
+        blocks = smCount_ * perSm;
+        const int need = (int) ((nt + warpsPerBlock - 1) / warpsPerBlock);
+        if (blocks > need) blocks = need;
+      } else {
+        // per-warp arena sized for the largest record layout in this launch at the full search budget
+        long long maxW = 0;
+        for (int q = r0; q < r1; ++q) maxW = std::max(maxW, (long long) regs[q].layoutW);
+        const long long mc = sp.maxChildren;
+        const long long capFull = (long long) sc.maxPaths + 1 + mc;
+        long long words = (capFull + 1 + mc + 2) * maxW + (2 * capFull + 2) + (capFull + 1 + mc) + 16 + 2 * mc + 64;
+        const long long budgetWords = (long long) (48ull << 30) / 4;  // 48 GB of HBM for search arenas
+        long long warpsWanted = std::min<long long>((long long) nt, (long long) smCount_ * kFastWarps);
+        if (words > budgetWords) words = budgetWords;  // a single region larger than the budget runs with reduced capacity
+        long long warpsFit = std::max<long long>(1, budgetWords / words);
+        long long nw = std::min(warpsWanted, warpsFit);
+        blocks = (int) ((nw + kFastWarps - 1) / kFastWarps);
+        const size_t totalWords = (size_t) blocks * kFastWarps * (size_t) words;
+        CUDA_TRY(arena_.ensure(totalWords));
+        sp.arena = arena_.p;
+        sp.arenaWordsPerWarp = words;
+        sp.tabBytes = 4096;
+        const int kcWords = (int) ((sizeof(RegionConst) + 15) / 16) * 4;
+        smemBytes = ((size_t) sp.tabBytes + (size_t) kcWords * 4) * kFastWarps;
+      }
+      blocksT[tier] = blocks; threadsT[tier] = threads; smemT[tier] = smemBytes;
+      maxWarps = std::max(maxWarps, blocks * (threads / 32));
     }
-    CUDA_TRY(cudaMemsetAsync(ints_.p + 4, 0, 2 * sizeof(int), stream_));  // [4] work counter, [5] warning count
-
-    SearchParams sp;
-    std::memset(&sp, 0, sizeof(sp));
-    sp.regs = dRegs; sp.nRegs = (int) nr;
-    sp.S[0] = sideArrays(0); sp.S[1] = sideArrays(1);
-    sp.windows = dWindows; sp.cfg = sc; sp.out = rres_.p; sp.syncOff = dSyncOff; sp.syncOut = syncBuf_.p;
-    sp.warns = warns_.p; sp.warnCount = ints_.p + 5; sp.warnCap = warnCap; sp.counter = ints_.p + 4;
-    sp.H = pd.H;
-    sp.maxChildren = 1 + std::max(pd.maxOrient[0], pd.maxOrient[1]);
-
-    int blocks = 0, threads = kFastWarps * 32;
-    size_t smemBytes = 0;
-    if (!general) {
-      const FastShape fs = fastShape(tier);
-      sp.fs = fs;
-      PathLayout LM;
-      LM.init(2, fs.q, fs.kv, fs.smax, 4);
-      const int preWords = (fs.slots() + 2) * LM.W + fs.ordCap() + fs.slots();
-      const int ctlWords = ((preWords + 16 + 2 * fs.maxChildren + 3) & ~3) - preWords;
-      sp.winSmemBytes = 256;
-      sp.tabBytes = fs.tabBytes;
-      const int kcWords = (int) ((sizeof(RegionConst) + 15) / 16) * 4;
-      sp.wordsPerWarp = kcWords + preWords + ctlWords + (sp.tabBytes + sp.winSmemBytes) / 4;
-      const size_t bytesPerWarp = (size_t) sp.wordsPerWarp * 4;
-      int warpsPerBlock = (int) std::min<size_t>(kFastWarps, (size_t) maxSmemOptin_ / bytesPerWarp);
-      if (warpsPerBlock < 1) { err_ = "fast kernel shared memory exceeds the device limit"; return VCE_ERR_CUDA; }
-      // prefer several smaller blocks per SM over one large one
-      if (warpsPerBlock < kFastWarps) warpsPerBlock = std::max(1, (int) ((size_t) maxSmemOptin_ / bytesPerWarp) / 2);
-      threads = warpsPerBlock * 32;
-      smemBytes = bytesPerWarp * warpsPerBlock;
-      int perSm = 0;
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_search<false>, threads, smemBytes));
-      if (perSm < 1) perSm = 1;
-      blocks = smCount_ * perSm;
-      const int need = (int) ((nr + warpsPerBlock - 1) / warpsPerBlock);
-      if (blocks > need) blocks = need;
-    } else {
-      // per-warp arena sized for the largest record layout in this launch at the full search budget
-      long long maxW = 0;
-      for (const RegionDesc& d : regs) maxW = std::max(maxW, (long long) d.layoutW);
-      const long long mc = sp.maxChildren;
-      const long long capFull = (long long) sc.maxPaths + 1 + mc;
-      long long words = (capFull + 1 + mc + 2) * maxW + (2 * capFull + 2) + (capFull + 1 + mc) + 16 + 2 * mc + 64;
-      const long long budgetWords = (long long) (48ull << 30) / 4;  // 48 GB of HBM for search arenas
-      long long warpsWanted = std::min<long long>((long long) nr, (long long) smCount_ * kFastWarps);
-      if (words > budgetWords) words = budgetWords;  // a single region larger than the budget runs with reduced capacity
-      long long warpsFit = std::max<long long>(1, budgetWords / words);
-      long long nw = std::min(warpsWanted, warpsFit);
-      blocks = (int) ((nw + kFastWarps - 1) / kFastWarps);
-      const size_t totalWords = (size_t) blocks * kFastWarps * (size_t) words;
-      CUDA_TRY(arena_.ensure(totalWords));
-      sp.arena = arena_.p;
-      sp.arenaWordsPerWarp = words;
-      sp.tabBytes = 4096;
-      const int kcWords = (int) ((sizeof(RegionConst) + 15) / 16) * 4;
-      smemBytes = ((size_t) sp.tabBytes + (size_t) kcWords * 4) * kFastWarps;
-    }
-    CUDA_TRY(warnScratch_.ensure((size_t) blocks * kFastWarps * kWarnPerRegion));
-    sp.warnScratch = warnScratch_.p;
-
+    CUDA_TRY(warnScratch_.ensure((size_t) std::max(1, maxWarps) * kWarnPerRegion));
     CUDA_TRY(cudaEventRecord(ev0_, stream_));
-    if (general) k_search<true><<<blocks, threads, smemBytes, stream_>>>(sp);
-    else k_search<false><<<blocks, threads, smemBytes, stream_>>>(sp);
-    CUDA_TRY(cudaGetLastError());
+    for (int tier = 0; tier <= kTierGeneral; ++tier) {
+      if (blocksT[tier] == 0) continue;
+      spT[tier].warnScratch = warnScratch_.p;
+      if (tier >= kTierGeneral) k_search<true><<<blocksT[tier], threadsT[tier], smemT[tier], stream_>>>(spT[tier]);
+      else k_search<false><<<blocksT[tier], threadsT[tier], smemT[tier], stream_>>>(spT[tier]);
+      CUDA_TRY(cudaGetLastError());
+      ++stats.launches;
+      ++inFlightLaunches_;
+      if (std::getenv("VCE_TIMING")) {
+        fprintf(stderr, "[vce]     k_search tier %d: %d regions, %d blocks x %d threads, %zu B shared memory per block\n", tier,
+                tierFirst[tier + 1] - tierFirst[tier], blocksT[tier], threadsT[tier], smemT[tier]);
+      }
+    }
     CUDA_TRY(cudaEventRecord(ev1_, stream_));
-    ++stats.launches;
+    return VCE_OK;
+  }
+
+  int searchFinish(std::vector<RegionResult>& out, std::vector<WarnRec>& warns) override {
+    CUDA_TRY(cudaSetDevice(device_));
+    const size_t nr = inFlight_;
     out.resize(nr);
+    if (nr == 0) return VCE_OK;
     int nWarn = 0;
+    const int warnCap = 1 << 16;
     CUDA_TRY(cudaMemcpyAsync(out.data(), rres_.p, nr * sizeof(RegionResult), cudaMemcpyDeviceToHost, stream_));
-    CUDA_TRY(cudaMemcpyAsync(&nWarn, ints_.p + 5, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    CUDA_TRY(cudaMemcpyAsync(&nWarn, ints_.p + 7, sizeof(int), cudaMemcpyDeviceToHost, stream_));
     CUDA_TRY(cudaStreamSynchronize(stream_));
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, ev0_, ev1_));
     stats.searchMs += ms;
     stats.d2hBytes += (int64_t) (nr * sizeof(RegionResult));
-    if (std::getenv("VCE_TIMING")) {
-      fprintf(stderr, "[vce]     k_search tier %d: %d blocks x %d threads, %zu B shared memory per block\n", tier, blocks, threads, smemBytes);
-    }
-    if (!general && (long long) nr >= lastFastRegions_) {
-      lastFastMs_ = ms;
-      lastFastRegions_ = (long long) nr;
-      long long nv = 0;
-      for (const RegionDesc& d : regs) nv += d.cCount + d.bCount;
-      lastFastVariants_ = nv;
-    }
     if (nWarn > 0) {
       nWarn = std::min(nWarn, warnCap);
       const size_t at = warns.size();
@@ -690,8 +717,11 @@ class CudaBackend : public Backend {
       // keep each region's warnings in emission order
       std::stable_sort(warns.begin() + at, warns.end(), [](const WarnRec& a, const WarnRec& b) { return a.region < b.region; });
     }
+    inFlight_ = 0;
     return VCE_OK;
   }
+  size_t inFlight_ = 0;
+  int inFlightLaunches_ = 0;
 
   int fetchPass(PassData& pd, std::vector<int32_t>& syncBuf) override {
     CUDA_TRY(cudaSetDevice(device_));
@@ -705,13 +735,14 @@ class CudaBackend : public Backend {
       d.nRows = (size_t) rows;
       hs.decision.resize(n);
       hs.weight.resize(n);
-      hs.oOff.resize(n + 1);
-      hs.oIds.resize(d.nRows * 4 + 4);
-      hs.oOrig.resize(d.nRows + 4);
       if (n) {
         CUDA_TRY(cudaMemcpyAsync(hs.decision.data(), d.decision.p, n, cudaMemcpyDeviceToHost, stream_));
         CUDA_TRY(cudaMemcpyAsync(hs.weight.data(), d.weight.p, n * sizeof(double), cudaMemcpyDeviceToHost, stream_));
       }
+      if (!pd.wantOrientTables) continue;
+      hs.oOff.resize(n + 1);
+      hs.oIds.resize(d.nRows * 4 + 4);
+      hs.oOrig.resize(d.nRows + 4);
       CUDA_TRY(cudaMemcpyAsync(hs.oOff.data(), d.oOff.p, (n + 1) * 4, cudaMemcpyDeviceToHost, stream_));
       if (d.nRows) {
         CUDA_TRY(cudaMemcpyAsync(hs.oIds.data(), d.oIds.p, d.nRows * 4, cudaMemcpyDeviceToHost, stream_));
@@ -815,6 +846,7 @@ class CudaBackend : public Backend {
     mp.table = nullptr;
     mp.nChunks = 1;
     mp.total = j.n;
+    mp.refill = microRefill_;
     mp.cfg = mc;
     microLaunch(mp, j.cls, st);
     CUDA_TRY(cudaGetLastError());
@@ -849,6 +881,7 @@ class CudaBackend : public Backend {
     mp.table = mTable_.p;
     mp.nChunks = (int) table.size();
     mp.total = total;
+    mp.refill = microRefill_;
     mp.cfg = mc;
     CUDA_TRY(cudaEventRecord(evM0_, st));
     microLaunch(mp, jobs[0]->cls, st);
@@ -931,6 +964,7 @@ class CudaBackend : public Backend {
   int mNextEvent_ = 0, mNextLane_ = 0;
   cudaEvent_t evM0_ = nullptr, evM1_ = nullptr;
   int microBlocksPerSm_[2] = {1, 1};
+  int microRefill_ = 16;
   DevBuf<MicroChunkDesc> mTable_;
   std::string err_;
 };

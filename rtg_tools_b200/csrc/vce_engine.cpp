@@ -591,6 +591,7 @@ int Engine::buildChunk(PassCtx& pc, Chunk& ch, int worker, bool launch) {
   const int32_t* bs = pc.vStart[1].data();
   for (int q = 0; q < nr; ++q) {
     const int j = listed ? ch.list[q] : ch.r0 + q;
+    if (!listed && cls[j] == kClsEarly) continue;  // already running in the warp-per-region kernels
     if (!listed && j + 12 < nReg) {  // the reference window of a region is a cache miss: request it well ahead
       const RegRange& f = rrk[j + 12];
       const int32_t pos = f.cCount > 0 ? cs[f.cFirst] : (f.bCount > 0 ? bs[f.bFirst] : 0);
@@ -749,7 +750,7 @@ void Engine::resetPassRun(PassCtx& pc) {
     const size_t n = pc.rs[k].size();
     for (size_t j = 0; j < n; ++j) {
       std::memset(&rs[j], 0, sizeof(RegRes));
-      rs[j].state = cls[j] ? RS_PENDING : RS_RESIDUAL;
+      rs[j].state = cls[j] == kClsEarly ? RS_EARLY : (cls[j] ? RS_PENDING : RS_RESIDUAL);
     }
   });
 }
@@ -765,6 +766,26 @@ int Engine::runChunks(PassCtx& pc) {
   pc.mc.pruneNoOps = cfg_.prune_no_ops;
   pc.mc.preference = cfg_.preference;
   splitAll(pc);
+  // regions that cannot go through the thread-per-region kernel are known from their shape alone: they start right
+  // away in the warp-per-region kernels, concurrently with the packet pipeline
+  {
+    std::vector<std::vector<std::pair<RegKey, int>>> per(nSeq_);
+    pool_->parallelFor(nSeq_, [&](int k, int) {
+      const std::vector<RegRange>& rr = pc.rr[k];
+      const int n = (int) rr.size();
+      for (int j = 0; j < n; ++j) {
+        const RegRange& g = rr[j];
+        const bool shape = g.cCount > MicroB::KV || g.bCount > MicroB::KV || j == 0 || j == n - 1;
+        if (shape || !pc.microOk) {
+          per[k].push_back(std::make_pair(RegKey{k, j}, startTier(pc, g)));
+          pc.rcls[k][j] = kClsEarly;
+          pc.rs[k][j].state = RS_EARLY;
+        }
+      }
+    });
+    pc.earlyItems.clear();
+    for (int k = 0; k < nSeq_; ++k) pc.earlyItems.insert(pc.earlyItems.end(), per[k].begin(), per[k].end());
+  }
   planChunks(pc);
   return VCE_OK;
 }
@@ -782,9 +803,12 @@ int Engine::execute() {
       tm.lap("pass 2 set-up");
     }
     std::atomic<int> failed(0);
+    WideBatch early;
     if (!rerun) {
       if ((rc = runChunks(pc))) return rc;
       tm.lap("split into regions");
+      if ((rc = wideStart(pc, pc.earlyItems, early))) return rc;
+      tm.lap("early warp-per-region batch");
       pool_->parallelFor((int) pc.chunks.size(), [&](int t, int worker) {
         if (failed.load()) return;
         const int r = buildChunk(pc, pc.chunks[t], worker, true);
@@ -801,6 +825,7 @@ int Engine::execute() {
         arenaRewind();
         be_->microRewind();
       }
+      if ((rc = wideStart(pc, pc.earlyItems, early))) return rc;
       for (int c = 0; c < 2; ++c) {
         std::vector<MicroJob*> jobs;
         for (Chunk& ch : pc.chunks) if (ch.job[c].n > 0) jobs.push_back(&ch.job[c]);
@@ -830,7 +855,7 @@ int Engine::execute() {
       microRegions += ch.job[0].n + ch.job[1].n;
       microVariants += ch.variants;
     }
-    if ((rc = settle(pc))) return rc;
+    if ((rc = settle(pc, early))) return rc;
     tm.lap("settle residual");
   }
   executed_ = true;
@@ -847,155 +872,231 @@ int Engine::run(const vce_config& cfg, int32_t nSeq, const vce_sequence* seqs, v
 // ------------------------------------------------------------------------------------------- warp-per-region path
 // Runs the regions `ids` through the warp-per-region kernels (vce_search.h).  The variants and alleles of just these
 // regions are packed into compact arrays, so that the cost is proportional to the residual, not to the batch.
-int Engine::startTier(const PassCtx& pc, const RegRange& g) const { return fastEligible(pc, g) ? 0 : kTierGeneral; }
+// Tier of the warp-per-region kernels a region starts in: small regions in the many-warps tier, regions that will
+// grow a large frontier (many variants on one side) directly in the large shared-memory tier, the rest in HBM arenas.
+int Engine::startTier(const PassCtx& pc, const RegRange& g) const {
+  if (opt_.forceGeneral || pc.H > 2) return kTierGeneral;
+  const int m = std::max(g.cCount, g.bCount);
+  if (m <= fastShape(0).kv) return m >= 5 ? 1 : 0;
+  if (m <= fastShape(1).kv) return 1;
+  return kTierGeneral;
+}
 
-int Engine::wideLaunch(PassCtx& pc, const std::vector<RegKey>& ids, int tier, std::vector<int>& statusOut) {
-  statusOut.assign(ids.size(), kRegionPending);
-  if (ids.empty()) return VCE_OK;
+// Packs the regions `items` (region, tier) for the warp-per-region kernels and starts them: the variants and alleles of
+// just these regions go into compact arrays (cost proportional to the residual, not to the batch), K1 expands the
+// orientations on the device, one launch per tier.  Returns without waiting; wideFinish collects.
+int Engine::wideStart(PassCtx& pc, const std::vector<std::pair<RegKey, int>>& itemsIn, WideBatch& wb) {
+  wb = WideBatch();
+  if (itemsIn.empty()) return VCE_OK;
   StageTimer tmw;
-  bool general = tier >= kTierGeneral;
-  PassData pd;
+  std::vector<std::pair<RegKey, int>> items(itemsIn);
+  std::stable_sort(items.begin(), items.end(), [](const std::pair<RegKey, int>& a, const std::pair<RegKey, int>& b) { return a.second < b.second; });
+  const size_t n = items.size();
+  wb.ids.resize(n);
+  wb.tier.resize(n);
+  for (size_t q = 0; q < n; ++q) { wb.ids[q] = items[q].first; wb.tier[q] = items[q].second; }
+  PassData& pd = wb.pd;
   pd.pass = pc.pass;
   pd.H = pc.H;
   pd.kind[0] = pc.kind[0];
   pd.kind[1] = pc.kind[1];
-  AlleleTable at[2];
-  std::vector<RegionDesc> descs(ids.size());
-  std::vector<int32_t> syncOff(ids.size());
-  size_t so = 0;
-  int maxSl[2] = {2, 2};
-  {
-    size_t nvar[2] = {0, 0};
-    for (const RegKey& id : ids) { nvar[0] += pc.rr[id.seq][id.j].cCount; nvar[1] += pc.rr[id.seq][id.j].bCount; }
-    for (int side = 0; side < 2; ++side) {
-      HostSide& hs = pd.side[side];
-      hs.vStart.reserve(nvar[side]); hs.vEnd.reserve(nvar[side]); hs.slot0.reserve(nvar[side]); hs.nSl.reserve(nvar[side]);
-      hs.vFlags.reserve(nvar[side]); hs.gt.reserve(nvar[side] * 4); hs.inputIdx.reserve(nvar[side]);
-      at[side].aStart.reserve(nvar[side] * 3 + 8); at[side].aEnd.reserve(nvar[side] * 3 + 8);
-      at[side].aNull.reserve(nvar[side] * 3 + 8); at[side].aNtOff.reserve(nvar[side] * 3 + 8);
-      at[side].nt.reserve(nvar[side] * 4 + 64);
-    }
-  }
-  for (size_t q = 0; q < ids.size(); ++q) {
-    const int k = ids[q].seq, j = ids[q].j;
-    const RegRange& g = pc.rr[k][j];
-    RegionDesc& d = descs[q];
-    std::memset(&d, 0, sizeof(d));
-    d.seq = k;
-    d.tmplLen = seqs_[k].template_len;
-    const int first[2] = {g.cFirst, g.bFirst};
-    const int count[2] = {g.cCount, g.bCount};
-    int lo = INT_MAX;
-    long hi = 0;
-    for (int side = 0; side < 2; ++side) {
-      const SideSeq& s = pc.ss[side][k];
-      const vce_variants& in = *s.in;
-      HostSide& hs = pd.side[side];
-      hs.gtPloidy = pc.gtPloidy[side];
-      AlleleTable& t = at[side];
-      (side == 0 ? d.cFirst : d.bFirst) = (int32_t) hs.vStart.size();
-      (side == 0 ? d.cCount : d.bCount) = count[side];
-      (side == 0 ? d.cSlot0 : d.bSlot0) = (int32_t) t.aStart.size();
-      const int e = first[side] + count[side];
-      (side == 0 ? d.cNextStart : d.bNextStart) = e < s.first + s.n ? pc.vStart[side][e] : kNoNext;
-      for (int v = first[side]; v < e; ++v) {
-        const int li = v - s.first;
-        const int ii = s.idx ? s.idx[li] : li;
-        lo = std::min(lo, pc.vStart[side][v]);
-        hi = std::max(hi, (long) pc.vEnd[side][v]);
-        hs.vStart.push_back(pc.vStart[side][v]);
-        hs.vEnd.push_back(pc.vEnd[side][v]);
-        hs.slot0.push_back((int32_t) t.aStart.size());
-        const int off0 = in.allele_off[ii], nSl = in.allele_off[ii + 1] - off0;
-        hs.nSl.push_back(nSl);
-        maxSl[side] = std::max(maxSl[side], nSl);
-        uint8_t f = (in.phased && in.phased[ii]) ? 1 : 0;
-        if (in.status_in) f |= in.status_in[ii] & VCE_STATUS_OUTSIDE_EVAL;
-        hs.vFlags.push_back(f);
-        for (int h = 0; h < 4; ++h) hs.gt.push_back(h < in.gt_ploidy ? in.gt[(size_t) ii * in.gt_ploidy + h] : (int8_t) -2);
-        hs.inputIdx.push_back(ii);
-        const int nb0 = in.allele_nt_off[off0];
-        const int base = (int) t.nt.size() - nb0;
-        for (int sl = off0; sl < off0 + nSl; ++sl) {
-          t.aStart.push_back(in.allele_start[sl]);
-          t.aEnd.push_back(in.allele_end[sl]);
-          t.aNull.push_back(in.allele_null[sl]);
-          t.aNtOff.push_back(base + in.allele_nt_off[sl]);
+  pd.wantOrientTables = false;
+  wb.descs.assign(n, RegionDesc());
+  wb.syncOff.assign(n, 0);
+  // pass A (parallel): sizes per region
+  struct Sz { int32_t nv[2], nsl[2], nnt[2], lo, maxSl[2]; long hi; };
+  std::vector<Sz> sz(n);
+  const int blockA = 256;
+  pool_->parallelFor((int) ((n + blockA - 1) / blockA), [&](int t, int) {
+    for (size_t q = (size_t) t * blockA; q < std::min(n, (size_t) (t + 1) * blockA); ++q) {
+      const int k = wb.ids[q].seq, j = wb.ids[q].j;
+      const RegRange& g = pc.rr[k][j];
+      Sz& z = sz[q];
+      z.lo = INT_MAX;
+      z.hi = 0;
+      const int first[2] = {g.cFirst, g.bFirst}, count[2] = {g.cCount, g.bCount};
+      for (int side = 0; side < 2; ++side) {
+        const SideSeq& s = pc.ss[side][k];
+        const vce_variants& in = *s.in;
+        z.nv[side] = count[side];
+        z.nsl[side] = 0;
+        z.nnt[side] = 0;
+        z.maxSl[side] = 2;
+        for (int v = first[side]; v < first[side] + count[side]; ++v) {
+          const int li = v - s.first;
+          const int ii = s.idx ? s.idx[li] : li;
+          const int off0 = in.allele_off[ii], nSl = in.allele_off[ii + 1] - off0;
+          z.nsl[side] += nSl;
+          z.nnt[side] += in.allele_nt_off[off0 + nSl] - in.allele_nt_off[off0];
+          z.maxSl[side] = std::max(z.maxSl[side], nSl);
+          z.lo = std::min(z.lo, pc.vStart[side][v]);
+          z.hi = std::max(z.hi, (long) pc.vEnd[side][v]);
         }
-        t.nt.insert(t.nt.end(), in.nt + nb0, in.nt + in.allele_nt_off[off0 + nSl]);
       }
-      (side == 0 ? d.cSlotN : d.bSlotN) = (int32_t) t.aStart.size() - (side == 0 ? d.cSlot0 : d.bSlot0);
     }
-    d.startPos = j == 0 ? -1 : lo - 1;
-    const auto rit = pc.rare.find(key(k, j));
-    d.prefixAlleleId = j == 0 ? kPrefixEmpty : kDummyPrefix;
-    int extra = 0;
-    if (rit != pc.rare.end()) {
-      if (rit->second.hasPrefix) d.prefixAlleleId = rit->second.assumedPrefix;
-      extra = rit->second.extraMargin;
+  });
+  // serial prefix: offsets of every region in the compact arrays, windows, sync space
+  std::vector<int32_t> vOff[2], sOff[2], nOff[2];
+  int maxSl[2] = {2, 2};
+  for (int side = 0; side < 2; ++side) { vOff[side].resize(n + 1); sOff[side].resize(n + 1); nOff[side].resize(n + 1); }
+  size_t so = 0, winBytes = 0;
+  {
+    int32_t av[2] = {0, 0}, as[2] = {0, 0}, an[2] = {0, 0};
+    for (size_t q = 0; q < n; ++q) {
+      const int k = wb.ids[q].seq, j = wb.ids[q].j;
+      RegionDesc& d = wb.descs[q];
+      std::memset(&d, 0, sizeof(d));
+      for (int side = 0; side < 2; ++side) {
+        vOff[side][q] = av[side]; sOff[side][q] = as[side]; nOff[side][q] = an[side];
+        av[side] += sz[q].nv[side]; as[side] += sz[q].nsl[side]; an[side] += sz[q].nnt[side];
+        maxSl[side] = std::max(maxSl[side], sz[q].maxSl[side]);
+      }
+      d.seq = k;
+      d.tmplLen = seqs_[k].template_len;
+      d.cFirst = vOff[0][q]; d.cCount = sz[q].nv[0]; d.bFirst = vOff[1][q]; d.bCount = sz[q].nv[1];
+      d.cSlot0 = sOff[0][q]; d.cSlotN = sz[q].nsl[0]; d.bSlot0 = sOff[1][q]; d.bSlotN = sz[q].nsl[1];
+      const RegRange& g = pc.rr[k][j];
+      const SideSeq& C = pc.ss[0][k];
+      const SideSeq& B = pc.ss[1][k];
+      d.cNextStart = g.cFirst + g.cCount < C.first + C.n ? pc.vStart[0][g.cFirst + g.cCount] : kNoNext;
+      d.bNextStart = g.bFirst + g.bCount < B.first + B.n ? pc.vStart[1][g.bFirst + g.bCount] : kNoNext;
+      int lo = sz[q].lo;
+      d.startPos = j == 0 ? -1 : lo - 1;
+      d.prefixAlleleId = j == 0 ? kPrefixEmpty : kDummyPrefix;
+      int extra = 0;
+      if (!pc.rare.empty()) {
+        const auto rit = pc.rare.find(key(k, j));
+        if (rit != pc.rare.end()) {
+          if (rit->second.hasPrefix) d.prefixAlleleId = rit->second.assumedPrefix;
+          extra = rit->second.extraMargin;
+        }
+      }
+      if (lo == INT_MAX) lo = 0;
+      const int ws = std::max(0, std::min(lo, d.startPos < 0 ? 0 : d.startPos) - 1);
+      long we = extra < 0 ? (long) d.tmplLen : sz[q].hi + opt_.margin + extra;
+      we = std::min(we, (long) d.tmplLen);
+      if (we < ws) we = ws;
+      d.winStart = ws;
+      d.winLen = (int32_t) (we - ws);
+      d.winOff = (uint32_t) winBytes;
+      winBytes += ((size_t) d.winLen + 15 + 16) & ~(size_t) 15;
+      wb.syncOff[q] = (int32_t) so;
+      so += (size_t) d.cCount + d.bCount + 2;
     }
-    if (lo == INT_MAX) lo = 0;
-    const int ws = std::max(0, std::min(lo, d.startPos < 0 ? 0 : d.startPos) - 1);
-    long we = extra < 0 ? (long) d.tmplLen : hi + opt_.margin + extra;
-    we = std::min(we, (long) d.tmplLen);
-    if (we < ws) we = ws;
-    d.winStart = ws;
-    d.winLen = (int32_t) (we - ws);
-    syncOff[q] = (int32_t) so;
-    so += (size_t) d.cCount + d.bCount + 2;
+    for (int side = 0; side < 2; ++side) { vOff[side][n] = av[side]; sOff[side][n] = as[side]; nOff[side][n] = an[side]; }
   }
+  wb.so = so;
   for (int side = 0; side < 2; ++side) {
-    at[side].aNtOff.push_back((int32_t) at[side].nt.size());
-    pd.side[side].seqFirst.assign(2, 0);
-    pd.side[side].seqFirst[1] = (int32_t) pd.side[side].n();
+    HostSide& hs = pd.side[side];
+    hs.gtPloidy = pc.gtPloidy[side];
+    const size_t nv = (size_t) vOff[side][n], ns = (size_t) sOff[side][n];
+    hs.vStart.resize(nv); hs.vEnd.resize(nv); hs.slot0.resize(nv); hs.nSl.resize(nv); hs.vFlags.resize(nv); hs.gt.resize(nv * 4);
+    wb.at[side].aStart.resize(ns); wb.at[side].aEnd.resize(ns); wb.at[side].aNull.resize(ns); wb.at[side].aNtOff.resize(ns + 1);
+    wb.at[side].nt.resize((size_t) nOff[side][n]);
+    wb.at[side].aNtOff[ns] = nOff[side][n];
+    hs.seqFirst.assign(2, 0);
+    hs.seqFirst[1] = (int32_t) nv;
     pd.maxOrient[side] = orientBound(pc.kind[side], pc.H, pc.gtPloidy[side], maxSl[side]);
     if (pd.maxOrient[side] + 2 > 255) { err_ = "too many orientations per variant for this engine"; return VCE_ERR_UNSUPPORTED; }
   }
   const int mo = std::max(pd.maxOrient[0], pd.maxOrient[1]);
-  if (!general && 1 + mo > FastLimits::kMaxChildren) { general = true; tier = kTierGeneral; }
-  size_t winBytes = 0;
-  for (RegionDesc& d : descs) {
-    if (general) {
-      d.qMax = std::max(1, std::max(d.cCount, d.bCount));
-      d.decBits = (mo + 2 <= 15) ? 4 : 8;
-      PathLayout PL;
-      PL.init(pc.H, d.qMax, std::max(1, std::max(d.cCount, d.bCount)), d.cCount + d.bCount + 2, d.decBits);
-      d.layoutW = PL.W;
+  if (1 + mo > FastLimits::kMaxChildren) for (size_t q = 0; q < n; ++q) wb.tier[q] = kTierGeneral;
+  for (int t = 0; t <= kTierGeneral + 1; ++t) wb.tierFirst[t] = 0;
+  for (size_t q = 0; q < n; ++q) ++wb.tierFirst[wb.tier[q] + 1];
+  for (int t = 1; t <= kTierGeneral + 1; ++t) wb.tierFirst[t] += wb.tierFirst[t - 1];
+  wb.windows.assign(winBytes + 16, 0);
+  // pass B (parallel): fill
+  pool_->parallelFor((int) ((n + blockA - 1) / blockA), [&](int t, int) {
+    for (size_t q = (size_t) t * blockA; q < std::min(n, (size_t) (t + 1) * blockA); ++q) {
+      const int k = wb.ids[q].seq, j = wb.ids[q].j;
+      const RegRange& g = pc.rr[k][j];
+      RegionDesc& d = wb.descs[q];
+      if (wb.tier[q] >= kTierGeneral) {
+        d.qMax = std::max(1, std::max(d.cCount, d.bCount));
+        d.decBits = (mo + 2 <= 15) ? 4 : 8;
+        PathLayout PL;
+        PL.init(pc.H, d.qMax, std::max(1, std::max(d.cCount, d.bCount)), d.cCount + d.bCount + 2, d.decBits);
+        d.layoutW = PL.W;
+      }
+      if (d.winLen > 0) std::memcpy(wb.windows.data() + d.winOff, seqs_[k].template_bases + d.winStart, (size_t) d.winLen);
+      const int first[2] = {g.cFirst, g.bFirst}, count[2] = {g.cCount, g.bCount};
+      for (int side = 0; side < 2; ++side) {
+        const SideSeq& s = pc.ss[side][k];
+        const vce_variants& in = *s.in;
+        HostSide& hs = pd.side[side];
+        AlleleTable& tb = wb.at[side];
+        int vo = vOff[side][q], slo = sOff[side][q], no = nOff[side][q];
+        for (int v = first[side]; v < first[side] + count[side]; ++v, ++vo) {
+          const int li = v - s.first;
+          const int ii = s.idx ? s.idx[li] : li;
+          hs.vStart[vo] = pc.vStart[side][v];
+          hs.vEnd[vo] = pc.vEnd[side][v];
+          hs.slot0[vo] = slo;
+          const int off0 = in.allele_off[ii], nSl = in.allele_off[ii + 1] - off0;
+          hs.nSl[vo] = nSl;
+          uint8_t f = (in.phased && in.phased[ii]) ? 1 : 0;
+          if (in.status_in) f |= in.status_in[ii] & VCE_STATUS_OUTSIDE_EVAL;
+          hs.vFlags[vo] = f;
+          for (int h = 0; h < 4; ++h) hs.gt[(size_t) vo * 4 + h] = h < in.gt_ploidy ? in.gt[(size_t) ii * in.gt_ploidy + h] : (int8_t) -2;
+          const int nb0 = in.allele_nt_off[off0];
+          for (int sl = off0; sl < off0 + nSl; ++sl, ++slo) {
+            tb.aStart[slo] = in.allele_start[sl];
+            tb.aEnd[slo] = in.allele_end[sl];
+            tb.aNull[slo] = in.allele_null[sl];
+            tb.aNtOff[slo] = no + (in.allele_nt_off[sl] - nb0);
+          }
+          const int nbytes = in.allele_nt_off[off0 + nSl] - nb0;
+          if (nbytes > 0) std::memcpy(tb.nt.data() + no, in.nt + nb0, (size_t) nbytes);
+          no += nbytes;
+        }
+      }
     }
-    d.winOff = (uint32_t) winBytes;
-    winBytes += ((size_t) d.winLen + 15 + 16) & ~(size_t) 15;
-  }
-  std::vector<uint8_t> windows(winBytes + 16, 0);
-  for (const RegionDesc& d : descs) {
-    if (d.winLen > 0) std::memcpy(windows.data() + d.winOff, seqs_[d.seq].template_bases + d.winStart, (size_t) d.winLen);
-  }
+  });
+  tmw.lap("  wide: pack");
   int rc;
   for (int side = 0; side < 2; ++side) {
-    if ((rc = be_->setAlleles(side, at[side]))) { err_ = be_->lastError(); return rc; }
+    if ((rc = be_->setAlleles(side, wb.at[side]))) { err_ = be_->lastError(); return rc; }
   }
   if ((rc = be_->uploadPass(pd))) { err_ = be_->lastError(); return rc; }
   if ((rc = be_->orient(pd))) { err_ = be_->lastError(); return rc; }
-  std::vector<RegionResult> out(ids.size());
-  std::vector<WarnRec> warns;
   const SearchConfig sc{cfg_.max_paths, cfg_.max_iterations, cfg_.prune_no_ops, cfg_.preference};
-  const double searchBefore = be_->stats.searchMs;
-  tmw.lap("  wide: pack");
-  if ((rc = be_->search(pd, sc, descs, windows, tier, false, out, syncOff, so, warns))) { err_ = be_->lastError(); return rc; }
-  if (std::getenv("VCE_TIMING")) {
-    long long it = 0, nv = 0;
-    int maxIt = 0, maxItVars = 0, maxF = 0;
-    for (size_t q = 0; q < out.size(); ++q) {
-      it += out[q].iterations;
-      nv += descs[q].cCount + descs[q].bCount;
-      if (out[q].iterations > maxIt) { maxIt = out[q].iterations; maxItVars = descs[q].cCount + descs[q].bCount; }
-      maxF = std::max(maxF, out[q].maxFrontier);
+  wb.searchBefore = be_->stats.searchMs;
+  if ((rc = be_->searchStart(pd, sc, wb.descs, wb.windows, wb.tierFirst, wb.syncOff, wb.so))) { err_ = be_->lastError(); return rc; }
+  wb.started = true;
+  tmw.lap("  wide: upload + launch");
+  return VCE_OK;
+}
+
+// Waits for the batch, extracts the settled regions' results; statusOut[q] is the kRegion* status of wb.ids[q].
+int Engine::wideFinish(PassCtx& pc, WideBatch& wb, std::vector<int>& statusOut) {
+  statusOut.assign(wb.ids.size(), kRegionPending);
+  if (!wb.started) return VCE_OK;
+  StageTimer tmw;
+  int rc;
+  PassData& pd = wb.pd;
+  const std::vector<RegKey>& ids = wb.ids;
+  std::vector<RegionResult> out;
+  std::vector<WarnRec> warns;
+  if ((rc = be_->searchFinish(out, warns))) { err_ = be_->lastError(); return rc; }
+  if (tmw.on) {
+    for (int t = 0; t <= kTierGeneral; ++t) {
+      long long it = 0, nv = 0;
+      int maxIt = 0, maxF = 0;
+      for (int q = wb.tierFirst[t]; q < wb.tierFirst[t + 1]; ++q) {
+        it += out[q].iterations;
+        nv += wb.descs[q].cCount + wb.descs[q].bCount;
+        maxIt = std::max(maxIt, out[q].iterations);
+        maxF = std::max(maxF, out[q].maxFrontier);
+      }
+      if (wb.tierFirst[t + 1] > wb.tierFirst[t]) {
+        std::fprintf(stderr, "[vce]   wide tier %d: %d regions, %lld variants, %lld iterations (longest %d, largest frontier %d)\n", t,
+                     wb.tierFirst[t + 1] - wb.tierFirst[t], nv, it, maxIt, maxF);
+      }
     }
-    std::fprintf(stderr, "[vce]   longest region: %d iterations (%d variants), largest frontier %d\n", maxIt, maxItVars, maxF);
-    std::fprintf(stderr, "[vce]   wide launch: %zu regions, %lld variants, tier %d, %lld iterations, kernel %.2f ms\n", ids.size(), nv,
-                 tier, it, be_->stats.searchMs - searchBefore);
+    std::fprintf(stderr, "[vce]   wide kernels: %.2f ms\n", be_->stats.searchMs - wb.searchBefore);
   }
-  tmw.lap("  wide: upload + search");
-  std::vector<int32_t> syncBuf(so, 0);
+  tmw.lap("  wide: wait");
+  std::vector<int32_t> syncBuf(wb.so, 0);
   if ((rc = be_->fetchPass(pd, syncBuf))) { err_ = be_->lastError(); return rc; }
   tmw.lap("  wide: fetch");
   // a re-run region reports its warnings afresh
@@ -1013,7 +1114,8 @@ int Engine::wideLaunch(PassCtx& pc, const std::vector<RegKey>& ids, int tier, st
     const RegRange& g = pc.rr[k][j];
     RegRes& s = pc.rs[k][j];
     const RegionResult& r = out[q];
-    const RegionDesc& d = descs[q];
+    const RegionDesc& d = wb.descs[q];
+    const int tier = wb.tier[q];
     statusOut[q] = r.status;
     be_->stats.iterations += r.iterations;
     if (r.status != kRegionClean && r.status != kRegionFinished) {
@@ -1028,7 +1130,7 @@ int Engine::wideLaunch(PassCtx& pc, const std::vector<RegKey>& ids, int tier, st
       s.nSync = 0;
       s.ext.idx = (int32_t) pc.wideSync.size();
       s.ext.n = r.nSync;
-      pc.wideSync.insert(pc.wideSync.end(), syncBuf.begin() + syncOff[q], syncBuf.begin() + syncOff[q] + r.nSync);
+      pc.wideSync.insert(pc.wideSync.end(), syncBuf.begin() + wb.syncOff[q], syncBuf.begin() + wb.syncOff[q] + r.nSync);
       for (int i = 0; i < g.cCount; ++i) {
         pc.decision[0][g.cFirst + i] = pd.side[0].decision[d.cFirst + i];
         pc.weight[g.cFirst + i] = pd.side[0].weight[d.cFirst + i];
@@ -1051,14 +1153,16 @@ int Engine::wideLaunch(PassCtx& pc, const std::vector<RegKey>& ids, int tier, st
     pc.warns.push_back(WarnEntry{ids[w.region].seq, ids[w.region].j, w});
   }
   tmw.lap("  wide: extract");
+  wb.started = false;
   return VCE_OK;
 }
 
-// Settles every region the thread-per-region kernel left open: SPILL -> merge with the following region and re-run,
-// capacity -> large-capacity kernel, then the prefix-dependent tie-breaks (MaxSumBoth.java:55,76).
-int Engine::settle(PassCtx& pc) {
+// Settles every region that is still open: the regions started early in the warp-per-region kernels (`early`), the
+// ones the thread-per-region kernel handed back, then SPILL -> merge with the following region and re-run, capacity ->
+// next tier, and finally the prefix-dependent tie-breaks (MaxSumBoth.java:55,76).
+int Engine::settle(PassCtx& pc, WideBatch& early) {
   int rc;
-  std::vector<RegKey> todo[kTierGeneral + 1];
+  std::vector<std::pair<RegKey, int>> todo;   // (region, tier)
   {
     std::vector<std::vector<RegKey>> per(nSeq_);
     pool_->parallelFor(nSeq_, [&](int k, int) {
@@ -1067,21 +1171,23 @@ int Engine::settle(PassCtx& pc) {
       for (size_t j = 0; j < n; ++j) if (rs[j].state == RS_RESIDUAL) per[k].push_back(RegKey{k, (int) j});
     });
     for (int k = 0; k < nSeq_; ++k) {
-      for (const RegKey& id : per[k]) todo[startTier(pc, pc.rr[k][id.j])].push_back(id);
+      for (const RegKey& id : per[k]) todo.push_back(std::make_pair(id, startTier(pc, pc.rr[k][id.j])));
     }
   }
-  for (int t = 0; t <= kTierGeneral; ++t) be_->stats.escalated += (int64_t) todo[t].size();
+  be_->stats.escalated += (int64_t) (todo.size() + early.ids.size());
   auto nextAlive = [&](int k, int j) {
     const int n = (int) pc.rs[k].size();
     int nx = j + 1;
     while (nx < n && pc.rs[k][nx].state == RS_DEAD) ++nx;
     return nx;
   };
-  auto pending = [&]() {
-    for (int t = 0; t <= kTierGeneral; ++t) if (!todo[t].empty()) return true;
-    return false;
-  };
   std::vector<RegKey> retry;  // merged regions: their new shape may fit the thread-per-region kernel
+  std::vector<std::pair<RegKey, int>> all;  // (region, status) to inspect
+  {
+    std::vector<int> st;
+    if ((rc = wideFinish(pc, early, st))) return rc;
+    for (size_t q = 0; q < early.ids.size(); ++q) all.push_back(std::make_pair(early.ids[q], st[q]));
+  }
   for (int round = 0; round < 100000; ++round) {
     if (!retry.empty()) {
       std::sort(retry.begin(), retry.end(), [](const RegKey& a, const RegKey& b) { return a.seq != b.seq ? a.seq < b.seq : a.j < b.j; });
@@ -1102,11 +1208,11 @@ int Engine::settle(PassCtx& pc) {
       }
       be_->stats.iterations += it;
       for (const RegKey& id : retry) {
-        if (pc.rs[id.seq][id.j].state == RS_RESIDUAL) todo[startTier(pc, pc.rr[id.seq][id.j])].push_back(id);
+        if (pc.rs[id.seq][id.j].state == RS_RESIDUAL) todo.push_back(std::make_pair(id, startTier(pc, pc.rr[id.seq][id.j])));
       }
       retry.clear();
     }
-    if (!pending()) {
+    if (todo.empty() && all.empty()) {
       // prefix-dependent tie-breaks: re-run the first region per sequence whose assumption was wrong
       std::vector<int> fix(nSeq_, -1);
       std::vector<int> fixPrefix(nSeq_, 0);
@@ -1136,36 +1242,35 @@ int Engine::settle(PassCtx& pc) {
         ra.assumedPrefix = fixPrefix[k];
         int tier = startTier(pc, pc.rr[k][fix[k]]);
         if (s.state == RS_WIDE_DONE) tier = std::max(tier, (int) (s.flags >> 2) & 3);  // the tier that settled it before
-        todo[tier].push_back(RegKey{k, fix[k]});
+        todo.push_back(std::make_pair(RegKey{k, fix[k]}, tier));
         ++be_->stats.prefixReruns;
       }
-      if (!pending()) break;
+      if (todo.empty()) break;
     }
-    if (!pending() && !retry.empty()) continue;
-    // run every tier's list, then inspect in sequence order so that chains of spilling regions merge front to back
-    std::vector<std::pair<RegKey, int>> all;
-    std::vector<int> allTier;
-    for (int t = 0; t <= kTierGeneral; ++t) {
-      std::vector<RegKey> ran;
+    // one batch with every tier's regions, then inspect in sequence order so that chains of spilling regions merge
+    // front to back
+    if (!todo.empty()) {
+      WideBatch wb;
       std::vector<int> st;
-      ran.swap(todo[t]);
-      if ((rc = wideLaunch(pc, ran, t, st))) return rc;
-      for (size_t q = 0; q < ran.size(); ++q) { all.push_back(std::make_pair(ran[q], st[q])); allTier.push_back(t); }
+      if ((rc = wideStart(pc, todo, wb))) return rc;
+      if ((rc = wideFinish(pc, wb, st))) return rc;
+      for (size_t q = 0; q < wb.ids.size(); ++q) all.push_back(std::make_pair(wb.ids[q], st[q]));
+      todo.clear();
     }
-    std::vector<size_t> ord(all.size());
-    for (size_t q = 0; q < ord.size(); ++q) ord[q] = q;
-    std::sort(ord.begin(), ord.end(), [&](size_t a, size_t b) {
-      return all[a].first.seq != all[b].first.seq ? all[a].first.seq < all[b].first.seq : all[a].first.j < all[b].first.j;
+    std::sort(all.begin(), all.end(), [](const std::pair<RegKey, int>& a, const std::pair<RegKey, int>& b) {
+      return a.first.seq != b.first.seq ? a.first.seq < b.first.seq : a.first.j < b.first.j;
     });
-    for (size_t oq = 0; oq < ord.size(); ++oq) {
-      const size_t q = ord[oq];
+    for (size_t q = 0; q < all.size(); ++q) {
       const int k = all[q].first.seq, j = all[q].first.j;
       const int st = all[q].second;
       if (pc.rs[k][j].state == RS_DEAD) continue;
       if (st == kRegionOverflow) {
         Rare& ra = pc.rare[key(k, j)];
         if (ra.tier >= kTierGeneral) { err_ = "search capacity exceeded in the large-capacity kernel"; return VCE_ERR_CAPACITY; }
-        todo[ra.tier + 1].push_back(all[q].first);
+        int nt = ra.tier + 1;
+        const RegRange& g = pc.rr[k][j];
+        if (nt < kTierGeneral && std::max(g.cCount, g.bCount) > fastShape(nt).kv) nt = kTierGeneral;
+        todo.push_back(std::make_pair(all[q].first, nt));
         ++be_->stats.escalated;
       } else if (st == kRegionSpill) {
         Rare& ra = pc.rare[key(k, j)];
@@ -1177,7 +1282,7 @@ int Engine::settle(PassCtx& pc) {
           // last region of its sequence ran off its reference window: widen it
           if (ra.extraMargin < 0) { err_ = "region spilled with the whole template in its window"; return VCE_ERR_CAPACITY; }
           ra.extraMargin = ra.extraMargin == 0 ? 256 : (ra.extraMargin >= (1 << 20) ? -1 : ra.extraMargin * 16);
-          todo[std::max(ra.tier, startTier(pc, g))].push_back(all[q].first);
+          todo.push_back(std::make_pair(all[q].first, std::max(ra.tier, startTier(pc, g))));
         } else {
           // absorb the following region (and further ones while they are themselves known to spill)
           pc.undo.push_back(std::make_pair(RegKey{k, j}, g));
@@ -1197,12 +1302,13 @@ int Engine::settle(PassCtx& pc) {
             ra.microTried = true;
             retry.push_back(all[q].first);
           } else {
-            todo[startTier(pc, g)].push_back(all[q].first);
+            todo.push_back(std::make_pair(all[q].first, startTier(pc, g)));
           }
         }
         pc.rs[k][j].state = RS_RESIDUAL;
       }
     }
+    all.clear();
   }
   return VCE_OK;
 }

@@ -69,7 +69,8 @@ class Engine {
     };
   };
   enum : uint8_t { RS_PENDING = 0, RS_MICRO_DONE = 1, RS_WIDE_DONE = 2, RS_DEAD = 3, RS_RESIDUAL = 4, RS_ERR_NULL = 5,
-                   RS_ERR_MOVE = 6, RS_ERR_ORDER = 7 };
+                   RS_ERR_MOVE = 6, RS_ERR_ORDER = 7, RS_EARLY = 8 };
+  static constexpr uint8_t kClsEarly = 255;   // region started early in the warp-per-region kernels
   struct RegKey { int32_t seq, j; };
   struct Rare {               // state only re-run regions carry
     int extraMargin = 0;      // reference bases added after a window miss (< 0: rest of the template)
@@ -102,6 +103,7 @@ class Engine {
     std::vector<std::vector<RegRes>> rs;
     std::vector<std::vector<uint8_t>> rcls;      // 0 = warp-per-region path, 1 = MicroA, 2 = MicroB
     std::vector<Chunk> chunks;
+    std::vector<std::pair<RegKey, int>> earlyItems;   // (region, tier) started early in the warp-per-region kernels
     std::vector<int32_t> wideSync;
     std::vector<WarnEntry> warns;
     std::unordered_map<uint64_t, Rare> rare;
@@ -129,8 +131,23 @@ class Engine {
   int runChunks(PassCtx& pc);
   void decodeChunk(PassCtx& pc, Chunk& ch, int64_t& iterations);
   template <class T> void decodeJob(PassCtx& pc, int k, const MicroJob& job, const std::vector<int32_t>& pktRegion, int64_t& iterations);
-  int settle(PassCtx& pc);
-  int wideLaunch(PassCtx& pc, const std::vector<RegKey>& ids, int tier, std::vector<int>& statusOut);
+  struct WideBatch {           // one batch of regions in the warp-per-region kernels
+    std::vector<RegKey> ids;   // grouped by tier
+    std::vector<int> tier;
+    int tierFirst[kTierGeneral + 2] = {0, 0, 0, 0};
+    PassData pd;
+    AlleleTable at[2];
+    std::vector<RegionDesc> descs;
+    std::vector<int32_t> syncOff;
+    std::vector<uint8_t> windows;
+    size_t so = 0;
+    double searchBefore = 0;
+    bool started = false;
+  };
+  int settle(PassCtx& pc, WideBatch& early);
+  int wideStart(PassCtx& pc, const std::vector<std::pair<RegKey, int>>& items, WideBatch& wb);
+  int wideFinish(PassCtx& pc, WideBatch& wb, std::vector<int>& statusOut);
+  int startEarly(PassCtx& pc, WideBatch& early);
   int startTier(const PassCtx& pc, const RegRange& g) const;
   bool fastEligible(const PassCtx& pc, const RegRange& g) const;
   int regionStartPos(const PassCtx& pc, int k, int j) const;

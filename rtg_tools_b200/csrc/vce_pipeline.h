@@ -41,6 +41,7 @@ struct HostSide {  // one side of one pass, whole batch, sorted by (sequence, st
 };
 
 struct PassData {
+  bool wantOrientTables = true;   // fetchPass also copies the orientation tables (oOff / oIds / oOrig) back
   int pass = 0;
   int H = 2;
   int kind[2] = {0, 0};  // [0] = calls orientor, [1] = baseline orientor
@@ -107,6 +108,13 @@ class Backend {
   virtual int search(PassData& pd, const SearchConfig& sc, const std::vector<RegionDesc>& regs,
                      const std::vector<uint8_t>& windows, int tier, bool staged, std::vector<RegionResult>& out,
                      const std::vector<int32_t>& syncOff, size_t syncTotal, std::vector<WarnRec>& warns) = 0;
+  // Asynchronous form for a batch whose regions are grouped by tier: regs [tierFirst[t], tierFirst[t+1]) run in tier t
+  // (one launch per non-empty tier, all on the backend's stream).  searchStart returns once everything is enqueued;
+  // searchFinish waits and delivers the per-region results.  One batch can be in flight at a time.
+  virtual int searchStart(PassData& pd, const SearchConfig& sc, const std::vector<RegionDesc>& regs,
+                          const std::vector<uint8_t>& windows, const int* tierFirst, const std::vector<int32_t>& syncOff,
+                          size_t syncTotal) = 0;
+  virtual int searchFinish(std::vector<RegionResult>& out, std::vector<WarnRec>& warns) = 0;
   // Copies decision / weight / orientation-id arrays of the pass and the sync-point buffer back to the host.
   virtual int fetchPass(PassData& pd, std::vector<int32_t>& syncBuf) = 0;
   virtual const char* lastError() const = 0;
@@ -130,7 +138,7 @@ struct FastShape {
 };
 constexpr int kTierGeneral = 2;
 inline FastShape fastShape(int tier) {
-  return tier == 0 ? FastShape{8, 2, 8, 24, 7, 1536} : FastShape{8, 8, 12, 112, 7, 3072};
+  return tier == 0 ? FastShape{8, 2, 8, 24, 7, 1536} : FastShape{16, 8, 20, 112, 7, 4096};
 }
 struct FastLimits {
   static constexpr int kMaxVarPerSide = 8;

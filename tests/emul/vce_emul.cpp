@@ -96,12 +96,40 @@ class EmulBackend : public Backend {
   int search(PassData& pd, const SearchConfig& sc, const std::vector<RegionDesc>& regs, const std::vector<uint8_t>& windows,
              int tier, bool /*staged*/, std::vector<RegionResult>& out, const std::vector<int32_t>& syncOff, size_t syncTotal,
              std::vector<WarnRec>& warns) override {
+    int tierFirst[kTierGeneral + 2];
+    for (int t = 0; t <= kTierGeneral + 1; ++t) tierFirst[t] = t <= tier ? 0 : (int) regs.size();
+    const int rc = searchStart(pd, sc, regs, windows, tierFirst, syncOff, syncTotal);
+    if (rc) return rc;
+    return searchFinish(out, warns);
+  }
+  int searchStart(PassData& pd, const SearchConfig& sc, const std::vector<RegionDesc>& regs, const std::vector<uint8_t>& windows,
+                  const int* tierFirst, const std::vector<int32_t>& syncOff, size_t syncTotal) override {
+    pendOut_.assign(regs.size(), RegionResult());
+    pendWarns_.clear();
+    for (int tier = 0; tier <= kTierGeneral; ++tier) {
+      if (tierFirst[tier + 1] > tierFirst[tier]) {
+        runTier(pd, sc, regs, (size_t) tierFirst[tier], (size_t) tierFirst[tier + 1], windows, tier, pendOut_, syncOff, syncTotal, pendWarns_);
+      }
+    }
+    return 0;
+  }
+  int searchFinish(std::vector<RegionResult>& out, std::vector<WarnRec>& warns) override {
+    out = pendOut_;
+    warns.insert(warns.end(), pendWarns_.begin(), pendWarns_.end());
+    return 0;
+  }
+  std::vector<RegionResult> pendOut_;
+  std::vector<WarnRec> pendWarns_;
+
+  int runTier(PassData& pd, const SearchConfig& sc, const std::vector<RegionDesc>& regs, size_t q0, size_t q1,
+              const std::vector<uint8_t>& windows, int tier, std::vector<RegionResult>& out, const std::vector<int32_t>& syncOff,
+              size_t syncTotal, std::vector<WarnRec>& warns) {
     const bool general = tier >= kTierGeneral;
     const FastShape fs = fastShape(general ? 0 : tier);
     ++stats.launches;
     std::vector<int32_t>& syncOut = sync_[pd.pass];
     if (syncOut.size() < syncTotal) syncOut.resize(syncTotal, 0);
-    for (size_t q = 0; q < regs.size(); ++q) {
+    for (size_t q = q0; q < q1; ++q) {
       RegionConst rk;
       RegionSearch<HostLane> rs(&rk);
       rs.R = regs[q];
