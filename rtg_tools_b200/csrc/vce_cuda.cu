@@ -605,11 +605,11 @@ class CudaBackend : public Backend {
     CUDA_TRY(cudaMemcpyAsync(syncOff_.p, syncOff.data(), nr * 4, cudaMemcpyHostToDevice, stream_));
     CUDA_TRY(cudaMemcpyAsync(windows_.p, windows.data(), windows.size(), cudaMemcpyHostToDevice, stream_));
     stats.h2dBytes += (int64_t) (nr * (sizeof(RegionDesc) + 4) + windows.size());
-    CUDA_TRY(cudaMemsetAsync(ints_.p + 4, 0, 8 * sizeof(int), stream_));  // [4..6] work counters per tier, [7] warning count
+    CUDA_TRY(cudaMemsetAsync(ints_.p + 4, 0, 8 * sizeof(int), stream_));  // [4..7] work counters per tier, [8] warning count
 
     // arena / scratch sizes over all tiers first (buffers must not move between the launches)
-    int blocksT[kTierGeneral + 1] = {0, 0, 0}, threadsT[kTierGeneral + 1] = {0, 0, 0};
-    size_t smemT[kTierGeneral + 1] = {0, 0, 0};
+    int blocksT[kTierGeneral + 1] = {0}, threadsT[kTierGeneral + 1] = {0};
+    size_t smemT[kTierGeneral + 1] = {0};
     SearchParams spT[kTierGeneral + 1];
     int maxWarps = 0;
     for (int tier = 0; tier <= kTierGeneral; ++tier) {
@@ -622,7 +622,7 @@ class CudaBackend : public Backend {
       sp.regs = regs_.p + r0; sp.nRegs = (int) nt;
       sp.S[0] = sideArrays(0); sp.S[1] = sideArrays(1);
       sp.windows = windows_.p; sp.cfg = sc; sp.out = rres_.p + r0; sp.syncOff = syncOff_.p + r0; sp.syncOut = syncBuf_.p;
-      sp.warns = warns_.p; sp.warnCount = ints_.p + 7; sp.warnCap = warnCap; sp.counter = ints_.p + 4 + tier;
+      sp.warns = warns_.p; sp.warnCount = ints_.p + 8; sp.warnCap = warnCap; sp.counter = ints_.p + 4 + tier;
       sp.H = pd.H;
       sp.maxChildren = 1 + std::max(pd.maxOrient[0], pd.maxOrient[1]);
       sp.regionBase = r0;
@@ -703,7 +703,7 @@ class CudaBackend : public Backend {
     int nWarn = 0;
     const int warnCap = 1 << 16;
     CUDA_TRY(cudaMemcpyAsync(out.data(), rres_.p, nr * sizeof(RegionResult), cudaMemcpyDeviceToHost, stream_));
-    CUDA_TRY(cudaMemcpyAsync(&nWarn, ints_.p + 7, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    CUDA_TRY(cudaMemcpyAsync(&nWarn, ints_.p + 8, sizeof(int), cudaMemcpyDeviceToHost, stream_));
     CUDA_TRY(cudaStreamSynchronize(stream_));
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, ev0_, ev1_));
@@ -964,7 +964,7 @@ class CudaBackend : public Backend {
   int mNextEvent_ = 0, mNextLane_ = 0;
   cudaEvent_t evM0_ = nullptr, evM1_ = nullptr;
   int microBlocksPerSm_[2] = {1, 1};
-  int microRefill_ = 16;
+  int microRefill_ = 24;
   DevBuf<MicroChunkDesc> mTable_;
   std::string err_;
 };

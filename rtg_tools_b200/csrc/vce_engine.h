@@ -134,7 +134,7 @@ class Engine {
   struct WideBatch {           // one batch of regions in the warp-per-region kernels
     std::vector<RegKey> ids;   // grouped by tier
     std::vector<int> tier;
-    int tierFirst[kTierGeneral + 2] = {0, 0, 0, 0};
+    int tierFirst[kTierGeneral + 2] = {0};
     PassData pd;
     AlleleTable at[2];
     std::vector<RegionDesc> descs;
