@@ -400,7 +400,10 @@ class CudaBackend : public Backend {
 
   int init() {
     CUDA_TRY(cudaSetDevice(device_));
-    CUDA_TRY(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    // the thread-per-region chunks feed the host pipeline and go first; the warp-per-region batches fill the gaps
+    int prLow = 0, prHigh = 0;
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prLow, &prHigh));
+    CUDA_TRY(cudaStreamCreateWithPriority(&stream_, cudaStreamNonBlocking, prLow));
     CUDA_TRY(cudaEventCreate(&ev0_));
     CUDA_TRY(cudaEventCreate(&ev1_));
     CUDA_TRY(cudaEventCreate(&evT0_));
@@ -413,7 +416,7 @@ class CudaBackend : public Backend {
     CUDA_TRY(cudaFuncSetAttribute(k_search<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (4096 + 1024) * kFastWarps));
     CUDA_TRY(cudaFuncSetAttribute(k_micro<MicroA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMicroThreads * MicroA::WS_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(k_micro<MicroB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMicroThreads * MicroB::WS_BYTES));
-    for (int i = 0; i < kMicroLanes; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&mStream_[i], cudaStreamNonBlocking));
+    for (int i = 0; i < kMicroLanes; ++i) CUDA_TRY(cudaStreamCreateWithPriority(&mStream_[i], cudaStreamNonBlocking, prHigh));
     CUDA_TRY(cudaEventCreate(&evM0_));
     CUDA_TRY(cudaEventCreate(&evM1_));
     {
@@ -646,12 +649,16 @@ class CudaBackend : public Backend {
         if (warpsPerBlock < kFastWarps) warpsPerBlock = std::max(1, (int) ((size_t) maxSmemOptin_ / bytesPerWarp) / 2);
         threads = warpsPerBlock * 32;
         smemBytes = bytesPerWarp * warpsPerBlock;
-        int perSm = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_search<false>, threads, smemBytes));
-        if (perSm < 1) perSm = 1;
-        blocks = smCount_ * perSm;
+        // moderate batches: one region per warp, short-lived blocks, so that the block scheduler can favour the
+        // high-priority streams; huge batches: resident blocks pulling from the work queue
         const int need = (int) ((nt + warpsPerBlock - 1) / warpsPerBlock);
-        if (blocks > need) blocks = need;
+        blocks = need;
+        if (need > 16384) {
+          int perSm = 0;
+          CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_search<false>, threads, smemBytes));
+          if (perSm < 1) perSm = 1;
+          blocks = std::min(need, smCount_ * perSm);
+        }
       } else {
         // per-warp arena sized for the largest record layout in this launch at the full search budget
         long long maxW = 0;

@@ -876,9 +876,11 @@ int Engine::run(const vce_config& cfg, int32_t nSeq, const vce_sequence* seqs, v
 // grow a large frontier (many variants on one side) directly in the large shared-memory tier, the rest in HBM arenas.
 int Engine::startTier(const PassCtx& pc, const RegRange& g) const {
   if (opt_.forceGeneral || pc.H > 2) return kTierGeneral;
+  // the frontier grows with the variants on one side (orientations multiply): pick the tier that will hold it
   const int m = std::max(g.cCount, g.bCount);
-  if (m <= fastShape(0).kv) return m >= 5 ? 1 : 0;
-  if (m <= fastShape(1).kv) return 1;
+  if (m <= 4) return 0;
+  if (m == 5) return 1;
+  if (m <= fastShape(2).kv) return 2;
   return kTierGeneral;
 }
 
@@ -1317,18 +1319,6 @@ int Engine::settle(PassCtx& pc, WideBatch& early) {
 // PhasingEvaluator.countMisphasings, src/com/rtg/vcf/eval/PhasingEvaluator.java:55-142, on the flat pass-0 results.
 namespace {
 struct VSum { int start; bool phased, included, phase; };
-struct CallIter {  // PhasingEvaluator.CallIterator :160-195
-  const std::vector<VSum>& inc;
-  const std::vector<VSum>& exc;
-  size_t i = 0, e = 0;
-  CallIter(const std::vector<VSum>& a, const std::vector<VSum>& b) : inc(a), exc(b) {}
-  bool hasNext() const { return i < inc.size() || e < exc.size(); }
-  VSum next() {
-    const bool haveI = i < inc.size(), haveE = e < exc.size();
-    if (!haveI || (haveE && exc[e].start < inc[i].start)) return exc[e++];
-    return inc[i++];
-  }
-};
 bool groupInPhase(const std::vector<VSum>& g) {  // :143-155
   if (g.empty()) return true;
   if (!g[0].phased) return false;
@@ -1340,31 +1330,47 @@ bool groupInPhase(const std::vector<VSum>& g) {  // :143-155
 
 static inline void pickRow(int kind, int H, int gtPloidy, const vce_variants& in, int ii, int row, int8_t* ids, uint8_t* original);
 
+namespace {
+// PhasingEvaluator.CallIterator :160-195 streamed over the flat results of one side: merges the included and the
+// excluded variants by start, included first on ties.
+struct CallIter {
+  const uint8_t* dec;      // decisions of the side's variants of this sequence (sorted order)
+  const int32_t* start;
+  const vce_variants& in;
+  const int32_t* idx;
+  int n, kind, H, gtPloidy;
+  int i = 0, e = 0;        // next included / excluded candidate
+  CallIter(const uint8_t* d, const int32_t* st, const vce_variants& v, const int32_t* ix, int n_, int kind_, int H_, int gp)
+      : dec(d), start(st), in(v), idx(ix), n(n_), kind(kind_), H(H_), gtPloidy(gp) {
+    while (i < n && dec[i] < 2) ++i;
+    while (e < n && dec[e] != 1) ++e;
+  }
+  bool hasNext() const { return i < n || e < n; }
+  VSum next() {
+    const bool haveI = i < n, haveE = e < n;
+    if (!haveI || (haveE && start[e] < start[i])) {
+      const int li = e;
+      do { ++e; } while (e < n && dec[e] != 1);
+      const int ii = idx ? idx[li] : li;
+      return VSum{start[li], in.phased && in.phased[ii], false, false};
+    }
+    const int li = i;
+    do { ++i; } while (i < n && dec[i] < 2);
+    const int ii = idx ? idx[li] : li;
+    int8_t ids[4];
+    uint8_t orig = 0;
+    pickRow(kind, H, gtPloidy, in, ii, dec[li] - 2, ids, &orig);
+    return VSum{start[li], in.phased && in.phased[ii], true, orig != 0};
+  }
+};
+}  // namespace
+
 void Engine::phasing(int k, const std::vector<int32_t>& sync, int32_t out[3]) const {
   const PassCtx& pc = pass_[0];
-  std::vector<VSum> inc[2], exc[2];
-  for (int side = 0; side < 2; ++side) {
-    const SideSeq& s = pc.ss[side][k];
-    const vce_variants& in = *s.in;
-    inc[side].reserve((size_t) s.n);
-    for (int li = 0; li < s.n; ++li) {
-      const int v = s.first + li;
-      const int dec = pc.decision[side][v];
-      if (dec == 0) continue;
-      const int ii = s.idx ? s.idx[li] : li;
-      const bool ph = in.phased && in.phased[ii];
-      if (dec == 1) {
-        exc[side].push_back(VSum{pc.vStart[side][v], ph, false, false});
-      } else {
-        int8_t ids[4];
-        uint8_t orig = 0;
-        pickRow(pc.kind[side], pc.H, pc.gtPloidy[side], in, ii, dec - 2, ids, &orig);
-        inc[side].push_back(VSum{pc.vStart[side][v], ph, true, orig != 0});
-      }
-    }
-  }
-  CallIter baseline(inc[1], exc[1]);
-  CallIter calls(inc[0], exc[0]);
+  const SideSeq& sc = pc.ss[0][k];
+  const SideSeq& sb = pc.ss[1][k];
+  CallIter baseline(pc.decision[1].data() + sb.first, pc.vStart[1].data() + sb.first, *sb.in, sb.idx, sb.n, pc.kind[1], pc.H, pc.gtPloidy[1]);
+  CallIter calls(pc.decision[0].data() + sc.first, pc.vStart[0].data() + sc.first, *sc.in, sc.idx, sc.n, pc.kind[0], pc.H, pc.gtPloidy[0]);
   int mis = 0, unph = 0, correct = 0;
   bool baseIsPhased = false, basePhase = false, callIsPhased = false, callPhase = false;
   bool haveCall = false, haveBase = false;
@@ -1481,29 +1487,16 @@ bool Engine::assembleHeader(int k, vce_sequence_result& res) {
   for (int p = 0; p < cfg_.n_passes; ++p) {
     const PassCtx& pc = pass_[p];
     std::vector<int32_t>& sync = seqSync_[p][k];
-    const int n = (int) pc.rs[k].size();
-    sync.reserve((size_t) n + 8);
-    const RegRes* rs = pc.rs[k].data();
-    for (int j = 0; j < n; ++j) {
-      const RegRes& s = rs[j];
-      if (s.state == RS_MICRO_DONE) {
-        const int base = regionStartPos(pc, k, j);
-        for (int q = 0; q < s.nSync; ++q) {
-          const int sp = base + s.rel[q];
-          if (sync.empty() || sync.back() != sp) sync.push_back(sp);  // Path.java:293 de-duplication
-        }
-      } else if (s.state == RS_WIDE_DONE) {
-        for (int q = 0; q < s.ext.n; ++q) {
-          const int sp = pc.wideSync[s.ext.idx + q];
-          if (sync.empty() || sync.back() != sp) sync.push_back(sp);
-        }
-      } else if (s.state == RS_ERR_NULL) {
-        res.error = VCE_ERR_BEST_PATH_NULL;
-      } else if (s.state == RS_ERR_MOVE) {
-        res.error = VCE_ERR_MOVE_IN_VARIANT;
-      } else if (s.state == RS_ERR_ORDER) {
-        res.error = VCE_ERR_UNSUPPORTED;
-      }
+    // the sync points of the sequence's region blocks were gathered in parallel (finish()); join them here
+    size_t total = 0;
+    for (int t = syncPartFirst_[p][k]; t < syncPartFirst_[p][k + 1]; ++t) total += syncParts_[t].v.size();
+    sync.reserve(total + 8);
+    for (int t = syncPartFirst_[p][k]; t < syncPartFirst_[p][k + 1]; ++t) {
+      const SyncPart& sp = syncParts_[t];
+      if (sp.err) res.error = sp.err;
+      size_t from = 0;
+      if (!sync.empty() && !sp.v.empty() && sp.v[0] == sync.back()) from = 1;  // Path.java:293 de-duplication across the joint
+      sync.insert(sync.end(), sp.v.begin() + (long) from, sp.v.end());
     }
     // re-runs append out of order: report in region order, as the sequential reference would
     std::vector<WarnEntry> ws;
@@ -1635,6 +1628,53 @@ int Engine::finish(vce_sequence_result* results) {
     const int na = seqs_[a].calls.n + seqs_[a].baseline.n, nb = seqs_[b].calls.n + seqs_[b].baseline.n;
     return na != nb ? na > nb : a < b;
   });
+  // sync points of every pass, gathered per block of regions (Path.getSyncPoints with the Path.java:293 de-duplication)
+  syncParts_.clear();
+  const int rblock = 1 << 15;
+  for (int p = 0; p < 2; ++p) {
+    syncPartFirst_[p].assign((size_t) nSeq_ + 1, (int) syncParts_.size());
+    if (p >= cfg_.n_passes) continue;
+    for (int k = 0; k < nSeq_; ++k) {
+      syncPartFirst_[p][k] = (int) syncParts_.size();
+      const int n = pass_[0].shortCircuit[k] ? 0 : (int) pass_[p].rs[k].size();
+      for (int r0 = 0; r0 < n; r0 += rblock) {
+        SyncPart sp;
+        sp.pass = p; sp.seq = k; sp.r0 = r0; sp.r1 = std::min(n, r0 + rblock); sp.err = 0;
+        syncParts_.push_back(std::move(sp));
+      }
+    }
+    syncPartFirst_[p][nSeq_] = (int) syncParts_.size();
+  }
+  pool_->parallelFor((int) syncParts_.size(), [&](int t, int) {
+    SyncPart& sp = syncParts_[t];
+    const PassCtx& pc = pass_[sp.pass];
+    const int k = sp.seq;
+    const RegRes* rs = pc.rs[k].data();
+    std::vector<int32_t>& sync = sp.v;
+    sync.reserve((size_t) (sp.r1 - sp.r0) + 8);
+    for (int j = sp.r0; j < sp.r1; ++j) {
+      const RegRes& s = rs[j];
+      if (s.state == RS_MICRO_DONE) {
+        const int base = regionStartPos(pc, k, j);
+        for (int q = 0; q < s.nSync; ++q) {
+          const int pos = base + s.rel[q];
+          if (sync.empty() || sync.back() != pos) sync.push_back(pos);
+        }
+      } else if (s.state == RS_WIDE_DONE) {
+        for (int q = 0; q < s.ext.n; ++q) {
+          const int pos = pc.wideSync[s.ext.idx + q];
+          if (sync.empty() || sync.back() != pos) sync.push_back(pos);
+        }
+      } else if (s.state == RS_ERR_NULL) {
+        sp.err = VCE_ERR_BEST_PATH_NULL;
+      } else if (s.state == RS_ERR_MOVE) {
+        sp.err = VCE_ERR_MOVE_IN_VARIANT;
+      } else if (s.state == RS_ERR_ORDER) {
+        sp.err = VCE_ERR_UNSUPPORTED;
+      }
+    }
+  });
+  tm.lap("assemble: sync point blocks");
   std::vector<uint8_t> live(nSeq_, 0);
   pool_->parallelFor(nSeq_, [&](int t, int) {
     const int k = order[t];

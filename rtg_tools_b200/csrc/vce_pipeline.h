@@ -136,11 +136,12 @@ struct FastShape {
   VCE_HD int slots() const { return cap + 1 + maxChildren; }
   VCE_HD int ordCap() const { return 2 * cap; }
 };
-constexpr int kTierGeneral = 3;
+constexpr int kTierGeneral = 4;
 inline FastShape fastShape(int tier) {
   switch (tier) {
     case 0: return FastShape{8, 2, 8, 24, 7, 1536};      // ~9 KB per warp: many resident warps
-    case 1: return FastShape{16, 8, 20, 112, 7, 4096};   // ~50 KB per warp
+    case 1: return FastShape{8, 8, 12, 48, 7, 2048};     // ~22 KB per warp
+    case 2: return FastShape{16, 8, 20, 112, 7, 4096};   // ~50 KB per warp
     default: return FastShape{16, 8, 20, 480, 7, 4096};  // ~190 KB: one warp per SM, for the few regions in between
   }
 }
