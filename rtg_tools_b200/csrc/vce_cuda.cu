@@ -608,7 +608,8 @@ class CudaBackend : public Backend {
     CUDA_TRY(cudaMemcpyAsync(syncOff_.p, syncOff.data(), nr * 4, cudaMemcpyHostToDevice, stream_));
     CUDA_TRY(cudaMemcpyAsync(windows_.p, windows.data(), windows.size(), cudaMemcpyHostToDevice, stream_));
     stats.h2dBytes += (int64_t) (nr * (sizeof(RegionDesc) + 4) + windows.size());
-    CUDA_TRY(cudaMemsetAsync(ints_.p + 4, 0, 8 * sizeof(int), stream_));  // [4..7] work counters per tier, [8] warning count
+    static_assert(kTierGeneral + 1 <= 8, "work counters live in ints_[4..11]");
+    CUDA_TRY(cudaMemsetAsync(ints_.p + 4, 0, 9 * sizeof(int), stream_));  // [4..11] work counters per tier, [12] warning count
 
     // arena / scratch sizes over all tiers first (buffers must not move between the launches)
     int blocksT[kTierGeneral + 1] = {0}, threadsT[kTierGeneral + 1] = {0};
@@ -625,7 +626,7 @@ class CudaBackend : public Backend {
       sp.regs = regs_.p + r0; sp.nRegs = (int) nt;
       sp.S[0] = sideArrays(0); sp.S[1] = sideArrays(1);
       sp.windows = windows_.p; sp.cfg = sc; sp.out = rres_.p + r0; sp.syncOff = syncOff_.p + r0; sp.syncOut = syncBuf_.p;
-      sp.warns = warns_.p; sp.warnCount = ints_.p + 8; sp.warnCap = warnCap; sp.counter = ints_.p + 4 + tier;
+      sp.warns = warns_.p; sp.warnCount = ints_.p + 12; sp.warnCap = warnCap; sp.counter = ints_.p + 4 + tier;
       sp.H = pd.H;
       sp.maxChildren = 1 + std::max(pd.maxOrient[0], pd.maxOrient[1]);
       sp.regionBase = r0;
@@ -710,7 +711,7 @@ class CudaBackend : public Backend {
     int nWarn = 0;
     const int warnCap = 1 << 16;
     CUDA_TRY(cudaMemcpyAsync(out.data(), rres_.p, nr * sizeof(RegionResult), cudaMemcpyDeviceToHost, stream_));
-    CUDA_TRY(cudaMemcpyAsync(&nWarn, ints_.p + 8, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    CUDA_TRY(cudaMemcpyAsync(&nWarn, ints_.p + 12, sizeof(int), cudaMemcpyDeviceToHost, stream_));
     CUDA_TRY(cudaStreamSynchronize(stream_));
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, ev0_, ev1_));
