@@ -100,39 +100,25 @@ class ClockSampler:
 
 
 def build_workload(name, rank, world, scaling, total_bp=None):
-    from rtg_tools_b200 import partition, synth
+    """Returns (sequences, call scores, description, global sequence ids, total sequences of the job)."""
+    from rtg_tools_b200 import multigpu, synth
     bp, n_chrom, desc = WORKLOADS[name]
     if total_bp:
         bp = int(total_bp)
     if scaling == "strong" and world > 1:
+        # ONE sample pair, its chromosomes sharded over the ranks by LPT (weights: chromosome lengths ~ variant counts)
         lens = synth.genome_lengths(bp, n_chrom) if n_chrom > 1 else [bp]
-        mine = partition.lpt_partition(lens, world)[rank]
+        mine = multigpu.shard_sequences(lens, rank, world)
         seqs, quals = synth.make_pair(bp, n_chrom=n_chrom, only=mine, return_qual=True)
-        pair = 0
-    else:
-        # weak: sample pair `rank` of the cohort (pair 0 = the canonical seeds 42 / 572 / 126)
-        pair = rank
-        seqs, quals = synth.make_pair(bp, n_chrom=n_chrom, sample_seed=572 + 1000 * pair, perturb_seed=126 + 1000 * pair,
-                                      return_qual=True)
-    return seqs, quals, desc, pair
+        return seqs, quals, desc, mine, len(lens)
+    # weak: rank r evaluates sample pair r of the cohort (pair 0 = the canonical seeds 42 / 572 / 126)
+    seqs, quals = synth.make_pair(bp, n_chrom=n_chrom, sample_seed=572 + 1000 * rank, perturb_seed=126 + 1000 * rank,
+                                  return_qual=True)
+    return seqs, quals, desc, list(range(rank * len(seqs), (rank + 1) * len(seqs))), world * len(seqs)
 
 
 def n_variants(seqs):
     return int(sum(s.baseline.n + s.calls.n for s in seqs))
-
-
-def summary_counts(seqs, results):
-    """TP-baseline / FN / TP-call / FP / skipped totals (the numbers summary.txt is made of)."""
-    from rtg_tools_b200 import capi
-    tot = np.zeros(6, np.int64)
-    for r in results:
-        b, c = r.baseline.status, r.calls.status
-        tot[0] += int(((b & capi.STATUS_GT_MATCH) != 0).sum())
-        tot[1] += int(((b & capi.STATUS_NO_MATCH) != 0).sum())
-        tot[2] += int(((c & capi.STATUS_GT_MATCH) != 0).sum())
-        tot[3] += int(((c & capi.STATUS_NO_MATCH) != 0).sum())
-        tot[4] += int(((b & capi.STATUS_SKIPPED) != 0).sum()) + int(((c & capi.STATUS_SKIPPED) != 0).sum())
-    return tot
 
 
 def run_reference(args, rank, world):
@@ -141,7 +127,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from rtg_tools_b200 import capi
-    seqs, quals, desc, pair = build_workload(args.workload, 0, 1, "weak", args.total_bp)
+    seqs, quals, desc, _, _ = build_workload(args.workload, 0, 1, "weak", args.total_bp)
     oracle = capi.Library(os.path.join(ROOT, "oracle", "liboracle.so"), prefix="oracle_")
     cores = os.cpu_count() or 1
     threads = max(1, min(cores, len(seqs)))
@@ -194,7 +180,10 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from rtg_tools_b200 import capi, vcfeval
+    # the ranks of one box share its host cores: give every rank's digest / assembly pool its share
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("VCE_THREADS", str(max(1, cores // max(1, world))))
+    from rtg_tools_b200 import capi, multigpu, vcfeval
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
@@ -209,7 +198,7 @@ def main():
         torch.cuda.synchronize()
 
     t_gen = time.perf_counter()
-    seqs, quals, desc, pair = build_workload(args.workload, rank, world, args.scaling, args.total_bp)
+    seqs, quals, desc, seq_ids, n_seq_total = build_workload(args.workload, rank, world, args.scaling, args.total_bp)
     nv = n_variants(seqs)
     log("[rank %d] workload %s: %d sequences, %d variants (generated in %.1fs)" % (rank, args.workload, len(seqs), nv,
                                                                                time.perf_counter() - t_gen))
@@ -254,11 +243,7 @@ def main():
         rc = eng.lib.submit_packed(packed)
         if rc != 0:
             raise RuntimeError("vce_submit failed: %s" % eng.lib.last_error())
-        counts = summary_counts(seqs, res)
-        if world > 1:  # the summary merge: the only collective of the path
-            t = torch.from_numpy(counts).cuda()
-            dist.all_reduce(t)
-            counts = t.cpu().numpy()
+        counts = multigpu.merge_counts(multigpu.summary_counts(res))  # the summary merge: the only collective of the path
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     e2e_results = capi.Library.unpack(packed[2], packed[3], packed[4])
@@ -285,6 +270,9 @@ def main():
     total_regions = reduce_sum(regions)
     total_launches = reduce_sum(launches)
 
+    # ROC tuples of every rank travel to rank 0 in (sequence, record) order: K4 runs once on the merged stream
+    roc_rows = multigpu.gather_roc([multigpu.roc_tuples([r], [q]) for r, q in zip(results, quals)], seq_ids, n_seq_total) \
+        if (world > 1 and not args.no_roc) else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -336,17 +324,20 @@ def main():
     # ------------------------------------------------------------------ ROC (K4) on the scored calls of the run, reported beside
     roc = None
     if not args.no_roc:
-        score = np.concatenate(quals) if quals else np.zeros(0)
-        wts = np.concatenate([r.calls.weight for r in results]) if results else np.zeros(0)
-        stc = np.concatenate([r.calls.status for r in results]) if results else np.zeros(0, np.uint8)
-        tp = np.where((stc & capi.STATUS_GT_MATCH) != 0, wts, 0.0)
-        raw = ((stc & capi.STATUS_GT_MATCH) != 0).astype(np.float64)
-        fp = ((stc & capi.STATUS_NO_MATCH) != 0).astype(np.float64)
+        if roc_rows is None:
+            roc_rows = multigpu.roc_tuples(results, quals)
+        score, tp, fp, raw = (np.ascontiguousarray(roc_rows[:, i]) for i in range(4))
         eng.roc(score, tp, fp, raw, None, 1)
         t0 = time.perf_counter()
         rows, _ = eng.roc(score, tp, fp, raw, None, 1)
         dt = time.perf_counter() - t0
-        roc = {"scored_calls": int(score.shape[0]), "rows": int(rows[0][0].shape[0]), "e2e_calls_per_s": score.shape[0] / dt}
+        roc = {"scored_calls": int(score.shape[0]), "rows": int(rows[0][0].shape[0]), "e2e_calls_per_s": score.shape[0] / dt,
+               "merged_over_ranks": world}
+        if cpu is not None:
+            want_rows, _ = oracle.roc(score, tp, fp, raw, None, 1)
+            for x, y in zip(rows[0], want_rows[0]):
+                assert np.array_equal(x.view(np.int64), y.view(np.int64)), "ROC rows differ from the oracle"
+            roc["parity"] = "bit-exact vs oracle"
 
     value = total_variants / (ms_per_step * 1e-3)
     out = {
@@ -356,7 +347,8 @@ def main():
         "config": {"workload": "%s: %s" % (args.workload, desc), "variants_per_step": int(total_variants),
                    "sync_regions_per_step": int(total_regions), "sequences_per_rank": len(seqs),
                    "l2": "inputs larger than L2 (per-variant arrays + reference windows > 126 MB)" if nv > 2_000_000 else "inputs smaller than L2 (small workload)",
-                   "sharding": "none (1 GPU)" if world == 1 else ("sample pair per rank" if args.scaling == "weak" else "LPT over chromosomes")},
+                   "sharding": "none (1 GPU)" if world == 1 else ("one sample pair per rank" if args.scaling == "weak" else "LPT over chromosomes"),
+                   "host_threads_per_rank": int(os.environ.get("VCE_THREADS", "0"))},
         "sync_regions_per_s": total_regions / (ms_per_step * 1e-3),
         "wall_ms_per_step": wall_per_step,
         "e2e": {"value": total_variants / (e2e_ms * 1e-3), "unit": "variants/s", "ms_per_step": e2e_ms,
