@@ -26,14 +26,18 @@ def shard_sequences(weights: Sequence[float], rank: int, world: int) -> List[int
 def _device(backend_device: Optional[torch.device]) -> torch.device:
     if backend_device is not None:
         return backend_device
+    if not dist.is_initialized():
+        return torch.device("cpu")
     return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
 
 
 def merge_counts(counts: np.ndarray, device: Optional[torch.device] = None) -> np.ndarray:
     """Sum of the per-rank int64 counters (TP / FN / FP totals, phasing counts, skipped ...)."""
-    t = torch.from_numpy(np.ascontiguousarray(counts, np.int64)).to(_device(device))
-    if dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    counts = np.ascontiguousarray(counts, np.int64)
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return counts
+    t = torch.from_numpy(counts).to(_device(device))
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t.cpu().numpy()
 
 

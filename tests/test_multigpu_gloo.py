@@ -86,3 +86,11 @@ def test_lpt_partition_balances_by_variant_count():
         bins = partition.lpt_partition(lens, world)
         assert sorted(i for b in bins for i in b) == list(range(24))
         assert partition.imbalance(lens, bins) < 1.12
+
+
+def test_merge_is_a_no_op_without_a_process_group():
+    from rtg_tools_b200 import multigpu
+    c = np.arange(8, dtype=np.int64)
+    assert np.array_equal(multigpu.merge_counts(c), c)
+    rows = multigpu.gather_roc([np.ones((2, 4)), np.zeros((1, 4))], [1, 0], 2)
+    assert rows.shape == (3, 4) and rows[0, 0] == 0.0
