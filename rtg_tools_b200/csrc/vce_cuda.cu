@@ -784,6 +784,8 @@ class CudaBackend : public Backend {
     for (DevBlock& b : dBlocks_) b.used = 0;
     mNextEvent_ = 0;
     mNextLane_ = 0;
+    lastMicroMs_ = 0;
+    lastMicroRegions_ = 0;
     return VCE_OK;
   }
   void microMark() override {
@@ -906,7 +908,7 @@ class CudaBackend : public Backend {
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, evM0_, evM1_));
     stats.searchMs += ms;
-    if (total >= lastMicroRegions_ || jobs[0]->cls == 0) {
+    if (jobs[0]->cls == 0 && total >= lastMicroRegions_ / 2) {  // the main MicroA launch (not the small settle retries)
       lastMicroMs_ = ms;
       lastMicroRegions_ = total;
     }

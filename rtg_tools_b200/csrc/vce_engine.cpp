@@ -582,6 +582,7 @@ int Engine::buildChunk(PassCtx& pc, Chunk& ch, int worker, bool launch) {
   }
   ch.pktRegion[0].reserve(nr);
   ch.variants = 0;
+  ch.variantsA = 0;
   uint8_t* cls = pc.rcls[k].data();
   RegRes* rs = pc.rs[k].data();
   const RegRange* rrk = pc.rr[k].data();
@@ -616,6 +617,7 @@ int Engine::buildChunk(PassCtx& pc, Chunk& ch, int worker, bool launch) {
       if (!ch.transient) cls[j] = (uint8_t) (1 + c);
       rs[j].state = RS_PENDING;
       ch.variants += rrk[j].cCount + rrk[j].bCount;
+      if (c == 0) ch.variantsA += rrk[j].cCount + rrk[j].bCount;
     } else {
       if (!ch.transient) cls[j] = 0;
       rs[j].state = RS_RESIDUAL;
@@ -853,7 +855,7 @@ int Engine::execute() {
     for (const Chunk& ch : pc.chunks) {
       be_->stats.regions += ch.r1 - ch.r0;
       microRegions += ch.job[0].n + ch.job[1].n;
-      microVariants += ch.variants;
+      microVariants += ch.variantsA;
     }
     if ((rc = settle(pc, early))) return rc;
     tm.lap("settle residual");
@@ -1202,7 +1204,13 @@ int Engine::settle(PassCtx& pc, WideBatch& early) {
         }
         rch.back().list.push_back(id.j);
       }
-      for (Chunk& ch : rch) if ((rc = buildChunk(pc, ch, 0, true))) return rc;
+      // build every sequence's packets, then ONE launch per packet class over all of them
+      for (Chunk& ch : rch) if ((rc = buildChunk(pc, ch, 0, false))) return rc;
+      for (int c = 0; c < 2; ++c) {
+        std::vector<MicroJob*> jobs;
+        for (Chunk& ch : rch) if (ch.job[c].n > 0) jobs.push_back(&ch.job[c]);
+        if (!jobs.empty() && (rc = be_->microRunAll(jobs, pc.mc))) { err_ = be_->lastError(); return rc; }
+      }
       int64_t it = 0;
       for (Chunk& ch : rch) {
         for (int c = 0; c < 2; ++c) if (ch.job[c].n > 0 && (rc = be_->microWait(ch.job[c]))) { err_ = be_->lastError(); return rc; }

@@ -48,7 +48,7 @@ class Engine {
   int finish(vce_sequence_result* results);
   const std::string& error() const { return err_; }
   Backend* backend() { return be_; }
-  // diagnostics of the last execute(): milliseconds of the largest thread-per-region launch, its regions and variants
+  // diagnostics of the last execute(): regions of the thread-per-region launches, variants of the MicroA class
   double microMs = 0;
   int64_t microRegions = 0, microVariants = 0;
 
@@ -86,7 +86,7 @@ class Engine {
     bool transient = false;              // settling: leaves the per-region packet class of the main chunks alone
     MicroJob job[2];                     // one job per packet class (MicroA, MicroB)
     std::vector<int32_t> pktRegion[2];   // packet -> region index within the sequence
-    int64_t variants = 0;
+    int64_t variants = 0, variantsA = 0;
   };
   struct WarnEntry { int32_t seq, j; WarnRec w; };
   struct PassCtx {
