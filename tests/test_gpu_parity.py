@@ -58,6 +58,33 @@ def test_cuda_dense_clusters(engine, oracle):
     compare_results(want, engine.submit(cfg, seqs), seqs)
 
 
+def test_cuda_dense_clusters_default_budget(engine, oracle):
+    """BASELINE.json configs[2] at the reference's own budget (50 000 paths / 10^7 iterations): the large-capacity
+    kernel must reproduce the too-complex skip, the warning text fields and every surviving assignment."""
+    rng = np.random.default_rng(11)
+    seqs = [synth.dense_cluster_sequence(rng, n_clusters=3, per_side=(12, 16), name="d%d" % i) for i in range(2)]
+    want = oracle.submit(capi.Config(), seqs, threads=2)
+    assert any(w["paths"] > 50000 for r in want for w in r.warnings), "stress input should exceed the default budget"
+    compare_results(want, engine.submit(capi.Config(), seqs), seqs)
+
+
+def test_cuda_genome_slice_all_modes(engine, oracle):
+    """BASELINE.json configs[3] on a 10 % slice of the 24-chromosome genome: --squash-ploidy (haploid SQUASH_GT) and the
+    two-pass mode of ga4gh / annotate / combine (diploid, then haploid allele matching on FN / FP)."""
+    seqs = synth.make_pair(300_000_000, n_chrom=24)
+    assert sum(s.baseline.n + s.calls.n for s in seqs) > 800_000
+    for name in ("squash", "twopass", "phased"):
+        compare_results(oracle.submit(CONFIGS[name], seqs, threads=8), engine.submit(CONFIGS[name], seqs), seqs, what=name)
+
+
+def test_cuda_repeated_runs_are_identical(engine, oracle):
+    """Determinism: the same batch gives bit-identical results on every call (chunks, streams and re-runs race-free)."""
+    seqs = synth.make_pair(60_000_000, n_chrom=24)
+    want = oracle.submit(CONFIGS["twopass"], seqs, threads=8)
+    for rep in range(6):
+        compare_results(want, engine.submit(CONFIGS["twopass"], seqs), seqs, what="rep %d" % rep)
+
+
 def test_cuda_staged_job_equals_submit(engine, oracle):
     seqs = synth.make_pair(2_000_000, n_chrom=2)
     job = engine.job(CONFIGS["twopass"], seqs)
