@@ -104,6 +104,7 @@ struct SearchParams {
 
 constexpr int kWarnPerRegion = 64;
 constexpr int kFastWarps = 8;
+constexpr int kHeadWords = 768;   // large-capacity kernel: shared-memory record of the path being expanded
 
 // Copies the region's slices of the variant / orientation / allele tables into shared memory and points the search at
 // them (the pointers are re-based so that the search keeps indexing with the batch-wide indices).  The serial part of
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(kFastWarps * 32) k_search(const __grid_constan
 
   // per-warp shared memory: [RegionConst | tier layout ...] (fast tiers) or [RegionConst | tables] (general)
   const int kcWords = (int) ((sizeof(RegionConst) + 15) / 16) * 4;
-  int32_t* warpBase = GENERAL ? smem + (size_t) warp * (kcWords + p.tabBytes / 4) : smem + (size_t) warp * p.wordsPerWarp;
+  int32_t* warpBase = GENERAL ? smem + (size_t) warp * (kcWords + p.tabBytes / 4 + kHeadWords) : smem + (size_t) warp * p.wordsPerWarp;
   RegionConst* kc = reinterpret_cast<RegionConst*>(warpBase);
   RegionSearch<DeviceWarp> rs(kc);
   if (lane == 0) kc->cfg = p.cfg;
@@ -197,6 +198,7 @@ __global__ void __launch_bounds__(kFastWarps * 32) k_search(const __grid_constan
   } else {
     tabS = reinterpret_cast<uint8_t*>(warpBase + kcWords);
   }
+  int32_t* headS = GENERAL ? reinterpret_cast<int32_t*>(tabS + p.tabBytes) : nullptr;
 
   while (true) {
     int r = 0;
@@ -217,15 +219,17 @@ __global__ void __launch_bounds__(kFastWarps * 32) k_search(const __grid_constan
       rs.maxChildren = p.maxChildren;
       const long long ctlWords = 16 + 2 * p.maxChildren;
       // capacity that fits this warp's arena:  (nSlots+2)*W + ordCap + nSlots + ctl <= arenaWords,
-      // nSlots = cap + 1 + MC, ordCap = 2*cap + 2
+      // nSlots = cap + 1 + MC, ordCap = chunkWords(cap) <= 3*cap + 1024 (two-level frontier)
       long long cap = p.cfg.maxPaths + 1 + p.maxChildren;
-      const long long fixed = (long long) (3 + p.maxChildren) * rs.L.W + 2 + (1 + p.maxChildren) + ctlWords;
-      const long long fit = (p.arenaWordsPerWarp - fixed) / (rs.L.W + 3);
+      const long long fixed = (long long) (3 + p.maxChildren) * rs.L.W + 1024 + (1 + p.maxChildren) + ctlWords;
+      const long long fit = (p.arenaWordsPerWarp - fixed) / (rs.L.W + 4);
       if (cap > fit) cap = fit;
       if (cap < 1) cap = 1;
       rs.cap = (int) cap;
       rs.nSlots = rs.cap + 1 + p.maxChildren;
-      rs.ordCap = 2 * rs.cap + 2;
+      rs.ordCap = RegionSearch<DeviceWarp>::chunkWords(rs.cap);
+      rs.chunked = true;
+      rs.headBuf = rs.L.W <= kHeadWords ? headS : nullptr;
       int32_t* base = p.arena + (size_t) gwarp * p.arenaWordsPerWarp;
       rs.slots = base;
       rs.order = base + (size_t) (rs.nSlots + 2) * rs.L.W;
@@ -413,7 +417,7 @@ class CudaBackend : public Backend {
     CUDA_TRY(cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_));
     maxSmemOptin_ = maxSmem;
     CUDA_TRY(cudaFuncSetAttribute(k_search<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
-    CUDA_TRY(cudaFuncSetAttribute(k_search<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (4096 + 1024) * kFastWarps));
+    CUDA_TRY(cudaFuncSetAttribute(k_search<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (4096 + 1024 + kHeadWords * 4) * kFastWarps));
     CUDA_TRY(cudaFuncSetAttribute(k_micro<MicroA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMicroThreads * MicroA::WS_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(k_micro<MicroB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMicroThreads * MicroB::WS_BYTES));
     for (int i = 0; i < kMicroLanes; ++i) CUDA_TRY(cudaStreamCreateWithPriority(&mStream_[i], cudaStreamNonBlocking, prHigh));
@@ -666,7 +670,7 @@ class CudaBackend : public Backend {
         for (int q = r0; q < r1; ++q) maxW = std::max(maxW, (long long) regs[q].layoutW);
         const long long mc = sp.maxChildren;
         const long long capFull = (long long) sc.maxPaths + 1 + mc;
-        long long words = (capFull + 1 + mc + 2) * maxW + (2 * capFull + 2) + (capFull + 1 + mc) + 16 + 2 * mc + 64;
+        long long words = (capFull + 1 + mc + 2) * maxW + (3 * capFull + 1024) + (capFull + 1 + mc) + 16 + 2 * mc + 64;
         const long long budgetWords = (long long) (48ull << 30) / 4;  // 48 GB of HBM for search arenas
         long long warpsWanted = std::min<long long>((long long) nt, (long long) smCount_ * kFastWarps);
         if (words > budgetWords) words = budgetWords;  // a single region larger than the budget runs with reduced capacity
@@ -679,7 +683,7 @@ class CudaBackend : public Backend {
         sp.arenaWordsPerWarp = words;
         sp.tabBytes = 4096;
         const int kcWords = (int) ((sizeof(RegionConst) + 15) / 16) * 4;
-        smemBytes = ((size_t) sp.tabBytes + (size_t) kcWords * 4) * kFastWarps;
+        smemBytes = ((size_t) sp.tabBytes + (size_t) kcWords * 4 + (size_t) kHeadWords * 4) * kFastWarps;
       }
       blocksT[tier] = blocks; threadsT[tier] = threads; smemT[tier] = smemBytes;
       maxWarps = std::max(maxWarps, blocks * (threads / 32));

@@ -115,6 +115,20 @@ struct RegionSearch {
   int32_t* ctl;          // 16 + 2*maxChildren words of lane-0 -> warp mailbox
   int cap;               // frontier capacity of this kernel (overflow beyond)
   int ordCap;            // physical length of order[] (>= cap + 1)
+  // Large frontiers (large-capacity kernel): the sorted frontier is a two-level structure inside order[] -- a directory
+  // of blocks of up to kBlk slot ids each -- so that an insert moves at most one block (java.util.TreeSet is O(log n);
+  // a flat sorted array would move half the frontier per insert).  See the frontier* / chunk* members.
+  bool chunked = false;
+  static constexpr int kBlk = 64;          // slot ids per block
+  static constexpr int kBlkStride = kBlk + 2;  // [0] = start, [1] = count, then the ids
+  int nbMax = 0, nb = 0, dh = 0, nbFree = 0;  // blocks available / in use, directory head offset, free blocks
+  VCE_HD static int chunkWords(int capacity) {  // words of order[] the chunked frontier needs for `capacity` paths
+    const int nbm = capacity / (kBlk / 2) + 8;
+    return 2 * nbm + nbm + nbm * kBlkStride;
+  }
+  VCE_HD int32_t* cdir() const { return order; }                       // [2*nbMax] directory (deque, head offset dh)
+  VCE_HD int32_t* cfree() const { return order + 2 * nbMax; }          // [nbMax] free block stack
+  VCE_HD int32_t* cblk(int b) const { return order + 3 * nbMax + b * kBlkStride; }
   int nSlots;
   int maxChildren;
   int oh;                // deque head offset (warp-uniform)
@@ -132,9 +146,13 @@ struct RegionSearch {
   enum { ACT_ENQUEUE = 1, ACT_STEP_DROP = 2, ACT_STEP_REINSERT = 3, ACT_STEP_FINISH = 4, ACT_BOUNDARY_CLEAN = 5,
          ACT_BOUNDARY_SPILL = 6 };
 
-  VCE_HD int32_t* P(int slot) const { return slots + (size_t) slot * L.W; }
+  // The path being expanded ("head") is worked on many times per iteration: the large-capacity kernel, whose path
+  // records live in HBM, keeps it in a shared-memory record (slot id slotHead()) and writes it back only on re-insert.
+  int32_t* headBuf = nullptr;
+  VCE_HD int32_t* P(int slot) const { return slot == nSlots + 2 ? headBuf : slots + (size_t) slot * L.W; }
   VCE_HD int slotLS() const { return nSlots; }
   VCE_HD int slotBest() const { return nSlots + 1; }
+  VCE_HD int slotHead() const { return nSlots + 2; }
   VCE_HD void flag(int f) {
 #if defined(__CUDA_ARCH__)
     atomicOr(ctl + CTL_FLAGS, f);
@@ -449,8 +467,196 @@ struct RegionSearch {
     }
   }
 
+  // ---- chunked frontier (see `chunked`)
+  VCE_HD void chunkInit(int firstSlot) {  // frontier = { firstSlot } (firstSlot < 0: empty)
+    nbMax = (ordCap - 0) / (kBlkStride + 3);
+    for (int i = w.lane(); i < nbMax; i += WP::L) cfree()[i] = nbMax - 1 - i;  // pop order 0, 1, 2, ...
+    w.sync();
+    nbFree = nbMax - 1;
+    nb = 1;
+    dh = 0;
+    if (w.lane() == 0) {
+      cdir()[0] = 0;
+      int32_t* B = cblk(0);
+      B[0] = 0;
+      B[1] = firstSlot >= 0 ? 1 : 0;
+      B[2] = firstSlot;
+    }
+    w.sync();
+  }
+  VCE_HD int chunkPop() {  // pollFirst; n > 0
+    int32_t* B = cblk(cdir()[dh]);
+    const int st = B[0], cnt = B[1];
+    const int head = B[2 + st];
+    w.sync();
+    if (cnt == 1 && nb > 1) {  // first block drained: release it
+      if (w.lane() == 0) cfree()[nbFree] = cdir()[dh];
+      ++nbFree;
+      ++dh;
+      --nb;
+    } else if (w.lane() == 0) {
+      B[0] = cnt == 1 ? 0 : st + 1;
+      B[1] = cnt - 1;
+    }
+    w.sync();
+    return head;
+  }
+  VCE_HD int chunkLastSlot(int bi) const {  // greatest path of directory entry bi
+    const int32_t* B = cblk(cdir()[dh + bi]);
+    return B[2 + B[0] + B[1] - 1];
+  }
+  // Block bi (directory index) and local position pos of path c: pos = #paths of the block that are less than c;
+  // eq = true when the path at pos equals c.
+  VCE_HD void chunkFind(int c, int& bi, int& pos, bool& eq) {
+    const int32_t* pc = P(c);
+    eq = false;
+    // 1. the first block whose greatest path is >= c (the last block if there is none)
+    int lo = 0, hi = nb - 1;  // answer in [lo, hi]
+    while (lo < hi) {
+      // probe up to WP::L block maxima spread over [lo, hi)
+      const int span = hi - lo;
+      const int step = (span + WP::L - 1) / WP::L;
+      const int j = lo + w.lane() * step;   // probes lo, lo+step, ...
+      int ge = 1;
+      if (j < hi) ge = pathCompare(P(chunkLastSlot(j)), pc) >= 0 ? 1 : 0;
+      const unsigned m = w.ballot(j < hi && ge);
+      const unsigned valid = w.ballot(j < hi);
+      if (m != 0) {
+        const int k = vffs(m);             // first probed block with max >= c
+        hi = lo + k * step;
+        lo = k == 0 ? lo : lo + (k - 1) * step + 1;
+        if (lo > hi) lo = hi;
+      } else {
+        lo = lo + (vpopc(valid) - 1) * step + 1;  // beyond the last probe
+        if (lo > hi) lo = hi;
+      }
+    }
+    bi = lo;
+    // 2. position inside the block
+    const int32_t* B = cblk(cdir()[dh + bi]);
+    const int st = B[0], cnt = B[1];
+    pos = cnt;
+    for (int base = 0; base < cnt; base += WP::L) {
+      const int i = base + w.lane();
+      int cmp = 1;
+      if (i < cnt) cmp = pathCompare(P(B[2 + st + i]), pc);
+      const unsigned less = w.ballot(cmp < 0);
+      const unsigned e = w.ballot(cmp == 0);
+      if (e) { pos = base + vffs(e); eq = true; return; }
+      const int k = vpopc(less);
+      if (k < WP::L) { pos = base + k; return; }
+    }
+  }
+  VCE_HD void chunkShiftUp(int32_t* a, int from, int to) {  // a[from..to) -> a[from+1..to+1), highest chunk first
+    for (int base = ((to - from - 1) / WP::L) * WP::L; base >= 0 && to > from; base -= WP::L) {
+      const int i = from + base + w.lane();
+      int v = 0;
+      const bool act = i < to;
+      if (act) v = a[i];
+      w.sync();
+      if (act) a[i + 1] = v;
+      w.sync();
+    }
+  }
+  VCE_HD void chunkShiftDown(int32_t* a, int from, int to) {  // a[from..to) -> a[from-1..to-1)
+    for (int base = 0; from + base < to; base += WP::L) {
+      const int i = from + base + w.lane();
+      int v = 0;
+      const bool act = i < to;
+      if (act) v = a[i];
+      w.sync();
+      if (act) a[i - 1] = v;
+      w.sync();
+    }
+  }
+  VCE_HD bool chunkInsert(int bi, int pos, int c) {
+    if (n >= cap) return false;
+    int32_t* B = cblk(cdir()[dh + bi]);
+    if (B[1] >= kBlk) {  // full: move the upper half to a new block right after this one
+      if (nbFree <= 0) return false;
+      const int nbk = cfree()[nbFree - 1];
+      --nbFree;
+      int32_t* N = cblk(nbk);
+      const int st = B[0], half = kBlk / 2;
+      for (int i = w.lane(); i < half; i += WP::L) N[2 + i] = B[2 + st + half + i];
+      w.sync();
+      if (w.lane() == 0) { N[0] = 0; N[1] = half; B[1] = half; }
+      // directory: open entry bi + 1
+      if (dh + nb >= 2 * nbMax) {  // out of room at the top: compact to the bottom
+        for (int base = 0; base < nb; base += WP::L) {
+          const int i = base + w.lane();
+          int v = 0;
+          const bool act = i < nb;
+          if (act) v = cdir()[dh + i];
+          w.sync();
+          if (act) cdir()[i] = v;
+          w.sync();
+        }
+        dh = 0;
+      }
+      chunkShiftUp(cdir() + dh, bi + 1, nb);
+      if (w.lane() == 0) cdir()[dh + bi + 1] = nbk;
+      ++nb;
+      w.sync();
+      if (pos > half) { ++bi; pos -= half; B = N; }
+    }
+    const int st = B[0], cnt = B[1];
+    if (st > 0 && pos <= cnt - pos) {  // cheaper to move the front part down
+      chunkShiftDown(B + 2, st, st + pos);
+      if (w.lane() == 0) { B[2 + st - 1 + pos] = c; B[0] = st - 1; B[1] = cnt + 1; }
+    } else {
+      if (st + cnt >= kBlk) {  // no room at the top of the block: compact it first
+        chunkShiftDownBy(B + 2, st, st + cnt, st);
+        if (w.lane() == 0) B[0] = 0;
+        w.sync();
+        chunkShiftUp(B + 2, pos, cnt);
+        if (w.lane() == 0) { B[2 + pos] = c; B[1] = cnt + 1; }
+      } else {
+        chunkShiftUp(B + 2, st + pos, st + cnt);
+        if (w.lane() == 0) { B[2 + st + pos] = c; B[1] = cnt + 1; }
+      }
+    }
+    ++n;
+    if (n > maxFrontier) maxFrontier = n;
+    w.sync();
+    return true;
+  }
+  VCE_HD void chunkShiftDownBy(int32_t* a, int from, int to, int by) {  // a[from..to) -> a[from-by..to-by), by <= from
+    for (int base = 0; from + base < to; base += WP::L) {
+      const int i = from + base + w.lane();
+      int v = 0;
+      const bool act = i < to;
+      if (act) v = a[i];
+      w.sync();
+      if (act) a[i - by] = v;
+      w.sync();
+    }
+  }
+  VCE_HD bool addIfBetterChunked(int c) {
+    int bi, pos;
+    bool eq;
+    w.sync();
+    chunkFind(c, bi, pos, eq);
+    if (eq) {
+      int32_t* B = cblk(cdir()[dh + bi]);
+      const int other = B[2 + B[0] + pos];
+      const bool cWins = firstIsBetter(P(c), P(other));
+      w.sync();
+      if (cWins) {
+        if (w.lane() == 0) B[2 + B[0] + pos] = c;
+        pushFree(other);
+      } else {
+        pushFree(c);
+      }
+      w.sync();
+      return true;
+    }
+    return chunkInsert(bi, pos, c);
+  }
+
   // PathFinder.addIfBetter :321-348.  Returns false on frontier overflow.
   VCE_HD bool addIfBetter(int c) {
+    if (chunked) return addIfBetterChunked(c);
     int pos, eqPos;
     w.sync();
     findPos(c, pos, eqPos);
@@ -603,20 +809,34 @@ struct RegionSearch {
     if (w.lane() == 0) {
       for (int i = 0; i < 16; ++i) ctl[i] = 0;
       initPath(P(0));
-      order[0] = 0;
+      if (!chunked) order[0] = 0;
     }
     oh = 0;
     nFree -= 1;  // slot 0 taken
     n = 1;
     w.sync();
+    if (chunked) chunkInit(0);
     resultSlot = -1;
 
     while (n > 0) {
       ++iters;  // :145 currentIterations++
       ++totalIters;
-      int head = ORD(0);
-      ++oh;  // pollFirst
+      int head;
+      if (chunked) {
+        head = chunkPop();
+      } else {
+        head = ORD(0);
+        ++oh;  // pollFirst
+      }
       --n;
+      if (headBuf != nullptr) {  // move the head into the fast record, release its slot
+        w.sync();
+        copyPath(slotHead(), head);
+        w.sync();
+        pushFree(head);
+        w.sync();
+        head = slotHead();
+      }
       bool headIsLS = false;
       if (n == 0) {  // :151-161 only one path in play
         lastSyncPos = sidePos(P(head), 0);
@@ -636,6 +856,7 @@ struct RegionSearch {
         head = 0;
         nFree -= 1;
         w.sync();
+        if (chunked) chunkInit(-1);
         copyPath(head, slotLS());
         w.sync();
         if (w.lane() == 0) {
@@ -775,7 +996,7 @@ struct RegionSearch {
         }
         // claim the child slots, release the parent
         nFree -= nChild;
-        pushFree(head);
+        if (head != slotHead()) pushFree(head);
         w.sync();
         for (int k = 0; k < nChild; ++k) {
           const int cs = childSlot(k);
@@ -790,7 +1011,7 @@ struct RegionSearch {
       }
 
       if (act == ACT_STEP_DROP) {
-        pushFree(head);
+        if (head != slotHead()) pushFree(head);
         w.sync();
         continue;
       }
@@ -799,11 +1020,19 @@ struct RegionSearch {
         if (bestValid) take = !firstIsBetter(P(slotBest()), P(head));
         w.sync();
         if (take) { copyPath(slotBest(), head); bestValid = 1; }
-        pushFree(head);
+        if (head != slotHead()) pushFree(head);
         w.sync();
         continue;
       }
       // ACT_STEP_REINSERT :203
+      if (head == slotHead()) {  // back into a real slot (the one released at the pop is still free)
+        if (nFree <= 0) return kRegionOverflow;
+        const int s2 = freeList[nFree - 1];
+        --nFree;
+        copyPath(s2, head);
+        w.sync();
+        head = s2;
+      }
       if (!addIfBetter(head)) return kRegionOverflow;
     }
     if (R.cNextStart != kNoNext || R.bNextStart != kNoNext) {

@@ -162,9 +162,12 @@ class EmulBackend : public Backend {
       while (true) {
         rs.cap = capTry;
         rs.nSlots = rs.cap + 1 + rs.maxChildren;
-        rs.ordCap = 2 * rs.cap + 2;
+        rs.chunked = general || forceGeneral;
+        rs.ordCap = rs.chunked ? RegionSearch<HostLane>::chunkWords(rs.cap) : 2 * rs.cap + 2;
         std::vector<int32_t> slots((size_t) (rs.nSlots + 2) * rs.L.W), order(rs.ordCap), freeList(rs.nSlots), ctl(16 + 2 * rs.maxChildren);
         rs.slots = slots.data(); rs.order = order.data(); rs.freeList = freeList.data(); rs.ctl = ctl.data();
+        std::vector<int32_t> headRec((size_t) rs.L.W + 4);
+        rs.headBuf = rs.chunked ? headRec.data() : nullptr;   // the large-capacity path keeps the head in a side record
         std::vector<WarnRec> lw(64);
         rs.warnOut = lw.data(); rs.warnCap = 64; rs.regionId = (int) q;
         int resultSlot = -1;
