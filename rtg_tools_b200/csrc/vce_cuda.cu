@@ -100,6 +100,7 @@ struct SearchParams {
   int wordsPerWarp;      // shared-memory words per warp (whole layout)
   int tabBytes;          // shared memory per warp for the region's tables
   int regionBase;        // index of regs[0] within the batch (warnings carry batch-wide region indices)
+  int useHead;           // large-capacity kernel: keep the expanded path in shared memory
 };
 
 constexpr int kWarnPerRegion = 64;
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(kFastWarps * 32) k_search(const __grid_constan
       rs.nSlots = rs.cap + 1 + p.maxChildren;
       rs.ordCap = RegionSearch<DeviceWarp>::chunkWords(rs.cap);
       rs.chunked = true;
-      rs.headBuf = rs.L.W <= kHeadWords ? headS : nullptr;
+      rs.headBuf = (p.useHead && rs.L.W <= kHeadWords) ? headS : nullptr;
       int32_t* base = p.arena + (size_t) gwarp * p.arenaWordsPerWarp;
       rs.slots = base;
       rs.order = base + (size_t) (rs.nSlots + 2) * rs.L.W;
@@ -634,6 +635,9 @@ class CudaBackend : public Backend {
       sp.H = pd.H;
       sp.maxChildren = 1 + std::max(pd.maxOrient[0], pd.maxOrient[1]);
       sp.regionBase = r0;
+      // experimental (off by default): on the device this showed a non-terminating search on the too-complex fixture
+      // that the 1-lane host instantiation does not reproduce; the arena-only path is the verified one
+      sp.useHead = std::getenv("VCE_HEADBUF") ? 1 : 0;
       int blocks = 0, threads = kFastWarps * 32;
       size_t smemBytes = 0;
       if (!general) {
