@@ -296,7 +296,6 @@ struct MicroParams {
   MicroConfig cfg;
 };
 constexpr int kMicroThreads = 64;
-constexpr int kMicroThreadsC = 32;   // MicroC slices are 5.6 KB: one warp per block
 
 template <class T>
 __global__ void __launch_bounds__(kMicroThreads) k_micro(const __grid_constant__ MicroParams p) {
@@ -422,7 +421,6 @@ class CudaBackend : public Backend {
     CUDA_TRY(cudaFuncSetAttribute(k_search<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (4096 + 1024 + kHeadWords * 4) * kFastWarps));
     CUDA_TRY(cudaFuncSetAttribute(k_micro<MicroA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMicroThreads * MicroA::WS_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(k_micro<MicroB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMicroThreads * MicroB::WS_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(k_micro<MicroC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMicroThreadsC * MicroC::WS_BYTES));
     for (int i = 0; i < kMicroLanes; ++i) CUDA_TRY(cudaStreamCreateWithPriority(&mStream_[i], cudaStreamNonBlocking, prHigh));
     CUDA_TRY(cudaEventCreate(&evM0_));
     CUDA_TRY(cudaEventCreate(&evM1_));
@@ -432,8 +430,6 @@ class CudaBackend : public Backend {
       microBlocksPerSm_[0] = perSm < 1 ? 1 : perSm;
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_micro<MicroB>, kMicroThreads, kMicroThreads * MicroB::WS_BYTES));
       microBlocksPerSm_[1] = perSm < 1 ? 1 : perSm;
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_micro<MicroC>, kMicroThreadsC, kMicroThreadsC * MicroC::WS_BYTES));
-      microBlocksPerSm_[2] = perSm < 1 ? 1 : perSm;
       if (const char* e = std::getenv("VCE_MICRO_REFILL")) microRefill_ = std::max(1, std::min(32, std::atoi(e)));
     }
     ready_ = true;
@@ -851,14 +847,12 @@ class CudaBackend : public Backend {
     return VCE_OK;
   }
   int microGrid(int n, int cls) const {
-    const int th = cls == 2 ? kMicroThreadsC : kMicroThreads;
-    const int need = (n + th - 1) / th;
+    const int need = (n + kMicroThreads - 1) / kMicroThreads;
     return std::max(1, std::min(need, smCount_ * microBlocksPerSm_[cls]));
   }
   void microLaunch(const MicroParams& mp, int cls, cudaStream_t st) {
     if (cls == 0) k_micro<MicroA><<<microGrid(mp.total, 0), kMicroThreads, kMicroThreads * MicroA::WS_BYTES, st>>>(mp);
-    else if (cls == 1) k_micro<MicroB><<<microGrid(mp.total, 1), kMicroThreads, kMicroThreads * MicroB::WS_BYTES, st>>>(mp);
-    else k_micro<MicroC><<<microGrid(mp.total, 2), kMicroThreadsC, kMicroThreadsC * MicroC::WS_BYTES, st>>>(mp);
+    else k_micro<MicroB><<<microGrid(mp.total, 1), kMicroThreads, kMicroThreads * MicroB::WS_BYTES, st>>>(mp);
   }
   int microRun(MicroJob& j, const MicroConfig& mc) override {
     CUDA_TRY(cudaSetDevice(device_));
@@ -987,8 +981,8 @@ class CudaBackend : public Backend {
   std::vector<cudaEvent_t> mEvents_;
   int mNextEvent_ = 0, mNextLane_ = 0;
   cudaEvent_t evM0_ = nullptr, evM1_ = nullptr;
-  int microBlocksPerSm_[kMicroClasses] = {1, 1, 1};
-  int microRefill_ = 32;
+  int microBlocksPerSm_[2] = {1, 1};
+  int microRefill_ = 24;
   DevBuf<MicroChunkDesc> mTable_;
   std::string err_;
 };

@@ -68,11 +68,8 @@ struct RowPick {  // selects one orientation row of a variant (host side of K1, 
 }  // namespace
 
 Engine::Engine(Backend* b, WorkerPool* pool, const EngineOptions& o) : be_(b), pool_(pool), opt_(o) {
-  classCount_.resize(pool_->threads());
-  classKeys_.resize(pool_->threads());
-  classOrder_.resize(pool_->threads());
-  scratch_ = new std::vector<uint8_t>[pool_->threads()][kMicroClasses];
-  scratchOff_ = new std::vector<uint32_t>[pool_->threads()][kMicroClasses];
+  scratch_ = new std::vector<uint8_t>[pool_->threads()][2];
+  scratchOff_ = new std::vector<uint32_t>[pool_->threads()][2];
 }
 
 Engine::~Engine() {
@@ -560,33 +557,6 @@ int Engine::buildPacket(const PassCtx& pc, int k, int j, uint8_t* out) const {
   return bytes;
 }
 
-// Shape class of a MicroA packet: regions of one class take the same branches in the search, so packets are emitted
-// grouped by class -- the lanes of a warp (32 consecutive packets) then run in lock step.
-static inline uint32_t packetClass(const uint8_t* pk) {
-  const int cC = pk[MP_COUNTS] & 0xf, bC = pk[MP_COUNTS] >> 4;
-  const uint8_t* al = pk + MP_VARS + (cC + bC) * MV_BYTES;
-  uint32_t key = (uint32_t) (cC | (bC << 1));
-  const uint8_t* v = pk + MP_VARS;
-  uint32_t sig[16] = {0};
-  for (int i = 0; i < cC + bC && i < 16; ++i, v += MV_BYTES) {
-    const int a0 = v[MV_A0], a1 = v[MV_A1];
-    const uint32_t l0 = a0 == kMicroNoAllele ? 3u : std::min<uint32_t>(al[a0 * MA_BYTES + MA_LEN], 2u);
-    const uint32_t l1 = a1 == kMicroNoAllele ? 3u : std::min<uint32_t>(al[a1 * MA_BYTES + MA_LEN], 2u);
-    const uint32_t span = std::min<uint32_t>((uint32_t) (v[MV_END] - v[MV_START]), 3u);
-    const uint32_t het = v[MV_GT0] != v[MV_GT1] ? 1u : 0u;
-    const uint32_t ph = v[MV_FLAGS] & 1u;
-    sig[i] = l0 | (l1 << 2) | (span << 4) | (het << 6) | (ph << 7);
-    key = key * 257u + sig[i];
-  }
-  if (cC == 1 && bC == 1) {
-    const uint8_t* vc = pk + MP_VARS;
-    const uint8_t* vb = vc + MV_BYTES;
-    const uint32_t same = (vc[MV_START] == vb[MV_START] && vc[MV_END] == vb[MV_END] && sig[0] == sig[1]) ? 1u : 0u;
-    key = key * 2u + same;
-  }
-  return key & 0x7fffu;
-}
-
 static std::atomic<long long> g_tBuild(0), g_tCopy(0), g_tUpload(0);
 static inline long long nowNs() {
   return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -603,9 +573,9 @@ int Engine::buildChunk(PassCtx& pc, Chunk& ch, int worker, bool launch) {
   std::vector<uint32_t>* so = scratchOff_[worker];
   sc[0].resize((size_t) nr * MicroA::PKT_MAX + 16);
   so[0].resize(nr);
-  size_t at[kMicroClasses] = {0, 0, 0};
-  int np[kMicroClasses] = {0, 0, 0};
-  for (int c = 0; c < kMicroClasses; ++c) {
+  size_t at[2] = {0, 0};
+  int np[2] = {0, 0};
+  for (int c = 0; c < 2; ++c) {
     ch.pktRegion[c].clear();
     ch.job[c] = MicroJob();
     ch.job[c].cls = c;
@@ -637,14 +607,10 @@ int Engine::buildChunk(PassCtx& pc, Chunk& ch, int worker, bool launch) {
         c = 1;
         if (sc[1].size() < at[1] + MicroB::PKT_MAX + 16) sc[1].resize(std::max(sc[1].size() * 2, at[1] + (size_t) 64 * MicroB::PKT_MAX));
         bytes = buildPacket<MicroB>(pc, k, j, sc[1].data() + at[1]);
-      } else if (g.cCount <= MicroC::KV && g.bCount <= MicroC::KV) {
-        c = 2;
-        if (sc[2].size() < at[2] + MicroC::PKT_MAX + 16) sc[2].resize(std::max(sc[2].size() * 2, at[2] + (size_t) 64 * MicroC::PKT_MAX));
-        bytes = buildPacket<MicroC>(pc, k, j, sc[2].data() + at[2]);
       }
     }
     if (bytes > 0) {
-      if (c >= 1 && (int) so[c].size() <= np[c]) so[c].resize(std::max<size_t>(so[c].size() * 2, 64));
+      if (c == 1 && (int) so[1].size() <= np[1]) so[1].resize(std::max<size_t>(so[1].size() * 2, 64));
       so[c][np[c]++] = (uint32_t) (at[c] >> 2);
       ch.pktRegion[c].push_back(j);
       at[c] += (size_t) bytes;
@@ -660,10 +626,10 @@ int Engine::buildChunk(PassCtx& pc, Chunk& ch, int worker, bool launch) {
   const long long tB = nowNs();
   g_tBuild += tB - tA;
   int rc = VCE_OK;
-  for (int c = 0; c < kMicroClasses && rc == VCE_OK; ++c) {
+  for (int c = 0; c < 2 && rc == VCE_OK; ++c) {
     MicroJob& job = ch.job[c];
     job.n = np[c];
-    job.resBytes = c == 0 ? MicroA::RES_BYTES : (c == 1 ? MicroB::RES_BYTES : MicroC::RES_BYTES);
+    job.resBytes = c == 0 ? MicroA::RES_BYTES : MicroB::RES_BYTES;
     if (np[c] == 0) continue;
     uint8_t* pk = arenaAlloc(at[c] + 16);
     uint8_t* off = arenaAlloc((size_t) np[c] * 4);
@@ -673,38 +639,8 @@ int Engine::buildChunk(PassCtx& pc, Chunk& ch, int worker, bool launch) {
       err_ = "out of page-locked host memory";
       return VCE_ERR_CUDA;
     }
-    if (opt_.sortPackets && np[c] > 64) {
-      // counting sort of the packets by shape class while they are copied to page-locked memory
-      std::vector<uint32_t>& cnt = classCount_[worker];
-      std::vector<uint32_t>& keys = classKeys_[worker];
-      cnt.assign(0x8000 + 1, 0);
-      keys.resize((size_t) np[c]);
-      const uint8_t* src = sc[c].data();
-      for (int q = 0; q < np[c]; ++q) {
-        keys[q] = packetClass(src + (size_t) so[c][q] * 4);
-        ++cnt[keys[q] + 1];
-      }
-      for (int kx = 0; kx < 0x8000; ++kx) cnt[kx + 1] += cnt[kx];   // first output index of every class
-      // output order -> packet: place, then lay the packets out back to back
-      std::vector<int32_t>& orderOut = classOrder_[worker];
-      orderOut.resize((size_t) np[c]);
-      for (int q = 0; q < np[c]; ++q) orderOut[cnt[keys[q]]++] = q;
-      std::vector<int32_t> regs(ch.pktRegion[c]);
-      uint32_t* offOut = reinterpret_cast<uint32_t*>(off);
-      size_t w = 0;
-      for (int o = 0; o < np[c]; ++o) {
-        const int q = orderOut[o];
-        const uint8_t* pkt = src + (size_t) so[c][q] * 4;
-        const size_t bytes = (size_t) pkt[MP_NWORDS] * 4;
-        std::memcpy(pk + w, pkt, bytes);
-        offOut[o] = (uint32_t) (w >> 2);
-        ch.pktRegion[c][o] = regs[q];
-        w += bytes;
-      }
-    } else {
-      std::memcpy(pk, sc[c].data(), at[c]);
-      std::memcpy(off, so[c].data(), (size_t) np[c] * 4);
-    }
+    std::memcpy(pk, sc[c].data(), at[c]);
+    std::memcpy(off, so[c].data(), (size_t) np[c] * 4);
     job.packets = pk;
     job.packetBytes = at[c];
     job.offsets = reinterpret_cast<const uint32_t*>(off);
@@ -741,7 +677,6 @@ void Engine::decodeJob(PassCtx& pc, int k, const MicroJob& job, const std::vecto
     s.flags = rec[MR_FLAGS] & 1;
     s.lastId = (int8_t) rec[MR_LASTID];
     s.nSync = rec[MR_NSYNC];
-    static_assert(T::SMAX <= (int) sizeof(s.rel), "RegRes holds the relative sync points of a packet result");
     for (int i = 0; i < T::SMAX; ++i) s.rel[i] = rec[MR_SYNC + i];
     const uint8_t* dec = rec + MR_SYNC + T::SMAX;
     const uint8_t* wn = dec + 2 * T::KV;
@@ -758,7 +693,6 @@ void Engine::decodeJob(PassCtx& pc, int k, const MicroJob& job, const std::vecto
 void Engine::decodeChunk(PassCtx& pc, Chunk& ch, int64_t& iterations) {
   decodeJob<MicroA>(pc, ch.seq, ch.job[0], ch.pktRegion[0], iterations);
   decodeJob<MicroB>(pc, ch.seq, ch.job[1], ch.pktRegion[1], iterations);
-  decodeJob<MicroC>(pc, ch.seq, ch.job[2], ch.pktRegion[2], iterations);
 }
 
 // ------------------------------------------------------------------------------------------- life cycle
@@ -843,7 +777,7 @@ int Engine::runChunks(PassCtx& pc) {
       const int n = (int) rr.size();
       for (int j = 0; j < n; ++j) {
         const RegRange& g = rr[j];
-        const bool shape = g.cCount > MicroC::KV || g.bCount > MicroC::KV || j == 0 || j == n - 1;
+        const bool shape = g.cCount > MicroB::KV || g.bCount > MicroB::KV || j == 0 || j == n - 1;
         if (shape || !pc.microOk) {
           per[k].push_back(std::make_pair(RegKey{k, j}, startTier(pc, g)));
           pc.rcls[k][j] = kClsEarly;
@@ -894,7 +828,7 @@ int Engine::execute() {
         be_->microRewind();
       }
       if ((rc = wideStart(pc, pc.earlyItems, early))) return rc;
-      for (int c = 0; c < kMicroClasses; ++c) {
+      for (int c = 0; c < 2; ++c) {
         std::vector<MicroJob*> jobs;
         for (Chunk& ch : pc.chunks) if (ch.job[c].n > 0) jobs.push_back(&ch.job[c]);
         if (!jobs.empty()) {
@@ -907,7 +841,7 @@ int Engine::execute() {
     std::vector<int64_t> iters(pool_->threads(), 0);
     pool_->parallelFor((int) pc.chunks.size(), [&](int t, int worker) {
       Chunk& ch = pc.chunks[t];
-      for (int c = 0; c < kMicroClasses; ++c) {
+      for (int c = 0; c < 2; ++c) {
         if (ch.job[c].n > 0) {
           const int r = be_->microWait(ch.job[c]);
           if (r) { failed.store(r); return; }
@@ -920,7 +854,7 @@ int Engine::execute() {
     for (int64_t v : iters) be_->stats.iterations += v;
     for (const Chunk& ch : pc.chunks) {
       be_->stats.regions += ch.r1 - ch.r0;
-      microRegions += ch.job[0].n + ch.job[1].n + ch.job[2].n;
+      microRegions += ch.job[0].n + ch.job[1].n;
       microVariants += ch.variantsA;
     }
     if ((rc = settle(pc, early))) return rc;
@@ -1272,14 +1206,14 @@ int Engine::settle(PassCtx& pc, WideBatch& early) {
       }
       // build every sequence's packets, then ONE launch per packet class over all of them
       for (Chunk& ch : rch) if ((rc = buildChunk(pc, ch, 0, false))) return rc;
-      for (int c = 0; c < kMicroClasses; ++c) {
+      for (int c = 0; c < 2; ++c) {
         std::vector<MicroJob*> jobs;
         for (Chunk& ch : rch) if (ch.job[c].n > 0) jobs.push_back(&ch.job[c]);
         if (!jobs.empty() && (rc = be_->microRunAll(jobs, pc.mc))) { err_ = be_->lastError(); return rc; }
       }
       int64_t it = 0;
       for (Chunk& ch : rch) {
-        for (int c = 0; c < kMicroClasses; ++c) if (ch.job[c].n > 0 && (rc = be_->microWait(ch.job[c]))) { err_ = be_->lastError(); return rc; }
+        for (int c = 0; c < 2; ++c) if (ch.job[c].n > 0 && (rc = be_->microWait(ch.job[c]))) { err_ = be_->lastError(); return rc; }
         decodeChunk(pc, ch, it);
       }
       be_->stats.iterations += it;

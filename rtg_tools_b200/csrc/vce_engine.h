@@ -34,7 +34,6 @@ struct EngineOptions {
   bool disableMicro = false;   // tests: no thread-per-region kernel
   int chunkRegions = 0;        // regions per chunk, 0 = automatic
   int splitSegment = 1 << 16;  // variants per segment of the parallel region split
-  bool sortPackets = true;     // emit the packets of a chunk grouped by shape class (lock-step lanes)
 };
 
 class Engine {
@@ -85,8 +84,8 @@ class Engine {
     int seq = 0, r0 = 0, r1 = 0;
     std::vector<int32_t> list;           // explicit region indices (settling), empty = the range [r0, r1)
     bool transient = false;              // settling: leaves the per-region packet class of the main chunks alone
-    MicroJob job[kMicroClasses];                     // one job per packet class (MicroA, MicroB, MicroC)
-    std::vector<int32_t> pktRegion[kMicroClasses];   // packet -> region index within the sequence
+    MicroJob job[2];                     // one job per packet class (MicroA, MicroB)
+    std::vector<int32_t> pktRegion[2];   // packet -> region index within the sequence
     int64_t variants = 0, variantsA = 0;
   };
   struct WarnEntry { int32_t seq, j; WarnRec w; };
@@ -177,10 +176,8 @@ class Engine {
   std::vector<std::vector<int32_t>> seqSync_[2];   // [pass][seq] sync points (assembly)
   std::vector<std::vector<uint8_t>> seqDec1_[2];   // [side][seq] pass-2 decision by input index
   std::vector<std::vector<double>> seqW1_;         // [seq] pass-2 call weight by input index
-  std::vector<std::vector<uint32_t>> classCount_, classKeys_;   // per worker: counting sort of packets by shape class
-  std::vector<std::vector<int32_t>> classOrder_;
-  std::vector<uint8_t> (*scratch_)[kMicroClasses] = nullptr;     // [worker][class] packet staging
-  std::vector<uint32_t> (*scratchOff_)[kMicroClasses] = nullptr;
+  std::vector<uint8_t> (*scratch_)[2] = nullptr;     // [worker][class] packet staging
+  std::vector<uint32_t> (*scratchOff_)[2] = nullptr;
 };
 
 }  // namespace vce

@@ -15,7 +15,7 @@
 //     a few dozen bytes;
 //   * genotype/phase expansion (K1, Orientor.orientations) happens in place while the packet is unpacked;
 //   * search nodes are fixed-size int8 records in shared memory, the frontier is a small sorted index array,
-//     the free list a 64-bit mask in registers;
+//     the free list a 32-bit mask in a register;
 //   * the tie-break / weight epilogue (K3) writes one fixed-size result record.
 // Anything that does not fit the fixed capacities (frontier, pending alleles, sync points, window misses, the
 // reference's own too-complex budget, finishing at the template end) is reported as kMicroFallback and re-run by
@@ -101,14 +101,11 @@ struct MicroTraits {
   static constexpr int WS_RAW = OFF_PKT + ((PKT_MAX + 3) & ~3);
   // odd number of words per slice: lanes that read the same field of their own slice hit 32 different banks
   static constexpr int WS_BYTES = ((WS_RAW / 4) | 1) * 4;
-  static_assert(NSLOTS <= 64, "free list is one 64-bit mask");
-  static_assert(2 * KV <= 16, "packet header holds the counts in two nibbles, the class key 16 variants");
+  static_assert(NSLOTS <= 32, "free list is one 32-bit mask");
 };
 
 typedef MicroTraits<1, 0, 3, 10> MicroA;   // one variant per side
 typedef MicroTraits<4, 3, 6, 20> MicroB;   // up to four variants per side
-typedef MicroTraits<8, 7, 8, 60> MicroC;   // up to eight variants per side, frontiers up to 60 paths (split MNPs, merged spills)
-constexpr int kMicroClasses = 3;
 
 template <class T>
 struct MicroSearch {
@@ -124,7 +121,7 @@ struct MicroSearch {
   // region scalars
   int cCount, bCount, winLen, cNext, bNext, tmplLen, winBase, varsOff, allelesOff, ntOff;
   int n, iters, totalIters, usedPrefix, maxFrontier, flags;
-  uint64_t freeMask;
+  uint32_t freeMask;
 
   VCE_HD static int hapOff(int side, int h) { return side * T::SW + h * T::HW; }
   VCE_HD static int sideOff(int side) { return side * T::SW + 2 * T::HW; }
@@ -375,14 +372,14 @@ struct MicroSearch {
   }
   VCE_HD int allocSlot() {
 #if defined(__CUDA_ARCH__)
-    const int s = __ffsll((long long) freeMask) - 1;
+    const int s = __ffs((int) freeMask) - 1;
 #else
-    const int s = __builtin_ctzll(freeMask);
+    const int s = __builtin_ctz(freeMask);
 #endif
-    freeMask &= ~(1ull << s);
+    freeMask &= ~(1u << s);
     return s;
   }
-  VCE_HD void freeSlot(int s) { freeMask |= 1ull << s; }
+  VCE_HD void freeSlot(int s) { freeMask |= 1u << s; }
 
   // The frontier is kept in DESCENDING order: order()[n-1] is the least path, so that pollFirst is --n and new
   // paths (children of the least path) are inserted near the end.
@@ -511,7 +508,7 @@ struct MicroSearch {
       }
     }
     n = 1; iters = 0; totalIters = 0; usedPrefix = 0; maxFrontier = 1; flags = 0;
-    freeMask = T::NSLOTS >= 64 ? ~0ull : ((1ull << T::NSLOTS) - 1ull);
+    freeMask = T::NSLOTS >= 32 ? 0xffffffffu : ((1u << T::NSLOTS) - 1u);
     const int s0 = allocSlot();
     E* p = P(s0);
     for (int i = 0; i < T::W; ++i) p[i] = 0;

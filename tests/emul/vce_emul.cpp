@@ -44,7 +44,7 @@ class EmulBackend : public Backend {
     }
   }
   int microRun(MicroJob& j, const MicroConfig& mc) override {
-    if (j.cls == 0) microRunT<MicroA>(j, mc); else if (j.cls == 1) microRunT<MicroB>(j, mc); else microRunT<MicroC>(j, mc);
+    if (j.cls == 0) microRunT<MicroA>(j, mc); else microRunT<MicroB>(j, mc);
     microRegions += j.n;
     ++stats.launches;
     return 0;
