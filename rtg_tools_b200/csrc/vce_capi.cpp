@@ -59,6 +59,7 @@ Context* acquire(int& rc) {
   vce::EngineOptions opt;
   if (const char* e = std::getenv("VCE_DISABLE_MICRO")) opt.disableMicro = std::atoi(e) != 0;   // diagnostics
   if (const char* e = std::getenv("VCE_CHUNK_REGIONS")) opt.chunkRegions = std::atoi(e);
+  if (const char* e = std::getenv("VCE_SORT_PACKETS")) opt.sortPackets = std::atoi(e) != 0;
   c->engine.reset(new vce::Engine(c->backend.get(), g_pool.get(), opt));
   return c;
 }

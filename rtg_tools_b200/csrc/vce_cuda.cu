@@ -982,7 +982,7 @@ class CudaBackend : public Backend {
   int mNextEvent_ = 0, mNextLane_ = 0;
   cudaEvent_t evM0_ = nullptr, evM1_ = nullptr;
   int microBlocksPerSm_[2] = {1, 1};
-  int microRefill_ = 24;
+  int microRefill_ = 32;
   DevBuf<MicroChunkDesc> mTable_;
   std::string err_;
 };

@@ -68,6 +68,9 @@ struct RowPick {  // selects one orientation row of a variant (host side of K1, 
 }  // namespace
 
 Engine::Engine(Backend* b, WorkerPool* pool, const EngineOptions& o) : be_(b), pool_(pool), opt_(o) {
+  classCount_.resize(pool_->threads());
+  classKeys_.resize(pool_->threads());
+  classOrder_.resize(pool_->threads());
   scratch_ = new std::vector<uint8_t>[pool_->threads()][2];
   scratchOff_ = new std::vector<uint32_t>[pool_->threads()][2];
 }
@@ -557,6 +560,33 @@ int Engine::buildPacket(const PassCtx& pc, int k, int j, uint8_t* out) const {
   return bytes;
 }
 
+// Shape class of a packet: regions of one class take the same branches in the search, so the packets of a chunk are
+// handed to the kernel grouped by class -- the lanes of a warp (32 consecutive packets) then run in lock step.
+static inline uint32_t packetClass(const uint8_t* pk) {
+  const int cC = pk[MP_COUNTS] & 0xf, bC = pk[MP_COUNTS] >> 4;
+  const uint8_t* al = pk + MP_VARS + (cC + bC) * MV_BYTES;
+  uint32_t key = (uint32_t) (cC | (bC << 4));
+  const uint8_t* v = pk + MP_VARS;
+  uint32_t sig[16] = {0};
+  for (int i = 0; i < cC + bC && i < 16; ++i, v += MV_BYTES) {
+    const int a0 = v[MV_A0], a1 = v[MV_A1];
+    const uint32_t l0 = a0 == kMicroNoAllele ? 3u : std::min<uint32_t>(al[a0 * MA_BYTES + MA_LEN], 2u);
+    const uint32_t l1 = a1 == kMicroNoAllele ? 3u : std::min<uint32_t>(al[a1 * MA_BYTES + MA_LEN], 2u);
+    const uint32_t span = std::min<uint32_t>((uint32_t) (v[MV_END] - v[MV_START]), 3u);
+    const uint32_t het = v[MV_GT0] != v[MV_GT1] ? 1u : 0u;
+    const uint32_t ph = v[MV_FLAGS] & 1u;
+    sig[i] = l0 | (l1 << 2) | (span << 4) | (het << 6) | (ph << 7);
+    key = key * 257u + sig[i];
+  }
+  if (cC == 1 && bC == 1) {
+    const uint8_t* vc = pk + MP_VARS;
+    const uint8_t* vb = vc + MV_BYTES;
+    const uint32_t same = (vc[MV_START] == vb[MV_START] && vc[MV_END] == vb[MV_END] && sig[0] == sig[1]) ? 1u : 0u;
+    key = key * 2u + same;
+  }
+  return key & 0x7fffu;
+}
+
 static std::atomic<long long> g_tBuild(0), g_tCopy(0), g_tUpload(0);
 static inline long long nowNs() {
   return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -640,7 +670,29 @@ int Engine::buildChunk(PassCtx& pc, Chunk& ch, int worker, bool launch) {
       return VCE_ERR_CUDA;
     }
     std::memcpy(pk, sc[c].data(), at[c]);
-    std::memcpy(off, so[c].data(), (size_t) np[c] * 4);
+    if (opt_.sortPackets && np[c] > 64) {
+      // counting sort by shape class of the OFFSETS only: the kernel reaches every packet through its offset, so the
+      // packet bytes stay where they were built
+      std::vector<uint32_t>& cnt = classCount_[worker];
+      std::vector<uint32_t>& keys = classKeys_[worker];
+      cnt.assign(0x8000 + 1, 0);
+      keys.resize((size_t) np[c]);
+      for (int q = 0; q < np[c]; ++q) {
+        keys[q] = packetClass(pk + (size_t) so[c][q] * 4);
+        ++cnt[keys[q] + 1];
+      }
+      for (int kx = 0; kx < 0x8000; ++kx) cnt[kx + 1] += cnt[kx];   // first output index of every class
+      std::vector<int32_t>& regs = classOrder_[worker];
+      regs.assign(ch.pktRegion[c].begin(), ch.pktRegion[c].end());
+      uint32_t* offOut = reinterpret_cast<uint32_t*>(off);
+      for (int q = 0; q < np[c]; ++q) {
+        const uint32_t o = cnt[keys[q]]++;
+        offOut[o] = so[c][q];
+        ch.pktRegion[c][o] = regs[q];
+      }
+    } else {
+      std::memcpy(off, so[c].data(), (size_t) np[c] * 4);
+    }
     job.packets = pk;
     job.packetBytes = at[c];
     job.offsets = reinterpret_cast<const uint32_t*>(off);

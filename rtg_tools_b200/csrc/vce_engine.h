@@ -34,6 +34,7 @@ struct EngineOptions {
   bool disableMicro = false;   // tests: no thread-per-region kernel
   int chunkRegions = 0;        // regions per chunk, 0 = automatic
   int splitSegment = 1 << 16;  // variants per segment of the parallel region split
+  bool sortPackets = true;     // hand the packets of a chunk to the kernel grouped by shape class (lock-step lanes)
 };
 
 class Engine {
@@ -176,6 +177,8 @@ class Engine {
   std::vector<std::vector<int32_t>> seqSync_[2];   // [pass][seq] sync points (assembly)
   std::vector<std::vector<uint8_t>> seqDec1_[2];   // [side][seq] pass-2 decision by input index
   std::vector<std::vector<double>> seqW1_;         // [seq] pass-2 call weight by input index
+  std::vector<std::vector<uint32_t>> classCount_, classKeys_;   // per worker: counting sort of packets by shape class
+  std::vector<std::vector<int32_t>> classOrder_;
   std::vector<uint8_t> (*scratch_)[2] = nullptr;     // [worker][class] packet staging
   std::vector<uint32_t> (*scratchOff_)[2] = nullptr;
 };
