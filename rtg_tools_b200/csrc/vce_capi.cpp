@@ -5,6 +5,7 @@
 // Contexts (CUDA backend: streams, device arenas, page-locked staging + engine) are pooled and reused across calls,
 // so that a steady-state vce_submit() pays no allocation; concurrent callers each get their own context and share
 // the host worker pool.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -60,6 +61,7 @@ Context* acquire(int& rc) {
   if (const char* e = std::getenv("VCE_DISABLE_MICRO")) opt.disableMicro = std::atoi(e) != 0;   // diagnostics
   if (const char* e = std::getenv("VCE_CHUNK_REGIONS")) opt.chunkRegions = std::atoi(e);
   if (const char* e = std::getenv("VCE_SORT_PACKETS")) opt.sortPackets = std::atoi(e) != 0;
+  if (const char* e = std::getenv("VCE_SPLIT_GAP")) opt.gap = std::max(1, std::atoi(e));
   c->engine.reset(new vce::Engine(c->backend.get(), g_pool.get(), opt));
   return c;
 }

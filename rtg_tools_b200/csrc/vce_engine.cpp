@@ -723,7 +723,22 @@ void Engine::decodeJob(PassCtx& pc, int k, const MicroJob& job, const std::vecto
     const int j = pktRegion[q];
     RegRes& s = rs[j];
     it += rec[MR_ITERS] | (rec[MR_ITERS + 1] << 8);
-    if (rec[MR_STATUS] != kMicroClean) { s.state = RS_RESIDUAL; continue; }
+    if (rec[MR_STATUS] != kMicroClean) {
+      s.state = RS_RESIDUAL;
+      if (std::getenv("VCE_DEBUG_FALLBACK") && rr[j].cCount + rr[j].bCount == 1) {
+        static std::atomic<int> shown(0);
+        if (shown.fetch_add(1) < 6) {
+          const RegRange& g = rr[j];
+          const int side = g.cCount ? 0 : 1;
+          const int v = side == 0 ? g.cFirst : g.bFirst;
+          const int nxC = g.cFirst + g.cCount < pc.ss[0][k].first + pc.ss[0][k].n ? pc.vStart[0][g.cFirst + g.cCount] : -1;
+          const int nxB = g.bFirst + g.bCount < pc.ss[1][k].first + pc.ss[1][k].n ? pc.vStart[1][g.bFirst + g.bCount] : -1;
+          std::fprintf(stderr, "[vce] single-variant fallback: seq %d region %d side %d start %d end %d nextC %d nextB %d iters %d maxF %d\n", k, j, side,
+                       pc.vStart[side][v], pc.vEnd[side][v], nxC, nxB, rec[MR_ITERS] | (rec[MR_ITERS + 1] << 8), rec[MR_MAXF]);
+        }
+      }
+      continue;
+    }
     const RegRange& g = rr[j];
     s.state = RS_MICRO_DONE;
     s.flags = rec[MR_FLAGS] & 1;
@@ -932,8 +947,8 @@ int Engine::startTier(const PassCtx& pc, const RegRange& g) const {
   if (opt_.forceGeneral || pc.H > 2) return kTierGeneral;
   // the frontier grows with the variants on one side (orientations multiply): pick the tier that will hold it
   const int m = std::max(g.cCount, g.bCount);
-  if (m <= 4) return 0;
-  if (m == 5) return 1;
+  if (m <= 3) return 0;
+  if (m == 4) return 1;
   if (m <= fastShape(2).kv) return 2;
   return kTierGeneral;
 }
@@ -1135,6 +1150,13 @@ int Engine::wideFinish(PassCtx& pc, WideBatch& wb, std::vector<int>& statusOut) 
   std::vector<WarnRec> warns;
   if ((rc = be_->searchFinish(out, warns))) { err_ = be_->lastError(); return rc; }
   if (tmw.on) {
+    std::unordered_map<int, int> shapes;
+    for (size_t q = 0; q < ids.size(); ++q) ++shapes[wb.descs[q].cCount * 100 + wb.descs[q].bCount + 10000 * wb.tier[q]];
+    std::vector<std::pair<int, int>> sh(shapes.begin(), shapes.end());
+    std::sort(sh.begin(), sh.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.second > b.second; });
+    std::fprintf(stderr, "[vce]   shapes (tier: calls x baseline = regions):");
+    for (size_t i = 0; i < sh.size() && i < 10; ++i) std::fprintf(stderr, " %d:%dx%d=%d", sh[i].first / 10000, (sh[i].first % 10000) / 100, sh[i].first % 100, sh[i].second);
+    std::fprintf(stderr, "\n");
     for (int t = 0; t <= kTierGeneral; ++t) {
       long long it = 0, nv = 0;
       int maxIt = 0, maxF = 0;

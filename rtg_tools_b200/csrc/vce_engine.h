@@ -27,7 +27,8 @@
 namespace vce {
 
 struct EngineOptions {
-  int gap = 1;            // split when next.start >= maxEnd + gap (gap >= 1)
+  int gap = 4;            // split when next.start >= maxEnd + gap (any gap >= 1 is exact); a few bases
+                          // keep an indel and its shifted re-representation in one region instead of a SPILL + merge
   int margin = 24;        // reference bases beyond the last variant end of a region (warp-per-region kernels)
   int microMargin = 12;   // same, thread-per-region kernel
   bool forceGeneral = false;   // tests: every region through the large-capacity kernel

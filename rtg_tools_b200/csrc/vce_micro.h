@@ -105,7 +105,7 @@ struct MicroTraits {
 };
 
 typedef MicroTraits<1, 0, 3, 10> MicroA;   // one variant per side
-typedef MicroTraits<4, 3, 6, 20> MicroB;   // up to four variants per side
+typedef MicroTraits<4, 3, 6, 28> MicroB;   // up to four variants per side
 
 template <class T>
 struct MicroSearch {

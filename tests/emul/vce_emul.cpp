@@ -215,7 +215,7 @@ class EmulBackend : public Backend {
   std::string err_;
 };
 
-int g_gap = 1, g_margin = 24, g_forceGeneral = 0, g_disableMicro = 0, g_threads = 3, g_chunk = 0, g_split = 1 << 16;
+int g_gap = 0 /* 0 = the product default */, g_margin = 24, g_forceGeneral = 0, g_disableMicro = 0, g_threads = 3, g_chunk = 0, g_split = 1 << 16;
 int64_t g_stats[8];
 }  // namespace
 
@@ -233,7 +233,7 @@ int emul_vce_submit(const vce_config* cfg, int32_t n_seq, const vce_sequence* se
   be.forceGeneral = g_forceGeneral != 0;
   WorkerPool pool(g_threads);
   EngineOptions opt;
-  opt.gap = g_gap;
+  if (g_gap > 0) opt.gap = g_gap;
   opt.margin = g_margin;
   opt.forceGeneral = g_forceGeneral != 0;
   opt.disableMicro = g_disableMicro != 0;
@@ -255,7 +255,7 @@ int emul_vce_job(const vce_config* cfg, int32_t n_seq, const vce_sequence* seqs,
   EmulBackend be;
   WorkerPool pool(g_threads);
   EngineOptions opt;
-  opt.gap = g_gap;
+  if (g_gap > 0) opt.gap = g_gap;
   opt.margin = g_margin;
   opt.chunkRegions = g_chunk;
   opt.splitSegment = g_split;

@@ -48,7 +48,7 @@ def test_every_split_gap_and_margin_is_exact(emul, oracle):
             emul.lib.emul_set_options(gap, margin, 0)
             compare_results(want, emul.submit(CONFIGS["twopass"], seqs), seqs, what="gap %d margin %d" % (gap, margin))
     finally:
-        emul.lib.emul_set_options(1, 24, 0)
+        emul.lib.emul_set_options(0, 24, 0)
 
 
 def test_large_capacity_path_is_exact(emul, oracle):
@@ -59,7 +59,7 @@ def test_large_capacity_path_is_exact(emul, oracle):
             seqs = fuzz_batch(5000 + seed)
             compare_results(oracle.submit(CONFIGS["twopass"], seqs), emul.submit(CONFIGS["twopass"], seqs), seqs)
     finally:
-        emul.lib.emul_set_options(1, 24, 0)
+        emul.lib.emul_set_options(0, 24, 0)
 
 
 def test_synthetic_genome_pair(emul, oracle):
