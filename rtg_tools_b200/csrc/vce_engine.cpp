@@ -844,7 +844,8 @@ int Engine::runChunks(PassCtx& pc) {
       const int n = (int) rr.size();
       for (int j = 0; j < n; ++j) {
         const RegRange& g = rr[j];
-        const bool shape = g.cCount > MicroB::KV || g.bCount > MicroB::KV || j == 0 || j == n - 1;
+        // four or more variants on one side mostly outgrow the packet kernel's frontier: start them in the warp tiers
+        const bool shape = g.cCount >= MicroB::KV || g.bCount >= MicroB::KV || j == 0 || j == n - 1;
         if (shape || !pc.microOk) {
           per[k].push_back(std::make_pair(RegKey{k, j}, startTier(pc, g)));
           pc.rcls[k][j] = kClsEarly;
