@@ -165,6 +165,9 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--total-bp", type=float, default=None, help="override the genome size of the workload (testing)")
+    ap.add_argument("--config", default="default", choices=["default", "squash", "twopass"],
+                    help="engine configuration: default (diploid, single pass), squash (--squash-ploidy), twopass (ga4gh / annotate)")
+    ap.add_argument("--roc-calls", type=int, default=0, help="also time K4 alone on this many synthetic scored calls (BASELINE configs[4])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roc", action="store_true")
     args = ap.parse_args()
@@ -203,7 +206,9 @@ def main():
     log("[rank %d] workload %s: %d sequences, %d variants (generated in %.1fs)" % (rank, args.workload, len(seqs), nv,
                                                                                time.perf_counter() - t_gen))
     eng = vcfeval.Engine(local_rank)
-    cfg = capi.Config()
+    cfg = {"default": capi.Config(),
+           "squash": capi.Config(n_passes=1, baseline_orientor=(3, 3), calls_orientor=(3, 3), ploidy=(1, 1)),
+           "twopass": capi.Config(n_passes=2)}[args.config]
 
     # ------------------------------------------------------------------ device-resident throughput (value)
     job = eng.job(cfg, seqs)
@@ -342,12 +347,40 @@ def main():
                 assert np.array_equal(x.view(np.int64), y.view(np.int64)), "ROC rows differ from the oracle"
             roc["parity"] = "bit-exact vs oracle"
 
+    roc_heavy = None
+    if args.roc_calls > 0:  # BASELINE configs[4]: QUAL-like scores (40 % distinct at 3 dp), 5 filters, K4 alone
+        rng = np.random.default_rng(5)
+        nr = args.roc_calls
+        score = np.round(rng.uniform(0, 100, nr), 3)
+        dup = rng.random(nr) < 0.6
+        score[dup] = np.round(score[dup], 1)
+        tpw = rng.choice([1.0, 0.5, 1.0 / 3, 2.0 / 3, 2.0, 0.0], nr)
+        fpw = (tpw == 0).astype(np.float64)
+        raww = (tpw > 0).astype(np.float64)
+        mask = rng.integers(1, 32, nr).astype(np.uint32)
+        eng.roc(score, tpw, fpw, raww, mask, 5)
+        t0 = time.perf_counter()
+        rows5, _ = eng.roc(score, tpw, fpw, raww, mask, 5)
+        dt = time.perf_counter() - t0
+        roc_heavy = {"scored_calls": nr, "filters": 5, "e2e_calls_per_s": nr / dt, "ms": dt * 1e3,
+                     "algorithmic_bytes_per_call": ALG_BYTES_PER_ROC_CALL,
+                     "e2e_GBps_algorithmic": ALG_BYTES_PER_ROC_CALL * nr / dt / 1e9}
+        if not args.no_cpu_baseline and world == 1:
+            orc = capi.Library(os.path.join(ROOT, "oracle", "liboracle.so"), prefix="oracle_")
+            t0 = time.perf_counter()
+            want5, _ = orc.roc(score, tpw, fpw, raww, mask, 5)
+            roc_heavy["cpu_calls_per_s"] = nr / (time.perf_counter() - t0)
+            for fa, fb in zip(rows5, want5):
+                for x, y in zip(fa, fb):
+                    assert np.array_equal(x.view(np.int64), y.view(np.int64)), "ROC rows differ from the oracle"
+            roc_heavy["parity"] = "bit-exact vs oracle"
+
     value = total_variants / (ms_per_step * 1e-3)
     out = {
         "metric": "vcfeval variants evaluated/sec", "value": value, "unit": "variants/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": "%s: %s" % (args.workload, desc), "variants_per_step": int(total_variants),
+        "config": {"workload": "%s: %s" % (args.workload, desc), "engine_config": args.config, "variants_per_step": int(total_variants),
                    "sync_regions_per_step": int(total_regions), "sequences_per_rank": len(seqs),
                    "l2": "inputs larger than L2 (per-variant arrays + reference windows > 126 MB)" if nv > 2_000_000 else "inputs smaller than L2 (small workload)",
                    "sharding": "none (1 GPU)" if world == 1 else ("one sample pair per rank" if args.scaling == "weak" else "LPT over chromosomes"),
@@ -361,6 +394,7 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu,
         "roc": roc,
+        "roc_heavy": roc_heavy,
         "summary_counts": [int(x) for x in counts] if counts is not None else None,
         "engine_stats": {k: st[k] for k in ("regions", "escalated", "spilled", "prefix_reruns", "iterations")},
     }
