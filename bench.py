@@ -48,6 +48,16 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# stdout carries exactly ONE line, the result JSON: libraries that print to file descriptor 1 (NCCL prints its version
+# there) are diverted to stderr for the whole run, the JSON line goes to the saved descriptor.
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj):
+    os.write(_RESULT_FD, (json.dumps(obj) + "\n").encode())
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
 
@@ -153,7 +163,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": v, "unit": "variants/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "sync_regions_per_s": regions / dt,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def main():
@@ -398,7 +408,7 @@ def main():
         "summary_counts": [int(x) for x in counts] if counts is not None else None,
         "engine_stats": {k: st[k] for k in ("regions", "escalated", "spilled", "prefix_reruns", "iterations")},
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
