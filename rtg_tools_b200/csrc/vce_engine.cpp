@@ -601,7 +601,14 @@ int Engine::buildChunk(PassCtx& pc, Chunk& ch, int worker, bool launch) {
   const int nr = listed ? (int) ch.list.size() : ch.r1 - ch.r0;
   std::vector<uint8_t>* sc = scratch_[worker];
   std::vector<uint32_t>* so = scratchOff_[worker];
-  sc[0].resize((size_t) nr * MicroA::PKT_MAX + 16);
+  // MicroA packets (the bulk) are built straight into page-locked memory, sized for the worst case; the few MicroB
+  // packets go through a scratch buffer
+  uint8_t* pkA = pc.microOk ? arenaAlloc((size_t) nr * MicroA::PKT_MAX + 16) : nullptr;
+  if (pc.microOk && !pkA) {
+    std::lock_guard<std::mutex> lk(errMu_);
+    err_ = "out of page-locked host memory";
+    return VCE_ERR_CUDA;
+  }
   so[0].resize(nr);
   size_t at[2] = {0, 0};
   int np[2] = {0, 0};
@@ -627,12 +634,30 @@ int Engine::buildChunk(PassCtx& pc, Chunk& ch, int worker, bool launch) {
       const RegRange& f = rrk[j + 12];
       const int32_t pos = f.cCount > 0 ? cs[f.cFirst] : (f.bCount > 0 ? bs[f.bFirst] : 0);
       __builtin_prefetch(tmpl + (pos > 0 ? pos - 1 : 0));
+      // the caller's arrays are two dozen sequential streams, more than the hardware prefetchers follow
+      if ((j & 3) == 0) {
+        for (int side = 0; side < 2; ++side) {
+          const SideSeq& ssd = pc.ss[side][k];
+          if (ssd.idx != nullptr) continue;
+          const vce_variants& in = *ssd.in;
+          const int li = (side == 0 ? f.cFirst : f.bFirst) - ssd.first + 8;
+          if (li + 1 >= ssd.n) continue;
+          const int sl = in.allele_off[li];
+          __builtin_prefetch(in.allele_off + li + 16);
+          __builtin_prefetch(in.allele_start + sl + 16);
+          __builtin_prefetch(in.allele_end + sl + 16);
+          __builtin_prefetch(in.allele_nt_off + sl + 16);
+          __builtin_prefetch(in.allele_null + sl + 64);
+          __builtin_prefetch(in.gt + (size_t) (li + 32) * in.gt_ploidy);
+          __builtin_prefetch(in.nt + in.allele_nt_off[sl] + 64);
+        }
+      }
     }
     int bytes = 0, c = 0;
     if (pc.microOk) {
       const RegRange& g = rrk[j];
       if (g.cCount <= MicroA::KV && g.bCount <= MicroA::KV) {
-        bytes = buildPacket<MicroA>(pc, k, j, sc[0].data() + at[0]);
+        bytes = buildPacket<MicroA>(pc, k, j, pkA + at[0]);
       } else if (g.cCount <= MicroB::KV && g.bCount <= MicroB::KV) {
         c = 1;
         if (sc[1].size() < at[1] + MicroB::PKT_MAX + 16) sc[1].resize(std::max(sc[1].size() * 2, at[1] + (size_t) 64 * MicroB::PKT_MAX));
@@ -661,7 +686,7 @@ int Engine::buildChunk(PassCtx& pc, Chunk& ch, int worker, bool launch) {
     job.n = np[c];
     job.resBytes = c == 0 ? MicroA::RES_BYTES : MicroB::RES_BYTES;
     if (np[c] == 0) continue;
-    uint8_t* pk = arenaAlloc(at[c] + 16);
+    uint8_t* pk = c == 0 ? pkA : arenaAlloc(at[c] + 16);
     uint8_t* off = arenaAlloc((size_t) np[c] * 4);
     uint8_t* res = arenaAlloc((size_t) np[c] * job.resBytes);
     if (!pk || !off || !res) {
@@ -669,7 +694,7 @@ int Engine::buildChunk(PassCtx& pc, Chunk& ch, int worker, bool launch) {
       err_ = "out of page-locked host memory";
       return VCE_ERR_CUDA;
     }
-    std::memcpy(pk, sc[c].data(), at[c]);
+    if (c != 0) std::memcpy(pk, sc[c].data(), at[c]);
     if (opt_.sortPackets && np[c] > 64) {
       // counting sort by shape class of the OFFSETS only: the kernel reaches every packet through its offset, so the
       // packet bytes stay where they were built
