@@ -778,8 +778,60 @@ void Engine::decodeJob(PassCtx& pc, int k, const MicroJob& job, const std::vecto
       wt[g.cFirst + i] = dec[i] >= 2 ? (double) wn[i] / (double) wd[i] : 0.0;  // Path.java:450
     }
     for (int i = 0; i < g.bCount; ++i) db[g.bFirst + i] = dec[T::KV + i];
+    if (liveResults_ != nullptr) assembleRegionEarly(pc, k, j);
   }
   iterations += it;
+}
+
+static inline void pickRow(int kind, int H, int gtPloidy, const vce_variants& in, int ii, int row, int8_t* ids, uint8_t* original);
+
+// Single-pass runs through vce_submit: the per-variant outputs of a region the packet kernel settled are final as
+// soon as its record is decoded (unless the region is later absorbed by a spilling neighbour or re-run for a prefix
+// tie-break: settle() clears the marks then).  Writing them here, while the GPU is still busy with the warp-per-region
+// batch, takes the bulk of the assembly off the critical path.  Same rules as assembleBlock().
+void Engine::assembleRegionEarly(PassCtx& pc, int k, int j) {
+  const RegRange& g = pc.rr[k][j];
+  const RegRes& rsj = pc.rs[k][j];
+  const int base = regionStartPos(pc, k, j);
+  vce_sequence_result& res = liveResults_[k];
+  const vce_sequence& sq = seqs_[k];
+  const int first[2] = {g.cFirst, g.bFirst}, count[2] = {g.cCount, g.bCount};
+  for (int side = 0; side < 2; ++side) {
+    vce_side_result& o = side == 0 ? res.calls : res.baseline;
+    const vce_variants& in = side == 0 ? sq.calls : sq.baseline;
+    const SideSeq& a = pc.ss[side][k];
+    for (int v = first[side]; v < first[side] + count[side]; ++v) {
+      const int li = v - a.first;
+      const int ii = a.idx ? a.idx[li] : li;
+      int st = in.status_in ? in.status_in[ii] : 0;
+      const int d0 = pc.decision[side][v];
+      int8_t* ids = o.allele_ids + (size_t) ii * VCE_MAX_PLOIDY;
+      double wgt = 0.0;
+      if (d0 >= 2) {
+        st |= VCE_STATUS_GT_MATCH;
+        pickRow(pc.kind[side], pc.H, pc.gtPloidy[side], in, ii, d0 - 2, ids, &o.original[ii]);
+        wgt = side == 0 ? pc.weight[v] : 0.0;
+      } else {
+        st |= d0 == 1 ? VCE_STATUS_NO_MATCH : VCE_STATUS_SKIPPED;
+        ids[0] = ids[1] = ids[2] = ids[3] = -2;
+        o.original[ii] = 0;
+      }
+      o.status[ii] = (uint8_t) st;
+      o.weight[ii] = wgt;
+      if (o.sync_id) {
+        // floorSyncPos over the region's own sync points: the first one stands right before the region's first variant
+        int val = 0;
+        if (!(st & VCE_STATUS_SKIPPED)) {
+          const int vv = pc.vStart[side][v] - 1;
+          int fl = base + rsj.rel[0];
+          for (int q = 1; q < rsj.nSync && base + rsj.rel[q] <= vv; ++q) fl = base + rsj.rel[q];
+          val = fl + 2;
+        }
+        o.sync_id[ii] = val;
+      }
+      earlyDone_[side][v] = 1;
+    }
+  }
 }
 
 void Engine::decodeChunk(PassCtx& pc, Chunk& ch, int64_t& iterations) {
@@ -890,6 +942,20 @@ int Engine::execute() {
   StageTimer tm;
   microMs = 0;
   microRegions = microVariants = 0;
+  earlyUsed_ = liveResults_ != nullptr;
+  if (earlyUsed_) {
+    for (int side = 0; side < 2; ++side) {
+      ensureSize(earlyDone_[side], pass_[0].vStart[side].size());
+      // cleared in parallel below, per chunk of variants
+    }
+    const size_t blockE = (size_t) 1 << 20;
+    for (int side = 0; side < 2; ++side) {
+      const size_t nE = pass_[0].vStart[side].size();
+      pool_->parallelFor((int) ((nE + blockE - 1) / blockE), [&](int t, int) {
+        std::memset(earlyDone_[side].data() + (size_t) t * blockE, 0, std::min(blockE, nE - (size_t) t * blockE));
+      });
+    }
+  }
   for (int p = 0; p < cfg_.n_passes; ++p) {
     PassCtx& pc = pass_[p];
     const bool rerun = p == 0 && staged_;
@@ -960,7 +1026,10 @@ int Engine::execute() {
 int Engine::run(const vce_config& cfg, int32_t nSeq, const vce_sequence* seqs, vce_sequence_result* results) {
   int rc = prepare(cfg, nSeq, seqs, false);
   if (rc) return rc;
-  if ((rc = execute())) return rc;
+  liveResults_ = cfg.n_passes == 1 ? results : nullptr;
+  rc = execute();
+  liveResults_ = nullptr;
+  if (rc) return rc;
   return finish(results);
 }
 
@@ -1285,6 +1354,12 @@ int Engine::settle(PassCtx& pc, WideBatch& early) {
     while (nx < n && pc.rs[k][nx].state == RS_DEAD) ++nx;
     return nx;
   };
+  auto unmark = [&](int k, int j) {  // the region's early-assembled outputs are no longer final
+    if (!earlyUsed_ || pc.pass != 0) return;
+    const RegRange& g = pc.rr[k][j];
+    for (int v = g.cFirst; v < g.cFirst + g.cCount; ++v) earlyDone_[0][v] = 0;
+    for (int v = g.bFirst; v < g.bFirst + g.bCount; ++v) earlyDone_[1][v] = 0;
+  };
   std::vector<RegKey> retry;  // merged regions: their new shape may fit the thread-per-region kernel
   std::vector<std::pair<RegKey, int>> all;  // (region, status) to inspect
   {
@@ -1350,6 +1425,7 @@ int Engine::settle(PassCtx& pc, WideBatch& early) {
         Rare& ra = pc.rare[key(k, fix[k])];
         ra.hasPrefix = true;
         ra.assumedPrefix = fixPrefix[k];
+        unmark(k, fix[k]);
         int tier = startTier(pc, pc.rr[k][fix[k]]);
         if (s.state == RS_WIDE_DONE) tier = std::max(tier, (int) (s.flags >> 2) & 3);  // the tier that settled it before
         todo.push_back(std::make_pair(RegKey{k, fix[k]}, tier));
@@ -1402,6 +1478,7 @@ int Engine::settle(PassCtx& pc, WideBatch& early) {
             const RegRange& og = pc.rr[k][nx];
             const auto oit = pc.rare.find(key(k, nx));
             more = o.state == RS_RESIDUAL && oit != pc.rare.end() && oit->second.lastStatus == kRegionSpill;
+            unmark(k, nx);
             g.cCount += og.cCount;
             g.bCount += og.bCount;
             o.state = RS_DEAD;
@@ -1675,8 +1752,10 @@ void Engine::assembleBlock(int k, int side, int lo, int hi, vce_sequence_result&
     while (cur + 1 < sp.size() && sp[cur + 1] <= vv) ++cur;
     return sp[cur] + 1;
   };
+  const uint8_t* early = earlyUsed_ ? earlyDone_[side].data() : nullptr;
   for (int li = lo; li < hi; ++li) {
     const int v = a.first + li;
+    if (early != nullptr && early[v]) continue;  // written while the region's record was decoded
     const int ii = a.idx ? a.idx[li] : li;
     int st = in.status_in ? in.status_in[ii] : 0;
     const int d0 = p0.decision[side][v];

@@ -132,6 +132,7 @@ class Engine {
   int buildChunk(PassCtx& pc, Chunk& ch, int worker, bool launch);
   int runChunks(PassCtx& pc);
   void decodeChunk(PassCtx& pc, Chunk& ch, int64_t& iterations);
+  void assembleRegionEarly(PassCtx& pc, int k, int j);
   template <class T> void decodeJob(PassCtx& pc, int k, const MicroJob& job, const std::vector<int32_t>& pktRegion, int64_t& iterations);
   struct WideBatch {           // one batch of regions in the warp-per-region kernels
     std::vector<RegKey> ids;   // grouped by tier
@@ -165,6 +166,9 @@ class Engine {
   int32_t nSeq_ = 0;
   const vce_sequence* seqs_ = nullptr;
   PassCtx pass_[2];
+  vce_sequence_result* liveResults_ = nullptr;   // vce_submit, single pass: outputs are written as records are decoded
+  bool earlyUsed_ = false;
+  std::vector<uint8_t> earlyDone_[2];            // [side][variant of pass 0] outputs already written
   bool executed_ = false;
   bool staged_ = false;
   std::string err_;
