@@ -603,7 +603,11 @@ int Engine::buildChunk(PassCtx& pc, Chunk& ch, int worker, bool launch) {
   std::vector<uint32_t>* so = scratchOff_[worker];
   // MicroA packets (the bulk) are built straight into page-locked memory, sized for the worst case; the few MicroB
   // packets go through a scratch buffer
-  uint8_t* pkA = pc.microOk ? arenaAlloc((size_t) nr * MicroA::PKT_MAX + 16) : nullptr;
+  static const bool directPinned = std::getenv("VCE_DIRECT_PINNED") ? std::atoi(std::getenv("VCE_DIRECT_PINNED")) != 0 : true;
+  static const bool inputPrefetch = std::getenv("VCE_PREFETCH") ? std::atoi(std::getenv("VCE_PREFETCH")) != 0 : true;
+  uint8_t* pkA = nullptr;
+  if (pc.microOk && directPinned) pkA = arenaAlloc((size_t) nr * MicroA::PKT_MAX + 16);
+  else if (pc.microOk) { sc[0].resize((size_t) nr * MicroA::PKT_MAX + 16); pkA = sc[0].data(); }
   if (pc.microOk && !pkA) {
     std::lock_guard<std::mutex> lk(errMu_);
     err_ = "out of page-locked host memory";
@@ -635,7 +639,7 @@ int Engine::buildChunk(PassCtx& pc, Chunk& ch, int worker, bool launch) {
       const int32_t pos = f.cCount > 0 ? cs[f.cFirst] : (f.bCount > 0 ? bs[f.bFirst] : 0);
       __builtin_prefetch(tmpl + (pos > 0 ? pos - 1 : 0));
       // the caller's arrays are two dozen sequential streams, more than the hardware prefetchers follow
-      if ((j & 3) == 0) {
+      if (inputPrefetch && (j & 3) == 0) {
         for (int side = 0; side < 2; ++side) {
           const SideSeq& ssd = pc.ss[side][k];
           if (ssd.idx != nullptr) continue;
@@ -686,7 +690,7 @@ int Engine::buildChunk(PassCtx& pc, Chunk& ch, int worker, bool launch) {
     job.n = np[c];
     job.resBytes = c == 0 ? MicroA::RES_BYTES : MicroB::RES_BYTES;
     if (np[c] == 0) continue;
-    uint8_t* pk = c == 0 ? pkA : arenaAlloc(at[c] + 16);
+    uint8_t* pk = (c == 0 && directPinned) ? pkA : arenaAlloc(at[c] + 16);
     uint8_t* off = arenaAlloc((size_t) np[c] * 4);
     uint8_t* res = arenaAlloc((size_t) np[c] * job.resBytes);
     if (!pk || !off || !res) {
@@ -694,7 +698,7 @@ int Engine::buildChunk(PassCtx& pc, Chunk& ch, int worker, bool launch) {
       err_ = "out of page-locked host memory";
       return VCE_ERR_CUDA;
     }
-    if (c != 0) std::memcpy(pk, sc[c].data(), at[c]);
+    if (c != 0 || !directPinned) std::memcpy(pk, sc[c].data(), at[c]);
     if (opt_.sortPackets && np[c] > 64) {
       // counting sort by shape class of the OFFSETS only: the kernel reaches every packet through its offset, so the
       // packet bytes stay where they were built
@@ -1542,10 +1546,15 @@ struct CallIter {
     const int li = i;
     do { ++i; } while (i < n && dec[i] < 2);
     const int ii = idx ? idx[li] : li;
-    int8_t ids[4];
-    uint8_t orig = 0;
-    pickRow(kind, H, gtPloidy, in, ii, dec[li] - 2, ids, &orig);
-    return VSum{start[li], in.phased && in.phased[ii], true, orig != 0};
+    const bool ph = in.phased && in.phased[ii];
+    // OrientedVariant.isOriginal() of the chosen orientation (Orientor.java): only the diploid unphased expansion
+    // (first row) and the phased orientor (as-is) produce "original" orientations
+    bool orig = false;
+    const int row = dec[li] - 2;
+    if (kind == VCE_ORIENT_PHASED && ph) orig = true;
+    else if (kind == VCE_ORIENT_PHASED_INVERT && ph) orig = false;
+    else if (kind == VCE_ORIENT_UNPHASED || kind == VCE_ORIENT_PHASED || kind == VCE_ORIENT_PHASED_INVERT) orig = H == 2 && row == 0;
+    return VSum{start[li], ph, true, orig};
   }
 };
 }  // namespace
