@@ -61,8 +61,8 @@ def test_cuda_dense_clusters(engine, oracle):
 def test_cuda_dense_clusters_default_budget(engine, oracle):
     """BASELINE.json configs[2] at the reference's own budget (50 000 paths / 10^7 iterations): the large-capacity
     kernel must reproduce the too-complex skip, the warning text fields and every surviving assignment."""
-    rng = np.random.default_rng(11)
-    seqs = [synth.dense_cluster_sequence(rng, n_clusters=3, per_side=(12, 16), name="d%d" % i) for i in range(2)]
+    seqs = [synth.dense_cluster_sequence(np.random.default_rng(31), n_clusters=1, per_side=(11, 13), name="d31"),
+            synth.dense_cluster_sequence(np.random.default_rng(17), n_clusters=1, per_side=(12, 14), name="d17")]
     want = oracle.submit(capi.Config(), seqs, threads=2)
     assert any(w["paths"] > 50000 for r in want for w in r.warnings), "stress input should exceed the default budget"
     compare_results(want, engine.submit(capi.Config(), seqs), seqs)

@@ -78,6 +78,14 @@ def test_dense_clusters_hit_the_budget(emul, oracle):
     compare_results(want, emul.submit(cfg, seqs), seqs)
 
 
+def test_dense_cluster_default_budget(emul, oracle):
+    """The reference's own budget (50 000 paths): the too-complex skip and its warning fields through the engine."""
+    seqs = [synth.dense_cluster_sequence(np.random.default_rng(31), n_clusters=1, per_side=(11, 13), name="d31")]
+    want = oracle.submit(capi.Config(), seqs)
+    assert any(w["paths"] > 50000 for w in want[0].warnings)
+    compare_results(want, emul.submit(capi.Config(), seqs), seqs)
+
+
 def test_empty_and_one_sided_sequences(emul, oracle):
     rng = np.random.default_rng(5)
     full = synth.fuzz_sequence(rng, n_base=5, n_calls=5, name="full")
