@@ -278,5 +278,23 @@ int emul_bench_prepare(const vce_config* cfg, int32_t n_seq, const vce_sequence*
   for (int i = 0; i < reps && !rc; ++i) rc = en.prepare(*cfg, n_seq, seqs, true);
   return rc;
 }
+// Unit-test hook: the product's K1 source (vce_orient.h) for one variant, same signature as oracle_orientations.
+int emul_orientations(int32_t kind, int32_t H, int32_t gt_ploidy, const int8_t* gt, int32_t phased, int32_t n_slots,
+                      const uint8_t* slot_null, int8_t* out_ids, uint8_t* out_original, int32_t cap) {
+  VariantGt g;
+  g.gtPloidy = gt_ploidy;
+  for (int h = 0; h < 4; ++h) g.gt[h] = h < gt_ploidy ? gt[h] : -2;
+  g.phased = phased;
+  g.slot0 = 0;
+  g.nSlots = n_slots;
+  g.aNull = slot_null;
+  OrientCount cnt;
+  orientVariant(kind, H, g, cnt);
+  if (cnt.n > cap) return cnt.n;
+  std::vector<int32_t> oSlot((size_t) cnt.n * H + 4);
+  OrientFill f{0, H, 0, n_slots, slot_null, oSlot.data(), out_ids, out_original};
+  orientVariant(kind, H, g, f);
+  return cnt.n;
+}
 int emul_vce_roc(const vce_roc_in*, vce_roc_out*) { return VCE_ERR_UNSUPPORTED; }
 }

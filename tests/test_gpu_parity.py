@@ -141,3 +141,10 @@ def test_cuda_roc_known_answer(engine):
     thr, ctp, cfp, craw = rows[0]
     assert list(thr) == [0.3, 0.2, 0.1]
     assert list(ctp) == [1.0, 2.0, 5.0] and list(cfp) == [0.0, 1.0, 1.0]
+
+
+@pytest.mark.parametrize("name", sorted(__import__("test_unit_vectors").PATH_CASES))
+def test_cuda_pathfinder_known_answers(engine, name):
+    """PathTest.java:173-262 micro-cases (expected include / exclude per variant) through the CUDA engine."""
+    from test_unit_vectors import check_path_case
+    check_path_case(engine, name)
