@@ -148,3 +148,29 @@ def test_cuda_pathfinder_known_answers(engine, name):
     """PathTest.java:173-262 micro-cases (expected include / exclude per variant) through the CUDA engine."""
     from test_unit_vectors import check_path_case
     check_path_case(engine, name)
+
+
+def test_cuda_concurrent_submits(engine, oracle):
+    """vce_submit is re-entrant: the reference calls SequenceEvaluator.run() from several pool workers
+    (VcfEvalTask.java:131-137).  Two host threads submit different batches at the same time."""
+    import threading
+    batches = [synth.make_pair(20_000_000, n_chrom=4, sample_seed=572 + 7 * i, perturb_seed=126 + 7 * i) for i in range(3)]
+    want = [oracle.submit(CONFIGS["twopass"], b, threads=4) for b in batches]
+    got = [None] * len(batches)
+    errs = []
+
+    def work(i):
+        try:
+            for _ in range(3):
+                got[i] = engine.submit(CONFIGS["twopass"], batches[i])
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(len(batches))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    for i, b in enumerate(batches):
+        compare_results(want[i], got[i], b, what="thread %d" % i)
