@@ -421,13 +421,6 @@ int Engine::regionStartPos(const PassCtx& pc, int k, int j) const {
   return first - 1;
 }
 
-bool Engine::fastEligible(const PassCtx& pc, const RegRange& g) const {
-  if (opt_.forceGeneral) return false;
-  if (pc.H > 2) return false;
-  if (g.cCount > FastLimits::kMaxVarPerSide || g.bCount > FastLimits::kMaxVarPerSide) return false;
-  return true;
-}
-
 void Engine::planChunks(PassCtx& pc) {
   pc.chunks.clear();
   size_t total = 0;

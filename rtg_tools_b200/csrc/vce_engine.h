@@ -152,7 +152,6 @@ class Engine {
   int wideFinish(PassCtx& pc, WideBatch& wb, std::vector<int>& statusOut);
   int startEarly(PassCtx& pc, WideBatch& early);
   int startTier(const PassCtx& pc, const RegRange& g) const;
-  bool fastEligible(const PassCtx& pc, const RegRange& g) const;
   int regionStartPos(const PassCtx& pc, int k, int j) const;
   bool assembleHeader(int k, vce_sequence_result& res);
   void assembleBlock(int k, int side, int lo, int hi, vce_sequence_result& res) const;
