@@ -100,18 +100,20 @@ struct SearchParams {
   int wordsPerWarp;      // shared-memory words per warp (whole layout)
   int tabBytes;          // shared memory per warp for the region's tables
   int regionBase;        // index of regs[0] within the batch (warnings carry batch-wide region indices)
-  int useHead;           // large-capacity kernel: keep the expanded path in shared memory
 };
 
 constexpr int kWarnPerRegion = 64;
 constexpr int kFastWarps = 8;
-constexpr int kHeadWords = 768;   // large-capacity kernel: shared-memory record of the path being expanded
+#ifndef VCE_GEN_MINB
+#define VCE_GEN_MINB 3   // resident blocks per SM the large-capacity kernel is compiled for
+#endif
 
 // Copies the region's slices of the variant / orientation / allele tables into shared memory and points the search at
 // them (the pointers are re-based so that the search keeps indexing with the batch-wide indices).  The serial part of
 // the search is a chain of dependent table reads: from HBM each costs ~700 cycles, from shared memory ~30.
 // Returns false (nothing changed) when the slices do not fit `cap` bytes.
-__device__ bool stageTables(RegionSearch<DeviceWarp>& rs, const SideArrays* G, int H, uint8_t* buf, int cap, int lane) {
+template <class RS>
+__device__ bool stageTables(RS& rs, const SideArrays* G, int H, uint8_t* buf, int cap, int lane) {
   const RegionDesc& R = rs.R;
   int need = 0;
   int rows0[2], rowsN[2], nt0[2], ntN[2];
@@ -161,7 +163,7 @@ __device__ bool stageTables(RegionSearch<DeviceWarp>& rs, const SideArrays* G, i
 }
 
 template <bool GENERAL>
-__global__ void __launch_bounds__(kFastWarps * 32) k_search(const __grid_constant__ SearchParams p) {
+__global__ void __launch_bounds__(kFastWarps * 32, GENERAL ? VCE_GEN_MINB : 1) k_search(const __grid_constant__ SearchParams p) {
   extern __shared__ __align__(16) int32_t smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -169,9 +171,9 @@ __global__ void __launch_bounds__(kFastWarps * 32) k_search(const __grid_constan
 
   // per-warp shared memory: [RegionConst | tier layout ...] (fast tiers) or [RegionConst | tables] (general)
   const int kcWords = (int) ((sizeof(RegionConst) + 15) / 16) * 4;
-  int32_t* warpBase = GENERAL ? smem + (size_t) warp * (kcWords + p.tabBytes / 4 + kHeadWords) : smem + (size_t) warp * p.wordsPerWarp;
+  int32_t* warpBase = GENERAL ? smem + (size_t) warp * (kcWords + p.tabBytes / 4) : smem + (size_t) warp * p.wordsPerWarp;
   RegionConst* kc = reinterpret_cast<RegionConst*>(warpBase);
-  RegionSearch<DeviceWarp> rs(kc);
+  RegionSearch<DeviceWarp, GENERAL> rs(kc);
   if (lane == 0) kc->cfg = p.cfg;
   rs.warnOut = p.warnScratch + (size_t) gwarp * kWarnPerRegion;
   rs.warnCap = kWarnPerRegion;
@@ -199,7 +201,6 @@ __global__ void __launch_bounds__(kFastWarps * 32) k_search(const __grid_constan
   } else {
     tabS = reinterpret_cast<uint8_t*>(warpBase + kcWords);
   }
-  int32_t* headS = GENERAL ? reinterpret_cast<int32_t*>(tabS + p.tabBytes) : nullptr;
 
   while (true) {
     int r = 0;
@@ -228,9 +229,7 @@ __global__ void __launch_bounds__(kFastWarps * 32) k_search(const __grid_constan
       if (cap < 1) cap = 1;
       rs.cap = (int) cap;
       rs.nSlots = rs.cap + 1 + p.maxChildren;
-      rs.ordCap = RegionSearch<DeviceWarp>::chunkWords(rs.cap);
-      rs.chunked = true;
-      rs.headBuf = (p.useHead && rs.L.W <= kHeadWords) ? headS : nullptr;
+      rs.ordCap = RegionSearch<DeviceWarp, GENERAL>::chunkWords(rs.cap);
       int32_t* base = p.arena + (size_t) gwarp * p.arenaWordsPerWarp;
       rs.slots = base;
       rs.order = base + (size_t) (rs.nSlots + 2) * rs.L.W;
@@ -418,7 +417,7 @@ class CudaBackend : public Backend {
     CUDA_TRY(cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_));
     maxSmemOptin_ = maxSmem;
     CUDA_TRY(cudaFuncSetAttribute(k_search<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
-    CUDA_TRY(cudaFuncSetAttribute(k_search<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (4096 + 1024 + kHeadWords * 4) * kFastWarps));
+    CUDA_TRY(cudaFuncSetAttribute(k_search<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (4096 + 1024) * kFastWarps));
     CUDA_TRY(cudaFuncSetAttribute(k_micro<MicroA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMicroThreads * MicroA::WS_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(k_micro<MicroB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMicroThreads * MicroB::WS_BYTES));
     for (int i = 0; i < kMicroLanes; ++i) CUDA_TRY(cudaStreamCreateWithPriority(&mStream_[i], cudaStreamNonBlocking, prHigh));
@@ -620,11 +619,12 @@ class CudaBackend : public Backend {
     int blocksT[kTierGeneral + 1] = {0}, threadsT[kTierGeneral + 1] = {0};
     size_t smemT[kTierGeneral + 1] = {0};
     SearchParams spT[kTierGeneral + 1];
+    size_t arenaWords = 0;
     int maxWarps = 0;
     for (int tier = 0; tier <= kTierGeneral; ++tier) {
       const int r0 = tierFirst[tier], r1 = tierFirst[tier + 1];
       if (r1 <= r0) continue;
-      const bool general = tier >= kTierGeneral;
+      const bool general = tier >= kTierMid;
       const size_t nt = (size_t) (r1 - r0);
       SearchParams& sp = spT[tier];
       std::memset(&sp, 0, sizeof(sp));
@@ -635,9 +635,6 @@ class CudaBackend : public Backend {
       sp.H = pd.H;
       sp.maxChildren = 1 + std::max(pd.maxOrient[0], pd.maxOrient[1]);
       sp.regionBase = r0;
-      // experimental (off by default): on the device this showed a non-terminating search on the too-complex fixture
-      // that the 1-lane host instantiation does not reproduce; the arena-only path is the verified one
-      sp.useHead = std::getenv("VCE_HEADBUF") ? 1 : 0;
       int blocks = 0, threads = kFastWarps * 32;
       size_t smemBytes = 0;
       if (!general) {
@@ -673,31 +670,37 @@ class CudaBackend : public Backend {
         long long maxW = 0;
         for (int q = r0; q < r1; ++q) maxW = std::max(maxW, (long long) regs[q].layoutW);
         const long long mc = sp.maxChildren;
-        const long long capFull = (long long) sc.maxPaths + 1 + mc;
+        long long capFull = (long long) sc.maxPaths + 1 + mc;
+        if (tier == kTierMid) capFull = std::min<long long>(capFull, kMidCap);
+        // resident blocks per SM pulling regions from the work queue (registers allow 3 blocks of 8 warps; a 4th
+        // queued block evens out the tail)
+        static const int bps = std::getenv("VCE_GENERAL_BPS") ? std::max(1, std::atoi(std::getenv("VCE_GENERAL_BPS"))) : 4;
         long long words = (capFull + 1 + mc + 2) * maxW + (3 * capFull + 1024) + (capFull + 1 + mc) + 16 + 2 * mc + 64;
-        const long long budgetWords = (long long) (48ull << 30) / 4;  // 48 GB of HBM for search arenas
-        long long warpsWanted = std::min<long long>((long long) nt, (long long) smCount_ * kFastWarps);
+        const long long budgetWords = (long long) (24ull << 30) / 4;  // 24 GB of HBM for search arenas
+        long long warpsWanted = std::min<long long>((long long) nt, (long long) smCount_ * kFastWarps * bps);
+        words = (words + 3) & ~3LL;
         if (words > budgetWords) words = budgetWords;  // a single region larger than the budget runs with reduced capacity
         long long warpsFit = std::max<long long>(1, budgetWords / words);
         long long nw = std::min(warpsWanted, warpsFit);
         blocks = (int) ((nw + kFastWarps - 1) / kFastWarps);
-        const size_t totalWords = (size_t) blocks * kFastWarps * (size_t) words;
-        CUDA_TRY(arena_.ensure(totalWords));
-        sp.arena = arena_.p;
+        words &= ~3LL;   // records stay 16-byte aligned
+        arenaWords = std::max(arenaWords, (size_t) blocks * kFastWarps * (size_t) words);
         sp.arenaWordsPerWarp = words;
         sp.tabBytes = 4096;
         const int kcWords = (int) ((sizeof(RegionConst) + 15) / 16) * 4;
-        smemBytes = ((size_t) sp.tabBytes + (size_t) kcWords * 4 + (size_t) kHeadWords * 4) * kFastWarps;
+        smemBytes = ((size_t) sp.tabBytes + (size_t) kcWords * 4) * kFastWarps;
       }
       blocksT[tier] = blocks; threadsT[tier] = threads; smemT[tier] = smemBytes;
       maxWarps = std::max(maxWarps, blocks * (threads / 32));
     }
     CUDA_TRY(warnScratch_.ensure((size_t) std::max(1, maxWarps) * kWarnPerRegion));
+    if (arenaWords > 0) CUDA_TRY(arena_.ensure(arenaWords));   // shared by the launches below (they run in stream order)
     CUDA_TRY(cudaEventRecord(ev0_, stream_));
     for (int tier = 0; tier <= kTierGeneral; ++tier) {
       if (blocksT[tier] == 0) continue;
       spT[tier].warnScratch = warnScratch_.p;
-      if (tier >= kTierGeneral) k_search<true><<<blocksT[tier], threadsT[tier], smemT[tier], stream_>>>(spT[tier]);
+      spT[tier].arena = arena_.p;
+      if (tier >= kTierMid) k_search<true><<<blocksT[tier], threadsT[tier], smemT[tier], stream_>>>(spT[tier]);
       else k_search<false><<<blocksT[tier], threadsT[tier], smemT[tier], stream_>>>(spT[tier]);
       CUDA_TRY(cudaGetLastError());
       ++stats.launches;

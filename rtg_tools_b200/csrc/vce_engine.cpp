@@ -1036,13 +1036,11 @@ int Engine::run(const vce_config& cfg, int32_t nSeq, const vce_sequence* seqs, v
 // Tier of the warp-per-region kernels a region starts in: small regions in the many-warps tier, regions that will
 // grow a large frontier (many variants on one side) directly in the large shared-memory tier, the rest in HBM arenas.
 int Engine::startTier(const PassCtx& pc, const RegRange& g) const {
-  if (opt_.forceGeneral || pc.H > 2) return kTierGeneral;
+  if (opt_.forceGeneral) return kTierGeneral;
+  if (pc.H > 2) return kTierMid;
   // the frontier grows with the variants on one side (orientations multiply): pick the tier that will hold it
   const int m = std::max(g.cCount, g.bCount);
-  if (m <= 3) return 0;
-  if (m == 4) return 1;
-  if (m <= fastShape(2).kv) return 2;
-  return kTierGeneral;
+  return m <= 3 ? 0 : kTierMid;
 }
 
 // Packs the regions `items` (region, tier) for the warp-per-region kernels and starts them: the variants and alleles of
@@ -1163,7 +1161,7 @@ int Engine::wideStart(PassCtx& pc, const std::vector<std::pair<RegKey, int>>& it
     if (pd.maxOrient[side] + 2 > 255) { err_ = "too many orientations per variant for this engine"; return VCE_ERR_UNSUPPORTED; }
   }
   const int mo = std::max(pd.maxOrient[0], pd.maxOrient[1]);
-  if (1 + mo > FastLimits::kMaxChildren) for (size_t q = 0; q < n; ++q) wb.tier[q] = kTierGeneral;
+  if (1 + mo > FastLimits::kMaxChildren) for (size_t q = 0; q < n; ++q) wb.tier[q] = std::max(wb.tier[q], kTierMid);
   for (int t = 0; t <= kTierGeneral + 1; ++t) wb.tierFirst[t] = 0;
   for (size_t q = 0; q < n; ++q) ++wb.tierFirst[wb.tier[q] + 1];
   for (int t = 1; t <= kTierGeneral + 1; ++t) wb.tierFirst[t] += wb.tierFirst[t - 1];
@@ -1174,7 +1172,7 @@ int Engine::wideStart(PassCtx& pc, const std::vector<std::pair<RegKey, int>>& it
       const int k = wb.ids[q].seq, j = wb.ids[q].j;
       const RegRange& g = pc.rr[k][j];
       RegionDesc& d = wb.descs[q];
-      if (wb.tier[q] >= kTierGeneral) {
+      if (wb.tier[q] >= kTierMid) {
         d.qMax = std::max(1, std::max(d.cCount, d.bCount));
         d.decBits = (mo + 2 <= 15) ? 4 : 8;
         PathLayout PL;
@@ -1452,7 +1450,7 @@ int Engine::settle(PassCtx& pc, WideBatch& early) {
         if (ra.tier >= kTierGeneral) { err_ = "search capacity exceeded in the large-capacity kernel"; return VCE_ERR_CAPACITY; }
         int nt = ra.tier + 1;
         const RegRange& g = pc.rr[k][j];
-        if (nt < kTierGeneral && std::max(g.cCount, g.bCount) > fastShape(nt).kv) nt = kTierGeneral;
+        if (nt < kTierMid && std::max(g.cCount, g.bCount) > fastShape(nt).kv) nt = kTierMid;
         todo.push_back(std::make_pair(all[q].first, nt));
         ++be_->stats.escalated;
       } else if (st == kRegionSpill) {

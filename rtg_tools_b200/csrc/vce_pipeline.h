@@ -124,8 +124,12 @@ class Backend {
   SearchStats stats;
 };
 
-// Fixed capacities of the shared-memory warp-per-region kernel, two tiers: small frontier / many resident warps, and
-// larger frontier + pending-allele queue / fewer resident warps.
+// Warp-per-region tiers.  Tiers 0 / 1: shared-memory kernel with the fixed capacities of fastShape(tier) -- the whole
+// search state of a region sits in shared memory, which bounds the resident warps per SM.  Tier kTierMid: the
+// large-capacity kernel (path records in per-warp HBM arenas, tables in shared memory) with a frontier capacity of
+// kMidCap and several dozen resident warps per SM: past ~50 paths the search is latency bound and resident warps are
+// worth more than shared-memory records.  Tier kTierGeneral: the same kernel at the full PathFinder budget
+// (--max-paths), fewer warps with large arenas.
 struct FastShape {
   int kv;            // variants per side (4-bit decisions in one word per side)
   int q;             // pending alleles per haplotype
@@ -136,13 +140,13 @@ struct FastShape {
   VCE_HD int slots() const { return cap + 1 + maxChildren; }
   VCE_HD int ordCap() const { return 2 * cap; }
 };
-constexpr int kTierGeneral = 4;
+constexpr int kTierMid = 2;
+constexpr int kTierGeneral = 3;
+constexpr int kMidCap = 2048;
 inline FastShape fastShape(int tier) {
   switch (tier) {
-    case 0: return FastShape{8, 2, 8, 24, 7, 1536};      // ~9 KB per warp: many resident warps
-    case 1: return FastShape{8, 8, 12, 48, 7, 2048};     // ~22 KB per warp
-    case 2: return FastShape{16, 8, 20, 112, 7, 4096};   // ~50 KB per warp
-    default: return FastShape{16, 8, 20, 480, 7, 4096};  // ~190 KB: one warp per SM, for the few regions in between
+    case 0: return FastShape{8, 2, 8, 24, 7, 1536};      // ~9 KB per warp
+    default: return FastShape{8, 8, 12, 48, 7, 2048};    // ~22 KB per warp
   }
 }
 struct FastLimits {

@@ -30,7 +30,9 @@ namespace vce {
 // side  : H haps, then [0]=variantIndex(local) [1]=variantEnd [2]=includedVariantEnd [3]=includedCount
 //         [4]=alleleId() of last included   [5..5+DW) = decision nibbles/bytes
 // path  : calls side, baseline side, then [0]=nSync [1]=cSinceSync [2]=bSinceSync [3]=spare [4..4+SMAX) = sync positions
-enum { HP_TPOS = 0, HP_PIA = 1, HP_LASTEND = 2, HP_NEXT = 3, HP_QINFO = 4, HP_Q0 = 5 };
+// the four words every comparison reads come first: one 16-byte load per haplotype (records are 16-byte aligned)
+enum { HP_TPOS = 0, HP_NEXT = 1, HP_PIA = 2, HP_QINFO = 3, HP_LASTEND = 4, HP_Q0 = 5 };
+struct alignas(16) Quad { int32_t x, y, z, w; };
 enum { SD_VARIDX = 0, SD_VAREND = 1, SD_INCLEND = 2, SD_INCLCNT = 3, SD_LASTID = 4, SD_DEC0 = 5 };
 enum { PT_NSYNC = 0, PT_CSINCE = 1, PT_BSINCE = 2, PT_SPARE = 3, PT_SYNC0 = 4 };
 
@@ -42,9 +44,9 @@ struct PathLayout {
     DW = (nVarMaxSide * bits + 31) / 32;
     if (DW < 1) DW = 1;
     SMAX = smax;
-    HW = HP_Q0 + Q;
-    SW = H * HW + SD_DEC0 + DW;
-    W = 2 * SW + PT_SYNC0 + SMAX;
+    HW = (HP_Q0 + Q + 3) & ~3;
+    SW = (H * HW + SD_DEC0 + DW + 3) & ~3;
+    W = (2 * SW + PT_SYNC0 + SMAX + 3) & ~3;
   }
   VCE_HD int hap(int side, int h) const { return side * SW + h * HW; }
   VCE_HD int sideBase(int side) const { return side * SW + H * HW; }
@@ -54,6 +56,14 @@ struct PathLayout {
 struct SearchConfig {
   int maxPaths, maxIterations, pruneNoOps, preference;  // PathFinder.Config
 };
+
+// The search is a chain of dependent, data-dependent steps: unrolled loops only grow the instruction stream, and the
+// kernels are bound by instruction fetch (every resident warp walks a different part of it), so loops stay rolled.
+#if defined(__CUDA_ARCH__)
+#define VCE_NOUNROLL _Pragma("unroll 1")
+#else
+#define VCE_NOUNROLL
+#endif
 
 // ---- warp policies ----------------------------------------------------------------------------------
 #if defined(__CUDACC__)
@@ -99,7 +109,7 @@ struct RegionConst {
   SideArrays S[2];       // 0 = calls, 1 = baseline
 };
 
-template <class WP>
+template <class WP, bool CHUNKED>
 struct RegionSearch {
   WP w;
   RegionConst* K;        // see RegionConst
@@ -118,7 +128,7 @@ struct RegionSearch {
   // Large frontiers (large-capacity kernel): the sorted frontier is a two-level structure inside order[] -- a directory
   // of blocks of up to kBlk slot ids each -- so that an insert moves at most one block (java.util.TreeSet is O(log n);
   // a flat sorted array would move half the frontier per insert).  See the frontier* / chunk* members.
-  bool chunked = false;
+  static constexpr bool chunked = CHUNKED;
   static constexpr int kBlk = 64;          // slot ids per block
   static constexpr int kBlkStride = kBlk + 2;  // [0] = start, [1] = count, then the ids
   int nbMax = 0, nb = 0, dh = 0, nbFree = 0;  // blocks available / in use, directory head offset, free blocks
@@ -146,13 +156,9 @@ struct RegionSearch {
   enum { ACT_ENQUEUE = 1, ACT_STEP_DROP = 2, ACT_STEP_REINSERT = 3, ACT_STEP_FINISH = 4, ACT_BOUNDARY_CLEAN = 5,
          ACT_BOUNDARY_SPILL = 6 };
 
-  // The path being expanded ("head") is worked on many times per iteration: the large-capacity kernel, whose path
-  // records live in HBM, keeps it in a shared-memory record (slot id slotHead()) and writes it back only on re-insert.
-  int32_t* headBuf = nullptr;
-  VCE_HD int32_t* P(int slot) const { return slot == nSlots + 2 ? headBuf : slots + (size_t) slot * L.W; }
+  VCE_HD int32_t* P(int slot) const { return slots + (size_t) slot * L.W; }
   VCE_HD int slotLS() const { return nSlots; }
   VCE_HD int slotBest() const { return nSlots + 1; }
-  VCE_HD int slotHead() const { return nSlots + 2; }
   VCE_HD void flag(int f) {
 #if defined(__CUDA_ARCH__)
     atomicOr(ctl + CTL_FLAGS, f);
@@ -181,6 +187,7 @@ struct RegionSearch {
     const int oa = s.aNtOff[a], ob = s.aNtOff[b];
     x = s.aNtOff[a + 1] - oa; y = s.aNtOff[b + 1] - ob;
     if (x != y) return x < y ? -1 : 1;
+    VCE_NOUNROLL
     for (int i = 0; i < x; ++i) {
       const int p = s.nt[oa + i], q = s.nt[ob + i];
       if (p != q) return q < p ? -1 : 1;
@@ -229,6 +236,7 @@ struct RegionSearch {
         const int ql = qi & 0xffff;
         if (ql > 0) {
           nx = hp[HP_Q0];
+          VCE_NOUNROLL
           for (int i = 1; i < ql; ++i) hp[HP_Q0 + i - 1] = hp[HP_Q0 + i];
           hp[HP_QINFO] = (qi & ~0xffff) | (ql - 1);
         } else {
@@ -253,6 +261,7 @@ struct RegionSearch {
     const int pia = hp[HP_PIA];
     if (pia >= 0 && pia < alLen(side, nx) - 1) return false;
     const int ql = hp[HP_QINFO] & 0xffff;
+    VCE_NOUNROLL
     for (int i = 0; i < ql; ++i) if (alLen(side, hp[HP_Q0 + i]) > 0) return false;
     return true;
   }
@@ -262,16 +271,18 @@ struct RegionSearch {
     hapNext(hp, side);
   }
   VCE_HD int hapCompare(const int32_t* a, const int32_t* b, int side) const {  // :326-365
-    const int d = a[HP_TPOS] - b[HP_TPOS];
+    const Quad A = *reinterpret_cast<const Quad*>(a), B = *reinterpret_cast<const Quad*>(b);  // TPOS, NEXT, PIA, QINFO
+    const int d = A.x - B.x;
     if (d != 0) return d;
-    const int na = a[HP_NEXT], nb = b[HP_NEXT];
+    const int na = A.y, nb = B.y;
     if (na < 0) return nb < 0 ? 0 : -1;
     if (nb < 0) return 1;
     const int c = alleleCompare(side, na, nb);
     if (c != 0) return c;
-    const int v = a[HP_PIA] - b[HP_PIA];
+    const int v = A.z - B.z;
     if (v != 0) return v;
-    const int qa = a[HP_QINFO] & 0xffff, qb = b[HP_QINFO] & 0xffff;
+    const int qa = A.w & 0xffff, qb = B.w & 0xffff;
+    VCE_NOUNROLL
     for (int i = 0; i < qa; ++i) {
       if (i >= qb) return 1;
       const int f = alleleCompare(side, a[HP_Q0 + i], b[HP_Q0 + i]);
@@ -284,6 +295,7 @@ struct RegionSearch {
   // ---------------------------------------------------------------- HalfPath / Path (read side)
   VCE_HD int sidePos(const int32_t* p, int side) const {  // HalfPath.getPosition :256-262
     int m = p[L.hap(side, 0) + HP_TPOS];
+    VCE_NOUNROLL
     for (int h = 1; h < L.H; ++h) { const int t = p[L.hap(side, h) + HP_TPOS]; m = t > m ? t : m; }
     return m;
   }
@@ -291,6 +303,7 @@ struct RegionSearch {
     int minh = 0;
     int minp = p[L.hap(side, 0) + HP_TPOS];
     int maxp = minp;
+    VCE_NOUNROLL
     for (int h = 1; h < L.H; ++h) {
       const int t = p[L.hap(side, h) + HP_TPOS];
       if (t < minp) { minp = t; minh = h; }
@@ -299,14 +312,17 @@ struct RegionSearch {
     return minp == maxp ? -1 : minh;
   }
   VCE_HD bool sideOnTemplate(const int32_t* p, int side) const {
+    VCE_NOUNROLL
     for (int h = 0; h < L.H; ++h) if (p[L.hap(side, h) + HP_PIA] >= 0) return false;
     return true;
   }
   VCE_HD bool sideFinished(const int32_t* p, int side) const {
+    VCE_NOUNROLL
     for (int h = 0; h < L.H; ++h) if (!hapFinished(p + L.hap(side, h))) return false;
     return true;
   }
   VCE_HD bool sideWants(const int32_t* p, int side) const {  // HalfPath.wantsFutureVariantBases :176-178
+    VCE_NOUNROLL
     for (int h = 0; h < L.H; ++h) if (hapWants(p + L.hap(side, h), side)) return true;
     return false;
   }
@@ -326,6 +342,7 @@ struct RegionSearch {
     return (b == 0 && c > 0) || (c == 0 && b > 0);
   }
   VCE_HD bool pathMatches(const int32_t* p) {  // Path.matches :346 -> HalfPath.matches :278-286 -> HaplotypePlayback.matches :316
+    VCE_NOUNROLL
     for (int h = 0; h < L.H; ++h) {
       const int32_t* a = p + L.hap(0, h);
       const int32_t* b = p + L.hap(1, h);
@@ -337,7 +354,9 @@ struct RegionSearch {
     return true;
   }
   VCE_HD int pathCompare(const int32_t* a, const int32_t* b) const {  // Path.compareTo :351-357
+    VCE_NOUNROLL
     for (int side = 0; side < 2; ++side) {
+      VCE_NOUNROLL
       for (int h = 0; h < L.H; ++h) {
         const int c = hapCompare(a + L.hap(side, h), b + L.hap(side, h), side);
         if (c != 0) return c;
@@ -404,7 +423,10 @@ struct RegionSearch {
   VCE_HD void copyPath(int dst, int src) {  // cooperative
     int32_t* d = P(dst);
     const int32_t* s = P(src);
-    for (int i = w.lane(); i < L.W; i += WP::L) d[i] = s[i];
+    Quad* d4 = reinterpret_cast<Quad*>(d);
+    const Quad* s4 = reinterpret_cast<const Quad*>(s);
+    VCE_NOUNROLL
+    for (int i = w.lane(); i < (L.W >> 2); i += WP::L) d4[i] = s4[i];
   }
   VCE_HD void pushFree(int slot) {  // lane 0 writes; callers sync before the next pop
     if (w.lane() == 0) freeList[nFree] = slot;
@@ -470,6 +492,7 @@ struct RegionSearch {
   // ---- chunked frontier (see `chunked`)
   VCE_HD void chunkInit(int firstSlot) {  // frontier = { firstSlot } (firstSlot < 0: empty)
     nbMax = (ordCap - 0) / (kBlkStride + 3);
+    VCE_NOUNROLL
     for (int i = w.lane(); i < nbMax; i += WP::L) cfree()[i] = nbMax - 1 - i;  // pop order 0, 1, 2, ...
     w.sync();
     nbFree = nbMax - 1;
@@ -536,6 +559,7 @@ struct RegionSearch {
     const int32_t* B = cblk(cdir()[dh + bi]);
     const int st = B[0], cnt = B[1];
     pos = cnt;
+    VCE_NOUNROLL
     for (int base = 0; base < cnt; base += WP::L) {
       const int i = base + w.lane();
       int cmp = 1;
@@ -548,6 +572,7 @@ struct RegionSearch {
     }
   }
   VCE_HD void chunkShiftUp(int32_t* a, int from, int to) {  // a[from..to) -> a[from+1..to+1), highest chunk first
+    VCE_NOUNROLL
     for (int base = ((to - from - 1) / WP::L) * WP::L; base >= 0 && to > from; base -= WP::L) {
       const int i = from + base + w.lane();
       int v = 0;
@@ -559,6 +584,7 @@ struct RegionSearch {
     }
   }
   VCE_HD void chunkShiftDown(int32_t* a, int from, int to) {  // a[from..to) -> a[from-1..to-1)
+    VCE_NOUNROLL
     for (int base = 0; from + base < to; base += WP::L) {
       const int i = from + base + w.lane();
       int v = 0;
@@ -578,11 +604,13 @@ struct RegionSearch {
       --nbFree;
       int32_t* N = cblk(nbk);
       const int st = B[0], half = kBlk / 2;
+      VCE_NOUNROLL
       for (int i = w.lane(); i < half; i += WP::L) N[2 + i] = B[2 + st + half + i];
       w.sync();
       if (w.lane() == 0) { N[0] = 0; N[1] = half; B[1] = half; }
       // directory: open entry bi + 1
       if (dh + nb >= 2 * nbMax) {  // out of room at the top: compact to the bottom
+        VCE_NOUNROLL
         for (int base = 0; base < nb; base += WP::L) {
           const int i = base + w.lane();
           int v = 0;
@@ -622,6 +650,7 @@ struct RegionSearch {
     return true;
   }
   VCE_HD void chunkShiftDownBy(int32_t* a, int from, int to, int by) {  // a[from..to) -> a[from-by..to-by), by <= from
+    VCE_NOUNROLL
     for (int base = 0; from + base < to; base += WP::L) {
       const int i = from + base + w.lane();
       int v = 0;
@@ -676,6 +705,7 @@ struct RegionSearch {
     if (n >= cap) return false;
     if (oh > 0 && pos <= n - pos) {
       // shift [0, pos) down by one (cheap: new paths land near the front)
+      VCE_NOUNROLL
       for (int base = 0; base < pos; base += WP::L) {
         const int i = base + w.lane();
         int v = 0;
@@ -688,6 +718,7 @@ struct RegionSearch {
       --oh;
     } else {
       if (oh + n >= ordCap) {  // out of room at the top: compact to the bottom
+        VCE_NOUNROLL
         for (int base = 0; base < n; base += WP::L) {
           const int i = base + w.lane();
           int v = 0;
@@ -700,6 +731,7 @@ struct RegionSearch {
         oh = 0;
       }
       // shift [pos, n) up by one, highest chunk first
+      VCE_NOUNROLL
       for (int base = ((n - pos - 1) / WP::L) * WP::L; base >= 0; base -= WP::L) {
         const int i = pos + base + w.lane();
         int v = 0;
@@ -745,7 +777,9 @@ struct RegionSearch {
     return S[side].vStart[sideFirst(side) + nextIdx];
   }
   VCE_HD void pathMoveForward(int32_t* p, int position) {  // Path.moveForward :325-328
+    VCE_NOUNROLL
     for (int side = 0; side < 2; ++side)
+      VCE_NOUNROLL
       for (int h = 0; h < L.H; ++h) hapMoveForward(p + L.hap(side, h), side, position);
   }
   VCE_HD void skipToNextVariant(int32_t* p) {  // :271-282
@@ -764,12 +798,15 @@ struct RegionSearch {
     --varIndex;
     p[L.sideBase(side) + SD_VARIDX] = varIndex;
     const int mv = maxPos < R.tmplLen - 1 ? maxPos : R.tmplLen - 1;
+    VCE_NOUNROLL
     for (int h = 0; h < L.H; ++h) hapMoveForward(p + L.hap(side, h), side, mv);
   }
   VCE_HD void pathStep(int32_t* p) {  // Path.step :330-341
     const int trailing = sideTrailing(p, 0);
     if (trailing == -1) {
+      VCE_NOUNROLL
       for (int side = 0; side < 2; ++side)
+        VCE_NOUNROLL
         for (int h = 0; h < L.H; ++h) hapStep(p + L.hap(side, h), side);
     } else {
       hapStep(p + L.hap(0, trailing), 0);
@@ -778,6 +815,7 @@ struct RegionSearch {
   }
   VCE_HD bool sideIsNew(const int32_t* p, int side, int vGlobal, int row) const {  // HalfPath.isNew :140-151
     if (S[side].vStart[vGlobal] >= p[L.sideBase(side) + SD_INCLEND]) return true;
+    VCE_NOUNROLL
     for (int h = 0; h < L.H; ++h) {
       if (!hapIsNew(p + L.hap(side, h), side, S[side].oSlot[(size_t) row * L.H + h])) return false;
     }
@@ -785,8 +823,11 @@ struct RegionSearch {
   }
 
   VCE_HD void initPath(int32_t* p) {
+    VCE_NOUNROLL
     for (int i = 0; i < L.W; ++i) p[i] = 0;
+    VCE_NOUNROLL
     for (int side = 0; side < 2; ++side) {
+      VCE_NOUNROLL
       for (int h = 0; h < L.H; ++h) {
         int32_t* hp = p + L.hap(side, h);
         hp[HP_TPOS] = R.startPos;
@@ -804,9 +845,11 @@ struct RegionSearch {
     n = 0; iters = 0; curMaxPos = 0; lastSyncPos = 0; bestValid = 0; usedPrefix = 0; nWarn = 0; maxFrontier = 1;
     totalIters = 0;
     nFree = 0;
+    VCE_NOUNROLL
     for (int i = w.lane(); i < nSlots; i += WP::L) freeList[i] = nSlots - 1 - i;  // pop order 0,1,2,...
     nFree = nSlots;
     if (w.lane() == 0) {
+      VCE_NOUNROLL
       for (int i = 0; i < 16; ++i) ctl[i] = 0;
       initPath(P(0));
       if (!chunked) order[0] = 0;
@@ -829,14 +872,6 @@ struct RegionSearch {
         ++oh;  // pollFirst
       }
       --n;
-      if (headBuf != nullptr) {  // move the head into the fast record, release its slot
-        w.sync();
-        copyPath(slotHead(), head);
-        w.sync();
-        pushFree(head);
-        w.sync();
-        head = slotHead();
-      }
       bool headIsLS = false;
       if (n == 0) {  // :151-161 only one path in play
         lastSyncPos = sidePos(P(head), 0);
@@ -848,6 +883,7 @@ struct RegionSearch {
         }
         ++nWarn;
         w.sync();
+        VCE_NOUNROLL
         for (int i = w.lane(); i < nSlots; i += WP::L) freeList[i] = nSlots - 1 - i;
         nFree = nSlots;
         n = 0;
@@ -954,8 +990,10 @@ struct RegionSearch {
         const int nChild = 1 + nOr;
         if (nChild > maxChildren || nChild > nFree) return kRegionOverflow;
         // children: cooperative copy of the parent, then lane k specialises child k
+        VCE_NOUNROLL
         for (int k = 0; k < nChild; ++k) copyPath(freeList[nFree - 1 - k], head);
         w.sync();
+        VCE_NOUNROLL
         for (int k = w.lane(); k < nChild; k += WP::L) {
           const int cs = freeList[nFree - 1 - k];
           int32_t* cp = P(cs);
@@ -975,6 +1013,7 @@ struct RegionSearch {
               sb[SD_INCLCNT] += 1;
               sb[SD_LASTID] = S[side].oIds[(size_t) row * 4];
               setDecision(cp, side, vidx, 1 + k);
+              VCE_NOUNROLL
               for (int h = 0; h < L.H; ++h) hapAdd(cp + L.hap(side, h), side, S[side].oSlot[(size_t) row * L.H + h]);
               cp[L.pathBase() + (side == 0 ? PT_CSINCE : PT_BSINCE)] += 1;
             } else {
@@ -996,8 +1035,9 @@ struct RegionSearch {
         }
         // claim the child slots, release the parent
         nFree -= nChild;
-        if (head != slotHead()) pushFree(head);
+        pushFree(head);
         w.sync();
+        VCE_NOUNROLL
         for (int k = 0; k < nChild; ++k) {
           const int cs = childSlot(k);
           if (childValid(k)) {
@@ -1011,7 +1051,7 @@ struct RegionSearch {
       }
 
       if (act == ACT_STEP_DROP) {
-        if (head != slotHead()) pushFree(head);
+        pushFree(head);
         w.sync();
         continue;
       }
@@ -1020,19 +1060,11 @@ struct RegionSearch {
         if (bestValid) take = !firstIsBetter(P(slotBest()), P(head));
         w.sync();
         if (take) { copyPath(slotBest(), head); bestValid = 1; }
-        if (head != slotHead()) pushFree(head);
+        pushFree(head);
         w.sync();
         continue;
       }
       // ACT_STEP_REINSERT :203
-      if (head == slotHead()) {  // back into a real slot (the one released at the pop is still free)
-        if (nFree <= 0) return kRegionOverflow;
-        const int s2 = freeList[nFree - 1];
-        --nFree;
-        copyPath(s2, head);
-        w.sync();
-        head = s2;
-      }
       if (!addIfBetter(head)) return kRegionOverflow;
     }
     if (R.cNextStart != kNoNext || R.bNextStart != kNoNext) {
@@ -1053,12 +1085,16 @@ struct RegionSearch {
     const int32_t* p = P(slot);
     const int ns = p[L.pathBase() + PT_NSYNC];
     const int32_t* sy = p + L.pathBase() + PT_SYNC0;
+    VCE_NOUNROLL
     for (int i = w.lane(); i < ns; i += WP::L) syncOut[i] = sy[i];
+    VCE_NOUNROLL
     for (int side = 0; side < 2; ++side) {
       const int cnt = sideCount(side), first = sideFirst(side);
+      VCE_NOUNROLL
       for (int i = w.lane(); i < cnt; i += WP::L) S[side].outDecision[first + i] = (uint8_t) getDecision(p, side, i);
     }
     // weights for included calls
+    VCE_NOUNROLL
     for (int i = w.lane(); i < R.cCount; i += WP::L) {
       double wgt = 0.0;
       if (getDecision(p, 0, i) >= 2) {
@@ -1068,12 +1104,14 @@ struct RegionSearch {
         const int lo = k == 0 ? -0x7fffffff : sy[k - 1];  // interval = starts in (lo, hi]
         const int hi = k < ns ? sy[k] : 0x7fffffff;
         int calledTP = 0, baseTP = 0, baseInside = 0;
+        VCE_NOUNROLL
         for (int j = 0; j < R.cCount; ++j) {
           if (getDecision(p, 0, j) >= 2) {
             const int sj = S[0].vStart[R.cFirst + j];
             if (sj > lo && sj <= hi) ++calledTP;
           }
         }
+        VCE_NOUNROLL
         for (int j = 0; j < R.bCount; ++j) {
           if (getDecision(p, 1, j) >= 2) {
             const int sj = S[1].vStart[R.bFirst + j];

@@ -124,14 +124,23 @@ class EmulBackend : public Backend {
   int runTier(PassData& pd, const SearchConfig& sc, const std::vector<RegionDesc>& regs, size_t q0, size_t q1,
               const std::vector<uint8_t>& windows, int tier, std::vector<RegionResult>& out, const std::vector<int32_t>& syncOff,
               size_t syncTotal, std::vector<WarnRec>& warns) {
-    const bool general = tier >= kTierGeneral;
+    const bool general = tier >= kTierMid;
     const FastShape fs = fastShape(general ? 0 : tier);
     ++stats.launches;
     std::vector<int32_t>& syncOut = sync_[pd.pass];
     if (syncOut.size() < syncTotal) syncOut.resize(syncTotal, 0);
     for (size_t q = q0; q < q1; ++q) {
+      if (general || forceGeneral) runRegion<true>(pd, sc, regs, q, windows, tier, general, fs, out, syncOff, warns, syncOut);
+      else runRegion<false>(pd, sc, regs, q, windows, tier, general, fs, out, syncOff, warns, syncOut);
+    }
+    return 0;
+  }
+  template <bool CH>
+  void runRegion(PassData& pd, const SearchConfig& sc, const std::vector<RegionDesc>& regs, size_t q,
+                 const std::vector<uint8_t>& windows, int tier, bool general, const FastShape& fs, std::vector<RegionResult>& out,
+                 const std::vector<int32_t>& syncOff, std::vector<WarnRec>& warns, std::vector<int32_t>& syncOut) {
       RegionConst rk;
-      RegionSearch<HostLane> rs(&rk);
+      RegionSearch<HostLane, CH> rs(&rk);
       rs.R = regs[q];
       rs.cfg = sc;
       for (int side = 0; side < 2; ++side) {
@@ -150,6 +159,7 @@ class EmulBackend : public Backend {
                   regs[q].cCount + regs[q].bCount + 2, regs[q].decBits ? regs[q].decBits : 4);
         rs.maxChildren = 1 + mo;
         rs.cap = sc.maxPaths + 1 + rs.maxChildren;
+        if (tier == kTierMid && !forceGeneral) rs.cap = std::min(rs.cap, kMidCap);
         // grow the arena lazily in the emulation: start small, retry bigger on overflow
       } else {
         rs.L.init(pd.H, fs.q, fs.kv, fs.smax, 4);
@@ -162,12 +172,9 @@ class EmulBackend : public Backend {
       while (true) {
         rs.cap = capTry;
         rs.nSlots = rs.cap + 1 + rs.maxChildren;
-        rs.chunked = general || forceGeneral;
-        rs.ordCap = rs.chunked ? RegionSearch<HostLane>::chunkWords(rs.cap) : 2 * rs.cap + 2;
+        rs.ordCap = rs.chunked ? RegionSearch<HostLane, CH>::chunkWords(rs.cap) : 2 * rs.cap + 2;
         std::vector<int32_t> slots((size_t) (rs.nSlots + 2) * rs.L.W), order(rs.ordCap), freeList(rs.nSlots), ctl(16 + 2 * rs.maxChildren);
         rs.slots = slots.data(); rs.order = order.data(); rs.freeList = freeList.data(); rs.ctl = ctl.data();
-        std::vector<int32_t> headRec((size_t) rs.L.W + 4);
-        rs.headBuf = rs.chunked ? headRec.data() : nullptr;   // the large-capacity path keeps the head in a side record
         std::vector<WarnRec> lw(64);
         rs.warnOut = lw.data(); rs.warnCap = 64; rs.regionId = (int) q;
         int resultSlot = -1;
@@ -187,8 +194,6 @@ class EmulBackend : public Backend {
         break;
       }
       out[q] = rr;
-    }
-    return 0;
   }
   int fetchPass(PassData& pd, std::vector<int32_t>& syncBuf) override {
     std::vector<int32_t>& so = sync_[pd.pass];
