@@ -113,7 +113,7 @@ constexpr int kFastWarps = 8;
 // the search is a chain of dependent table reads: from HBM each costs ~700 cycles, from shared memory ~30.
 // Returns false (nothing changed) when the slices do not fit `cap` bytes.
 template <class RS>
-__device__ bool stageTables(RS& rs, const SideArrays* G, int H, uint8_t* buf, int cap, int lane) {
+__device__ __noinline__ bool stageTables(RS& rs, const SideArrays* G, int H, uint8_t* buf, int cap, int lane) {
   const RegionDesc& R = rs.R;
   int need = 0;
   int rows0[2], rowsN[2], nt0[2], ntN[2];
@@ -145,12 +145,19 @@ __device__ bool stageTables(RS& rs, const SideArrays* G, int H, uint8_t* buf, in
     int8_t* oI = reinterpret_cast<int8_t*>(at); at += rowsN[side] * 4;
     uint8_t* vF = at; at += (cnt + 3) & ~3;
     uint8_t* nt = at; at += (ntN[side] + 3) & ~3;
+    _Pragma("unroll 1")
     for (int i = lane; i < cnt; i += 32) { vS[i] = g.vStart[first + i]; vE[i] = g.vEnd[first + i]; vF[i] = g.vFlags[first + i]; }
+    _Pragma("unroll 1")
     for (int i = lane; i <= cnt; i += 32) oO[i] = cnt > 0 ? g.oOff[first + i] : 0;
+    _Pragma("unroll 1")
     for (int i = lane; i < rowsN[side] * H; i += 32) oS[i] = g.oSlot[(size_t) rows0[side] * H + i];
+    _Pragma("unroll 1")
     for (int i = lane; i < rowsN[side] * 4; i += 32) oI[i] = g.oIds[(size_t) rows0[side] * 4 + i];
+    _Pragma("unroll 1")
     for (int i = lane; i < slN; i += 32) { aS[i] = g.aStart[sl0 + i]; aE[i] = g.aEnd[sl0 + i]; }
+    _Pragma("unroll 1")
     for (int i = lane; i <= slN; i += 32) aN[i] = slN > 0 ? g.aNtOff[sl0 + i] : 0;
+    _Pragma("unroll 1")
     for (int i = lane; i < ntN[side]; i += 32) nt[i] = g.nt[nt0[side] + i];
     if (lane == 0) {
       S.vStart = vS - first; S.vEnd = vE - first; S.vFlags = vF - first; S.oOff = oO - first;

@@ -9,8 +9,12 @@
 
 #if defined(__CUDACC__)
 #define VCE_HD __host__ __device__ __forceinline__
+// out-of-line helpers: ONE copy in the instruction stream (the search kernels are bound by instruction fetch); they are
+// static and take what they need as arguments so that the caller's state can stay in registers
+#define VCE_HDN __host__ __device__ __noinline__
 #else
 #define VCE_HD inline
+#define VCE_HDN inline
 #endif
 
 namespace vce {

@@ -159,11 +159,12 @@ struct RegionSearch {
   VCE_HD int32_t* P(int slot) const { return slots + (size_t) slot * L.W; }
   VCE_HD int slotLS() const { return nSlots; }
   VCE_HD int slotBest() const { return nSlots + 1; }
-  VCE_HD void flag(int f) {
+  VCE_HD void flag(int f) { flagS(ctl, f); }
+  VCE_HD static void flagS(int32_t* ctlp, int f) {
 #if defined(__CUDA_ARCH__)
-    atomicOr(ctl + CTL_FLAGS, f);
+    atomicOr(ctlp + CTL_FLAGS, f);
 #else
-    ctl[CTL_FLAGS] |= f;
+    ctlp[CTL_FLAGS] |= f;
 #endif
   }
 
@@ -177,9 +178,10 @@ struct RegionSearch {
   VCE_HD int alLen(int side, int slot) const { return S[side].aNtOff[slot + 1] - S[side].aNtOff[slot]; }
 
   // Allele.compareTo :95-119 (reversed base comparison)
-  VCE_HD int alleleCompare(int side, int a, int b) const {
+  VCE_HD int alleleCompare(int side, int a, int b) const { return a == b ? 0 : alleleCompareS(S + side, a, b); }
+  VCE_HDN static int alleleCompareS(const SideArrays* sp, int a, int b) {
     if (a == b) return 0;
-    const SideArrays& s = S[side];
+    const SideArrays& s = *sp;
     int x = s.aStart[a], y = s.aStart[b];
     if (x != y) return x < y ? -1 : 1;
     x = s.aEnd[a]; y = s.aEnd[b];
@@ -218,9 +220,10 @@ struct RegionSearch {
     if (hp[HP_PIA] < 0) return tmplBase(hp[HP_TPOS]);
     return S[side].nt[S[side].aNtOff[hp[HP_NEXT]] + hp[HP_PIA]];
   }
-  VCE_HD void hapNext(int32_t* hp, int side) {  // :170-214
+  VCE_HD void hapNext(int32_t* hp, int side) { hapNextS(hp, S + side, ctl); }  // :170-214
+  VCE_HDN static void hapNextS(int32_t* hp, const SideArrays* sp, int32_t* ctlp) {
     int tpos = hp[HP_TPOS], pia = hp[HP_PIA], nx = hp[HP_NEXT];
-    const SideArrays& s = S[side];
+    const SideArrays& s = *sp;
     if (pia < 0) {
       ++tpos;
       if (nx >= 0 && s.aStart[nx] == tpos) pia = 0;
@@ -229,7 +232,7 @@ struct RegionSearch {
     }
     if (nx >= 0) {
       while (true) {
-        if (pia != alLen(side, nx)) break;
+        if (pia != s.aNtOff[nx + 1] - s.aNtOff[nx]) break;
         tpos = s.aEnd[nx];
         pia = -1;
         const int qi = hp[HP_QINFO];
@@ -245,7 +248,7 @@ struct RegionSearch {
         }
         if (tpos < s.aStart[nx]) break;
         pia = 0;
-        if (tpos != s.aStart[nx]) { flag(FL_ERRORDER); break; }
+        if (tpos != s.aStart[nx]) { flagS(ctlp, FL_ERRORDER); break; }
       }
     }
     hp[HP_TPOS] = tpos; hp[HP_PIA] = pia; hp[HP_NEXT] = nx;
@@ -270,14 +273,15 @@ struct RegionSearch {
     hp[HP_TPOS] = position - 1;
     hapNext(hp, side);
   }
-  VCE_HD int hapCompare(const int32_t* a, const int32_t* b, int side) const {  // :326-365
+  VCE_HD int hapCompare(const int32_t* a, const int32_t* b, int side) const { return hapCompareS(a, b, S + side); }
+  VCE_HD static int hapCompareS(const int32_t* a, const int32_t* b, const SideArrays* sp) {  // :326-365
     const Quad A = *reinterpret_cast<const Quad*>(a), B = *reinterpret_cast<const Quad*>(b);  // TPOS, NEXT, PIA, QINFO
     const int d = A.x - B.x;
     if (d != 0) return d;
     const int na = A.y, nb = B.y;
     if (na < 0) return nb < 0 ? 0 : -1;
     if (nb < 0) return 1;
-    const int c = alleleCompare(side, na, nb);
+    const int c = (na == nb ? 0 : alleleCompareS(sp, na, nb));
     if (c != 0) return c;
     const int v = A.z - B.z;
     if (v != 0) return v;
@@ -285,7 +289,7 @@ struct RegionSearch {
     VCE_NOUNROLL
     for (int i = 0; i < qa; ++i) {
       if (i >= qb) return 1;
-      const int f = alleleCompare(side, a[HP_Q0 + i], b[HP_Q0 + i]);
+      const int f = alleleCompareS(sp, a[HP_Q0 + i], b[HP_Q0 + i]);
       if (f != 0) return f;
     }
     if (qb > qa) return -1;
@@ -353,12 +357,14 @@ struct RegionSearch {
     }
     return true;
   }
-  VCE_HD int pathCompare(const int32_t* a, const int32_t* b) const {  // Path.compareTo :351-357
+  VCE_HD int pathCompare(const int32_t* a, const int32_t* b) const { return pathCompareS(a, b, K); }
+  VCE_HDN static int pathCompareS(const int32_t* a, const int32_t* b, const RegionConst* k) {  // Path.compareTo :351-357
+    const PathLayout& pl = k->L;
     VCE_NOUNROLL
     for (int side = 0; side < 2; ++side) {
       VCE_NOUNROLL
-      for (int h = 0; h < L.H; ++h) {
-        const int c = hapCompare(a + L.hap(side, h), b + L.hap(side, h), side);
+      for (int h = 0; h < pl.H; ++h) {
+        const int c = hapCompareS(a + pl.hap(side, h), b + pl.hap(side, h), k->S + side);
         if (c != 0) return c;
       }
     }
