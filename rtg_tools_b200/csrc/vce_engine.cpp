@@ -928,6 +928,7 @@ int Engine::runChunks(PassCtx& pc) {
       }
     });
     pc.earlyItems.clear();
+    pc.earlyBatch = WideBatch();
     for (int k = 0; k < nSeq_; ++k) pc.earlyItems.insert(pc.earlyItems.end(), per[k].begin(), per[k].end());
   }
   planChunks(pc);
@@ -961,7 +962,9 @@ int Engine::execute() {
       tm.lap("pass 2 set-up");
     }
     std::atomic<int> failed(0);
-    WideBatch early;
+    WideBatch localEarly;
+    // a staged job keeps the packed early batch: re-runs start from the same regions
+    WideBatch& early = staged_ && p == 0 ? pc.earlyBatch : localEarly;
     if (!rerun) {
       if ((rc = runChunks(pc))) return rc;
       tm.lap("split into regions");
@@ -982,8 +985,9 @@ int Engine::execute() {
         resetPassRun(pc);
         arenaRewind();
         be_->microRewind();
+        tm.lap("reset for re-run");
       }
-      if ((rc = wideStart(pc, pc.earlyItems, early))) return rc;
+      // the packets are resident: their kernels start first and cover the packing of the warp-per-region batch
       for (int c = 0; c < 2; ++c) {
         std::vector<MicroJob*> jobs;
         for (Chunk& ch : pc.chunks) if (ch.job[c].n > 0) jobs.push_back(&ch.job[c]);
@@ -992,6 +996,10 @@ int Engine::execute() {
           if (r) { err_ = be_->lastError(); return r; }
         }
       }
+      tm.lap("packet kernel launches");
+      if (!early.packed && (rc = widePack(pc, pc.earlyItems, early))) return rc;
+      if ((rc = wideLaunch(early))) return rc;
+      tm.lap("early warp-per-region batch");
     }
     if (failed.load()) return failed.load();
     std::vector<int64_t> iters(pool_->threads(), 0);
@@ -1046,7 +1054,12 @@ int Engine::startTier(const PassCtx& pc, const RegRange& g) const {
 // Packs the regions `items` (region, tier) for the warp-per-region kernels and starts them: the variants and alleles of
 // just these regions go into compact arrays (cost proportional to the residual, not to the batch), K1 expands the
 // orientations on the device, one launch per tier.  Returns without waiting; wideFinish collects.
-int Engine::wideStart(PassCtx& pc, const std::vector<std::pair<RegKey, int>>& itemsIn, WideBatch& wb) {
+int Engine::wideStart(PassCtx& pc, const std::vector<std::pair<RegKey, int>>& items, WideBatch& wb) {
+  const int rc = widePack(pc, items, wb);
+  return rc ? rc : wideLaunch(wb);
+}
+
+int Engine::widePack(PassCtx& pc, const std::vector<std::pair<RegKey, int>>& itemsIn, WideBatch& wb) {
   wb = WideBatch();
   if (itemsIn.empty()) return VCE_OK;
   StageTimer tmw;
@@ -1214,6 +1227,13 @@ int Engine::wideStart(PassCtx& pc, const std::vector<std::pair<RegKey, int>>& it
     }
   });
   tmw.lap("  wide: pack");
+  wb.packed = true;
+  return VCE_OK;
+}
+
+int Engine::wideLaunch(WideBatch& wb) {
+  StageTimer tmw;
+  PassData& pd = wb.pd;
   int rc;
   for (int side = 0; side < 2; ++side) {
     if ((rc = be_->setAlleles(side, wb.at[side]))) { err_ = be_->lastError(); return rc; }

@@ -91,6 +91,21 @@ class Engine {
     int64_t variants = 0, variantsA = 0;
   };
   struct WarnEntry { int32_t seq, j; WarnRec w; };
+  struct WideBatch {           // one batch of regions in the warp-per-region kernels
+    std::vector<RegKey> ids;   // grouped by tier
+    std::vector<int> tier;
+    int tierFirst[kTierGeneral + 2] = {0};
+    PassData pd;
+    AlleleTable at[2];
+    std::vector<RegionDesc> descs;
+    std::vector<int32_t> syncOff;
+    std::vector<uint8_t> windows;
+    size_t so = 0;
+    double searchBefore = 0;
+    bool started = false;
+    bool packed = false;      // host-side image is complete (a staged job packs its early batch once)
+  };
+
   struct PassCtx {
     int pass = 0, H = 2, kind[2] = {0, 0};
     int gtPloidy[2] = {0, 0};
@@ -106,6 +121,7 @@ class Engine {
     std::vector<std::vector<uint8_t>> rcls;      // 0 = warp-per-region path, 1 = MicroA, 2 = MicroB
     std::vector<Chunk> chunks;
     std::vector<std::pair<RegKey, int>> earlyItems;   // (region, tier) started early in the warp-per-region kernels
+    WideBatch earlyBatch;                             // staged jobs: packed once, launched by every execute()
     std::vector<int32_t> wideSync;
     std::vector<WarnEntry> warns;
     std::unordered_map<uint64_t, Rare> rare;
@@ -134,21 +150,10 @@ class Engine {
   void decodeChunk(PassCtx& pc, Chunk& ch, int64_t& iterations);
   void assembleRegionEarly(PassCtx& pc, int k, int j);
   template <class T> void decodeJob(PassCtx& pc, int k, const MicroJob& job, const std::vector<int32_t>& pktRegion, int64_t& iterations);
-  struct WideBatch {           // one batch of regions in the warp-per-region kernels
-    std::vector<RegKey> ids;   // grouped by tier
-    std::vector<int> tier;
-    int tierFirst[kTierGeneral + 2] = {0};
-    PassData pd;
-    AlleleTable at[2];
-    std::vector<RegionDesc> descs;
-    std::vector<int32_t> syncOff;
-    std::vector<uint8_t> windows;
-    size_t so = 0;
-    double searchBefore = 0;
-    bool started = false;
-  };
   int settle(PassCtx& pc, WideBatch& early);
   int wideStart(PassCtx& pc, const std::vector<std::pair<RegKey, int>>& items, WideBatch& wb);
+  int widePack(PassCtx& pc, const std::vector<std::pair<RegKey, int>>& items, WideBatch& wb);
+  int wideLaunch(WideBatch& wb);
   int wideFinish(PassCtx& pc, WideBatch& wb, std::vector<int>& statusOut);
   int startEarly(PassCtx& pc, WideBatch& early);
   int startTier(const PassCtx& pc, const RegRange& g) const;
