@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -428,8 +429,7 @@ class CudaBackend : public Backend {
     CUDA_TRY(cudaFuncSetAttribute(k_micro<MicroA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMicroThreads * MicroA::WS_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(k_micro<MicroB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMicroThreads * MicroB::WS_BYTES));
     for (int i = 0; i < kMicroLanes; ++i) CUDA_TRY(cudaStreamCreateWithPriority(&mStream_[i], cudaStreamNonBlocking, prHigh));
-    CUDA_TRY(cudaEventCreate(&evM0_));
-    CUDA_TRY(cudaEventCreate(&evM1_));
+    for (int i = 0; i < 2; ++i) { CUDA_TRY(cudaEventCreate(&evM0_[i])); CUDA_TRY(cudaEventCreate(&evM1_[i])); }
     {
       int perSm = 0;
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_micro<MicroA>, kMicroThreads, kMicroThreads * MicroA::WS_BYTES));
@@ -448,12 +448,12 @@ class CudaBackend : public Backend {
     sRegs_.release(); sSyncOff_.release(); sWindows_.release();
     regs_.release(); rres_.release(); syncOff_.release(); syncBuf_.release(); windows_.release(); warns_.release();
     warnScratch_.release(); ints_.release(); arena_.release(); scanTmp_.release();
+    mTableC_[0].release(); mTableC_[1].release();
     cudaEventDestroy(ev0_);
     cudaEventDestroy(ev1_);
     cudaEventDestroy(evT0_);
     cudaEventDestroy(evT1_);
-    cudaEventDestroy(evM0_);
-    cudaEventDestroy(evM1_);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(evM0_[i]); cudaEventDestroy(evM1_[i]); }
     for (cudaEvent_t e : mEvents_) cudaEventDestroy(e);
     mEvents_.clear();
     for (int i = 0; i < kMicroLanes; ++i) cudaStreamDestroy(mStream_[i]);
@@ -852,6 +852,7 @@ class CudaBackend : public Backend {
     }
     if (!j.dPackets || !j.dOffsets || !j.dResults) { err_ = "out of device memory for region packets"; return VCE_ERR_CUDA; }
     cudaStream_t st = mStream_[j.lane];
+    uploadsPending_.store(true);
     CUDA_TRY(cudaMemcpyAsync(j.dPackets, j.packets, j.packetBytes, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(j.dOffsets, j.offsets, (size_t) j.n * 4, cudaMemcpyHostToDevice, st));
     return VCE_OK;
@@ -891,7 +892,9 @@ class CudaBackend : public Backend {
     CUDA_TRY(cudaSetDevice(device_));
     if (jobs.empty()) return VCE_OK;
     // every upload has to be complete before the one launch that reads them all
-    for (int i = 0; i < kMicroLanes; ++i) CUDA_TRY(cudaStreamSynchronize(mStream_[i]));
+    if (uploadsPending_.exchange(false)) {
+      for (int i = 0; i < kMicroLanes; ++i) CUDA_TRY(cudaStreamSynchronize(mStream_[i]));
+    }
     std::vector<MicroChunkDesc> table(jobs.size());
     int total = 0;
     for (size_t i = 0; i < jobs.size(); ++i) {
@@ -900,38 +903,51 @@ class CudaBackend : public Backend {
                                 static_cast<uint8_t*>(j.dResults), j.n, total};
       total += j.n;
     }
-    CUDA_TRY(mTable_.ensure(table.size()));
-    cudaStream_t st = mStream_[0];
-    CUDA_TRY(cudaMemcpyAsync(mTable_.p, table.data(), table.size() * sizeof(MicroChunkDesc), cudaMemcpyHostToDevice, st));
+    const int pc = jobs[0]->cls & 1;
+    cudaStream_t st = mStream_[pc];   // the two packet classes run side by side
+    CUDA_TRY(mTableC_[pc].ensure(table.size()));
+    CUDA_TRY(cudaMemcpyAsync(mTableC_[pc].p, table.data(), table.size() * sizeof(MicroChunkDesc), cudaMemcpyHostToDevice, st));
     MicroParams mp;
     std::memset(&mp, 0, sizeof(mp));
     mp.one = table[0];
-    mp.table = mTable_.p;
+    mp.table = mTableC_[pc].p;
     mp.nChunks = (int) table.size();
     mp.total = total;
     mp.refill = microRefill_;
     mp.cfg = mc;
-    CUDA_TRY(cudaEventRecord(evM0_, st));
+    if (microPending_[pc]) microCollect();   // the event pair of this class is still waiting to be read
+    CUDA_TRY(cudaEventRecord(evM0_[pc], st));
     microLaunch(mp, jobs[0]->cls, st);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaEventRecord(evM1_, st));
+    CUDA_TRY(cudaEventRecord(evM1_[pc], st));
+    microPending_[pc] = true;
+    microPendingTotal_[pc] = total;
     for (MicroJob* j : jobs) {
       CUDA_TRY(cudaMemcpyAsync(j->results, j->dResults, (size_t) j->n * j->resBytes, cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(j->evHandle), st));
-      j->lane = 0;
+      j->lane = pc;
       stats.d2hBytes += (int64_t) j->n * j->resBytes;
     }
     ++stats.launches;
-    CUDA_TRY(cudaEventSynchronize(evM1_));
-    float ms = 0;
-    CUDA_TRY(cudaEventElapsedTime(&ms, evM0_, evM1_));
-    stats.searchMs += ms;
-    if (jobs[0]->cls == 0 && total >= lastMicroRegions_ / 2) {  // the main MicroA launch (not the small settle retries)
-      lastMicroMs_ = ms;
-      lastMicroRegions_ = total;
-    }
-    return VCE_OK;
+    return VCE_OK;   // no wait here: the caller decodes job by job (microWait) and reads the device times afterwards
   }
+  // Device times of the launches started by microRunAll (blocks until they have finished).
+  void microCollect() override {
+    cudaSetDevice(device_);
+    for (int pc = 0; pc < 2; ++pc) {
+      if (!microPending_[pc]) continue;
+      microPending_[pc] = false;
+      float ms = 0;
+      if (cudaEventSynchronize(evM1_[pc]) != cudaSuccess || cudaEventElapsedTime(&ms, evM0_[pc], evM1_[pc]) != cudaSuccess) continue;
+      stats.searchMs += ms;
+      if (pc == 0 && microPendingTotal_[pc] >= lastMicroRegions_ / 2) {  // the main MicroA launch (not the small settle retries)
+        lastMicroMs_ = ms;
+        lastMicroRegions_ = microPendingTotal_[pc];
+      }
+    }
+  }
+  bool microPending_[2] = {false, false};
+  long long microPendingTotal_[2] = {0, 0};
   int microWait(MicroJob& j) override {
     CUDA_TRY(cudaSetDevice(device_));
     CUDA_TRY(cudaEventSynchronize(static_cast<cudaEvent_t>(j.evHandle)));
@@ -990,10 +1006,11 @@ class CudaBackend : public Backend {
   cudaStream_t mStream_[kMicroLanes] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> mEvents_;
   int mNextEvent_ = 0, mNextLane_ = 0;
-  cudaEvent_t evM0_ = nullptr, evM1_ = nullptr;
+  cudaEvent_t evM0_[2] = {nullptr, nullptr}, evM1_[2] = {nullptr, nullptr};
   int microBlocksPerSm_[2] = {1, 1};
   int microRefill_ = 32;
-  DevBuf<MicroChunkDesc> mTable_;
+  DevBuf<MicroChunkDesc> mTableC_[2];
+  std::atomic<bool> uploadsPending_{false};
   std::string err_;
 };
 
@@ -1022,6 +1039,7 @@ void cudaBackendFastStats(Backend* b, double* ms, long long* regions, long long*
 
 void cudaBackendMicroStats(Backend* b, double* ms, long long* regions) {
   CudaBackend* c = static_cast<CudaBackend*>(b);
+  c->microCollect();
   *ms = c->lastMicroMs_;
   *regions = c->lastMicroRegions_;
 }

@@ -1014,6 +1014,7 @@ int Engine::execute() {
       decodeChunk(pc, ch, iters[worker]);
     });
     if (failed.load()) { err_ = be_->lastError(); return failed.load(); }
+    be_->microCollect();
     tm.lap("wait + decode");
     for (int64_t v : iters) be_->stats.iterations += v;
     for (const Chunk& ch : pc.chunks) {

@@ -90,6 +90,7 @@ class Backend {
   // one kernel launch over all (uploaded) jobs + one async result copy per job: the staged / HBM-resident path
   virtual int microRunAll(std::vector<MicroJob*>& jobs, const MicroConfig& mc) = 0;
   virtual int microWait(MicroJob& j) = 0;                     // blocks until the results of j are on the host
+  virtual void microCollect() {}                              // reads the device times of finished microRunAll launches
   virtual int setAlleles(int side, const AlleleTable& t) = 0;
   // Host -> device copy of the pass's variant arrays; clears the per-variant outputs.
   virtual int uploadPass(PassData& pd) = 0;
