@@ -446,30 +446,27 @@ void Engine::planChunks(PassCtx& pc) {
 // Writes the packet of region (k, j) in the layout of vce_micro.h; returns its length in bytes (a multiple of 4) or
 // 0 when the region does not fit the thread-per-region kernel.
 template <class T>
-int Engine::buildPacket(const PassCtx& pc, int k, int j, uint8_t* out) const {
+int Engine::buildPacket(const PassCtx& pc, const PacketSrc& ps, int j, uint8_t* out) const {
   if (j == 0) return 0;  // the first path of a sequence starts at -1 and is not in sync (HalfPath.java:50-57)
-  const RegRange& g = pc.rr[k][j];
+  const RegRange& g = ps.rr[j];
   if (g.cCount > T::KV || g.bCount > T::KV) return 0;
-  const SideSeq* SS[2] = {&pc.ss[0][k], &pc.ss[1][k]};
   const int first[2] = {g.cFirst, g.bFirst};
   const int count[2] = {g.cCount, g.bCount};
   int nextStart[2];
-  for (int side = 0; side < 2; ++side) {
-    const int e = first[side] + count[side];
-    nextStart[side] = e < SS[side]->first + SS[side]->n ? pc.vStart[side][e] : kNoNext;
-  }
-  if (nextStart[0] == kNoNext && nextStart[1] == kNoNext) return 0;  // the last region finishes at the template end
   int firstStart = INT_MAX;
   long maxEnd = LONG_MIN;
   for (int side = 0; side < 2; ++side) {
-    for (int v = first[side]; v < first[side] + count[side]; ++v) {
-      firstStart = std::min(firstStart, pc.vStart[side][v]);
-      maxEnd = std::max(maxEnd, (long) pc.vEnd[side][v]);
+    const int e = first[side] + count[side];
+    nextStart[side] = e < ps.sideEnd[side] ? ps.vStart[side][e] : kNoNext;
+    for (int v = first[side]; v < e; ++v) {
+      firstStart = std::min(firstStart, ps.vStart[side][v]);
+      maxEnd = std::max(maxEnd, (long) ps.vEnd[side][v]);
     }
   }
+  if (nextStart[0] == kNoNext && nextStart[1] == kNoNext) return 0;  // the last region finishes at the template end
   if (firstStart == INT_MAX || firstStart < 1 || maxEnd < firstStart) return 0;
   const int winStart = firstStart - 1;
-  const int tl = seqs_[k].template_len;
+  const int tl = ps.tl;
   const long winEnd = std::min<long>(maxEnd + opt_.microMargin, tl);
   const long winLen = winEnd - winStart;
   if (winLen < 1 || winLen > kMicroMaxWin) return 0;
@@ -480,7 +477,7 @@ int Engine::buildPacket(const PassCtx& pc, int k, int j, uint8_t* out) const {
   int nAl = 0;
   uint8_t* vout = out + MP_VARS;
   for (int side = 0; side < 2; ++side) {
-    const SideSeq& s = *SS[side];
+    const SideSeq& s = *ps.ss[side];
     const vce_variants& in = *s.in;
     const int P = in.gt_ploidy;
     if (P != pc.gtPloidy[side]) return 0;
@@ -509,7 +506,7 @@ int Engine::buildPacket(const PassCtx& pc, int k, int j, uint8_t* out) const {
         nBases += len;
         al[h] = nAl++;
       }
-      const long vs = (long) pc.vStart[side][v] - winStart, ve = (long) pc.vEnd[side][v] - winStart;
+      const long vs = (long) ps.vStart[side][v] - winStart, ve = (long) ps.vEnd[side][v] - winStart;
       if (vs < 1 || ve < vs || ve > kMicroMaxWin) return 0;
       uint8_t f = (uint8_t) ((in.phased && in.phased[ii]) ? 1 : 0);
       f |= (uint8_t) (P << 1);
@@ -521,19 +518,26 @@ int Engine::buildPacket(const PassCtx& pc, int k, int j, uint8_t* out) const {
     }
   }
   const int winBase = nBases;
-  std::memcpy(raw + nBases, seqs_[k].template_bases + winStart, (size_t) winLen);
+  std::memcpy(raw + nBases, ps.tmpl + winStart, (size_t) winLen);
   nBases += (int) winLen;
   raw[nBases] = raw[nBases + 1] = raw[nBases + 2] = 1;  // padding of the last 2-bit byte
   std::memcpy(vout, alleles, (size_t) nAl * MA_BYTES);
   uint8_t* bout = vout + nAl * MA_BYTES;
   const int nb2 = (nBases + 3) >> 2;
-  unsigned bad = 0;
+  // four bases (1..4, one per byte) -> one byte of 2-bit codes, 32 bits at a time: y = codes 0..3 per byte,
+  // t = y | y >> 6 pairs them up, t | t >> 12 brings the upper pair down.  N (0) and the explicit-unknown token (5)
+  // leave bits outside 0x03 per byte: such regions do not become packets.
+  uint32_t bad = 0;
   for (int q = 0; q < nb2; ++q) {
-    const unsigned b0 = raw[4 * q] - 1u, b1 = raw[4 * q + 1] - 1u, b2 = raw[4 * q + 2] - 1u, b3 = raw[4 * q + 3] - 1u;
-    bad |= b0 | b1 | b2 | b3;  // N (0) wraps to 0xffffffff, the explicit-unknown token 5 gives 4: neither fits 2 bits
-    bout[q] = (uint8_t) ((b0 & 3u) | ((b1 & 3u) << 2) | ((b2 & 3u) << 4) | ((b3 & 3u) << 6));
+    uint32_t x;
+    std::memcpy(&x, raw + 4 * q, 4);
+    const uint32_t y = x - 0x01010101u;
+    bad |= y;
+    const uint32_t t = y | (y >> 6);
+    bout[q] = (uint8_t) (t | (t >> 12));
   }
-  if (bad > 3u) return 0;
+  bad &= 0xfcfcfcfcu;
+  if (bad != 0) return 0;
   int bytes = (int) (bout + nb2 - out);
   while (bytes & 3) out[bytes++] = 0;
   if (bytes > T::PKT_MAX) return 0;
@@ -624,6 +628,16 @@ int Engine::buildChunk(PassCtx& pc, Chunk& ch, int worker, bool launch) {
   const int nReg = (int) pc.rr[k].size();
   const int32_t* cs = pc.vStart[0].data();
   const int32_t* bs = pc.vStart[1].data();
+  PacketSrc ps;
+  ps.rr = rrk;
+  ps.tmpl = tmpl;
+  ps.tl = seqs_[k].template_len;
+  for (int side = 0; side < 2; ++side) {
+    ps.ss[side] = &pc.ss[side][k];
+    ps.vStart[side] = pc.vStart[side].data();
+    ps.vEnd[side] = pc.vEnd[side].data();
+    ps.sideEnd[side] = pc.ss[side][k].first + pc.ss[side][k].n;
+  }
   for (int q = 0; q < nr; ++q) {
     const int j = listed ? ch.list[q] : ch.r0 + q;
     if (!listed && cls[j] == kClsEarly) continue;  // already running in the warp-per-region kernels
@@ -654,11 +668,11 @@ int Engine::buildChunk(PassCtx& pc, Chunk& ch, int worker, bool launch) {
     if (pc.microOk) {
       const RegRange& g = rrk[j];
       if (g.cCount <= MicroA::KV && g.bCount <= MicroA::KV) {
-        bytes = buildPacket<MicroA>(pc, k, j, pkA + at[0]);
+        bytes = buildPacket<MicroA>(pc, ps, j, pkA + at[0]);
       } else if (g.cCount <= MicroB::KV && g.bCount <= MicroB::KV) {
         c = 1;
         if (sc[1].size() < at[1] + MicroB::PKT_MAX + 16) sc[1].resize(std::max(sc[1].size() * 2, at[1] + (size_t) 64 * MicroB::PKT_MAX));
-        bytes = buildPacket<MicroB>(pc, k, j, sc[1].data() + at[1]);
+        bytes = buildPacket<MicroB>(pc, ps, j, sc[1].data() + at[1]);
       }
     }
     if (bytes > 0) {
@@ -1030,13 +1044,16 @@ int Engine::execute() {
 }
 
 int Engine::run(const vce_config& cfg, int32_t nSeq, const vce_sequence* seqs, vce_sequence_result* results) {
+  StageTimer tm;
   int rc = prepare(cfg, nSeq, seqs, false);
   if (rc) return rc;
   liveResults_ = cfg.n_passes == 1 ? results : nullptr;
   rc = execute();
   liveResults_ = nullptr;
   if (rc) return rc;
-  return finish(results);
+  rc = finish(results);
+  tm.lap("vce_submit total");
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------- warp-per-region path

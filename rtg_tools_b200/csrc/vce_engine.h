@@ -144,7 +144,16 @@ class Engine {
   void splitSlice(const PassCtx& pc, int i, int ie, int j, int je, long maxEnd, std::vector<RegRange>& out, bool* continues) const;
   void splitAll(PassCtx& pc);
   void planChunks(PassCtx& pc);
-  template <class T> int buildPacket(const PassCtx& pc, int k, int j, uint8_t* out) const;
+  struct PacketSrc {          // what buildPacket reads, resolved once per chunk
+    const RegRange* rr;
+    const SideSeq* ss[2];
+    const int32_t* vStart[2];
+    const int32_t* vEnd[2];
+    int32_t sideEnd[2];       // one past the last pass-wide variant index of the sequence
+    const uint8_t* tmpl;
+    int32_t tl;
+  };
+  template <class T> int buildPacket(const PassCtx& pc, const PacketSrc& ps, int j, uint8_t* out) const;
   int buildChunk(PassCtx& pc, Chunk& ch, int worker, bool launch);
   int runChunks(PassCtx& pc);
   void decodeChunk(PassCtx& pc, Chunk& ch, int64_t& iterations);

@@ -41,16 +41,23 @@ def merge_counts(counts: np.ndarray, device: Optional[torch.device] = None) -> n
     return t.cpu().numpy()
 
 
+def _flag_counts(status: np.ndarray, flags) -> List[int]:
+    """How many status bytes carry each of the single-bit `flags` (two passes per flag, no boolean temporaries)."""
+    return [int(np.count_nonzero(status & np.uint8(f))) for f in flags]
+
+
 def summary_counts(results: List[capi.SequenceResult]) -> np.ndarray:
     """[baseline TP, baseline FN, call TP, call FP, skipped, mis-phasings, correct phasings, unphaseable]."""
     tot = np.zeros(8, np.int64)
+    flags = (capi.STATUS_GT_MATCH, capi.STATUS_NO_MATCH, capi.STATUS_SKIPPED)
     for r in results:
-        b, c = r.baseline.status, r.calls.status
-        tot[0] += int(((b & capi.STATUS_GT_MATCH) != 0).sum())
-        tot[1] += int(((b & capi.STATUS_NO_MATCH) != 0).sum())
-        tot[2] += int(((c & capi.STATUS_GT_MATCH) != 0).sum())
-        tot[3] += int(((c & capi.STATUS_NO_MATCH) != 0).sum())
-        tot[4] += int(((b & capi.STATUS_SKIPPED) != 0).sum()) + int(((c & capi.STATUS_SKIPPED) != 0).sum())
+        b = _flag_counts(r.baseline.status, flags)
+        c = _flag_counts(r.calls.status, flags)
+        tot[0] += b[0]
+        tot[1] += b[1]
+        tot[2] += c[0]
+        tot[3] += c[1]
+        tot[4] += b[2] + c[2]
         tot[5:8] += np.asarray(r.phasing, np.int64)
     return tot
 
