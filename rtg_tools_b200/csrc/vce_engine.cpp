@@ -1870,7 +1870,41 @@ int Engine::finish(vce_sequence_result* results) {
     }
     syncPartFirst_[p][nSeq_] = (int) syncParts_.size();
   }
-  pool_->parallelFor((int) syncParts_.size(), [&](int t, int) {
+  // One task list.  First the region blocks, largest sequence first; the worker that finishes the last block of one of
+  // the few LARGEST sequences goes on with that sequence's join and phasing counts (a sequential state machine,
+  // PhasingEvaluator.java:55-142: the longest chains have to start early).  The other sequences' joins follow as tasks
+  // of their own at the end of the list, so that the block work is never starved of workers.
+  std::vector<int> partOrder;
+  partOrder.reserve(syncParts_.size());
+  std::vector<std::atomic<int>> remaining(nSeq_);
+  std::vector<uint8_t> live(nSeq_, 0), inlineClose(nSeq_, 0);
+  for (int k = 0; k < nSeq_; ++k) remaining[k].store(0);
+  const int nInline = std::max(1, pool_->threads() / 4);
+  std::vector<int> tailSeqs;
+  for (int t = 0; t < nSeq_; ++t) {
+    const int k = order[t];
+    for (int p = 0; p < cfg_.n_passes; ++p) {
+      for (int q = syncPartFirst_[p][k]; q < syncPartFirst_[p][k + 1]; ++q) partOrder.push_back(q);
+      remaining[k].fetch_add(syncPartFirst_[p][k + 1] - syncPartFirst_[p][k]);
+    }
+    if (t < nInline) inlineClose[k] = 1;
+    else tailSeqs.push_back(k);
+  }
+  auto closeSequence = [&](int k) {
+    live[k] = assembleHeader(k, results[k]) ? 1 : 0;
+    if (live[k]) phasing(k, seqSync_[0][k], results[k].phasing);
+  };
+  for (int k = 0; k < nSeq_; ++k) if (inlineClose[k] && remaining[k].load() == 0) closeSequence(k);   // nothing to gather
+  const int nParts = (int) partOrder.size();
+  pool_->parallelFor(nParts + (int) tailSeqs.size(), [&](int tt, int) {
+    if (tt >= nParts) {
+      // every block was handed out before this task: the few still running finish within a block's time
+      const int k = tailSeqs[(size_t) (tt - nParts)];
+      while (remaining[k].load() != 0) std::this_thread::yield();
+      closeSequence(k);
+      return;
+    }
+    const int t = partOrder[tt];
     SyncPart& sp = syncParts_[t];
     const PassCtx& pc = pass_[sp.pass];
     const int k = sp.seq;
@@ -1898,17 +1932,11 @@ int Engine::finish(vce_sequence_result* results) {
         sp.err = VCE_ERR_UNSUPPORTED;
       }
     }
+    if (remaining[k].fetch_sub(1) == 1 && inlineClose[k]) closeSequence(k);
   });
-  tm.lap("assemble: sync point blocks");
-  std::vector<uint8_t> live(nSeq_, 0);
-  pool_->parallelFor(nSeq_, [&](int t, int) {
-    const int k = order[t];
-    live[k] = assembleHeader(k, results[k]) ? 1 : 0;
-  });
-  tm.lap("assemble: sync points");
-  struct Task { int seq, side, lo, hi; };  // side < 0: phasing counts of the sequence
+  tm.lap("assemble: sync points + phasing");
+  struct Task { int seq, side, lo, hi; };
   std::vector<Task> tasks;
-  for (int t = 0; t < nSeq_; ++t) if (live[order[t]]) tasks.push_back(Task{order[t], -1, 0, 0});
   const int block = 1 << 15;
   for (int t = 0; t < nSeq_; ++t) {
     const int k = order[t];
@@ -1920,10 +1948,9 @@ int Engine::finish(vce_sequence_result* results) {
   }
   pool_->parallelFor((int) tasks.size(), [&](int t, int) {
     const Task& tk = tasks[t];
-    if (tk.side < 0) phasing(tk.seq, seqSync_[0][tk.seq], results[tk.seq].phasing);
-    else assembleBlock(tk.seq, tk.side, tk.lo, tk.hi, results[tk.seq]);
+    assembleBlock(tk.seq, tk.side, tk.lo, tk.hi, results[tk.seq]);
   });
-  tm.lap("assemble: variants + phasing");
+  tm.lap("assemble: variants");
   int rc = VCE_OK;
   for (int k = 0; k < nSeq_; ++k) {
     if (results[k].error != VCE_OK && rc == VCE_OK) rc = results[k].error;
