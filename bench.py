@@ -307,7 +307,8 @@ def main():
     achieved = (ALG_BYTES_PER_VARIANT * fast_var / (fast_ms * 1e-3) / 1e9) if fast_ms > 0 else 0.0
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    # the ncu capture is of the C2 default-configuration launch; other workloads have no measured traffic figure
+    if os.path.exists(tpath) and args.workload == "c2" and args.config == "default" and not args.total_bp:
         try:
             traffic = json.load(open(tpath)).get("k_micro_dram_bytes_per_launch")
         except Exception:
