@@ -62,6 +62,7 @@ Context* acquire(int& rc) {
   if (const char* e = std::getenv("VCE_CHUNK_REGIONS")) opt.chunkRegions = std::atoi(e);
   if (const char* e = std::getenv("VCE_SORT_PACKETS")) opt.sortPackets = std::atoi(e) != 0;
   if (const char* e = std::getenv("VCE_SPLIT_GAP")) opt.gap = std::max(1, std::atoi(e));
+  if (const char* e = std::getenv("VCE_DEVICE_BUILD")) opt.deviceBuild = std::atoi(e) != 0;
   c->engine.reset(new vce::Engine(c->backend.get(), g_pool.get(), opt));
   return c;
 }
@@ -194,6 +195,7 @@ int vce_submit(const vce_config* cfg, int32_t n_seq, const vce_sequence* seqs, v
   Context* c = acquire(rc);
   if (!c) return rc;
   c->backend->stats = vce::SearchStats();
+  if (const char* e = std::getenv("VCE_DEVICE_BUILD")) c->engine->options().deviceBuild = std::atoi(e) != 0;   // contexts are pooled
   rc = c->engine->run(*cfg, n_seq, seqs, results);
   const std::string msg = rc ? c->engine->error() : std::string();
   release(c);

@@ -303,6 +303,31 @@ struct MicroParams {
   MicroConfig cfg;
 };
 constexpr int kMicroThreads = 64;
+constexpr uint32_t kNoPacket = 0xffffffffu;   // offsets[] entry of a region the builder could not pack
+
+// Device-side digest (vce_packet.h): one thread packs one region's packet from the uploaded slices of the caller's arrays.
+struct BuildParams {
+  PacketView pv;              // pointers into the device copy of the slab, moved back by the slices' first indices
+  const RegRange* regs;
+  const uint32_t* winOff;
+  const uint8_t* windows;
+  uint8_t* packets;           // [n * stride]
+  uint32_t* offsets;          // [n] packet offset in 4-byte words, kNoPacket when the region does not fit
+  int n, stride;
+};
+template <class T>
+__global__ void __launch_bounds__(128) k_build(const __grid_constant__ BuildParams p) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= p.n) return;
+  const RegRange g = p.regs[q];
+  int32_t winStart = 0, winLen = 0, nextStart[2];
+  int bytes = 0;
+  uint8_t* out = p.packets + (size_t) q * p.stride;
+  if (microWindow(p.pv, g, &winStart, &winLen, nextStart)) {
+    bytes = microBuildPacket<T>(p.pv, g, winStart, winLen, nextStart, p.windows + p.winOff[q], out);
+  }
+  p.offsets[q] = bytes > 0 ? (uint32_t) (((size_t) q * p.stride) >> 2) : kNoPacket;
+}
 
 template <class T>
 __global__ void __launch_bounds__(kMicroThreads) k_micro(const __grid_constant__ MicroParams p) {
@@ -332,17 +357,26 @@ __global__ void __launch_bounds__(kMicroThreads) k_micro(const __grid_constant__
         c = p.table[lo];
       }
       const int q = r - c.first;
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(c.packets) + __ldg(c.offsets + q);
-      uint32_t* dst = reinterpret_cast<uint32_t*>(ms.ws + T::OFF_PKT);
-      const uint32_t w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
-      const int nw = (int) (w2 >> 24);
-      dst[0] = w0; dst[1] = w1; dst[2] = w2;
-      for (int i = 3; i < nw; ++i) dst[i] = __ldg(src + i);
+      const uint32_t off = __ldg(c.offsets + q);
       resOut = c.results + (size_t) q * T::RES_BYTES;
-      ms.begin();
-      running = true;
+      if (off == kNoPacket) {
+        // the device-side builder found that the region does not fit a packet: hand it back right away
+        uint32_t* o = reinterpret_cast<uint32_t*>(resOut);
+#pragma unroll
+        for (int i = 0; i < T::RES_BYTES / 4; ++i) o[i] = i == 0 ? (uint32_t) kMicroFallback << (8 * MR_STATUS) : 0u;
+        r += stride;
+      } else {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(c.packets) + off;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(ms.ws + T::OFF_PKT);
+        const uint32_t w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
+        const int nw = (int) (w2 >> 24);
+        dst[0] = w0; dst[1] = w1; dst[2] = w2;
+        for (int i = 3; i < nw; ++i) dst[i] = __ldg(src + i);
+        ms.begin();
+        running = true;
+      }
     }
-    if (__all_sync(0xffffffffu, !running)) break;  // nothing left for any lane
+    if (__all_sync(0xffffffffu, !running && r >= p.total)) break;  // nothing left for any lane
     if (running) {
       const int st = ms.iterate(slot);
       if (st != kMicroPending) {
@@ -802,6 +836,7 @@ class CudaBackend : public Backend {
     for (DevBlock& b : dBlocks_) b.used = 0;
     mNextEvent_ = 0;
     mNextLane_ = 0;
+    pendingB_.clear();
     lastMicroMs_ = 0;
     lastMicroRegions_ = 0;
     return VCE_OK;
@@ -948,6 +983,136 @@ class CudaBackend : public Backend {
   }
   bool microPending_[2] = {false, false};
   long long microPendingTotal_[2] = {0, 0};
+  // Device-side digest of one chunk: slab up, k_build per packet class, the search kernels, results down.
+  int microBuildRun(MicroBuildJob& b, MicroJob& ja, MicroJob& jb, const MicroConfig& mc) override {
+    CUDA_TRY(cudaSetDevice(device_));
+    MicroJob* jobs[2] = {&ja, &jb};
+    const int strides[2] = {(MicroA::PKT_MAX + 15) & ~15, (MicroB::PKT_MAX + 15) & ~15};
+    void* dSlab = nullptr;
+    int lane = 0;
+    {
+      std::lock_guard<std::mutex> lk(mMu_);
+      dSlab = devAlloc(b.slabBytes + 16);
+      lane = mNextLane_;
+      mNextLane_ = (mNextLane_ + 1) % kMicroLanes;
+      for (int c = 0; c < 2; ++c) {
+        MicroJob& j = *jobs[c];
+        if (j.n == 0) continue;
+        j.dPackets = devAlloc((size_t) j.n * strides[c] + 16);
+        j.dOffsets = devAlloc((size_t) j.n * 4);
+        j.dResults = devAlloc((size_t) j.n * j.resBytes);
+        j.lane = lane;
+        if ((int) mEvents_.size() <= mNextEvent_) {
+          cudaEvent_t e;
+          if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { err_ = "cudaEventCreate failed"; return VCE_ERR_CUDA; }
+          mEvents_.push_back(e);
+        }
+        j.event = mNextEvent_++;
+        j.evHandle = mEvents_[j.event];
+        if (!j.dPackets || !j.dOffsets || !j.dResults) { err_ = "out of device memory for region packets"; return VCE_ERR_CUDA; }
+        stats.d2hBytes += (int64_t) j.n * j.resBytes;
+        ++stats.launches;
+      }
+      stats.h2dBytes += (int64_t) b.slabBytes;
+    }
+    if (!dSlab) { err_ = "out of device memory for region packets"; return VCE_ERR_CUDA; }
+    cudaStream_t st = mStream_[lane];
+    CUDA_TRY(cudaMemcpyAsync(dSlab, b.slab, b.slabBytes, cudaMemcpyHostToDevice, st));
+    const uint8_t* base = static_cast<const uint8_t*>(dSlab);
+    int q0 = 0;
+    for (int c = 0; c < 2; ++c) {
+      MicroJob& j = *jobs[c];
+      if (j.n > 0) {
+        BuildParams bp;
+        bp.pv = microBuildView(b, base);
+        bp.regs = reinterpret_cast<const RegRange*>(base + b.regions) + q0;
+        bp.winOff = reinterpret_cast<const uint32_t*>(base + b.winOff) + q0;
+        bp.windows = base + b.windows;
+        bp.packets = static_cast<uint8_t*>(j.dPackets);
+        bp.offsets = static_cast<uint32_t*>(j.dOffsets);
+        bp.n = j.n;
+        bp.stride = strides[c];
+        const int blocks = (j.n + 127) / 128;
+        if (c == 0) k_build<MicroA><<<blocks, 128, 0, st>>>(bp);
+        else k_build<MicroB><<<blocks, 128, 0, st>>>(bp);
+        CUDA_TRY(cudaGetLastError());
+        MicroParams mp;
+        std::memset(&mp, 0, sizeof(mp));
+        mp.one = MicroChunkDesc{static_cast<const uint8_t*>(j.dPackets), static_cast<const uint32_t*>(j.dOffsets),
+                                static_cast<uint8_t*>(j.dResults), j.n, 0};
+        mp.table = nullptr;
+        mp.nChunks = 1;
+        mp.total = j.n;
+        mp.refill = microRefill_;
+        mp.cfg = mc;
+        if (c == 1) {
+          // the few MicroB-shaped regions of a chunk would be a tiny, latency-bound launch of their own: their packets are
+          // built now, the search runs once over all chunks (microBuildFlush)
+          cudaEvent_t built = nullptr;
+          {
+            std::lock_guard<std::mutex> lk(mMu_);
+            if ((int) mEvents_.size() <= mNextEvent_) {
+              cudaEvent_t e;
+              if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { err_ = "cudaEventCreate failed"; return VCE_ERR_CUDA; }
+              mEvents_.push_back(e);
+            }
+            built = mEvents_[mNextEvent_++];
+            pendingB_.push_back(PendingB{&j, built});
+          }
+          CUDA_TRY(cudaEventRecord(built, st));
+          continue;
+        }
+        microLaunch(mp, c, st);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(j.results, j.dResults, (size_t) j.n * j.resBytes, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(j.evHandle), st));
+      }
+      q0 += c == 0 ? b.nA : 0;
+    }
+    return VCE_OK;
+  }
+  // One search launch over the MicroB packets of every chunk built since the last flush.
+  int microBuildFlush(const MicroConfig& mc) override {
+    CUDA_TRY(cudaSetDevice(device_));
+    std::vector<PendingB> pend;
+    {
+      std::lock_guard<std::mutex> lk(mMu_);
+      pend.swap(pendingB_);
+    }
+    if (pend.empty()) return VCE_OK;
+    cudaStream_t st = mStream_[1];
+    std::vector<MicroChunkDesc> table(pend.size());
+    int total = 0;
+    for (size_t i = 0; i < pend.size(); ++i) {
+      MicroJob& j = *pend[i].job;
+      CUDA_TRY(cudaStreamWaitEvent(st, pend[i].built, 0));
+      table[i] = MicroChunkDesc{static_cast<const uint8_t*>(j.dPackets), static_cast<const uint32_t*>(j.dOffsets),
+                                static_cast<uint8_t*>(j.dResults), j.n, total};
+      total += j.n;
+    }
+    CUDA_TRY(mTableC_[1].ensure(table.size()));
+    CUDA_TRY(cudaMemcpyAsync(mTableC_[1].p, table.data(), table.size() * sizeof(MicroChunkDesc), cudaMemcpyHostToDevice, st));
+    MicroParams mp;
+    std::memset(&mp, 0, sizeof(mp));
+    mp.one = table[0];
+    mp.table = mTableC_[1].p;
+    mp.nChunks = (int) table.size();
+    mp.total = total;
+    mp.refill = microRefill_;
+    mp.cfg = mc;
+    microLaunch(mp, 1, st);
+    CUDA_TRY(cudaGetLastError());
+    for (const PendingB& pb : pend) {
+      MicroJob& j = *pb.job;
+      CUDA_TRY(cudaMemcpyAsync(j.results, j.dResults, (size_t) j.n * j.resBytes, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(j.evHandle), st));
+      j.lane = 1;
+    }
+    ++stats.launches;
+    return VCE_OK;
+  }
+  struct PendingB { MicroJob* job; cudaEvent_t built; };
+  std::vector<PendingB> pendingB_;
   int microWait(MicroJob& j) override {
     CUDA_TRY(cudaSetDevice(device_));
     CUDA_TRY(cudaEventSynchronize(static_cast<cudaEvent_t>(j.evHandle)));

@@ -446,115 +446,43 @@ void Engine::planChunks(PassCtx& pc) {
 // Writes the packet of region (k, j) in the layout of vce_micro.h; returns its length in bytes (a multiple of 4) or
 // 0 when the region does not fit the thread-per-region kernel.
 template <class T>
-int Engine::buildPacket(const PassCtx& pc, const PacketSrc& ps, int j, uint8_t* out) const {
+int Engine::buildPacket(const PassCtx&, const PacketSrc& ps, int j, uint8_t* out) const {
   if (j == 0) return 0;  // the first path of a sequence starts at -1 and is not in sync (HalfPath.java:50-57)
   const RegRange& g = ps.rr[j];
   if (g.cCount > T::KV || g.bCount > T::KV) return 0;
-  const int first[2] = {g.cFirst, g.bFirst};
-  const int count[2] = {g.cCount, g.bCount};
-  int nextStart[2];
-  int firstStart = INT_MAX;
-  long maxEnd = LONG_MIN;
-  for (int side = 0; side < 2; ++side) {
-    const int e = first[side] + count[side];
-    nextStart[side] = e < ps.sideEnd[side] ? ps.vStart[side][e] : kNoNext;
-    for (int v = first[side]; v < e; ++v) {
-      firstStart = std::min(firstStart, ps.vStart[side][v]);
-      maxEnd = std::max(maxEnd, (long) ps.vEnd[side][v]);
-    }
-  }
-  if (nextStart[0] == kNoNext && nextStart[1] == kNoNext) return 0;  // the last region finishes at the template end
-  if (firstStart == INT_MAX || firstStart < 1 || maxEnd < firstStart) return 0;
-  const int winStart = firstStart - 1;
-  const int tl = ps.tl;
-  const long winEnd = std::min<long>(maxEnd + opt_.microMargin, tl);
-  const long winLen = winEnd - winStart;
-  if (winLen < 1 || winLen > kMicroMaxWin) return 0;
+  int32_t winStart = 0, winLen = 0, nextStart[2];
+  if (!microWindow(ps.pv, g, &winStart, &winLen, nextStart)) return 0;
+  return microBuildPacket<T>(ps.pv, g, winStart, winLen, nextStart, ps.tmpl + winStart, out);
+}
 
-  uint8_t raw[256 + 8];   // allele bases then window bases, one per byte; packed to 2 bits at the end
-  int nBases = 0;
-  uint8_t alleles[4 * T::KV * MA_BYTES];
-  int nAl = 0;
-  uint8_t* vout = out + MP_VARS;
+// The caller's arrays of sequence k as the packet builder reads them.
+PacketView Engine::packetView(const PassCtx& pc, int k) const {
+  PacketView pv;
   for (int side = 0; side < 2; ++side) {
-    const SideSeq& s = *ps.ss[side];
-    const vce_variants& in = *s.in;
-    const int P = in.gt_ploidy;
-    if (P != pc.gtPloidy[side]) return 0;
-    if (pc.H == 2 ? P != 2 : (P < 1 || P > 2)) return 0;
-    for (int v = first[side]; v < first[side] + count[side]; ++v) {
-      const int li = v - s.first;
-      const int ii = s.idx ? s.idx[li] : li;
-      const int off0 = in.allele_off[ii];
-      const int nSl = in.allele_off[ii + 1] - off0;
-      const int gt[2] = {in.gt[(size_t) ii * P], P > 1 ? in.gt[(size_t) ii * P + 1] : in.gt[(size_t) ii * P]};
-      int al[2] = {kMicroNoAllele, kMicroNoAllele};
-      for (int h = 0; h < 2; ++h) {
-        if (h == 1 && gt[1] == gt[0]) { al[1] = al[0]; break; }
-        const int id = gt[h];
-        if (id < -1 || id + 1 >= nSl) continue;
-        const int slot = off0 + id + 1;
-        if (in.allele_null[slot]) continue;
-        const long st = (long) in.allele_start[slot] - winStart, en = (long) in.allele_end[slot] - winStart;
-        const int nb = in.allele_nt_off[slot];
-        const int len = in.allele_nt_off[slot + 1] - nb;
-        if (st < 0 || en < st || en > kMicroMaxWin || len > kMicroMaxWin || nBases + len + winLen > 255) return 0;
-        const uint8_t* nt = in.nt + nb;
-        for (int q = 0; q < len; ++q) raw[nBases + q] = nt[q];
-        uint8_t* a = alleles + nAl * MA_BYTES;
-        a[MA_START] = (uint8_t) st; a[MA_END] = (uint8_t) en; a[MA_NT] = (uint8_t) nBases; a[MA_LEN] = (uint8_t) len;
-        nBases += len;
-        al[h] = nAl++;
-      }
-      const long vs = (long) ps.vStart[side][v] - winStart, ve = (long) ps.vEnd[side][v] - winStart;
-      if (vs < 1 || ve < vs || ve > kMicroMaxWin) return 0;
-      uint8_t f = (uint8_t) ((in.phased && in.phased[ii]) ? 1 : 0);
-      f |= (uint8_t) (P << 1);
-      if (in.status_in) f |= in.status_in[ii] & VCE_STATUS_OUTSIDE_EVAL;
-      vout[MV_START] = (uint8_t) vs; vout[MV_END] = (uint8_t) ve; vout[MV_FLAGS] = f;
-      vout[MV_GT0] = (uint8_t) (int8_t) gt[0]; vout[MV_GT1] = (uint8_t) (int8_t) gt[1];
-      vout[MV_A0] = (uint8_t) al[0]; vout[MV_A1] = (uint8_t) al[1]; vout[7] = 0;
-      vout += MV_BYTES;
-    }
+    const SideSeq& ss = pc.ss[side][k];
+    const vce_variants& in = *ss.in;
+    PacketSideView& s = pv.s[side];
+    s.vStart = pc.vStart[side].data();
+    s.vEnd = pc.vEnd[side].data();
+    s.sideEnd = ss.first + ss.n;
+    s.first = ss.first;
+    s.idx = ss.idx;
+    s.gtPloidy = in.gt_ploidy;
+    s.gt = in.gt;
+    s.phased = in.phased;
+    s.statusIn = in.status_in;
+    s.alleleOff = in.allele_off;
+    s.aStart = in.allele_start;
+    s.aEnd = in.allele_end;
+    s.aNull = in.allele_null;
+    s.aNtOff = in.allele_nt_off;
+    s.nt = in.nt;
+    pv.expectPloidy[side] = pc.gtPloidy[side];
   }
-  const int winBase = nBases;
-  std::memcpy(raw + nBases, ps.tmpl + winStart, (size_t) winLen);
-  nBases += (int) winLen;
-  raw[nBases] = raw[nBases + 1] = raw[nBases + 2] = 1;  // padding of the last 2-bit byte
-  std::memcpy(vout, alleles, (size_t) nAl * MA_BYTES);
-  uint8_t* bout = vout + nAl * MA_BYTES;
-  const int nb2 = (nBases + 3) >> 2;
-  // four bases (1..4, one per byte) -> one byte of 2-bit codes, 32 bits at a time: y = codes 0..3 per byte,
-  // t = y | y >> 6 pairs them up, t | t >> 12 brings the upper pair down.  N (0) and the explicit-unknown token (5)
-  // leave bits outside 0x03 per byte: such regions do not become packets.
-  uint32_t bad = 0;
-  for (int q = 0; q < nb2; ++q) {
-    uint32_t x;
-    std::memcpy(&x, raw + 4 * q, 4);
-    const uint32_t y = x - 0x01010101u;
-    bad |= y;
-    const uint32_t t = y | (y >> 6);
-    bout[q] = (uint8_t) (t | (t >> 12));
-  }
-  bad &= 0xfcfcfcfcu;
-  if (bad != 0) return 0;
-  int bytes = (int) (bout + nb2 - out);
-  while (bytes & 3) out[bytes++] = 0;
-  if (bytes > T::PKT_MAX) return 0;
-  const int32_t ws32 = winStart;
-  std::memcpy(out + MP_WINSTART, &ws32, 4);
-  out[MP_COUNTS] = (uint8_t) (g.cCount | (g.bCount << 4));
-  out[MP_WINLEN] = (uint8_t) winLen;
-  for (int side = 0; side < 2; ++side) {
-    int rel = kMicroNoNext;
-    if (nextStart[side] != kNoNext) rel = (int) std::min<long>((long) nextStart[side] - winStart, kMicroFar);
-    out[side == 0 ? MP_CNEXT : MP_BNEXT] = (uint8_t) rel;
-  }
-  out[MP_TMPLLEN] = (uint8_t) std::min<long>((long) tl - winStart, kMicroFar + 2);
-  out[MP_NALLELES] = (uint8_t) nAl;
-  out[MP_WINBASE] = (uint8_t) winBase;
-  out[MP_NWORDS] = (uint8_t) (bytes / 4);
-  return bytes;
+  pv.tl = seqs_[k].template_len;
+  pv.H = pc.H;
+  pv.margin = opt_.microMargin;
+  return pv;
 }
 
 // Shape class of a packet: regions of one class take the same branches in the search, so the packets of a chunk are
@@ -631,13 +559,7 @@ int Engine::buildChunk(PassCtx& pc, Chunk& ch, int worker, bool launch) {
   PacketSrc ps;
   ps.rr = rrk;
   ps.tmpl = tmpl;
-  ps.tl = seqs_[k].template_len;
-  for (int side = 0; side < 2; ++side) {
-    ps.ss[side] = &pc.ss[side][k];
-    ps.vStart[side] = pc.vStart[side].data();
-    ps.vEnd[side] = pc.vEnd[side].data();
-    ps.sideEnd[side] = pc.ss[side][k].first + pc.ss[side][k].n;
-  }
+  ps.pv = packetView(pc, k);
   for (int q = 0; q < nr; ++q) {
     const int j = listed ? ch.list[q] : ch.r0 + q;
     if (!listed && cls[j] == kClsEarly) continue;  // already running in the warp-per-region kernels
@@ -892,6 +814,166 @@ int Engine::prepare(const vce_config& cfg, int32_t nSeq, const vce_sequence* seq
   return VCE_OK;
 }
 
+// Device-side digest of one chunk (vce_submit on sorted inputs): instead of chasing variant -> alleles -> bases per region,
+// the host copies the slices of the caller's arrays that the chunk touches wholesale into one page-locked slab, adds the
+// regions and their reference windows (the template itself stays on the host), and k_build packs the packets on the
+// device (vce_packet.h is the one source of the packing for both sides).
+int Engine::buildChunkDevice(PassCtx& pc, Chunk& ch, int worker) {
+  const int k = ch.seq;
+  const SideSeq* SS[2] = {&pc.ss[0][k], &pc.ss[1][k]};
+  if (!pc.microOk || SS[0]->idx != nullptr || SS[1]->idx != nullptr || !ch.list.empty()) return buildChunk(pc, ch, worker, true);
+  const long long tA = nowNs();
+  uint8_t* cls = pc.rcls[k].data();
+  RegRes* rs = pc.rs[k].data();
+  const RegRange* rrk = pc.rr[k].data();
+  const PacketView hv = packetView(pc, k);
+  for (int c = 0; c < 2; ++c) {
+    ch.pktRegion[c].clear();
+    ch.job[c] = MicroJob();
+    ch.job[c].cls = c;
+  }
+  ch.variants = 0;
+  ch.variantsA = 0;
+  thread_local std::vector<int32_t> wsv[2], wlv[2];
+  for (int c = 0; c < 2; ++c) { wsv[c].clear(); wlv[c].clear(); }
+  size_t winBytes = 0;
+  int lo[2] = {INT_MAX, INT_MAX}, hi[2] = {-1, -1};
+  for (int j = ch.r0; j < ch.r1; ++j) {
+    if (cls[j] == kClsEarly) continue;  // already running in the warp-per-region kernels
+    const RegRange& g = rrk[j];
+    int c = -1;
+    if (j != 0) {  // the first path of a sequence starts at -1 and is not in sync (HalfPath.java:50-57)
+      if (g.cCount <= MicroA::KV && g.bCount <= MicroA::KV) c = 0;
+      else if (g.cCount <= MicroB::KV && g.bCount <= MicroB::KV) c = 1;
+    }
+    int32_t ws = 0, wl = 0, ns[2];
+    if (c >= 0 && !microWindow(hv, g, &ws, &wl, ns)) c = -1;
+    if (c < 0) {
+      if (!ch.transient) cls[j] = 0;
+      rs[j].state = RS_RESIDUAL;
+      continue;
+    }
+    ch.pktRegion[c].push_back(j);
+    wsv[c].push_back(ws);
+    wlv[c].push_back(wl);
+    winBytes += (size_t) wl;
+    cls[j] = (uint8_t) (1 + c);
+    rs[j].state = RS_PENDING;
+    ch.variants += g.cCount + g.bCount;
+    if (c == 0) ch.variantsA += g.cCount + g.bCount;
+    lo[0] = std::min(lo[0], g.cFirst); hi[0] = std::max(hi[0], g.cFirst + g.cCount);
+    lo[1] = std::min(lo[1], g.bFirst); hi[1] = std::max(hi[1], g.bFirst + g.bCount);
+  }
+  const int nA = (int) ch.pktRegion[0].size(), nB = (int) ch.pktRegion[1].size();
+  if (nA + nB == 0) { g_tBuild += nowNs() - tA; return VCE_OK; }
+  // ---- slab layout
+  MicroBuildJob bj;
+  size_t at = 0;
+  auto place = [&](size_t bytes) { const size_t o = at; at = (at + bytes + 15) & ~(size_t) 15; return (int64_t) o; };
+  bj.regions = place((size_t) (nA + nB) * sizeof(RegRange));
+  bj.winOff = place((size_t) (nA + nB) * 4);
+  bj.windows = place(winBytes + 8);
+  int nV[2], nVs[2], nSl[2], nNt[2];
+  for (int side = 0; side < 2; ++side) {
+    const SideSeq& ss = *SS[side];
+    const vce_variants& in = *ss.in;
+    MicroBuildSide& m = bj.side[side];
+    nV[side] = hi[side] - lo[side];
+    nVs[side] = std::min(hi[side] + 1, ss.first + ss.n) - lo[side];   // one more start: the next variant after the chunk
+    m.v0 = lo[side];
+    m.i0 = lo[side] - ss.first;
+    m.slot0 = in.allele_off[m.i0];
+    const int slotN = in.allele_off[m.i0 + nV[side]];
+    nSl[side] = slotN - m.slot0;
+    m.nt0 = in.allele_nt_off[m.slot0];
+    nNt[side] = in.allele_nt_off[slotN] - m.nt0;
+    m.sideEnd = ss.first + ss.n;
+    m.first = ss.first;
+    m.gtPloidy = in.gt_ploidy;
+    m.vStart = place((size_t) nVs[side] * 4 + 4);
+    m.vEnd = place((size_t) nVs[side] * 4 + 4);
+    m.gt = place((size_t) nV[side] * (size_t) std::max(1, in.gt_ploidy) + 4);
+    m.phased = in.phased ? place((size_t) nV[side] + 4) : -1;
+    m.statusIn = in.status_in ? place((size_t) nV[side] + 4) : -1;
+    m.alleleOff = place((size_t) (nV[side] + 1) * 4);
+    m.aStart = place((size_t) nSl[side] * 4 + 4);
+    m.aEnd = place((size_t) nSl[side] * 4 + 4);
+    m.aNull = place((size_t) nSl[side] + 4);
+    m.aNtOff = place((size_t) (nSl[side] + 1) * 4);
+    m.nt = place((size_t) nNt[side] + 4);
+  }
+  uint8_t* slab = arenaAlloc(at + 16);
+  if (!slab) {
+    std::lock_guard<std::mutex> lk(errMu_);
+    err_ = "out of page-locked host memory";
+    return VCE_ERR_CUDA;
+  }
+  // ---- fill
+  RegRange* regs = reinterpret_cast<RegRange*>(slab + bj.regions);
+  uint32_t* winOff = reinterpret_cast<uint32_t*>(slab + bj.winOff);
+  uint8_t* wins = slab + bj.windows;
+  const uint8_t* tmpl = seqs_[k].template_bases;
+  size_t wo = 0;
+  int q = 0;
+  for (int c = 0; c < 2; ++c) {
+    const std::vector<int32_t>& list = ch.pktRegion[c];
+    for (size_t i = 0; i < list.size(); ++i, ++q) {
+      if (i + 8 < list.size()) __builtin_prefetch(tmpl + wsv[c][i + 8]);
+      regs[q] = rrk[list[i]];
+      winOff[q] = (uint32_t) wo;
+      std::memcpy(wins + wo, tmpl + wsv[c][i], (size_t) wlv[c][i]);
+      wo += (size_t) wlv[c][i];
+    }
+  }
+  for (int side = 0; side < 2; ++side) {
+    const vce_variants& in = *SS[side]->in;
+    const MicroBuildSide& m = bj.side[side];
+    const int P = in.gt_ploidy;
+    std::memcpy(slab + m.vStart, pc.vStart[side].data() + m.v0, (size_t) nVs[side] * 4);
+    std::memcpy(slab + m.vEnd, pc.vEnd[side].data() + m.v0, (size_t) nVs[side] * 4);
+    if (P > 0) std::memcpy(slab + m.gt, in.gt + (size_t) m.i0 * P, (size_t) nV[side] * P);
+    if (m.phased >= 0) std::memcpy(slab + m.phased, in.phased + m.i0, (size_t) nV[side]);
+    if (m.statusIn >= 0) std::memcpy(slab + m.statusIn, in.status_in + m.i0, (size_t) nV[side]);
+    std::memcpy(slab + m.alleleOff, in.allele_off + m.i0, (size_t) (nV[side] + 1) * 4);
+    std::memcpy(slab + m.aStart, in.allele_start + m.slot0, (size_t) nSl[side] * 4);
+    std::memcpy(slab + m.aEnd, in.allele_end + m.slot0, (size_t) nSl[side] * 4);
+    std::memcpy(slab + m.aNull, in.allele_null + m.slot0, (size_t) nSl[side]);
+    std::memcpy(slab + m.aNtOff, in.allele_nt_off + m.slot0, (size_t) (nSl[side] + 1) * 4);
+    std::memcpy(slab + m.nt, in.nt + m.nt0, (size_t) nNt[side]);
+  }
+  bj.slab = slab;
+  bj.slabBytes = at;
+  bj.tl = hv.tl;
+  bj.H = hv.H;
+  bj.expectPloidy[0] = hv.expectPloidy[0];
+  bj.expectPloidy[1] = hv.expectPloidy[1];
+  bj.margin = hv.margin;
+  bj.nA = nA;
+  bj.nB = nB;
+  for (int c = 0; c < 2; ++c) {
+    MicroJob& job = ch.job[c];
+    job.n = c == 0 ? nA : nB;
+    job.resBytes = c == 0 ? MicroA::RES_BYTES : MicroB::RES_BYTES;
+    if (job.n == 0) continue;
+    job.results = arenaAlloc((size_t) job.n * job.resBytes);
+    if (!job.results) {
+      std::lock_guard<std::mutex> lk(errMu_);
+      err_ = "out of page-locked host memory";
+      return VCE_ERR_CUDA;
+    }
+  }
+  const long long tB = nowNs();
+  g_tBuild += tB - tA;
+  const int rc = be_->microBuildRun(bj, ch.job[0], ch.job[1], pc.mc);
+  g_tUpload += nowNs() - tB;
+  g_tCopy += nowNs() - tB;
+  if (rc) {
+    std::lock_guard<std::mutex> lk(errMu_);
+    err_ = be_->lastError();
+  }
+  return rc;
+}
+
 // Splits the pass into regions, builds + uploads (+ starts, when `launch`) every chunk.
 static inline bool orientorPairMicro(int kc, int kb, int H) { return microOrientorSupported(kc, H) && microOrientorSupported(kb, H); }
 
@@ -986,9 +1068,10 @@ int Engine::execute() {
       tm.lap("early warp-per-region batch");
       pool_->parallelFor((int) pc.chunks.size(), [&](int t, int worker) {
         if (failed.load()) return;
-        const int r = buildChunk(pc, pc.chunks[t], worker, true);
+        const int r = opt_.deviceBuild ? buildChunkDevice(pc, pc.chunks[t], worker) : buildChunk(pc, pc.chunks[t], worker, true);
         if (r) failed.store(r);
       });
+      if (opt_.deviceBuild && !failed.load() && (rc = be_->microBuildFlush(pc.mc))) { err_ = be_->lastError(); return rc; }
       tm.lap("packets + upload + launch");
       if (tm.on) {
         std::fprintf(stderr, "[vce]   summed over workers: build %.1f ms, copy to page-locked %.1f ms, upload+launch calls %.1f ms\n",

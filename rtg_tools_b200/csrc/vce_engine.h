@@ -21,6 +21,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "vce_packet.h"
 #include "vce_pipeline.h"
 #include "vce_pool.h"
 
@@ -36,6 +37,7 @@ struct EngineOptions {
   int chunkRegions = 0;        // regions per chunk, 0 = automatic
   int splitSegment = 1 << 16;  // variants per segment of the parallel region split
   bool sortPackets = true;     // hand the packets of a chunk to the kernel grouped by shape class (lock-step lanes)
+  bool deviceBuild = false;    // vce_submit: pack the packets on the device from wholesale copies of the caller's arrays
 };
 
 class Engine {
@@ -49,6 +51,7 @@ class Engine {
   int execute();
   int finish(vce_sequence_result* results);
   const std::string& error() const { return err_; }
+  EngineOptions& options() { return opt_; }
   Backend* backend() { return be_; }
   // diagnostics of the last execute(): regions of the thread-per-region launches, variants of the MicroA class
   double microMs = 0;
@@ -60,7 +63,6 @@ class Engine {
     int32_t first = 0, n = 0; // slice of the pass-wide arrays
     const int32_t* idx = nullptr;  // (start,end)-sorted position -> input index, nullptr = identity
   };
-  struct RegRange { int32_t cFirst, cCount, bFirst, bCount; };  // pass-wide sorted indices
   struct RegRes {
     uint8_t state, flags;     // RS_*, bit0 usedPrefix, bit1 finished (last region of the sequence)
     int8_t lastId;            // alleleId() of the last baseline variant included in the region, -128 = none
@@ -146,15 +148,13 @@ class Engine {
   void planChunks(PassCtx& pc);
   struct PacketSrc {          // what buildPacket reads, resolved once per chunk
     const RegRange* rr;
-    const SideSeq* ss[2];
-    const int32_t* vStart[2];
-    const int32_t* vEnd[2];
-    int32_t sideEnd[2];       // one past the last pass-wide variant index of the sequence
+    PacketView pv;            // the caller's arrays of the chunk's sequence (vce_packet.h)
     const uint8_t* tmpl;
-    int32_t tl;
   };
+  PacketView packetView(const PassCtx& pc, int k) const;
   template <class T> int buildPacket(const PassCtx& pc, const PacketSrc& ps, int j, uint8_t* out) const;
   int buildChunk(PassCtx& pc, Chunk& ch, int worker, bool launch);
+  int buildChunkDevice(PassCtx& pc, Chunk& ch, int worker);
   int runChunks(PassCtx& pc);
   void decodeChunk(PassCtx& pc, Chunk& ch, int64_t& iterations);
   void assembleRegionEarly(PassCtx& pc, int k, int j);

@@ -14,6 +14,7 @@
 #include "../../include/vce.h"
 #include "vce_device.h"
 #include "vce_micro.h"
+#include "vce_packet.h"
 #include "vce_search.h"
 
 namespace vce {
@@ -76,6 +77,60 @@ struct MicroJob {
   void* evHandle = nullptr;
 };
 
+// ---- device-side packet building (vce_packet.h).  One slab per chunk: wholesale copies of the slices of the caller's
+// arrays that the chunk's regions touch, the regions themselves and their reference windows.  Offsets are in bytes from
+// the start of the slab, every array starts on a 16-byte boundary.
+struct MicroBuildSide {
+  int64_t vStart, vEnd;          // int32[nV + 1]   element 0 = pass-wide variant index v0 (the extra one: the next variant)
+  int64_t gt;                    // int8[nV * gtPloidy]   element 0 = input index i0
+  int64_t phased, statusIn;      // uint8[nV] or -1 when the caller passed no such array
+  int64_t alleleOff;             // int32[nV + 1]
+  int64_t aStart, aEnd;          // int32[nSlots]   element 0 = slot slot0
+  int64_t aNull;                 // uint8[nSlots]
+  int64_t aNtOff;                // int32[nSlots + 1]
+  int64_t nt;                    // uint8[nNt]      element 0 = nt offset nt0
+  int32_t v0, i0, slot0, nt0;
+  int32_t sideEnd, first, gtPloidy;
+};
+struct MicroBuildJob {
+  const uint8_t* slab = nullptr;   // host buffer (Backend::hostAlloc)
+  size_t slabBytes = 0;
+  MicroBuildSide side[2];
+  int32_t tl = 0, H = 0, expectPloidy[2] = {0, 0}, margin = 0;
+  int64_t regions = 0;             // RegRange[nA + nB]: the MicroA-shaped regions, then the MicroB-shaped ones
+  int64_t winOff = 0;              // uint32[nA + nB]: offset of each region's window bases within `windows`
+  int64_t windows = 0;             // uint8[]: reference bases from each region's window start
+  int32_t nA = 0, nB = 0;
+};
+// The packet builder's view of a slab that lives at `base` (host or device address).
+inline PacketView microBuildView(const MicroBuildJob& b, const uint8_t* base) {
+  PacketView pv;
+  for (int side = 0; side < 2; ++side) {
+    const MicroBuildSide& m = b.side[side];
+    PacketSideView& s = pv.s[side];
+    s.vStart = reinterpret_cast<const int32_t*>(base + m.vStart) - m.v0;
+    s.vEnd = reinterpret_cast<const int32_t*>(base + m.vEnd) - m.v0;
+    s.sideEnd = m.sideEnd;
+    s.first = m.first;
+    s.idx = nullptr;
+    s.gtPloidy = m.gtPloidy;
+    s.gt = reinterpret_cast<const int8_t*>(base + m.gt) - (ptrdiff_t) m.i0 * m.gtPloidy;
+    s.phased = m.phased >= 0 ? base + m.phased - m.i0 : nullptr;
+    s.statusIn = m.statusIn >= 0 ? base + m.statusIn - m.i0 : nullptr;
+    s.alleleOff = reinterpret_cast<const int32_t*>(base + m.alleleOff) - m.i0;
+    s.aStart = reinterpret_cast<const int32_t*>(base + m.aStart) - m.slot0;
+    s.aEnd = reinterpret_cast<const int32_t*>(base + m.aEnd) - m.slot0;
+    s.aNull = base + m.aNull - m.slot0;
+    s.aNtOff = reinterpret_cast<const int32_t*>(base + m.aNtOff) - m.slot0;
+    s.nt = base + m.nt - m.nt0;
+    pv.expectPloidy[side] = b.expectPloidy[side];
+  }
+  pv.tl = b.tl;
+  pv.H = b.H;
+  pv.margin = b.margin;
+  return pv;
+}
+
 class Backend {
  public:
   virtual ~Backend() {}
@@ -91,6 +146,13 @@ class Backend {
   virtual int microRunAll(std::vector<MicroJob*>& jobs, const MicroConfig& mc) = 0;
   virtual int microWait(MicroJob& j) = 0;                     // blocks until the results of j are on the host
   virtual void microCollect() {}                              // reads the device times of finished microRunAll launches
+  // Uploads the slab, builds the packets of its regions on the device (k_build), runs the search kernels and starts the
+  // device -> host copies of the results: a.n == b.nA records for the MicroA-shaped regions, bj.n == b.nB for the others.
+  // A region that does not fit a packet comes back with status kMicroFallback.  Asynchronous; microWait() collects.
+  virtual int microBuildRun(MicroBuildJob& b, MicroJob& a, MicroJob& bj, const MicroConfig& mc) = 0;
+  // The backend may hold the MicroB-shaped regions of the chunks back and search them in one launch: call this once every
+  // chunk has been handed over (the MicroJob objects have to stay where they are until then).
+  virtual int microBuildFlush(const MicroConfig&) { return 0; }
   virtual int setAlleles(int side, const AlleleTable& t) = 0;
   // Host -> device copy of the pass's variant arrays; clears the per-variant outputs.
   virtual int uploadPass(PassData& pd) = 0;

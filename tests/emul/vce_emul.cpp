@@ -54,6 +54,40 @@ class EmulBackend : public Backend {
     return 0;
   }
   int microWait(MicroJob&) override { return 0; }
+  // device-side packet building, emulated: the same builder source over the host slab, then the search as above
+  template <class T>
+  void buildRunT(const MicroBuildJob& b, const PacketView& pv, int q0, MicroJob& j, const MicroConfig& mc) {
+    const RegRange* regs = reinterpret_cast<const RegRange*>(b.slab + b.regions);
+    const uint32_t* winOff = reinterpret_cast<const uint32_t*>(b.slab + b.winOff);
+    std::vector<uint8_t> ws(T::WS_BYTES + 16), pk(T::PKT_MAX + 16);
+    for (int q = 0; q < j.n; ++q) {
+      uint8_t* res = j.results + (size_t) q * j.resBytes;
+      int32_t winStart = 0, winLen = 0, nextStart[2];
+      int bytes = 0;
+      if (microWindow(pv, regs[q0 + q], &winStart, &winLen, nextStart)) {
+        bytes = microBuildPacket<T>(pv, regs[q0 + q], winStart, winLen, nextStart, b.slab + b.windows + winOff[q0 + q], pk.data());
+      }
+      if (bytes <= 0) {
+        std::memset(res, 0, (size_t) j.resBytes);
+        res[MR_STATUS] = kMicroFallback;
+        continue;
+      }
+      MicroSearch<T> ms;
+      ms.ws = ws.data();
+      ms.cfg = mc;
+      std::memcpy(ws.data() + T::OFF_PKT, pk.data(), (size_t) pk[MP_NWORDS] * 4);
+      ms.runRegion(res);
+      if (res[MR_STATUS] == kMicroClean) ++microClean;
+    }
+  }
+  int microBuildRun(MicroBuildJob& b, MicroJob& a, MicroJob& bj, const MicroConfig& mc) override {
+    const PacketView pv = microBuildView(b, b.slab);
+    buildRunT<MicroA>(b, pv, 0, a, mc);
+    buildRunT<MicroB>(b, pv, b.nA, bj, mc);
+    microRegions += a.n + bj.n;
+    stats.launches += 2;
+    return 0;
+  }
 
   int setAlleles(int side, const AlleleTable& t) override { al_copy_[side] = t; al_[side] = &al_copy_[side]; return 0; }
 
@@ -232,6 +266,8 @@ void emul_get_stats(int64_t* out) { for (int i = 0; i < 7; ++i) out[i] = g_stats
 // disableMicro: no thread-per-region kernel; threads: host worker threads; chunk: regions per chunk (0 = automatic)
 void emul_set_engine(int disableMicro, int threads, int chunk) { g_disableMicro = disableMicro; g_threads = threads; g_chunk = chunk; }
 void emul_set_split(int variantsPerSegment) { g_split = variantsPerSegment; }
+int g_deviceBuild = 0;
+void emul_set_device_build(int on) { g_deviceBuild = on; }
 
 int emul_vce_submit(const vce_config* cfg, int32_t n_seq, const vce_sequence* seqs, vce_sequence_result* results) {
   EmulBackend be;
@@ -244,6 +280,7 @@ int emul_vce_submit(const vce_config* cfg, int32_t n_seq, const vce_sequence* se
   opt.disableMicro = g_disableMicro != 0;
   opt.chunkRegions = g_chunk;
   opt.splitSegment = g_split;
+  opt.deviceBuild = g_deviceBuild != 0;
   int rc;
   {
     Engine en(&be, &pool, opt);

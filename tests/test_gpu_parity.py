@@ -77,6 +77,41 @@ def test_cuda_genome_slice_all_modes(engine, oracle):
         compare_results(oracle.submit(CONFIGS[name], seqs, threads=8), engine.submit(CONFIGS[name], seqs), seqs, what=name)
 
 
+@pytest.fixture()
+def device_build():
+    """vce_submit packs the packets on the device (k_build) from wholesale copies of the caller's arrays."""
+    old = os.environ.get("VCE_DEVICE_BUILD")
+    os.environ["VCE_DEVICE_BUILD"] = "1"
+    yield
+    if old is None:
+        del os.environ["VCE_DEVICE_BUILD"]
+    else:
+        os.environ["VCE_DEVICE_BUILD"] = old
+
+
+@pytest.mark.parametrize("cfg_name", sorted(CONFIGS))
+def test_cuda_device_build_matches_oracle_on_fuzz(engine, oracle, device_build, cfg_name):
+    cfg = CONFIGS[cfg_name]
+    seqs = []
+    for seed in range(40):
+        seqs += fuzz_batch(seed, n_seq=4)
+    seqs += synth.make_pair(2_000_000, n_chrom=2)
+    compare_results(oracle.submit(cfg, seqs), engine.submit(cfg, seqs), seqs, what="device build " + cfg_name)
+
+
+def test_cuda_device_build_genome_slice(engine, oracle, device_build):
+    seqs = synth.make_pair(300_000_000, n_chrom=24)
+    for name in ("default", "squash", "twopass"):
+        want = oracle.submit(CONFIGS[name], seqs, threads=8)
+        for rep in range(2):
+            compare_results(want, engine.submit(CONFIGS[name], seqs), seqs, what="device build %s rep %d" % (name, rep))
+
+
+def test_cuda_device_build_golden(engine, fixtures, device_build):
+    for name in SCENARIOS:
+        assert check_scenario(engine, fixtures[name]), name
+
+
 def test_cuda_repeated_runs_are_identical(engine, oracle):
     """Determinism: the same batch gives bit-identical results on every call (chunks, streams and re-runs race-free)."""
     seqs = synth.make_pair(60_000_000, n_chrom=24)
