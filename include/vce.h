@@ -220,6 +220,10 @@ int  vce_job_stats(const vce_job* job, int64_t* n_launches, double* device_ms, d
    device ms of the whole run (CUDA events on the job's stream), variants searched by that largest launch. */
 int  vce_job_stats_ex(const vce_job* job, double* out, int32_t n);
 
+/* Diagnostics of the calling thread's last vce_submit, out[0..n): kernel launches, H2D bytes, D2H bytes, regions,
+   regions settled by the warp-per-region kernels, best-first iterations. */
+int  vce_submit_stats(double* out, int32_t n);
+
 /* RocContainer accumulate + sort + cumulative scan on the device. */
 int vce_roc(const vce_roc_in* in, vce_roc_out* out);
 /* Same, also reporting host->device and kernel milliseconds (CUDA events) and the number of kernel launches. */

@@ -189,6 +189,14 @@ int vce_job_stats_ex(const vce_job* job, double* out, int32_t n) {
   return VCE_OK;
 }
 
+static thread_local double t_submitStats[6] = {0, 0, 0, 0, 0, 0};
+
+int vce_submit_stats(double* out, int32_t n) {
+  if (!out) return fail(VCE_ERR_BAD_ARGUMENT, "null argument");
+  for (int i = 0; i < n && i < 6; ++i) out[i] = t_submitStats[i];
+  return VCE_OK;
+}
+
 int vce_submit(const vce_config* cfg, int32_t n_seq, const vce_sequence* seqs, vce_sequence_result* results) {
   if (!cfg || !results || n_seq < 0 || (n_seq > 0 && !seqs)) return fail(VCE_ERR_BAD_ARGUMENT, "null argument");
   int rc = VCE_OK;
@@ -198,6 +206,11 @@ int vce_submit(const vce_config* cfg, int32_t n_seq, const vce_sequence* seqs, v
   if (const char* e = std::getenv("VCE_DEVICE_BUILD")) c->engine->options().deviceBuild = std::atoi(e) != 0;   // contexts are pooled
   rc = c->engine->run(*cfg, n_seq, seqs, results);
   const std::string msg = rc ? c->engine->error() : std::string();
+  {
+    const vce::SearchStats& s = c->backend->stats;
+    t_submitStats[0] = (double) s.launches; t_submitStats[1] = (double) s.h2dBytes; t_submitStats[2] = (double) s.d2hBytes;
+    t_submitStats[3] = (double) s.regions; t_submitStats[4] = (double) s.escalated; t_submitStats[5] = (double) s.iterations;
+  }
   release(c);
   if (rc) return fail(rc, msg.empty() ? std::string("one or more sequences reported an error") : msg);
   return VCE_OK;

@@ -37,7 +37,7 @@ struct EngineOptions {
   int chunkRegions = 0;        // regions per chunk, 0 = automatic
   int splitSegment = 1 << 16;  // variants per segment of the parallel region split
   bool sortPackets = true;     // hand the packets of a chunk to the kernel grouped by shape class (lock-step lanes)
-  bool deviceBuild = false;    // vce_submit: pack the packets on the device from wholesale copies of the caller's arrays
+  bool deviceBuild = true;     // vce_submit: pack the packets on the device from wholesale copies of the caller's arrays
 };
 
 class Engine {

@@ -266,7 +266,7 @@ void emul_get_stats(int64_t* out) { for (int i = 0; i < 7; ++i) out[i] = g_stats
 // disableMicro: no thread-per-region kernel; threads: host worker threads; chunk: regions per chunk (0 = automatic)
 void emul_set_engine(int disableMicro, int threads, int chunk) { g_disableMicro = disableMicro; g_threads = threads; g_chunk = chunk; }
 void emul_set_split(int variantsPerSegment) { g_split = variantsPerSegment; }
-int g_deviceBuild = 0;
+int g_deviceBuild = 1;   // the product default
 void emul_set_device_build(int on) { g_deviceBuild = on; }
 
 int emul_vce_submit(const vce_config* cfg, int32_t n_seq, const vce_sequence* seqs, vce_sequence_result* results) {

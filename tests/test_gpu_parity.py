@@ -77,11 +77,11 @@ def test_cuda_genome_slice_all_modes(engine, oracle):
         compare_results(oracle.submit(CONFIGS[name], seqs, threads=8), engine.submit(CONFIGS[name], seqs), seqs, what=name)
 
 
-@pytest.fixture()
-def device_build():
-    """vce_submit packs the packets on the device (k_build) from wholesale copies of the caller's arrays."""
+@pytest.fixture(params=[1, 0], ids=["device_build", "host_build"])
+def device_build(request):
+    """vce_submit packs the packets on the device (k_build, the default) or in the host digest (VCE_DEVICE_BUILD=0)."""
     old = os.environ.get("VCE_DEVICE_BUILD")
-    os.environ["VCE_DEVICE_BUILD"] = "1"
+    os.environ["VCE_DEVICE_BUILD"] = str(request.param)
     yield
     if old is None:
         del os.environ["VCE_DEVICE_BUILD"]
@@ -90,16 +90,16 @@ def device_build():
 
 
 @pytest.mark.parametrize("cfg_name", sorted(CONFIGS))
-def test_cuda_device_build_matches_oracle_on_fuzz(engine, oracle, device_build, cfg_name):
+def test_cuda_packet_build_modes_match_oracle_on_fuzz(engine, oracle, device_build, cfg_name):
     cfg = CONFIGS[cfg_name]
     seqs = []
     for seed in range(40):
         seqs += fuzz_batch(seed, n_seq=4)
     seqs += synth.make_pair(2_000_000, n_chrom=2)
-    compare_results(oracle.submit(cfg, seqs), engine.submit(cfg, seqs), seqs, what="device build " + cfg_name)
+    compare_results(oracle.submit(cfg, seqs), engine.submit(cfg, seqs), seqs, what="packet build mode %s %s" % (os.environ["VCE_DEVICE_BUILD"], cfg_name))
 
 
-def test_cuda_device_build_genome_slice(engine, oracle, device_build):
+def test_cuda_packet_build_modes_genome_slice(engine, oracle, device_build):
     seqs = synth.make_pair(300_000_000, n_chrom=24)
     for name in ("default", "squash", "twopass"):
         want = oracle.submit(CONFIGS[name], seqs, threads=8)
@@ -107,7 +107,7 @@ def test_cuda_device_build_genome_slice(engine, oracle, device_build):
             compare_results(want, engine.submit(CONFIGS[name], seqs), seqs, what="device build %s rep %d" % (name, rep))
 
 
-def test_cuda_device_build_golden(engine, fixtures, device_build):
+def test_cuda_packet_build_modes_golden(engine, fixtures, device_build):
     for name in SCENARIOS:
         assert check_scenario(engine, fixtures[name]), name
 

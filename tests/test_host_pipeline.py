@@ -157,25 +157,29 @@ def test_results_do_not_depend_on_threads_chunks_or_the_small_kernel(emul, oracl
         emul.lib.emul_set_engine(0, 3, 0)
 
 
-def test_device_side_packet_building_is_exact(emul, oracle):
-    """vce_submit on sorted inputs packs the packets from wholesale copies of the caller's arrays (vce_packet.h is the one
-    source for the host digest and the builder kernel): every configuration, fuzz (unsorted inputs fall back to the host
-    digest), genome-like pairs, chunks down to one region."""
+def test_host_and_device_side_packet_building_are_exact(emul, oracle):
+    """vce_submit on sorted inputs packs the packets from wholesale copies of the caller's arrays (the product default;
+    vce_packet.h is the one source for the host digest and the builder kernel), staged jobs / settle retries / unsorted
+    inputs use the host digest: both modes, every configuration, fuzz, genome-like pairs, chunks down to one region."""
     batches = [synth.make_pair(1_500_000, n_chrom=3), fuzz_batch(77, n_seq=5) + fuzz_batch(78, n_seq=5)]
     try:
-        emul.lib.emul_set_device_build(1)
-        for name in ("default", "twopass", "squash", "phased", "allele_gt", "small_budget"):
-            for seqs in batches:
-                compare_results(oracle.submit(CONFIGS[name], seqs), emul.submit(CONFIGS[name], seqs), seqs, what="device build " + name)
-        seqs = batches[0] + batches[1]
-        want = oracle.submit(CONFIGS["default"], seqs)
-        for threads, chunk in ((1, 1), (3, 7), (4, 64), (2, 1000)):
-            emul.lib.emul_set_engine(0, threads, chunk)
-            compare_results(want, emul.submit(CONFIGS["default"], seqs), seqs, what="device build threads %d chunk %d" % (threads, chunk))
-        st = emul_stats(emul)
-        assert st["micro_regions"] > 0.5 * st["regions"]
+        for mode in (1, 0):
+            emul.lib.emul_set_device_build(mode)
+            for name in ("default", "twopass", "squash", "phased", "allele_gt", "small_budget"):
+                for seqs in batches:
+                    compare_results(oracle.submit(CONFIGS[name], seqs), emul.submit(CONFIGS[name], seqs), seqs,
+                                    what="device build %d %s" % (mode, name))
+            seqs = batches[0] + batches[1]
+            want = oracle.submit(CONFIGS["default"], seqs)
+            for threads, chunk in ((1, 1), (3, 7), (4, 64), (2, 1000)):
+                emul.lib.emul_set_engine(0, threads, chunk)
+                compare_results(want, emul.submit(CONFIGS["default"], seqs), seqs,
+                                what="device build %d threads %d chunk %d" % (mode, threads, chunk))
+            emul.lib.emul_set_engine(0, 3, 0)
+            st = emul_stats(emul)
+            assert st["micro_regions"] > 0.5 * st["regions"]
     finally:
-        emul.lib.emul_set_device_build(0)
+        emul.lib.emul_set_device_build(1)
         emul.lib.emul_set_engine(0, 3, 0)
 
 
