@@ -293,6 +293,7 @@ struct MicroChunkDesc {
   uint8_t* results;
   int n;
   int first;   // global index of the chunk's first region within the launch
+  const uint32_t* order;   // optional: position in the launch order -> packet index (grouped by shape class)
 };
 struct MicroParams {
   MicroChunkDesc one;            // single-chunk launch
@@ -304,6 +305,7 @@ struct MicroParams {
 };
 constexpr int kMicroThreads = 64;
 constexpr uint32_t kNoPacket = 0xffffffffu;   // offsets[] entry of a region the builder could not pack
+constexpr int kClassBins = 0x8000;             // shape classes (microPacketClass is 15 bits)
 
 // Device-side digest (vce_packet.h): one thread packs one region's packet from the uploaded slices of the caller's arrays.
 struct BuildParams {
@@ -313,6 +315,7 @@ struct BuildParams {
   const uint8_t* windows;
   uint8_t* packets;           // [n * stride]
   uint32_t* offsets;          // [n] packet offset in 4-byte words, kNoPacket when the region does not fit
+  uint32_t* keys;             // optional [n]: shape class of each packet (kClassBins - 1 for the rejected ones)
   int n, stride;
 };
 template <class T>
@@ -327,6 +330,49 @@ __global__ void __launch_bounds__(128) k_build(const __grid_constant__ BuildPara
     bytes = microBuildPacket<T>(p.pv, g, winStart, winLen, nextStart, p.windows + p.winOff[q], out);
   }
   p.offsets[q] = bytes > 0 ? (uint32_t) (((size_t) q * p.stride) >> 2) : kNoPacket;
+  if (p.keys != nullptr) p.keys[q] = bytes > 0 ? microPacketClass(out) : (uint32_t) (kClassBins - 1);
+}
+
+// Counting sort of one chunk's packets by shape class, one block: order[] lists the packet indices class by class, so
+// that the 32 regions a warp of k_micro takes together behave alike (the host digest does the same for staged jobs).
+constexpr int kOrderThreads = 1024;
+__global__ void __launch_bounds__(kOrderThreads) k_class_order(const uint32_t* __restrict__ keys, uint32_t* __restrict__ order, int n) {
+  extern __shared__ uint32_t hist[];   // kClassBins counters, then one partial sum per warp
+  uint32_t* warpSum = hist + kClassBins;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < kClassBins; i += kOrderThreads) hist[i] = 0;
+  __syncthreads();
+  for (int q = tid; q < n; q += kOrderThreads) atomicAdd(&hist[keys[q]], 1u);
+  __syncthreads();
+  // exclusive scan: every thread owns kClassBins / kOrderThreads consecutive bins
+  constexpr int per = kClassBins / kOrderThreads;
+  uint32_t local = 0;
+  for (int i = 0; i < per; ++i) local += hist[tid * per + i];
+  uint32_t incl = local;
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+    if ((tid & 31) >= d) incl += v;
+  }
+  if ((tid & 31) == 31) warpSum[tid >> 5] = incl;
+  __syncthreads();
+  if (tid < 32) {
+    const uint32_t w = warpSum[tid];
+    uint32_t wi = w;
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, wi, d);
+      if (tid >= d) wi += v;
+    }
+    warpSum[tid] = wi - w;   // exclusive
+  }
+  __syncthreads();
+  uint32_t run = warpSum[tid >> 5] + incl - local;
+  for (int i = 0; i < per; ++i) {
+    const uint32_t c = hist[tid * per + i];
+    hist[tid * per + i] = run;
+    run += c;
+  }
+  __syncthreads();
+  for (int q = tid; q < n; q += kOrderThreads) order[atomicAdd(&hist[keys[q]], 1u)] = (uint32_t) q;
 }
 
 template <class T>
@@ -356,7 +402,8 @@ __global__ void __launch_bounds__(kMicroThreads) k_micro(const __grid_constant__
         }
         c = p.table[lo];
       }
-      const int q = r - c.first;
+      int q = r - c.first;
+      if (c.order != nullptr) q = (int) __ldg(c.order + q);
       const uint32_t off = __ldg(c.offsets + q);
       resOut = c.results + (size_t) q * T::RES_BYTES;
       if (off == kNoPacket) {
@@ -460,6 +507,8 @@ class CudaBackend : public Backend {
     maxSmemOptin_ = maxSmem;
     CUDA_TRY(cudaFuncSetAttribute(k_search<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
     CUDA_TRY(cudaFuncSetAttribute(k_search<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (4096 + 1024) * kFastWarps));
+    CUDA_TRY(cudaFuncSetAttribute(k_class_order, cudaFuncAttributeMaxDynamicSharedMemorySize, (kClassBins + 32) * (int) sizeof(uint32_t)));
+    if (const char* e = std::getenv("VCE_CLASS_ORDER")) classOrder_ = std::atoi(e) != 0;
     CUDA_TRY(cudaFuncSetAttribute(k_micro<MicroA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMicroThreads * MicroA::WS_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(k_micro<MicroB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMicroThreads * MicroB::WS_BYTES));
     for (int i = 0; i < kMicroLanes; ++i) CUDA_TRY(cudaStreamCreateWithPriority(&mStream_[i], cudaStreamNonBlocking, prHigh));
@@ -906,7 +955,7 @@ class CudaBackend : public Backend {
     MicroParams mp;
     std::memset(&mp, 0, sizeof(mp));
     mp.one = MicroChunkDesc{static_cast<const uint8_t*>(j.dPackets), static_cast<const uint32_t*>(j.dOffsets),
-                            static_cast<uint8_t*>(j.dResults), j.n, 0};
+                            static_cast<uint8_t*>(j.dResults), j.n, 0, nullptr};
     mp.table = nullptr;
     mp.nChunks = 1;
     mp.total = j.n;
@@ -935,7 +984,7 @@ class CudaBackend : public Backend {
     for (size_t i = 0; i < jobs.size(); ++i) {
       MicroJob& j = *jobs[i];
       table[i] = MicroChunkDesc{static_cast<const uint8_t*>(j.dPackets), static_cast<const uint32_t*>(j.dOffsets),
-                                static_cast<uint8_t*>(j.dResults), j.n, total};
+                                static_cast<uint8_t*>(j.dResults), j.n, total, nullptr};
       total += j.n;
     }
     const int pc = jobs[0]->cls & 1;
@@ -989,6 +1038,8 @@ class CudaBackend : public Backend {
     MicroJob* jobs[2] = {&ja, &jb};
     const int strides[2] = {(MicroA::PKT_MAX + 15) & ~15, (MicroB::PKT_MAX + 15) & ~15};
     void* dSlab = nullptr;
+    uint32_t* dKeys = nullptr;
+    uint32_t* dOrder = nullptr;
     int lane = 0;
     {
       std::lock_guard<std::mutex> lk(mMu_);
@@ -1002,6 +1053,11 @@ class CudaBackend : public Backend {
         j.dOffsets = devAlloc((size_t) j.n * 4);
         j.dResults = devAlloc((size_t) j.n * j.resBytes);
         j.lane = lane;
+        if (c == 0 && j.n > kOrderMin && classOrder_) {
+          dKeys = static_cast<uint32_t*>(devAlloc((size_t) j.n * 4));
+          dOrder = static_cast<uint32_t*>(devAlloc((size_t) j.n * 4));
+          if (!dKeys || !dOrder) { err_ = "out of device memory for region packets"; return VCE_ERR_CUDA; }
+        }
         if ((int) mEvents_.size() <= mNextEvent_) {
           cudaEvent_t e;
           if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { err_ = "cudaEventCreate failed"; return VCE_ERR_CUDA; }
@@ -1030,16 +1086,22 @@ class CudaBackend : public Backend {
         bp.windows = base + b.windows;
         bp.packets = static_cast<uint8_t*>(j.dPackets);
         bp.offsets = static_cast<uint32_t*>(j.dOffsets);
+        bp.keys = c == 0 ? dKeys : nullptr;
         bp.n = j.n;
         bp.stride = strides[c];
         const int blocks = (j.n + 127) / 128;
         if (c == 0) k_build<MicroA><<<blocks, 128, 0, st>>>(bp);
         else k_build<MicroB><<<blocks, 128, 0, st>>>(bp);
         CUDA_TRY(cudaGetLastError());
+        if (c == 0 && dKeys != nullptr) {
+          k_class_order<<<1, kOrderThreads, (kClassBins + 32) * sizeof(uint32_t), st>>>(dKeys, dOrder, j.n);
+          CUDA_TRY(cudaGetLastError());
+        }
         MicroParams mp;
         std::memset(&mp, 0, sizeof(mp));
         mp.one = MicroChunkDesc{static_cast<const uint8_t*>(j.dPackets), static_cast<const uint32_t*>(j.dOffsets),
-                                static_cast<uint8_t*>(j.dResults), j.n, 0};
+                                static_cast<uint8_t*>(j.dResults), j.n, 0, nullptr};
+        if (c == 0) mp.one.order = dOrder;
         mp.table = nullptr;
         mp.nChunks = 1;
         mp.total = j.n;
@@ -1087,7 +1149,7 @@ class CudaBackend : public Backend {
       MicroJob& j = *pend[i].job;
       CUDA_TRY(cudaStreamWaitEvent(st, pend[i].built, 0));
       table[i] = MicroChunkDesc{static_cast<const uint8_t*>(j.dPackets), static_cast<const uint32_t*>(j.dOffsets),
-                                static_cast<uint8_t*>(j.dResults), j.n, total};
+                                static_cast<uint8_t*>(j.dResults), j.n, total, nullptr};
       total += j.n;
     }
     CUDA_TRY(mTableC_[1].ensure(table.size()));
@@ -1111,6 +1173,8 @@ class CudaBackend : public Backend {
     ++stats.launches;
     return VCE_OK;
   }
+  static constexpr int kOrderMin = 256;   // smaller chunks are not worth the ordering launch
+  bool classOrder_ = true;
   struct PendingB { MicroJob* job; cudaEvent_t built; };
   std::vector<PendingB> pendingB_;
   int microWait(MicroJob& j) override {

@@ -485,33 +485,6 @@ PacketView Engine::packetView(const PassCtx& pc, int k) const {
   return pv;
 }
 
-// Shape class of a packet: regions of one class take the same branches in the search, so the packets of a chunk are
-// handed to the kernel grouped by class -- the lanes of a warp (32 consecutive packets) then run in lock step.
-static inline uint32_t packetClass(const uint8_t* pk) {
-  const int cC = pk[MP_COUNTS] & 0xf, bC = pk[MP_COUNTS] >> 4;
-  const uint8_t* al = pk + MP_VARS + (cC + bC) * MV_BYTES;
-  uint32_t key = (uint32_t) (cC | (bC << 4));
-  const uint8_t* v = pk + MP_VARS;
-  uint32_t sig[16] = {0};
-  for (int i = 0; i < cC + bC && i < 16; ++i, v += MV_BYTES) {
-    const int a0 = v[MV_A0], a1 = v[MV_A1];
-    const uint32_t l0 = a0 == kMicroNoAllele ? 3u : std::min<uint32_t>(al[a0 * MA_BYTES + MA_LEN], 2u);
-    const uint32_t l1 = a1 == kMicroNoAllele ? 3u : std::min<uint32_t>(al[a1 * MA_BYTES + MA_LEN], 2u);
-    const uint32_t span = std::min<uint32_t>((uint32_t) (v[MV_END] - v[MV_START]), 3u);
-    const uint32_t het = v[MV_GT0] != v[MV_GT1] ? 1u : 0u;
-    const uint32_t ph = v[MV_FLAGS] & 1u;
-    sig[i] = l0 | (l1 << 2) | (span << 4) | (het << 6) | (ph << 7);
-    key = key * 257u + sig[i];
-  }
-  if (cC == 1 && bC == 1) {
-    const uint8_t* vc = pk + MP_VARS;
-    const uint8_t* vb = vc + MV_BYTES;
-    const uint32_t same = (vc[MV_START] == vb[MV_START] && vc[MV_END] == vb[MV_END] && sig[0] == sig[1]) ? 1u : 0u;
-    key = key * 2u + same;
-  }
-  return key & 0x7fffu;
-}
-
 static std::atomic<long long> g_tBuild(0), g_tCopy(0), g_tUpload(0);
 static inline long long nowNs() {
   return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -636,7 +609,7 @@ int Engine::buildChunk(PassCtx& pc, Chunk& ch, int worker, bool launch) {
       cnt.assign(0x8000 + 1, 0);
       keys.resize((size_t) np[c]);
       for (int q = 0; q < np[c]; ++q) {
-        keys[q] = packetClass(pk + (size_t) so[c][q] * 4);
+        keys[q] = microPacketClass(pk + (size_t) so[c][q] * 4);
         ++cnt[keys[q] + 1];
       }
       for (int kx = 0; kx < 0x8000; ++kx) cnt[kx + 1] += cnt[kx];   // first output index of every class
@@ -1100,16 +1073,17 @@ int Engine::execute() {
     }
     if (failed.load()) return failed.load();
     std::vector<int64_t> iters(pool_->threads(), 0);
-    pool_->parallelFor((int) pc.chunks.size(), [&](int t, int worker) {
-      Chunk& ch = pc.chunks[t];
-      for (int c = 0; c < 2; ++c) {
-        if (ch.job[c].n > 0) {
-          const int r = be_->microWait(ch.job[c]);
-          if (r) { failed.store(r); return; }
-        }
-      }
-      decodeChunk(pc, ch, iters[worker]);
-    });
+    // the MicroA records of every chunk first: the MicroB-shaped regions may still be in their one late launch
+    for (int c = 0; c < 2; ++c) {
+      pool_->parallelFor((int) pc.chunks.size(), [&](int t, int worker) {
+        Chunk& ch = pc.chunks[t];
+        if (ch.job[c].n == 0) return;
+        const int r = be_->microWait(ch.job[c]);
+        if (r) { failed.store(r); return; }
+        if (c == 0) decodeJob<MicroA>(pc, ch.seq, ch.job[0], ch.pktRegion[0], iters[worker]);
+        else decodeJob<MicroB>(pc, ch.seq, ch.job[1], ch.pktRegion[1], iters[worker]);
+      });
+    }
     if (failed.load()) { err_ = be_->lastError(); return failed.load(); }
     be_->microCollect();
     tm.lap("wait + decode");

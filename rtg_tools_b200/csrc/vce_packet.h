@@ -172,5 +172,36 @@ VCE_HD int microBuildPacket(const PacketView& pv, const RegRange& g, int32_t win
   return bytes;
 }
 
+// Shape class of a packet (15 bits): regions of one class take the same branches in the search, so packets are handed to
+// the kernel grouped by class -- the lanes of a warp (32 consecutive packets) then run in lock step.
+VCE_HD uint32_t microPacketClass(const uint8_t* pk) {
+  const int cC = pk[MP_COUNTS] & 0xf, bC = pk[MP_COUNTS] >> 4;
+  const uint8_t* al = pk + MP_VARS + (cC + bC) * MV_BYTES;
+  uint32_t key = (uint32_t) (cC | (bC << 4));
+  const uint8_t* v = pk + MP_VARS;
+  uint32_t sig0 = 0, sig1 = 0;
+  for (int i = 0; i < cC + bC && i < 16; ++i, v += MV_BYTES) {
+    const int a0 = v[MV_A0], a1 = v[MV_A1];
+    uint32_t l0 = 3u, l1 = 3u;
+    if (a0 != kMicroNoAllele) { l0 = al[a0 * MA_BYTES + MA_LEN]; l0 = l0 < 2u ? l0 : 2u; }
+    if (a1 != kMicroNoAllele) { l1 = al[a1 * MA_BYTES + MA_LEN]; l1 = l1 < 2u ? l1 : 2u; }
+    uint32_t span = (uint32_t) (v[MV_END] - v[MV_START]);
+    span = span < 3u ? span : 3u;
+    const uint32_t het = v[MV_GT0] != v[MV_GT1] ? 1u : 0u;
+    const uint32_t ph = v[MV_FLAGS] & 1u;
+    const uint32_t sig = l0 | (l1 << 2) | (span << 4) | (het << 6) | (ph << 7);
+    if (i == 0) sig0 = sig;
+    if (i == 1) sig1 = sig;
+    key = key * 257u + sig;
+  }
+  if (cC == 1 && bC == 1) {
+    const uint8_t* vc = pk + MP_VARS;
+    const uint8_t* vb = vc + MV_BYTES;
+    const uint32_t same = (vc[MV_START] == vb[MV_START] && vc[MV_END] == vb[MV_END] && sig0 == sig1) ? 1u : 0u;
+    key = key * 2u + same;
+  }
+  return key & 0x7fffu;
+}
+
 }  // namespace vce
 #endif
