@@ -328,7 +328,8 @@ void Engine::splitAll(PassCtx& pc) {
   ensureSize(pc.rr, (size_t) nSeq_);
   ensureSize(pc.rs, (size_t) nSeq_);
   ensureSize(pc.rcls, (size_t) nSeq_);
-  struct Seg { int seq, i, ie, j, je; long maxEndLocal, carry; bool continues; std::vector<RegRange> out; };
+  // (the segments' output vectors persist across calls and keep their capacity: no allocation, no page faults)
+  struct Seg { int seq, i, ie, j, je; long maxEndLocal, carry; bool continues; std::vector<RegRange>* outp; };
   std::vector<Seg> segs;
   std::vector<int> segFirst(nSeq_ + 1, 0);
   const int per = std::max(1, opt_.splitSegment);
@@ -355,14 +356,16 @@ void Engine::splitAll(PassCtx& pc) {
         nj = std::max(nj, pj);
       }
       if (sgi == nSeg || ni > pi || nj > pj) {
-        Seg sg{k, C.first + pi, C.first + ni, B.first + pj, B.first + nj, LONG_MIN, LONG_MIN, false, {}};
-        segs.push_back(std::move(sg));
+        Seg sg{k, C.first + pi, C.first + ni, B.first + pj, B.first + nj, LONG_MIN, LONG_MIN, false, nullptr};
+        segs.push_back(sg);
         pi = ni;
         pj = nj;
       }
     }
   }
   segFirst[nSeq_] = (int) segs.size();
+  if (splitOut_.size() < segs.size()) splitOut_.resize(segs.size());
+  for (size_t t = 0; t < segs.size(); ++t) { segs[t].outp = &splitOut_[t].v; splitOut_[t].v.clear(); }
   // phase 1: largest variant end per segment
   pool_->parallelFor((int) segs.size(), [&](int t, int) {
     Seg& sg = segs[t];
@@ -383,9 +386,9 @@ void Engine::splitAll(PassCtx& pc) {
   // phase 2: split every segment with the carried maximum end
   pool_->parallelFor((int) segs.size(), [&](int t, int) {
     Seg& sg = segs[t];
-    sg.out.reserve((size_t) std::max(sg.ie - sg.i, sg.je - sg.j) + 16);
+    sg.outp->reserve((size_t) std::max(sg.ie - sg.i, sg.je - sg.j) + 16);
     const bool firstOfSeq = t == segFirst[sg.seq];
-    splitSlice(pc, sg.i, sg.ie, sg.j, sg.je, sg.carry, sg.out, firstOfSeq ? nullptr : &sg.continues);
+    splitSlice(pc, sg.i, sg.ie, sg.j, sg.je, sg.carry, *sg.outp, firstOfSeq ? nullptr : &sg.continues);
   });
   // phase 3: stitch per sequence
   pool_->parallelFor(nSeq_, [&](int k, int) {
@@ -393,17 +396,18 @@ void Engine::splitAll(PassCtx& pc) {
     out.clear();
     if (!pc.shortCircuit[k]) {
       size_t total = 0;
-      for (int t = segFirst[k]; t < segFirst[k + 1]; ++t) total += segs[t].out.size();
+      for (int t = segFirst[k]; t < segFirst[k + 1]; ++t) total += segs[t].outp->size();
       out.reserve(total + 1);
       for (int t = segFirst[k]; t < segFirst[k + 1]; ++t) {
         const Seg& sg = segs[t];
+        const std::vector<RegRange>& so = *sg.outp;
         size_t from = 0;
-        if (sg.continues && !out.empty() && !sg.out.empty()) {
-          out.back().cCount += sg.out[0].cCount;
-          out.back().bCount += sg.out[0].bCount;
+        if (sg.continues && !out.empty() && !so.empty()) {
+          out.back().cCount += so[0].cCount;
+          out.back().bCount += so[0].bCount;
           from = 1;
         }
-        out.insert(out.end(), sg.out.begin() + (long) from, sg.out.end());
+        out.insert(out.end(), so.begin() + (long) from, so.end());
       }
     }
     pc.rs[k].resize(out.size());
@@ -422,7 +426,8 @@ int Engine::regionStartPos(const PassCtx& pc, int k, int j) const {
 }
 
 void Engine::planChunks(PassCtx& pc) {
-  pc.chunks.clear();
+  // (chunk objects persist across calls: their packet -> region lists keep their capacity)
+  size_t nChunks = 0;
   size_t total = 0;
   for (int k = 0; k < nSeq_; ++k) total += pc.rr[k].size();
   int per = opt_.chunkRegions;
@@ -433,13 +438,18 @@ void Engine::planChunks(PassCtx& pc) {
   for (int k = 0; k < nSeq_; ++k) {
     const int n = (int) pc.rr[k].size();
     for (int r0 = 0; r0 < n; r0 += per) {
-      Chunk ch;
+      if (pc.chunks.size() <= nChunks) pc.chunks.emplace_back();
+      Chunk& ch = pc.chunks[nChunks++];
       ch.seq = k;
       ch.r0 = r0;
       ch.r1 = std::min(n, r0 + per);
-      pc.chunks.push_back(std::move(ch));
+      ch.list.clear();
+      ch.transient = false;
+      ch.variants = ch.variantsA = 0;
+      for (int c = 0; c < 2; ++c) { ch.job[c] = MicroJob(); ch.pktRegion[c].clear(); }
     }
   }
+  pc.chunks.resize(nChunks);
 }
 
 // ------------------------------------------------------------------------------------------- packets
@@ -891,7 +901,7 @@ int Engine::buildChunkDevice(PassCtx& pc, Chunk& ch, int worker) {
   for (int c = 0; c < 2; ++c) {
     const std::vector<int32_t>& list = ch.pktRegion[c];
     for (size_t i = 0; i < list.size(); ++i, ++q) {
-      if (i + 8 < list.size()) __builtin_prefetch(tmpl + wsv[c][i + 8]);
+      if (i + 24 < list.size()) __builtin_prefetch(tmpl + wsv[c][i + 24]);
       regs[q] = rrk[list[i]];
       winOff[q] = (uint32_t) wo;
       std::memcpy(wins + wo, tmpl + wsv[c][i], (size_t) wlv[c][i]);
@@ -1594,13 +1604,6 @@ int Engine::settle(PassCtx& pc, WideBatch& early) {
 // PhasingEvaluator.countMisphasings, src/com/rtg/vcf/eval/PhasingEvaluator.java:55-142, on the flat pass-0 results.
 namespace {
 struct VSum { int start; bool phased, included, phase; };
-bool groupInPhase(const std::vector<VSum>& g) {  // :143-155
-  if (g.empty()) return true;
-  if (!g[0].phased) return false;
-  const bool ph = g[0].phase;
-  for (const VSum& v : g) if (!v.phased || v.phase != ph) return false;
-  return true;
-}
 }  // namespace
 
 static inline void pickRow(int kind, int H, int gtPloidy, const vce_variants& in, int ii, int row, int8_t* ids, uint8_t* original);
@@ -1655,13 +1658,16 @@ void Engine::phasing(int k, const std::vector<int32_t>& sync, int32_t out[3]) co
   bool baseIsPhased = false, basePhase = false, callIsPhased = false, callPhase = false;
   bool haveCall = false, haveBase = false;
   VSum call{0, false, false, false}, base{0, false, false, false};
-  std::vector<VSum> bsec, csec;
+  // One pass per sync region, no lists: the baseline section only matters through "all phased the same way" (:143-155)
+  // and its phase, and that is known before the calls of the section are looked at.
   for (int point : sync) {
-    bsec.clear();
-    csec.clear();
+    int nb = 0;
+    bool inPhase = true, phase = false;
     do {
       if (haveBase && base.start < point) {
-        bsec.push_back(base);
+        if (nb == 0) { inPhase = base.phased; phase = base.phase; }
+        else if (!base.phased || base.phase != phase) inPhase = false;
+        ++nb;
         haveBase = baseline.hasNext();
         if (haveBase) base = baseline.next();
       }
@@ -1670,38 +1676,40 @@ void Engine::phasing(int k, const std::vector<int32_t>& sync, int32_t out[3]) co
         if (haveBase) base = baseline.next();
       }
     } while (haveBase && base.start < point);
+    bool transition = false;
+    if (inPhase) {
+      if (!baseIsPhased) callIsPhased = false;
+      if (nb > 0) {
+        transition = basePhase != phase;
+        baseIsPhased = true;
+        basePhase = phase;
+      }
+    }
     do {
-      if (haveCall) csec.push_back(call);
+      if (haveCall) {
+        const VSum& c = call;
+        if (!inPhase) {
+          if (c.phased) ++unph;
+        } else {
+          if (!c.phased) {
+            callIsPhased = false;
+          } else if (!callIsPhased) {
+            callIsPhased = true;
+            callPhase = c.phase;
+          } else {
+            const bool callTransition = c.phase != callPhase;
+            if (c.included && !(callTransition == transition)) { ++mis; callPhase = c.phase; }
+            else if (c.included) { ++correct; callPhase = c.phase; }
+          }
+          transition = false;
+        }
+      }
       haveCall = calls.hasNext();
       if (haveCall) call = calls.next();
     } while (haveCall && call.start < point);
-    if (!groupInPhase(bsec)) {
-      for (const VSum& s : csec) if (s.phased) ++unph;
+    if (!inPhase) {
       baseIsPhased = false;
       callIsPhased = false;
-      continue;
-    }
-    bool transition = false;
-    if (!baseIsPhased) callIsPhased = false;
-    for (const VSum& b : bsec) {
-      if (b.phased) {
-        if (basePhase != b.phase) transition = true;
-        baseIsPhased = true;
-      }
-      basePhase = b.phase;
-    }
-    for (const VSum& c : csec) {
-      if (!c.phased) {
-        callIsPhased = false;
-      } else if (!callIsPhased) {
-        callIsPhased = true;
-        callPhase = c.phase;
-      } else {
-        const bool callTransition = c.phase != callPhase;
-        if (c.included && !(callTransition == transition)) { ++mis; callPhase = c.phase; }
-        else if (c.included) { ++correct; callPhase = c.phase; }
-      }
-      transition = false;
     }
   }
   out[0] = mis; out[1] = correct; out[2] = unph;
@@ -1911,28 +1919,30 @@ int Engine::finish(vce_sequence_result* results) {
     return na != nb ? na > nb : a < b;
   });
   // sync points of every pass, gathered per block of regions (Path.getSyncPoints with the Path.java:293 de-duplication)
-  syncParts_.clear();
+  // (the part objects persist across calls: their vectors keep their capacity, a steady-state call allocates nothing)
   const int rblock = 1 << 15;
+  size_t nSyncParts = 0;
   for (int p = 0; p < 2; ++p) {
-    syncPartFirst_[p].assign((size_t) nSeq_ + 1, (int) syncParts_.size());
+    syncPartFirst_[p].assign((size_t) nSeq_ + 1, (int) nSyncParts);
     if (p >= cfg_.n_passes) continue;
     for (int k = 0; k < nSeq_; ++k) {
-      syncPartFirst_[p][k] = (int) syncParts_.size();
+      syncPartFirst_[p][k] = (int) nSyncParts;
       const int n = pass_[0].shortCircuit[k] ? 0 : (int) pass_[p].rs[k].size();
       for (int r0 = 0; r0 < n; r0 += rblock) {
-        SyncPart sp;
+        if (syncParts_.size() <= nSyncParts) syncParts_.emplace_back();
+        SyncPart& sp = syncParts_[nSyncParts++];
         sp.pass = p; sp.seq = k; sp.r0 = r0; sp.r1 = std::min(n, r0 + rblock); sp.err = 0;
-        syncParts_.push_back(std::move(sp));
+        sp.v.clear();
       }
     }
-    syncPartFirst_[p][nSeq_] = (int) syncParts_.size();
+    syncPartFirst_[p][nSeq_] = (int) nSyncParts;
   }
   // One task list.  First the region blocks, largest sequence first; the worker that finishes the last block of one of
   // the few LARGEST sequences goes on with that sequence's join and phasing counts (a sequential state machine,
   // PhasingEvaluator.java:55-142: the longest chains have to start early).  The other sequences' joins follow as tasks
   // of their own at the end of the list, so that the block work is never starved of workers.
   std::vector<int> partOrder;
-  partOrder.reserve(syncParts_.size());
+  partOrder.reserve(nSyncParts);
   std::vector<std::atomic<int>> remaining(nSeq_);
   std::vector<uint8_t> live(nSeq_, 0), inlineClose(nSeq_, 0);
   for (int k = 0; k < nSeq_; ++k) remaining[k].store(0);

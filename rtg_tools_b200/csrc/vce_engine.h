@@ -189,8 +189,10 @@ class Engine {
   std::mutex arenaMu_;
   std::vector<HostBlock> arena_;
   std::vector<size_t> arenaMarks_;
-  struct SyncPart { int pass, seq, r0, r1; int err; std::vector<int32_t> v; };
+  struct alignas(64) SyncPart { int pass, seq, r0, r1; int err; std::vector<int32_t> v; };
   std::vector<SyncPart> syncParts_;               // sync points per block of regions (assembly)
+  struct alignas(64) SplitOut { std::vector<RegRange> v; };   // one cache line each: neighbours are filled concurrently
+  std::vector<SplitOut> splitOut_;                // regions per segment of the parallel split
   std::vector<int> syncPartFirst_[2];             // [pass][seq] first part of the sequence
   std::vector<std::vector<int32_t>> seqSync_[2];   // [pass][seq] sync points (assembly)
   std::vector<std::vector<uint8_t>> seqDec1_[2];   // [side][seq] pass-2 decision by input index
