@@ -65,15 +65,16 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, interval_ms=250):
         self.index = index
+        self.interval_ms = int(interval_ms)
         self.proc = None
         self.lines = []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", str(self.interval_ms)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -189,6 +190,7 @@ def main():
     ap.add_argument("--config", default="default", choices=["default", "squash", "twopass"],
                     help="engine configuration: default (diploid, single pass), squash (--squash-ploidy), twopass (ga4gh / annotate)")
     ap.add_argument("--roc-calls", type=int, default=0, help="also time K4 alone on this many synthetic scored calls (BASELINE configs[4])")
+    ap.add_argument("--pair", type=int, default=None, help="N=1 only: evaluate the sample pair that rank PAIR of a weak-scaling run would get (diagnostics)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roc", action="store_true")
     args = ap.parse_args()
@@ -222,7 +224,8 @@ def main():
         torch.cuda.synchronize()
 
     t_gen = time.perf_counter()
-    seqs, quals, desc, seq_ids, n_seq_total = build_workload(args.workload, rank, world, args.scaling, args.total_bp)
+    pair_rank = args.pair if (args.pair is not None and world == 1) else rank
+    seqs, quals, desc, seq_ids, n_seq_total = build_workload(args.workload, pair_rank, world, args.scaling, args.total_bp)
     nv = n_variants(seqs)
     log("[rank %d] workload %s: %d sequences, %d variants (generated in %.1fs)" % (rank, args.workload, len(seqs), nv,
                                                                                time.perf_counter() - t_gen))
@@ -235,7 +238,8 @@ def main():
     job = eng.job(cfg, seqs)
     # nvidia-smi needs a few hundred ms before its first line and a timed region is ~150 ms: the sampler runs from the
     # warm-up steps (the same kernels, the same load) through both timed regions
-    sampler = ClockSampler(local_rank)
+    # (several pollers on one box contend in the driver: the more ranks, the slower each polls)
+    sampler = ClockSampler(local_rank, 250 if world == 1 else 125 * world)
     sampler.start()
     for _ in range(max(args.warmup, 3)):
         job.run()
