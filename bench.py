@@ -21,7 +21,6 @@ all-reduce).  Default scaling is weak: rank r evaluates sample pair r of the coh
 layout, different sample seeds); `--scaling strong` shards ONE pair's chromosomes over the ranks by LPT.
 """
 import argparse
-import ctypes
 import json
 import os
 import subprocess
@@ -278,10 +277,7 @@ def main():
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     clocks = sampler.stop()
-    sub = (ctypes.c_double * 6)()   # launches, H2D bytes, D2H bytes, ... of this thread's last vce_submit
-    eng.lib.lib.vce_submit_stats.restype = ctypes.c_int
-    eng.lib.lib.vce_submit_stats.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.c_int32]
-    eng.lib.lib.vce_submit_stats(sub, 6)
+    sub_stats = eng.submit_stats()   # launches, H2D bytes, D2H bytes, ... of this thread's last vce_submit
     e2e_results = capi.Library.unpack(packed[2], packed[3], packed[4])
 
     # max over ranks / totals
@@ -420,7 +416,8 @@ def main():
         "sync_regions_per_s": total_regions / (ms_per_step * 1e-3),
         "wall_ms_per_step": wall_per_step,
         "e2e": {"value": total_variants / (e2e_ms * 1e-3), "unit": "variants/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": int(sub[1]), "d2h_bytes_per_step": int(sub[2]), "gpu_launches_per_step": int(sub[0])},
+                "h2d_bytes_per_step": sub_stats["h2d_bytes"], "d2h_bytes_per_step": sub_stats["d2h_bytes"],
+                "gpu_launches_per_step": sub_stats["launches"]},
         "gpu_launches": int(total_launches),
         "clocks": clocks,
         "roofline": roofline,

@@ -1067,7 +1067,8 @@ class CudaBackend : public Backend {
         j.evHandle = mEvents_[j.event];
         if (!j.dPackets || !j.dOffsets || !j.dResults) { err_ = "out of device memory for region packets"; return VCE_ERR_CUDA; }
         stats.d2hBytes += (int64_t) j.n * j.resBytes;
-        ++stats.launches;
+        // k_build, and for MicroA the search launch (+ the class ordering); the MicroB search is counted by the flush
+        stats.launches += c == 0 ? (dKeys != nullptr ? 3 : 2) : 1;
       }
       stats.h2dBytes += (int64_t) b.slabBytes;
     }

@@ -103,6 +103,8 @@ class Engine:
                                       C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         lib.vce_job_stats_ex.restype = C.c_int
         lib.vce_job_stats_ex.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int32]
+        lib.vce_submit_stats.restype = C.c_int
+        lib.vce_submit_stats.argtypes = [C.POINTER(C.c_double), C.c_int32]
         rc = lib.vce_init(device)
         if rc != 0:
             raise EngineUnavailable("vce_init(%d) failed: %s %s" % (device, capi.ERR_NAMES.get(rc, rc), self.lib.last_error()))
@@ -110,6 +112,13 @@ class Engine:
 
     def submit(self, cfg: capi.Config, seqs: List[capi.Sequence]) -> List[capi.SequenceResult]:
         return self.lib.submit(cfg, seqs)
+
+    def submit_stats(self) -> dict:
+        """Diagnostics of the calling thread's last submit(): launches, H2D / D2H bytes, regions, iterations."""
+        out = (C.c_double * 6)()
+        self.lib.lib.vce_submit_stats(out, 6)
+        return dict(launches=int(out[0]), h2d_bytes=int(out[1]), d2h_bytes=int(out[2]), regions=int(out[3]),
+                    escalated=int(out[4]), iterations=int(out[5]))
 
     def job(self, cfg, seqs) -> Job:
         return Job(self, cfg, seqs)
