@@ -1382,43 +1382,57 @@ int Engine::wideFinish(PassCtx& pc, WideBatch& wb, std::vector<int>& statusOut) 
     }
     pc.warns.swap(keep);
   }
+  // pass 1 (serial, sequential reads): statuses, the rare bookkeeping of unsettled regions, where each settled region's
+  // sync points go; pass 2 (parallel): the scattered writes into the per-region / per-variant arrays
+  std::vector<int32_t> syncIdx(ids.size(), -1);
+  size_t syncAt = pc.wideSync.size();
   for (size_t q = 0; q < ids.size(); ++q) {
-    const int k = ids[q].seq, j = ids[q].j;
-    const RegRange& g = pc.rr[k][j];
-    RegRes& s = pc.rs[k][j];
     const RegionResult& r = out[q];
-    const RegionDesc& d = wb.descs[q];
-    const int tier = wb.tier[q];
     statusOut[q] = r.status;
     be_->stats.iterations += r.iterations;
-    if (r.status != kRegionClean && r.status != kRegionFinished) {
-      Rare& ra = pc.rare[key(k, j)];
-      ra.tier = tier;
+    if (r.status == kRegionClean || r.status == kRegionFinished) {
+      syncIdx[q] = (int32_t) syncAt;
+      syncAt += (size_t) r.nSync;
+    } else {
+      Rare& ra = pc.rare[key(ids[q].seq, ids[q].j)];
+      ra.tier = wb.tier[q];
       ra.lastStatus = r.status;
     }
-    if (r.status == kRegionClean || r.status == kRegionFinished) {
-      s.state = RS_WIDE_DONE;
-      s.flags = (uint8_t) ((r.usedPrefix ? 1 : 0) | (r.status == kRegionFinished ? 2 : 0) | (tier << 2));
-      s.lastId = r.lastBaseAlleleId == kPrefixEmpty ? (int8_t) kMicroNoLastId : (int8_t) r.lastBaseAlleleId;
-      s.nSync = 0;
-      s.ext.idx = (int32_t) pc.wideSync.size();
-      s.ext.n = r.nSync;
-      pc.wideSync.insert(pc.wideSync.end(), syncBuf.begin() + wb.syncOff[q], syncBuf.begin() + wb.syncOff[q] + r.nSync);
-      for (int i = 0; i < g.cCount; ++i) {
-        pc.decision[0][g.cFirst + i] = pd.side[0].decision[d.cFirst + i];
-        pc.weight[g.cFirst + i] = pd.side[0].weight[d.cFirst + i];
-      }
-      for (int i = 0; i < g.bCount; ++i) pc.decision[1][g.bFirst + i] = pd.side[1].decision[d.bFirst + i];
-    } else if (r.status == kRegionErrNull) {
-      s.state = RS_ERR_NULL;
-    } else if (r.status == kRegionErrMove) {
-      s.state = RS_ERR_MOVE;
-    } else if (r.status == kRegionErrOrder) {
-      s.state = RS_ERR_ORDER;
-    } else {
-      s.state = RS_RESIDUAL;
-    }
   }
+  pc.wideSync.resize(syncAt);
+  const size_t blockX = 512;
+  pool_->parallelFor((int) ((ids.size() + blockX - 1) / blockX), [&](int t, int) {
+    for (size_t q = (size_t) t * blockX; q < std::min(ids.size(), (size_t) (t + 1) * blockX); ++q) {
+      const int k = ids[q].seq, j = ids[q].j;
+      const RegRange& g = pc.rr[k][j];
+      RegRes& s = pc.rs[k][j];
+      const RegionResult& r = out[q];
+      const RegionDesc& d = wb.descs[q];
+      const int tier = wb.tier[q];
+      if (r.status == kRegionClean || r.status == kRegionFinished) {
+        s.state = RS_WIDE_DONE;
+        s.flags = (uint8_t) ((r.usedPrefix ? 1 : 0) | (r.status == kRegionFinished ? 2 : 0) | (tier << 2));
+        s.lastId = r.lastBaseAlleleId == kPrefixEmpty ? (int8_t) kMicroNoLastId : (int8_t) r.lastBaseAlleleId;
+        s.nSync = 0;
+        s.ext.idx = syncIdx[q];
+        s.ext.n = r.nSync;
+        std::copy(syncBuf.begin() + wb.syncOff[q], syncBuf.begin() + wb.syncOff[q] + r.nSync, pc.wideSync.begin() + syncIdx[q]);
+        for (int i = 0; i < g.cCount; ++i) {
+          pc.decision[0][g.cFirst + i] = pd.side[0].decision[d.cFirst + i];
+          pc.weight[g.cFirst + i] = pd.side[0].weight[d.cFirst + i];
+        }
+        for (int i = 0; i < g.bCount; ++i) pc.decision[1][g.bFirst + i] = pd.side[1].decision[d.bFirst + i];
+      } else if (r.status == kRegionErrNull) {
+        s.state = RS_ERR_NULL;
+      } else if (r.status == kRegionErrMove) {
+        s.state = RS_ERR_MOVE;
+      } else if (r.status == kRegionErrOrder) {
+        s.state = RS_ERR_ORDER;
+      } else {
+        s.state = RS_RESIDUAL;
+      }
+    }
+  });
   for (const WarnRec& w : warns) {
     if (w.region < 0 || (size_t) w.region >= ids.size()) continue;
     const int st = statusOut[w.region];
