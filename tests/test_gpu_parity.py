@@ -185,6 +185,13 @@ def test_cuda_pathfinder_known_answers(engine, name):
     check_path_case(engine, name)
 
 
+@pytest.mark.parametrize("name", sorted(__import__("test_unit_vectors").PHASING_CASES))
+def test_cuda_phasing_evaluator_known_answers(engine, name):
+    """PhasingEvaluatorTest.java:142-262 (expected correct / unphasable / mis-phasing counts) through the CUDA engine."""
+    from test_unit_vectors import check_phasing_case
+    check_phasing_case(engine, name)
+
+
 def test_cuda_concurrent_submits(engine, oracle):
     """vce_submit is re-entrant: the reference calls SequenceEvaluator.run() from several pool workers
     (VcfEvalTask.java:131-137).  Two host threads submit different batches at the same time."""

@@ -165,6 +165,48 @@ def test_pathfinder_known_answers(oracle, name):
     check_path_case(emul_library(), name)
 
 
+# PhasingEvaluatorTest.java:142-262 -- SNVs G>T on the first 200 bases of VcfEvalTaskTest.REF (VcfEvalTaskTest.java:498),
+# UnphasedOrientor(2) on both sides; (baseline, calls) as (pos1, GT), expected (correct, unphasable, misphasings)
+PHASING_REF = ("CTTTCTCTTTCTTTCTTTCTCTCTTTCCATCCTTCTTTCTTTCTTTCTCTTTCTTTCTTTCTCTCTTTCCATCCTTCTTTCTTTCTTTCCTTCCTTCTTTCTTTCCTTCCTTTCTTT"
+               "CTTTTTCTTTCTTTCTCTTTCCTTTTTCTTTCTTTCTCTCTCCCTCTTTCTTTTTTTTTTGAGTACCTAAAATCTACTCTCTT")
+PHASING_CASES = {
+    "testPhasing": ([(9, "1|0"), (13, "0|1")], [(9, "1|0"), (13, "1|0")], (0, 0, 1)),
+    "testDoublePhasing": ([(9, "1|0"), (13, "0|1"), (16, "0|1")], [(9, "1|0"), (13, "1|0"), (16, "0|1")], (0, 0, 2)),
+    "testPhasingUnphased": ([(9, "1|0"), (13, "0|1"), (16, "0|1"), (19, "0|1"), (22, "0|1"), (25, "1|0")],
+                            [(9, "1|0"), (13, "1|0"), (16, "1|0"), (19, "0/1"), (22, "1|0"), (25, "1|0")], (1, 0, 2)),
+    "testPhasingUnphased2": ([(9, "1|0"), (13, "0|1"), (16, "0|1"), (19, "0|1"), (22, "0|1"), (25, "1|0")],
+                             [(9, "1|0"), (13, "1|0"), (16, "1|0"), (19, "0/1"), (22, "0|1"), (25, "1|0")], (2, 0, 1)),
+    "testCluster": ([(9, "1|0"), (13, "0|1"), (15, "0|1"), (17, "0|1"), (19, "0|1"), (25, "1|0")],
+                    [(9, "0|1"), (13, "1|0"), (15, "1|0"), (17, "0|1"), (19, "1|0"), (25, "0|1")], (3, 0, 2)),
+    "testUnphaseable": ([(9, "1|0"), (13, "0/1")], [(9, "1|0"), (13, "1|0")], (0, 1, 0)),
+    "testFalsePositive": ([(9, "1|0"), (16, "0|1")], [(9, "1|0"), (13, "1|0"), (16, "1|0")], (0, 0, 1)),
+}
+_DNA = {"N": 0, "A": 1, "C": 2, "G": 3, "T": 4}
+
+
+def _phasing_side(vs):
+    out = []
+    for i, (pos1, gt) in enumerate(vs):
+        p0 = pos1 - 1
+        alleles = [None, (p0, p0 + 1, bytes([_DNA["G"]])), (p0, p0 + 1, bytes([_DNA["T"]]))]   # missing, REF G, ALT T
+        out.append({"id": i + 1, "alleles": alleles, "gt": [int(gt[0]), int(gt[2])], "phased": gt[1] == "|", "status": 0})
+    return capi.VariantSide.from_variants(out, 2)
+
+
+def check_phasing_case(engine, name):
+    base, calls, (correct, unph, mis) = PHASING_CASES[name]
+    template = np.array([_DNA[c] for c in PHASING_REF], np.uint8)
+    res = engine.submit(capi.Config(), [capi.Sequence("10", template, _phasing_side(base), _phasing_side(calls))])[0]
+    assert res.error == 0
+    assert list(res.phasing) == [mis, correct, unph], "%s: (mis, correct, unphasable) = %s" % (name, list(res.phasing))
+
+
+@pytest.mark.parametrize("name", sorted(PHASING_CASES))
+def test_phasing_evaluator_known_answers(oracle, name):
+    check_phasing_case(oracle, name)
+    check_phasing_case(emul_library(), name)
+
+
 def test_roc_container_known_answers(oracle):
     """RocContainerTest.java:45-85."""
     score = np.array([0.1, 0.1, 0.2, 0.2, 0.1, 0.3])
