@@ -10,6 +10,7 @@ from helpers import emul_library
 from rtg_tools_b200 import capi
 
 T9 = [1, 1, 1, 1, 1, 1, 2, 1, 1]
+T9H = [1, 1, 1, 1, 1, 3, 2, 1, 1]
 
 # HaplotypePlaybackTest.java:42-149 -- (template, [(start0, end0, bases)], expected bases or None = "Out of order" exception).
 # MockVariant coordinates are one-based there; createOrientedVariant(v, true/false).allele(0) picks plus / minus.
@@ -20,6 +21,10 @@ PLAYBACK = [
     (T9, [(1, 1, [3, 3, 3]), (1, 2, [2])], [1, 3, 3, 3, 2, 1, 1, 1, 1, 2, 1, 1]),                     # testInsertPriorToSnp
     (T9, [(0, 1, [2, 4, 4]), (3, 4, [3, 1]), (4, 5, [4]), (5, 6, []), (6, 7, [3])], [2, 4, 4, 1, 1, 3, 1, 4, 3, 1, 1]),  # testMoreComplexAlternate
     ([1, 4, 1, 1, 1], [(1, 2, [3]), (2, 2, [2, 2])], [1, 3, 2, 2, 1, 1, 1]),                          # testBackToBack
+    # HalfPathTest.java:59-117 -- the haplotypes a HalfPath replays after include() (the excluded variant leaves no trace)
+    (T9H, [(0, 1, [2]), (3, 3, [3]), (5, 6, [])], [2, 1, 1, 3, 1, 1, 2, 1, 1]),                      # testNextBase
+    (T9H, [(0, 1, [1]), (3, 3, [3]), (5, 6, [])], [1, 1, 1, 3, 1, 1, 2, 1, 1]),                      # testHetero, haplotype 0
+    (T9H, [(0, 1, [2]), (3, 3, [4, 3]), (5, 6, [])], [2, 1, 1, 4, 3, 1, 1, 2, 1, 1]),                # testHetero, haplotype 1
 ]
 
 
