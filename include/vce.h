@@ -84,7 +84,8 @@ enum {
  */
 typedef struct vce_variants {
   int32_t        n;             /* number of variants                              */
-  int32_t        gt_ploidy;     /* entries per variant in gt[]; 0 = no GT (AllAlts factory) */
+  int32_t        gt_ploidy;     /* entries per variant in gt[]; 0 = no GT (AllAlts factory).  Must be the same for every
+                                   non-empty sequence of a batch on this side (else VCE_ERR_BAD_ARGUMENT) */
   const int32_t* id;            /* [n] VariantId.getId(): 1-based record ordinal, strictly ascending */
   const uint8_t* phased;        /* [n] Variant.isPhased()                          */
   const uint8_t* status_in;     /* [n] pre-set status bits (only OUTSIDE_EVAL is meaningful) or NULL */

@@ -72,11 +72,16 @@ void release(Context* c) {
   if (g_device < 0 || g_free.size() >= 4) { delete c; return; }
   g_free.emplace_back(c);
 }
+
+// A context whose call failed may still have work in flight on its streams, or a sticky CUDA error: it does not go back
+// into the pool (the backend's destructor waits for the device before it frees anything).
+void discard(Context* c) { delete c; }
 }  // namespace
 
 struct vce_job {
   Context* ctx = nullptr;
   double executeMs = 0;
+  bool failed = false;
 };
 
 extern "C" {
@@ -123,7 +128,7 @@ int vce_job_create(const vce_config* cfg, int32_t n_seq, const vce_sequence* seq
   rc = c->engine->prepare(*cfg, n_seq, seqs, true);
   if (rc) {
     const std::string msg = c->engine->error();
-    release(c);
+    discard(c);
     return fail(rc, msg);
   }
   vce_job* j = new vce_job();
@@ -142,7 +147,7 @@ int vce_job_run(vce_job* job) {
   be->timerStart();
   const int rc = job->ctx->engine->execute();
   job->executeMs = be->timerStopMs();
-  if (rc) return fail(rc, job->ctx->engine->error());
+  if (rc) { job->failed = true; return fail(rc, job->ctx->engine->error()); }
   return VCE_OK;
 }
 
@@ -155,7 +160,7 @@ int vce_job_fetch(vce_job* job, vce_sequence_result* results) {
 
 void vce_job_destroy(vce_job* job) {
   if (!job) return;
-  if (job->ctx) release(job->ctx);
+  if (job->ctx) { if (job->failed) discard(job->ctx); else release(job->ctx); }
   delete job;
 }
 
@@ -211,7 +216,10 @@ int vce_submit(const vce_config* cfg, int32_t n_seq, const vce_sequence* seqs, v
     t_submitStats[0] = (double) s.launches; t_submitStats[1] = (double) s.h2dBytes; t_submitStats[2] = (double) s.d2hBytes;
     t_submitStats[3] = (double) s.regions; t_submitStats[4] = (double) s.escalated; t_submitStats[5] = (double) s.iterations;
   }
-  release(c);
+  // per-sequence errors (results[k].error) are ordinary outcomes; anything else leaves the context in an unknown state
+  bool perSequence = false;
+  if (rc) for (int32_t k = 0; k < n_seq; ++k) if (results[k].error == rc) perSequence = true;
+  if (rc && !perSequence) discard(c); else release(c);
   if (rc) return fail(rc, msg.empty() ? std::string("one or more sequences reported an error") : msg);
   return VCE_OK;
 }

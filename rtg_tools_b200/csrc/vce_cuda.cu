@@ -26,6 +26,7 @@
 #include "vce_micro.h"
 #include "vce_orient.h"
 #include "vce_search.h"
+#include "vce_cta.h"
 
 namespace vce {
 
@@ -283,6 +284,165 @@ __global__ void __launch_bounds__(kFastWarps * 32, GENERAL ? VCE_GEN_MINB : 1) k
   }
 }
 
+// ------------------------------------------------------------------------------------------------ K2 / K3, one region per CTA
+// Warp policy of the CTA kernel (vce_cta.h): frontier blocks move between the CTA's HBM arena and its shared-memory cache
+// as 1-D bulk TMA copies (cp.async.bulk, completion on an mbarrier for loads, bulk groups for stores); tma = 0 keeps plain
+// cooperative 16-byte copies (diagnostics).
+struct DeviceWarpMove : DeviceWarp {
+  uint32_t mbar;     // shared-memory address of the CTA's mbarrier
+  uint32_t phase;
+  int tma;
+  __device__ __forceinline__ void loadBlock(uint32_t* dst, const uint32_t* src, int bytes) {
+    if (tma) {
+      const uint32_t d = (uint32_t) __cvta_generic_to_shared(dst);
+      // the slot was last touched through the generic proxy; earlier bulk stores of this block have to be complete
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane() == 0) {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"((uint32_t) bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(d), "l"(src), "r"((uint32_t) bytes), "r"(mbar) : "memory");
+      }
+      uint32_t done = 0;
+      while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(mbar), "r"(phase) : "memory");
+      }
+      phase ^= 1u;
+    } else {
+      const uint4* s4 = reinterpret_cast<const uint4*>(src);
+      uint4* d4 = reinterpret_cast<uint4*>(dst);
+      __syncwarp();
+      for (int i = lane(); i < (bytes >> 4); i += 32) d4[i] = s4[i];
+    }
+  }
+  __device__ __forceinline__ void storeBlock(uint32_t* dst, const uint32_t* src, int bytes) {
+    if (tma) {
+      const uint32_t s = (uint32_t) __cvta_generic_to_shared(src);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes of every lane, before the async read
+      __syncwarp();
+      if (lane() == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst), "r"(s), "r"((uint32_t) bytes) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    } else {
+      const uint4* s4 = reinterpret_cast<const uint4*>(src);
+      uint4* d4 = reinterpret_cast<uint4*>(dst);
+      for (int i = lane(); i < (bytes >> 4); i += 32) d4[i] = s4[i];   // lane i <-> chunk i, as loadBlock reads them back
+    }
+  }
+  // The shared-memory sources of earlier storeBlock calls may be overwritten after this.
+  __device__ __forceinline__ void storeWait() {
+    if (tma) {
+      if (lane() == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    __syncwarp();
+  }
+};
+
+struct CtaParams {
+  SearchParams sp;
+  CtaShape shape;
+  long long arenaWordsPerCta;
+  int tma;
+};
+
+__global__ void __launch_bounds__(32) k_cta(const __grid_constant__ CtaParams cp) {
+  extern __shared__ __align__(16) int32_t smem[];
+  const SearchParams& p = cp.sp;
+  const int lane = threadIdx.x & 31;
+  const int kcWords = (int) ((sizeof(RegionConst) + 15) / 16) * 4;
+  RegionConst* kc = reinterpret_cast<RegionConst*>(smem);
+  CtaSearch<DeviceWarpMove> cs(kc);
+  cs.shape = cp.shape;
+  uint32_t* rest = cs.carve(reinterpret_cast<uint32_t*>(smem + kcWords));
+  uint64_t* mbarP = reinterpret_cast<uint64_t*>(rest);
+  rest += 4;
+  uint8_t* tabS = reinterpret_cast<uint8_t*>(rest);
+  uint8_t* winS = tabS + cp.shape.tabBytes;
+  cs.w.mbar = (uint32_t) __cvta_generic_to_shared(mbarP);
+  cs.w.phase = 0;
+  cs.w.tma = cp.tma;
+  cs.rs.w = cs.w;
+  if (lane == 0) {
+    kc->cfg = p.cfg;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(cs.w.mbar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  cs.rs.warnOut = p.warnScratch + (size_t) blockIdx.x * kWarnPerRegion;
+  cs.rs.warnCap = kWarnPerRegion;
+  cs.rs.maxChildren = p.maxChildren;
+
+  while (true) {
+    int r = 0;
+    if (lane == 0) r = atomicAdd(p.counter, 1);
+    r = __shfl_sync(0xffffffffu, r, 0);
+    if (r >= p.nRegs) break;
+    __syncwarp();
+    if (lane == 0) {
+      kc->R = p.regs[r];
+      kc->S[0] = p.S[0];
+      kc->S[1] = p.S[1];
+    }
+    __syncwarp();
+    bool ok = true;
+    {
+      PathLayout PL;
+      ok = ctaLayout(PL, p.H, kc->R.cCount, kc->R.bCount, kc->R.decBits ? kc->R.decBits : 4);
+      if (lane == 0) kc->L = PL;
+    }
+    cs.rs.regionId = p.regionBase + r;
+    // the allele ranks take the head of the table area; the region's tables follow (or stay in HBM when they do not fit)
+    const int nSl = kc->R.cSlotN + kc->R.bSlotN;
+    const int rankBytes = (nSl * 2 + 15) & ~15;
+    if (rankBytes > cp.shape.tabBytes) ok = false;
+    cs.rank[0] = reinterpret_cast<uint16_t*>(tabS);
+    cs.rank[1] = cs.rank[0] + kc->R.cSlotN;
+    __syncwarp();
+    int st = kRegionOverflow;
+    int resultSlot = -1;
+    cs.rs.usedPrefix = 0; cs.rs.nWarn = 0; cs.rs.maxFrontier = 0; cs.rs.totalIters = 0;
+    if (ok) {
+      stageTables(cs.rs, p.S, p.H, tabS + rankBytes, cp.shape.tabBytes - rankBytes, lane);
+      const uint8_t* gw = p.windows + cs.rs.R.winOff;
+      if (cs.rs.R.winLen > 0 && cs.rs.R.winLen <= cp.shape.winBytes) {   // reference window -> shared memory (the buffer is 16 B aligned and padded)
+        cs.w.loadBlock(reinterpret_cast<uint32_t*>(winS), reinterpret_cast<const uint32_t*>(gw), (cs.rs.R.winLen + 15) & ~15);
+        cs.rs.win = winS;
+      } else {
+        cs.rs.win = gw;
+      }
+      __syncwarp();
+      cs.bindArena(p.arena + (size_t) blockIdx.x * cp.arenaWordsPerCta, cp.arenaWordsPerCta);
+      cs.computeRanks();
+      st = cs.run(resultSlot);
+    }
+    RegionResult rr;
+    rr.status = st;
+    rr.usedPrefix = cs.rs.usedPrefix;
+    rr.nSync = 0;
+    rr.nWarn = cs.rs.nWarn;
+    rr.lastBaseAlleleId = kPrefixEmpty;
+    rr.maxFrontier = cs.rs.maxFrontier;
+    rr.iterations = cs.rs.totalIters;
+    rr.pad = 0;
+    __syncwarp();
+    if (st == kRegionClean || st == kRegionFinished) {
+      cs.rs.writeResults(resultSlot, p.syncOut + p.syncOff[r], &rr);
+      if (lane == 0 && cs.rs.nWarn > 0) {
+        const int nw = min(cs.rs.nWarn, kWarnPerRegion);
+        const int at = atomicAdd(p.warnCount, nw);
+        for (int i = 0; i < nw; ++i) if (at + i < p.warnCap) p.warns[at + i] = cs.rs.warnOut[i];
+      }
+    }
+    if (lane == 0) p.out[r] = rr;
+    // no bulk copy of this region may still be reading the cache when the next region resets it
+    cs.w.storeWait();
+    __syncwarp();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ K1+K2+K3, one region per thread
 // Thread-per-region search (vce_micro.h).  Every lane owns a shared-memory slice; a lane that settles its region
 // takes the next one (grid-stride), so the warp keeps all lanes busy on "one search iteration" per loop trip while
@@ -446,7 +606,7 @@ __global__ void __launch_bounds__(kMicroThreads) k_micro(const __grid_constant__
     if (e_ != cudaSuccess) {                                                                 \
       char b_[512];                                                                          \
       snprintf(b_, sizeof(b_), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
-      err_ = b_;                                                                             \
+      setErr(b_);                                                                            \
       return VCE_ERR_CUDA;                                                                   \
     }                                                                                        \
   } while (0)
@@ -507,6 +667,9 @@ class CudaBackend : public Backend {
     maxSmemOptin_ = maxSmem;
     CUDA_TRY(cudaFuncSetAttribute(k_search<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
     CUDA_TRY(cudaFuncSetAttribute(k_search<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (4096 + 1024) * kFastWarps));
+    CUDA_TRY(cudaFuncSetAttribute(k_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+    if (const char* e = std::getenv("VCE_MID_KERNEL")) oldMid_ = std::string(e) == "old";   // diagnostics: the round-1 HBM-arena warp kernel
+    if (const char* e = std::getenv("VCE_CTA_TMA")) ctaTma_ = std::atoi(e) != 0;
     CUDA_TRY(cudaFuncSetAttribute(k_class_order, cudaFuncAttributeMaxDynamicSharedMemorySize, (kClassBins + 32) * (int) sizeof(uint32_t)));
     if (const char* e = std::getenv("VCE_CLASS_ORDER")) classOrder_ = std::atoi(e) != 0;
     CUDA_TRY(cudaFuncSetAttribute(k_micro<MicroA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMicroThreads * MicroA::WS_BYTES));
@@ -527,6 +690,9 @@ class CudaBackend : public Backend {
   void destroy() {
     if (!ready_) return;
     cudaSetDevice(device_);
+    // nothing of this backend may still be running when its buffers go (a failed call leaves work in flight)
+    cudaStreamSynchronize(stream_);
+    for (int i = 0; i < kMicroLanes; ++i) if (mStream_[i]) cudaStreamSynchronize(mStream_[i]);
     for (int s = 0; s < 2; ++s) { al_[s].release(); pdev_[0][s].release(); pdev_[1][s].release(); }
     sRegs_.release(); sSyncOff_.release(); sWindows_.release();
     regs_.release(); rres_.release(); syncOff_.release(); syncBuf_.release(); windows_.release(); warns_.release();
@@ -709,6 +875,8 @@ class CudaBackend : public Backend {
     int blocksT[kTierGeneral + 1] = {0}, threadsT[kTierGeneral + 1] = {0};
     size_t smemT[kTierGeneral + 1] = {0};
     SearchParams spT[kTierGeneral + 1];
+    CtaParams cpT[kTierGeneral + 1];
+    bool isCta[kTierGeneral + 1] = {false};
     size_t arenaWords = 0;
     int maxWarps = 0;
     for (int tier = 0; tier <= kTierGeneral; ++tier) {
@@ -718,6 +886,7 @@ class CudaBackend : public Backend {
       const size_t nt = (size_t) (r1 - r0);
       SearchParams& sp = spT[tier];
       std::memset(&sp, 0, sizeof(sp));
+      isCta[tier] = (tier == kTierMid && !oldMid_) || tier == kTierCta;
       sp.regs = regs_.p + r0; sp.nRegs = (int) nt;
       sp.S[0] = sideArrays(0); sp.S[1] = sideArrays(1);
       sp.windows = windows_.p; sp.cfg = sc; sp.out = rres_.p + r0; sp.syncOff = syncOff_.p + r0; sp.syncOut = syncBuf_.p;
@@ -740,7 +909,7 @@ class CudaBackend : public Backend {
         sp.wordsPerWarp = kcWords + preWords + ctlWords + (sp.tabBytes + sp.winSmemBytes) / 4;
         const size_t bytesPerWarp = (size_t) sp.wordsPerWarp * 4;
         int warpsPerBlock = (int) std::min<size_t>(kFastWarps, (size_t) maxSmemOptin_ / bytesPerWarp);
-        if (warpsPerBlock < 1) { err_ = "fast kernel shared memory exceeds the device limit"; return VCE_ERR_CUDA; }
+        if (warpsPerBlock < 1) { setErr("fast kernel shared memory exceeds the device limit"); return VCE_ERR_CUDA; }
         // prefer several smaller blocks per SM over one large one
         if (warpsPerBlock < kFastWarps) warpsPerBlock = std::max(1, (int) ((size_t) maxSmemOptin_ / bytesPerWarp) / 2);
         threads = warpsPerBlock * 32;
@@ -755,13 +924,34 @@ class CudaBackend : public Backend {
           if (perSm < 1) perSm = 1;
           blocks = std::min(need, smCount_ * perSm);
         }
+      } else if (isCta[tier]) {
+        // one region per CTA (vce_cta.h): frontier directory + block cache + work records in shared memory, blocks and
+        // path records in a per-CTA arena
+        CtaParams& cp = cpT[tier];
+        cp.shape = ctaShape(tier);
+        cp.tma = ctaTma_ ? 1 : 0;
+        const int kcWords = (int) ((sizeof(RegionConst) + 15) / 16) * 4;
+        smemBytes = ((size_t) kcWords + (size_t) ctaSmemWords(cp.shape) + 4) * 4;
+        threads = 32;
+        int perSm = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_cta, threads, smemBytes));
+        if (perSm < 1) { setErr("CTA kernel shared memory exceeds the device limit"); return VCE_ERR_CUDA; }
+        const long long mc = sp.maxChildren;
+        const long long pool = std::min<long long>(cp.shape.capacity(), (long long) sc.maxPaths + 1 + mc) + 64;
+        long long words = (ctaArenaWords(cp.shape, cta::kMaxW, pool) + 3) & ~3LL;
+        const long long budgetWords = (long long) (24ull << 30) / 4;  // 24 GB of HBM for search arenas
+        long long ctasWanted = std::min<long long>((long long) nt, (long long) smCount_ * perSm);
+        ctasWanted = std::min(ctasWanted, std::max<long long>(1, budgetWords / words));
+        blocks = (int) ctasWanted;
+        arenaWords = std::max(arenaWords, (size_t) blocks * (size_t) words);
+        cp.arenaWordsPerCta = words;
       } else {
         // per-warp arena sized for the largest record layout in this launch at the full search budget
         long long maxW = 0;
         for (int q = r0; q < r1; ++q) maxW = std::max(maxW, (long long) regs[q].layoutW);
         const long long mc = sp.maxChildren;
         long long capFull = (long long) sc.maxPaths + 1 + mc;
-        if (tier == kTierMid) capFull = std::min<long long>(capFull, kMidCap);
+        if (tier == kTierMid) capFull = std::min<long long>(capFull, kMidCap);   // (only with VCE_MID_KERNEL=old)
         // resident blocks per SM pulling regions from the work queue (registers allow 3 blocks of 8 warps; a 4th
         // queued block evens out the tail)
         static const int bps = std::getenv("VCE_GENERAL_BPS") ? std::max(1, std::atoi(std::getenv("VCE_GENERAL_BPS"))) : 4;
@@ -781,7 +971,7 @@ class CudaBackend : public Backend {
         smemBytes = ((size_t) sp.tabBytes + (size_t) kcWords * 4) * kFastWarps;
       }
       blocksT[tier] = blocks; threadsT[tier] = threads; smemT[tier] = smemBytes;
-      maxWarps = std::max(maxWarps, blocks * (threads / 32));
+      maxWarps = std::max(maxWarps, blocks * std::max(1, threads / 32));
     }
     CUDA_TRY(warnScratch_.ensure((size_t) std::max(1, maxWarps) * kWarnPerRegion));
     if (arenaWords > 0) CUDA_TRY(arena_.ensure(arenaWords));   // shared by the launches below (they run in stream order)
@@ -790,8 +980,14 @@ class CudaBackend : public Backend {
       if (blocksT[tier] == 0) continue;
       spT[tier].warnScratch = warnScratch_.p;
       spT[tier].arena = arena_.p;
-      if (tier >= kTierMid) k_search<true><<<blocksT[tier], threadsT[tier], smemT[tier], stream_>>>(spT[tier]);
-      else k_search<false><<<blocksT[tier], threadsT[tier], smemT[tier], stream_>>>(spT[tier]);
+      if (isCta[tier]) {
+        cpT[tier].sp = spT[tier];
+        k_cta<<<blocksT[tier], threadsT[tier], smemT[tier], stream_>>>(cpT[tier]);
+      } else if (tier >= kTierMid) {
+        k_search<true><<<blocksT[tier], threadsT[tier], smemT[tier], stream_>>>(spT[tier]);
+      } else {
+        k_search<false><<<blocksT[tier], threadsT[tier], smemT[tier], stream_>>>(spT[tier]);
+      }
       CUDA_TRY(cudaGetLastError());
       ++stats.launches;
       ++inFlightLaunches_;
@@ -873,7 +1069,7 @@ class CudaBackend : public Backend {
   void* hostAlloc(size_t bytes) override {
     cudaSetDevice(device_);
     void* p = nullptr;
-    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { err_ = "cudaHostAlloc failed"; return nullptr; }
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { setErr("cudaHostAlloc failed"); return nullptr; }
     return p;
   }
   void hostFree(void* p) override {
@@ -927,14 +1123,14 @@ class CudaBackend : public Backend {
       mNextLane_ = (mNextLane_ + 1) % kMicroLanes;
       if ((int) mEvents_.size() <= mNextEvent_) {
         cudaEvent_t e;
-        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { err_ = "cudaEventCreate failed"; return VCE_ERR_CUDA; }
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { setErr("cudaEventCreate failed"); return VCE_ERR_CUDA; }
         mEvents_.push_back(e);
       }
       j.event = mNextEvent_++;
       j.evHandle = mEvents_[j.event];
       stats.h2dBytes += (int64_t) (j.packetBytes + (size_t) j.n * 4);
     }
-    if (!j.dPackets || !j.dOffsets || !j.dResults) { err_ = "out of device memory for region packets"; return VCE_ERR_CUDA; }
+    if (!j.dPackets || !j.dOffsets || !j.dResults) { setErr("out of device memory for region packets"); return VCE_ERR_CUDA; }
     cudaStream_t st = mStream_[j.lane];
     uploadsPending_.store(true);
     CUDA_TRY(cudaMemcpyAsync(j.dPackets, j.packets, j.packetBytes, cudaMemcpyHostToDevice, st));
@@ -1056,23 +1252,23 @@ class CudaBackend : public Backend {
         if (c == 0 && j.n > kOrderMin && classOrder_) {
           dKeys = static_cast<uint32_t*>(devAlloc((size_t) j.n * 4));
           dOrder = static_cast<uint32_t*>(devAlloc((size_t) j.n * 4));
-          if (!dKeys || !dOrder) { err_ = "out of device memory for region packets"; return VCE_ERR_CUDA; }
+          if (!dKeys || !dOrder) { setErr("out of device memory for region packets"); return VCE_ERR_CUDA; }
         }
         if ((int) mEvents_.size() <= mNextEvent_) {
           cudaEvent_t e;
-          if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { err_ = "cudaEventCreate failed"; return VCE_ERR_CUDA; }
+          if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { setErr("cudaEventCreate failed"); return VCE_ERR_CUDA; }
           mEvents_.push_back(e);
         }
         j.event = mNextEvent_++;
         j.evHandle = mEvents_[j.event];
-        if (!j.dPackets || !j.dOffsets || !j.dResults) { err_ = "out of device memory for region packets"; return VCE_ERR_CUDA; }
+        if (!j.dPackets || !j.dOffsets || !j.dResults) { setErr("out of device memory for region packets"); return VCE_ERR_CUDA; }
         stats.d2hBytes += (int64_t) j.n * j.resBytes;
         // k_build, and for MicroA the search launch (+ the class ordering); the MicroB search is counted by the flush
         stats.launches += c == 0 ? (dKeys != nullptr ? 3 : 2) : 1;
       }
       stats.h2dBytes += (int64_t) b.slabBytes;
     }
-    if (!dSlab) { err_ = "out of device memory for region packets"; return VCE_ERR_CUDA; }
+    if (!dSlab) { setErr("out of device memory for region packets"); return VCE_ERR_CUDA; }
     cudaStream_t st = mStream_[lane];
     CUDA_TRY(cudaMemcpyAsync(dSlab, b.slab, b.slabBytes, cudaMemcpyHostToDevice, st));
     const uint8_t* base = static_cast<const uint8_t*>(dSlab);
@@ -1116,7 +1312,7 @@ class CudaBackend : public Backend {
             std::lock_guard<std::mutex> lk(mMu_);
             if ((int) mEvents_.size() <= mNextEvent_) {
               cudaEvent_t e;
-              if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { err_ = "cudaEventCreate failed"; return VCE_ERR_CUDA; }
+              if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { setErr("cudaEventCreate failed"); return VCE_ERR_CUDA; }
               mEvents_.push_back(e);
             }
             built = mEvents_[mNextEvent_++];
@@ -1174,6 +1370,8 @@ class CudaBackend : public Backend {
     ++stats.launches;
     return VCE_OK;
   }
+  bool oldMid_ = false;   // mid tier through the HBM-arena warp kernel instead of the CTA kernel
+  bool ctaTma_ = true;    // the CTA kernel moves frontier blocks with bulk TMA copies
   static constexpr int kOrderMin = 256;   // smaller chunks are not worth the ordering launch
   bool classOrder_ = true;
   struct PendingB { MicroJob* job; cudaEvent_t built; };
@@ -1187,6 +1385,15 @@ class CudaBackend : public Backend {
   long long lastMicroRegions_ = 0;
 
   const char* lastError() const override { return err_.c_str(); }
+  // worker threads report failures concurrently (microUpload / microBuildRun): the first message is kept
+  void setErr(const char* msg) {
+    std::lock_guard<std::mutex> lk(errMu_);
+    if (err_.empty()) err_ = msg;
+  }
+  void clearErr() {
+    std::lock_guard<std::mutex> lk(errMu_);
+    err_.clear();
+  }
   void timerStart() override {
     cudaSetDevice(device_);
     cudaEventRecord(evT0_, stream_);
@@ -1241,6 +1448,7 @@ class CudaBackend : public Backend {
   int microRefill_ = 32;
   DevBuf<MicroChunkDesc> mTableC_[2];
   std::atomic<bool> uploadsPending_{false};
+  std::mutex errMu_;
   std::string err_;
 };
 

@@ -145,12 +145,24 @@ int Engine::setupPass0() {
     ensureSize(pc.idxStore[side], (size_t) nSeq_);
   }
   int32_t tot[2] = {0, 0};
+  bool havePloidy[2] = {false, false};
   for (int k = 0; k < nSeq_; ++k) {
     const bool sc = seqs_[k].baseline.n == 0 || seqs_[k].calls.n == 0;  // SequenceEvaluator.java:94-97
     pc.shortCircuit[k] = sc ? 1 : 0;
     for (int side = 0; side < 2; ++side) {
       const vce_variants& v = side == 0 ? seqs_[k].calls : seqs_[k].baseline;
-      if (v.n > 0) pc.gtPloidy[side] = std::max(pc.gtPloidy[side], (int) v.gt_ploidy);
+      if (v.n > 0) {
+        // one genotype width per side and batch (the orientation tables and the GT padding are per pass): a mixed
+        // batch, e.g. haploid chrX records beside diploid autosomes, is the caller's to split (VariantFactory.java:170-174
+        // already widens haploid GTs in diploid mode)
+        if (v.gt_ploidy < 0 || v.gt_ploidy > VCE_MAX_PLOIDY) { err_ = "gt_ploidy out of range"; return VCE_ERR_BAD_ARGUMENT; }
+        if (havePloidy[side] && pc.gtPloidy[side] != (int) v.gt_ploidy) {
+          err_ = "gt_ploidy differs between the sequences of one batch";
+          return VCE_ERR_BAD_ARGUMENT;
+        }
+        havePloidy[side] = true;
+        pc.gtPloidy[side] = (int) v.gt_ploidy;
+      }
       SideSeq& s = pc.ss[side][k];
       s.in = &v;
       s.first = tot[side];
@@ -1130,10 +1142,11 @@ int Engine::run(const vce_config& cfg, int32_t nSeq, const vce_sequence* seqs, v
 // grow a large frontier (many variants on one side) directly in the large shared-memory tier, the rest in HBM arenas.
 int Engine::startTier(const PassCtx& pc, const RegRange& g) const {
   if (opt_.forceGeneral) return kTierGeneral;
-  if (pc.H > 2) return kTierMid;
+  if (pc.H > 2) return kTierGeneral;   // the CTA kernel's keys hold two haplotypes per side
   // the frontier grows with the variants on one side (orientations multiply): pick the tier that will hold it
   const int m = std::max(g.cCount, g.bCount);
-  return m <= 3 ? 0 : kTierMid;
+  if (opt_.forceCta) return m >= 10 ? kTierCta : kTierMid;
+  return m <= 3 ? 0 : (m >= 10 ? kTierCta : kTierMid);
 }
 
 // Packs the regions `items` (region, tier) for the warp-per-region kernels and starts them: the variants and alleles of
@@ -1259,7 +1272,7 @@ int Engine::widePack(PassCtx& pc, const std::vector<std::pair<RegKey, int>>& ite
     if (pd.maxOrient[side] + 2 > 255) { err_ = "too many orientations per variant for this engine"; return VCE_ERR_UNSUPPORTED; }
   }
   const int mo = std::max(pd.maxOrient[0], pd.maxOrient[1]);
-  if (1 + mo > FastLimits::kMaxChildren) for (size_t q = 0; q < n; ++q) wb.tier[q] = std::max(wb.tier[q], kTierMid);
+  if (1 + mo > FastLimits::kMaxChildren) for (size_t q = 0; q < n; ++q) wb.tier[q] = kTierGeneral;   // more children than the fixed shapes hold
   for (int t = 0; t <= kTierGeneral + 1; ++t) wb.tierFirst[t] = 0;
   for (size_t q = 0; q < n; ++q) ++wb.tierFirst[wb.tier[q] + 1];
   for (int t = 1; t <= kTierGeneral + 1; ++t) wb.tierFirst[t] += wb.tierFirst[t - 1];
@@ -1270,7 +1283,7 @@ int Engine::widePack(PassCtx& pc, const std::vector<std::pair<RegKey, int>>& ite
       const int k = wb.ids[q].seq, j = wb.ids[q].j;
       const RegRange& g = pc.rr[k][j];
       RegionDesc& d = wb.descs[q];
-      if (wb.tier[q] >= kTierMid) {
+      if (wb.tier[q] >= kTierMid) {   // (the CTA tiers derive their own record layout, vce_cta.h ctaLayout)
         d.qMax = std::max(1, std::max(d.cCount, d.bCount));
         d.decBits = (mo + 2 <= 15) ? 4 : 8;
         PathLayout PL;
@@ -1481,6 +1494,7 @@ int Engine::settle(PassCtx& pc, WideBatch& early) {
     if ((rc = wideFinish(pc, early, st))) return rc;
     for (size_t q = 0; q < early.ids.size(); ++q) all.push_back(std::make_pair(early.ids[q], st[q]));
   }
+  bool settled = false;
   for (int round = 0; round < 100000; ++round) {
     if (!retry.empty()) {
       std::sort(retry.begin(), retry.end(), [](const RegKey& a, const RegKey& b) { return a.seq != b.seq ? a.seq < b.seq : a.j < b.j; });
@@ -1513,8 +1527,9 @@ int Engine::settle(PassCtx& pc, WideBatch& early) {
     }
     if (todo.empty() && all.empty()) {
       // prefix-dependent tie-breaks: re-run the first region per sequence whose assumption was wrong
-      std::vector<int> fix(nSeq_, -1);
-      std::vector<int> fixPrefix(nSeq_, 0);
+      // Every region of a sequence whose assumption does not hold is collected in one round (the scan goes on with the
+      // region's current last allele id; should the re-run change it, the next round's scan catches what follows).
+      std::vector<std::vector<std::pair<int, int>>> fix(nSeq_);   // per sequence: (region, true prefix)
       pool_->parallelFor(nSeq_, [&](int k, int) {
         const RegRes* rs = pc.rs[k].data();
         const int n = (int) pc.rs[k].size();
@@ -1528,24 +1543,25 @@ int Engine::settle(PassCtx& pc, WideBatch& early) {
               const auto it = pc.rare.find(key(k, j));
               if (it != pc.rare.end() && it->second.hasPrefix) assumed = it->second.assumedPrefix;
             }
-            if (assumed != prefix) { fix[k] = j; fixPrefix[k] = prefix; return; }
+            if (assumed != prefix) fix[k].push_back(std::make_pair(j, prefix));
           }
           if (s.lastId != (int8_t) kMicroNoLastId) prefix = s.lastId;
         }
       });
       for (int k = 0; k < nSeq_; ++k) {
-        if (fix[k] < 0) continue;
-        const RegRes& s = pc.rs[k][fix[k]];
-        Rare& ra = pc.rare[key(k, fix[k])];
-        ra.hasPrefix = true;
-        ra.assumedPrefix = fixPrefix[k];
-        unmark(k, fix[k]);
-        int tier = startTier(pc, pc.rr[k][fix[k]]);
-        if (s.state == RS_WIDE_DONE) tier = std::max(tier, (int) (s.flags >> 2) & 3);  // the tier that settled it before
-        todo.push_back(std::make_pair(RegKey{k, fix[k]}, tier));
-        ++be_->stats.prefixReruns;
+        for (const std::pair<int, int>& fx : fix[k]) {
+          const RegRes& s = pc.rs[k][fx.first];
+          Rare& ra = pc.rare[key(k, fx.first)];
+          ra.hasPrefix = true;
+          ra.assumedPrefix = fx.second;
+          unmark(k, fx.first);
+          int tier = startTier(pc, pc.rr[k][fx.first]);
+          if (s.state == RS_WIDE_DONE) tier = std::max(tier, (int) (s.flags >> 2) & 7);  // the tier that settled it before
+          todo.push_back(std::make_pair(RegKey{k, fx.first}, tier));
+          ++be_->stats.prefixReruns;
+        }
       }
-      if (todo.empty()) break;
+      if (todo.empty()) { settled = true; break; }
     }
     // one batch with every tier's regions, then inspect in sequence order so that chains of spilling regions merge
     // front to back
@@ -1611,6 +1627,7 @@ int Engine::settle(PassCtx& pc, WideBatch& early) {
     }
     all.clear();
   }
+  if (!settled) { err_ = "regions left unsettled after the round limit"; return VCE_ERR_CAPACITY; }
   return VCE_OK;
 }
 

@@ -33,6 +33,7 @@ struct EngineOptions {
   int margin = 24;        // reference bases beyond the last variant end of a region (warp-per-region kernels)
   int microMargin = 12;   // same, thread-per-region kernel
   bool forceGeneral = false;   // tests: every region through the large-capacity kernel
+  bool forceCta = false;       // tests: every warp-path region through the CTA kernel
   bool disableMicro = false;   // tests: no thread-per-region kernel
   int chunkRegions = 0;        // regions per chunk, 0 = automatic
   int splitSegment = 1 << 16;  // variants per segment of the parallel region split

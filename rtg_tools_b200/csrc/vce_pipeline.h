@@ -16,6 +16,7 @@
 #include "vce_micro.h"
 #include "vce_packet.h"
 #include "vce_search.h"
+#include "vce_cta.h"
 
 namespace vce {
 
@@ -203,9 +204,14 @@ struct FastShape {
   VCE_HD int slots() const { return cap + 1 + maxChildren; }
   VCE_HD int ordCap() const { return 2 * cap; }
 };
-constexpr int kTierMid = 2;
-constexpr int kTierGeneral = 3;
+constexpr int kTierMid = 2;       // CTA kernel (vce_cta.h), small shape: frontiers up to kMidCap paths
+constexpr int kTierCta = 3;       // CTA kernel, full shape: the reference's own budget (--max-paths 50 000)
+constexpr int kTierGeneral = 4;   // large-capacity warp kernel: whatever the CTA kernel's fixed shapes cannot hold
 constexpr int kMidCap = 2048;
+inline CtaShape ctaShape(int tier) {
+  // nb blocks of up to 128 entries; split blocks stay at least half full: capacity = 64 * (nb - 1) paths
+  return tier == kTierMid ? CtaShape{40, 2, 6144, 512} : CtaShape{832, 3, 10240, 1024};
+}
 inline FastShape fastShape(int tier) {
   switch (tier) {
     case 0: return FastShape{8, 2, 8, 24, 7, 1536};      // ~9 KB per warp

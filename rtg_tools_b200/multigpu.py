@@ -41,40 +41,62 @@ def merge_counts(counts: np.ndarray, device: Optional[torch.device] = None) -> n
     return t.cpu().numpy()
 
 
-def _flag_counts(status: np.ndarray, flags) -> List[int]:
-    """How many status bytes carry each of the single-bit `flags` (two passes per flag, no boolean temporaries)."""
-    return [int(np.count_nonzero(status & np.uint8(f))) for f in flags]
+def call_classes(status: np.ndarray, weight: np.ndarray):
+    """Boolean masks (tp, fp_ca, fp, outside) of the calls of one sequence, split output mode
+    (SplitEvalSynchronizer.handleKnownCall :112-134): GT_MATCH with weight > 0 -> TP (a self-cancelling call with weight 0
+    is dropped), else ALLELE_MATCH with weight > 0 -> FP_CA, else NO_MATCH -> FP unless OUTSIDE_EVAL."""
+    st = np.asarray(status, np.uint8)
+    w = np.asarray(weight, np.float64)
+    gt = (st & capi.STATUS_GT_MATCH) != 0
+    am = ((st & capi.STATUS_ALLELE_MATCH) != 0) & ~gt
+    nm = ((st & capi.STATUS_NO_MATCH) != 0) & ~gt & ~am
+    out = (st & capi.STATUS_OUTSIDE_EVAL) != 0
+    tp = gt & (w > 0)
+    fp_ca = am & (w > 0)
+    fp = nm & ~out
+    return tp, fp_ca, fp, nm & out
+
+
+def baseline_classes(status: np.ndarray):
+    """(tp, fn_ca, fn) masks of the baseline variants of one sequence (SplitEvalSynchronizer.handleKnownBaseline :136-150):
+    OUTSIDE_EVAL variants are not counted at all."""
+    st = np.asarray(status, np.uint8)
+    inside = (st & capi.STATUS_OUTSIDE_EVAL) == 0
+    gt = (st & capi.STATUS_GT_MATCH) != 0
+    am = ((st & capi.STATUS_ALLELE_MATCH) != 0) & ~gt
+    nm = ((st & capi.STATUS_NO_MATCH) != 0) & ~gt & ~am
+    return gt & inside, am & inside, nm & inside
 
 
 def summary_counts(results: List[capi.SequenceResult]) -> np.ndarray:
-    """[baseline TP, baseline FN, call TP, call FP, skipped, mis-phasings, correct phasings, unphaseable]."""
+    """[baseline TP, baseline FN (incl. FN_CA), call TP, call FP (incl. FP_CA), skipped, mis-phasings, correct phasings,
+    unphaseable] with the reference's split-mode rules (see call_classes / baseline_classes)."""
     tot = np.zeros(8, np.int64)
-    flags = (capi.STATUS_GT_MATCH, capi.STATUS_NO_MATCH, capi.STATUS_SKIPPED)
     for r in results:
-        b = _flag_counts(r.baseline.status, flags)
-        c = _flag_counts(r.calls.status, flags)
-        tot[0] += b[0]
-        tot[1] += b[1]
-        tot[2] += c[0]
-        tot[3] += c[1]
-        tot[4] += b[2] + c[2]
+        btp, bca, bfn = baseline_classes(r.baseline.status)
+        ctp, cca, cfp, _ = call_classes(r.calls.status, r.calls.weight)
+        tot[0] += int(np.count_nonzero(btp))
+        tot[1] += int(np.count_nonzero(bca)) + int(np.count_nonzero(bfn))
+        tot[2] += int(np.count_nonzero(ctp))
+        tot[3] += int(np.count_nonzero(cca)) + int(np.count_nonzero(cfp))
+        tot[4] += int(np.count_nonzero(r.baseline.status & np.uint8(capi.STATUS_SKIPPED)))
+        tot[4] += int(np.count_nonzero(r.calls.status & np.uint8(capi.STATUS_SKIPPED)))
         tot[5:8] += np.asarray(r.phasing, np.int64)
     return tot
 
 
 def roc_tuples(results: List[capi.SequenceResult], scores: List[np.ndarray]) -> np.ndarray:
     """(n, 4) float64 rows (score, tpWeight, fpWeight, tpRaw) of the calls of this rank's sequences, in sequence then
-    record order: TP -> (w, 0, 1), FP -> (0, 1, 0)  (WithRocsEvalSynchronizer.java:132-141)."""
+    record order, as WithRocsEvalSynchronizer.addToROCContainer :132-141 feeds the default ROC: TP -> (w, 0, 1), an allele
+    match (two-pass) -> (0, 1, 0), FP -> (0, 1, 0); weight-0 matches and OUTSIDE_EVAL calls contribute nothing."""
     rows = []
     for r, sc in zip(results, scores):
-        st = r.calls.status
-        tp = (st & capi.STATUS_GT_MATCH) != 0
-        fp = (st & capi.STATUS_NO_MATCH) != 0
-        keep = tp | fp
+        tp, fp_ca, fp, _ = call_classes(r.calls.status, r.calls.weight)
+        keep = tp | fp_ca | fp
         t = np.zeros((int(keep.sum()), 4), np.float64)
         t[:, 0] = np.asarray(sc, np.float64)[keep]
         t[:, 1] = np.where(tp, r.calls.weight, 0.0)[keep]
-        t[:, 2] = fp[keep].astype(np.float64)
+        t[:, 2] = (fp_ca | fp)[keep].astype(np.float64)
         t[:, 3] = tp[keep].astype(np.float64)
         rows.append(t)
     return np.concatenate(rows) if rows else np.zeros((0, 4), np.float64)

@@ -326,8 +326,11 @@ def fuzz_sequence(rng, length=400, n_base=12, n_calls=12, repeat=True, multi=0.1
     return capi.Sequence(name, tmpl, side(n_base), side(n_calls))
 
 
-def dense_cluster_sequence(rng, n_clusters=4, cluster_len=500, per_side=(12, 40), spacing=3000, name="dense") -> capi.Sequence:
-    """clusters of overlapping indels / MNPs in short tandem repeats on both sides."""
+def dense_cluster_sequence(rng, n_clusters=4, cluster_len=500, per_side=(12, 40), spacing=3000, name="dense",
+                           long_frac=0.0, return_qual=False):
+    """clusters of overlapping indels / MNPs in short tandem repeats on both sides.  `long_frac` of the
+    variants are long alleles (100 .. 1000 bases, --Xmax-length, VcfEvalCli.java:163): deletions / insertions of whole
+    repeat units reaching far beyond a search window of the small kernels."""
     length = n_clusters * spacing + 1000
     tmpl = rng.integers(1, 5, size=length, dtype=np.uint8)
     bvs, cvs = [], []
@@ -340,13 +343,38 @@ def dense_cluster_sequence(rng, n_clusters=4, cluster_len=500, per_side=(12, 40)
             starts = np.sort(rng.choice(np.arange(c0 + 2, c0 + cluster_len - 10), size=nv, replace=False))
             for st in starts:
                 st = int(st)
-                if rng.random() < 0.5:
-                    L = int(rng.integers(1, 3)) * len(unit)
+                is_del = rng.random() < 0.5
+                L = int(rng.integers(1, 3)) * len(unit)
+                if long_frac > 0 and rng.random() < long_frac:
+                    L = (int(rng.integers(100, 1001)) // len(unit)) * len(unit)
+                if is_del:
                     ref = bytes(tmpl[st:st + L])
                     alleles = [None, (st, st + L, ref), (st, st + L, b"")]
                 else:
-                    L = int(rng.integers(1, 3)) * len(unit)
-                    alleles = [None, (st, st, b""), (st, st, bytes(tmpl[st:st + L]))]
+                    ins = np.tile(tmpl[st:st + len(unit)], L // len(unit) + 1)[:L] if L > 2 * len(unit) else tmpl[st:st + L]
+                    alleles = [None, (st, st, b""), (st, st, bytes(ins))]
                 gt = [0, 1] if rng.random() < 0.5 else [1, 0]
                 out.append({"id": len(out) + 1, "alleles": alleles, "gt": gt, "phased": False, "status": 0})
-    return capi.Sequence(name, tmpl, capi.VariantSide.from_variants(bvs, 2), capi.VariantSide.from_variants(cvs, 2))
+    seq = capi.Sequence(name, tmpl, capi.VariantSide.from_variants(bvs, 2), capi.VariantSide.from_variants(cvs, 2))
+    if return_qual:
+        return seq, np.round(rng.uniform(1, 100, size=len(cvs)), 1)
+    return seq
+
+
+def make_c3(n_clusters=2000, per_seq=50, seed=3, per_side=(12, 40), long_frac=0.01, only=None, return_qual=False):
+    """BASELINE.md C3 (BASELINE.json configs[2]): `n_clusters` 500 bp tandem-repeat clusters with 12-40 overlapping
+    heterozygous indels per side, alleles up to 1000 bases, spread over sequences of `per_seq` clusters each (sequences are
+    the reference's unit of parallelism, VcfEvalTask.java:131-135).  With these sizes every cluster exceeds the 50 000-path
+    budget at least once (ToolsGlobalFlags.java:139): the run exercises the too-complex skip semantics throughout.
+    Every sequence draws from its own (seed, index) stream: `only=[...]` builds any subset identically."""
+    n_seq = (n_clusters + per_seq - 1) // per_seq
+    out, quals = [], []
+    for k in range(n_seq):
+        if only is not None and k not in only:
+            continue
+        ncl = min(per_seq, n_clusters - k * per_seq)
+        seq, q = dense_cluster_sequence(np.random.default_rng((seed, k)), n_clusters=ncl, per_side=per_side, name="c3_%d" % k,
+                                        long_frac=long_frac, return_qual=True)
+        out.append(seq)
+        quals.append(q)
+    return (out, quals) if return_qual else out

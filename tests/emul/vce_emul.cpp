@@ -164,11 +164,70 @@ class EmulBackend : public Backend {
     std::vector<int32_t>& syncOut = sync_[pd.pass];
     if (syncOut.size() < syncTotal) syncOut.resize(syncTotal, 0);
     for (size_t q = q0; q < q1; ++q) {
-      if (general || forceGeneral) runRegion<true>(pd, sc, regs, q, windows, tier, general, fs, out, syncOff, warns, syncOut);
+      if ((tier == kTierMid || tier == kTierCta) && !forceGeneral) runRegionCta(pd, sc, regs, q, windows, tier, out, syncOff, warns, syncOut);
+      else if (general || forceGeneral) runRegion<true>(pd, sc, regs, q, windows, tier, general, fs, out, syncOff, warns, syncOut);
       else runRegion<false>(pd, sc, regs, q, windows, tier, general, fs, out, syncOff, warns, syncOut);
     }
     return 0;
   }
+  // The CTA kernel's source (vce_cta.h) with one lane: "shared memory" and the HBM arena are plain host buffers.
+  void runRegionCta(PassData& pd, const SearchConfig& sc, const std::vector<RegionDesc>& regs, size_t q,
+                    const std::vector<uint8_t>& windows, int tier, std::vector<RegionResult>& out,
+                    const std::vector<int32_t>& syncOff, std::vector<WarnRec>& warns, std::vector<int32_t>& syncOut) {
+    RegionConst rk;
+    CtaSearch<HostLaneMove> cs(&rk);
+    cs.rs.R = regs[q];
+    cs.rs.cfg = sc;
+    for (int side = 0; side < 2; ++side) {
+      HostSide& hs = pd.side[side];
+      SideArrays& S = cs.rs.S[side];
+      S.vStart = hs.vStart.data(); S.vEnd = hs.vEnd.data(); S.oOff = hs.oOff.data(); S.oSlot = oSlot_[side].data();
+      S.oIds = hs.oIds.data(); S.oOrig = hs.oOrig.data();
+      S.aStart = al_[side]->aStart.data(); S.aEnd = al_[side]->aEnd.data(); S.aNtOff = al_[side]->aNtOff.data();
+      S.nt = al_[side]->nt.data(); S.vFlags = hs.vFlags.data();
+      S.outDecision = hs.decision.data(); S.outWeight = hs.weight.data();
+    }
+    cs.rs.win = windows.data() + regs[q].winOff;
+    const int mo = std::max(pd.maxOrient[0], pd.maxOrient[1]);
+    cs.rs.maxChildren = 1 + mo;
+    cs.shape = ctaShape(tier);
+    if (ctaNbOverride > 0) cs.shape.nb = ctaNbOverride;
+    const bool layoutOk = ctaLayout(cs.rs.L, pd.H, regs[q].cCount, regs[q].bCount, regs[q].decBits ? regs[q].decBits : 4);
+    std::vector<uint32_t> sm((size_t) ctaSmemWords(cs.shape) + 64);
+    cs.carve(sm.data());
+    std::vector<uint16_t> ranks((size_t) regs[q].cSlotN + regs[q].bSlotN + 2);
+    cs.rank[0] = ranks.data();
+    cs.rank[1] = ranks.data() + regs[q].cSlotN;
+    long long pool = std::min<long long>(cs.shape.capacity(), (long long) sc.maxPaths + 1 + cs.rs.maxChildren) + 64;
+    if (ctaPoolOverride > 0) pool = ctaPoolOverride;
+    const long long words = ctaArenaWords(cs.shape, cs.rs.L.W, pool);
+    std::vector<int32_t> arena((size_t) words + 16);
+    cs.bindArena(arena.data(), words);
+    std::vector<WarnRec> lw(64);
+    cs.rs.warnOut = lw.data(); cs.rs.warnCap = 64; cs.rs.regionId = (int) q;
+    cs.rs.usedPrefix = cs.rs.nWarn = cs.rs.maxFrontier = cs.rs.totalIters = 0;
+    cs.computeRanks();
+    int resultSlot = -1;
+    const int st = layoutOk ? cs.run(resultSlot) : kRegionOverflow;
+    RegionResult rr;
+    std::memset(&rr, 0, sizeof(rr));
+    rr.status = st;
+    rr.usedPrefix = cs.rs.usedPrefix;
+    rr.nWarn = cs.rs.nWarn;
+    rr.maxFrontier = cs.rs.maxFrontier;
+    rr.iterations = cs.rs.totalIters;
+    rr.lastBaseAlleleId = kPrefixEmpty;
+    if (st == kRegionClean || st == kRegionFinished) {
+      cs.rs.writeResults(resultSlot, syncOut.data() + syncOff[q], &rr);
+      for (int i = 0; i < cs.rs.nWarn && i < 64; ++i) warns.push_back(lw[i]);
+    }
+    ++ctaRegions;
+    if (st == kRegionOverflow) ++ctaOverflows;
+    out[q] = rr;
+  }
+  int ctaNbOverride = 0;
+  long long ctaPoolOverride = 0;
+  std::atomic<int64_t> ctaRegions{0}, ctaOverflows{0};
   template <bool CH>
   void runRegion(PassData& pd, const SearchConfig& sc, const std::vector<RegionDesc>& regs, size_t q,
                  const std::vector<uint8_t>& windows, int tier, bool general, const FastShape& fs, std::vector<RegionResult>& out,
@@ -255,13 +314,15 @@ class EmulBackend : public Backend {
 };
 
 int g_gap = 0 /* 0 = the product default */, g_margin = 24, g_forceGeneral = 0, g_disableMicro = 0, g_threads = 3, g_chunk = 0, g_split = 1 << 16;
+int g_forceCta = 0, g_ctaNb = 0;
+long long g_ctaPool = 0;
 int64_t g_stats[8];
 }  // namespace
 
 extern "C" {
 void emul_set_options(int gap, int margin, int forceGeneral) { g_gap = gap; g_margin = margin; g_forceGeneral = forceGeneral; }
 // regions, escalated, spilled, prefixReruns, launches of the last emul_vce_submit
-void emul_get_stats(int64_t* out) { for (int i = 0; i < 7; ++i) out[i] = g_stats[i]; }
+void emul_get_stats(int64_t* out) { for (int i = 0; i < 8; ++i) out[i] = g_stats[i]; }
 
 // disableMicro: no thread-per-region kernel; threads: host worker threads; chunk: regions per chunk (0 = automatic)
 void emul_set_engine(int disableMicro, int threads, int chunk) { g_disableMicro = disableMicro; g_threads = threads; g_chunk = chunk; }
@@ -269,14 +330,21 @@ void emul_set_split(int variantsPerSegment) { g_split = variantsPerSegment; }
 int g_deviceBuild = 1;   // the product default
 void emul_set_device_build(int on) { g_deviceBuild = on; }
 
+// forceCta: every warp-path region starts in the CTA kernel's tiers; nb / pool: shrink its frontier directory / record pool
+// (exercises the overflow hand-over to the large-capacity kernel)
+void emul_set_cta(int forceCta, int nb, long long pool) { g_forceCta = forceCta; g_ctaNb = nb; g_ctaPool = pool; }
+
 int emul_vce_submit(const vce_config* cfg, int32_t n_seq, const vce_sequence* seqs, vce_sequence_result* results) {
   EmulBackend be;
   be.forceGeneral = g_forceGeneral != 0;
+  be.ctaNbOverride = g_ctaNb;
+  be.ctaPoolOverride = g_ctaPool;
   WorkerPool pool(g_threads);
   EngineOptions opt;
   if (g_gap > 0) opt.gap = g_gap;
   opt.margin = g_margin;
   opt.forceGeneral = g_forceGeneral != 0;
+  opt.forceCta = g_forceCta != 0;
   opt.disableMicro = g_disableMicro != 0;
   opt.chunkRegions = g_chunk;
   opt.splitSegment = g_split;
@@ -289,6 +357,7 @@ int emul_vce_submit(const vce_config* cfg, int32_t n_seq, const vce_sequence* se
   }
   g_stats[0] = be.stats.regions; g_stats[1] = be.stats.escalated; g_stats[2] = be.stats.spilled;
   g_stats[3] = be.stats.prefixReruns; g_stats[4] = be.stats.launches; g_stats[5] = be.microRegions.load(); g_stats[6] = be.microClean.load();
+  g_stats[7] = be.ctaRegions.load() | (be.ctaOverflows.load() << 32);
   return rc;
 }
 

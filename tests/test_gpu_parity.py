@@ -68,6 +68,27 @@ def test_cuda_dense_clusters_default_budget(engine, oracle):
     compare_results(want, engine.submit(capi.Config(), seqs), seqs)
 
 
+def test_cuda_c3_slice_default_budget(engine, oracle):
+    """BASELINE.json configs[2] (bench.py --workload c3): a slice of the 2 000-cluster workload at the reference's DEFAULT
+    budget through the CTA-per-region kernel -- identical skipped sets, warning fields and surviving assignments."""
+    seqs = synth.make_c3(n_clusters=2000, per_seq=4, only=range(6))   # 24 clusters of the full workload
+    want = oracle.submit(capi.Config(), seqs, threads=os.cpu_count() or 8)
+    assert sum(1 for r in want for w in r.warnings if w["paths"] > 50000) >= 12
+    got = engine.submit(capi.Config(), seqs)
+    compare_results(want, got, seqs, what="c3")
+    st = engine.submit_stats()
+    assert st["regions"] > 0
+
+
+def test_cuda_c3_long_alleles_reduced_budget(engine, oracle):
+    """Clusters with alleles of up to 1000 bases (beyond every small kernel's window) at several budgets."""
+    seqs = synth.make_c3(n_clusters=12, per_seq=3, per_side=(12, 24), long_frac=0.06, seed=9)
+    for mp, mi in ((3000, 100000), (200, 5000), (20000, 400000)):
+        cfg = capi.Config(max_paths=mp, max_iterations=mi)
+        want = oracle.submit(cfg, seqs, threads=4)
+        compare_results(want, engine.submit(cfg, seqs), seqs, what="c3 long alleles %d" % mp)
+
+
 def test_cuda_genome_slice_all_modes(engine, oracle):
     """BASELINE.json configs[3] on a 10 % slice of the 24-chromosome genome: --squash-ploidy (haploid SQUASH_GT) and the
     two-pass mode of ga4gh / annotate / combine (diploid, then haploid allele matching on FN / FP)."""

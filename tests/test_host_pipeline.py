@@ -62,6 +62,50 @@ def test_large_capacity_path_is_exact(emul, oracle):
         emul.lib.emul_set_options(0, 24, 0)
 
 
+def _set_cta(emul, force, nb=0, pool=0):
+    emul.lib.emul_set_cta.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_longlong]
+    emul.lib.emul_set_cta(force, nb, pool)
+
+
+@pytest.mark.parametrize("cfg_name", ["default", "twopass", "squash", "phased", "calls_min_base", "small_budget", "no_prune", "allele_gt"])
+def test_cta_kernel_source_is_exact(emul, oracle, cfg_name):
+    """Every warp-path region through the CTA kernel's source (vce_cta.h: rank keys, block frontier, record pool), the
+    thread-per-region kernel switched off so that ALL regions take it."""
+    try:
+        emul.lib.emul_set_engine(1, 3, 0)
+        _set_cta(emul, 1)
+        n_cta = 0
+        for seed in range(12):
+            seqs = fuzz_batch(7000 + seed)
+            compare_results(oracle.submit(CONFIGS[cfg_name], seqs), emul.submit(CONFIGS[cfg_name], seqs), seqs, what=cfg_name)
+            st = (ctypes.c_int64 * 8)()
+            emul.lib.emul_get_stats(st)
+            n_cta += st[7] & 0xffffffff
+        assert n_cta > 0
+    finally:
+        emul.lib.emul_set_engine(0, 3, 0)
+        _set_cta(emul, 0)
+
+
+@pytest.mark.parametrize("nb,pool", [(6, 0), (0, 300), (3, 100)])
+def test_cta_kernel_hands_over_what_its_arena_cannot_hold(emul, oracle, nb, pool):
+    """A frontier directory / record pool that is too small must end in kRegionOverflow and a bit-exact re-run in the
+    large-capacity warp kernel -- never in a different result."""
+    try:
+        _set_cta(emul, 1, nb, pool)
+        over = 0
+        for seed in range(6):
+            seqs = fuzz_batch(7100 + seed)
+            seqs.append(synth.dense_cluster_sequence(np.random.default_rng(seed), n_clusters=2, per_side=(4, 9), name="d"))
+            compare_results(oracle.submit(CONFIGS["twopass"], seqs), emul.submit(CONFIGS["twopass"], seqs), seqs)
+            st = (ctypes.c_int64 * 8)()
+            emul.lib.emul_get_stats(st)
+            over += st[7] >> 32
+        assert over > 0, "the shrunken arena should have overflowed at least once"
+    finally:
+        _set_cta(emul, 0)
+
+
 def test_synthetic_genome_pair(emul, oracle):
     seqs = synth.make_pair(3_000_000, n_chrom=3)
     assert sum(s.calls.n for s in seqs) > 3000
@@ -84,6 +128,16 @@ def test_dense_cluster_default_budget(emul, oracle):
     want = oracle.submit(capi.Config(), seqs)
     assert any(w["paths"] > 50000 for w in want[0].warnings)
     compare_results(want, emul.submit(capi.Config(), seqs), seqs)
+
+
+def test_c3_clusters_with_long_alleles(emul, oracle):
+    """BASELINE.json configs[2] as bench.py --workload c3 builds it (synth.make_c3: 12-40 variants per side, alleles up
+    to 1000 bases) at a reduced budget so that the 1-lane emulation stays fast: identical skipped sets, warnings, sync points."""
+    seqs = synth.make_c3(n_clusters=2, per_seq=1, per_side=(12, 20), long_frac=0.05)
+    cfg = capi.Config(max_paths=3000, max_iterations=100000)
+    want = oracle.submit(cfg, seqs)
+    assert sum(len(r.warnings) for r in want) > 0
+    compare_results(want, emul.submit(cfg, seqs), seqs)
 
 
 def test_empty_and_one_sided_sequences(emul, oracle):

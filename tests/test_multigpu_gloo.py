@@ -94,3 +94,23 @@ def test_merge_is_a_no_op_without_a_process_group():
     assert np.array_equal(multigpu.merge_counts(c), c)
     rows = multigpu.gather_roc([np.ones((2, 4)), np.zeros((1, 4))], [1, 0], 2)
     assert rows.shape == (3, 4) and rows[0, 0] == 0.0
+
+
+@pytest.mark.parametrize("name", ["annotate", "updel2", "updel4", "split", "tricky", "small"])
+def test_roc_tuples_follow_the_reference_synchronizer_rules(oracle, fixtures, name):
+    """The merge's status -> (tp, fp, raw) mapping against the writers' restatement in oracle/ref_host.py (which the golden
+    fixtures pin): two-pass scenarios exercise ALLELE_MATCH -> FP and weight-0 matches, `split` the OUTSIDE_EVAL rules."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_host
+    from rtg_tools_b200 import multigpu
+    sc = fixtures[name]
+    rr = ref_host.run_vcfeval(oracle, sc["template_fa"], sc["baseline_vcf"], sc["calls_vcf"], sc["args"])
+    scores = [np.array([ref_host.score_of(v["rec"], rr.params.score_field, rr.csample) for v in cl], np.float64)
+              for _, cl in rr.loaded]
+    got = multigpu.roc_tuples(rr.results, scores)
+    want = np.array([rr.roc_inputs["score"], rr.roc_inputs["tp"], rr.roc_inputs["fp"], rr.roc_inputs["raw"]], np.float64).T.reshape(-1, 4)
+    assert got.shape == want.shape
+    assert np.array_equal(np.nan_to_num(got, nan=-1.0), np.nan_to_num(want, nan=-1.0))
+    counts = multigpu.summary_counts(rr.results)
+    assert counts[0] == rr.base_tp and counts[0] + counts[1] == rr.base_total
+    assert counts[2] + counts[3] == got.shape[0]
