@@ -41,7 +41,13 @@ WORKLOADS = {
     "c2": (3_000_000_000, 24, "synthetic 3 Gbp 24-chromosome genome, ~4.4M baseline/call variants per side (BASELINE.json configs[1])"),
     "c1": (10_000_000, 1, "synthetic 10 Mbp genome, ~15k variants per side (BASELINE.json configs[0])"),
     "tiny": (2_000_000, 4, "2 Mbp smoke workload"),
+    # BASELINE.json configs[2]: --c3-clusters 500 bp tandem-repeat clusters, 12-40 overlapping heterozygous indels per side,
+    # alleles up to 1000 bases, 4 clusters per sequence; every cluster exceeds the 50 000-path budget at least once
+    "c3": (0, 0, "dense complex-variant stress: 500 bp tandem-repeat clusters, 12-40 overlapping het indels per side, alleles up to "
+                 "1000 bases, default budget 50 000 paths / 10^7 iterations (BASELINE.json configs[2])"),
 }
+C3_PER_SEQ = 4
+C3_CLUSTERS = [2000]
 
 
 def log(*a):
@@ -126,6 +132,12 @@ def build_workload(name, rank, world, scaling, total_bp=None):
     bp, n_chrom, desc = WORKLOADS[name]
     if total_bp:
         bp = int(total_bp)
+    if name == "c3":
+        # sequences (4 clusters each) are the units; strong scaling shards them by LPT on their variant counts (uniform here)
+        n_seq = (C3_CLUSTERS[0] + C3_PER_SEQ - 1) // C3_PER_SEQ
+        mine = list(range(n_seq)) if world == 1 else multigpu.shard_sequences([1.0] * n_seq, rank, world)
+        seqs, quals = synth.make_c3(n_clusters=C3_CLUSTERS[0], per_seq=C3_PER_SEQ, only=set(mine), return_qual=True)
+        return seqs, quals, "%d x %s" % (C3_CLUSTERS[0], desc), mine, n_seq
     if scaling == "strong" and world > 1:
         # ONE sample pair, its chromosomes sharded over the ranks by LPT (weights: chromosome lengths ~ variant counts)
         lens = synth.genome_lengths(bp, n_chrom) if n_chrom > 1 else [bp]
@@ -148,33 +160,56 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from rtg_tools_b200 import capi
-    seqs, quals, desc, _, _ = build_workload(args.workload, 0, 1, "weak", args.total_bp)
+    seqs, quals, desc, _, _ = build_workload(args.workload, 0, 1, "strong", args.total_bp)
     oracle = capi.Library(os.path.join(ROOT, "oracle", "liboracle.so"), prefix="oracle_")
     cores = os.cpu_count() or 1
+    nv_full = n_variants(seqs)
+    sample = "the full workload per step"
+    if args.workload == "c3":
+        # a cluster costs ~2 s of one core: the step is a bounded sample, one sequence (4 clusters) per host core
+        seqs = seqs[:max(1, min(cores, len(seqs)))]
+        sample = "the first %d of the workload's sequences per step (%d clusters)" % (len(seqs), len(seqs) * C3_PER_SEQ)
     threads = max(1, min(cores, len(seqs)))
-    cfg = capi.Config()
+    cfg = engine_config(args.config)
     nv = n_variants(seqs)
+    # the caller owns and reuses every input / output buffer, exactly as the B200 arm's vce_submit calls do
+    packed = capi.Library.pack(cfg, seqs)
     for _ in range(args.warmup):
-        oracle.submit(cfg, seqs, threads=threads)
+        oracle.submit_packed(packed, threads=threads)
     t0 = time.perf_counter()
-    regions = 0
     for _ in range(args.steps):
-        res = oracle.submit(cfg, seqs, threads=threads)
-        regions = sum(len(r.sync_points[0]) for r in res)
-    dt = (time.perf_counter() - t0) / args.steps
+        rc = oracle.submit_packed(packed, threads=threads)
+        if rc != 0:
+            raise RuntimeError("oracle failed: %d" % rc)
+    dt = (time.perf_counter() - t0) / max(1, args.steps)
+    res = capi.Library.unpack(packed[2], packed[3], packed[4])
+    regions = sum(len(r.sync_points[0]) for r in res)
     v = nv / dt
     out = {
         "impl": "reference", "metric": "vcfeval variants evaluated/sec", "value": v, "unit": "variants/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": args.scaling,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": "%s: %s" % (args.workload, desc), "variants_per_step": nv, "sync_regions_per_step": regions},
+        "config": workload_config(args, desc, nv_full, None),
         "cpu_baseline": {"value": v, "unit": "variants/s", "cores": threads, "kind": "port",
-                         "sample": "the full workload per step (%d variants, %d sequences), %d worker threads of %d host cores" % (
-                             nv, len(seqs), threads, cores)},
+                         "sample": "%s (%d variants, %d sequences), %d worker threads of %d host cores" % (
+                             sample, nv, len(seqs), threads, cores)},
         "e2e": {"value": v, "unit": "variants/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "sync_regions_per_s": regions / dt,
     }
     emit(out)
+
+
+def engine_config(name):
+    from rtg_tools_b200 import capi
+    return {"default": capi.Config(),
+            "squash": capi.Config(n_passes=1, baseline_orientor=(3, 3), calls_orientor=(3, 3), ploidy=(1, 1)),
+            "twopass": capi.Config(n_passes=2)}[name]
+
+
+def workload_config(args, desc, variants, regions):
+    """The `config` object: the same keys in both arms (the driver compares them)."""
+    return {"workload": "%s: %s" % (args.workload, desc), "engine_config": args.config, "variants_per_step": int(variants),
+            "sync_regions_per_step": None if regions is None else int(regions)}
 
 
 def main():
@@ -184,7 +219,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="N > 1: strong (default) = ONE sample pair, its sequences sharded over the ranks by LPT; weak = one sample pair per rank")
+    ap.add_argument("--c3-clusters", type=int, default=2000, help="--workload c3: number of 500 bp clusters (BASELINE.md: 2000)")
     ap.add_argument("--total-bp", type=float, default=None, help="override the genome size of the workload (testing)")
     ap.add_argument("--config", default="default", choices=["default", "squash", "twopass"],
                     help="engine configuration: default (diploid, single pass), squash (--squash-ploidy), twopass (ga4gh / annotate)")
@@ -194,6 +231,7 @@ def main():
     ap.add_argument("--no-roc", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    C3_CLUSTERS[0] = args.c3_clusters
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -229,9 +267,7 @@ def main():
     log("[rank %d] workload %s: %d sequences, %d variants (generated in %.1fs)" % (rank, args.workload, len(seqs), nv,
                                                                                time.perf_counter() - t_gen))
     eng = vcfeval.Engine(local_rank)
-    cfg = {"default": capi.Config(),
-           "squash": capi.Config(n_passes=1, baseline_orientor=(3, 3), calls_orientor=(3, 3), ploidy=(1, 1)),
-           "twopass": capi.Config(n_passes=2)}[args.config]
+    cfg = engine_config(args.config)
 
     # ------------------------------------------------------------------ device-resident throughput (value)
     job = eng.job(cfg, seqs)

@@ -191,6 +191,17 @@ void        vce_shutdown(void);
 const char* vce_last_error(void);               /* thread-local message for the last non-zero return */
 const char* vce_version(void);
 
+/*
+ * Optional: make a reference sequence RESIDENT on the device (2 bits per base plus a map of the non-ACGT positions; a 3 Gbp
+ * genome takes ~0.8 GB of the 180 GB).  It belongs to the load phase, where the reference reads the sequence from the SDF
+ * (SequenceEvaluator.java:76-86, SequencesReader.read): call it once per sequence, before the evaluations that use it.
+ * vce_submit() recognises a registered sequence by its template_bases pointer + template_len; for such a sequence the
+ * caller's variant arrays are uploaded whole and every search window is cut out of HBM, instead of being gathered from
+ * template_bases on the host.  Results are identical either way.  The caller must keep the bytes unchanged while registered.
+ */
+int vce_template_register(const uint8_t* bases, int32_t len);
+int vce_template_unregister(const uint8_t* bases);
+
 /* Default configuration = `rtg vcfeval` defaults (diploid, unphased orientors, split mode single pass). */
 void        vce_default_config(vce_config* cfg);
 

@@ -362,10 +362,15 @@ class Library:
             raise RuntimeError("%ssubmit failed: %s %s" % (self.prefix, ERR_NAMES.get(rc, rc), self.last_error()))
         return results
 
-    def submit_packed(self, packed) -> int:
+    def submit_packed(self, packed, threads: int = 0) -> int:
         """vce_submit on buffers packed once with Library.pack (the caller owns and reuses every input / output array,
         as a JNI host would); returns the C return code.  Call Library.unpack(cres, results, keep) when done."""
         ccfg, cseqs, cres, results, keep = packed
+        if threads > 1 and self.has("vce_submit_mt"):
+            f = self._sym("vce_submit_mt")
+            f.restype = C.c_int
+            f.argtypes = [C.POINTER(CConfig), C.c_int32, C.POINTER(CSequence), C.POINTER(CSequenceResult), C.c_int32]
+            return f(C.byref(ccfg), len(results), cseqs, cres, threads)
         return self._submit(C.byref(ccfg), len(results), cseqs, cres)
 
     def roc(self, score, tp, fp, tp_raw, filter_mask=None, n_filters=1, ascending=False):

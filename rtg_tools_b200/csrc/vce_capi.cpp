@@ -63,6 +63,7 @@ Context* acquire(int& rc) {
   if (const char* e = std::getenv("VCE_SORT_PACKETS")) opt.sortPackets = std::atoi(e) != 0;
   if (const char* e = std::getenv("VCE_SPLIT_GAP")) opt.gap = std::max(1, std::atoi(e));
   if (const char* e = std::getenv("VCE_DEVICE_BUILD")) opt.deviceBuild = std::atoi(e) != 0;
+  if (const char* e = std::getenv("VCE_RESIDENT")) opt.residentInputs = std::atoi(e) != 0;
   c->engine.reset(new vce::Engine(c->backend.get(), g_pool.get(), opt));
   return c;
 }
@@ -116,7 +117,30 @@ int vce_init(int device) {
 void vce_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   g_free.clear();
+  vce::templateRegistryRemove(-1, nullptr);
   g_device = -1;
+}
+
+int vce_template_register(const uint8_t* bases, int32_t len) {
+  if (!bases || len <= 0) return fail(VCE_ERR_BAD_ARGUMENT, "null template");
+  int dev;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    dev = g_device;
+    if (dev < 0) return fail(VCE_ERR_NOT_INITIALISED, "call vce_init first");
+    if (!g_pool) g_pool.reset(new vce::WorkerPool(vce::WorkerPool::defaultThreads()));
+  }
+  std::vector<uint32_t> packed, nmask;
+  vce::packTemplate(bases, len, g_pool.get(), packed, nmask);
+  std::string err;
+  const int rc = vce::templateRegistryAdd(dev, bases, len, packed.data(), packed.size(), nmask.data(), nmask.size(), err);
+  if (rc) return fail(rc, err);
+  return VCE_OK;
+}
+
+int vce_template_unregister(const uint8_t* bases) {
+  vce::templateRegistryRemove(-1, bases);
+  return VCE_OK;
 }
 
 int vce_job_create(const vce_config* cfg, int32_t n_seq, const vce_sequence* seqs, vce_job** job) {

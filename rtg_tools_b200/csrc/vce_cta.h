@@ -32,6 +32,19 @@
 #include "vce_device.h"
 #include "vce_search.h"
 
+#if defined(VCE_CTA_DEBUG) && defined(__CUDA_ARCH__)
+#include <cstdio>
+#define VCE_CTA_CHECK(cond, code, a, b)                                                                          \
+  do {                                                                                                           \
+    if (!(cond)) {                                                                                               \
+      printf("[k_cta] check %d failed: block %d lane %d values %d %d\n", (int) (code), (int) blockIdx.x, (int) (threadIdx.x & 31), (int) (a), (int) (b)); \
+      __trap();                                                                                                  \
+    }                                                                                                            \
+  } while (0)
+#else
+#define VCE_CTA_CHECK(cond, code, a, b) do { } while (0)
+#endif
+
 namespace vce {
 
 struct CtaShape {
@@ -144,6 +157,7 @@ struct CtaSearch {
     return 0;
   }
   VCE_HD int rankOf(int side, int slot) const {
+    VCE_CTA_CHECK(slot - (side == 0 ? rs.R.cSlot0 : rs.R.bSlot0) >= 0 && slot - (side == 0 ? rs.R.cSlot0 : rs.R.bSlot0) < (side == 0 ? rs.R.cSlotN : rs.R.bSlotN), 1, slot, side);
     return rank[side][slot - (side == 0 ? rs.R.cSlot0 : rs.R.bSlot0)];
   }
   // Key and tie-break fields of the path record p (cooperative; call sync() before reading them).
@@ -243,7 +257,10 @@ struct CtaSearch {
 
   // ---------------------------------------------------------------------------------------------- block cache
   VCE_HD uint32_t* cacheBlock(int c) const { return cacheMem + (size_t) c * cta::B_WORDS; }
-  VCE_HD uint32_t* globalBlock(int id) const { return gBlocks + (size_t) id * cta::B_WORDS; }
+  VCE_HD uint32_t* globalBlock(int id) const {
+    VCE_CTA_CHECK(id >= 0 && id < shape.nb, 2, id, shape.nb);
+    return gBlocks + (size_t) id * cta::B_WORDS;
+  }
   // Moves are plain cooperative 16-byte copies here; the device backend replaces them with bulk TMA copies (blockMove).
   VCE_HD void copyWords16(uint32_t* dst, const uint32_t* src, int words) {
     Quad* d = reinterpret_cast<Quad*>(dst);
@@ -268,6 +285,7 @@ struct CtaSearch {
       if (cid[c] < 0) { victim = c; break; }
       if (victim < 0 || cuse[c] < cuse[victim]) victim = c;
     }
+    VCE_CTA_CHECK(victim >= 0 && victim < shape.ncache, 3, victim, keep);
     writeBack(victim);
     w.storeWait();   // the slot's old content has been read out
     cid[victim] = id;
@@ -320,23 +338,27 @@ struct CtaSearch {
       nFreeCache -= 32;
       w.sync();
     }
+    VCE_CTA_CHECK(nFreeCache >= 0 && nFreeCache < cta::kFreeCache && nFreeStack >= 0 && nFreeStack <= poolCap, 7, nFreeCache, nFreeStack);
     if (w.lane() == 0) freeCache[nFreeCache] = slot;
     ++nFreeCache;
     w.sync();
   }
   VCE_HD void storeRecord(int slot, const int32_t* p) {  // lane j writes chunk j (and later reads the same chunk)
+    VCE_CTA_CHECK(slot >= 0 && slot < poolCap, 4, slot, poolCap);
     Quad* d = reinterpret_cast<Quad*>(gPool + (size_t) slot * rs.L.W);
     const Quad* s = reinterpret_cast<const Quad*>(p);
     VCE_NOUNROLL
     for (int i = w.lane(); i < (rs.L.W >> 2); i += WP::L) d[i] = s[i];
   }
   VCE_HD void loadRecord(int32_t* p, int slot) {
+    VCE_CTA_CHECK(slot >= 0 && slot < poolCap, 5, slot, poolCap);
     const Quad* s = reinterpret_cast<const Quad*>(gPool + (size_t) slot * rs.L.W);
     Quad* d = reinterpret_cast<Quad*>(p);
     VCE_NOUNROLL
     for (int i = w.lane(); i < (rs.L.W >> 2); i += WP::L) d[i] = s[i];
   }
   VCE_HD void prefetchRecord(int slot) {
+    VCE_CTA_CHECK(slot >= 0 && slot < poolCap, 6, slot, poolCap);
     pfSlot = slot;
     const Quad* s = reinterpret_cast<const Quad*>(gPool + (size_t) slot * rs.L.W);
     if (WP::L == 1) {
@@ -430,6 +452,7 @@ struct CtaSearch {
     uint8_t* ord = ordOf(B);
     int st = (int) B[cta::B_START];
     const int cnt = (int) B[cta::B_CNT];
+    w.sync();   // every lane has read the header before lane 0 rewrites it (the shift loops below may be empty)
     if (st > 0 && pos <= cnt - pos) {  // move the front part down
       VCE_NOUNROLL
       for (int base = 0; base < pos; base += WP::L) {
@@ -521,11 +544,14 @@ struct CtaSearch {
     w.sync();
     const uint32_t* auxNew = keyNew + cta::kKeyW;
     int bi = findBlock(keyNew);
+    VCE_CTA_CHECK(bi >= 0 && bi < nbUsed && dh >= 0 && dh + nbUsed <= 2 * shape.nb, 8, bi, nbUsed);
     int id = dir[dh + bi];
     int c = ensureCached(id, -1, true);
     uint32_t* B = cacheBlock(c);
     bool eq;
+    VCE_CTA_CHECK((int) B[cta::B_CNT] >= 0 && (int) B[cta::B_CNT] <= cta::kBlk && (int) B[cta::B_START] + (int) B[cta::B_CNT] <= 256, 9, B[cta::B_CNT], B[cta::B_START]);
     int pos = findInBlock(B, keyNew, eq);
+    VCE_CTA_CHECK(pos >= 0 && pos <= (int) B[cta::B_CNT], 10, pos, B[cta::B_CNT]);
     if (eq) {
       const int e = entryAt(B, pos);
       const bool newWins = betterAux(auxNew, auxOf(B, e));
@@ -550,6 +576,7 @@ struct CtaSearch {
       // full: the upper half becomes a new block right after this one
       if (nbFree <= 0) return false;
       const int nid = blkFree[nbFree - 1];
+      VCE_CTA_CHECK(nid >= 0 && nid < shape.nb && nbFree <= shape.nb, 15, nid, nbFree);
       --nbFree;
       const int c2 = ensureCached(nid, c, false);
       uint32_t* N = cacheBlock(c2);
@@ -591,6 +618,7 @@ struct CtaSearch {
     int e = 0;
     if (w.lane() == 0) e = takeFreeEntry(B);
     e = w.bcast(e, 0);
+    VCE_CTA_CHECK(e >= 0 && e < cta::kBlk, 11, e, cnt);
     ordOpen(B, pos);
     if (w.lane() == 0) {
       ordOf(B)[B[cta::B_START] + pos] = (uint8_t) e;
@@ -616,8 +644,11 @@ struct CtaSearch {
     int c = ensureCached(id, -1, true);
     uint32_t* B = cacheBlock(c);
     const int st = (int) B[cta::B_START], cnt = (int) B[cta::B_CNT];
+    VCE_CTA_CHECK(cnt >= 1 && cnt <= cta::kBlk && st >= 0 && st + cnt <= 256, 12, cnt, st);
     const int e = ordOf(B)[st];
+    VCE_CTA_CHECK(e >= 0 && e < cta::kBlk, 13, e, st);
     const int slot = (int) B[cta::B_SLOT + e];
+    VCE_CTA_CHECK(slot >= 0 && slot < poolCap, 14, slot, e);
     // the record: still in a work slot, prefetched, or from the pool
     int hit = -1;
     for (int k = 0; k < nWork; ++k) if (tag[k] == slot) { hit = k; break; }

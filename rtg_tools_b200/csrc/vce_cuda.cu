@@ -477,6 +477,8 @@ struct BuildParams {
   uint32_t* offsets;          // [n] packet offset in 4-byte words, kNoPacket when the region does not fit
   uint32_t* keys;             // optional [n]: shape class of each packet (kClassBins - 1 for the rejected ones)
   int n, stride;
+  const uint32_t* t2;         // resident template (vce_template_register): 2 bits per base, nullptr = windows[] holds bytes
+  const uint32_t* nmask;      // one bit per 16-base granule with a non-ACGT base
 };
 template <class T>
 __global__ void __launch_bounds__(128) k_build(const __grid_constant__ BuildParams p) {
@@ -487,7 +489,8 @@ __global__ void __launch_bounds__(128) k_build(const __grid_constant__ BuildPara
   int bytes = 0;
   uint8_t* out = p.packets + (size_t) q * p.stride;
   if (microWindow(p.pv, g, &winStart, &winLen, nextStart)) {
-    bytes = microBuildPacket<T>(p.pv, g, winStart, winLen, nextStart, p.windows + p.winOff[q], out);
+    if (p.t2 != nullptr) bytes = microBuildPacketW<T>(p.pv, g, winStart, winLen, nextStart, WinPacked{p.t2, p.nmask, winStart}, out);
+    else bytes = microBuildPacket<T>(p.pv, g, winStart, winLen, nextStart, p.windows + p.winOff[q], out);
   }
   p.offsets[q] = bytes > 0 ? (uint32_t) (((size_t) q * p.stride) >> 2) : kNoPacket;
   if (p.keys != nullptr) p.keys[q] = bytes > 0 ? microPacketClass(out) : (uint32_t) (kClassBins - 1);
@@ -1272,15 +1275,28 @@ class CudaBackend : public Backend {
     cudaStream_t st = mStream_[lane];
     CUDA_TRY(cudaMemcpyAsync(dSlab, b.slab, b.slabBytes, cudaMemcpyHostToDevice, st));
     const uint8_t* base = static_cast<const uint8_t*>(dSlab);
+    if (b.resident) {   // the sequence's arrays were uploaded whole: the builder waits for those copies
+      for (int e = 0; e < 2; ++e) {
+        if (b.waitEvents[e] < 0) continue;
+        cudaEvent_t ev = nullptr;
+        {
+          std::lock_guard<std::mutex> lk(mMu_);
+          ev = mEvents_[b.waitEvents[e]];
+        }
+        CUDA_TRY(cudaStreamWaitEvent(st, ev, 0));
+      }
+    }
     int q0 = 0;
     for (int c = 0; c < 2; ++c) {
       MicroJob& j = *jobs[c];
       if (j.n > 0) {
         BuildParams bp;
-        bp.pv = microBuildView(b, base);
+        bp.pv = b.resident ? b.rv : microBuildView(b, base);
         bp.regs = reinterpret_cast<const RegRange*>(base + b.regions) + q0;
-        bp.winOff = reinterpret_cast<const uint32_t*>(base + b.winOff) + q0;
-        bp.windows = base + b.windows;
+        bp.winOff = b.resident ? nullptr : reinterpret_cast<const uint32_t*>(base + b.winOff) + q0;
+        bp.windows = b.resident ? nullptr : base + b.windows;
+        bp.t2 = b.resident ? b.t2 : nullptr;
+        bp.nmask = b.resident ? b.nmask : nullptr;
         bp.packets = static_cast<uint8_t*>(j.dPackets);
         bp.offsets = static_cast<uint32_t*>(j.dOffsets);
         bp.keys = c == 0 ? dKeys : nullptr;
@@ -1330,6 +1346,36 @@ class CudaBackend : public Backend {
     }
     return VCE_OK;
   }
+  // ---- resident inputs
+  bool templateLookup(const uint8_t* bases, int32_t len, const uint32_t** t2, const uint32_t** nmask) override {
+    return templateRegistryLookup(device_, bases, len, t2, nmask);
+  }
+  int residentUpload(const void* pinned, size_t bytes, void** dev, int* eventId) override {
+    CUDA_TRY(cudaSetDevice(device_));
+    void* d = nullptr;
+    cudaEvent_t ev = nullptr;
+    int lane = 0;
+    {
+      std::lock_guard<std::mutex> lk(mMu_);
+      d = devAlloc(bytes + 16);
+      lane = mNextLane_;
+      mNextLane_ = (mNextLane_ + 1) % kMicroLanes;
+      if ((int) mEvents_.size() <= mNextEvent_) {
+        cudaEvent_t e;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { setErr("cudaEventCreate failed"); return VCE_ERR_CUDA; }
+        mEvents_.push_back(e);
+      }
+      *eventId = mNextEvent_;
+      ev = mEvents_[mNextEvent_++];
+      stats.h2dBytes += (int64_t) bytes;
+    }
+    if (!d) { setErr("out of device memory for the resident inputs"); return VCE_ERR_CUDA; }
+    CUDA_TRY(cudaMemcpyAsync(d, pinned, bytes, cudaMemcpyHostToDevice, mStream_[lane]));
+    CUDA_TRY(cudaEventRecord(ev, mStream_[lane]));
+    *dev = d;
+    return VCE_OK;
+  }
+
   // One search launch over the MicroB packets of every chunk built since the last flush.
   int microBuildFlush(const MicroConfig& mc) override {
     CUDA_TRY(cudaSetDevice(device_));
@@ -1451,6 +1497,65 @@ class CudaBackend : public Backend {
   std::mutex errMu_;
   std::string err_;
 };
+
+// ---- registered templates: device-resident 2-bit copies, per device, keyed by the caller's pointer + length
+namespace {
+struct TemplateEntry { const uint8_t* bases; int32_t len; int device; uint32_t* t2; uint32_t* nmask; };
+std::mutex g_tmplMu;
+std::vector<TemplateEntry> g_templates;
+}  // namespace
+
+bool templateRegistryLookup(int device, const uint8_t* bases, int32_t len, const uint32_t** t2, const uint32_t** nmask) {
+  std::lock_guard<std::mutex> lk(g_tmplMu);
+  for (const TemplateEntry& e : g_templates) {
+    if (e.bases == bases && e.len == len && e.device == device) {
+      *t2 = e.t2;
+      *nmask = e.nmask;
+      return true;
+    }
+  }
+  return false;
+}
+
+int templateRegistryAdd(int device, const uint8_t* bases, int32_t len, const uint32_t* packed, size_t words, const uint32_t* nmask,
+                        size_t mwords, std::string& err) {
+  templateRegistryRemove(device, bases);
+  if (cudaSetDevice(device) != cudaSuccess) { err = "cudaSetDevice failed"; return VCE_ERR_CUDA; }
+  uint32_t* d2 = nullptr;
+  uint32_t* dn = nullptr;
+  // (a few words of slack: the packet builder may look one granule beyond the last base)
+  if (cudaMalloc(&d2, (words + 8) * 4) != cudaSuccess || cudaMalloc(&dn, (mwords + 8) * 4) != cudaSuccess) {
+    if (d2) cudaFree(d2);
+    err = "out of device memory for the resident template";
+    return VCE_ERR_CUDA;
+  }
+  cudaMemset(d2 + words, 0, 32);
+  cudaMemset(dn + mwords, 0, 32);
+  if (cudaMemcpy(d2, packed, words * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(dn, nmask, mwords * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaFree(d2);
+    cudaFree(dn);
+    err = "template upload failed";
+    return VCE_ERR_CUDA;
+  }
+  std::lock_guard<std::mutex> lk(g_tmplMu);
+  g_templates.push_back(TemplateEntry{bases, len, device, d2, dn});
+  return VCE_OK;
+}
+
+void templateRegistryRemove(int device, const uint8_t* bases) {
+  std::lock_guard<std::mutex> lk(g_tmplMu);
+  for (size_t i = 0; i < g_templates.size();) {
+    if ((device < 0 || g_templates[i].device == device) && (bases == nullptr || g_templates[i].bases == bases)) {
+      cudaSetDevice(g_templates[i].device);
+      cudaFree(g_templates[i].t2);
+      cudaFree(g_templates[i].nmask);
+      g_templates.erase(g_templates.begin() + (long) i);
+    } else {
+      ++i;
+    }
+  }
+}
 
 Backend* createCudaBackend(int device, std::string& err) {
   CudaBackend* b = new CudaBackend(device);

@@ -18,6 +18,13 @@ void cudaBackendFastStats(Backend* b, double* ms, long long* regions, long long*
 // Device milliseconds and region count of the last single-launch thread-per-region search (staged jobs).
 void cudaBackendMicroStats(Backend* b, double* ms, long long* regions);
 
+// Registered templates (vce_template_register): device-resident copies, 2 bits per base (base - 1, 16 bases per word) and
+// one bit per 16-base granule that holds a base other than A/C/G/T.
+bool templateRegistryLookup(int device, const uint8_t* bases, int32_t len, const uint32_t** t2, const uint32_t** nmask);
+int templateRegistryAdd(int device, const uint8_t* bases, int32_t len, const uint32_t* packed, size_t words, const uint32_t* nmask,
+                        size_t mwords, std::string& err);
+void templateRegistryRemove(int device, const uint8_t* bases);   // device < 0: every device; bases == nullptr: every template
+
 struct RocTiming { double h2dMs = 0, kernelMs = 0; int launches = 0; };
 int rocRun(int device, const vce_roc_in* in, vce_roc_out* out, std::string& err, RocTiming* timing);
 

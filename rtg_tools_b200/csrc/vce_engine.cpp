@@ -67,6 +67,38 @@ struct RowPick {  // selects one orientation row of a variant (host side of K1, 
 };
 }  // namespace
 
+void packTemplate(const uint8_t* bases, int32_t len, WorkerPool* pool, std::vector<uint32_t>& packed, std::vector<uint32_t>& nmask) {
+  const size_t words = ((size_t) len + 15) / 16;
+  const size_t mwords = (words + 31) / 32;
+  packed.assign(words, 0);
+  nmask.assign(mwords, 0);
+  const size_t block = 4096;   // mask words per task (2 Mi bases)
+  auto work = [&](int t, int) {
+    const size_t m0 = (size_t) t * block, m1 = std::min(mwords, m0 + block);
+    for (size_t m = m0; m < m1; ++m) {
+      uint32_t mask = 0;
+      for (int gi = 0; gi < 32; ++gi) {
+        const size_t w = m * 32 + (size_t) gi;
+        if (w >= words) break;
+        const size_t p0 = w * 16;
+        uint32_t v = 0;
+        bool other = false;
+        for (int q = 0; q < 16 && p0 + q < (size_t) len; ++q) {
+          const unsigned b = bases[p0 + q];
+          if (b < 1 || b > 4) other = true;
+          v |= ((b - 1u) & 3u) << (2 * q);
+        }
+        packed[w] = v;
+        if (other) mask |= 1u << gi;
+      }
+      nmask[m] = mask;
+    }
+  };
+  const int nTasks = (int) ((mwords + block - 1) / block);
+  if (pool) pool->parallelFor(nTasks, work);
+  else for (int t = 0; t < nTasks; ++t) work(t, 0);
+}
+
 Engine::Engine(Backend* b, WorkerPool* pool, const EngineOptions& o) : be_(b), pool_(pool), opt_(o) {
   classCount_.resize(pool_->threads());
   classKeys_.resize(pool_->threads());
@@ -969,6 +1001,181 @@ int Engine::buildChunkDevice(PassCtx& pc, Chunk& ch, int worker) {
   return rc;
 }
 
+// Resident inputs.  For every sequence of the pass whose template is registered on the backend's device
+// (vce_template_register) and whose sides are already in (start, end) order, the caller's arrays are uploaded WHOLE, once:
+// one page-locked block per side (parallel memcpys of the arrays as they are, no per-region work), one asynchronous copy.
+// The packet builder then reads the sequence through a PacketView of device pointers and cuts every reference window out of
+// the device copy of the template: the host digest of such a sequence is the region split plus a list of regions per chunk.
+int Engine::residentSetup(PassCtx& pc) {
+  resident_.assign((size_t) nSeq_, ResidentSeq());
+  if (!opt_.residentInputs || !opt_.deviceBuild || !pc.microOk || pc.pass != 0) return VCE_OK;
+  struct Task { int k, side; };
+  std::vector<Task> tasks;
+  for (int k = 0; k < nSeq_; ++k) {
+    if (pc.shortCircuit[k] || pc.ss[0][k].idx != nullptr || pc.ss[1][k].idx != nullptr) continue;
+    ResidentSeq& rsq = resident_[k];
+    if (!be_->templateLookup(seqs_[k].template_bases, seqs_[k].template_len, &rsq.t2, &rsq.nmask)) continue;
+    rsq.on = true;
+    tasks.push_back(Task{k, 0});
+    tasks.push_back(Task{k, 1});
+  }
+  if (tasks.empty()) return VCE_OK;
+  std::sort(tasks.begin(), tasks.end(), [&](const Task& a, const Task& b) { return pc.ss[a.side][a.k].n > pc.ss[b.side][b.k].n; });
+  std::atomic<int> failed(0);
+  pool_->parallelFor((int) tasks.size(), [&](int t, int) {
+    if (failed.load()) return;
+    const int k = tasks[t].k, side = tasks[t].side;
+    const SideSeq& ss = pc.ss[side][k];
+    const vce_variants& in = *ss.in;
+    const size_t n = (size_t) ss.n, nSl = (size_t) in.allele_off[ss.n], nNt = (size_t) in.allele_nt_off[nSl];
+    const int P = in.gt_ploidy;
+    size_t at = 0;
+    auto place = [&](size_t bytes) { const size_t o = at; at = (at + bytes + 15) & ~(size_t) 15; return o; };
+    const size_t oVs = place(n * 4 + 4), oVe = place(n * 4 + 4), oGt = place(n * (size_t) std::max(1, P) + 4);
+    const size_t oPh = place(n + 4), oSt = place(n + 4), oAo = place((n + 1) * 4);
+    const size_t oAs = place(nSl * 4 + 4), oAe = place(nSl * 4 + 4), oAn = place(nSl + 4), oNo = place((nSl + 1) * 4), oNt = place(nNt + 4);
+    uint8_t* blk = arenaAlloc(at + 16);
+    if (!blk) { failed.store(VCE_ERR_CUDA); return; }
+    std::memcpy(blk + oVs, pc.vStart[side].data() + ss.first, n * 4);
+    std::memcpy(blk + oVe, pc.vEnd[side].data() + ss.first, n * 4);
+    if (P > 0) std::memcpy(blk + oGt, in.gt, n * (size_t) P);
+    if (in.phased) std::memcpy(blk + oPh, in.phased, n);
+    if (in.status_in) std::memcpy(blk + oSt, in.status_in, n);
+    std::memcpy(blk + oAo, in.allele_off, (n + 1) * 4);
+    std::memcpy(blk + oAs, in.allele_start, nSl * 4);
+    std::memcpy(blk + oAe, in.allele_end, nSl * 4);
+    std::memcpy(blk + oAn, in.allele_null, nSl);
+    std::memcpy(blk + oNo, in.allele_nt_off, (nSl + 1) * 4);
+    std::memcpy(blk + oNt, in.nt, nNt);
+    void* dev = nullptr;
+    int ev = -1;
+    const int r = be_->residentUpload(blk, at, &dev, &ev);
+    if (r) { failed.store(r); return; }
+    const uint8_t* d = static_cast<const uint8_t*>(dev);
+    ResidentSeq& rsq = resident_[k];
+    PacketSideView& v = rsq.dv.s[side];
+    v.vStart = reinterpret_cast<const int32_t*>(d + oVs) - ss.first;   // indexed with pass-wide variant indices
+    v.vEnd = reinterpret_cast<const int32_t*>(d + oVe) - ss.first;
+    v.sideEnd = ss.first + ss.n;
+    v.first = ss.first;
+    v.idx = nullptr;
+    v.gtPloidy = P;
+    v.gt = reinterpret_cast<const int8_t*>(d + oGt);
+    v.phased = in.phased ? d + oPh : nullptr;
+    v.statusIn = in.status_in ? d + oSt : nullptr;
+    v.alleleOff = reinterpret_cast<const int32_t*>(d + oAo);
+    v.aStart = reinterpret_cast<const int32_t*>(d + oAs);
+    v.aEnd = reinterpret_cast<const int32_t*>(d + oAe);
+    v.aNull = d + oAn;
+    v.aNtOff = reinterpret_cast<const int32_t*>(d + oNo);
+    v.nt = d + oNt;
+    rsq.events[side] = ev;
+  });
+  if (failed.load()) {
+    err_ = be_->lastError();
+    if (err_.empty()) err_ = "out of page-locked host memory";
+    return failed.load();
+  }
+  for (int k = 0; k < nSeq_; ++k) {
+    ResidentSeq& rsq = resident_[k];
+    if (!rsq.on) continue;
+    rsq.dv.tl = seqs_[k].template_len;
+    rsq.dv.H = pc.H;
+    rsq.dv.margin = opt_.microMargin;
+    rsq.dv.expectPloidy[0] = pc.gtPloidy[0];
+    rsq.dv.expectPloidy[1] = pc.gtPloidy[1];
+  }
+  return VCE_OK;
+}
+
+// One chunk of a resident sequence: the packet-shaped regions go to the device as they are (16 bytes each); windows,
+// alleles and genotypes are read there.  A region the builder cannot pack comes back as a fallback record.
+int Engine::buildChunkResident(PassCtx& pc, Chunk& ch, int worker) {
+  const int k = ch.seq;
+  if (!resident_[k].on || !ch.list.empty()) return opt_.deviceBuild ? buildChunkDevice(pc, ch, worker) : buildChunk(pc, ch, worker, true);
+  const long long tA = nowNs();
+  uint8_t* cls = pc.rcls[k].data();
+  RegRes* rs = pc.rs[k].data();
+  const RegRange* rrk = pc.rr[k].data();
+  for (int c = 0; c < 2; ++c) {
+    ch.pktRegion[c].clear();
+    ch.job[c] = MicroJob();
+    ch.job[c].cls = c;
+  }
+  ch.variants = 0;
+  ch.variantsA = 0;
+  for (int j = ch.r0; j < ch.r1; ++j) {
+    if (cls[j] == kClsEarly) continue;  // already running in the warp-per-region kernels
+    const RegRange& g = rrk[j];
+    int c = -1;
+    if (j != 0) {  // the first path of a sequence starts at -1 and is not in sync (HalfPath.java:50-57)
+      if (g.cCount <= MicroA::KV && g.bCount <= MicroA::KV) c = 0;
+      else if (g.cCount <= MicroB::KV && g.bCount <= MicroB::KV) c = 1;
+    }
+    if (c < 0) {
+      if (!ch.transient) cls[j] = 0;
+      rs[j].state = RS_RESIDUAL;
+      continue;
+    }
+    ch.pktRegion[c].push_back(j);
+    cls[j] = (uint8_t) (1 + c);
+    rs[j].state = RS_PENDING;
+    ch.variants += g.cCount + g.bCount;
+    if (c == 0) ch.variantsA += g.cCount + g.bCount;
+  }
+  const int nA = (int) ch.pktRegion[0].size(), nB = (int) ch.pktRegion[1].size();
+  if (nA + nB == 0) { g_tBuild += nowNs() - tA; return VCE_OK; }
+  MicroBuildJob bj;
+  const size_t bytes = ((size_t) (nA + nB) * sizeof(RegRange) + 15) & ~(size_t) 15;
+  uint8_t* slab = arenaAlloc(bytes + 16);
+  if (!slab) {
+    std::lock_guard<std::mutex> lk(errMu_);
+    err_ = "out of page-locked host memory";
+    return VCE_ERR_CUDA;
+  }
+  RegRange* regs = reinterpret_cast<RegRange*>(slab);
+  int q = 0;
+  for (int c = 0; c < 2; ++c) for (int32_t j : ch.pktRegion[c]) regs[q++] = rrk[j];
+  const ResidentSeq& rsq = resident_[k];
+  bj.slab = slab;
+  bj.slabBytes = bytes;
+  bj.regions = 0;
+  bj.resident = true;
+  bj.rv = rsq.dv;
+  bj.t2 = rsq.t2;
+  bj.nmask = rsq.nmask;
+  bj.waitEvents[0] = rsq.events[0];
+  bj.waitEvents[1] = rsq.events[1];
+  bj.tl = rsq.dv.tl;
+  bj.H = rsq.dv.H;
+  bj.margin = rsq.dv.margin;
+  bj.expectPloidy[0] = rsq.dv.expectPloidy[0];
+  bj.expectPloidy[1] = rsq.dv.expectPloidy[1];
+  bj.nA = nA;
+  bj.nB = nB;
+  for (int c = 0; c < 2; ++c) {
+    MicroJob& job = ch.job[c];
+    job.n = c == 0 ? nA : nB;
+    job.resBytes = c == 0 ? MicroA::RES_BYTES : MicroB::RES_BYTES;
+    if (job.n == 0) continue;
+    job.results = arenaAlloc((size_t) job.n * job.resBytes);
+    if (!job.results) {
+      std::lock_guard<std::mutex> lk(errMu_);
+      err_ = "out of page-locked host memory";
+      return VCE_ERR_CUDA;
+    }
+  }
+  const long long tB = nowNs();
+  g_tBuild += tB - tA;
+  const int rc = be_->microBuildRun(bj, ch.job[0], ch.job[1], pc.mc);
+  g_tUpload += nowNs() - tB;
+  if (rc) {
+    std::lock_guard<std::mutex> lk(errMu_);
+    err_ = be_->lastError();
+  }
+  return rc;
+}
+
 // Splits the pass into regions, builds + uploads (+ starts, when `launch`) every chunk.
 static inline bool orientorPairMicro(int kc, int kb, int H) { return microOrientorSupported(kc, H) && microOrientorSupported(kb, H); }
 
@@ -1061,9 +1268,11 @@ int Engine::execute() {
       tm.lap("split into regions");
       if ((rc = wideStart(pc, pc.earlyItems, early))) return rc;
       tm.lap("early warp-per-region batch");
+      if ((rc = residentSetup(pc))) return rc;
+      tm.lap("resident inputs: staging + upload");
       pool_->parallelFor((int) pc.chunks.size(), [&](int t, int worker) {
         if (failed.load()) return;
-        const int r = opt_.deviceBuild ? buildChunkDevice(pc, pc.chunks[t], worker) : buildChunk(pc, pc.chunks[t], worker, true);
+        const int r = opt_.deviceBuild ? buildChunkResident(pc, pc.chunks[t], worker) : buildChunk(pc, pc.chunks[t], worker, true);
         if (r) failed.store(r);
       });
       if (opt_.deviceBuild && !failed.load() && (rc = be_->microBuildFlush(pc.mc))) { err_ = be_->lastError(); return rc; }

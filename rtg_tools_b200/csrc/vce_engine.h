@@ -39,7 +39,12 @@ struct EngineOptions {
   int splitSegment = 1 << 16;  // variants per segment of the parallel region split
   bool sortPackets = true;     // hand the packets of a chunk to the kernel grouped by shape class (lock-step lanes)
   bool deviceBuild = true;     // vce_submit: pack the packets on the device from wholesale copies of the caller's arrays
+  bool residentInputs = true;  // sequences with a registered template: whole-sequence upload, windows cut out on the device
 };
+
+// Host side of vce_template_register: 2 bits per base (base - 1; 16 bases per word) and one bit per 16-base granule that
+// holds a base other than A/C/G/T (bit g & 31 of word g >> 5, g = position >> 4).
+void packTemplate(const uint8_t* bases, int32_t len, WorkerPool* pool, std::vector<uint32_t>& packed, std::vector<uint32_t>& nmask);
 
 class Engine {
  public:
@@ -156,6 +161,17 @@ class Engine {
   template <class T> int buildPacket(const PassCtx& pc, const PacketSrc& ps, int j, uint8_t* out) const;
   int buildChunk(PassCtx& pc, Chunk& ch, int worker, bool launch);
   int buildChunkDevice(PassCtx& pc, Chunk& ch, int worker);
+  // resident inputs (registered template + whole-sequence upload): see residentSetup
+  struct ResidentSeq {
+    bool on = false;
+    PacketView dv;                 // device pointers to the sequence's arrays
+    const uint32_t* t2 = nullptr;  // device copy of the template
+    const uint32_t* nmask = nullptr;
+    int events[2] = {-1, -1};
+  };
+  std::vector<ResidentSeq> resident_;
+  int residentSetup(PassCtx& pc);
+  int buildChunkResident(PassCtx& pc, Chunk& ch, int worker);
   int runChunks(PassCtx& pc);
   void decodeChunk(PassCtx& pc, Chunk& ch, int64_t& iterations);
   void assembleRegionEarly(PassCtx& pc, int k, int j);

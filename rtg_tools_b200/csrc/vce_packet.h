@@ -73,11 +73,39 @@ VCE_HD bool microWindow(const PacketView& pv, const RegRange& g, int32_t* winSta
   return true;
 }
 
+// Where the reference bases of a window come from: the caller's template bytes (host digest, slab copies), or the
+// device-resident copy of a registered template (vce_template_register): 2 bits per base (base - 1), 16 bases per word,
+// plus one bit per 16-base granule that holds a base other than A/C/G/T (such windows are not packets).
+struct WinBytes {
+  const uint8_t* p;   // reference base of relative position 0
+  VCE_HD int at(int q) const { return p[q]; }
+};
+struct WinPacked {
+  const uint32_t* t2;
+  const uint32_t* nmask;
+  int32_t start;      // template position of relative position 0
+  VCE_HD int at(int q) const {
+    const uint32_t pos = (uint32_t) (start + q);
+    if ((nmask[pos >> 9] >> ((pos >> 4) & 31u)) & 1u) return 0;
+    return (int) ((t2[pos >> 4] >> ((pos & 15u) * 2u)) & 3u) + 1;
+  }
+};
+
 // Writes the packet of region `g` to `out` (T::PKT_MAX bytes available); returns its length in bytes, 0 when the region
-// does not fit the thread-per-region kernel.  `win` points at the reference base of relative position 0.
+// does not fit the thread-per-region kernel.  `win` delivers the reference bases from relative position 0.
+template <class T, class Win>
+VCE_HD int microBuildPacketW(const PacketView& pv, const RegRange& g, int32_t winStart, int32_t winLen, const int32_t nextStart[2],
+                             const Win& win, uint8_t* out);
+
 template <class T>
 VCE_HD int microBuildPacket(const PacketView& pv, const RegRange& g, int32_t winStart, int32_t winLen, const int32_t nextStart[2],
                             const uint8_t* win, uint8_t* out) {
+  return microBuildPacketW<T, WinBytes>(pv, g, winStart, winLen, nextStart, WinBytes{win}, out);
+}
+
+template <class T, class Win>
+VCE_HD int microBuildPacketW(const PacketView& pv, const RegRange& g, int32_t winStart, int32_t winLen, const int32_t nextStart[2],
+                             const Win& win, uint8_t* out) {
   if (g.cCount > T::KV || g.bCount > T::KV) return 0;
   const int first[2] = {g.cFirst, g.bFirst};
   const int count[2] = {g.cCount, g.bCount};
@@ -128,7 +156,7 @@ VCE_HD int microBuildPacket(const PacketView& pv, const RegRange& g, int32_t win
     }
   }
   const int winBase = nBases;
-  for (int q = 0; q < winLen; ++q) raw[nBases + q] = win[q];
+  for (int q = 0; q < winLen; ++q) raw[nBases + q] = (uint8_t) win.at(q);
   nBases += winLen;
   raw[nBases] = raw[nBases + 1] = raw[nBases + 2] = 1;  // padding of the last 2-bit byte
   for (int q = 0; q < nAl * MA_BYTES; ++q) vout[q] = alleles[q];

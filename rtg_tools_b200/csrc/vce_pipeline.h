@@ -98,6 +98,13 @@ struct MicroBuildJob {
   size_t slabBytes = 0;
   MicroBuildSide side[2];
   int32_t tl = 0, H = 0, expectPloidy[2] = {0, 0}, margin = 0;
+  // resident mode (registered template + whole-sequence upload, Backend::residentUpload): the slab holds the regions only,
+  // `rv` carries device pointers to the sequence's arrays, the windows are cut out of the device copy of the template
+  bool resident = false;
+  PacketView rv;
+  const uint32_t* t2 = nullptr;
+  const uint32_t* nmask = nullptr;
+  int waitEvents[2] = {-1, -1};    // uploads (Backend::residentUpload) the builder has to wait for
   int64_t regions = 0;             // RegRange[nA + nB]: the MicroA-shaped regions, then the MicroB-shaped ones
   int64_t winOff = 0;              // uint32[nA + nB]: offset of each region's window bases within `windows`
   int64_t windows = 0;             // uint8[]: reference bases from each region's window start
@@ -151,6 +158,12 @@ class Backend {
   // device -> host copies of the results: a.n == b.nA records for the MicroA-shaped regions, bj.n == b.nB for the others.
   // A region that does not fit a packet comes back with status kMicroFallback.  Asynchronous; microWait() collects.
   virtual int microBuildRun(MicroBuildJob& b, MicroJob& a, MicroJob& bj, const MicroConfig& mc) = 0;
+  // ---- resident inputs.  A registered template (vce_template_register) lives on the device as 2 bits per base + a map of
+  // the 16-base granules that hold anything else; false when `bases` is not registered on this backend's device.
+  virtual bool templateLookup(const uint8_t* /*bases*/, int32_t /*len*/, const uint32_t** /*t2*/, const uint32_t** /*nmask*/) { return false; }
+  // Asynchronous host -> device copy of one block of page-locked memory (from hostAlloc); *dev is valid right away for
+  // pointer arithmetic, the data once event *eventId has passed (MicroBuildJob::waitEvents).
+  virtual int residentUpload(const void* /*pinned*/, size_t /*bytes*/, void** /*dev*/, int* /*eventId*/) { return VCE_ERR_UNSUPPORTED; }
   // The backend may hold the MicroB-shaped regions of the chunks back and search them in one launch: call this once every
   // chunk has been handed over (the MicroJob objects have to stay where they are until then).
   virtual int microBuildFlush(const MicroConfig&) { return 0; }

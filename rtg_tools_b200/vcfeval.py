@@ -113,6 +113,28 @@ class Engine:
     def submit(self, cfg: capi.Config, seqs: List[capi.Sequence]) -> List[capi.SequenceResult]:
         return self.lib.submit(cfg, seqs)
 
+    def register_templates(self, seqs: List[capi.Sequence]) -> int:
+        """vce_template_register for every sequence: the reference sequences become resident on the device (load phase,
+        as the reference reads them from the SDF before matching, SequenceEvaluator.java:76-86).  Returns the bytes registered."""
+        lib = self.lib.lib
+        lib.vce_template_register.restype = C.c_int
+        lib.vce_template_register.argtypes = [C.c_void_p, C.c_int32]
+        total = 0
+        for s in seqs:
+            s.template = np.ascontiguousarray(s.template, np.uint8)
+            rc = lib.vce_template_register(s.template.ctypes.data, int(s.template.shape[0]))
+            if rc != 0:
+                raise RuntimeError("vce_template_register: %s %s" % (capi.ERR_NAMES.get(rc, rc), self.lib.last_error()))
+            total += int(s.template.shape[0])
+        return total
+
+    def unregister_templates(self, seqs: List[capi.Sequence]) -> None:
+        lib = self.lib.lib
+        lib.vce_template_unregister.restype = C.c_int
+        lib.vce_template_unregister.argtypes = [C.c_void_p]
+        for s in seqs:
+            lib.vce_template_unregister(s.template.ctypes.data)
+
     def submit_stats(self) -> dict:
         """Diagnostics of the calling thread's last submit(): launches, H2D / D2H bytes, regions, iterations."""
         out = (C.c_double * 6)()

@@ -11,7 +11,7 @@ from helpers import fuzz_batch  # noqa: E402
 from rtg_tools_b200 import capi, synth, vcfeval  # noqa: E402
 
 eng = vcfeval.Engine(0)
-seqs = synth.make_pair(6_000_000, n_chrom=3)
+seqs = synth.make_pair(int(os.environ.get("SAN_BP", "6000000")), n_chrom=3)
 for seed in range(6):
     seqs += fuzz_batch(seed, n_seq=3)
 rng = np.random.default_rng(3)

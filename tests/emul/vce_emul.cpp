@@ -65,7 +65,8 @@ class EmulBackend : public Backend {
       int32_t winStart = 0, winLen = 0, nextStart[2];
       int bytes = 0;
       if (microWindow(pv, regs[q0 + q], &winStart, &winLen, nextStart)) {
-        bytes = microBuildPacket<T>(pv, regs[q0 + q], winStart, winLen, nextStart, b.slab + b.windows + winOff[q0 + q], pk.data());
+        if (b.resident) bytes = microBuildPacketW<T>(pv, regs[q0 + q], winStart, winLen, nextStart, WinPacked{b.t2, b.nmask, winStart}, pk.data());
+        else bytes = microBuildPacket<T>(pv, regs[q0 + q], winStart, winLen, nextStart, b.slab + b.windows + winOff[q0 + q], pk.data());
       }
       if (bytes <= 0) {
         std::memset(res, 0, (size_t) j.resBytes);
@@ -80,8 +81,22 @@ class EmulBackend : public Backend {
       if (res[MR_STATUS] == kMicroClean) ++microClean;
     }
   }
+  // resident inputs, emulated: "device" pointers are the page-locked host blocks themselves
+  struct Tmpl { const uint8_t* bases; int32_t len; std::vector<uint32_t> t2, nmask; };
+  static std::vector<Tmpl>& templates() { static std::vector<Tmpl> t; return t; }
+  bool templateLookup(const uint8_t* bases, int32_t len, const uint32_t** t2, const uint32_t** nmask) override {
+    for (const Tmpl& t : templates()) if (t.bases == bases && t.len == len) { *t2 = t.t2.data(); *nmask = t.nmask.data(); return true; }
+    return false;
+  }
+  int residentUpload(const void* pinned, size_t, void** dev, int* eventId) override {
+    *dev = const_cast<void*>(pinned);
+    *eventId = 0;
+    ++residentUploads;
+    return 0;
+  }
+  std::atomic<int64_t> residentUploads{0};
   int microBuildRun(MicroBuildJob& b, MicroJob& a, MicroJob& bj, const MicroConfig& mc) override {
-    const PacketView pv = microBuildView(b, b.slab);
+    const PacketView pv = b.resident ? b.rv : microBuildView(b, b.slab);
     buildRunT<MicroA>(b, pv, 0, a, mc);
     buildRunT<MicroB>(b, pv, b.nA, bj, mc);
     microRegions += a.n + bj.n;
@@ -330,6 +345,30 @@ void emul_set_split(int variantsPerSegment) { g_split = variantsPerSegment; }
 int g_deviceBuild = 1;   // the product default
 void emul_set_device_build(int on) { g_deviceBuild = on; }
 
+// test hook of vce_template_register for the emulation (host copies); len <= 0 forgets every template
+void emul_template_register(const uint8_t* bases, int32_t len) {
+  std::vector<EmulBackend::Tmpl>& ts = EmulBackend::templates();
+  if (len <= 0) { ts.clear(); return; }
+  ts.emplace_back();
+  ts.back().bases = bases;
+  ts.back().len = len;
+  packTemplate(bases, len, nullptr, ts.back().t2, ts.back().nmask);
+  // slack, as on the device: the builder may look one granule beyond the last base
+  ts.back().t2.resize(ts.back().t2.size() + 8, 0);
+  ts.back().nmask.resize(ts.back().nmask.size() + 8, 0);
+}
+// test hook: what WinPacked delivers for one template position (0 = the position's granule holds a non-ACGT base)
+uint32_t emul_template_word(const uint8_t* bases, int32_t len, int32_t pos, int32_t) {
+  std::vector<uint32_t> t2, nm;
+  packTemplate(bases, len, nullptr, t2, nm);
+  t2.resize(t2.size() + 8, 0);
+  nm.resize(nm.size() + 8, 0);
+  const WinPacked w{t2.data(), nm.data(), pos};
+  return (uint32_t) w.at(0);
+}
+int64_t g_residentUploads = 0;
+int64_t emul_resident_uploads() { return g_residentUploads; }
+
 // forceCta: every warp-path region starts in the CTA kernel's tiers; nb / pool: shrink its frontier directory / record pool
 // (exercises the overflow hand-over to the large-capacity kernel)
 void emul_set_cta(int forceCta, int nb, long long pool) { g_forceCta = forceCta; g_ctaNb = nb; g_ctaPool = pool; }
@@ -358,6 +397,7 @@ int emul_vce_submit(const vce_config* cfg, int32_t n_seq, const vce_sequence* se
   g_stats[0] = be.stats.regions; g_stats[1] = be.stats.escalated; g_stats[2] = be.stats.spilled;
   g_stats[3] = be.stats.prefixReruns; g_stats[4] = be.stats.launches; g_stats[5] = be.microRegions.load(); g_stats[6] = be.microClean.load();
   g_stats[7] = be.ctaRegions.load() | (be.ctaOverflows.load() << 32);
+  g_residentUploads = be.residentUploads.load();
   return rc;
 }
 

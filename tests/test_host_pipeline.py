@@ -106,6 +106,46 @@ def test_cta_kernel_hands_over_what_its_arena_cannot_hold(emul, oracle, nb, pool
         _set_cta(emul, 0)
 
 
+def _register(emul, seqs):
+    emul.lib.emul_template_register.argtypes = [ctypes.c_void_p, ctypes.c_int32]
+    emul.lib.emul_resident_uploads.restype = ctypes.c_int64
+    for s in seqs:
+        s.template = np.ascontiguousarray(s.template, np.uint8)
+        emul.lib.emul_template_register(s.template.ctypes.data, int(s.template.shape[0]))
+
+
+@pytest.mark.parametrize("cfg_name", ["default", "twopass", "squash", "phased"])
+def test_resident_inputs_are_exact(emul, oracle, cfg_name):
+    """Registered templates (vce_template_register): whole-sequence upload, windows cut out of the 2-bit copy of the
+    template by the packet builder (N bases, window clipping at the template end, unsorted sides that stay on the host path)."""
+    seqs = synth.make_pair(1_500_000, n_chrom=3)
+    for seed in range(8):
+        seqs += fuzz_batch(7300 + seed)
+    seqs += [synth.dense_cluster_sequence(np.random.default_rng(2), n_clusters=2, per_side=(4, 8), name="dense")]
+    try:
+        _register(emul, seqs)
+        got = emul.submit(CONFIGS[cfg_name], seqs)
+        assert emul.lib.emul_resident_uploads() > 0
+        compare_results(oracle.submit(CONFIGS[cfg_name], seqs), got, seqs, what=cfg_name)
+    finally:
+        emul.lib.emul_template_register(None, 0)
+    # and the very same inputs without the resident copies
+    compare_results(oracle.submit(CONFIGS[cfg_name], seqs), emul.submit(CONFIGS[cfg_name], seqs), seqs, what=cfg_name)
+    assert emul.lib.emul_resident_uploads() == 0
+
+
+def test_template_packing_marks_every_non_acgt_granule(emul):
+    rng = np.random.default_rng(4)
+    t = rng.integers(1, 5, size=10_007, dtype=np.uint8)
+    t[[5, 16, 4000, 10_006]] = 0
+    emul.lib.emul_template_word.restype = ctypes.c_uint32
+    emul.lib.emul_template_word.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]
+    for pos in range(0, 10_007, 7):
+        got = emul.lib.emul_template_word(t.ctypes.data, 10_007, pos, 0)
+        want = 0 if not t[(pos // 16) * 16:(pos // 16) * 16 + 16].all() else int(t[pos])
+        assert got == want, (pos, got, want)
+
+
 def test_synthetic_genome_pair(emul, oracle):
     seqs = synth.make_pair(3_000_000, n_chrom=3)
     assert sum(s.calls.n for s in seqs) > 3000
