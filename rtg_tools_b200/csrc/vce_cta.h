@@ -59,7 +59,7 @@ namespace cta {
 constexpr int kBlk = 128;            // entries per block
 constexpr int kKeyW = 16;            // key words (4 per haplotype, calls h0 h1, baseline h0 h1)
 constexpr int kAuxW = 4;             // tie-break words
-constexpr int kQ = 4;                // pending alleles per haplotype a key holds
+constexpr int kQ = 8;                // pending alleles per haplotype a key holds with 8-bit ranks (4 with 16-bit ranks)
 constexpr int kSmaxCap = 44;         // sync points per record
 constexpr int kMaxW = 128;           // record words (one 16-byte chunk per lane)
 constexpr int kMaxWork = 8;          // work slots in shared memory that hold the head and its children (+ last-sync, best)
@@ -101,14 +101,17 @@ struct HostLaneMove : HostLane {
 
 // Record layout of a region in the CTA kernel: queue capacity of the keys, as many sync points as a 128-word record
 // allows.  Returns false when no layout fits (the region then runs in the large-capacity warp kernel).
-VCE_HD bool ctaLayout(PathLayout& L, int H, int cCount, int bCount, int decBits) {
+// Ranks fit 8 bits (and a key holds eight pending alleles per haplotype) when neither side has more than 254 allele slots.
+VCE_HD bool ctaNarrowRanks(int cSlotN, int bSlotN) { return cSlotN <= 254 && bSlotN <= 254; }
+VCE_HD bool ctaLayout(PathLayout& L, int H, int cCount, int bCount, int decBits, bool narrowRanks) {
   const int kv = cCount > bCount ? cCount : bCount;
+  const int q = narrowRanks ? cta::kQ : cta::kQ / 2;
   int smax = cCount + bCount + 2;
   if (smax > cta::kSmaxCap) smax = cta::kSmaxCap;
-  L.init(H, cta::kQ, kv < 1 ? 1 : kv, smax, decBits);
+  L.init(H, q, kv < 1 ? 1 : kv, smax, decBits);
   while (L.W > cta::kMaxW && smax > 8) {
     smax -= 4;
-    L.init(H, cta::kQ, kv < 1 ? 1 : kv, smax, decBits);
+    L.init(H, q, kv < 1 ? 1 : kv, smax, decBits);
   }
   return L.W <= cta::kMaxW;
 }
@@ -144,6 +147,7 @@ struct CtaSearch {
   int pfSlot;
   Quad pf[WP::L == 1 ? cta::kMaxW / 4 : 1];
   bool unsupported;
+  bool narrow;          // 8-bit ranks (ctaNarrowRanks)
 
   VCE_HD explicit CtaSearch(RegionConst* k) : rs(k) {}
 
@@ -174,11 +178,15 @@ struct CtaSearch {
         if (nx >= 0) {
           k1 = ((uint32_t) (rankOf(side, nx) + 1) << 16) | (uint32_t) (hp[HP_PIA] + 1);
           const int ql = hp[HP_QINFO] & 0xffff;
-          uint32_t qv[cta::kQ] = {0, 0, 0, 0};
+          // the pending alleles, most significant first, absent = 0: eight 8-bit ranks or four 16-bit ranks
+          const int bits = narrow ? 8 : 16;
           VCE_NOUNROLL
-          for (int i = 0; i < ql && i < cta::kQ; ++i) qv[i] = (uint32_t) (rankOf(side, hp[HP_Q0 + i]) + 1);
-          k2 = (qv[0] << 16) | qv[1];
-          k3 = (qv[2] << 16) | qv[3];
+          for (int i = 0; i < ql; ++i) {
+            const uint32_t rk = (uint32_t) (rankOf(side, hp[HP_Q0 + i]) + 1);
+            const int bit = i * bits;
+            if (bit < 32) k2 |= rk << (32 - bits - bit);
+            else k3 |= rk << (64 - bits - bit);
+          }
         }
       }
       key[q * 4 + 0] = k0; key[q * 4 + 1] = k1; key[q * 4 + 2] = k2; key[q * 4 + 3] = k3;
@@ -229,6 +237,7 @@ struct CtaSearch {
   // alleles share a rank).  Also checks what the keys cannot hold.
   VCE_HD void computeRanks() {
     unsupported = false;
+    narrow = ctaNarrowRanks(rs.R.cSlotN, rs.R.bSlotN);
     VCE_NOUNROLL
     for (int side = 0; side < 2; ++side) {
       const int s0 = side == 0 ? rs.R.cSlot0 : rs.R.bSlot0, sn = side == 0 ? rs.R.cSlotN : rs.R.bSlotN;
@@ -276,9 +285,11 @@ struct CtaSearch {
     cdirty[c] = 0;
   }
   // Cache slot holding block `id` (loaded if necessary); `keep` = a slot that must not be evicted (-1 = none).
+  long long statHit = 0, statMiss = 0, statInsFront = 0, statInsFar = 0, statMaxQ = 0;   // diagnostics (emulation / debug builds)
   VCE_HD int ensureCached(int id, int keep, bool load) {
     ++useClock;
-    for (int c = 0; c < shape.ncache; ++c) if (cid[c] == id) { cuse[c] = useClock; return c; }
+    for (int c = 0; c < shape.ncache; ++c) if (cid[c] == id) { cuse[c] = useClock; ++statHit; return c; }
+    if (load) ++statMiss;
     int victim = -1;
     for (int c = 0; c < shape.ncache; ++c) {
       if (c == keep) continue;
@@ -544,6 +555,7 @@ struct CtaSearch {
     w.sync();
     const uint32_t* auxNew = keyNew + cta::kKeyW;
     int bi = findBlock(keyNew);
+    if (bi == 0) ++statInsFront; else ++statInsFar;
     VCE_CTA_CHECK(bi >= 0 && bi < nbUsed && dh >= 0 && dh + nbUsed <= 2 * shape.nb, 8, bi, nbUsed);
     int id = dir[dh + bi];
     int c = ensureCached(id, -1, true);
@@ -841,7 +853,7 @@ struct CtaSearch {
       if (fl & R_::FL_ERRORDER) return kRegionErrOrder;
       if (fl & R_::FL_ERRMOVE) return kRegionErrMove;
       if (fl & R_::FL_OVERFLOW) return kRegionOverflow;
-      if (fl & R_::FL_WINMISS) return kRegionSpill;
+      if (fl & R_::FL_WINMISS) return kRegionWinMiss;
 
       if (act == R_::ACT_BOUNDARY_CLEAN) { resultSlot = head; return kRegionClean; }
       if (act == R_::ACT_BOUNDARY_SPILL) return kRegionSpill;

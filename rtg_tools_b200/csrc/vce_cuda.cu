@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(32) k_cta(const __grid_constant__ CtaParams cp
     bool ok = true;
     {
       PathLayout PL;
-      ok = ctaLayout(PL, p.H, kc->R.cCount, kc->R.bCount, kc->R.decBits ? kc->R.decBits : 4);
+      ok = ctaLayout(PL, p.H, kc->R.cCount, kc->R.bCount, kc->R.decBits ? kc->R.decBits : 4, ctaNarrowRanks(kc->R.cSlotN, kc->R.bSlotN));
       if (lane == 0) kc->L = PL;
     }
     cs.rs.regionId = p.regionBase + r;

@@ -31,7 +31,8 @@ enum : int32_t {
   kRegionOverflow = 4,   // exceeded this kernel's capacity: re-run in the large-capacity kernel
   kRegionErrNull = 5,    // best path null (SequenceEvaluator.java:105)
   kRegionErrMove = 6,    // moveForward while in a variant (HaplotypePlayback.java:260)
-  kRegionErrOrder = 7    // out of order alleles (HaplotypePlayback.java:208)
+  kRegionErrOrder = 7,   // out of order alleles (HaplotypePlayback.java:208)
+  kRegionWinMiss = 8     // a haplotype ran off the staged reference window: re-run with a wider window
 };
 
 // One independent search region (a run of variants on both sides separated from its neighbours by a gap).

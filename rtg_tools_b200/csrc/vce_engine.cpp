@@ -453,6 +453,47 @@ void Engine::splitAll(PassCtx& pc) {
         }
         out.insert(out.end(), so.begin() + (long) from, so.end());
       }
+      // Dense clusters (several variants per side a few bases apart, typically in a tandem repeat) rarely come back in
+      // sync at a gap of a few bases: their pieces would SPILL into each other one merge and one full re-run at a time.
+      // Neighbours closer than denseGap are joined up front when one of them is already crowded.  Any coarser split is
+      // exact; sparse genomes have almost no such regions, so this costs them nothing.
+      if (opt_.denseGap > opt_.gap && out.size() > 1) {
+        const int32_t* cs = pc.vStart[0].data();
+        const int32_t* ce = pc.vEnd[0].data();
+        const int32_t* bs = pc.vStart[1].data();
+        const int32_t* bee = pc.vEnd[1].data();
+        auto crowded = [&](const RegRange& g) { return g.cCount >= opt_.denseCount || g.bCount >= opt_.denseCount; };
+        auto maxEndOf = [&](const RegRange& g) {
+          long m = LONG_MIN;
+          for (int v = g.cFirst; v < g.cFirst + g.cCount; ++v) m = std::max(m, (long) ce[v]);
+          for (int v = g.bFirst; v < g.bFirst + g.bCount; ++v) m = std::max(m, (long) bee[v]);
+          return m;
+        };
+        auto firstStartOf = [&](const RegRange& g) {
+          long m = LONG_MAX;
+          if (g.cCount > 0) m = std::min(m, (long) cs[g.cFirst]);
+          if (g.bCount > 0) m = std::min(m, (long) bs[g.bFirst]);
+          return m;
+        };
+        bool any = false;
+        for (size_t j = 0; j + 1 < out.size() && !any; ++j) any = crowded(out[j]) || crowded(out[j + 1]);
+        if (any) {
+          size_t w = 0;
+          long curEnd = maxEndOf(out[0]);
+          for (size_t j = 1; j < out.size(); ++j) {
+            const RegRange& g = out[j];
+            if ((crowded(out[w]) || crowded(g)) && firstStartOf(g) - curEnd < (long) opt_.denseGap) {
+              out[w].cCount += g.cCount;
+              out[w].bCount += g.bCount;
+              curEnd = std::max(curEnd, maxEndOf(g));
+            } else {
+              out[++w] = g;
+              curEnd = maxEndOf(g);
+            }
+          }
+          out.resize(w + 1);
+        }
+      }
     }
     pc.rs[k].resize(out.size());
     pc.rcls[k].assign(out.size(), 0);
@@ -1454,7 +1495,9 @@ int Engine::widePack(PassCtx& pc, const std::vector<std::pair<RegKey, int>>& ite
       }
       if (lo == INT_MAX) lo = 0;
       const int ws = std::max(0, std::min(lo, d.startPos < 0 ? 0 : d.startPos) - 1);
-      long we = extra < 0 ? (long) d.tmplLen : sz[q].hi + opt_.margin + extra;
+      // regions of the CTA tiers sit in repeats more often than not: a wider window from the start (there are few of them)
+      const int baseMargin = wb.tier[q] >= kTierMid ? std::max(opt_.margin, opt_.wideMargin) : opt_.margin;
+      long we = extra < 0 ? (long) d.tmplLen : sz[q].hi + baseMargin + extra;
       we = std::min(we, (long) d.tmplLen);
       if (we < ws) we = ws;
       d.winStart = ws;
@@ -1797,6 +1840,14 @@ int Engine::settle(PassCtx& pc, WideBatch& early) {
         if (nt < kTierMid && std::max(g.cCount, g.bCount) > fastShape(nt).kv) nt = kTierMid;
         todo.push_back(std::make_pair(all[q].first, nt));
         ++be_->stats.escalated;
+      } else if (st == kRegionWinMiss) {
+        // a haplotype ran off the reference window (long repeats keep paths apart for longer than the margin): the same
+        // region again with a wider window -- merging with the next region would drag that region's variants in for nothing
+        Rare& ra = pc.rare[key(k, j)];
+        if (ra.extraMargin < 0) { err_ = "window miss with the whole template in the window"; return VCE_ERR_CAPACITY; }
+        ra.extraMargin = ra.extraMargin == 0 ? 1024 : (ra.extraMargin >= (1 << 20) ? -1 : ra.extraMargin * 16);
+        todo.push_back(std::make_pair(all[q].first, std::max(ra.tier, startTier(pc, pc.rr[k][j]))));
+        pc.rs[k][j].state = RS_RESIDUAL;
       } else if (st == kRegionSpill) {
         Rare& ra = pc.rare[key(k, j)];
         ++be_->stats.spilled;

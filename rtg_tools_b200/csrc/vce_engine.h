@@ -32,6 +32,9 @@ struct EngineOptions {
                           // keep an indel and its shifted re-representation in one region instead of a SPILL + merge
   int margin = 24;        // reference bases beyond the last variant end of a region (warp-per-region kernels)
   int microMargin = 12;   // same, thread-per-region kernel
+  int wideMargin = 192;   // same, regions that start in the CTA tiers
+  int denseGap = 256;     // neighbouring regions closer than this are joined up front when one of them already holds ...
+  int denseCount = 3;     // ... this many variants on a side (dense clusters in repeats spill into each other otherwise)
   bool forceGeneral = false;   // tests: every region through the large-capacity kernel
   bool forceCta = false;       // tests: every warp-path region through the CTA kernel
   bool disableMicro = false;   // tests: no thread-per-region kernel

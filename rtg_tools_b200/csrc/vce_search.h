@@ -980,7 +980,7 @@ struct RegionSearch {
       if (fl & FL_ERRORDER) return kRegionErrOrder;
       if (fl & FL_ERRMOVE) return kRegionErrMove;
       if (fl & FL_OVERFLOW) return kRegionOverflow;
-      if (fl & FL_WINMISS) return kRegionSpill;
+      if (fl & FL_WINMISS) return kRegionWinMiss;
 
       if (act == ACT_BOUNDARY_CLEAN) { resultSlot = head; return kRegionClean; }
       if (act == ACT_BOUNDARY_SPILL) return kRegionSpill;

@@ -207,7 +207,8 @@ class EmulBackend : public Backend {
     cs.rs.maxChildren = 1 + mo;
     cs.shape = ctaShape(tier);
     if (ctaNbOverride > 0) cs.shape.nb = ctaNbOverride;
-    const bool layoutOk = ctaLayout(cs.rs.L, pd.H, regs[q].cCount, regs[q].bCount, regs[q].decBits ? regs[q].decBits : 4);
+    const bool layoutOk = ctaLayout(cs.rs.L, pd.H, regs[q].cCount, regs[q].bCount, regs[q].decBits ? regs[q].decBits : 4,
+                                     ctaNarrowRanks(regs[q].cSlotN, regs[q].bSlotN));
     std::vector<uint32_t> sm((size_t) ctaSmemWords(cs.shape) + 64);
     cs.carve(sm.data());
     std::vector<uint16_t> ranks((size_t) regs[q].cSlotN + regs[q].bSlotN + 2);
@@ -238,6 +239,13 @@ class EmulBackend : public Backend {
     }
     ++ctaRegions;
     if (st == kRegionOverflow) ++ctaOverflows;
+    if (std::getenv("VCE_EMUL_DEBUG")) {
+      fprintf(stderr, "[emul] cta tier %d region %zu: %dx%d status %d iterations %d maxFrontier %d flags %d layoutOk %d W %d SMAX %d\n", tier, q,
+              regs[q].cCount, regs[q].bCount, st, cs.rs.totalIters, cs.rs.maxFrontier, cs.rs.ctl[RegionSearch<HostLaneMove, false>::CTL_FLAGS],
+              (int) layoutOk, cs.rs.L.W, cs.rs.L.SMAX);
+      fprintf(stderr, "[emul]    block cache: %lld hits %lld misses; inserts into the front block %lld, elsewhere %lld\n", cs.statHit, cs.statMiss,
+              cs.statInsFront, cs.statInsFar);
+    }
     out[q] = rr;
   }
   int ctaNbOverride = 0;
