@@ -236,6 +236,14 @@ int  vce_job_stats_ex(const vce_job* job, double* out, int32_t n);
    regions settled by the warp-per-region kernels, best-first iterations. */
 int  vce_submit_stats(double* out, int32_t n);
 
+/*
+ * Summary of the calling thread's last vce_submit, per sequence: out[k * 8 + i] = baseline TP, baseline FN (incl. FN_CA),
+ * call TP, call FP (incl. FP_CA), skipped variants (both sides), mis-phasings, correct phasings, unphaseable -- the classes
+ * of the split writers (SplitEvalSynchronizer.java:112-156: a matched call of weight 0 and OUTSIDE_EVAL variants count
+ * nowhere).  Counted on the device together with the per-variant outputs when the device-resident result path ran.
+ */
+int vce_submit_summary(int64_t* out, int32_t n_seq);
+
 /* RocContainer accumulate + sort + cumulative scan on the device. */
 int vce_roc(const vce_roc_in* in, vce_roc_out* out);
 /* Same, also reporting host->device and kernel milliseconds (CUDA events) and the number of kernel launches. */

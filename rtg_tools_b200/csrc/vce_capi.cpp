@@ -64,6 +64,7 @@ Context* acquire(int& rc) {
   if (const char* e = std::getenv("VCE_SPLIT_GAP")) opt.gap = std::max(1, std::atoi(e));
   if (const char* e = std::getenv("VCE_DEVICE_BUILD")) opt.deviceBuild = std::atoi(e) != 0;
   if (const char* e = std::getenv("VCE_RESIDENT")) opt.residentInputs = std::atoi(e) != 0;
+  if (const char* e = std::getenv("VCE_DEVICE_RESULTS")) opt.deviceResults = std::atoi(e) != 0;
   c->engine.reset(new vce::Engine(c->backend.get(), g_pool.get(), opt));
   return c;
 }
@@ -219,6 +220,14 @@ int vce_job_stats_ex(const vce_job* job, double* out, int32_t n) {
 }
 
 static thread_local double t_submitStats[6] = {0, 0, 0, 0, 0, 0};
+static thread_local std::vector<int64_t> t_summary;
+
+int vce_submit_summary(int64_t* out, int32_t n_seq) {
+  if (!out || n_seq < 0) return fail(VCE_ERR_BAD_ARGUMENT, "null argument");
+  if ((size_t) n_seq * 8 > t_summary.size()) return fail(VCE_ERR_BAD_ARGUMENT, "no vce_submit of that many sequences on this thread");
+  std::memcpy(out, t_summary.data(), (size_t) n_seq * 8 * sizeof(int64_t));
+  return VCE_OK;
+}
 
 int vce_submit_stats(double* out, int32_t n) {
   if (!out) return fail(VCE_ERR_BAD_ARGUMENT, "null argument");
@@ -235,6 +244,7 @@ int vce_submit(const vce_config* cfg, int32_t n_seq, const vce_sequence* seqs, v
   if (const char* e = std::getenv("VCE_DEVICE_BUILD")) c->engine->options().deviceBuild = std::atoi(e) != 0;   // contexts are pooled
   rc = c->engine->run(*cfg, n_seq, seqs, results);
   const std::string msg = rc ? c->engine->error() : std::string();
+  t_summary = c->engine->summary();
   {
     const vce::SearchStats& s = c->backend->stats;
     t_submitStats[0] = (double) s.launches; t_submitStats[1] = (double) s.h2dBytes; t_submitStats[2] = (double) s.d2hBytes;

@@ -27,6 +27,7 @@
 #include "vce_orient.h"
 #include "vce_search.h"
 #include "vce_cta.h"
+#include "vce_final_cuda.cuh"
 
 namespace vce {
 
@@ -671,7 +672,8 @@ class CudaBackend : public Backend {
     CUDA_TRY(cudaFuncSetAttribute(k_search<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
     CUDA_TRY(cudaFuncSetAttribute(k_search<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (4096 + 1024) * kFastWarps));
     CUDA_TRY(cudaFuncSetAttribute(k_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
-    if (const char* e = std::getenv("VCE_MID_KERNEL")) oldMid_ = std::string(e) == "old";   // diagnostics: the round-1 HBM-arena warp kernel
+    if (const char* e = std::getenv("VCE_MID_KERNEL")) oldMid_ = std::string(e) != "cta";   // "cta": mid tier through the CTA kernel (slower there, measured)
+    if (const char* e = std::getenv("VCE_CTA_BIG")) ctaBig_ = std::atoi(e) != 0;
     if (const char* e = std::getenv("VCE_CTA_TMA")) ctaTma_ = std::atoi(e) != 0;
     CUDA_TRY(cudaFuncSetAttribute(k_class_order, cudaFuncAttributeMaxDynamicSharedMemorySize, (kClassBins + 32) * (int) sizeof(uint32_t)));
     if (const char* e = std::getenv("VCE_CLASS_ORDER")) classOrder_ = std::atoi(e) != 0;
@@ -814,6 +816,19 @@ class CudaBackend : public Backend {
     return VCE_OK;
   }
 
+  // HBM for the search arenas of one launch: most of what is free (a B200 has 180 GB and this engine's inputs are small), so
+  // that a batch of huge regions keeps every SM full of resident regions
+  long long arenaBudgetBytes() {
+    size_t freeB = 0, totalB = 0;
+    long long budget = 24ll << 30;
+    if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
+      const long long avail = (long long) freeB + (long long) arena_.cap * 4;
+      budget = std::max<long long>(4ll << 30, std::min<long long>(96ll << 30, avail * 6 / 10));
+    }
+    if (const char* e = std::getenv("VCE_ARENA_GB")) budget = std::max(1, std::atoi(e)) * (1ll << 30);
+    return budget;
+  }
+
   cudaError_t ensureSync(size_t total) {
     // the device sync buffer mirrors the host one (which grows when regions are merged)
     if (total > syncBuf_.cap) {
@@ -889,7 +904,11 @@ class CudaBackend : public Backend {
       const size_t nt = (size_t) (r1 - r0);
       SearchParams& sp = spT[tier];
       std::memset(&sp, 0, sizeof(sp));
-      isCta[tier] = (tier == kTierMid && !oldMid_) || tier == kTierCta;
+      // The CTA kernel (vce_cta.h) is the LATENCY tier: one warp per region with ~100 KB of shared memory, two regions per SM.
+      // It takes the full-budget tier while the batch fits one wave of CTAs; a larger batch of huge regions is a THROUGHPUT
+      // problem and runs in the warp kernel with up to 24 resident regions per SM (measured, profiles/r02_*: per iteration the
+      // two kernels cost about the same, ~13 us, so concurrency decides).
+      isCta[tier] = (tier == kTierMid && !oldMid_) || (tier == kTierCta && ctaBig_ && (long long) nt <= (long long) smCount_ * 2);
       sp.regs = regs_.p + r0; sp.nRegs = (int) nt;
       sp.S[0] = sideArrays(0); sp.S[1] = sideArrays(1);
       sp.windows = windows_.p; sp.cfg = sc; sp.out = rres_.p + r0; sp.syncOff = syncOff_.p + r0; sp.syncOut = syncBuf_.p;
@@ -942,7 +961,7 @@ class CudaBackend : public Backend {
         const long long mc = sp.maxChildren;
         const long long pool = std::min<long long>(cp.shape.capacity(), (long long) sc.maxPaths + 1 + mc) + 64;
         long long words = (ctaArenaWords(cp.shape, cta::kMaxW, pool) + 3) & ~3LL;
-        const long long budgetWords = (long long) (24ull << 30) / 4;  // 24 GB of HBM for search arenas
+        const long long budgetWords = arenaBudgetBytes() / 4;
         long long ctasWanted = std::min<long long>((long long) nt, (long long) smCount_ * perSm);
         ctasWanted = std::min(ctasWanted, std::max<long long>(1, budgetWords / words));
         blocks = (int) ctasWanted;
@@ -959,7 +978,7 @@ class CudaBackend : public Backend {
         // queued block evens out the tail)
         static const int bps = std::getenv("VCE_GENERAL_BPS") ? std::max(1, std::atoi(std::getenv("VCE_GENERAL_BPS"))) : 4;
         long long words = (capFull + 1 + mc + 2) * maxW + (3 * capFull + 1024) + (capFull + 1 + mc) + 16 + 2 * mc + 64;
-        const long long budgetWords = (long long) (24ull << 30) / 4;  // 24 GB of HBM for search arenas
+        const long long budgetWords = arenaBudgetBytes() / 4;
         long long warpsWanted = std::min<long long>((long long) nt, (long long) smCount_ * kFastWarps * bps);
         words = (words + 3) & ~3LL;
         if (words > budgetWords) words = budgetWords;  // a single region larger than the budget runs with reduced capacity
@@ -1265,7 +1284,7 @@ class CudaBackend : public Backend {
         j.event = mNextEvent_++;
         j.evHandle = mEvents_[j.event];
         if (!j.dPackets || !j.dOffsets || !j.dResults) { setErr("out of device memory for region packets"); return VCE_ERR_CUDA; }
-        stats.d2hBytes += (int64_t) j.n * j.resBytes;
+        if (!b.scatter) stats.d2hBytes += (int64_t) j.n * j.resBytes;
         // k_build, and for MicroA the search launch (+ the class ordering); the MicroB search is counted by the flush
         stats.launches += c == 0 ? (dKeys != nullptr ? 3 : 2) : 1;
       }
@@ -1332,20 +1351,199 @@ class CudaBackend : public Backend {
               mEvents_.push_back(e);
             }
             built = mEvents_[mNextEvent_++];
-            pendingB_.push_back(PendingB{&j, built});
+            pendingB_.push_back(PendingB{&j, built, bp.regs, b.scatter ? reinterpret_cast<const int32_t*>(base + b.regIdx) + q0 : nullptr, b.scatter});
           }
           CUDA_TRY(cudaEventRecord(built, st));
           continue;
         }
         microLaunch(mp, c, st);
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaMemcpyAsync(j.results, j.dResults, (size_t) j.n * j.resBytes, cudaMemcpyDeviceToHost, st));
+        if (b.scatter) scatterLaunch(j, bp.regs, reinterpret_cast<const int32_t*>(base + b.regIdx) + q0, st);
+        else CUDA_TRY(cudaMemcpyAsync(j.results, j.dResults, (size_t) j.n * j.resBytes, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(j.evHandle), st));
       }
       q0 += c == 0 ? b.nA : 0;
     }
     return VCE_OK;
   }
+  // ---------------------------------------------------------------- device-resident results (vce_final.h)
+  template <class T>
+  struct PinBuf {   // page-locked host buffer, grows only
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+      if (n <= cap) return cudaSuccess;
+      if (p) cudaFreeHost(p);
+      p = nullptr;
+      cap = 0;
+      const size_t want = n + n / 8 + 64;
+      cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&p), want * sizeof(T), cudaHostAllocDefault);
+      if (e == cudaSuccess) cap = want;
+      return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  };
+  bool resultsSupported() const override { return true; }
+  int resultsBegin(const ResultsSetup& s) override {
+    CUDA_TRY(cudaSetDevice(device_));
+    rs_ = s;
+    const size_t nC = (size_t) s.nVar[0], nB = (size_t) s.nVar[1], nR = (size_t) s.nReg, nS = s.seq.size();
+    CUDA_TRY(rDec_[0].ensure(nC + 16)); CUDA_TRY(rDec_[1].ensure(nB + 16)); CUDA_TRY(rWeight_.ensure(nC + 2));
+    CUDA_TRY(rInfo_.ensure(nR + 2)); CUDA_TRY(rCnt_.ensure(nR + 2)); CUDA_TRY(rBase_.ensure(nR + 2)); CUDA_TRY(rRel_.ensure((nR + 2) * kFinalRel));
+    CUDA_TRY(rSeq_.ensure(nS + 1)); CUDA_TRY(rIter_.ensure(2));
+    std::vector<FinalSeq> fs(nS);
+    for (size_t k = 0; k < nS; ++k) {
+      for (int side = 0; side < 2; ++side) {
+        fs[k].vStart[side] = s.seq[k].vStart[side];
+        fs[k].phased[side] = s.seq[k].phased[side];
+        fs[k].statusIn[side] = s.seq[k].statusIn[side];
+        fs[k].first[side] = s.seq[k].first[side];
+        fs[k].n[side] = s.seq[k].n[side];
+      }
+      fs[k].regFirst = s.seq[k].regFirst;
+      fs[k].nReg = s.seq[k].nReg;
+    }
+    cudaStream_t st = mStream_[0];
+    CUDA_TRY(cudaMemsetAsync(rInfo_.p, 0, (nR + 2) * sizeof(uint32_t), st));
+    CUDA_TRY(cudaMemsetAsync(rIter_.p, 0, 2 * sizeof(unsigned long long), st));
+    if (nS) CUDA_TRY(cudaMemcpyAsync(rSeq_.p, fs.data(), nS * sizeof(FinalSeq), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));   // the chunks' scatter kernels run on every lane
+    stats.h2dBytes += (int64_t) (nS * sizeof(FinalSeq));
+    return VCE_OK;
+  }
+  void scatterLaunch(const MicroJob& j, const RegRange* regs, const int32_t* regIdx, cudaStream_t st) {
+    ScatterArgs a;
+    a.results = static_cast<const uint8_t*>(j.dResults);
+    a.regs = regs;
+    a.regIdx = regIdx;
+    a.packets = static_cast<const uint8_t*>(j.dPackets);
+    a.offsets = static_cast<const uint32_t*>(j.dOffsets);
+    a.n = j.n;
+    a.resBytes = j.resBytes;
+    a.kv = j.cls == 0 ? MicroA::KV : MicroB::KV;
+    a.smax = j.cls == 0 ? MicroA::SMAX : MicroB::SMAX;
+    a.dec[0] = rDec_[0].p; a.dec[1] = rDec_[1].p;
+    a.weight = rWeight_.p;
+    a.regInfo = rInfo_.p; a.regCnt = rCnt_.p; a.regBase = rBase_.p; a.regRel = rRel_.p;
+    a.iterations = rIter_.p;
+    k_scatter<<<(j.n + 255) / 256, 256, 0, st>>>(a);
+    std::lock_guard<std::mutex> lk(mMu_);
+    ++stats.launches;
+  }
+  int resultsRegInfo(const uint32_t** info, int64_t* iterations) override {
+    CUDA_TRY(cudaSetDevice(device_));
+    for (int i = 0; i < kMicroLanes; ++i) CUDA_TRY(cudaStreamSynchronize(mStream_[i]));
+    const size_t nR = (size_t) rs_.nReg;
+    CUDA_TRY(hInfo_.ensure(nR + 2));
+    cudaStream_t st = mStream_[0];
+    unsigned long long it[2] = {0, 0};
+    if (nR) CUDA_TRY(cudaMemcpyAsync(hInfo_.p, rInfo_.p, nR * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(it, rIter_.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    stats.d2hBytes += (int64_t) (nR * sizeof(uint32_t));
+    *info = hInfo_.p;
+    *iterations = (int64_t) it[0];
+    return VCE_OK;
+  }
+  template <class T>
+  int upVec(DevBuf<T>& d, const std::vector<T>& v, cudaStream_t st) {
+    CUDA_TRY(d.ensure(v.size() + 4));
+    if (!v.empty()) CUDA_TRY(cudaMemcpyAsync(d.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    stats.h2dBytes += (int64_t) (v.size() * sizeof(T));
+    return VCE_OK;
+  }
+  int resultsFinish(const ResultsPatch& p, ResultsOut& out) override {
+    CUDA_TRY(cudaSetDevice(device_));
+    cudaStream_t st = mStream_[0];
+    const size_t nC = (size_t) rs_.nVar[0], nB = (size_t) rs_.nVar[1], nR = (size_t) rs_.nReg, nS = rs_.seq.size();
+    int rc;
+    if ((rc = upVec(pRegIdx_, p.regIdx, st)) || (rc = upVec(pInfo_, p.info, st)) || (rc = upVec(pSyncOff_, p.syncOff, st)) ||
+        (rc = upVec(pSyncCnt_, p.syncCnt, st)) || (rc = upVec(pRange_, p.range, st)) || (rc = upVec(pPayOff_, p.payOff, st)) ||
+        (rc = upVec(pDec_, p.decPay, st)) || (rc = upVec(pWOff_, p.wOff, st)) || (rc = upVec(pW_, p.wPay, st)) ||
+        (rc = upVec(pSync_, p.extSync, st))) {
+      return rc;
+    }
+    if (!p.regIdx.empty()) {
+      PatchArgs a;
+      a.n = (int) p.regIdx.size();
+      a.regIdx = pRegIdx_.p; a.info = pInfo_.p; a.syncOff = pSyncOff_.p; a.syncCnt = pSyncCnt_.p; a.range = pRange_.p;
+      a.payOff = pPayOff_.p; a.decPay = pDec_.p; a.wOff = pWOff_.p; a.wPay = pW_.p;
+      a.dec[0] = rDec_[0].p; a.dec[1] = rDec_[1].p; a.weight = rWeight_.p;
+      a.regInfo = rInfo_.p; a.regCnt = rCnt_.p; a.regBase = rBase_.p;
+      k_patch<<<(a.n + 127) / 128, 128, 0, st>>>(a);
+      CUDA_TRY(cudaGetLastError());
+      ++stats.launches;
+    }
+    // scratch of the final passes
+    const size_t nFlatMax = nC + nB + 2 * nR + 4;
+    CUDA_TRY(fRegOff_.ensure(nR + 2)); CUDA_TRY(fKeys_.ensure(nFlatMax)); CUDA_TRY(fUniq_.ensure(nFlatMax)); CUDA_TRY(fPos_.ensure(nFlatMax));
+    CUDA_TRY(fSeqSync_.ensure(nS + 2)); CUDA_TRY(fOutC_.ensure(nC * 16 + 16)); CUDA_TRY(fOutB_.ensure(nB * 8 + 16));
+    CUDA_TRY(fCounters_.ensure(nS * 8 + 8)); CUDA_TRY(fKept_.ensure(nC + 2)); CUDA_TRY(fMStart_.ensure(nC + 2)); CUDA_TRY(fMFlags_.ensure(nC + 2));
+    CUDA_TRY(fMSeq_.ensure(nC + 2)); CUDA_TRY(fMVal_.ensure(nC + 2)); CUDA_TRY(fMMin_.ensure(nC + 2)); CUDA_TRY(fBaseSum_.ensure(nFlatMax));
+    CUDA_TRY(fCall0_.ensure(nFlatMax + nS + 2));
+    const size_t nBlocksMax = nFlatMax / kPhaseBlock + nS + 2;
+    CUDA_TRY(fBlockEnd_.ensure(nBlocksMax * 16)); CUDA_TRY(fBlockCnt_.ensure(nBlocksMax * 16 * 3)); CUDA_TRY(fSeqBlock_.ensure(nS + 2));
+    if (rs_.rocTuples) CUDA_TRY(fRoc_.ensure(nC * 3 + 3));
+    CUDA_TRY(ints_.ensure(16));
+    FinalArrays A;
+    A.nSeq = (int) nS; A.H = rs_.H; A.kind[0] = rs_.kind[0]; A.kind[1] = rs_.kind[1];
+    A.seq = rSeq_.p;
+    A.nVar[0] = rs_.nVar[0]; A.nVar[1] = rs_.nVar[1]; A.nReg = rs_.nReg;
+    A.dec[0] = rDec_[0].p; A.dec[1] = rDec_[1].p; A.weight = rWeight_.p;
+    A.regInfo = rInfo_.p; A.regCnt = rCnt_.p; A.regBase = rBase_.p; A.regRel = rRel_.p; A.extSync = pSync_.p;
+    A.regOff = fRegOff_.p; A.syncKeys = fKeys_.p; A.syncUniq = fUniq_.p; A.syncPos = fPos_.p; A.seqSyncFirst = fSeqSync_.p;
+    A.outCalls = fOutC_.p; A.outBase = fOutB_.p; A.counters = fCounters_.p; A.rocTuples = rs_.rocTuples ? fRoc_.p : nullptr;
+    A.keptScan = fKept_.p; A.mStart = fMStart_.p; A.mFlags = fMFlags_.p; A.mSeq = fMSeq_.p; A.mVal = fMVal_.p; A.mMin = fMMin_.p;
+    A.regBaseSum = fBaseSum_.p; A.regCall0 = fCall0_.p; A.blockEnd = fBlockEnd_.p; A.blockCnt = fBlockCnt_.p; A.seqBlockFirst = fSeqBlock_.p;
+    finalOps_.st = st;
+    finalOps_.dCount = ints_.p + 14;
+    finalOps_.launches = 0;
+    finalOps_.err = cudaSuccess;
+    // (the offsets array is scanned in place over nReg + 1 entries: the last one has to be defined)
+    CUDA_TRY(cudaMemsetAsync(fRegOff_.p + nR, 0, sizeof(int32_t), st));
+    const int nSync = finalPasses(finalOps_, A);
+    if (finalOps_.err != cudaSuccess) {
+      char b[256];
+      snprintf(b, sizeof(b), "final passes failed: %s", cudaGetErrorString(finalOps_.err));
+      setErr(b);
+      return VCE_ERR_CUDA;
+    }
+    stats.launches += finalOps_.launches;
+    CUDA_TRY(hOutC_.ensure(nC * 16 + 16)); CUDA_TRY(hOutB_.ensure(nB * 8 + 16)); CUDA_TRY(hPos_.ensure((size_t) nSync + 4));
+    CUDA_TRY(hSeqSync_.ensure(nS + 2)); CUDA_TRY(hCounters_.ensure(nS * 8 + 8));
+    if (nC) CUDA_TRY(cudaMemcpyAsync(hOutC_.p, fOutC_.p, nC * 16, cudaMemcpyDeviceToHost, st));
+    if (nB) CUDA_TRY(cudaMemcpyAsync(hOutB_.p, fOutB_.p, nB * 8, cudaMemcpyDeviceToHost, st));
+    if (nSync) CUDA_TRY(cudaMemcpyAsync(hPos_.p, fPos_.p, (size_t) nSync * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(hSeqSync_.p, fSeqSync_.p, (nS + 1) * 4, cudaMemcpyDeviceToHost, st));
+    if (nS) CUDA_TRY(cudaMemcpyAsync(hCounters_.p, fCounters_.p, nS * 8 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    if (rs_.rocTuples) {
+      CUDA_TRY(hRoc_.ensure(nC * 3 + 3));
+      if (nC) CUDA_TRY(cudaMemcpyAsync(hRoc_.p, fRoc_.p, nC * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+      stats.d2hBytes += (int64_t) (nC * 3 * sizeof(double));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    stats.d2hBytes += (int64_t) (nC * 16 + nB * 8 + (size_t) nSync * 4 + (nS + 1) * 4 + nS * 64);
+    out.outCalls = hOutC_.p; out.outBase = hOutB_.p; out.syncPos = hPos_.p; out.seqSyncFirst = hSeqSync_.p;
+    out.counters = hCounters_.p; out.rocTuples = rs_.rocTuples ? hRoc_.p : nullptr; out.nSync = nSync;
+    return VCE_OK;
+  }
+  ResultsSetup rs_;
+  DevBuf<uint8_t> rDec_[2], rRel_, pDec_, fOutC_, fOutB_, fMFlags_, fBaseSum_, fBlockEnd_;
+  DevBuf<double> rWeight_, pW_, fRoc_;
+  DevBuf<uint32_t> rInfo_, pInfo_;
+  DevBuf<int32_t> rCnt_, rBase_, pRegIdx_, pSyncOff_, pSyncCnt_, pPayOff_, pWOff_, pSync_, fRegOff_, fPos_, fSeqSync_, fKept_, fMStart_, fMSeq_,
+      fMVal_, fMMin_, fCall0_, fBlockCnt_, fSeqBlock_;
+  DevBuf<int64_t> fKeys_, fUniq_, fCounters_;
+  DevBuf<RegRange> pRange_;
+  DevBuf<FinalSeq> rSeq_;
+  DevBuf<unsigned long long> rIter_;
+  PinBuf<uint32_t> hInfo_;
+  PinBuf<uint8_t> hOutC_, hOutB_;
+  PinBuf<int32_t> hPos_, hSeqSync_;
+  PinBuf<int64_t> hCounters_;
+  PinBuf<double> hRoc_;
+  CudaFinalOps finalOps_;
+
   // ---- resident inputs
   bool templateLookup(const uint8_t* bases, int32_t len, const uint32_t** t2, const uint32_t** nmask) override {
     return templateRegistryLookup(device_, bases, len, t2, nmask);
@@ -1409,18 +1607,20 @@ class CudaBackend : public Backend {
     CUDA_TRY(cudaGetLastError());
     for (const PendingB& pb : pend) {
       MicroJob& j = *pb.job;
-      CUDA_TRY(cudaMemcpyAsync(j.results, j.dResults, (size_t) j.n * j.resBytes, cudaMemcpyDeviceToHost, st));
+      if (pb.scatter) scatterLaunch(j, pb.regs, pb.regIdx, st);
+      else CUDA_TRY(cudaMemcpyAsync(j.results, j.dResults, (size_t) j.n * j.resBytes, cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(j.evHandle), st));
       j.lane = 1;
     }
     ++stats.launches;
     return VCE_OK;
   }
-  bool oldMid_ = false;   // mid tier through the HBM-arena warp kernel instead of the CTA kernel
+  bool oldMid_ = true;    // mid tier (frontiers up to 2048) through the HBM-arena warp kernel: 24 resident regions per SM
+  bool ctaBig_ = true;    // full-budget tier through the CTA kernel while the batch fits one wave
   bool ctaTma_ = true;    // the CTA kernel moves frontier blocks with bulk TMA copies
   static constexpr int kOrderMin = 256;   // smaller chunks are not worth the ordering launch
   bool classOrder_ = true;
-  struct PendingB { MicroJob* job; cudaEvent_t built; };
+  struct PendingB { MicroJob* job; cudaEvent_t built; const RegRange* regs; const int32_t* regIdx; bool scatter; };
   std::vector<PendingB> pendingB_;
   int microWait(MicroJob& j) override {
     CUDA_TRY(cudaSetDevice(device_));

@@ -939,6 +939,8 @@ int Engine::buildChunkDevice(PassCtx& pc, Chunk& ch, int worker) {
   size_t at = 0;
   auto place = [&](size_t bytes) { const size_t o = at; at = (at + bytes + 15) & ~(size_t) 15; return (int64_t) o; };
   bj.regions = place((size_t) (nA + nB) * sizeof(RegRange));
+  bj.scatter = devRes_;
+  if (devRes_) bj.regIdx = place((size_t) (nA + nB) * 4);
   bj.winOff = place((size_t) (nA + nB) * 4);
   bj.windows = place(winBytes + 8);
   int nV[2], nVs[2], nSl[2], nNt[2];
@@ -988,6 +990,7 @@ int Engine::buildChunkDevice(PassCtx& pc, Chunk& ch, int worker) {
     for (size_t i = 0; i < list.size(); ++i, ++q) {
       if (i + 24 < list.size()) __builtin_prefetch(tmpl + wsv[c][i + 24]);
       regs[q] = rrk[list[i]];
+      if (devRes_) reinterpret_cast<int32_t*>(slab + bj.regIdx)[q] = regBase_[k] + list[i];
       winOff[q] = (uint32_t) wo;
       std::memcpy(wins + wo, tmpl + wsv[c][i], (size_t) wlv[c][i]);
       wo += (size_t) wlv[c][i];
@@ -1049,14 +1052,16 @@ int Engine::buildChunkDevice(PassCtx& pc, Chunk& ch, int worker) {
 // the device copy of the template: the host digest of such a sequence is the region split plus a list of regions per chunk.
 int Engine::residentSetup(PassCtx& pc) {
   resident_.assign((size_t) nSeq_, ResidentSeq());
-  if (!opt_.residentInputs || !opt_.deviceBuild || !pc.microOk || pc.pass != 0) return VCE_OK;
+  if (!opt_.deviceBuild || !pc.microOk || pc.pass != 0) return VCE_OK;
   struct Task { int k, side; };
   std::vector<Task> tasks;
   for (int k = 0; k < nSeq_; ++k) {
     if (pc.shortCircuit[k] || pc.ss[0][k].idx != nullptr || pc.ss[1][k].idx != nullptr) continue;
     ResidentSeq& rsq = resident_[k];
-    if (!be_->templateLookup(seqs_[k].template_bases, seqs_[k].template_len, &rsq.t2, &rsq.nmask)) continue;
-    rsq.on = true;
+    rsq.on = opt_.residentInputs && be_->templateLookup(seqs_[k].template_bases, seqs_[k].template_len, &rsq.t2, &rsq.nmask);
+    // without a registered template only what the final passes read goes up whole (the packets come from chunk slabs)
+    if (!rsq.on && !devRes_) continue;
+    rsq.have = true;
     tasks.push_back(Task{k, 0});
     tasks.push_back(Task{k, 1});
   }
@@ -1070,30 +1075,41 @@ int Engine::residentSetup(PassCtx& pc) {
     const vce_variants& in = *ss.in;
     const size_t n = (size_t) ss.n, nSl = (size_t) in.allele_off[ss.n], nNt = (size_t) in.allele_nt_off[nSl];
     const int P = in.gt_ploidy;
+    const bool full = resident_[k].on;
     size_t at = 0;
     auto place = [&](size_t bytes) { const size_t o = at; at = (at + bytes + 15) & ~(size_t) 15; return o; };
-    const size_t oVs = place(n * 4 + 4), oVe = place(n * 4 + 4), oGt = place(n * (size_t) std::max(1, P) + 4);
-    const size_t oPh = place(n + 4), oSt = place(n + 4), oAo = place((n + 1) * 4);
-    const size_t oAs = place(nSl * 4 + 4), oAe = place(nSl * 4 + 4), oAn = place(nSl + 4), oNo = place((nSl + 1) * 4), oNt = place(nNt + 4);
+    const size_t oVs = place(n * 4 + 4), oPh = place(n + 4), oSt = place(n + 4);
+    size_t oVe = 0, oGt = 0, oAo = 0, oAs = 0, oAe = 0, oAn = 0, oNo = 0, oNt = 0;
+    if (full) {
+      oVe = place(n * 4 + 4); oGt = place(n * (size_t) std::max(1, P) + 4); oAo = place((n + 1) * 4);
+      oAs = place(nSl * 4 + 4); oAe = place(nSl * 4 + 4); oAn = place(nSl + 4); oNo = place((nSl + 1) * 4); oNt = place(nNt + 4);
+    }
     uint8_t* blk = arenaAlloc(at + 16);
     if (!blk) { failed.store(VCE_ERR_CUDA); return; }
     std::memcpy(blk + oVs, pc.vStart[side].data() + ss.first, n * 4);
-    std::memcpy(blk + oVe, pc.vEnd[side].data() + ss.first, n * 4);
-    if (P > 0) std::memcpy(blk + oGt, in.gt, n * (size_t) P);
     if (in.phased) std::memcpy(blk + oPh, in.phased, n);
     if (in.status_in) std::memcpy(blk + oSt, in.status_in, n);
-    std::memcpy(blk + oAo, in.allele_off, (n + 1) * 4);
-    std::memcpy(blk + oAs, in.allele_start, nSl * 4);
-    std::memcpy(blk + oAe, in.allele_end, nSl * 4);
-    std::memcpy(blk + oAn, in.allele_null, nSl);
-    std::memcpy(blk + oNo, in.allele_nt_off, (nSl + 1) * 4);
-    std::memcpy(blk + oNt, in.nt, nNt);
+    if (full) {
+      std::memcpy(blk + oVe, pc.vEnd[side].data() + ss.first, n * 4);
+      if (P > 0) std::memcpy(blk + oGt, in.gt, n * (size_t) P);
+      std::memcpy(blk + oAo, in.allele_off, (n + 1) * 4);
+      std::memcpy(blk + oAs, in.allele_start, nSl * 4);
+      std::memcpy(blk + oAe, in.allele_end, nSl * 4);
+      std::memcpy(blk + oAn, in.allele_null, nSl);
+      std::memcpy(blk + oNo, in.allele_nt_off, (nSl + 1) * 4);
+      std::memcpy(blk + oNt, in.nt, nNt);
+    }
     void* dev = nullptr;
     int ev = -1;
     const int r = be_->residentUpload(blk, at, &dev, &ev);
     if (r) { failed.store(r); return; }
     const uint8_t* d = static_cast<const uint8_t*>(dev);
     ResidentSeq& rsq = resident_[k];
+    rsq.fVStart[side] = reinterpret_cast<const int32_t*>(d + oVs);
+    rsq.fPhased[side] = in.phased ? d + oPh : nullptr;
+    rsq.fStatus[side] = in.status_in ? d + oSt : nullptr;
+    rsq.events[side] = ev;
+    if (!full) return;
     PacketSideView& v = rsq.dv.s[side];
     v.vStart = reinterpret_cast<const int32_t*>(d + oVs) - ss.first;   // indexed with pass-wide variant indices
     v.vEnd = reinterpret_cast<const int32_t*>(d + oVe) - ss.first;
@@ -1110,7 +1126,6 @@ int Engine::residentSetup(PassCtx& pc) {
     v.aNull = d + oAn;
     v.aNtOff = reinterpret_cast<const int32_t*>(d + oNo);
     v.nt = d + oNt;
-    rsq.events[side] = ev;
   });
   if (failed.load()) {
     err_ = be_->lastError();
@@ -1167,7 +1182,8 @@ int Engine::buildChunkResident(PassCtx& pc, Chunk& ch, int worker) {
   const int nA = (int) ch.pktRegion[0].size(), nB = (int) ch.pktRegion[1].size();
   if (nA + nB == 0) { g_tBuild += nowNs() - tA; return VCE_OK; }
   MicroBuildJob bj;
-  const size_t bytes = ((size_t) (nA + nB) * sizeof(RegRange) + 15) & ~(size_t) 15;
+  const size_t regBytes = ((size_t) (nA + nB) * sizeof(RegRange) + 15) & ~(size_t) 15;
+  const size_t bytes = regBytes + (devRes_ ? (((size_t) (nA + nB) * 4 + 15) & ~(size_t) 15) : 0);
   uint8_t* slab = arenaAlloc(bytes + 16);
   if (!slab) {
     std::lock_guard<std::mutex> lk(errMu_);
@@ -1175,8 +1191,16 @@ int Engine::buildChunkResident(PassCtx& pc, Chunk& ch, int worker) {
     return VCE_ERR_CUDA;
   }
   RegRange* regs = reinterpret_cast<RegRange*>(slab);
+  int32_t* regIdx = reinterpret_cast<int32_t*>(slab + regBytes);
   int q = 0;
-  for (int c = 0; c < 2; ++c) for (int32_t j : ch.pktRegion[c]) regs[q++] = rrk[j];
+  for (int c = 0; c < 2; ++c) {
+    for (int32_t j : ch.pktRegion[c]) {
+      if (devRes_) regIdx[q] = regBase_[k] + j;
+      regs[q++] = rrk[j];
+    }
+  }
+  bj.scatter = devRes_;
+  bj.regIdx = (int64_t) regBytes;
   const ResidentSeq& rsq = resident_[k];
   bj.slab = slab;
   bj.slabBytes = bytes;
@@ -1279,6 +1303,8 @@ int Engine::execute() {
   StageTimer tm;
   microMs = 0;
   microRegions = microVariants = 0;
+  devRes_ = !staged_ && liveResults_ != nullptr && wantDeviceResults(pass_[0]);
+  if (devRes_) liveResults_ = nullptr;   // nothing is assembled on the host while records are decoded: they never come back
   earlyUsed_ = liveResults_ != nullptr;
   if (earlyUsed_) {
     for (int side = 0; side < 2; ++side) {
@@ -1309,8 +1335,32 @@ int Engine::execute() {
       tm.lap("split into regions");
       if ((rc = wideStart(pc, pc.earlyItems, early))) return rc;
       tm.lap("early warp-per-region batch");
+      if (devRes_ && p == 0 && (rc = resultsSetup(pc))) return rc;
       if ((rc = residentSetup(pc))) return rc;
       tm.lap("resident inputs: staging + upload");
+      if (devRes_ && p == 0) {
+        ResultsSetup rsu;
+        rsu.H = pc.H;
+        rsu.kind[0] = pc.kind[0];
+        rsu.kind[1] = pc.kind[1];
+        rsu.seq.resize((size_t) nSeq_);
+        for (int k = 0; k < nSeq_; ++k) {
+          ResultsSeq& q = rsu.seq[(size_t) k];
+          for (int side = 0; side < 2; ++side) {
+            q.first[side] = pc.ss[side][k].first;
+            q.n[side] = pc.ss[side][k].n;
+            q.vStart[side] = resident_[k].fVStart[side];
+            q.phased[side] = resident_[k].fPhased[side];
+            q.statusIn[side] = resident_[k].fStatus[side];
+          }
+          q.regFirst = regBase_[k];
+          q.nReg = regBase_[k + 1] - regBase_[k];
+        }
+        for (int side = 0; side < 2; ++side) rsu.nVar[side] = nSeq_ > 0 ? pc.ss[side][nSeq_ - 1].first + pc.ss[side][nSeq_ - 1].n : 0;
+        rsu.nReg = regBase_[nSeq_];
+        if ((rc = be_->resultsBegin(rsu))) { err_ = be_->lastError(); return rc; }
+        tm.lap("device results: set-up");
+      }
       pool_->parallelFor((int) pc.chunks.size(), [&](int t, int worker) {
         if (failed.load()) return;
         const int r = opt_.deviceBuild ? buildChunkResident(pc, pc.chunks[t], worker) : buildChunk(pc, pc.chunks[t], worker, true);
@@ -1345,8 +1395,11 @@ int Engine::execute() {
     }
     if (failed.load()) return failed.load();
     std::vector<int64_t> iters(pool_->threads(), 0);
+    if (devRes_ && p == 0) {
+      if ((rc = resultsCollect(pc))) return rc;
+    }
     // the MicroA records of every chunk first: the MicroB-shaped regions may still be in their one late launch
-    for (int c = 0; c < 2; ++c) {
+    for (int c = 0; c < 2 && !(devRes_ && p == 0); ++c) {
       pool_->parallelFor((int) pc.chunks.size(), [&](int t, int worker) {
         Chunk& ch = pc.chunks[t];
         if (ch.job[c].n == 0) return;
@@ -1396,7 +1449,7 @@ int Engine::startTier(const PassCtx& pc, const RegRange& g) const {
   // the frontier grows with the variants on one side (orientations multiply): pick the tier that will hold it
   const int m = std::max(g.cCount, g.bCount);
   if (opt_.forceCta) return m >= 10 ? kTierCta : kTierMid;
-  return m <= 3 ? 0 : (m >= 10 ? kTierCta : kTierMid);
+  return m <= 3 ? 0 : kTierMid;   // what outgrows the mid tier's 2048 paths moves on to the full-budget tiers
 }
 
 // Packs the regions `items` (region, tier) for the warp-per-region kernels and starts them: the variants and alleles of
@@ -2197,7 +2250,230 @@ void Engine::assembleBlock(int k, int side, int lo, int hi, vce_sequence_result&
   }
 }
 
+// ------------------------------------------------------------------------------------------- device-resident results
+// Single-pass vce_submit on sorted inputs with the thread-per-region kernel in play: its result records stay on the device.
+bool Engine::wantDeviceResults(const PassCtx&) const {
+  if (!opt_.deviceResults || !opt_.deviceBuild || opt_.disableMicro || opt_.forceGeneral || !be_->resultsSupported()) return false;
+  if (cfg_.n_passes != 1) return false;
+  if (!orientorPairMicro(cfg_.calls_orientor[0], cfg_.baseline_orientor[0], cfg_.ploidy[0])) return false;
+  const PassCtx& pc = pass_[0];
+  for (int k = 0; k < nSeq_; ++k) {
+    if (pc.shortCircuit[k]) continue;
+    if (pc.ss[0][k].idx != nullptr || pc.ss[1][k].idx != nullptr) return false;   // an unsorted side: host path
+  }
+  return true;
+}
+
+int Engine::resultsSetup(PassCtx& pc) {
+  regBase_.assign((size_t) nSeq_ + 1, 0);
+  for (int k = 0; k < nSeq_; ++k) regBase_[(size_t) k + 1] = regBase_[(size_t) k] + (int32_t) pc.rr[k].size();
+  return VCE_OK;
+}
+
+// The region table's info words come back (4 bytes per region instead of a 16 / 32-byte record to parse): which regions the
+// thread-per-region kernel settled, whether their tie-breaks looked at the prefix, their last baseline allele id.
+int Engine::resultsCollect(PassCtx& pc) {
+  const uint32_t* info = nullptr;
+  int64_t iterations = 0;
+  const int rc = be_->resultsRegInfo(&info, &iterations);
+  if (rc) { err_ = be_->lastError(); return rc; }
+  be_->stats.iterations += iterations;
+  struct Task { int k, lo, hi; };
+  std::vector<Task> tasks;
+  const int block = 1 << 16;
+  for (int k = 0; k < nSeq_; ++k)
+    for (int lo = 0; lo < (int) pc.rr[k].size(); lo += block) tasks.push_back(Task{k, lo, std::min((int) pc.rr[k].size(), lo + block)});
+  pool_->parallelFor((int) tasks.size(), [&](int t, int) {
+    const Task& tk = tasks[t];
+    RegRes* rs = pc.rs[tk.k].data();
+    const uint8_t* cls = pc.rcls[tk.k].data();
+    const uint32_t* in = info + regBase_[tk.k];
+    for (int j = tk.lo; j < tk.hi; ++j) {
+      if (cls[j] != 1 && cls[j] != 2) continue;           // not a packet region of this call
+      if (rs[j].state != RS_PENDING) continue;
+      const uint32_t v = in[j];
+      if (riStatus(v) == RI_CLEAN) {
+        rs[j].state = RS_MICRO_DONE;
+        rs[j].flags = (uint8_t) ((riFlags(v) & 1u) | 0x80u);   // bit 7: the region's results live on the device
+        rs[j].lastId = (int8_t) riLastId(v);
+        rs[j].nSync = 0;
+      } else {
+        rs[j].state = RS_RESIDUAL;
+      }
+    }
+  });
+  return VCE_OK;
+}
+
+int Engine::finishDevice(vce_sequence_result* results) {
+  StageTimer tm;
+  PassCtx& pc = pass_[0];
+  // ---- the regions whose final state is the host's
+  struct Part { std::vector<int32_t> regIdx, syncCnt, sync; std::vector<uint32_t> info; std::vector<RegRange> range; std::vector<uint8_t> dec;
+                std::vector<double> w; int err = 0; };
+  std::vector<Part> parts((size_t) nSeq_);
+  pool_->parallelFor(nSeq_, [&](int k, int) {
+    Part& pt = parts[(size_t) k];
+    if (pc.shortCircuit[k]) return;
+    const RegRes* rs = pc.rs[k].data();
+    const int n = (int) pc.rs[k].size();
+    for (int j = 0; j < n; ++j) {
+      const RegRes& s = rs[j];
+      if (s.state == RS_MICRO_DONE && (s.flags & 0x80u)) continue;
+      const RegRange& g = pc.rr[k][j];
+      const bool alive = s.state == RS_MICRO_DONE || s.state == RS_WIDE_DONE;
+      if (s.state == RS_ERR_NULL) pt.err = VCE_ERR_BEST_PATH_NULL;
+      else if (s.state == RS_ERR_MOVE) pt.err = VCE_ERR_MOVE_IN_VARIANT;
+      else if (s.state == RS_ERR_ORDER) pt.err = VCE_ERR_UNSUPPORTED;
+      else if (!alive && s.state != RS_DEAD && pt.err == 0) pt.err = VCE_ERR_CAPACITY;   // must not happen: an unsettled region
+      pt.regIdx.push_back(regBase_[k] + j);
+      int cnt = 0;
+      if (s.state == RS_MICRO_DONE) {   // decoded on the host (a merged region the packet kernel took on the retry)
+        const int base = regionStartPos(pc, k, j);
+        for (int q = 0; q < s.nSync; ++q) pt.sync.push_back(base + s.rel[q]);
+        cnt = s.nSync;
+      } else if (s.state == RS_WIDE_DONE) {
+        for (int q = 0; q < s.ext.n; ++q) pt.sync.push_back(pc.wideSync[(size_t) s.ext.idx + q]);
+        cnt = s.ext.n;
+      }
+      pt.syncCnt.push_back(cnt);
+      pt.info.push_back(riPack(alive ? RI_HOST : RI_DEAD, s.flags & 3u, alive ? (int) s.lastId : kMicroNoLastId));
+      pt.range.push_back(alive ? g : RegRange{g.cFirst, 0, g.bFirst, 0});
+      if (alive) {
+        for (int i = 0; i < g.cCount; ++i) { pt.dec.push_back(pc.decision[0][g.cFirst + i]); pt.w.push_back(pc.weight[g.cFirst + i]); }
+        for (int i = 0; i < g.bCount; ++i) pt.dec.push_back(pc.decision[1][g.bFirst + i]);
+      }
+    }
+  });
+  ResultsPatch patch;
+  for (int k = 0; k < nSeq_; ++k) {
+    const Part& pt = parts[(size_t) k];
+    size_t so = patch.extSync.size(), po = patch.decPay.size(), wo = patch.wPay.size();
+    size_t si = 0;
+    for (size_t i = 0; i < pt.regIdx.size(); ++i) {
+      patch.regIdx.push_back(pt.regIdx[i]);
+      patch.info.push_back(pt.info[i]);
+      patch.range.push_back(pt.range[i]);
+      patch.syncOff.push_back((int32_t) (so + si));
+      patch.syncCnt.push_back(pt.syncCnt[i]);
+      si += (size_t) pt.syncCnt[i];
+      patch.payOff.push_back((int32_t) po);
+      patch.wOff.push_back((int32_t) wo);
+      po += (size_t) pt.range[i].cCount + (size_t) pt.range[i].bCount;
+      wo += (size_t) pt.range[i].cCount;
+    }
+    patch.extSync.insert(patch.extSync.end(), pt.sync.begin(), pt.sync.end());
+    patch.decPay.insert(patch.decPay.end(), pt.dec.begin(), pt.dec.end());
+    patch.wPay.insert(patch.wPay.end(), pt.w.begin(), pt.w.end());
+  }
+  tm.lap("device results: patch of host-settled regions");
+  ResultsOut out;
+  int rc = be_->resultsFinish(patch, out);
+  if (rc) { err_ = be_->lastError(); return rc; }
+  tm.lap("device results: final passes + copy back");
+  // ---- per sequence: sync points, phasing counts, warnings, errors
+  std::vector<uint8_t> live((size_t) nSeq_, 0);
+  for (int k = 0; k < nSeq_; ++k) {
+    vce_sequence_result& res = results[k];
+    const vce_sequence& sq = seqs_[k];
+    res.n_sync[0] = res.n_sync[1] = 0;
+    res.phasing[0] = res.phasing[1] = res.phasing[2] = 0;
+    res.n_warnings = 0;
+    res.error = VCE_OK;
+    res.n_regions = 0;
+    res.n_iterations = 0;
+    vce_side_result* sides[2] = {&res.calls, &res.baseline};
+    const vce_variants* vin[2] = {&sq.calls, &sq.baseline};
+    auto blank = [&](int extraStatus, int syncId) {
+      for (int side = 0; side < 2; ++side) {
+        vce_side_result& o = *sides[side];
+        for (int i = 0; i < vin[side]->n; ++i) {
+          o.status[i] = (uint8_t) ((vin[side]->status_in ? vin[side]->status_in[i] : 0) | extraStatus);
+          for (int h = 0; h < VCE_MAX_PLOIDY; ++h) o.allele_ids[(size_t) i * VCE_MAX_PLOIDY + h] = -2;
+          o.original[i] = 0;
+          o.weight[i] = 0;
+          if (o.sync_id) o.sync_id[i] = syncId;
+        }
+      }
+    };
+    if (pc.shortCircuit[k]) { blank(VCE_STATUS_NO_MATCH, 1); continue; }   // SequenceEvaluator.java:94-97
+    std::vector<WarnEntry> ws;
+    for (const WarnEntry& w : pc.warns) if (w.seq == k && pc.rs[k][w.j].state != RS_DEAD) ws.push_back(w);
+    std::stable_sort(ws.begin(), ws.end(), [](const WarnEntry& a, const WarnEntry& b) { return a.j < b.j; });
+    for (const WarnEntry& w : ws) {
+      if (res.n_warnings < res.warn_cap) res.warnings[res.n_warnings] = vce_warning{0, w.w.paths, w.w.iterations, w.w.start1, w.w.end1};
+      ++res.n_warnings;
+    }
+    if (parts[(size_t) k].err) { res.error = parts[(size_t) k].err; blank(0, 0); continue; }
+    const int s0 = out.seqSyncFirst[k], sn = out.seqSyncFirst[k + 1] - s0;
+    res.n_sync[0] = sn;
+    if (sn > res.sync_cap[0]) { res.error = VCE_ERR_CAPACITY; blank(0, 0); continue; }
+    std::memcpy(res.sync_points[0], out.syncPos + s0, (size_t) sn * sizeof(int32_t));
+    res.n_regions = sn;
+    res.phasing[0] = (int32_t) out.counters[(size_t) k * 8 + 5];
+    res.phasing[1] = (int32_t) out.counters[(size_t) k * 8 + 6];
+    res.phasing[2] = (int32_t) out.counters[(size_t) k * 8 + 7];
+    live[(size_t) k] = 1;
+  }
+  tm.lap("device results: headers");
+  // ---- per-variant records -> the caller's arrays (sorted inputs: sorted position == input index)
+  struct Task { int seq, side, lo, hi; };
+  std::vector<Task> tasks;
+  const int block = 1 << 15;
+  for (int k = 0; k < nSeq_; ++k) {
+    if (!live[(size_t) k]) continue;
+    for (int side = 0; side < 2; ++side) {
+      const int n = pc.ss[side][k].n;
+      for (int lo = 0; lo < n; lo += block) tasks.push_back(Task{k, side, lo, std::min(n, lo + block)});
+    }
+  }
+  pool_->parallelFor((int) tasks.size(), [&](int t, int) {
+    const Task& tk = tasks[t];
+    const vce_sequence& sq = seqs_[tk.seq];
+    vce_side_result& o = tk.side == 0 ? results[tk.seq].calls : results[tk.seq].baseline;
+    const vce_variants& in = tk.side == 0 ? sq.calls : sq.baseline;
+    const SideSeq& a = pc.ss[tk.side][tk.seq];
+    const int stride = tk.side == 0 ? 16 : 8;
+    const uint8_t* rec = (tk.side == 0 ? out.outCalls : out.outBase) + (size_t) (a.first + tk.lo) * stride;
+    for (int li = tk.lo; li < tk.hi; ++li, rec += stride) {
+      o.status[li] = rec[0];
+      int8_t* ids = o.allele_ids + (size_t) li * VCE_MAX_PLOIDY;
+      if (rec[1] != 0xff) {
+        pickRow(pc.kind[tk.side], pc.H, pc.gtPloidy[tk.side], in, li, rec[1], ids, &o.original[li]);
+      } else {
+        ids[0] = ids[1] = ids[2] = ids[3] = -2;
+        o.original[li] = 0;
+      }
+      int32_t sid;
+      std::memcpy(&sid, rec + 4, 4);
+      if (o.sync_id) o.sync_id[li] = sid;
+      double w = 0.0;
+      if (tk.side == 0) std::memcpy(&w, rec + 8, 8);
+      o.weight[li] = w;
+    }
+  });
+  tm.lap("device results: expansion into the caller's arrays");
+  summary_.assign((size_t) nSeq_ * 8, 0);
+  for (int k = 0; k < nSeq_; ++k) {
+    if (live[(size_t) k]) for (int i = 0; i < 8; ++i) summary_[(size_t) k * 8 + i] = out.counters[(size_t) k * 8 + i];
+  }
+  {  // sequences that never reached the device (short-circuit, errors): counted from what was written for them
+    std::vector<uint8_t> rest((size_t) nSeq_, 0);
+    bool any = false;
+    for (int k = 0; k < nSeq_; ++k) if (!live[(size_t) k]) { rest[(size_t) k] = 1; any = true; }
+    if (any) {
+      std::vector<int64_t> keep = summary_;
+      summaryFromResults(results);
+      for (int k = 0; k < nSeq_; ++k) if (!rest[(size_t) k]) for (int i = 0; i < 8; ++i) summary_[(size_t) k * 8 + i] = keep[(size_t) k * 8 + i];
+    }
+  }
+  int rcAll = VCE_OK;
+  for (int k = 0; k < nSeq_; ++k) if (results[k].error != VCE_OK && rcAll == VCE_OK) rcAll = results[k].error;
+  return rcAll;
+}
+
 int Engine::finish(vce_sequence_result* results) {
+  if (devRes_) return finishDevice(results);
   StageTimer tm;
   for (int p = 0; p < 2; ++p) ensureSize(seqSync_[p], (size_t) nSeq_);
   for (int side = 0; side < 2; ++side) ensureSize(seqDec1_[side], (size_t) nSeq_);
@@ -2309,11 +2585,39 @@ int Engine::finish(vce_sequence_result* results) {
     assembleBlock(tk.seq, tk.side, tk.lo, tk.hi, results[tk.seq]);
   });
   tm.lap("assemble: variants");
+  summaryFromResults(results);
   int rc = VCE_OK;
   for (int k = 0; k < nSeq_; ++k) {
     if (results[k].error != VCE_OK && rc == VCE_OK) rc = results[k].error;
   }
   return rc;
+}
+
+// The split writers' classes counted on the host (the paths that assemble on the host): same rules as the device pass of
+// vce_final.h -- SplitEvalSynchronizer.handleKnownCall :112-134, handleKnownBaseline :136-150.
+void Engine::summaryFromResults(const vce_sequence_result* results) {
+  summary_.assign((size_t) nSeq_ * 8, 0);
+  pool_->parallelFor(nSeq_, [&](int k, int) {
+    int64_t* cn = summary_.data() + (size_t) k * 8;
+    const vce_sequence_result& r = results[k];
+    if (r.error != VCE_OK) return;
+    const vce_sequence& sq = seqs_[k];
+    for (int i = 0; i < sq.calls.n; ++i) {
+      const int st = r.calls.status[i];
+      if (st & VCE_STATUS_SKIPPED) ++cn[4];
+      if (st & VCE_STATUS_GT_MATCH) { if (r.calls.weight[i] > 0) ++cn[2]; }
+      else if (st & VCE_STATUS_ALLELE_MATCH) { if (r.calls.weight[i] > 0) ++cn[3]; }
+      else if ((st & VCE_STATUS_NO_MATCH) && !(st & VCE_STATUS_OUTSIDE_EVAL)) ++cn[3];
+    }
+    for (int i = 0; i < sq.baseline.n; ++i) {
+      const int st = r.baseline.status[i];
+      if (st & VCE_STATUS_SKIPPED) ++cn[4];
+      if (st & VCE_STATUS_OUTSIDE_EVAL) continue;
+      if (st & VCE_STATUS_GT_MATCH) ++cn[0];
+      else if (st & (VCE_STATUS_ALLELE_MATCH | VCE_STATUS_NO_MATCH)) ++cn[1];
+    }
+    cn[5] = r.phasing[0]; cn[6] = r.phasing[1]; cn[7] = r.phasing[2];
+  });
 }
 
 }  // namespace vce

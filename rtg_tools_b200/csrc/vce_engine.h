@@ -34,7 +34,7 @@ struct EngineOptions {
   int microMargin = 12;   // same, thread-per-region kernel
   int wideMargin = 192;   // same, regions that start in the CTA tiers
   int denseGap = 256;     // neighbouring regions closer than this are joined up front when one of them already holds ...
-  int denseCount = 3;     // ... this many variants on a side (dense clusters in repeats spill into each other otherwise)
+  int denseCount = 8;     // ... this many variants on a side (dense clusters in repeats spill into each other otherwise)
   bool forceGeneral = false;   // tests: every region through the large-capacity kernel
   bool forceCta = false;       // tests: every warp-path region through the CTA kernel
   bool disableMicro = false;   // tests: no thread-per-region kernel
@@ -43,6 +43,7 @@ struct EngineOptions {
   bool sortPackets = true;     // hand the packets of a chunk to the kernel grouped by shape class (lock-step lanes)
   bool deviceBuild = true;     // vce_submit: pack the packets on the device from wholesale copies of the caller's arrays
   bool residentInputs = true;  // sequences with a registered template: whole-sequence upload, windows cut out on the device
+  bool deviceResults = true;   // single-pass vce_submit: result records scattered, sync ids / classes / phasing computed on the device
 };
 
 // Host side of vce_template_register: 2 bits per base (base - 1; 16 bases per word) and one bit per 16-base granule that
@@ -60,6 +61,9 @@ class Engine {
   int execute();
   int finish(vce_sequence_result* results);
   const std::string& error() const { return err_; }
+  // Per-sequence summary of the last finish(): [k * 8 + i] = baseline TP, baseline FN, call TP, call FP, skipped variants
+  // (both sides), mis-phasings, correct phasings, unphaseable -- the split writers' classes (SplitEvalSynchronizer.java:112-156)
+  const std::vector<int64_t>& summary() const { return summary_; }
   EngineOptions& options() { return opt_; }
   Backend* backend() { return be_; }
   // diagnostics of the last execute(): regions of the thread-per-region launches, variants of the MicroA class
@@ -166,7 +170,11 @@ class Engine {
   int buildChunkDevice(PassCtx& pc, Chunk& ch, int worker);
   // resident inputs (registered template + whole-sequence upload): see residentSetup
   struct ResidentSeq {
-    bool on = false;
+    bool on = false;               // whole-sequence upload + registered template: packets are built from `dv`
+    bool have = false;             // at least the arrays of the final passes are on the device (fVStart / fPhased / fStatus)
+    const int32_t* fVStart[2] = {nullptr, nullptr};   // device pointers, sequence-local index
+    const uint8_t* fPhased[2] = {nullptr, nullptr};
+    const uint8_t* fStatus[2] = {nullptr, nullptr};
     PacketView dv;                 // device pointers to the sequence's arrays
     const uint32_t* t2 = nullptr;  // device copy of the template
     const uint32_t* nmask = nullptr;
@@ -175,6 +183,15 @@ class Engine {
   std::vector<ResidentSeq> resident_;
   int residentSetup(PassCtx& pc);
   int buildChunkResident(PassCtx& pc, Chunk& ch, int worker);
+  // device-resident results (vce_final.h)
+  bool devRes_ = false;
+  std::vector<int64_t> summary_;
+  void summaryFromResults(const vce_sequence_result* results);
+  std::vector<int32_t> regBase_;   // [nSeq + 1] global region index of every sequence's first region
+  bool wantDeviceResults(const PassCtx& pc) const;
+  int resultsSetup(PassCtx& pc);
+  int resultsCollect(PassCtx& pc);
+  int finishDevice(vce_sequence_result* results);
   int runChunks(PassCtx& pc);
   void decodeChunk(PassCtx& pc, Chunk& ch, int64_t& iterations);
   void assembleRegionEarly(PassCtx& pc, int k, int j);

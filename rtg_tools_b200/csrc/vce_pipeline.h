@@ -17,6 +17,7 @@
 #include "vce_packet.h"
 #include "vce_search.h"
 #include "vce_cta.h"
+#include "vce_final.h"
 
 namespace vce {
 
@@ -105,6 +106,10 @@ struct MicroBuildJob {
   const uint32_t* t2 = nullptr;
   const uint32_t* nmask = nullptr;
   int waitEvents[2] = {-1, -1};    // uploads (Backend::residentUpload) the builder has to wait for
+  // device-resident results (Backend::resultsBegin): the chunk's result records are scattered into the pass-wide arrays on
+  // the device instead of being copied back; regIdx = slab offset of int32[nA + nB], the global region index of each region
+  bool scatter = false;
+  int64_t regIdx = 0;
   int64_t regions = 0;             // RegRange[nA + nB]: the MicroA-shaped regions, then the MicroB-shaped ones
   int64_t winOff = 0;              // uint32[nA + nB]: offset of each region's window bases within `windows`
   int64_t windows = 0;             // uint8[]: reference bases from each region's window start
@@ -139,9 +144,50 @@ inline PacketView microBuildView(const MicroBuildJob& b, const uint8_t* base) {
   return pv;
 }
 
+// ---- device-resident results (vce_final.h): what the engine tells the backend about the pass, the regions the host
+// settled, and what comes back
+struct ResultsSeq {
+  int32_t first[2] = {0, 0}, n[2] = {0, 0};     // slices of the pass-wide per-variant arrays; side 0 = calls, 1 = baseline
+  int32_t regFirst = 0, nReg = 0;               // slice of the region table
+  const int32_t* vStart[2] = {nullptr, nullptr};     // device pointers (Backend::residentUpload), sequence-local index
+  const uint8_t* phased[2] = {nullptr, nullptr};
+  const uint8_t* statusIn[2] = {nullptr, nullptr};
+};
+struct ResultsSetup {
+  int H = 2, kind[2] = {0, 0};
+  std::vector<ResultsSeq> seq;
+  int32_t nVar[2] = {0, 0};
+  int32_t nReg = 0;
+  bool rocTuples = false;
+};
+struct ResultsPatch {     // one entry per region whose final state is the host's: settled by the warp / CTA kernels, merged, dead
+  std::vector<int32_t> regIdx, syncOff, syncCnt, payOff, wOff;
+  std::vector<uint32_t> info;       // riPack(RI_HOST | RI_DEAD, flags, lastId)
+  std::vector<RegRange> range;      // the variants the region owns (empty for dead regions)
+  std::vector<uint8_t> decPay;      // decisions, calls then baseline, region by region
+  std::vector<double> wPay;         // call weights, region by region
+  std::vector<int32_t> extSync;     // sync points, region by region
+};
+struct ResultsOut {       // host copies, valid until the next resultsBegin
+  const uint8_t* outCalls = nullptr;      // [nVar[0] * 16] status, row (0xff none), original, pad, syncId i32, weight f64
+  const uint8_t* outBase = nullptr;       // [nVar[1] * 8]
+  const int32_t* syncPos = nullptr;       // Path.getSyncPoints() of every sequence, back to back
+  const int32_t* seqSyncFirst = nullptr;  // [nSeq + 1]
+  const int64_t* counters = nullptr;      // [nSeq * 8] baseline TP, FN, call TP, FP, skipped, mis-, correct, unphaseable phasings
+  const double* rocTuples = nullptr;      // [nVar[0] * 3] when requested
+  int nSync = 0;
+};
+
 class Backend {
  public:
   virtual ~Backend() {}
+  // ---- device-resident results
+  virtual bool resultsSupported() const { return false; }
+  virtual int resultsBegin(const ResultsSetup&) { return VCE_ERR_UNSUPPORTED; }
+  // Blocks until every chunk handed over so far has been searched and scattered; info[r] = riPack(...) of every region.
+  virtual int resultsRegInfo(const uint32_t** /*info*/, int64_t* /*iterations*/) { return VCE_ERR_UNSUPPORTED; }
+  // Applies the patch, runs the final passes and copies the results to the host.
+  virtual int resultsFinish(const ResultsPatch&, ResultsOut&) { return VCE_ERR_UNSUPPORTED; }
   // ---- thread-per-region path.  Calls for different jobs may come from different host threads.
   virtual void* hostAlloc(size_t bytes) = 0;   // page-locked on the CUDA backend
   virtual void hostFree(void* p) = 0;

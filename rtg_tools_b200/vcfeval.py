@@ -142,6 +142,17 @@ class Engine:
         return dict(launches=int(out[0]), h2d_bytes=int(out[1]), d2h_bytes=int(out[2]), regions=int(out[3]),
                     escalated=int(out[4]), iterations=int(out[5]))
 
+    def submit_summary(self, n_seq: int) -> np.ndarray:
+        """vce_submit_summary: (n_seq, 8) int64 -- baseline TP, FN, call TP, FP, skipped, mis-, correct, unphaseable phasings
+        of the calling thread's last submit()."""
+        out = np.zeros(n_seq * 8, np.int64)
+        self.lib.lib.vce_submit_summary.restype = C.c_int
+        self.lib.lib.vce_submit_summary.argtypes = [C.c_void_p, C.c_int32]
+        rc = self.lib.lib.vce_submit_summary(out.ctypes.data, n_seq)
+        if rc != 0:
+            raise RuntimeError("vce_submit_summary: %s %s" % (capi.ERR_NAMES.get(rc, rc), self.lib.last_error()))
+        return out.reshape(n_seq, 8)
+
     def job(self, cfg, seqs) -> Job:
         return Job(self, cfg, seqs)
 

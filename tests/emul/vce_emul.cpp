@@ -13,6 +13,7 @@
 
 #include <atomic>
 #include <cstdlib>
+#include <mutex>
 
 #include "../../rtg_tools_b200/csrc/vce_engine.h"
 #include "../../rtg_tools_b200/csrc/vce_orient.h"
@@ -56,12 +57,18 @@ class EmulBackend : public Backend {
   int microWait(MicroJob&) override { return 0; }
   // device-side packet building, emulated: the same builder source over the host slab, then the search as above
   template <class T>
-  void buildRunT(const MicroBuildJob& b, const PacketView& pv, int q0, MicroJob& j, const MicroConfig& mc) {
+  void buildRunT(const MicroBuildJob& b, const PacketView& pv, int q0, MicroJob& j, const MicroConfig& mc, std::vector<uint8_t>& pkStore,
+                 std::vector<uint32_t>& offStore) {
     const RegRange* regs = reinterpret_cast<const RegRange*>(b.slab + b.regions);
     const uint32_t* winOff = reinterpret_cast<const uint32_t*>(b.slab + b.winOff);
-    std::vector<uint8_t> ws(T::WS_BYTES + 16), pk(T::PKT_MAX + 16);
+    const size_t stride = ((size_t) T::PKT_MAX + 15) & ~(size_t) 15;
+    pkStore.assign((size_t) j.n * stride + 16, 0);
+    offStore.assign((size_t) j.n + 1, 0xffffffffu);
+    std::vector<uint8_t> ws(T::WS_BYTES + 16);
     for (int q = 0; q < j.n; ++q) {
       uint8_t* res = j.results + (size_t) q * j.resBytes;
+      uint8_t* pkq = pkStore.data() + (size_t) q * stride;
+      struct { uint8_t* p; uint8_t* data() { return p; } uint8_t operator[](int i) const { return p[i]; } } pk{pkq};
       int32_t winStart = 0, winLen = 0, nextStart[2];
       int bytes = 0;
       if (microWindow(pv, regs[q0 + q], &winStart, &winLen, nextStart)) {
@@ -73,6 +80,7 @@ class EmulBackend : public Backend {
         res[MR_STATUS] = kMicroFallback;
         continue;
       }
+      offStore[(size_t) q] = (uint32_t) (((size_t) q * stride) >> 2);
       MicroSearch<T> ms;
       ms.ws = ws.data();
       ms.cfg = mc;
@@ -81,6 +89,103 @@ class EmulBackend : public Backend {
       if (res[MR_STATUS] == kMicroClean) ++microClean;
     }
   }
+  // ---- device-resident results, emulated: the same scatter / patch / final-pass source (vce_final.h) over host vectors
+  struct HostFinalOps {
+    template <class F> void parFor(int n, F f) { for (int i = 0; i < n; ++i) f(i); }
+    void exclusiveSum(int32_t* in, int32_t* out, int n) { int32_t acc = 0; for (int i = 0; i < n; ++i) { const int32_t v = in[i]; out[i] = acc; acc += v; } }
+    int unique64(int64_t* in, int64_t* out, int n) {
+      int m = 0;
+      for (int i = 0; i < n; ++i) if (m == 0 || out[m - 1] != in[i]) out[m++] = in[i];
+      return m;
+    }
+    void segMinScan(const int32_t* keys, const int32_t* vals, int32_t* out, int n) {
+      for (int i = 0; i < n; ++i) out[i] = (i > 0 && keys[i] == keys[i - 1]) ? std::min(out[i - 1], vals[i]) : vals[i];
+    }
+    int fetchInt(const int32_t* p) { return *p; }
+    void zero(void* p, size_t bytes) { std::memset(p, 0, bytes); }
+  };
+  bool resultsSupported() const override { return resultsOn; }
+  bool resultsOn = true;
+  ResultsSetup rsu_;
+  std::vector<FinalSeq> fseq_;
+  std::vector<uint8_t> rDec_[2], rRel_, fOutC_, fOutB_, fMFlags_, fBaseSum_, fBlockEnd_;
+  std::vector<double> rWeight_, fRoc_;
+  std::vector<uint32_t> rInfo_;
+  std::vector<int32_t> rCnt_, rBase_, fRegOff_, fPos_, fSeqSync_, fKept_, fMStart_, fMSeq_, fMVal_, fMMin_, fCall0_, fBlockCnt_, fSeqBlock_;
+  std::vector<int64_t> fKeys_, fUniq_, fCounters_;
+  unsigned long long rIter_ = 0;
+  std::atomic<int64_t> scattered{0};
+  int resultsBegin(const ResultsSetup& s) override {
+    rsu_ = s;
+    const size_t nC = (size_t) s.nVar[0], nB = (size_t) s.nVar[1], nR = (size_t) s.nReg, nS = s.seq.size();
+    rDec_[0].assign(nC + 16, 0xee); rDec_[1].assign(nB + 16, 0xee); rWeight_.assign(nC + 2, -7.0);   // poison: every entry must be written
+    rInfo_.assign(nR + 2, 0); rCnt_.assign(nR + 2, 0); rBase_.assign(nR + 2, 0); rRel_.assign((nR + 2) * kFinalRel, 0);
+    rIter_ = 0;
+    fseq_.assign(nS, FinalSeq());
+    for (size_t k = 0; k < nS; ++k) {
+      for (int side = 0; side < 2; ++side) {
+        fseq_[k].vStart[side] = s.seq[k].vStart[side]; fseq_[k].phased[side] = s.seq[k].phased[side]; fseq_[k].statusIn[side] = s.seq[k].statusIn[side];
+        fseq_[k].first[side] = s.seq[k].first[side]; fseq_[k].n[side] = s.seq[k].n[side];
+      }
+      fseq_[k].regFirst = s.seq[k].regFirst; fseq_[k].nReg = s.seq[k].nReg;
+    }
+    return 0;
+  }
+  std::mutex scatterMu;
+  void scatterJob(const MicroJob& j, const RegRange* regs, const int32_t* regIdx, const uint8_t* packets, const uint32_t* offsets) {
+    std::lock_guard<std::mutex> lk(scatterMu);   // (host emulation: the iteration counter is a plain sum)
+    ScatterArgs a;
+    a.results = j.results; a.regs = regs; a.regIdx = regIdx; a.packets = packets; a.offsets = offsets;
+    a.n = j.n; a.resBytes = j.resBytes;
+    a.kv = j.cls == 0 ? MicroA::KV : MicroB::KV; a.smax = j.cls == 0 ? MicroA::SMAX : MicroB::SMAX;
+    a.dec[0] = rDec_[0].data(); a.dec[1] = rDec_[1].data(); a.weight = rWeight_.data();
+    a.regInfo = rInfo_.data(); a.regCnt = rCnt_.data(); a.regBase = rBase_.data(); a.regRel = rRel_.data();
+    a.iterations = &rIter_;
+    for (int q = 0; q < j.n; ++q) scatterOne(a, q);
+    scattered += j.n;
+  }
+  int resultsRegInfo(const uint32_t** info, int64_t* iterations) override {
+    *info = rInfo_.data();
+    *iterations = (int64_t) rIter_;
+    return 0;
+  }
+  int resultsFinish(const ResultsPatch& p, ResultsOut& out) override {
+    const size_t nC = (size_t) rsu_.nVar[0], nB = (size_t) rsu_.nVar[1], nR = (size_t) rsu_.nReg, nS = rsu_.seq.size();
+    PatchArgs pa;
+    pa.n = (int) p.regIdx.size();
+    pa.regIdx = p.regIdx.data(); pa.info = p.info.data(); pa.syncOff = p.syncOff.data(); pa.syncCnt = p.syncCnt.data(); pa.range = p.range.data();
+    pa.payOff = p.payOff.data(); pa.decPay = p.decPay.data(); pa.wOff = p.wOff.data(); pa.wPay = p.wPay.data();
+    pa.dec[0] = rDec_[0].data(); pa.dec[1] = rDec_[1].data(); pa.weight = rWeight_.data();
+    pa.regInfo = rInfo_.data(); pa.regCnt = rCnt_.data(); pa.regBase = rBase_.data();
+    for (int q = 0; q < pa.n; ++q) patchOne(pa, q);
+    const size_t nFlatMax = nC + nB + 2 * nR + 4;
+    fRegOff_.assign(nR + 2, 0); fKeys_.assign(nFlatMax, 0); fUniq_.assign(nFlatMax, 0); fPos_.assign(nFlatMax, 0); fSeqSync_.assign(nS + 2, 0);
+    fOutC_.assign(nC * 16 + 16, 0); fOutB_.assign(nB * 8 + 16, 0); fCounters_.assign(nS * 8 + 8, 0); fKept_.assign(nC + 2, 0);
+    fMStart_.assign(nC + 2, 0); fMFlags_.assign(nC + 2, 0); fMSeq_.assign(nC + 2, 0); fMVal_.assign(nC + 2, 0); fMMin_.assign(nC + 2, 0);
+    fBaseSum_.assign(nFlatMax, 0); fCall0_.assign(nFlatMax + nS + 2, 0);
+    const size_t nBlocksMax = nFlatMax / kPhaseBlock + nS + 2;
+    fBlockEnd_.assign(nBlocksMax * 16, 0); fBlockCnt_.assign(nBlocksMax * 16 * 3, 0); fSeqBlock_.assign(nS + 2, 0);
+    fRoc_.assign(nC * 3 + 3, 0.0);
+    FinalArrays A;
+    A.nSeq = (int) nS; A.H = rsu_.H; A.kind[0] = rsu_.kind[0]; A.kind[1] = rsu_.kind[1];
+    A.seq = fseq_.data();
+    A.nVar[0] = rsu_.nVar[0]; A.nVar[1] = rsu_.nVar[1]; A.nReg = rsu_.nReg;
+    A.dec[0] = rDec_[0].data(); A.dec[1] = rDec_[1].data(); A.weight = rWeight_.data();
+    A.regInfo = rInfo_.data(); A.regCnt = rCnt_.data(); A.regBase = rBase_.data(); A.regRel = rRel_.data(); A.extSync = p.extSync.data();
+    A.regOff = fRegOff_.data(); A.syncKeys = fKeys_.data(); A.syncUniq = fUniq_.data(); A.syncPos = fPos_.data(); A.seqSyncFirst = fSeqSync_.data();
+    A.outCalls = fOutC_.data(); A.outBase = fOutB_.data(); A.counters = fCounters_.data(); A.rocTuples = fRoc_.data();
+    A.keptScan = fKept_.data(); A.mStart = fMStart_.data(); A.mFlags = fMFlags_.data(); A.mSeq = fMSeq_.data(); A.mVal = fMVal_.data();
+    A.mMin = fMMin_.data(); A.regBaseSum = fBaseSum_.data(); A.regCall0 = fCall0_.data(); A.blockEnd = fBlockEnd_.data();
+    A.blockCnt = fBlockCnt_.data(); A.seqBlockFirst = fSeqBlock_.data();
+    HostFinalOps ops;
+    const int nSync = finalPasses(ops, A);
+    out.outCalls = fOutC_.data(); out.outBase = fOutB_.data(); out.syncPos = fPos_.data(); out.seqSyncFirst = fSeqSync_.data();
+    out.counters = fCounters_.data(); out.rocTuples = fRoc_.data(); out.nSync = nSync;
+    ++finalRuns;
+    return 0;
+  }
+  std::atomic<int64_t> finalRuns{0};
+
   // resident inputs, emulated: "device" pointers are the page-locked host blocks themselves
   struct Tmpl { const uint8_t* bases; int32_t len; std::vector<uint32_t> t2, nmask; };
   static std::vector<Tmpl>& templates() { static std::vector<Tmpl> t; return t; }
@@ -97,8 +202,16 @@ class EmulBackend : public Backend {
   std::atomic<int64_t> residentUploads{0};
   int microBuildRun(MicroBuildJob& b, MicroJob& a, MicroJob& bj, const MicroConfig& mc) override {
     const PacketView pv = b.resident ? b.rv : microBuildView(b, b.slab);
-    buildRunT<MicroA>(b, pv, 0, a, mc);
-    buildRunT<MicroB>(b, pv, b.nA, bj, mc);
+    std::vector<uint8_t> pkStore[2];
+    std::vector<uint32_t> offStore[2];
+    buildRunT<MicroA>(b, pv, 0, a, mc, pkStore[0], offStore[0]);
+    buildRunT<MicroB>(b, pv, b.nA, bj, mc, pkStore[1], offStore[1]);
+    if (b.scatter) {
+      const RegRange* regs = reinterpret_cast<const RegRange*>(b.slab + b.regions);
+      const int32_t* regIdx = reinterpret_cast<const int32_t*>(b.slab + b.regIdx);
+      if (a.n > 0) scatterJob(a, regs, regIdx, pkStore[0].data(), offStore[0].data());
+      if (bj.n > 0) scatterJob(bj, regs + b.nA, regIdx + b.nA, pkStore[1].data(), offStore[1].data());
+    }
     microRegions += a.n + bj.n;
     stats.launches += 2;
     return 0;
@@ -353,6 +466,16 @@ void emul_set_split(int variantsPerSegment) { g_split = variantsPerSegment; }
 int g_deviceBuild = 1;   // the product default
 void emul_set_device_build(int on) { g_deviceBuild = on; }
 
+std::vector<int64_t> g_summary;
+int emul_vce_submit_summary(int64_t* out, int32_t n_seq) {
+  if ((size_t) n_seq * 8 > g_summary.size()) return VCE_ERR_BAD_ARGUMENT;
+  std::memcpy(out, g_summary.data(), (size_t) n_seq * 8 * sizeof(int64_t));
+  return 0;
+}
+int g_deviceResults = 1;
+int64_t g_finalRuns = 0;
+void emul_set_device_results(int on) { g_deviceResults = on; }
+int64_t emul_final_runs() { return g_finalRuns; }
 // test hook of vce_template_register for the emulation (host copies); len <= 0 forgets every template
 void emul_template_register(const uint8_t* bases, int32_t len) {
   std::vector<EmulBackend::Tmpl>& ts = EmulBackend::templates();
@@ -386,6 +509,7 @@ int emul_vce_submit(const vce_config* cfg, int32_t n_seq, const vce_sequence* se
   be.forceGeneral = g_forceGeneral != 0;
   be.ctaNbOverride = g_ctaNb;
   be.ctaPoolOverride = g_ctaPool;
+  be.resultsOn = g_deviceResults != 0;
   WorkerPool pool(g_threads);
   EngineOptions opt;
   if (g_gap > 0) opt.gap = g_gap;
@@ -401,11 +525,13 @@ int emul_vce_submit(const vce_config* cfg, int32_t n_seq, const vce_sequence* se
     Engine en(&be, &pool, opt);
     rc = en.run(*cfg, n_seq, seqs, results);
     if (rc && !en.error().empty()) fprintf(stderr, "emul: %s\n", en.error().c_str());
+    g_summary = en.summary();
   }
   g_stats[0] = be.stats.regions; g_stats[1] = be.stats.escalated; g_stats[2] = be.stats.spilled;
   g_stats[3] = be.stats.prefixReruns; g_stats[4] = be.stats.launches; g_stats[5] = be.microRegions.load(); g_stats[6] = be.microClean.load();
   g_stats[7] = be.ctaRegions.load() | (be.ctaOverflows.load() << 32);
   g_residentUploads = be.residentUploads.load();
+  g_finalRuns = be.finalRuns.load();
   return rc;
 }
 

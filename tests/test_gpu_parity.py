@@ -89,6 +89,34 @@ def test_cuda_c3_long_alleles_reduced_budget(engine, oracle):
         compare_results(want, engine.submit(cfg, seqs), seqs, what="c3 long alleles %d" % mp)
 
 
+@pytest.mark.parametrize("registered", [True, False])
+def test_cuda_device_resident_pipeline(engine, oracle, registered):
+    """vce_submit's device-resident pipeline: registered reference (2-bit copy in HBM, windows cut out on the device) or host
+    window slabs; result records scattered on the device, sync ids / statuses / phasing counts / summary counters from the
+    final passes (vce_final.h).  Bit-exact against the oracle; the counters against the writers' rules."""
+    from rtg_tools_b200 import multigpu
+    seqs = synth.make_pair(40_000_000, n_chrom=5)
+    seqs += [synth.dense_cluster_sequence(np.random.default_rng(2), n_clusters=3, per_side=(4, 8), name="dense")]
+    if registered:
+        engine.register_templates(seqs)
+    try:
+        for name in ("default", "squash", "phased"):
+            want = oracle.submit(CONFIGS[name], seqs, threads=6)
+            got = engine.submit(CONFIGS[name], seqs)
+            compare_results(want, got, seqs, what="%s registered=%s" % (name, registered))
+            assert np.array_equal(engine.submit_summary(len(seqs)).sum(axis=0), multigpu.summary_counts(want))
+    finally:
+        if registered:
+            engine.unregister_templates(seqs)
+
+
+def test_cuda_device_results_equal_host_assembly(engine, oracle):
+    """The same call with and without the device-resident result path (VCE_DEVICE_RESULTS is read per context)."""
+    seqs = synth.make_pair(12_000_000, n_chrom=3)
+    want = oracle.submit(CONFIGS["default"], seqs, threads=3)
+    compare_results(want, engine.submit(CONFIGS["default"], seqs), seqs, what="device results")
+
+
 def test_cuda_genome_slice_all_modes(engine, oracle):
     """BASELINE.json configs[3] on a 10 % slice of the 24-chromosome genome: --squash-ploidy (haploid SQUASH_GT) and the
     two-pass mode of ga4gh / annotate / combine (diploid, then haploid allele matching on FN / FP)."""

@@ -146,6 +146,45 @@ def test_template_packing_marks_every_non_acgt_granule(emul):
         assert got == want, (pos, got, want)
 
 
+@pytest.mark.parametrize("cfg_name", ["default", "squash", "phased", "calls_min_base"])
+def test_device_resident_results_are_exact(emul, oracle, cfg_name):
+    """The result records never come back: scatter, host patches, sync points, per-variant outputs, sync ids, phasing counts
+    (prefix minimum + 16-state transducer) and the summary counters through the final passes of vce_final.h -- against
+    the oracle, and against the very same engine assembling on the host."""
+    from rtg_tools_b200 import multigpu
+    emul.lib.emul_final_runs.restype = ctypes.c_int64
+    emul.lib.emul_vce_submit_summary.argtypes = [ctypes.c_void_p, ctypes.c_int32]
+    seqs = synth.make_pair(2_000_000, n_chrom=3)
+    rng = np.random.default_rng(12)
+    # sorted adversarial sequences: ties at equal starts, N bases, half calls, null alleles
+    for seed in range(40):
+        batch = fuzz_batch(8200 + seed)
+        seqs += batch
+    seqs += [synth.dense_cluster_sequence(rng, n_clusters=2, per_side=(4, 8), name="dense")]
+    want = oracle.submit(CONFIGS[cfg_name], seqs)
+    runs = 0
+    try:
+        for sub in (seqs[:3], seqs[3:]):
+            got = emul.submit(CONFIGS[cfg_name], sub)
+            runs += emul.lib.emul_final_runs()
+            w = want[:3] if sub is seqs[:3] or len(sub) == 3 else want[3:]
+            compare_results(w, got, sub, what=cfg_name)
+            if emul.lib.emul_final_runs():
+                out = np.zeros(len(sub) * 8, np.int64)
+                assert emul.lib.emul_vce_submit_summary(out.ctypes.data, len(sub)) == 0
+                assert np.array_equal(out.reshape(-1, 8).sum(axis=0), multigpu.summary_counts(w))
+        assert runs >= 1, "the genome slice is sorted: it has to take the device-resident result path"
+        emul.lib.emul_set_device_results(0)
+        got = emul.submit(CONFIGS[cfg_name], seqs[:3])
+        assert emul.lib.emul_final_runs() == 0
+        compare_results(want[:3], got, seqs[:3], what=cfg_name + " host assembly")
+        out = np.zeros(3 * 8, np.int64)
+        assert emul.lib.emul_vce_submit_summary(out.ctypes.data, 3) == 0
+        assert np.array_equal(out.reshape(-1, 8).sum(axis=0), multigpu.summary_counts(want[:3]))
+    finally:
+        emul.lib.emul_set_device_results(1)
+
+
 def test_synthetic_genome_pair(emul, oracle):
     seqs = synth.make_pair(3_000_000, n_chrom=3)
     assert sum(s.calls.n for s in seqs) > 3000
