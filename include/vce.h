@@ -187,6 +187,10 @@ typedef struct vce_roc_out {
 
 /* ---- life cycle ---- */
 int         vce_init(int device);               /* selects the CUDA device; fails with VCE_ERR_NO_DEVICE when none */
+/* One process, several devices: the sequences of a vce_submit batch are spread over `devices` (longest-processing-time
+   greedy by variant count; sequences are the reference's independent units, VcfEvalTask.java:131-135), one context, stream
+   set and share of the host cores per device.  Registered templates live on every device.  vce_init(d) == vce_init_devices(1, &d). */
+int         vce_init_devices(int device_count, const int* devices);
 void        vce_shutdown(void);
 const char* vce_last_error(void);               /* thread-local message for the last non-zero return */
 const char* vce_version(void);

@@ -12,6 +12,8 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <array>
+#include <thread>
 #include <vector>
 
 #include "../../include/vce.h"
@@ -20,7 +22,8 @@
 
 namespace {
 std::mutex g_mu;
-int g_device = -1;
+int g_device = -1;                 // the first device of g_devices (single-device entry points: jobs, ROC)
+std::vector<int> g_devices;        // vce_init_devices: a batch's sequences are spread over these
 thread_local std::string t_err;
 
 struct Context {
@@ -30,21 +33,33 @@ struct Context {
 };
 std::vector<std::unique_ptr<Context>> g_free;
 std::unique_ptr<vce::WorkerPool> g_pool;
+// with several devices every device's engine gets its own share of the host cores (a WorkerPool runs one parallelFor at a time)
+std::vector<std::unique_ptr<vce::WorkerPool>> g_devPools;
 
 int fail(int code, const std::string& msg) {
   t_err = msg;
   return code;
 }
 
-Context* acquire(int& rc) {
+Context* acquire(int& rc, int devIndex = -1) {
   int dev;
+  vce::WorkerPool* pool = nullptr;
   {
     std::lock_guard<std::mutex> lk(g_mu);
-    dev = g_device;
+    dev = devIndex >= 0 && devIndex < (int) g_devices.size() ? g_devices[(size_t) devIndex] : g_device;
     if (dev < 0) { rc = fail(VCE_ERR_NOT_INITIALISED, "call vce_init first"); return nullptr; }
     if (!g_pool) g_pool.reset(new vce::WorkerPool(vce::WorkerPool::defaultThreads()));
+    pool = g_pool.get();
+    if (devIndex >= 0 && g_devices.size() > 1) {
+      if (g_devPools.size() != g_devices.size()) {
+        g_devPools.clear();
+        const int per = std::max(2, vce::WorkerPool::defaultThreads() / (int) g_devices.size());
+        for (size_t i = 0; i < g_devices.size(); ++i) g_devPools.emplace_back(new vce::WorkerPool(per));
+      }
+      pool = g_devPools[(size_t) devIndex].get();
+    }
     for (size_t i = 0; i < g_free.size(); ++i) {
-      if (g_free[i]->device == dev) {
+      if (g_free[i]->device == dev && (g_devices.size() <= 1 || g_free[i]->engine->pool() == pool)) {
         Context* c = g_free[i].release();
         g_free.erase(g_free.begin() + (long) i);
         return c;
@@ -65,13 +80,13 @@ Context* acquire(int& rc) {
   if (const char* e = std::getenv("VCE_DEVICE_BUILD")) opt.deviceBuild = std::atoi(e) != 0;
   if (const char* e = std::getenv("VCE_RESIDENT")) opt.residentInputs = std::atoi(e) != 0;
   if (const char* e = std::getenv("VCE_DEVICE_RESULTS")) opt.deviceResults = std::atoi(e) != 0;
-  c->engine.reset(new vce::Engine(c->backend.get(), g_pool.get(), opt));
+  c->engine.reset(new vce::Engine(c->backend.get(), pool, opt));
   return c;
 }
 
 void release(Context* c) {
   std::lock_guard<std::mutex> lk(g_mu);
-  if (g_device < 0 || g_free.size() >= 4) { delete c; return; }
+  if (g_device < 0 || g_free.size() >= 4 + 2 * g_devices.size()) { delete c; return; }
   g_free.emplace_back(c);
 }
 
@@ -106,18 +121,30 @@ void vce_default_config(vce_config* cfg) {
   cfg->preference = VCE_PREFER_SUM;
 }
 
-int vce_init(int device) {
+int vce_init_devices(int device_count, const int* devices) {
   std::lock_guard<std::mutex> lk(g_mu);
   const int n = vce::cudaDeviceCount();
   if (n <= 0) return fail(VCE_ERR_NO_DEVICE, "no CUDA device is visible; this engine has no CPU fallback");
-  if (device < 0 || device >= n) return fail(VCE_ERR_BAD_ARGUMENT, "device index out of range");
-  g_device = device;
+  if (device_count < 1 || !devices) return fail(VCE_ERR_BAD_ARGUMENT, "no device given");
+  for (int i = 0; i < device_count; ++i) {
+    if (devices[i] < 0 || devices[i] >= n) return fail(VCE_ERR_BAD_ARGUMENT, "device index out of range");
+    for (int q = 0; q < i; ++q) if (devices[q] == devices[i]) return fail(VCE_ERR_BAD_ARGUMENT, "device listed twice");
+  }
+  g_devices.assign(devices, devices + device_count);
+  g_device = devices[0];
+  g_free.clear();      // (contexts are per device and per worker pool)
+  g_devPools.clear();
   return VCE_OK;
 }
+
+int vce_init(int device) { return vce_init_devices(1, &device); }
 
 void vce_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   g_free.clear();
+  g_devPools.clear();
+  g_devices.clear();
+  vce::rocRelease();
   vce::templateRegistryRemove(-1, nullptr);
   g_device = -1;
 }
@@ -133,9 +160,17 @@ int vce_template_register(const uint8_t* bases, int32_t len) {
   }
   std::vector<uint32_t> packed, nmask;
   vce::packTemplate(bases, len, g_pool.get(), packed, nmask);
-  std::string err;
-  const int rc = vce::templateRegistryAdd(dev, bases, len, packed.data(), packed.size(), nmask.data(), nmask.size(), err);
-  if (rc) return fail(rc, err);
+  std::vector<int> devs;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    devs = g_devices;
+  }
+  (void) dev;
+  for (int d : devs) {   // every device of the pool: the batch's sequences may land on any of them
+    std::string err;
+    const int rc = vce::templateRegistryAdd(d, bases, len, packed.data(), packed.size(), nmask.data(), nmask.size(), err);
+    if (rc) return fail(rc, err);
+  }
   return VCE_OK;
 }
 
@@ -235,8 +270,73 @@ int vce_submit_stats(double* out, int32_t n) {
   return VCE_OK;
 }
 
+// One device's share of a batch: the sequences `idx` through that device's own context and worker pool.
+static int submitOn(int devIndex, const vce_config* cfg, const std::vector<int32_t>& idx, const vce_sequence* seqs,
+                    vce_sequence_result* results, double stats[6], std::vector<int64_t>& summary, std::string& msg) {
+  int rc = VCE_OK;
+  Context* c = acquire(rc, devIndex);
+  if (!c) { msg = t_err; return rc; }
+  std::vector<vce_sequence> sub(idx.size());
+  std::vector<vce_sequence_result> res(idx.size());
+  for (size_t i = 0; i < idx.size(); ++i) { sub[i] = seqs[idx[i]]; res[i] = results[idx[i]]; }
+  c->backend->stats = vce::SearchStats();
+  rc = c->engine->run(*cfg, (int32_t) idx.size(), sub.data(), res.data());
+  if (rc) msg = c->engine->error();
+  const vce::SearchStats& st = c->backend->stats;
+  stats[0] = (double) st.launches; stats[1] = (double) st.h2dBytes; stats[2] = (double) st.d2hBytes;
+  stats[3] = (double) st.regions; stats[4] = (double) st.escalated; stats[5] = (double) st.iterations;
+  const std::vector<int64_t>& sm = c->engine->summary();
+  bool perSequence = false;
+  for (size_t i = 0; i < idx.size(); ++i) {
+    results[idx[i]] = res[i];
+    if (rc && res[i].error == rc) perSequence = true;
+    if (sm.size() >= (i + 1) * 8) for (int q = 0; q < 8; ++q) summary[(size_t) idx[i] * 8 + q] = sm[i * 8 + q];
+  }
+  if (rc && !perSequence) discard(c); else release(c);
+  return rc;
+}
+
 int vce_submit(const vce_config* cfg, int32_t n_seq, const vce_sequence* seqs, vce_sequence_result* results) {
   if (!cfg || !results || n_seq < 0 || (n_seq > 0 && !seqs)) return fail(VCE_ERR_BAD_ARGUMENT, "null argument");
+  size_t nDev;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    nDev = g_devices.size();
+  }
+  if (nDev > 1 && n_seq > 1) {
+    // Sequences are independent (VcfEvalTask.java:131-135): longest-processing-time greedy by variant count over the devices,
+    // one host thread per device, each with its own context, streams and share of the host cores; no data-path exchange
+    std::vector<int32_t> order((size_t) n_seq);
+    for (int32_t k = 0; k < n_seq; ++k) order[(size_t) k] = k;
+    auto weight = [&](int32_t k) { return (int64_t) seqs[k].baseline.n + (int64_t) seqs[k].calls.n; };
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return weight(a) > weight(b); });
+    std::vector<std::vector<int32_t>> share(nDev);
+    std::vector<int64_t> load(nDev, 0);
+    for (int32_t k : order) {
+      size_t best = 0;
+      for (size_t d = 1; d < nDev; ++d) if (load[d] < load[best]) best = d;
+      share[best].push_back(k);
+      load[best] += weight(k) + 1;
+    }
+    for (auto& sh : share) std::sort(sh.begin(), sh.end());
+    std::vector<int> rcs(nDev, VCE_OK);
+    std::vector<std::string> msgs(nDev);
+    std::vector<std::array<double, 6>> stats(nDev);
+    std::vector<int64_t> summary((size_t) n_seq * 8, 0);
+    std::vector<std::thread> threads;
+    for (size_t d = 0; d < nDev; ++d) {
+      for (double& v : stats[d]) v = 0;
+      if (share[d].empty()) continue;
+      threads.emplace_back([&, d] { rcs[d] = submitOn((int) d, cfg, share[d], seqs, results, stats[d].data(), summary, msgs[d]); });
+    }
+    for (std::thread& t : threads) t.join();
+    for (int i = 0; i < 6; ++i) { t_submitStats[i] = 0; for (size_t d = 0; d < nDev; ++d) t_submitStats[i] += stats[d][(size_t) i]; }
+    t_summary = summary;
+    for (size_t d = 0; d < nDev; ++d) {
+      if (rcs[d]) return fail(rcs[d], msgs[d].empty() ? std::string("one or more sequences reported an error") : msgs[d]);
+    }
+    return VCE_OK;
+  }
   int rc = VCE_OK;
   Context* c = acquire(rc);
   if (!c) return rc;
@@ -258,6 +358,12 @@ int vce_submit(const vce_config* cfg, int32_t n_seq, const vce_sequence* seqs, v
   return VCE_OK;
 }
 
+static vce::WorkerPool* rocPool() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_pool) g_pool.reset(new vce::WorkerPool(vce::WorkerPool::defaultThreads()));
+  return g_pool.get();
+}
+
 int vce_roc(const vce_roc_in* in, vce_roc_out* out) {
   if (!in || !out) return fail(VCE_ERR_BAD_ARGUMENT, "null argument");
   int dev;
@@ -267,7 +373,7 @@ int vce_roc(const vce_roc_in* in, vce_roc_out* out) {
   }
   if (dev < 0) return fail(VCE_ERR_NOT_INITIALISED, "call vce_init first");
   std::string err;
-  const int rc = vce::rocRun(dev, in, out, err, nullptr);
+  const int rc = vce::rocRun(dev, in, out, err, nullptr, rocPool());
   if (rc) return fail(rc, err);
   return VCE_OK;
 }
@@ -283,7 +389,7 @@ int vce_roc_timed(const vce_roc_in* in, vce_roc_out* out, double* h2d_ms, double
   if (dev < 0) return fail(VCE_ERR_NOT_INITIALISED, "call vce_init first");
   std::string err;
   vce::RocTiming t;
-  const int rc = vce::rocRun(dev, in, out, err, &t);
+  const int rc = vce::rocRun(dev, in, out, err, &t, rocPool());
   if (rc) return fail(rc, err);
   if (h2d_ms) *h2d_ms = t.h2dMs;
   if (kernel_ms) *kernel_ms = t.kernelMs;

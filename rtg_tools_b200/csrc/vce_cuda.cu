@@ -1391,7 +1391,8 @@ class CudaBackend : public Backend {
     CUDA_TRY(rDec_[0].ensure(nC + 16)); CUDA_TRY(rDec_[1].ensure(nB + 16)); CUDA_TRY(rWeight_.ensure(nC + 2));
     CUDA_TRY(rInfo_.ensure(nR + 2)); CUDA_TRY(rCnt_.ensure(nR + 2)); CUDA_TRY(rBase_.ensure(nR + 2)); CUDA_TRY(rRel_.ensure((nR + 2) * kFinalRel));
     CUDA_TRY(rSeq_.ensure(nS + 1)); CUDA_TRY(rIter_.ensure(2));
-    std::vector<FinalSeq> fs(nS);
+    std::vector<FinalSeq>& fs = fsHost_;
+    fs.assign(nS, FinalSeq());
     for (size_t k = 0; k < nS; ++k) {
       for (int side = 0; side < 2; ++side) {
         fs[k].vStart[side] = s.seq[k].vStart[side];
@@ -1407,11 +1408,14 @@ class CudaBackend : public Backend {
     CUDA_TRY(cudaMemsetAsync(rInfo_.p, 0, (nR + 2) * sizeof(uint32_t), st));
     CUDA_TRY(cudaMemsetAsync(rIter_.p, 0, 2 * sizeof(unsigned long long), st));
     if (nS) CUDA_TRY(cudaMemcpyAsync(rSeq_.p, fs.data(), nS * sizeof(FinalSeq), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaStreamSynchronize(st));   // the chunks' scatter kernels run on every lane
+    // the chunks' scatter kernels run on every lane: they wait for this event, the host does not
+    if (!rBeginEv_) CUDA_TRY(cudaEventCreateWithFlags(&rBeginEv_, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(rBeginEv_, st));
     stats.h2dBytes += (int64_t) (nS * sizeof(FinalSeq));
     return VCE_OK;
   }
   void scatterLaunch(const MicroJob& j, const RegRange* regs, const int32_t* regIdx, cudaStream_t st) {
+    cudaStreamWaitEvent(st, rBeginEv_, 0);
     ScatterArgs a;
     a.results = static_cast<const uint8_t*>(j.dResults);
     a.regs = regs;
@@ -1528,6 +1532,8 @@ class CudaBackend : public Backend {
     return VCE_OK;
   }
   ResultsSetup rs_;
+  std::vector<FinalSeq> fsHost_;
+  cudaEvent_t rBeginEv_ = nullptr;
   DevBuf<uint8_t> rDec_[2], rRel_, pDec_, fOutC_, fOutB_, fMFlags_, fBaseSum_, fBlockEnd_;
   DevBuf<double> rWeight_, pW_, fRoc_;
   DevBuf<uint32_t> rInfo_, pInfo_;

@@ -26,7 +26,10 @@ int templateRegistryAdd(int device, const uint8_t* bases, int32_t len, const uin
 void templateRegistryRemove(int device, const uint8_t* bases);   // device < 0: every device; bases == nullptr: every template
 
 struct RocTiming { double h2dMs = 0, kernelMs = 0; int launches = 0; };
-int rocRun(int device, const vce_roc_in* in, vce_roc_out* out, std::string& err, RocTiming* timing);
+class WorkerPool;
+// `pool`: host threads that stage the caller's (pageable) arrays into page-locked memory in parallel; nullptr = the caller's thread
+int rocRun(int device, const vce_roc_in* in, vce_roc_out* out, std::string& err, RocTiming* timing, WorkerPool* pool);
+void rocRelease();   // frees the per-device K4 contexts (vce_shutdown)
 
 }  // namespace vce
 #endif

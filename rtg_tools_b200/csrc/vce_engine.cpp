@@ -1261,8 +1261,7 @@ void Engine::resetPassRun(PassCtx& pc) {
   });
 }
 
-int Engine::runChunks(PassCtx& pc) {
-  // split (per sequence), plan, build + upload + start
+void Engine::configurePass(PassCtx& pc) {
   pc.microOk = !opt_.disableMicro && !opt_.forceGeneral && orientorPairMicro(pc.kind[0], pc.kind[1], pc.H);
   pc.mc.H = pc.H;
   pc.mc.kind[0] = pc.kind[0];
@@ -1271,6 +1270,11 @@ int Engine::runChunks(PassCtx& pc) {
   pc.mc.maxIterations = cfg_.max_iterations;
   pc.mc.pruneNoOps = cfg_.prune_no_ops;
   pc.mc.preference = cfg_.preference;
+}
+
+int Engine::runChunks(PassCtx& pc) {
+  // split (per sequence), plan, build + upload + start
+  configurePass(pc);
   splitAll(pc);
   // regions that cannot go through the thread-per-region kernel are known from their shape alone: they start right
   // away in the warp-per-region kernels, concurrently with the packet pipeline
@@ -1331,13 +1335,15 @@ int Engine::execute() {
     // a staged job keeps the packed early batch: re-runs start from the same regions
     WideBatch& early = staged_ && p == 0 ? pc.earlyBatch : localEarly;
     if (!rerun) {
+      // the whole-sequence uploads go first: their DMA runs while the host splits the sequences into regions
+      configurePass(pc);
+      if ((rc = residentSetup(pc))) return rc;
+      tm.lap("resident inputs: staging + upload");
       if ((rc = runChunks(pc))) return rc;
       tm.lap("split into regions");
       if ((rc = wideStart(pc, pc.earlyItems, early))) return rc;
       tm.lap("early warp-per-region batch");
       if (devRes_ && p == 0 && (rc = resultsSetup(pc))) return rc;
-      if ((rc = residentSetup(pc))) return rc;
-      tm.lap("resident inputs: staging + upload");
       if (devRes_ && p == 0) {
         ResultsSetup rsu;
         rsu.H = pc.H;
@@ -1411,7 +1417,7 @@ int Engine::execute() {
     }
     if (failed.load()) { err_ = be_->lastError(); return failed.load(); }
     be_->microCollect();
-    tm.lap("wait + decode");
+    tm.lap(devRes_ && p == 0 ? "wait for the packet kernels + region table" : "wait + decode");
     for (int64_t v : iters) be_->stats.iterations += v;
     for (const Chunk& ch : pc.chunks) {
       be_->stats.regions += ch.r1 - ch.r0;

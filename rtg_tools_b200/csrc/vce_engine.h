@@ -66,6 +66,7 @@ class Engine {
   const std::vector<int64_t>& summary() const { return summary_; }
   EngineOptions& options() { return opt_; }
   Backend* backend() { return be_; }
+  WorkerPool* pool() { return pool_; }
   // diagnostics of the last execute(): regions of the thread-per-region launches, variants of the MicroA class
   double microMs = 0;
   int64_t microRegions = 0, microVariants = 0;
@@ -192,6 +193,7 @@ class Engine {
   int resultsSetup(PassCtx& pc);
   int resultsCollect(PassCtx& pc);
   int finishDevice(vce_sequence_result* results);
+  void configurePass(PassCtx& pc);
   int runChunks(PassCtx& pc);
   void decodeChunk(PassCtx& pc, Chunk& ch, int64_t& iterations);
   void assembleRegionEarly(PassCtx& pc, int k, int j);

@@ -158,7 +158,11 @@ VCE_HD void scatterOne(const ScatterArgs& a, int q) {
   const int r = a.regIdx[q];
   const int it = rec[MR_ITERS] | (rec[MR_ITERS + 1] << 8);
 #if defined(__CUDA_ARCH__)
-  atomicAdd(a.iterations, (unsigned long long) it);
+  {  // one atomic per warp: millions of them on one address would serialise
+    const unsigned active = __activemask();
+    const unsigned sum = __reduce_add_sync(active, (unsigned) it);
+    if ((int) (threadIdx.x & 31) == __ffs((int) active) - 1) atomicAdd(a.iterations, (unsigned long long) sum);
+  }
 #else
   *a.iterations += (unsigned long long) it;
 #endif
@@ -215,6 +219,26 @@ VCE_HD void patchOne(const PatchArgs& a, int q) {
     a.weight[g.cFirst + i] = a.wPay[a.wOff[q] + i];
   }
   for (int i = 0; i < g.bCount; ++i) a.dec[1][g.bFirst + i] = d[g.cCount + i];
+}
+
+// One counter update per warp instead of one per thread when the lanes of a warp work on the same sequence (they almost
+// always do): millions of atomics on a handful of addresses would otherwise serialise in L2.
+VCE_HD void finalCount(int64_t* cn, int idx, bool pred, int k) {
+#if defined(__CUDA_ARCH__)
+  const unsigned active = __activemask();
+  const int leader = __ffs((int) active) - 1;
+  const int k0 = __shfl_sync(active, k, leader);
+  const bool same = __all_sync(active, k == k0);
+  if (same) {
+    const unsigned m = __ballot_sync(active, pred);
+    if ((int) (threadIdx.x & 31) == leader && m != 0) atomicAdd(reinterpret_cast<unsigned long long*>(cn + idx), (unsigned long long) __popc(m));
+  } else if (pred) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(cn + idx), 1ull);
+  }
+#else
+  (void) k;
+  if (pred) ++cn[idx];
+#endif
 }
 
 // ---- the final passes.  Ops provides: parFor(n, body), exclusiveSum(in, out, n), unique64(in, out, n) -> count (blocking),
@@ -289,15 +313,9 @@ int finalPasses(Ops& ops, const FinalArrays& A) {
           if (!(st & VCE_STATUS_OUTSIDE_EVAL)) fp = 1.0;
         }
         if (a.rocTuples) { a.rocTuples[(size_t) v * 3] = tp; a.rocTuples[(size_t) v * 3 + 1] = fp; a.rocTuples[(size_t) v * 3 + 2] = raw; }
-#if defined(__CUDA_ARCH__)
-        if (raw > 0) atomicAdd(reinterpret_cast<unsigned long long*>(cn + 2), 1ull);
-        if (fp > 0) atomicAdd(reinterpret_cast<unsigned long long*>(cn + 3), 1ull);
-        if (st & VCE_STATUS_SKIPPED) atomicAdd(reinterpret_cast<unsigned long long*>(cn + 4), 1ull);
-#else
-        if (raw > 0) ++cn[2];
-        if (fp > 0) ++cn[3];
-        if (st & VCE_STATUS_SKIPPED) ++cn[4];
-#endif
+        finalCount(cn, 2, raw > 0, k);
+        finalCount(cn, 3, fp > 0, k);
+        finalCount(cn, 4, (st & VCE_STATUS_SKIPPED) != 0, k);
       } else {
         uint8_t* o = a.outBase + (size_t) v * 8;
         o[0] = (uint8_t) st; o[1] = (uint8_t) row; o[2] = (uint8_t) orig; o[3] = 0;
@@ -306,15 +324,9 @@ int finalPasses(Ops& ops, const FinalArrays& A) {
         const bool inside = !(st & VCE_STATUS_OUTSIDE_EVAL);
         const bool tpb = inside && (st & VCE_STATUS_GT_MATCH);
         const bool fnb = inside && !(st & VCE_STATUS_GT_MATCH) && (st & VCE_STATUS_NO_MATCH);
-#if defined(__CUDA_ARCH__)
-        if (tpb) atomicAdd(reinterpret_cast<unsigned long long*>(cn + 0), 1ull);
-        if (fnb) atomicAdd(reinterpret_cast<unsigned long long*>(cn + 1), 1ull);
-        if (st & VCE_STATUS_SKIPPED) atomicAdd(reinterpret_cast<unsigned long long*>(cn + 4), 1ull);
-#else
-        if (tpb) ++cn[0];
-        if (fnb) ++cn[1];
-        if (st & VCE_STATUS_SKIPPED) ++cn[4];
-#endif
+        finalCount(cn, 0, tpb, k);
+        finalCount(cn, 1, fnb, k);
+        finalCount(cn, 4, (st & VCE_STATUS_SKIPPED) != 0, k);
       }
     });
   }

@@ -16,13 +16,18 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
 #include "../../include/vce.h"
 #include "vce_cuda.h"
+#include "vce_pool.h"
 
 namespace vce {
 
@@ -69,19 +74,58 @@ __global__ void k_roc_bucket_sums(int nBuckets, int nFilters, const int* __restr
                                   double* __restrict__ sRaw, int* __restrict__ nonEmpty) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   const int f = blockIdx.y;
-  if (b >= nBuckets) return;
-  const int s = bucketStart[b], e = bucketStart[b + 1];
+  const int lane = threadIdx.x & 31;
+  const bool have = b < nBuckets;
+  const int s = have ? bucketStart[b] : 0, e = have ? bucketStart[b + 1] : 0;
   double a = 0, c = 0, d = 0;
   int cnt = 0;
-  for (int j = s; j < e; ++j) {
-    const unsigned int i = idx[j];
-    const unsigned int m = mask ? mask[i] : 0xffffffffu;
-    if ((m >> f) & 1u) {
-      if (cnt == 0) { a = tp[i]; c = fp[i]; d = raw[i]; }  // new RocPoint<>(point), RocContainer.java:256
-      else { a += tp[i]; c += fp[i]; d += raw[i]; }          // RocPoint.add
-      ++cnt;
+  // small buckets: the owning lane walks its members; LARGE buckets (few distinct scores, e.g. QUAL at one decimal) are
+  // walked by the whole warp: 32 members are fetched with one coalesced index load + one gather, the additions still
+  // happen in arrival order (the dependent chain runs through shuffles), so the FP64 sums keep the reference's bits
+  const bool big = e - s > 64;
+  if (!big) {
+    for (int j = s; j < e; ++j) {
+      const unsigned int i = idx[j];
+      const unsigned int m = mask ? mask[i] : 0xffffffffu;
+      if ((m >> f) & 1u) {
+        if (cnt == 0) { a = tp[i]; c = fp[i]; d = raw[i]; }  // new RocPoint<>(point), RocContainer.java:256
+        else { a += tp[i]; c += fp[i]; d += raw[i]; }          // RocPoint.add
+        ++cnt;
+      }
     }
   }
+  unsigned todo = __ballot_sync(0xffffffffu, big);
+  while (todo) {
+    const int owner = __ffs((int) todo) - 1;
+    todo &= todo - 1;
+    const int os = __shfl_sync(0xffffffffu, s, owner), oe = __shfl_sync(0xffffffffu, e, owner);
+    double wa = 0, wc = 0, wd = 0;
+    int wcnt = 0;
+    for (int base = os; base < oe; base += 32) {
+      const int j = base + lane;
+      double vt = 0, vf = 0, vr = 0;
+      int in = 0;
+      if (j < oe) {
+        const unsigned int i = idx[j];
+        const unsigned int m = mask ? mask[i] : 0xffffffffu;
+        if ((m >> f) & 1u) { in = 1; vt = tp[i]; vf = fp[i]; vr = raw[i]; }
+      }
+      const unsigned mm = __ballot_sync(0xffffffffu, in);
+#pragma unroll 4
+      for (int q = 0; q < 32; ++q) {
+        const double xt = __shfl_sync(0xffffffffu, vt, q);
+        const double xf = __shfl_sync(0xffffffffu, vf, q);
+        const double xr = __shfl_sync(0xffffffffu, vr, q);
+        if ((mm >> q) & 1u) {
+          if (wcnt == 0) { wa = xt; wc = xf; wd = xr; }
+          else { wa += xt; wc += xf; wd += xr; }
+          ++wcnt;
+        }
+      }
+    }
+    if (lane == owner) { a = wa; c = wc; d = wd; cnt = wcnt; }
+  }
+  if (!have) return;
   const size_t o = (size_t) f * nBuckets + b;
   sTp[o] = a; sFp[o] = c; sRaw[o] = d;
   nonEmpty[o] = cnt > 0 ? 1 : 0;
@@ -143,33 +187,114 @@ __global__ void k_roc_chain(int nBuckets, const int* __restrict__ bucketStart, c
     }                                                                                         \
   } while (0)
 
-int rocRun(int device, const vce_roc_in* in, vce_roc_out* out, std::string& err, RocTiming* timing) {
+// Per-device K4 context, kept across calls: stream, events, ONE device slab and ONE page-locked staging slab (both grow
+// only), so that a steady-state vce_roc allocates nothing.  One call at a time per device (callers queue on the mutex).
+namespace {
+struct RocCtx {
+  int device = -1;
+  std::mutex mu;
+  cudaStream_t st = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+  uint8_t* dSlab = nullptr; size_t dCap = 0, dUsed = 0;
+  uint8_t* hSlab = nullptr; size_t hCap = 0;
+  cudaError_t init(int dev) {
+    device = dev;
+    cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    if (e == cudaSuccess) e = cudaEventCreate(&e2);
+    return e;
+  }
+  cudaError_t reserveDevice(size_t bytes) {
+    dUsed = 0;
+    if (bytes <= dCap) return cudaSuccess;
+    if (dSlab) cudaFree(dSlab);
+    dSlab = nullptr; dCap = 0;
+    const size_t want = bytes + bytes / 8 + (1 << 20);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&dSlab), want);
+    if (e == cudaSuccess) dCap = want;
+    return e;
+  }
+  cudaError_t reserveHost(size_t bytes) {
+    if (bytes <= hCap) return cudaSuccess;
+    if (hSlab) cudaFreeHost(hSlab);
+    hSlab = nullptr; hCap = 0;
+    const size_t want = bytes + bytes / 8 + (1 << 20);
+    cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&hSlab), want, cudaHostAllocDefault);
+    if (e == cudaSuccess) hCap = want;
+    return e;
+  }
+  void* take(size_t bytes) {   // bump allocation from the device slab (256-byte aligned)
+    bytes = (bytes + 255) & ~(size_t) 255;
+    if (dUsed + bytes > dCap) return nullptr;
+    void* p = dSlab + dUsed;
+    dUsed += bytes;
+    return p;
+  }
+};
+std::mutex g_rocMu;
+std::vector<RocCtx*> g_rocCtx;
+RocCtx* rocCtxFor(int device, cudaError_t* e) {
+  std::lock_guard<std::mutex> lk(g_rocMu);
+  for (RocCtx* c : g_rocCtx) if (c->device == device) return c;
+  RocCtx* c = new RocCtx();
+  *e = c->init(device);
+  if (*e != cudaSuccess) { delete c; return nullptr; }
+  g_rocCtx.push_back(c);
+  return c;
+}
+}  // namespace
+
+void rocRelease() {
+  std::lock_guard<std::mutex> lk(g_rocMu);
+  for (RocCtx* c : g_rocCtx) {
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->st);
+    if (c->dSlab) cudaFree(c->dSlab);
+    if (c->hSlab) cudaFreeHost(c->hSlab);
+    cudaEventDestroy(c->e0); cudaEventDestroy(c->e1); cudaEventDestroy(c->e2);
+    cudaStreamDestroy(c->st);
+    delete c;
+  }
+  g_rocCtx.clear();
+}
+
+int rocRun(int device, const vce_roc_in* in, vce_roc_out* out, std::string& err, RocTiming* timing, WorkerPool* pool) {
   const long long n = in->n;
   const int nF = in->n_filters;
   if (n < 0 || nF < 1 || nF > 32 || n > 0x7fffffffLL - 64) { err = "bad ROC arguments"; return VCE_ERR_BAD_ARGUMENT; }
   for (int f = 0; f < nF; ++f) out->n_rows[f] = 0;
   *out->no_score = 0;
   if (n == 0) return VCE_OK;
-  std::vector<void*> allocs;
-  cudaStream_t st = nullptr;
-  cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
-  auto cleanup = [&]() {
-    for (void* p : allocs) cudaFree(p);
-    if (e0) cudaEventDestroy(e0);
-    if (e1) cudaEventDestroy(e1);
-    if (e2) cudaEventDestroy(e2);
-    if (st) cudaStreamDestroy(st);
-  };
+  auto cleanup = [&]() {};
+  if (cudaSetDevice(device) != cudaSuccess) { err = "cudaSetDevice failed"; return VCE_ERR_CUDA; }
+  cudaError_t ce = cudaSuccess;
+  RocCtx* ctx = rocCtxFor(device, &ce);
+  if (!ctx) { err = std::string("ROC context: ") + cudaGetErrorString(ce); return VCE_ERR_CUDA; }
+  std::lock_guard<std::mutex> ctxLock(ctx->mu);
+  cudaStream_t st = ctx->st;
+  cudaEvent_t e0 = ctx->e0, e1 = ctx->e1, e2 = ctx->e2;
+  // everything the call needs on the device, up front (the bucket-level arrays are sized by n: no allocation after the sort)
+  {
+    size_t tmpA = 0, tmpB = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmpA, (unsigned long long*) nullptr, (unsigned long long*) nullptr, (unsigned int*) nullptr,
+                                    (unsigned int*) nullptr, (int) n, 0, 64, st);
+    cub::DeviceScan::InclusiveSum(nullptr, tmpB, (int*) nullptr, (int*) nullptr, (int) n, st);
+    const size_t un = (size_t) n;
+    size_t need = 4 * (un * 8 + 256) + (un * 4 + 256) + 2 * (un * 8 + 256) + 512 + 2 * (un * 4 + 256) + 3 * (un * 4 + 1024) + std::max(tmpA, tmpB) + 1024;
+    // bucket-level arrays (sums, cumulative rows per filter): at most one bucket per call record
+    const size_t fbMax = (size_t) nF * un;
+    need += 7 * (fbMax * 8 + 256) + (fbMax * 4 + 256) + ((size_t) nF * 8 + 256) + 1024;
+    ROC_TRY(ctx->reserveDevice(need));
+    ROC_TRY(ctx->reserveHost(un * 36 + 4096));
+  }
   auto alloc = [&](size_t bytes, void** p) -> cudaError_t {
-    cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
-    if (e == cudaSuccess) allocs.push_back(*p);
-    return e;
+    *p = ctx->take(bytes ? bytes : 16);
+    if (*p) return cudaSuccess;
+    // the bucket-level arrays come after the sort, when their size is known: a separate, also persistent, allocation would
+    // do; growing the slab is simpler and happens once
+    return cudaErrorMemoryAllocation;
   };
-  ROC_TRY(cudaSetDevice(device));
-  ROC_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  ROC_TRY(cudaEventCreate(&e0));
-  ROC_TRY(cudaEventCreate(&e1));
-  ROC_TRY(cudaEventCreate(&e2));
   double *dScore, *dTp, *dFp, *dRaw;
   unsigned int* dMask = nullptr;
   unsigned long long *dKey, *dKey2, *dNoScore;
@@ -182,11 +307,38 @@ int rocRun(int device, const vce_roc_in* in, vce_roc_out* out, std::string& err,
   ROC_TRY(alloc(n * 8, (void**) &dKey)); ROC_TRY(alloc(n * 8, (void**) &dKey2)); ROC_TRY(alloc(8, (void**) &dNoScore));
   ROC_TRY(alloc(n * 4, (void**) &dIdx)); ROC_TRY(alloc(n * 4, (void**) &dIdx2));
   ROC_TRY(alloc(n * 4, (void**) &dHead)); ROC_TRY(alloc(n * 4, (void**) &dScan)); ROC_TRY(alloc((n + 1) * 4, (void**) &dStart));
-  ROC_TRY(cudaMemcpyAsync(dScore, in->score, n * 8, cudaMemcpyHostToDevice, st));
-  ROC_TRY(cudaMemcpyAsync(dTp, in->tp, n * 8, cudaMemcpyHostToDevice, st));
-  ROC_TRY(cudaMemcpyAsync(dFp, in->fp, n * 8, cudaMemcpyHostToDevice, st));
-  ROC_TRY(cudaMemcpyAsync(dRaw, in->tp_raw, n * 8, cudaMemcpyHostToDevice, st));
-  if (dMask) ROC_TRY(cudaMemcpyAsync(dMask, in->filter_mask, n * 4, cudaMemcpyHostToDevice, st));
+  {
+    // the caller's arrays are pageable: they go through the page-locked slab in parallel pieces (a direct copy from pageable
+    // memory runs at a fraction of the PCIe rate), every piece is uploaded as soon as it is staged
+    struct Piece { const uint8_t* src; uint8_t* stage; uint8_t* dst; size_t bytes; };
+    std::vector<Piece> pieces;
+    const size_t chunk = (size_t) 4 << 20;
+    size_t hoff = 0;
+    auto add = [&](const void* src, void* dst, size_t bytes) {
+      for (size_t o = 0; o < bytes; o += chunk) {
+        const size_t b = std::min(chunk, bytes - o);
+        pieces.push_back(Piece{static_cast<const uint8_t*>(src) + o, ctx->hSlab + hoff, static_cast<uint8_t*>(dst) + o, b});
+        hoff += b;
+      }
+    };
+    add(in->score, dScore, (size_t) n * 8);
+    add(in->tp, dTp, (size_t) n * 8);
+    add(in->fp, dFp, (size_t) n * 8);
+    add(in->tp_raw, dRaw, (size_t) n * 8);
+    if (dMask) add(in->filter_mask, dMask, (size_t) n * 4);
+    std::atomic<int> bad(0);
+    std::mutex issue;
+    auto work = [&](int t, int) {
+      const Piece& pc = pieces[(size_t) t];
+      std::memcpy(pc.stage, pc.src, pc.bytes);
+      std::lock_guard<std::mutex> lk(issue);   // (one stream: the copies are issued from whichever thread staged the piece)
+      cudaSetDevice(device);
+      if (cudaMemcpyAsync(pc.dst, pc.stage, pc.bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) bad.store(1);
+    };
+    if (pool) pool->parallelFor((int) pieces.size(), work);
+    else for (int t = 0; t < (int) pieces.size(); ++t) work(t, 0);
+    if (bad.load()) { err = "ROC upload failed"; return VCE_ERR_CUDA; }
+  }
   ROC_TRY(cudaMemsetAsync(dNoScore, 0, 8, st));
   ROC_TRY(cudaEventRecord(e1, st));
   const int tb = 256;
@@ -245,7 +397,6 @@ int rocRun(int device, const vce_roc_in* in, vce_roc_out* out, std::string& err,
     timing->kernelMs = b;
     timing->launches = 9;
   }
-  cleanup();
   return rc;
 }
 

@@ -265,3 +265,18 @@ def test_cuda_concurrent_submits(engine, oracle):
     assert not errs, errs
     for i, b in enumerate(batches):
         compare_results(want[i], got[i], b, what="thread %d" % i)
+
+
+def test_c_abi_from_plain_c_threads(tmp_path):
+    """include/vce.h compiled by a C compiler and vce_submit driven the way the JNI stub drives it (jni/vce_jni.c): one
+    sequence per call from 8 threads; the program checks every variant's outcome and reports the per-call latency."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "test_submit_threads")
+    lib = os.path.join(root, "rtg_tools_b200", "csrc")
+    subprocess.check_call(["gcc", "-O2", "-Wall", "-o", exe, os.path.join(root, "tests", "c", "test_submit_threads.c"), "-L" + lib, "-lvce",
+                           "-lpthread", "-Wl,-rpath," + lib])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    print(out.stdout, out.stderr)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.startswith("OK")
