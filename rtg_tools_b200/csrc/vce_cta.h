@@ -206,7 +206,7 @@ struct CtaSearch {
     if (rs.cfg.preference == 0) {  // MaxSumBoth.java:43-82
       const int fs = fc + fb, ss = sc + sb;
       if (fs == ss) {
-        if (fb == 0 || sb == 0) rs.usedPrefix = 1;
+        if (fb == 0 || sb == 0) rs.usedPrefix |= 1;
         const bool fiNonNull = prefixNonEmpty || fb > 0;
         const bool siNonNull = prefixNonEmpty || sb > 0;
         if (fiNonNull && siNonNull) {
@@ -217,6 +217,7 @@ struct CtaSearch {
           if (fd != sd) return fd < sd;
           const int syncDelta = (int) f[2] - (int) s[2];
           if (syncDelta != 0) return syncDelta > 0;
+          if ((fb == 0) != (sb == 0)) rs.usedPrefix |= 2;
           const int fid = fb > 0 ? (int) f[3] : rs.R.prefixAlleleId;
           const int sid = sb > 0 ? (int) s[3] : rs.R.prefixAlleleId;
           return fid < sid;

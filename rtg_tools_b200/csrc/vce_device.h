@@ -59,7 +59,7 @@ struct RegionDesc {
 // Per-region result header.
 struct RegionResult {
   int32_t status;         // kRegion*
-  int32_t usedPrefix;     // 1 if a tie-break depended on prefixAlleleId / prefix emptiness
+  int32_t usedPrefix;     // bit0: a tie-break depended on whether a baseline variant was included before the region, bit1: on its allele id
   int32_t nSync;          // number of sync points written for this region
   int32_t nWarn;          // too-complex events in this region
   int32_t lastBaseAlleleId; // alleleId() of the last baseline variant included in this region, kPrefixEmpty if none

@@ -475,24 +475,31 @@ void Engine::splitAll(PassCtx& pc) {
           if (g.bCount > 0) m = std::min(m, (long) bs[g.bFirst]);
           return m;
         };
-        bool any = false;
-        for (size_t j = 0; j + 1 < out.size() && !any; ++j) any = crowded(out[j]) || crowded(out[j + 1]);
-        if (any) {
-          size_t w = 0;
-          long curEnd = maxEndOf(out[0]);
-          for (size_t j = 1; j < out.size(); ++j) {
-            const RegRange& g = out[j];
-            if ((crowded(out[w]) || crowded(g)) && firstStartOf(g) - curEnd < (long) opt_.denseGap) {
-              out[w].cCount += g.cCount;
-              out[w].bCount += g.bCount;
-              curEnd = std::max(curEnd, maxEndOf(g));
-            } else {
-              out[++w] = g;
-              curEnd = maxEndOf(g);
-            }
+        // chains of regions whose gaps stay below denseGap; a chain becomes ONE region when it is crowded as a whole
+        size_t j = 0, w = 0;   // in place: the write index never passes the read index
+        const size_t nOut = out.size();
+        while (j < nOut) {
+          size_t e = j + 1;
+          long curEnd = maxEndOf(out[j]);
+          long nc = out[j].cCount, nb = out[j].bCount;
+          while (e < nOut && firstStartOf(out[e]) - curEnd < (long) opt_.denseGap) {
+            curEnd = std::max(curEnd, maxEndOf(out[e]));
+            nc += out[e].cCount;
+            nb += out[e].bCount;
+            ++e;
           }
-          out.resize(w + 1);
+          if (e - j > 1 && (nc >= opt_.denseCount || nb >= opt_.denseCount)) {
+            RegRange g = out[j];
+            g.cCount = (int32_t) nc;
+            g.bCount = (int32_t) nb;
+            out[w++] = g;
+          } else {
+            for (size_t q = j; q < e; ++q) out[w++] = out[q];
+          }
+          j = e;
         }
+        out.resize(w);
+        (void) crowded;
       }
     }
     pc.rs[k].resize(out.size());
@@ -767,7 +774,7 @@ void Engine::decodeJob(PassCtx& pc, int k, const MicroJob& job, const std::vecto
     }
     const RegRange& g = rr[j];
     s.state = RS_MICRO_DONE;
-    s.flags = rec[MR_FLAGS] & 1;
+    s.flags = (uint8_t) ((rec[MR_FLAGS] & 1) | ((rec[MR_FLAGS] & 2) ? 0x20 : 0));
     s.lastId = (int8_t) rec[MR_LASTID];
     s.nSync = rec[MR_NSYNC];
     for (int i = 0; i < T::SMAX; ++i) s.rel[i] = rec[MR_SYNC + i];
@@ -1735,7 +1742,7 @@ int Engine::wideFinish(PassCtx& pc, WideBatch& wb, std::vector<int>& statusOut) 
       const int tier = wb.tier[q];
       if (r.status == kRegionClean || r.status == kRegionFinished) {
         s.state = RS_WIDE_DONE;
-        s.flags = (uint8_t) ((r.usedPrefix ? 1 : 0) | (r.status == kRegionFinished ? 2 : 0) | (tier << 2));
+        s.flags = (uint8_t) ((r.usedPrefix & 1) | ((r.usedPrefix & 2) ? 0x20 : 0) | (r.status == kRegionFinished ? 2 : 0) | (tier << 2));
         s.lastId = r.lastBaseAlleleId == kPrefixEmpty ? (int8_t) kMicroNoLastId : (int8_t) r.lastBaseAlleleId;
         s.nSync = 0;
         s.ext.idx = syncIdx[q];
@@ -1854,7 +1861,9 @@ int Engine::settle(PassCtx& pc, WideBatch& early) {
               const auto it = pc.rare.find(key(k, j));
               if (it != pc.rare.end() && it->second.hasPrefix) assumed = it->second.assumedPrefix;
             }
-            if (assumed != prefix) fix[k].push_back(std::make_pair(j, prefix));
+            // wrong only if the emptiness differs, or -- when the tie-break got as far as comparing allele ids -- the id does
+            const bool emptyDiffers = (assumed == kPrefixEmpty) != (prefix == kPrefixEmpty);
+            if (emptyDiffers || ((s.flags & 0x20) && assumed != prefix)) fix[k].push_back(std::make_pair(j, prefix));
           }
           if (s.lastId != (int8_t) kMicroNoLastId) prefix = s.lastId;
         }
@@ -2300,7 +2309,7 @@ int Engine::resultsCollect(PassCtx& pc) {
       const uint32_t v = in[j];
       if (riStatus(v) == RI_CLEAN) {
         rs[j].state = RS_MICRO_DONE;
-        rs[j].flags = (uint8_t) ((riFlags(v) & 1u) | 0x80u);   // bit 7: the region's results live on the device
+        rs[j].flags = (uint8_t) ((riFlags(v) & 1u) | ((riFlags(v) & 2u) ? 0x20u : 0u) | 0x80u);   // bit 7: the region's results live on the device
         rs[j].lastId = (int8_t) riLastId(v);
         rs[j].nSync = 0;
       } else {

@@ -78,7 +78,7 @@ class Engine {
     const int32_t* idx = nullptr;  // (start,end)-sorted position -> input index, nullptr = identity
   };
   struct RegRes {
-    uint8_t state, flags;     // RS_*, bit0 usedPrefix, bit1 finished (last region of the sequence)
+    uint8_t state, flags;     // RS_*, bit0 usedPrefix (emptiness), bit5 usedPrefix (allele id), bit1 finished (last region of the sequence), bits 2-4 tier, bit7 results on the device
     int8_t lastId;            // alleleId() of the last baseline variant included in the region, -128 = none
     uint8_t nSync;            // thread-per-region results: sync points relative to the region start position
     union {

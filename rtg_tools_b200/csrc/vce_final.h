@@ -181,7 +181,7 @@ VCE_HD void scatterOne(const ScatterArgs& a, int q) {
   }
   for (int i = 0; i < g.bCount; ++i) a.dec[1][g.bFirst + i] = dec[a.kv + i];
   const int ns = rec[MR_NSYNC];
-  a.regInfo[r] = riPack(RI_CLEAN, rec[MR_FLAGS] & 1u, (int) (int8_t) rec[MR_LASTID]);
+  a.regInfo[r] = riPack(RI_CLEAN, rec[MR_FLAGS] & 3u, (int) (int8_t) rec[MR_LASTID]);
   a.regCnt[r] = ns;
   const uint8_t* pk = a.packets + (size_t) a.offsets[q] * 4;
   a.regBase[r] = (int32_t) ((uint32_t) pk[MP_WINSTART] | ((uint32_t) pk[MP_WINSTART + 1] << 8) | ((uint32_t) pk[MP_WINSTART + 2] << 16) |

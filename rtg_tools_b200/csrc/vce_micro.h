@@ -57,7 +57,7 @@ constexpr int kMicroNoAllele = 0xff;
 
 // result status
 enum : uint8_t { kMicroPending = 0, kMicroClean = 1, kMicroFallback = 2 };
-// result record (bytes): status, flags (bit0 usedPrefix), nSync, lastBaseAlleleId (-128 = none), iterations (u16),
+// result record (bytes): status, flags (bit0 a tie-break looked at the prefix's emptiness, bit1 at its allele id), nSync, lastBaseAlleleId (-128 = none), iterations (u16),
 // maxFrontier, pad, sync[SMAX] (relative), decision[2*KV] (calls then baseline: 0 untouched, 1 excluded, 2+k orientation k),
 // weightNum[KV], weightDen[KV] (calls)
 enum { MR_STATUS = 0, MR_FLAGS = 1, MR_NSYNC = 2, MR_LASTID = 3, MR_ITERS = 4, MR_MAXF = 6, MR_SYNC = 8 };
@@ -330,7 +330,7 @@ struct MicroSearch {
     if (cfg.preference == 0) {  // MaxSumBoth.java:43-82
       const int fs = fc + fb, ss = sc + sb;
       if (fs == ss) {
-        if (fb == 0 || sb == 0) usedPrefix = 1;
+        if (fb == 0 || sb == 0) usedPrefix |= 1;   // whether ANY baseline variant was included before the region matters
         int fd = f[pathOff() + PT_BSINCE] - f[pathOff() + PT_CSINCE];
         int sd = s[pathOff() + PT_BSINCE] - s[pathOff() + PT_CSINCE];
         fd = fd < 0 ? -fd : fd;
@@ -338,6 +338,7 @@ struct MicroSearch {
         if (fd != sd) return fd < sd;
         const int syncDelta = lastSync(f) - lastSync(s);
         if (syncDelta != 0) return syncDelta > 0;
+        if ((fb == 0) != (sb == 0)) usedPrefix |= 2;   // ... and here its allele id does
         const int fid = fb > 0 ? f[sideOff(1) + SD_LASTID] : 0;
         const int sid = sb > 0 ? s[sideOff(1) + SD_LASTID] : 0;
         return fid < sid;
@@ -624,7 +625,7 @@ struct MicroSearch {
   VCE_HD void writeResult(int status, int slot, uint8_t* out) const {
     for (int i = 0; i < T::RES_BYTES; ++i) out[i] = 0;
     out[MR_STATUS] = (uint8_t) status;
-    out[MR_FLAGS] = (uint8_t) (usedPrefix ? 1 : 0);
+    out[MR_FLAGS] = (uint8_t) (usedPrefix & 3);
     const int it = totalIters > 0xffff ? 0xffff : totalIters;
     out[MR_ITERS] = (uint8_t) (it & 0xff);
     out[MR_ITERS + 1] = (uint8_t) (it >> 8);

@@ -383,7 +383,7 @@ struct RegionSearch {
     if (cfg.preference == 0) {  // MaxSumBoth.java:43-82
       const int fs = fc + fb, ss = sc + sb;
       if (fs == ss) {
-        if (fb == 0 || sb == 0) usedPrefix = 1;
+        if (fb == 0 || sb == 0) usedPrefix |= 1;   // bit0: the prefix's emptiness matters, bit1: its allele id does
         const bool fiNonNull = prefixNonEmpty || fb > 0;
         const bool siNonNull = prefixNonEmpty || sb > 0;
         if (fiNonNull && siNonNull) {
@@ -394,6 +394,7 @@ struct RegionSearch {
           if (fd != sd) return fd < sd;
           const int syncDelta = lastSync(f) - lastSync(s);
           if (syncDelta != 0) return syncDelta > 0;
+          if ((fb == 0) != (sb == 0)) usedPrefix |= 2;
           const int fid = fb > 0 ? f[L.sideBase(1) + SD_LASTID] : R.prefixAlleleId;
           const int sid = sb > 0 ? s[L.sideBase(1) + SD_LASTID] : R.prefixAlleleId;
           return fid < sid;
