@@ -229,6 +229,8 @@ def main():
     ap.add_argument("--pair", type=int, default=None, help="N=1 only: evaluate the sample pair that rank PAIR of a weak-scaling run would get (diagnostics)")
     ap.add_argument("--no-register", action="store_true",
                     help="do not make the reference sequences resident on the device (vce_template_register): windows gathered on the host per call")
+    ap.add_argument("--no-pin", action="store_true",
+                    help="do not page-lock the caller's input arrays (vce_host_register): the engine stages them through its own pinned slabs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roc", action="store_true")
     args = ap.parse_args()
@@ -305,6 +307,8 @@ def main():
     t_reg = time.perf_counter()
     registered = 0 if args.no_register else eng.register_templates(seqs)
     t_reg = time.perf_counter() - t_reg
+    # the caller's input arrays are page-locked once, as the bench contract asks (inputs copied from pinned host memory)
+    pinned_bytes = 0 if args.no_pin else eng.host_register(seqs)
     packed = capi.Library.pack(cfg, seqs)
     res = packed[3]
     for _ in range(max(1, min(args.warmup, 3))):
@@ -462,7 +466,7 @@ def main():
         "e2e": {"value": total_variants / (e2e_ms * 1e-3), "unit": "variants/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": sub_stats["h2d_bytes"], "d2h_bytes_per_step": sub_stats["d2h_bytes"],
                 "gpu_launches_per_step": sub_stats["launches"],
-                "reference_resident_in_hbm": bool(registered), "reference_register_ms_once": t_reg * 1e3 if registered else None},
+                "input_bytes_page_locked_by_caller": int(pinned_bytes), "reference_resident_in_hbm": bool(registered), "reference_register_ms_once": t_reg * 1e3 if registered else None},
         "gpu_launches": int(total_launches),
         "clocks": clocks,
         "roofline": roofline,

@@ -203,6 +203,14 @@ const char* vce_version(void);
  * caller's variant arrays are uploaded whole and every search window is cut out of HBM, instead of being gathered from
  * template_bases on the host.  Results are identical either way.  The caller must keep the bytes unchanged while registered.
  */
+/*
+ * Optional: page-lock a block of the caller's memory (cudaHostRegister).  Input arrays of vce_submit that lie inside a
+ * registered block are copied to the device straight from where they are -- no staging copy on the host.  Meant for buffers
+ * the host keeps and refills across calls (JNI: direct ByteBuffers).  Unregister before freeing the memory.
+ */
+int vce_host_register(const void* p, uint64_t bytes);
+int vce_host_unregister(const void* p);
+
 int vce_template_register(const uint8_t* bases, int32_t len);
 int vce_template_unregister(const uint8_t* bases);
 

@@ -146,6 +146,7 @@ void vce_shutdown(void) {
   g_devices.clear();
   vce::rocRelease();
   vce::templateRegistryRemove(-1, nullptr);
+  vce::pinnedRegistryRemove(nullptr);
   g_device = -1;
 }
 
@@ -171,6 +172,22 @@ int vce_template_register(const uint8_t* bases, int32_t len) {
     const int rc = vce::templateRegistryAdd(d, bases, len, packed.data(), packed.size(), nmask.data(), nmask.size(), err);
     if (rc) return fail(rc, err);
   }
+  return VCE_OK;
+}
+
+int vce_host_register(const void* p, uint64_t bytes) {
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_device < 0) return fail(VCE_ERR_NOT_INITIALISED, "call vce_init first");
+  }
+  std::string err;
+  const int rc = vce::pinnedRegistryAdd(p, (size_t) bytes, err);
+  if (rc) return fail(rc, err);
+  return VCE_OK;
+}
+
+int vce_host_unregister(const void* p) {
+  vce::pinnedRegistryRemove(p);
   return VCE_OK;
 }
 

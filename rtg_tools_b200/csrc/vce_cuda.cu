@@ -1580,6 +1580,41 @@ class CudaBackend : public Backend {
     return VCE_OK;
   }
 
+  bool hostPinned(const void* p, size_t bytes) const override { return pinnedRegistryCovers(p, bytes); }
+  int residentAlloc(size_t bytes, void** dev, int* lane) override {
+    CUDA_TRY(cudaSetDevice(device_));
+    std::lock_guard<std::mutex> lk(mMu_);
+    *dev = devAlloc(bytes + 16);
+    *lane = mNextLane_;
+    mNextLane_ = (mNextLane_ + 1) % kMicroLanes;
+    if (!*dev) { setErr("out of device memory for the resident inputs"); return VCE_ERR_CUDA; }
+    return VCE_OK;
+  }
+  int residentCopy(void* dst, const void* src, size_t bytes, int lane) override {
+    if (bytes == 0) return VCE_OK;
+    CUDA_TRY(cudaSetDevice(device_));
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, mStream_[lane]));
+    std::lock_guard<std::mutex> lk(mMu_);
+    stats.h2dBytes += (int64_t) bytes;
+    return VCE_OK;
+  }
+  int residentMark(int lane, int* eventId) override {
+    CUDA_TRY(cudaSetDevice(device_));
+    cudaEvent_t ev = nullptr;
+    {
+      std::lock_guard<std::mutex> lk(mMu_);
+      if ((int) mEvents_.size() <= mNextEvent_) {
+        cudaEvent_t e;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { setErr("cudaEventCreate failed"); return VCE_ERR_CUDA; }
+        mEvents_.push_back(e);
+      }
+      *eventId = mNextEvent_;
+      ev = mEvents_[mNextEvent_++];
+    }
+    CUDA_TRY(cudaEventRecord(ev, mStream_[lane]));
+    return VCE_OK;
+  }
+
   // One search launch over the MicroB packets of every chunk built since the last flush.
   int microBuildFlush(const MicroConfig& mc) override {
     CUDA_TRY(cudaSetDevice(device_));
@@ -1703,6 +1738,41 @@ class CudaBackend : public Backend {
   std::mutex errMu_;
   std::string err_;
 };
+
+// ---- caller memory page-locked through vce_host_register
+namespace {
+struct PinnedRange { const uint8_t* p; size_t bytes; };
+std::mutex g_pinMu;
+std::vector<PinnedRange> g_pinned;
+}  // namespace
+bool pinnedRegistryCovers(const void* p, size_t bytes) {
+  if (bytes == 0) return true;
+  if (p == nullptr) return false;
+  const uint8_t* q = static_cast<const uint8_t*>(p);
+  std::lock_guard<std::mutex> lk(g_pinMu);
+  for (const PinnedRange& r : g_pinned) if (q >= r.p && q + bytes <= r.p + r.bytes) return true;
+  return false;
+}
+int pinnedRegistryAdd(const void* p, size_t bytes, std::string& err) {
+  if (p == nullptr || bytes == 0) return VCE_OK;
+  if (pinnedRegistryCovers(p, bytes)) return VCE_OK;
+  const cudaError_t e = cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterPortable);
+  if (e != cudaSuccess) { cudaGetLastError(); err = std::string("cudaHostRegister failed: ") + cudaGetErrorString(e); return VCE_ERR_CUDA; }
+  std::lock_guard<std::mutex> lk(g_pinMu);
+  g_pinned.push_back(PinnedRange{static_cast<const uint8_t*>(p), bytes});
+  return VCE_OK;
+}
+void pinnedRegistryRemove(const void* p) {
+  std::lock_guard<std::mutex> lk(g_pinMu);
+  for (size_t i = 0; i < g_pinned.size();) {
+    if (p == nullptr || g_pinned[i].p == p) {
+      cudaHostUnregister(const_cast<uint8_t*>(g_pinned[i].p));
+      g_pinned.erase(g_pinned.begin() + (long) i);
+    } else {
+      ++i;
+    }
+  }
+}
 
 // ---- registered templates: device-resident 2-bit copies, per device, keyed by the caller's pointer + length
 namespace {

@@ -25,6 +25,11 @@ int templateRegistryAdd(int device, const uint8_t* bases, int32_t len, const uin
                         size_t mwords, std::string& err);
 void templateRegistryRemove(int device, const uint8_t* bases);   // device < 0: every device; bases == nullptr: every template
 
+// Caller memory page-locked through vce_host_register (one registry for the process; the ranges are portable across devices).
+bool pinnedRegistryCovers(const void* p, size_t bytes);
+int pinnedRegistryAdd(const void* p, size_t bytes, std::string& err);
+void pinnedRegistryRemove(const void* p);   // nullptr: everything
+
 struct RocTiming { double h2dMs = 0, kernelMs = 0; int launches = 0; };
 class WorkerPool;
 // `pool`: host threads that stage the caller's (pageable) arrays into page-locked memory in parallel; nullptr = the caller's thread

@@ -1091,25 +1091,58 @@ int Engine::residentSetup(PassCtx& pc) {
       oVe = place(n * 4 + 4); oGt = place(n * (size_t) std::max(1, P) + 4); oAo = place((n + 1) * 4);
       oAs = place(nSl * 4 + 4); oAe = place(nSl * 4 + 4); oAn = place(nSl + 4); oNo = place((nSl + 1) * 4); oNt = place(nNt + 4);
     }
-    uint8_t* blk = arenaAlloc(at + 16);
-    if (!blk) { failed.store(VCE_ERR_CUDA); return; }
-    std::memcpy(blk + oVs, pc.vStart[side].data() + ss.first, n * 4);
-    if (in.phased) std::memcpy(blk + oPh, in.phased, n);
-    if (in.status_in) std::memcpy(blk + oSt, in.status_in, n);
-    if (full) {
-      std::memcpy(blk + oVe, pc.vEnd[side].data() + ss.first, n * 4);
-      if (P > 0) std::memcpy(blk + oGt, in.gt, n * (size_t) P);
-      std::memcpy(blk + oAo, in.allele_off, (n + 1) * 4);
-      std::memcpy(blk + oAs, in.allele_start, nSl * 4);
-      std::memcpy(blk + oAe, in.allele_end, nSl * 4);
-      std::memcpy(blk + oAn, in.allele_null, nSl);
-      std::memcpy(blk + oNo, in.allele_nt_off, (nSl + 1) * 4);
-      std::memcpy(blk + oNt, in.nt, nNt);
-    }
     void* dev = nullptr;
     int ev = -1;
-    const int r = be_->residentUpload(blk, at, &dev, &ev);
-    if (r) { failed.store(r); return; }
+    // page-locked caller arrays (vce_host_register) go up from where they are; only the locus bounds (computed here) are staged
+    const bool direct = (!in.phased || be_->hostPinned(in.phased, n)) && (!in.status_in || be_->hostPinned(in.status_in, n)) &&
+                        (!full || ((P == 0 || be_->hostPinned(in.gt, n * (size_t) P)) && be_->hostPinned(in.allele_off, (n + 1) * 4) &&
+                                   be_->hostPinned(in.allele_start, nSl * 4) && be_->hostPinned(in.allele_end, nSl * 4) &&
+                                   be_->hostPinned(in.allele_null, nSl) && be_->hostPinned(in.allele_nt_off, (nSl + 1) * 4) &&
+                                   be_->hostPinned(in.nt, nNt)));
+    if (direct) {
+      int lane = 0;
+      int r = be_->residentAlloc(at, &dev, &lane);
+      if (r) { failed.store(r); return; }
+      uint8_t* dd = static_cast<uint8_t*>(dev);
+      const size_t bBytes = n * 4;
+      uint8_t* bounds = arenaAlloc(2 * bBytes + 32);
+      if (!bounds) { failed.store(VCE_ERR_CUDA); return; }
+      std::memcpy(bounds, pc.vStart[side].data() + ss.first, bBytes);
+      r = be_->residentCopy(dd + oVs, bounds, bBytes, lane);
+      if (!r && in.phased) r = be_->residentCopy(dd + oPh, in.phased, n, lane);
+      if (!r && in.status_in) r = be_->residentCopy(dd + oSt, in.status_in, n, lane);
+      if (!r && full) {
+        std::memcpy(bounds + bBytes, pc.vEnd[side].data() + ss.first, bBytes);
+        r = be_->residentCopy(dd + oVe, bounds + bBytes, bBytes, lane);
+        if (!r && P > 0) r = be_->residentCopy(dd + oGt, in.gt, n * (size_t) P, lane);
+        if (!r) r = be_->residentCopy(dd + oAo, in.allele_off, (n + 1) * 4, lane);
+        if (!r) r = be_->residentCopy(dd + oAs, in.allele_start, nSl * 4, lane);
+        if (!r) r = be_->residentCopy(dd + oAe, in.allele_end, nSl * 4, lane);
+        if (!r) r = be_->residentCopy(dd + oAn, in.allele_null, nSl, lane);
+        if (!r) r = be_->residentCopy(dd + oNo, in.allele_nt_off, (nSl + 1) * 4, lane);
+        if (!r) r = be_->residentCopy(dd + oNt, in.nt, nNt, lane);
+      }
+      if (!r) r = be_->residentMark(lane, &ev);
+      if (r) { failed.store(r); return; }
+    } else {
+      uint8_t* blk = arenaAlloc(at + 16);
+      if (!blk) { failed.store(VCE_ERR_CUDA); return; }
+      std::memcpy(blk + oVs, pc.vStart[side].data() + ss.first, n * 4);
+      if (in.phased) std::memcpy(blk + oPh, in.phased, n);
+      if (in.status_in) std::memcpy(blk + oSt, in.status_in, n);
+      if (full) {
+        std::memcpy(blk + oVe, pc.vEnd[side].data() + ss.first, n * 4);
+        if (P > 0) std::memcpy(blk + oGt, in.gt, n * (size_t) P);
+        std::memcpy(blk + oAo, in.allele_off, (n + 1) * 4);
+        std::memcpy(blk + oAs, in.allele_start, nSl * 4);
+        std::memcpy(blk + oAe, in.allele_end, nSl * 4);
+        std::memcpy(blk + oAn, in.allele_null, nSl);
+        std::memcpy(blk + oNo, in.allele_nt_off, (nSl + 1) * 4);
+        std::memcpy(blk + oNt, in.nt, nNt);
+      }
+      const int r = be_->residentUpload(blk, at, &dev, &ev);
+      if (r) { failed.store(r); return; }
+    }
     const uint8_t* d = static_cast<const uint8_t*>(dev);
     ResidentSeq& rsq = resident_[k];
     rsq.fVStart[side] = reinterpret_cast<const int32_t*>(d + oVs);

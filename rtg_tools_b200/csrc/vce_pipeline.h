@@ -210,6 +210,13 @@ class Backend {
   // Asynchronous host -> device copy of one block of page-locked memory (from hostAlloc); *dev is valid right away for
   // pointer arithmetic, the data once event *eventId has passed (MicroBuildJob::waitEvents).
   virtual int residentUpload(const void* /*pinned*/, size_t /*bytes*/, void** /*dev*/, int* /*eventId*/) { return VCE_ERR_UNSUPPORTED; }
+  // Caller memory that was page-locked with vce_host_register goes to the device without a staging copy:
+  // hostPinned = the whole range lies inside a registered block; residentAlloc + residentCopy = one device block, filled by
+  // asynchronous copies straight from the caller's arrays (event as for residentUpload, recorded after the last copy of a lane).
+  virtual bool hostPinned(const void* /*p*/, size_t /*bytes*/) const { return false; }
+  virtual int residentAlloc(size_t /*bytes*/, void** /*dev*/, int* /*lane*/) { return VCE_ERR_UNSUPPORTED; }
+  virtual int residentCopy(void* /*dst*/, const void* /*src*/, size_t /*bytes*/, int /*lane*/) { return VCE_ERR_UNSUPPORTED; }
+  virtual int residentMark(int /*lane*/, int* /*eventId*/) { return VCE_ERR_UNSUPPORTED; }
   // The backend may hold the MicroB-shaped regions of the chunks back and search them in one launch: call this once every
   // chunk has been handed over (the MicroJob objects have to stay where they are until then).
   virtual int microBuildFlush(const MicroConfig&) { return 0; }

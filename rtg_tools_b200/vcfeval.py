@@ -128,6 +128,33 @@ class Engine:
             total += int(s.template.shape[0])
         return total
 
+    def host_register(self, seqs: List[capi.Sequence], min_bytes: int = 1 << 16) -> int:
+        """vce_host_register for the input arrays of `seqs` (arrays of at least min_bytes: small heap arrays share pages and
+        cannot be page-locked one by one).  The engine then copies them to the device without a staging copy.  Returns the
+        bytes page-locked; call host_unregister before the arrays are freed."""
+        lib = self.lib.lib
+        lib.vce_host_register.restype = C.c_int
+        lib.vce_host_register.argtypes = [C.c_void_p, C.c_uint64]
+        total = 0
+        self._pinned = getattr(self, "_pinned", [])
+        for s in seqs:
+            for side in (s.baseline, s.calls):
+                side.gt = np.ascontiguousarray(side.gt, np.int8)
+                for a in (side.phased, side.status_in, side.gt, side.allele_off, side.allele_start, side.allele_end, side.allele_null,
+                          side.allele_nt_off, side.nt):
+                    if a is not None and a.nbytes >= min_bytes and lib.vce_host_register(a.ctypes.data, a.nbytes) == 0:
+                        total += a.nbytes
+                        self._pinned.append(a)
+        return total
+
+    def host_unregister(self) -> None:
+        lib = self.lib.lib
+        lib.vce_host_unregister.restype = C.c_int
+        lib.vce_host_unregister.argtypes = [C.c_void_p]
+        for a in getattr(self, "_pinned", []):
+            lib.vce_host_unregister(a.ctypes.data)
+        self._pinned = []
+
     def unregister_templates(self, seqs: List[capi.Sequence]) -> None:
         lib = self.lib.lib
         lib.vce_template_unregister.restype = C.c_int

@@ -110,6 +110,21 @@ def test_cuda_device_resident_pipeline(engine, oracle, registered):
             engine.unregister_templates(seqs)
 
 
+def test_cuda_page_locked_inputs(engine, oracle):
+    """vce_host_register: the caller's arrays go to the device straight from where they are (no staging copy)."""
+    seqs = synth.make_pair(30_000_000, n_chrom=3)
+    engine.register_templates(seqs)
+    assert engine.host_register(seqs) > 0
+    try:
+        want = oracle.submit(CONFIGS["default"], seqs, threads=3)
+        for _ in range(2):
+            compare_results(want, engine.submit(CONFIGS["default"], seqs), seqs, what="page-locked inputs")
+    finally:
+        engine.host_unregister()
+        engine.unregister_templates(seqs)
+    compare_results(want, engine.submit(CONFIGS["default"], seqs), seqs, what="after unregistering")
+
+
 def test_cuda_device_results_equal_host_assembly(engine, oracle):
     """The same call with and without the device-resident result path (VCE_DEVICE_RESULTS is read per context)."""
     seqs = synth.make_pair(12_000_000, n_chrom=3)
