@@ -280,7 +280,9 @@ def main():
     # (several pollers on one box contend in the driver: the more ranks, the slower each polls)
     sampler = ClockSampler(local_rank, 250 if world == 1 else 125 * world)
     sampler.start()
-    for _ in range(max(args.warmup, 3)):
+    # (the dense-cluster workload takes minutes per step: it honours --warmup as given, the others warm up at least 3 times)
+    n_warm = args.warmup if args.workload == "c3" else max(args.warmup, 3)
+    for _ in range(n_warm):
         job.run()
     barrier()
     dev_ms = 0.0
@@ -311,7 +313,7 @@ def main():
     pinned_bytes = 0 if args.no_pin else eng.host_register(seqs)
     packed = capi.Library.pack(cfg, seqs)
     res = packed[3]
-    for _ in range(max(1, min(args.warmup, 3))):
+    for _ in range(min(args.warmup, 3) if args.workload == "c3" else max(1, min(args.warmup, 3))):
         eng.lib.submit_packed(packed)
     barrier()
     t0 = time.perf_counter()
@@ -454,12 +456,12 @@ def main():
     value = total_variants / (ms_per_step * 1e-3)
     out = {
         "metric": "vcfeval variants evaluated/sec", "value": value, "unit": "variants/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak",
+        "warmup": n_warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": {"workload": "%s: %s" % (args.workload, desc), "engine_config": args.config, "variants_per_step": int(total_variants),
                    "sync_regions_per_step": int(total_regions), "sequences_per_rank": len(seqs),
                    "l2": "inputs larger than L2 (per-variant arrays + reference windows > 126 MB)" if nv > 2_000_000 else "inputs smaller than L2 (small workload)",
-                   "sharding": "none (1 GPU)" if world == 1 else ("one sample pair per rank" if args.scaling == "weak" else "LPT over chromosomes"),
+                   "sharding": "none (1 GPU)" if world == 1 else ("one sample pair per rank" if args.scaling == "weak" else "one sample pair, its sequences LPT-sharded over the ranks by variant count"),
                    "host_threads_per_rank": int(os.environ.get("VCE_THREADS", "0"))},
         "sync_regions_per_s": total_regions / (ms_per_step * 1e-3),
         "wall_ms_per_step": wall_per_step,

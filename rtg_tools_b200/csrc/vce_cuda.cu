@@ -1487,6 +1487,8 @@ class CudaBackend : public Backend {
     CUDA_TRY(fCall0_.ensure(nFlatMax + nS + 2));
     const size_t nBlocksMax = nFlatMax / kPhaseBlock + nS + 2;
     CUDA_TRY(fBlockEnd_.ensure(nBlocksMax * 16)); CUDA_TRY(fBlockCnt_.ensure(nBlocksMax * 16 * 3)); CUDA_TRY(fSeqBlock_.ensure(nS + 2));
+    const size_t nSuperMax = nBlocksMax / kPhaseGroup + nS + 2;
+    CUDA_TRY(fSuperEnd_.ensure(nSuperMax * 16)); CUDA_TRY(fSuperCnt_.ensure(nSuperMax * 16 * 3)); CUDA_TRY(fSeqSuper_.ensure(nS + 2));
     if (rs_.rocTuples) CUDA_TRY(fRoc_.ensure(nC * 3 + 3));
     CUDA_TRY(ints_.ensure(16));
     FinalArrays A;
@@ -1499,6 +1501,7 @@ class CudaBackend : public Backend {
     A.outCalls = fOutC_.p; A.outBase = fOutB_.p; A.counters = fCounters_.p; A.rocTuples = rs_.rocTuples ? fRoc_.p : nullptr;
     A.keptScan = fKept_.p; A.mStart = fMStart_.p; A.mFlags = fMFlags_.p; A.mSeq = fMSeq_.p; A.mVal = fMVal_.p; A.mMin = fMMin_.p;
     A.regBaseSum = fBaseSum_.p; A.regCall0 = fCall0_.p; A.blockEnd = fBlockEnd_.p; A.blockCnt = fBlockCnt_.p; A.seqBlockFirst = fSeqBlock_.p;
+    A.superEnd = fSuperEnd_.p; A.superCnt = fSuperCnt_.p; A.seqSuperFirst = fSeqSuper_.p;
     finalOps_.st = st;
     finalOps_.dCount = ints_.p + 14;
     finalOps_.launches = 0;
@@ -1534,7 +1537,8 @@ class CudaBackend : public Backend {
   ResultsSetup rs_;
   std::vector<FinalSeq> fsHost_;
   cudaEvent_t rBeginEv_ = nullptr;
-  DevBuf<uint8_t> rDec_[2], rRel_, pDec_, fOutC_, fOutB_, fMFlags_, fBaseSum_, fBlockEnd_;
+  DevBuf<uint8_t> rDec_[2], rRel_, pDec_, fOutC_, fOutB_, fMFlags_, fBaseSum_, fBlockEnd_, fSuperEnd_;
+  DevBuf<int32_t> fSuperCnt_, fSeqSuper_;
   DevBuf<double> rWeight_, pW_, fRoc_;
   DevBuf<uint32_t> rInfo_, pInfo_;
   DevBuf<int32_t> rCnt_, rBase_, pRegIdx_, pSyncOff_, pSyncCnt_, pPayOff_, pWOff_, pSync_, fRegOff_, fPos_, fSeqSync_, fKept_, fMStart_, fMSeq_,

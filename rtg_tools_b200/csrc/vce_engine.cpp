@@ -526,6 +526,9 @@ void Engine::planChunks(PassCtx& pc) {
   if (per <= 0) {
     per = (int) (total / ((size_t) pool_->threads() * 6 + 1));
     per = std::max(8192, std::min(131072, per));
+    // resident inputs + device-resident results: a chunk costs the host a list of regions, nothing else -- large chunks give
+    // the search kernel full waves (one launch per chunk) and the host few launches
+    if (devRes_ && pc.pass == 0) per = std::max(per, 1 << 18);
   }
   for (int k = 0; k < nSeq_; ++k) {
     const int n = (int) pc.rr[k].size();

@@ -46,6 +46,7 @@ VCE_HD int riLastId(uint32_t v) { return (int) (int8_t) ((v >> 16) & 0xffu); }
 constexpr int kFinalRel = 8;          // relative sync points kept per thread-per-region result
 constexpr int64_t kSyncBias = 16;     // sync positions are >= -1: biased so that the sequence id can sit above them
 constexpr int kPhaseBlock = 32;       // sync regions per transducer block
+constexpr int kPhaseGroup = 64;       // blocks per super-block of the composition
 
 struct FinalSeq {   // one sequence of the pass; side 0 = calls, 1 = baseline
   const int32_t* vStart[2];     // [n] locus start, sequence-local index
@@ -92,6 +93,9 @@ struct FinalArrays {
   uint8_t* blockEnd;            // [blocks * 16] end state per start state
   int32_t* blockCnt;            // [blocks * 16 * 3] counts per start state
   int32_t* seqBlockFirst;       // [nSeq + 1]
+  uint8_t* superEnd;            // [super-blocks * 16]
+  int32_t* superCnt;            // [super-blocks * 16 * 3]
+  int32_t* seqSuperFirst;       // [nSeq + 1]
 };
 
 VCE_HD int finalSeqOfRegion(const FinalSeq* seq, int nSeq, int r) {
@@ -485,13 +489,50 @@ int finalPasses(Ops& ops, const FinalArrays& A) {
       a.blockCnt[((size_t) blk * 16 + t) * 3 + 2] = unp[t];
     }
   });
-  ops.parFor(nSeq, VCE_LAMBDA(int k) {
-    int state = 0;
-    int64_t mis = 0, cor = 0, unp = 0;
-    for (int blk = a.seqBlockFirst[k]; blk < a.seqBlockFirst[k + 1]; ++blk) {
+  // 3d. composition, two levels: kPhaseGroup blocks -> one super-block per start state (in parallel), then one short
+  // sequential walk per sequence (a chromosome has tens of thousands of blocks: walking them one by one is a chain of
+  // dependent loads that takes longer than every other pass together)
+  ops.parFor(nSeq + 1, VCE_LAMBDA(int k) {
+    int acc = 0;
+    for (int q = 0; q < k; ++q) {
+      const int nbk = a.seqBlockFirst[q + 1] - a.seqBlockFirst[q];
+      acc += (nbk + kPhaseGroup - 1) / kPhaseGroup;
+    }
+    a.seqSuperFirst[k] = acc;
+  });
+  const int nSuperMax = nBlocks / kPhaseGroup + nSeq + 1;
+  ops.parFor(nSuperMax * 16, VCE_LAMBDA(int i) {
+    const int sup = i >> 4, t = i & 15;
+    if (sup >= a.seqSuperFirst[nSeq]) return;
+    int k = 0;
+    {
+      int lo = 0, hi = nSeq - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (a.seqSuperFirst[mid] <= sup) lo = mid; else hi = mid - 1;
+      }
+      k = lo;
+    }
+    const int b0 = a.seqBlockFirst[k] + (sup - a.seqSuperFirst[k]) * kPhaseGroup;
+    const int b1 = b0 + kPhaseGroup < a.seqBlockFirst[k + 1] ? b0 + kPhaseGroup : a.seqBlockFirst[k + 1];
+    int state = t, mis = 0, cor = 0, unp = 0;
+    for (int blk = b0; blk < b1; ++blk) {
       const size_t e = (size_t) blk * 16 + (size_t) state;
       mis += a.blockCnt[e * 3]; cor += a.blockCnt[e * 3 + 1]; unp += a.blockCnt[e * 3 + 2];
       state = a.blockEnd[e];
+    }
+    a.superEnd[(size_t) sup * 16 + t] = (uint8_t) state;
+    a.superCnt[((size_t) sup * 16 + t) * 3] = mis;
+    a.superCnt[((size_t) sup * 16 + t) * 3 + 1] = cor;
+    a.superCnt[((size_t) sup * 16 + t) * 3 + 2] = unp;
+  });
+  ops.parFor(nSeq, VCE_LAMBDA(int k) {
+    int state = 0;
+    int64_t mis = 0, cor = 0, unp = 0;
+    for (int sup = a.seqSuperFirst[k]; sup < a.seqSuperFirst[k + 1]; ++sup) {
+      const size_t e = (size_t) sup * 16 + (size_t) state;
+      mis += a.superCnt[e * 3]; cor += a.superCnt[e * 3 + 1]; unp += a.superCnt[e * 3 + 2];
+      state = a.superEnd[e];
     }
     a.counters[(size_t) k * 8 + 5] = mis;
     a.counters[(size_t) k * 8 + 6] = cor;

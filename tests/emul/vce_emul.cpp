@@ -108,7 +108,8 @@ class EmulBackend : public Backend {
   bool resultsOn = true;
   ResultsSetup rsu_;
   std::vector<FinalSeq> fseq_;
-  std::vector<uint8_t> rDec_[2], rRel_, fOutC_, fOutB_, fMFlags_, fBaseSum_, fBlockEnd_;
+  std::vector<uint8_t> rDec_[2], rRel_, fOutC_, fOutB_, fMFlags_, fBaseSum_, fBlockEnd_, fSuperEnd_;
+  std::vector<int32_t> fSuperCnt_, fSeqSuper_;
   std::vector<double> rWeight_, fRoc_;
   std::vector<uint32_t> rInfo_;
   std::vector<int32_t> rCnt_, rBase_, fRegOff_, fPos_, fSeqSync_, fKept_, fMStart_, fMSeq_, fMVal_, fMMin_, fCall0_, fBlockCnt_, fSeqBlock_;
@@ -165,6 +166,8 @@ class EmulBackend : public Backend {
     fBaseSum_.assign(nFlatMax, 0); fCall0_.assign(nFlatMax + nS + 2, 0);
     const size_t nBlocksMax = nFlatMax / kPhaseBlock + nS + 2;
     fBlockEnd_.assign(nBlocksMax * 16, 0); fBlockCnt_.assign(nBlocksMax * 16 * 3, 0); fSeqBlock_.assign(nS + 2, 0);
+    const size_t nSuperMax = nBlocksMax / kPhaseGroup + nS + 2;
+    fSuperEnd_.assign(nSuperMax * 16, 0); fSuperCnt_.assign(nSuperMax * 16 * 3, 0); fSeqSuper_.assign(nS + 2, 0);
     fRoc_.assign(nC * 3 + 3, 0.0);
     FinalArrays A;
     A.nSeq = (int) nS; A.H = rsu_.H; A.kind[0] = rsu_.kind[0]; A.kind[1] = rsu_.kind[1];
@@ -177,6 +180,7 @@ class EmulBackend : public Backend {
     A.keptScan = fKept_.data(); A.mStart = fMStart_.data(); A.mFlags = fMFlags_.data(); A.mSeq = fMSeq_.data(); A.mVal = fMVal_.data();
     A.mMin = fMMin_.data(); A.regBaseSum = fBaseSum_.data(); A.regCall0 = fCall0_.data(); A.blockEnd = fBlockEnd_.data();
     A.blockCnt = fBlockCnt_.data(); A.seqBlockFirst = fSeqBlock_.data();
+    A.superEnd = fSuperEnd_.data(); A.superCnt = fSuperCnt_.data(); A.seqSuperFirst = fSeqSuper_.data();
     HostFinalOps ops;
     const int nSync = finalPasses(ops, A);
     out.outCalls = fOutC_.data(); out.outBase = fOutB_.data(); out.syncPos = fPos_.data(); out.seqSyncFirst = fSeqSync_.data();
