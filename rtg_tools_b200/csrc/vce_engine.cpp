@@ -1514,7 +1514,15 @@ int Engine::widePack(PassCtx& pc, const std::vector<std::pair<RegKey, int>>& ite
   if (itemsIn.empty()) return VCE_OK;
   StageTimer tmw;
   std::vector<std::pair<RegKey, int>> items(itemsIn);
-  std::stable_sort(items.begin(), items.end(), [](const std::pair<RegKey, int>& a, const std::pair<RegKey, int>& b) { return a.second < b.second; });
+  // by tier; within the arena tiers the regions with the most variants first: the kernels pull regions from a work
+  // queue, and the longest searches should not be the last ones to start
+  std::stable_sort(items.begin(), items.end(), [&pc](const std::pair<RegKey, int>& a, const std::pair<RegKey, int>& b) {
+    if (a.second != b.second) return a.second < b.second;
+    if (a.second < kTierMid) return false;
+    const RegRange& ga = pc.rr[a.first.seq][a.first.j];
+    const RegRange& gb = pc.rr[b.first.seq][b.first.j];
+    return ga.cCount + ga.bCount > gb.cCount + gb.bCount;
+  });
   const size_t n = items.size();
   wb.ids.resize(n);
   wb.tier.resize(n);
@@ -1597,8 +1605,8 @@ int Engine::widePack(PassCtx& pc, const std::vector<std::pair<RegKey, int>>& ite
       }
       if (lo == INT_MAX) lo = 0;
       const int ws = std::max(0, std::min(lo, d.startPos < 0 ? 0 : d.startPos) - 1);
-      // regions of the CTA tiers sit in repeats more often than not: a wider window from the start (there are few of them)
-      const int baseMargin = wb.tier[q] >= kTierMid ? std::max(opt_.margin, opt_.wideMargin) : opt_.margin;
+      // regions of the full-budget tiers sit in repeats more often than not: a wider window from the start (there are few of them)
+      const int baseMargin = wb.tier[q] >= kTierCta ? std::max(opt_.margin, opt_.wideMargin) : opt_.margin;
       long we = extra < 0 ? (long) d.tmplLen : sz[q].hi + baseMargin + extra;
       we = std::min(we, (long) d.tmplLen);
       if (we < ws) we = ws;
