@@ -131,14 +131,6 @@ int vce_init_devices(int device_count, const int* devices) {
     for (int q = 0; q < i; ++q) if (devices[q] == devices[i]) return fail(VCE_ERR_BAD_ARGUMENT, "device listed twice");
   }
   g_devices.assign(devices, devices + device_count);
-  // VCE_PIPELINES=k: k concurrent pipelines per device (each with 1/k of the host threads and its share of the sequences):
-  // one pipeline's host phases overlap another one's device phases
-  if (const char* e = std::getenv("VCE_PIPELINES")) {
-    const int k = std::max(1, std::min(8, std::atoi(e)));
-    std::vector<int> rep;
-    for (int i = 0; i < device_count; ++i) for (int q = 0; q < k; ++q) rep.push_back(devices[i]);
-    g_devices.swap(rep);
-  }
   g_device = devices[0];
   g_free.clear();      // (contexts are per device and per worker pool)
   g_devPools.clear();

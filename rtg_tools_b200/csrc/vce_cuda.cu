@@ -998,6 +998,7 @@ class CudaBackend : public Backend {
     CUDA_TRY(warnScratch_.ensure((size_t) std::max(1, maxWarps) * kWarnPerRegion));
     if (arenaWords > 0) CUDA_TRY(arena_.ensure(arenaWords));   // shared by the launches below (they run in stream order)
     CUDA_TRY(cudaEventRecord(ev0_, stream_));
+    tlMark(stream_, "wide batch: inputs resident, kernels next; regions", (int) nr);
     for (int tier = 0; tier <= kTierGeneral; ++tier) {
       if (blocksT[tier] == 0) continue;
       spT[tier].warnScratch = warnScratch_.p;
@@ -1019,6 +1020,7 @@ class CudaBackend : public Backend {
       }
     }
     CUDA_TRY(cudaEventRecord(ev1_, stream_));
+    tlMark(stream_, "wide batch: kernels done; regions", (int) nr);
     return VCE_OK;
   }
 
@@ -1305,6 +1307,7 @@ class CudaBackend : public Backend {
         CUDA_TRY(cudaStreamWaitEvent(st, ev, 0));
       }
     }
+    tlMark(st, "chunk: slab + sequence arrays resident, k_build next; lane", lane);
     int q0 = 0;
     for (int c = 0; c < 2; ++c) {
       MicroJob& j = *jobs[c];
@@ -1356,8 +1359,10 @@ class CudaBackend : public Backend {
           CUDA_TRY(cudaEventRecord(built, st));
           continue;
         }
+        tlMark(st, "chunk: packets built, k_micro<MicroA> next; lane", lane);
         microLaunch(mp, c, st);
         CUDA_TRY(cudaGetLastError());
+        tlMark(st, "chunk: k_micro<MicroA> done; regions", j.n);
         if (b.scatter) scatterLaunch(j, bp.regs, reinterpret_cast<const int32_t*>(base + b.regIdx) + q0, st);
         else CUDA_TRY(cudaMemcpyAsync(j.results, j.dResults, (size_t) j.n * j.resBytes, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(j.evHandle), st));
@@ -1508,7 +1513,9 @@ class CudaBackend : public Backend {
     finalOps_.err = cudaSuccess;
     // (the offsets array is scanned in place over nReg + 1 entries: the last one has to be defined)
     CUDA_TRY(cudaMemsetAsync(fRegOff_.p + nR, 0, sizeof(int32_t), st));
+    tlMark(st, "final passes next");
     const int nSync = finalPasses(finalOps_, A);
+    tlMark(st, "final passes done");
     if (finalOps_.err != cudaSuccess) {
       char b[256];
       snprintf(b, sizeof(b), "final passes failed: %s", cudaGetErrorString(finalOps_.err));
@@ -1528,11 +1535,41 @@ class CudaBackend : public Backend {
       if (nC) CUDA_TRY(cudaMemcpyAsync(hRoc_.p, fRoc_.p, nC * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
       stats.d2hBytes += (int64_t) (nC * 3 * sizeof(double));
     }
+    tlMark(st, "results copied back");
     CUDA_TRY(cudaStreamSynchronize(st));
+    tlDump();
     stats.d2hBytes += (int64_t) (nC * 16 + nB * 8 + (size_t) nSync * 4 + (nS + 1) * 4 + nS * 64);
     out.outCalls = hOutC_.p; out.outBase = hOutB_.p; out.syncPos = hPos_.p; out.seqSyncFirst = hSeqSync_.p;
     out.counters = hCounters_.p; out.rocTuples = rs_.rocTuples ? hRoc_.p : nullptr; out.nSync = nSync;
     return VCE_OK;
+  }
+  // ---- VCE_TIMELINE=1: when each stream reached the marked points of one vce_submit (diagnostics; the events are
+  // created per mark and destroyed by the dump)
+  struct TlMark { cudaEvent_t ev; const char* what; int a; };
+  std::vector<TlMark> tl_;
+  std::mutex tlMu_;
+  bool tlOn_ = std::getenv("VCE_TIMELINE") != nullptr;
+  void tlMark(cudaStream_t st, const char* what, int a = 0) {
+    if (!tlOn_) return;
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    std::lock_guard<std::mutex> lk(tlMu_);
+    tl_.push_back(TlMark{e, what, a});
+  }
+  void tlDump() {
+    if (!tlOn_) return;
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(tlMu_);
+    std::vector<std::pair<float, size_t>> at;
+    for (size_t i = 0; i < tl_.size(); ++i) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, tl_[0].ev, tl_[i].ev) == cudaSuccess) at.push_back(std::make_pair(ms, i));
+    }
+    std::sort(at.begin(), at.end());
+    for (const auto& q : at) fprintf(stderr, "[vce timeline] %8.3f ms  %s %d\n", q.first, tl_[q.second].what, tl_[q.second].a);
+    for (TlMark& m : tl_) cudaEventDestroy(m.ev);
+    tl_.clear();
   }
   ResultsSetup rs_;
   std::vector<FinalSeq> fsHost_;
@@ -1578,8 +1615,10 @@ class CudaBackend : public Backend {
       stats.h2dBytes += (int64_t) bytes;
     }
     if (!d) { setErr("out of device memory for the resident inputs"); return VCE_ERR_CUDA; }
+    tlMark(mStream_[lane], "sequence arrays: copy next; lane", lane);
     CUDA_TRY(cudaMemcpyAsync(d, pinned, bytes, cudaMemcpyHostToDevice, mStream_[lane]));
     CUDA_TRY(cudaEventRecord(ev, mStream_[lane]));
+    tlMark(mStream_[lane], "sequence arrays: resident; MB", (int) (bytes >> 20));
     *dev = d;
     return VCE_OK;
   }
@@ -1616,6 +1655,7 @@ class CudaBackend : public Backend {
       ev = mEvents_[mNextEvent_++];
     }
     CUDA_TRY(cudaEventRecord(ev, mStream_[lane]));
+    tlMark(mStream_[lane], "sequence arrays (page-locked caller memory): resident; lane", lane);
     return VCE_OK;
   }
 
@@ -1648,8 +1688,10 @@ class CudaBackend : public Backend {
     mp.total = total;
     mp.refill = microRefill_;
     mp.cfg = mc;
+    tlMark(st, "all MicroB packets built, k_micro<MicroB> next; regions", total);
     microLaunch(mp, 1, st);
     CUDA_TRY(cudaGetLastError());
+    tlMark(st, "k_micro<MicroB> done");
     for (const PendingB& pb : pend) {
       MicroJob& j = *pb.job;
       if (pb.scatter) scatterLaunch(j, pb.regs, pb.regIdx, st);

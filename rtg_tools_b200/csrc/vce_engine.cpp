@@ -336,7 +336,10 @@ int Engine::setupPass1() {
 // Splits calls [i, ie) and baseline [j, je) (pass-wide indices, merged by start, calls first on ties) into runs
 // separated by a gap; `maxEnd` carries the largest variant end seen before the slice (LONG_MIN = nothing).
 // *continues is set when the first run of the slice is not separated from what came before.
-void Engine::splitSlice(const PassCtx& pc, int i, int ie, int j, int je, long maxEnd, std::vector<RegRange>& out, bool* continues) const {
+// `near` (optional): one flag per region, set when the next region of the slice starts less than denseGap bases after this
+// region's largest variant end (the last region of a slice has none).
+void Engine::splitSlice(const PassCtx& pc, int i, int ie, int j, int je, long maxEnd, std::vector<RegRange>& out, bool* continues,
+                        std::vector<uint8_t>* near) const {
   const int32_t* cs = pc.vStart[0].data();
   const int32_t* ce = pc.vEnd[0].data();
   const int32_t* bs = pc.vStart[1].data();
@@ -346,13 +349,17 @@ void Engine::splitSlice(const PassCtx& pc, int i, int ie, int j, int je, long ma
   do {
     RegRange g{i, 0, j, 0};
     bool any = false;
+    uint8_t nearNext = 0;
     if (!firstRun) maxEnd = LONG_MIN;  // a new run starts after a gap
     while (i < ie || j < je) {
       const bool takeC = j >= je || (i < ie && cs[i] <= bs[j]);
       const int s = takeC ? cs[i] : bs[j];
       const int e = takeC ? ce[i] : bee[j];
       if (maxEnd != LONG_MIN && (long) s >= maxEnd + gap) {
-        if (any) break;
+        if (any) {
+          nearNext = (long) s - maxEnd < (long) opt_.denseGap ? 1 : 0;
+          break;
+        }
         maxEnd = LONG_MIN;  // the slice itself starts with a gap: its first run is a fresh region
       } else if (!any && firstRun && maxEnd != LONG_MIN && continues) {
         *continues = true;
@@ -364,11 +371,13 @@ void Engine::splitSlice(const PassCtx& pc, int i, int ie, int j, int je, long ma
     g.cCount = i - g.cFirst;
     g.bCount = j - g.bFirst;
     out.push_back(g);
+    if (near) near->push_back(nearNext);
     firstRun = false;
   } while (i < ie || j < je);
 }
 
 void Engine::splitAll(PassCtx& pc) {
+  StageTimer ts;
   ensureSize(pc.rr, (size_t) nSeq_);
   ensureSize(pc.rs, (size_t) nSeq_);
   ensureSize(pc.rcls, (size_t) nSeq_);
@@ -410,6 +419,7 @@ void Engine::splitAll(PassCtx& pc) {
   segFirst[nSeq_] = (int) segs.size();
   if (splitOut_.size() < segs.size()) splitOut_.resize(segs.size());
   for (size_t t = 0; t < segs.size(); ++t) { segs[t].outp = &splitOut_[t].v; splitOut_[t].v.clear(); }
+  ts.lap("  split: segment table");
   // phase 1: largest variant end per segment
   pool_->parallelFor((int) segs.size(), [&](int t, int) {
     Seg& sg = segs[t];
@@ -427,85 +437,92 @@ void Engine::splitAll(PassCtx& pc) {
       carry = std::max(carry, segs[t].maxEndLocal);
     }
   }
+  ts.lap("  split: largest ends");
   // phase 2: split every segment with the carried maximum end
+  // Dense clusters (several variants per side a few bases apart, typically in a tandem repeat) rarely come back in sync
+  // at a gap of a few bases: their pieces would SPILL into each other one merge and one full re-run at a time.
+  // Neighbours closer than denseGap are joined up front when the chain they form is crowded.  Any coarser split is exact
+  // (SURVEY.md A.13); sparse genomes have almost no such regions, so this costs them nothing.  Chains are looked for
+  // within a segment (a chain across a segment boundary simply stays apart, as it would with a smaller denseGap).
   pool_->parallelFor((int) segs.size(), [&](int t, int) {
     Seg& sg = segs[t];
     sg.outp->reserve((size_t) std::max(sg.ie - sg.i, sg.je - sg.j) + 16);
     const bool firstOfSeq = t == segFirst[sg.seq];
-    splitSlice(pc, sg.i, sg.ie, sg.j, sg.je, sg.carry, *sg.outp, firstOfSeq ? nullptr : &sg.continues);
-  });
-  // phase 3: stitch per sequence
-  pool_->parallelFor(nSeq_, [&](int k, int) {
-    std::vector<RegRange>& out = pc.rr[k];
-    out.clear();
-    if (!pc.shortCircuit[k]) {
-      size_t total = 0;
-      for (int t = segFirst[k]; t < segFirst[k + 1]; ++t) total += segs[t].outp->size();
-      out.reserve(total + 1);
-      for (int t = segFirst[k]; t < segFirst[k + 1]; ++t) {
-        const Seg& sg = segs[t];
-        const std::vector<RegRange>& so = *sg.outp;
-        size_t from = 0;
-        if (sg.continues && !out.empty() && !so.empty()) {
-          out.back().cCount += so[0].cCount;
-          out.back().bCount += so[0].bCount;
-          from = 1;
+    std::vector<uint8_t>& near = splitOut_[(size_t) t].near;
+    near.clear();
+    const bool dense = opt_.denseGap > opt_.gap;
+    splitSlice(pc, sg.i, sg.ie, sg.j, sg.je, sg.carry, *sg.outp, firstOfSeq ? nullptr : &sg.continues, dense ? &near : nullptr);
+    std::vector<RegRange>& out = *sg.outp;
+    if (dense && out.size() > 1) {
+      // chains of regions whose gaps stay below denseGap (the splitter noted them: a region ends at its largest variant
+      // end, the next one starts at its first variant); a chain becomes ONE region when it is crowded as a whole
+      size_t j = 0, w = 0;   // in place: the write index never passes the read index
+      const size_t nOut = out.size();
+      while (j < nOut) {
+        if (!near[j]) { out[w++] = out[j++]; continue; }
+        size_t e = j + 1;
+        long nc = out[j].cCount, nb = out[j].bCount;
+        while (e < nOut && near[e - 1]) {
+          nc += out[e].cCount;
+          nb += out[e].bCount;
+          ++e;
         }
-        out.insert(out.end(), so.begin() + (long) from, so.end());
-      }
-      // Dense clusters (several variants per side a few bases apart, typically in a tandem repeat) rarely come back in
-      // sync at a gap of a few bases: their pieces would SPILL into each other one merge and one full re-run at a time.
-      // Neighbours closer than denseGap are joined up front when one of them is already crowded.  Any coarser split is
-      // exact; sparse genomes have almost no such regions, so this costs them nothing.
-      if (opt_.denseGap > opt_.gap && out.size() > 1) {
-        const int32_t* cs = pc.vStart[0].data();
-        const int32_t* ce = pc.vEnd[0].data();
-        const int32_t* bs = pc.vStart[1].data();
-        const int32_t* bee = pc.vEnd[1].data();
-        auto crowded = [&](const RegRange& g) { return g.cCount >= opt_.denseCount || g.bCount >= opt_.denseCount; };
-        auto maxEndOf = [&](const RegRange& g) {
-          long m = LONG_MIN;
-          for (int v = g.cFirst; v < g.cFirst + g.cCount; ++v) m = std::max(m, (long) ce[v]);
-          for (int v = g.bFirst; v < g.bFirst + g.bCount; ++v) m = std::max(m, (long) bee[v]);
-          return m;
-        };
-        auto firstStartOf = [&](const RegRange& g) {
-          long m = LONG_MAX;
-          if (g.cCount > 0) m = std::min(m, (long) cs[g.cFirst]);
-          if (g.bCount > 0) m = std::min(m, (long) bs[g.bFirst]);
-          return m;
-        };
-        // chains of regions whose gaps stay below denseGap; a chain becomes ONE region when it is crowded as a whole
-        size_t j = 0, w = 0;   // in place: the write index never passes the read index
-        const size_t nOut = out.size();
-        while (j < nOut) {
-          size_t e = j + 1;
-          long curEnd = maxEndOf(out[j]);
-          long nc = out[j].cCount, nb = out[j].bCount;
-          while (e < nOut && firstStartOf(out[e]) - curEnd < (long) opt_.denseGap) {
-            curEnd = std::max(curEnd, maxEndOf(out[e]));
-            nc += out[e].cCount;
-            nb += out[e].bCount;
-            ++e;
-          }
-          if (e - j > 1 && (nc >= opt_.denseCount || nb >= opt_.denseCount)) {
-            RegRange g = out[j];
-            g.cCount = (int32_t) nc;
-            g.bCount = (int32_t) nb;
-            out[w++] = g;
-          } else {
-            for (size_t q = j; q < e; ++q) out[w++] = out[q];
-          }
-          j = e;
+        if (e - j > 1 && (nc >= opt_.denseCount || nb >= opt_.denseCount)) {
+          RegRange g = out[j];
+          g.cCount = (int32_t) nc;
+          g.bCount = (int32_t) nb;
+          out[w++] = g;
+        } else {
+          for (size_t q = j; q < e; ++q) out[w++] = out[q];
         }
-        out.resize(w);
-        (void) crowded;
+        j = e;
       }
+      out.resize(w);
     }
-    pc.rs[k].resize(out.size());
-    pc.rcls[k].assign(out.size(), 0);
-    if (!out.empty()) std::memset(pc.rs[k].data(), 0, out.size() * sizeof(RegRes));
   });
+  ts.lap("  split: segments");
+  // phase 3: stitch.  Where every segment's regions land in its sequence's table (a segment whose first region continues
+  // the previous segment's last one gives that region's variants to it), then all segments copy side by side.
+  struct Join { int seq; size_t at; int32_t c, b; };
+  std::vector<size_t> segAt(segs.size(), 0), segFrom(segs.size(), 0);
+  std::vector<Join> joins;
+  std::vector<size_t> seqTotal((size_t) nSeq_, 0);
+  for (int k = 0; k < nSeq_; ++k) {
+    size_t n = 0;
+    for (int t = segFirst[k]; t < segFirst[k + 1]; ++t) {
+      const std::vector<RegRange>& so = *segs[t].outp;
+      size_t from = 0;
+      if (segs[t].continues && n > 0 && !so.empty()) {
+        joins.push_back(Join{k, n - 1, so[0].cCount, so[0].bCount});
+        from = 1;
+      }
+      segAt[(size_t) t] = n;
+      segFrom[(size_t) t] = from;
+      n += so.size() - from;
+    }
+    seqTotal[(size_t) k] = n;
+  }
+  pool_->parallelFor(nSeq_, [&](int k, int) {   // (the tables keep their capacity: growing is the rare case)
+    const size_t n = pc.shortCircuit[k] ? 0 : seqTotal[(size_t) k];
+    pc.rr[k].resize(n);
+    pc.rs[k].resize(n);
+    pc.rcls[k].resize(n);
+  });
+  pool_->parallelFor((int) segs.size(), [&](int t, int) {
+    const Seg& sg = segs[t];
+    const std::vector<RegRange>& so = *sg.outp;
+    const size_t from = segFrom[(size_t) t], cnt = so.size() - from, at = segAt[(size_t) t];
+    if (cnt == 0) return;
+    std::memcpy(pc.rr[sg.seq].data() + at, so.data() + from, cnt * sizeof(RegRange));
+    std::memset(static_cast<void*>(pc.rs[sg.seq].data() + at), 0, cnt * sizeof(RegRes));
+    std::memset(pc.rcls[sg.seq].data() + at, 0, cnt);
+  });
+  for (const Join& jn : joins) {
+    RegRange& g = pc.rr[jn.seq][jn.at];
+    g.cCount += jn.c;
+    g.bCount += jn.b;
+  }
+  ts.lap("  split: stitch + dense chains");
 }
 
 int Engine::regionStartPos(const PassCtx& pc, int k, int j) const {
@@ -1319,19 +1336,29 @@ int Engine::runChunks(PassCtx& pc) {
   // split (per sequence), plan, build + upload + start
   configurePass(pc);
   splitAll(pc);
+  StageTimer ts;
   // regions that cannot go through the thread-per-region kernel are known from their shape alone: they start right
   // away in the warp-per-region kernels, concurrently with the packet pipeline
   {
-    std::vector<std::vector<std::pair<RegKey, int>>> per(nSeq_);
-    pool_->parallelFor(nSeq_, [&](int k, int) {
-      const std::vector<RegRange>& rr = pc.rr[k];
-      const int n = (int) rr.size();
-      for (int j = 0; j < n; ++j) {
+    struct Blk { int k, j0, j1; };
+    std::vector<Blk> blks;
+    const int perBlk = 1 << 15;
+    for (int k = 0; k < nSeq_; ++k) {
+      const int n = (int) pc.rr[k].size();
+      for (int j0 = 0; j0 < n; j0 += perBlk) blks.push_back(Blk{k, j0, std::min(n, j0 + perBlk)});
+    }
+    std::vector<std::vector<std::pair<RegKey, int>>> per(blks.size());
+    pool_->parallelFor((int) blks.size(), [&](int t, int) {
+      const Blk& bl = blks[(size_t) t];
+      const int k = bl.k;
+      const RegRange* rr = pc.rr[k].data();
+      const int n = (int) pc.rr[k].size();
+      for (int j = bl.j0; j < bl.j1; ++j) {
         const RegRange& g = rr[j];
         // four or more variants on one side mostly outgrow the packet kernel's frontier: start them in the warp tiers
         const bool shape = g.cCount >= MicroB::KV || g.bCount >= MicroB::KV || j == 0 || j == n - 1;
         if (shape || !pc.microOk) {
-          per[k].push_back(std::make_pair(RegKey{k, j}, startTier(pc, g)));
+          per[(size_t) t].push_back(std::make_pair(RegKey{k, j}, startTier(pc, g)));
           pc.rcls[k][j] = kClsEarly;
           pc.rs[k][j].state = RS_EARLY;
         }
@@ -1339,9 +1366,11 @@ int Engine::runChunks(PassCtx& pc) {
     });
     pc.earlyItems.clear();
     pc.earlyBatch = WideBatch();
-    for (int k = 0; k < nSeq_; ++k) pc.earlyItems.insert(pc.earlyItems.end(), per[k].begin(), per[k].end());
+    for (size_t t = 0; t < blks.size(); ++t) pc.earlyItems.insert(pc.earlyItems.end(), per[t].begin(), per[t].end());
   }
+  ts.lap("  split: early regions");
   planChunks(pc);
+  ts.lap("  split: chunk plan");
   return VCE_OK;
 }
 
@@ -1384,8 +1413,9 @@ int Engine::execute() {
       tm.lap("resident inputs: staging + upload");
       if ((rc = runChunks(pc))) return rc;
       tm.lap("split into regions");
-      if ((rc = wideStart(pc, pc.earlyItems, early))) return rc;
-      tm.lap("early warp-per-region batch");
+      // The packet kernels go first: the warp-per-region kernel of the mid tier keeps every SM's register file for itself until
+      // its longest regions are done (measured with VCE_TIMELINE: k_build sat behind it for 11 ms), whereas the packet kernels'
+      // blocks are short-lived -- and the early batch is packed while they run.
       if (devRes_ && p == 0 && (rc = resultsSetup(pc))) return rc;
       if (devRes_ && p == 0) {
         ResultsSetup rsu;
@@ -1420,6 +1450,10 @@ int Engine::execute() {
       if (tm.on) {
         std::fprintf(stderr, "[vce]   summed over workers: build %.1f ms, copy to page-locked %.1f ms, upload+launch calls %.1f ms\n",
                      g_tBuild.exchange(0) / 1e6, g_tCopy.exchange(0) / 1e6, g_tUpload.exchange(0) / 1e6);
+      }
+      if (!failed.load()) {
+        if ((rc = wideStart(pc, pc.earlyItems, early))) return rc;
+        tm.lap("early warp-per-region batch");
       }
     } else {
       if (executed_) {
@@ -1513,20 +1547,25 @@ int Engine::widePack(PassCtx& pc, const std::vector<std::pair<RegKey, int>>& ite
   wb = WideBatch();
   if (itemsIn.empty()) return VCE_OK;
   StageTimer tmw;
-  std::vector<std::pair<RegKey, int>> items(itemsIn);
   // by tier; within the arena tiers the regions with the most variants first: the kernels pull regions from a work
   // queue, and the longest searches should not be the last ones to start
-  std::stable_sort(items.begin(), items.end(), [&pc](const std::pair<RegKey, int>& a, const std::pair<RegKey, int>& b) {
-    if (a.second != b.second) return a.second < b.second;
-    if (a.second < kTierMid) return false;
-    const RegRange& ga = pc.rr[a.first.seq][a.first.j];
-    const RegRange& gb = pc.rr[b.first.seq][b.first.j];
-    return ga.cCount + ga.bCount > gb.cCount + gb.bCount;
+  struct Item { RegKey id; int32_t tier, weight; };
+  std::vector<Item> items(itemsIn.size());
+  pool_->parallelFor((int) ((itemsIn.size() + 1023) / 1024), [&](int t, int) {
+    for (size_t q = (size_t) t * 1024; q < std::min(itemsIn.size(), (size_t) (t + 1) * 1024); ++q) {
+      const RegKey id = itemsIn[q].first;
+      const RegRange& g = pc.rr[id.seq][id.j];
+      items[q] = Item{id, itemsIn[q].second, itemsIn[q].second >= kTierMid ? g.cCount + g.bCount : 0};
+    }
   });
+  std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) {
+    return a.tier != b.tier ? a.tier < b.tier : a.weight > b.weight;
+  });
+  tmw.lap("  wide: order");
   const size_t n = items.size();
   wb.ids.resize(n);
   wb.tier.resize(n);
-  for (size_t q = 0; q < n; ++q) { wb.ids[q] = items[q].first; wb.tier[q] = items[q].second; }
+  for (size_t q = 0; q < n; ++q) { wb.ids[q] = items[q].id; wb.tier[q] = items[q].tier; }
   PassData& pd = wb.pd;
   pd.pass = pc.pass;
   pd.H = pc.H;
@@ -1536,7 +1575,7 @@ int Engine::widePack(PassCtx& pc, const std::vector<std::pair<RegKey, int>>& ite
   wb.descs.assign(n, RegionDesc());
   wb.syncOff.assign(n, 0);
   // pass A (parallel): sizes per region
-  struct Sz { int32_t nv[2], nsl[2], nnt[2], lo, maxSl[2]; long hi; };
+  struct Sz { int32_t nv[2], nsl[2], nnt[2], lo, maxSl[2], nextStart[2]; long hi; };
   std::vector<Sz> sz(n);
   const int blockA = 256;
   pool_->parallelFor((int) ((n + blockA - 1) / blockA), [&](int t, int) {
@@ -1550,6 +1589,7 @@ int Engine::widePack(PassCtx& pc, const std::vector<std::pair<RegKey, int>>& ite
       for (int side = 0; side < 2; ++side) {
         const SideSeq& s = pc.ss[side][k];
         const vce_variants& in = *s.in;
+        z.nextStart[side] = first[side] + count[side] < s.first + s.n ? pc.vStart[side][first[side] + count[side]] : kNoNext;
         z.nv[side] = count[side];
         z.nsl[side] = 0;
         z.nnt[side] = 0;
@@ -1567,6 +1607,7 @@ int Engine::widePack(PassCtx& pc, const std::vector<std::pair<RegKey, int>>& ite
       }
     }
   });
+  tmw.lap("  wide: sizes");
   // serial prefix: offsets of every region in the compact arrays, windows, sync space
   std::vector<int32_t> vOff[2], sOff[2], nOff[2];
   int maxSl[2] = {2, 2};
@@ -1587,11 +1628,8 @@ int Engine::widePack(PassCtx& pc, const std::vector<std::pair<RegKey, int>>& ite
       d.tmplLen = seqs_[k].template_len;
       d.cFirst = vOff[0][q]; d.cCount = sz[q].nv[0]; d.bFirst = vOff[1][q]; d.bCount = sz[q].nv[1];
       d.cSlot0 = sOff[0][q]; d.cSlotN = sz[q].nsl[0]; d.bSlot0 = sOff[1][q]; d.bSlotN = sz[q].nsl[1];
-      const RegRange& g = pc.rr[k][j];
-      const SideSeq& C = pc.ss[0][k];
-      const SideSeq& B = pc.ss[1][k];
-      d.cNextStart = g.cFirst + g.cCount < C.first + C.n ? pc.vStart[0][g.cFirst + g.cCount] : kNoNext;
-      d.bNextStart = g.bFirst + g.bCount < B.first + B.n ? pc.vStart[1][g.bFirst + g.bCount] : kNoNext;
+      d.cNextStart = sz[q].nextStart[0];
+      d.bNextStart = sz[q].nextStart[1];
       int lo = sz[q].lo;
       d.startPos = j == 0 ? -1 : lo - 1;
       d.prefixAlleleId = j == 0 ? kPrefixEmpty : kDummyPrefix;
@@ -1639,6 +1677,7 @@ int Engine::widePack(PassCtx& pc, const std::vector<std::pair<RegKey, int>>& ite
   for (size_t q = 0; q < n; ++q) ++wb.tierFirst[wb.tier[q] + 1];
   for (int t = 1; t <= kTierGeneral + 1; ++t) wb.tierFirst[t] += wb.tierFirst[t - 1];
   wb.windows.assign(winBytes + 16, 0);
+  tmw.lap("  wide: offsets + tables");
   // pass B (parallel): fill
   pool_->parallelFor((int) ((n + blockA - 1) / blockA), [&](int t, int) {
     for (size_t q = (size_t) t * blockA; q < std::min(n, (size_t) (t + 1) * blockA); ++q) {
@@ -1823,6 +1862,7 @@ int Engine::wideFinish(PassCtx& pc, WideBatch& wb, std::vector<int>& statusOut) 
 // ones the thread-per-region kernel handed back, then SPILL -> merge with the following region and re-run, capacity ->
 // next tier, and finally the prefix-dependent tie-breaks (MaxSumBoth.java:55,76).
 int Engine::settle(PassCtx& pc, WideBatch& early) {
+  StageTimer tms;
   int rc;
   std::vector<std::pair<RegKey, int>> todo;   // (region, tier)
   {
@@ -1856,6 +1896,7 @@ int Engine::settle(PassCtx& pc, WideBatch& early) {
     if ((rc = wideFinish(pc, early, st))) return rc;
     for (size_t q = 0; q < early.ids.size(); ++q) all.push_back(std::make_pair(early.ids[q], st[q]));
   }
+  tms.lap("  settle: early batch collected");
   bool settled = false;
   for (int round = 0; round < 100000; ++round) {
     if (!retry.empty()) {
@@ -1886,6 +1927,7 @@ int Engine::settle(PassCtx& pc, WideBatch& early) {
         if (pc.rs[id.seq][id.j].state == RS_RESIDUAL) todo.push_back(std::make_pair(id, startTier(pc, pc.rr[id.seq][id.j])));
       }
       retry.clear();
+      tms.lap("  settle: merged regions through the packet kernel");
     }
     if (todo.empty() && all.empty()) {
       // prefix-dependent tie-breaks: re-run the first region per sequence whose assumption was wrong
@@ -1925,6 +1967,7 @@ int Engine::settle(PassCtx& pc, WideBatch& early) {
           ++be_->stats.prefixReruns;
         }
       }
+      tms.lap("  settle: prefix scan");
       if (todo.empty()) { settled = true; break; }
     }
     // one batch with every tier's regions, then inspect in sequence order so that chains of spilling regions merge
@@ -1998,6 +2041,7 @@ int Engine::settle(PassCtx& pc, WideBatch& early) {
       }
     }
     all.clear();
+    tms.lap("  settle: statuses");
   }
   if (!settled) { err_ = "regions left unsettled after the round limit"; return VCE_ERR_CAPACITY; }
   return VCE_OK;

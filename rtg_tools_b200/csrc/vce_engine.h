@@ -157,7 +157,8 @@ class Engine {
   int setupPass1();
   void computeBounds(PassCtx& pc);
   void resetPass(PassCtx& pc);
-  void splitSlice(const PassCtx& pc, int i, int ie, int j, int je, long maxEnd, std::vector<RegRange>& out, bool* continues) const;
+  void splitSlice(const PassCtx& pc, int i, int ie, int j, int je, long maxEnd, std::vector<RegRange>& out, bool* continues,
+                  std::vector<uint8_t>* near = nullptr) const;
   void splitAll(PassCtx& pc);
   void planChunks(PassCtx& pc);
   struct PacketSrc {          // what buildPacket reads, resolved once per chunk
@@ -230,7 +231,7 @@ class Engine {
   std::vector<size_t> arenaMarks_;
   struct alignas(64) SyncPart { int pass, seq, r0, r1; int err; std::vector<int32_t> v; };
   std::vector<SyncPart> syncParts_;               // sync points per block of regions (assembly)
-  struct alignas(64) SplitOut { std::vector<RegRange> v; };   // one cache line each: neighbours are filled concurrently
+  struct alignas(64) SplitOut { std::vector<RegRange> v; std::vector<uint8_t> near; };   // one cache line each: neighbours are filled concurrently
   std::vector<SplitOut> splitOut_;                // regions per segment of the parallel split
   std::vector<int> syncPartFirst_[2];             // [pass][seq] first part of the sequence
   std::vector<std::vector<int32_t>> seqSync_[2];   // [pass][seq] sync points (assembly)
