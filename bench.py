@@ -225,7 +225,8 @@ def main():
     ap.add_argument("--total-bp", type=float, default=None, help="override the genome size of the workload (testing)")
     ap.add_argument("--config", default="default", choices=["default", "squash", "twopass"],
                     help="engine configuration: default (diploid, single pass), squash (--squash-ploidy), twopass (ga4gh / annotate)")
-    ap.add_argument("--roc-calls", type=int, default=0, help="also time K4 alone on this many synthetic scored calls (BASELINE configs[4])")
+    ap.add_argument("--roc-calls", type=int, default=10_000_000,
+                    help="also time K4 alone on this many synthetic scored calls x 5 filters (BASELINE configs[4]: 10 M); 0 = skip")
     ap.add_argument("--pair", type=int, default=None, help="N=1 only: evaluate the sample pair that rank PAIR of a weak-scaling run would get (diagnostics)")
     ap.add_argument("--no-register", action="store_true",
                     help="do not make the reference sequences resident on the device (vce_template_register): windows gathered on the host per call")
@@ -426,7 +427,7 @@ def main():
             roc["parity"] = "bit-exact vs oracle"
 
     roc_heavy = None
-    if args.roc_calls > 0:  # BASELINE configs[4]: QUAL-like scores (40 % distinct at 3 dp), 5 filters, K4 alone
+    if args.roc_calls > 0 and not args.no_roc and rank == 0:  # BASELINE configs[4]: QUAL-like scores (40 % distinct at 3 dp), 5 filters, K4 alone
         rng = np.random.default_rng(5)
         nr = args.roc_calls
         score = np.round(rng.uniform(0, 100, nr), 3)
@@ -438,11 +439,18 @@ def main():
         mask = rng.integers(1, 32, nr).astype(np.uint32)
         eng.roc(score, tpw, fpw, raww, mask, 5)
         t0 = time.perf_counter()
-        rows5, _ = eng.roc(score, tpw, fpw, raww, mask, 5)
+        rows5, _ = eng.roc(score, tpw, fpw, raww, mask, 5, timed=True)
         dt = time.perf_counter() - t0
+        tmg = eng.lib.last_roc_timing or {}
         roc_heavy = {"scored_calls": nr, "filters": 5, "e2e_calls_per_s": nr / dt, "ms": dt * 1e3,
                      "algorithmic_bytes_per_call": ALG_BYTES_PER_ROC_CALL,
                      "e2e_GBps_algorithmic": ALG_BYTES_PER_ROC_CALL * nr / dt / 1e9}
+        if tmg.get("kernel_ms"):
+            # K4's own roofline: sort + bucket sums + scans of all five filters, CUDA events on the ROC stream
+            ach = ALG_BYTES_PER_ROC_CALL * nr / (tmg["kernel_ms"] * 1e-3) / 1e9
+            roc_heavy.update({"kernel_ms": tmg["kernel_ms"], "h2d_ms": tmg["h2d_ms"], "gpu_launches": tmg["launches"],
+                              "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                           "traffic": None, "peak_source": peak_src}})
         if not args.no_cpu_baseline and world == 1:
             orc = capi.Library(os.path.join(ROOT, "oracle", "liboracle.so"), prefix="oracle_")
             t0 = time.perf_counter()

@@ -292,6 +292,16 @@ class Library:
         self._roc = self._sym("roc" if prefix == "vce_" else "vce_roc")
         self._roc.restype = C.c_int
         self._roc.argtypes = [C.POINTER(CRocIn), C.POINTER(CRocOut)]
+        self._roc_timed = None
+        if prefix == "vce_":
+            try:
+                self._roc_timed = self._sym("roc_timed")
+                self._roc_timed.restype = C.c_int
+                self._roc_timed.argtypes = [C.POINTER(CRocIn), C.POINTER(CRocOut), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                            C.POINTER(C.c_int32)]
+            except AttributeError:
+                self._roc_timed = None
+        self.last_roc_timing = None
 
     def _sym(self, name):
         return getattr(self.lib, self.prefix + name)
@@ -373,8 +383,10 @@ class Library:
             return f(C.byref(ccfg), len(results), cseqs, cres, threads)
         return self._submit(C.byref(ccfg), len(results), cseqs, cres)
 
-    def roc(self, score, tp, fp, tp_raw, filter_mask=None, n_filters=1, ascending=False):
-        """Returns (rows per filter: list of (threshold, cum_tp, cum_fp, cum_tp_raw) arrays, no_score count)."""
+    def roc(self, score, tp, fp, tp_raw, filter_mask=None, n_filters=1, ascending=False, timed=False):
+        """Returns (rows per filter: list of (threshold, cum_tp, cum_fp, cum_tp_raw) arrays, no_score count).
+        timed=True (product library only) goes through vce_roc_timed and leaves {"h2d_ms", "kernel_ms", "launches"} (CUDA
+        events on the ROC stream) in `last_roc_timing`."""
         score = np.ascontiguousarray(score, np.float64)
         tp = np.ascontiguousarray(tp, np.float64)
         fp = np.ascontiguousarray(fp, np.float64)
@@ -406,7 +418,12 @@ class Library:
         cout.cum_fp = _ptr(cfp, _f64p)
         cout.cum_tp_raw = _ptr(craw, _f64p)
         cout.no_score = _ptr(no_score, _i64p)
-        rc = self._roc(C.byref(cin), C.byref(cout))
+        if timed and self._roc_timed is not None:
+            h2d, ker, nl = C.c_double(0), C.c_double(0), C.c_int32(0)
+            rc = self._roc_timed(C.byref(cin), C.byref(cout), C.byref(h2d), C.byref(ker), C.byref(nl))
+            self.last_roc_timing = {"h2d_ms": h2d.value, "kernel_ms": ker.value, "launches": int(nl.value)}
+        else:
+            rc = self._roc(C.byref(cin), C.byref(cout))
         if rc != 0:
             raise RuntimeError("%sroc failed: %s %s" % (self.prefix, ERR_NAMES.get(rc, rc), self.last_error()))
         rows = []

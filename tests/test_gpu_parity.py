@@ -231,6 +231,22 @@ def test_cuda_roc_matches_oracle(engine, oracle, n, asc):
     _roc_equal(engine.roc(score, tp, fp, raw, None, 1, asc), oracle.roc(score, tp, fp, raw, None, 1, asc))
 
 
+def test_cuda_roc_ten_million_calls_five_filters(engine, oracle):
+    """BASELINE.json configs[4] at its full size: 10 M scored calls (QUAL-like scores, 40 % distinct at three decimals, the
+    rest rounded to one), five filters, weights that include the non-dyadic 1/3 and 2/3 -- every row of every filter
+    bit-identical to RocContainer's ordered sums (RocContainer.java:204-318)."""
+    n = 10_000_000
+    rng = np.random.default_rng(5)
+    score = np.round(rng.uniform(0, 100, n), 3)
+    dup = rng.random(n) < 0.6
+    score[dup] = np.round(score[dup], 1)
+    tp = rng.choice([1.0, 0.5, 1.0 / 3, 2.0 / 3, 2.0, 0.0], n)
+    fp = (tp == 0).astype(np.float64)
+    raw = (tp > 0).astype(np.float64)
+    mask = rng.integers(1, 32, n).astype(np.uint32)
+    _roc_equal(engine.roc(score, tp, fp, raw, mask, 5), oracle.roc(score, tp, fp, raw, mask, 5))
+
+
 def test_cuda_roc_known_answer(engine):
     """RocContainerTest.java:45-85: accumulate + cumulative known answers."""
     score = np.array([0.1, 0.1, 0.2, 0.2, 0.1, 0.3])
