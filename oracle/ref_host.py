@@ -796,6 +796,9 @@ def run_vcfeval(engine, template_fa, baseline_vcf, calls_vcf, args, cfg_over=Non
     rr = RunResult()
     rr.params = p
     rr.cfg = cfg
+    rr.seq_names = [name for name, _ in seqs]
+    rr.brecs, rr.crecs = brecs, crecs
+    rr.bsample = bsample
     rr.sequences = []
     batch = []
     loaded = []
@@ -828,7 +831,7 @@ def run_vcfeval(engine, template_fa, baseline_vcf, calls_vcf, args, cfg_over=Non
     base_tp = 0
     call_outside = 0
     S = capi
-    annotate = p.output_mode in ("annotate", "combine")
+    annotate = p.output_mode in ("annotate", "combine", "ga4gh")
     for (bl, cl), r in zip(loaded, results):
         for i, v in enumerate(cl):
             st = int(r.calls.status[i])
@@ -931,3 +934,340 @@ def run_vcfeval(engine, template_fa, baseline_vcf, calls_vcf, args, cfg_over=Non
     rr.phasing_txt = "Correct phasings: %d\nIncorrect phasings: %d\nUnresolvable phasings: %d\n" % (
         rr.phasing[1], rr.phasing[0], rr.phasing[2])
     return rr
+
+
+# ------------------------------------------------------------------------------ combined output (--output-mode combine)
+def _join_gt(phased, gt):  # VcfUtils.joinGt :267-286
+    if not gt:
+        return "."
+    return ("|" if phased else "/").join("." if g < 0 else str(g) for g in gt)
+
+
+def _normalize_allele(a):  # VcfUtils.normalizeAllele :478-505 (nucleotide alleles to upper case)
+    return a.upper() if a and all(c in "acgtnACGTN" for c in a) else a
+
+
+def _gt_str(rec, sample):  # CombinedEvalSynchronizer.resetRecordFields :168-183 (VcfUtils.getValidGtStr, or missing without a sample)
+    if sample < 0:
+        return "."
+    v = rec.sample_field(sample, "GT")
+    return "." if v is None else v
+
+
+def _clean_alts(alts, gts):  # VcfAltCleaner.annotate :57-94
+    used = [False] * len(alts)
+    for gt in gts:
+        for a in split_gt(gt):
+            if 0 < a <= len(used):
+                used[a - 1] = True
+    if all(used):
+        return alts, gts
+    remap = [0] * (len(used) + 1)
+    out = []
+    for k, u in enumerate(used):
+        if u:
+            out.append(alts[k])
+            remap[k + 1] = len(out)
+    new_gts = []
+    for gt in gts:
+        sp = [remap[a] if 0 < a < len(remap) else a for a in split_gt(gt)]
+        new_gts.append(_join_gt("|" in gt, sp))
+    return out, new_gts
+
+
+def _call_info(item, info):  # WithInfoEvalSynchronizer.updateForCall :121-181 (item None = record without a variant)
+    if item is None:
+        info["CALL"] = "IGN"
+        return
+    _, cls, w, sync, st = item
+    if sync is not None:
+        sy = str(sync)
+        old = info.get("SYNC")
+        info["SYNC"] = sy if old is None or old == sy else old + "," + sy
+    if cls in ("TP", "FP_CA") and abs(w - 1.0) > 0.001:
+        info["CALL_WEIGHT"] = format(w, "#.3g")
+    info["CALL"] = cls
+    if cls == "FP" and st & capi.STATUS_ANY_MATCH:
+        info["CALL_ALTERNATE"] = None
+
+
+def _base_info(item, info):  # WithInfoEvalSynchronizer.updateForBaseline :183-226
+    if item is None:
+        info["BASE"] = "IGN"
+        return
+    _, cls, sync, st = item
+    if sync is not None:
+        sy = str(sync)
+        old = info.get("SYNC")
+        info["SYNC"] = sy if old is None or old == sy else sy + "," + old
+    info["BASE"] = cls
+    if cls == "FN" and st & capi.STATUS_ANY_MATCH:
+        info["BASE_ALTERNATE"] = None
+
+
+def format_combine(rr):
+    """Body lines of output.vcf as CombinedEvalSynchronizer writes them (E/CombinedEvalSynchronizer.java:104-166 over the
+    interleaving of E/InterleavingEvalSynchronizer.java:86-200): both record streams in (start, end) order, records with
+    the same span merged into one two-sample row (VcfRecordMerger.mergeRecordsWithSameRef), unused ALTs removed when both
+    sides are samples (VcfAltCleaner)."""
+    clean = rr.bsample >= 0 and rr.csample >= 0
+    known_b = {id(it[0]): it for it in rr.base_class}
+    known_c = {id(it[0]): it for it in rr.call_class}
+    lines = []
+
+    def emit(chrom, start, ref, alts, info, gts):
+        if clean:
+            alts, gts = _clean_alts(alts, gts)
+        inf = ";".join(k if v is None else "%s=%s" % (k, v) for k, v in info.items()) or "."
+        lines.append("\t".join([chrom, str(start + 1), ".", ref, ",".join(alts) if alts else ".", ".", ".", inf, "GT"] + gts))
+
+    for chrom in rr.seq_names:
+        bs = sort_refine([r for r in rr.brecs if r.chrom == chrom])
+        cs = sort_refine([r for r in rr.crecs if r.chrom == chrom])
+        i = j = 0
+        while i < len(bs) or j < len(cs):
+            b = bs[i] if i < len(bs) else None
+            c = cs[j] if j < len(cs) else None
+            if b is not None and c is not None:
+                order = (b.start > c.start) - (b.start < c.start) or (b.end > c.end) - (b.end < c.end)
+            else:
+                order = -1 if c is None else 1
+            info = {}
+            if order < 0:
+                _base_info(known_b.get(id(b)), info)
+                emit(chrom, b.start, b.ref, list(b.alts), info, [_gt_str(b, rr.bsample), "."])
+                i += 1
+            elif order > 0:
+                _call_info(known_c.get(id(c)), info)
+                emit(chrom, c.start, c.ref, list(c.alts), info, [".", _gt_str(c, rr.csample)])
+                j += 1
+            else:
+                _base_info(known_b.get(id(b)), info)
+                _call_info(known_c.get(id(c)), info)
+                # VcfRecordMerger.AlleleMap :128-160: union of the ALTs, allele codes remapped
+                ref = _normalize_allele(b.ref)
+                alts = []
+                gts = []
+                for rec, sample in ((b, rr.bsample), (c, rr.csample)):
+                    m = [0]
+                    for a in rec.alts:
+                        a = _normalize_allele(a)
+                        if a == ref:
+                            m.append(0)
+                        else:
+                            if a not in alts:
+                                alts.append(a)
+                            m.append(alts.index(a) + 1)
+                    g = _gt_str(rec, sample)
+                    gts.append(_join_gt("|" in g, [m[x] if x >= 0 else x for x in split_gt(g)]))
+                emit(chrom, b.start, ref, alts, info, gts)
+                i += 1
+                j += 1
+    return lines
+
+
+# ------------------------------------------------------------------------------ GA4GH intermediate output (--output-mode ga4gh)
+def _java_double(x):  # Double.toString for the values a score takes
+    if x == int(x) and abs(x) < 1e7:
+        return "%.1f" % x
+    r = repr(float(x))
+    if "e" in r:
+        m, e = r.split("e")
+        if "." not in m:
+            m += ".0"
+        return "%sE%d" % (m, int(e))
+    return r
+
+
+class _OutRec:
+    def __init__(self, chrom, start, ref, alts, filters):
+        self.chrom, self.start, self.ref, self.alts, self.filters = chrom, start, ref, alts, filters
+        self.end = start + len(ref)
+        self.bs = []
+        self.fmt = {"GT": [".", "."]}   # insertion-ordered like the LinkedHashMap of VcfRecord.java:104
+
+    def set(self, key, val, sample):  # VcfRecord.setFormatAndSample :530-541
+        self.fmt.setdefault(key, [".", "."])[sample] = val
+
+    def line(self):  # VcfRecord.toString :586-613, trailing missing sub-fields omitted (:658-680)
+        cols = []
+        for k in range(2):
+            vals = [v[k] for v in self.fmt.values()]
+            while len(vals) > 1 and vals[-1] == ".":
+                vals.pop()
+            cols.append(":".join(vals))
+        info = "BS=" + ",".join(self.bs) if self.bs else "."
+        return "\t".join([self.chrom, str(self.start + 1), ".", self.ref, ",".join(self.alts) if self.alts else ".", ".",
+                          ";".join(self.filters) if self.filters else ".", info, ":".join(self.fmt)] + cols)
+
+
+def format_ga4gh(rr, loose_distance=30):
+    """Body lines of output.vcf as Ga4ghEvalSynchronizer writes them (E/Ga4ghEvalSynchronizer.java:139-321) behind
+    Ga4ghLooseMatchFilter (E/Ga4ghLooseMatchFilter.java:68-150): TRUTH / QUERY columns with BD / BK / BI / QQ, BS = sync ids."""
+    T, Q = 0, 1
+    known_b = {id(it[0]): it for it in rr.base_class}
+    known_c = {id(it[0]): it for it in rr.call_class}
+    gt_of = {}
+    for bl, cl in rr.loaded:
+        for v in bl + cl:
+            gt_of[id(v["rec"])] = v["gt"]
+    S = capi
+
+    def multi(rec):  # isMultiAllelicCall :262-271
+        g = gt_of.get(id(rec))
+        return g is not None and len(g) == 2 and g[0] > 0 and g[1] > 0 and g[0] != g[1]
+
+    def set_sync(o, sync):  # :314-321
+        if sync is not None and (not o.bs or o.bs[-1] != str(sync)):
+            o.bs.append(str(sync))
+
+    def for_call(item, o, rec):  # updateForCall :218-260
+        if item is None:
+            o.set("BD", "N", Q)
+            return
+        _, cls, w, sync, st = item
+
+        def score():
+            x = score_of(rec, rr.params.score_field, rr.csample)
+            if x == x:
+                o.set("QQ", _java_double(x), Q)
+        if st & S.STATUS_SKIPPED:
+            o.set("BD", "N", Q)
+            o.set("BI", "too-hard", Q)
+            sync = None
+        elif st & S.STATUS_GT_MATCH:
+            score()
+            o.set("BD", "TP", Q)
+            o.set("BK", "gm", Q)
+        elif st & S.STATUS_ALLELE_MATCH:
+            score()
+            o.set("BD", "FP", Q)
+            o.set("BK", "am", Q)
+            if multi(rec):
+                o.set("BI", "multi", Q)
+        elif st & S.STATUS_OUTSIDE_EVAL:
+            o.set("BD", "N", Q)
+            o.set("BI", "non-confident", Q)
+            sync = None
+        else:
+            score()
+            o.set("BD", "FP", Q)
+            o.set("BK", ".", Q)
+        set_sync(o, sync)
+
+    def for_base(item, o, rec):  # updateForBaseline :273-305
+        if item is None:
+            o.set("BD", "N", T)
+            return
+        _, cls, sync, st = item
+        if st & S.STATUS_SKIPPED:
+            o.set("BD", "N", T)
+            o.set("BI", "too-hard", T)
+            sync = None
+        elif st & S.STATUS_OUTSIDE_EVAL:
+            o.set("BD", "N", T)
+            o.set("BI", "non-confident", T)
+            sync = None
+        elif st & S.STATUS_GT_MATCH:
+            o.set("BD", "TP", T)
+            o.set("BK", "gm", T)
+        elif st & S.STATUS_ALLELE_MATCH:
+            o.set("BD", "FN", T)
+            o.set("BK", "am", T)
+            if multi(rec):
+                o.set("BI", "multi", T)
+        else:
+            o.set("BD", "FN", T)
+            o.set("BK", ".", T)
+        set_sync(o, sync)
+
+    recs = []
+    for chrom in rr.seq_names:
+        bs = sort_refine([r for r in rr.brecs if r.chrom == chrom])
+        cs = sort_refine([r for r in rr.crecs if r.chrom == chrom])
+        i = j = 0
+        while i < len(bs) or j < len(cs):
+            b = bs[i] if i < len(bs) else None
+            c = cs[j] if j < len(cs) else None
+            if b is not None and c is not None:
+                order = (b.start > c.start) - (b.start < c.start) or (b.end > c.end) - (b.end < c.end)
+            else:
+                order = -1 if c is None else 1
+            if order < 0:
+                o = _OutRec(chrom, b.start, b.ref, list(b.alts), [])
+                o.fmt["GT"] = [_gt_str(b, rr.bsample), "."]
+                for_base(known_b.get(id(b)), o, b)
+                i += 1
+            elif order > 0:
+                o = _OutRec(chrom, c.start, c.ref, list(c.alts), list(c.filters))
+                o.fmt["GT"] = [".", _gt_str(c, rr.csample)]
+                for_call(known_c.get(id(c)), o, c)
+                j += 1
+            else:  # makeCombinedRecord :187-191: the query record merges first (field priority), columns stay TRUTH, QUERY
+                ref = _normalize_allele(c.ref)
+                alts = []
+                gts = {}
+                for rec, sample, col in ((c, rr.csample, Q), (b, rr.bsample, T)):
+                    m = [0]
+                    for a in rec.alts:
+                        a = _normalize_allele(a)
+                        if a == ref:
+                            m.append(0)
+                        else:
+                            if a not in alts:
+                                alts.append(a)
+                            m.append(alts.index(a) + 1)
+                    g = _gt_str(rec, sample)
+                    gts[col] = _join_gt("|" in g, [m[x] if x >= 0 else x for x in split_gt(g)])
+                o = _OutRec(chrom, c.start, ref, alts, list(c.filters))
+                o.fmt["GT"] = [gts[T], gts[Q]]
+                for_base(known_b.get(id(b)), o, b)
+                for_call(known_c.get(id(c)), o, c)
+                i += 1
+                j += 1
+            o.alts, o.fmt["GT"] = _clean_alts(o.alts, o.fmt["GT"])   # writeRecord :182-185
+            recs.append(o)
+
+    # ---- Ga4ghLooseMatchFilter: BK "." -> "lm" for FP / FN records with the other side's TP/FP/FN records nearby
+    out = []
+    if loose_distance < 0:
+        return [o.line() for o in recs]
+    buf, truth, query = [], [], []
+
+    def wants(o, col, dec):
+        return "BK" in o.fmt and "BD" in o.fmt and o.fmt["BD"][col] == dec and o.fmt["BK"][col] == "."
+
+    def flush_first():
+        o = buf.pop(0)
+        while truth and truth[0].end <= o.start:
+            truth.pop(0)
+        while query and query[0].end <= o.start:
+            query.pop(0)
+        if wants(o, Q, "FP") and truth and truth[0].start - loose_distance < o.end:
+            o.fmt["BK"][Q] = "lm"
+        if wants(o, T, "FN") and query and query[0].start - loose_distance < o.end:
+            o.fmt["BK"][T] = "lm"
+        out.append(o.line())
+
+    for o in recs:
+        if buf:
+            if buf[0].chrom != o.chrom:
+                while buf:
+                    flush_first()
+                del truth[:], query[:]
+            else:
+                while buf and buf[0].end < o.start - loose_distance:
+                    flush_first()
+        if wants(o, Q, "FP") and truth and o.start < truth[-1].end + loose_distance:
+            o.fmt["BK"][Q] = "lm"
+        if wants(o, T, "FN") and query and o.start < query[-1].end + loose_distance:
+            o.fmt["BK"][T] = "lm"
+        buf.append(o)
+        if "BD" in o.fmt:
+            if o.fmt["BD"][Q] in ("TP", "FP"):
+                query.append(o)
+            if o.fmt["BD"][T] in ("TP", "FN"):
+                truth.append(o)
+    while buf:
+        flush_first()
+    return out

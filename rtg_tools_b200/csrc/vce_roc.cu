@@ -131,48 +131,82 @@ __global__ void k_roc_bucket_sums(int nBuckets, int nFilters, const int* __restr
   nonEmpty[o] = cnt > 0 ? 1 : 0;
 }
 
-// One warp per filter: cumulative sums over the buckets in key order, rows compacted to non-empty buckets.
-__global__ void k_roc_chain(int nBuckets, const int* __restrict__ bucketStart, const unsigned int* __restrict__ idx,
+// One CTA per filter: cumulative sums over the buckets in key order, rows compacted to non-empty buckets.  The sums are a
+// left fold in bucket order (RocContainer.java:297-311 adds the points of one threshold after the other, FP64), so the
+// additions stay a dependent chain -- but nothing else does: a tile of bucket sums is staged into shared memory by the
+// whole block, three threads (one per quantity, in three different warps) fold it in place, and the row numbers
+// (prefix count of non-empty buckets), the threshold gather and the stores are done by all threads again.
+constexpr int kChainTile = 1024;
+constexpr int kChainThreads = 256;
+__global__ void __launch_bounds__(kChainThreads) k_roc_chain(int nBuckets, const int* __restrict__ bucketStart, const unsigned int* __restrict__ idx,
                             const double* __restrict__ score, const double* __restrict__ sTp, const double* __restrict__ sFp,
                             const double* __restrict__ sRaw, const int* __restrict__ nonEmpty, long long cap,
                             double* __restrict__ oThr, double* __restrict__ oTp, double* __restrict__ oFp, double* __restrict__ oRaw,
                             long long* __restrict__ nRows) {
+  __shared__ double sv[3][kChainTile];
+  __shared__ int sne[kChainTile];
+  __shared__ int warpCnt[kChainThreads / 32];
+  __shared__ double carry[3];
   const int f = blockIdx.x;
-  const int lane = threadIdx.x;
-  double ct = 0, cf = 0, cr = 0;   // new RocPoint<>() : zeros, RocContainer.java:297
-  long long row = 0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t fo = (size_t) f * nBuckets;
-  for (int base = 0; base < nBuckets; base += 32) {
-    const int b = base + lane;
-    double vt = 0, vf = 0, vr = 0;
-    int ne = 0;
-    if (b < nBuckets) {
-      ne = nonEmpty[fo + b];
-      vt = sTp[fo + b]; vf = sFp[fo + b]; vr = sRaw[fo + b];
+  if (tid < 3) carry[tid] = 0.0;   // new RocPoint<>() : zeros, RocContainer.java:297
+  long long row = 0;               // rows written so far (the same value in every thread)
+  __syncthreads();
+  for (int base = 0; base < nBuckets; base += kChainTile) {
+    const int cnt = min(kChainTile, nBuckets - base);
+    for (int j = tid; j < cnt; j += kChainThreads) {
+      const size_t o = fo + base + j;
+      sne[j] = nonEmpty[o];
+      sv[0][j] = sTp[o]; sv[1][j] = sFp[o]; sv[2][j] = sRaw[o];
     }
-    const unsigned m = __ballot_sync(0xffffffffu, ne);
-    double mt = 0, mf = 0, mr = 0;
-    // every lane replays the same dependent chain; lane j keeps the value after step j
+    __syncthreads();
+    if (lane == 0 && warp < 3) {
+      double* v = sv[warp];
+      double c = carry[warp];
+      int j = 0;
+      // an empty bucket holds +0.0 (k_roc_bucket_sums) and the running sum starts at +0.0, so it is never -0.0: adding
+      // the zero leaves every bit of it alone, and the chain is one DADD per bucket with nothing else on it
+      for (; j + 8 <= cnt; j += 8) {
+        double x[8];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const double xt = __shfl_sync(0xffffffffu, vt, j);
-      const double xf = __shfl_sync(0xffffffffu, vf, j);
-      const double xr = __shfl_sync(0xffffffffu, vr, j);
-      if ((m >> j) & 1u) { ct += xt; cf += xf; cr += xr; }
-      if (j == lane) { mt = ct; mf = cf; mr = cr; }
-    }
-    if (ne) {
-      const long long r = row + __popc(m & ((1u << lane) - 1u));
-      if (r < cap) {
-        const size_t o = (size_t) f * cap + r;
-        double s = score[idx[bucketStart[b]]];
-        if (isnan(s) || isinf(s)) s = nan("");
-        oThr[o] = s; oTp[o] = mt; oFp[o] = mf; oRaw[o] = mr;
+        for (int k = 0; k < 8; ++k) x[k] = v[j + k];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { c += x[k]; x[k] = c; }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[j + k] = x[k];
       }
+      for (; j < cnt; ++j) { c += v[j]; v[j] = c; }
+      carry[warp] = c;
     }
-    row += __popc(m);
+    __syncthreads();
+    for (int j0 = 0; j0 < cnt; j0 += kChainThreads) {
+      const int j = j0 + tid;
+      const int ne = j < cnt ? sne[j] : 0;
+      const unsigned m = __ballot_sync(0xffffffffu, ne);
+      if (lane == 0) warpCnt[warp] = __popc(m);
+      __syncthreads();
+      int before = 0, total = 0;
+#pragma unroll
+      for (int w = 0; w < kChainThreads / 32; ++w) {
+        const int c = warpCnt[w];
+        if (w < warp) before += c;
+        total += c;
+      }
+      if (ne) {
+        const long long r = row + before + __popc(m & ((1u << lane) - 1u));
+        if (r < cap) {
+          const size_t o = (size_t) f * cap + r;
+          double s = score[idx[bucketStart[base + j]]];
+          if (isnan(s) || isinf(s)) s = nan("");
+          oThr[o] = s; oTp[o] = sv[0][j]; oFp[o] = sv[1][j]; oRaw[o] = sv[2][j];
+        }
+      }
+      row += total;
+      __syncthreads();   // warpCnt is rewritten by the next round, the tile by the next pass
+    }
   }
-  if (lane == 0) nRows[f] = row;
+  if (tid == 0) nRows[f] = row;
 }
 
 #define ROC_TRY(expr)                                                                         \
@@ -367,7 +401,7 @@ int rocRun(int device, const vce_roc_in* in, vce_roc_out* out, std::string& err,
   ROC_TRY(alloc(fb * 8, (void**) &oRaw));
   dim3 g((nBuckets + tb - 1) / tb, nF);
   k_roc_bucket_sums<<<g, tb, 0, st>>>(nBuckets, nF, dStart, dIdx2, dTp, dFp, dRaw, dMask, sTp, sFp, sRaw, dNe);
-  k_roc_chain<<<nF, 32, 0, st>>>(nBuckets, dStart, dIdx2, dScore, sTp, sFp, sRaw, dNe, cap, oThr, oTp, oFp, oRaw, dRows);
+  k_roc_chain<<<nF, kChainThreads, 0, st>>>(nBuckets, dStart, dIdx2, dScore, sTp, sFp, sRaw, dNe, cap, oThr, oTp, oFp, oRaw, dRows);
   ROC_TRY(cudaGetLastError());
   ROC_TRY(cudaEventRecord(e2, st));
   std::vector<long long> rows(nF);

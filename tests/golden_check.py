@@ -89,7 +89,19 @@ def check_scenario(engine, sc, cfg_over=None):
                 want.append((_key(l), info.get(tag), info.get("SYNC"), info.get("CALL_WEIGHT")))
             assert got == want, "%s differs:\n got %s\nwant %s" % (fname, got, want)
             checked.append(fname)
-    if "summary.txt" in exp and p.output_mode == "split":
+    if p.output_mode == "combine" and "output.vcf" in exp:
+        got = ref_host.format_combine(rr)
+        want = _body(exp["output.vcf"])
+        assert got == want, "output.vcf (combine) differs:\n" + "\n".join(
+            "got  %s\nwant %s" % (g, w) for g, w in zip(got + [""] * len(want), want + [""] * len(got)) if g != w)
+        checked.append("output.vcf")
+    if p.output_mode == "ga4gh" and "output.vcf" in exp:
+        got = ref_host.format_ga4gh(rr)
+        want = _body(exp["output.vcf"])
+        assert got == want, "output.vcf (ga4gh) differs:\n" + "\n".join(
+            "got  %s\nwant %s" % (g, w) for g, w in zip(got + [""] * len(want), want + [""] * len(got)) if g != w)
+        checked.append("output.vcf")
+    if "summary.txt" in exp and p.output_mode in ("split", "combine"):
         assert rr.summary == exp["summary.txt"], "summary differs:\n%s\n%s" % (rr.summary, exp["summary.txt"])
         checked.append("summary.txt")
     if "phasing.txt" in exp:
