@@ -7,18 +7,25 @@ batch of synthetic input.
 
   value : whole-job variants/s with the batch already resident in HBM (staged job: vce_job_run), timed with CUDA
           events on the engine's stream, max over ranks
-  e2e   : the same metric through the reference-facing C-ABI call vce_submit() with HOST buffers: packing, H2D,
-          kernels, D2H and result assembly all inside the timed region
+  e2e   : the same metric through the reference-facing C-ABI call vce_submit() with HOST buffers: uploads, region
+          split, kernels, final passes, D2H and the expansion into the caller's arrays all inside the timed region.
+          Before the timed region the reference sequences are registered (vce_template_register: the load phase, which
+          BASELINE.md excludes from both arms) and the input arrays page-locked (vce_host_register: "pinned host memory",
+          as the contract asks); --no-register / --no-pin measure without either
   roofline : the dominant kernel (thread-per-region search), 48 algorithmic bytes per variant
   cpu_baseline : the CPU oracle (C++ restatement of the reference, "port": the reference is Java and the image
           has no JDK) on the host cores, one worker per sequence like the reference's SimpleThreadPool
+  roc_heavy : BASELINE configs[4], K4 alone on --roc-calls (default 10 M) synthetic scored calls x 5 filters: end to end,
+          kernel time (vce_roc_timed) with its own roofline at 72 algorithmic bytes per call, CPU oracle beside it
 
 `--impl reference` times that CPU path alone, on the same workload, as the reference arm.
+`--workload c3 --c3-clusters N` is BASELINE configs[2] (dense clusters at the default 50 000-path budget).
 
 Multi-GPU (torchrun, one rank per GPU): sequences are independent units (VcfEvalTask.java:131-135), so every rank
 evaluates its own shard with no data-path collective; the only exchange is the summary-count merge (NCCL
-all-reduce).  Default scaling is weak: rank r evaluates sample pair r of the cohort (same 24-chromosome genome
-layout, different sample seeds); `--scaling strong` shards ONE pair's chromosomes over the ranks by LPT.
+all-reduce) and the ROC tuple gather.  Default scaling is STRONG: ONE sample pair, its 24 chromosomes LPT-sharded over
+the ranks by variant count (the reference arm evaluates the same pair); `--scaling weak` gives rank r its own sample
+pair r of a cohort (same genome layout, different sample seeds).
 """
 import argparse
 import json

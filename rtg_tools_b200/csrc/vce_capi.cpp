@@ -35,6 +35,7 @@ std::vector<std::unique_ptr<Context>> g_free;
 std::unique_ptr<vce::WorkerPool> g_pool;
 // with several devices every device's engine gets its own share of the host cores (a WorkerPool runs one parallelFor at a time)
 std::vector<std::unique_ptr<vce::WorkerPool>> g_devPools;
+std::vector<int64_t> g_devLoad;   // variants queued per device by the one-sequence calls in flight (under g_mu)
 
 int fail(int code, const std::string& msg) {
   t_err = msg;
@@ -321,6 +322,31 @@ int vce_submit(const vce_config* cfg, int32_t n_seq, const vce_sequence* seqs, v
   {
     std::lock_guard<std::mutex> lk(g_mu);
     nDev = g_devices.size();
+  }
+  if (nDev > 1 && n_seq == 1) {
+    // one sequence per call (the reference's pool workers, VcfEvalTask.java:131-137): the device with the least work queued
+    const int64_t w = (int64_t) seqs[0].baseline.n + (int64_t) seqs[0].calls.n + 1;
+    size_t best = 0;
+    {
+      std::lock_guard<std::mutex> lk(g_mu);
+      if (g_devLoad.size() != nDev) g_devLoad.assign(nDev, 0);
+      for (size_t d = 1; d < nDev; ++d) if (g_devLoad[d] < g_devLoad[best]) best = d;
+      g_devLoad[best] += w;
+    }
+    std::vector<int32_t> idx(1, 0);
+    std::array<double, 6> st;
+    for (double& v : st) v = 0;
+    std::vector<int64_t> summary(8, 0);
+    std::string msg;
+    const int rc = submitOn((int) best, cfg, idx, seqs, results, st.data(), summary, msg);
+    {
+      std::lock_guard<std::mutex> lk(g_mu);
+      if (g_devLoad.size() == nDev) g_devLoad[best] -= w;
+    }
+    for (int i = 0; i < 6; ++i) t_submitStats[i] = st[(size_t) i];
+    t_summary = summary;
+    if (rc) return fail(rc, msg.empty() ? std::string("one or more sequences reported an error") : msg);
+    return VCE_OK;
   }
   if (nDev > 1 && n_seq > 1) {
     // Sequences are independent (VcfEvalTask.java:131-135): longest-processing-time greedy by variant count over the devices,

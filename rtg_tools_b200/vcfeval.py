@@ -81,9 +81,10 @@ class Job:
 
 
 class Engine:
-    """The CUDA vcfeval engine on one device."""
+    """The CUDA vcfeval engine on one device, or -- `devices=[...]` -- on several devices driven from this one process
+    (vce_init_devices: the sequences of every submit are spread over the devices by variant count)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, devices: Optional[List[int]] = None):
         if not os.path.exists(LIB_PATH):
             raise EngineUnavailable("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'`" % LIB_PATH)
         self.lib = capi.Library(LIB_PATH, prefix="vce_")
@@ -105,10 +106,19 @@ class Engine:
         lib.vce_job_stats_ex.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int32]
         lib.vce_submit_stats.restype = C.c_int
         lib.vce_submit_stats.argtypes = [C.POINTER(C.c_double), C.c_int32]
-        rc = lib.vce_init(device)
+        if devices is not None:
+            lib.vce_init_devices.restype = C.c_int
+            lib.vce_init_devices.argtypes = [C.c_int, C.POINTER(C.c_int)]
+            arr = (C.c_int * len(devices))(*devices)
+            rc = lib.vce_init_devices(len(devices), arr)
+            device = devices[0] if devices else 0
+        else:
+            rc = lib.vce_init(device)
         if rc != 0:
-            raise EngineUnavailable("vce_init(%d) failed: %s %s" % (device, capi.ERR_NAMES.get(rc, rc), self.lib.last_error()))
+            raise EngineUnavailable("vce_init(%s) failed: %s %s" % (devices if devices is not None else device,
+                                                                    capi.ERR_NAMES.get(rc, rc), self.lib.last_error()))
         self.device = device
+        self.devices = list(devices) if devices is not None else [device]
 
     def submit(self, cfg: capi.Config, seqs: List[capi.Sequence]) -> List[capi.SequenceResult]:
         return self.lib.submit(cfg, seqs)

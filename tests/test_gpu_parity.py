@@ -132,6 +132,18 @@ def test_cuda_device_results_equal_host_assembly(engine, oracle):
     compare_results(want, engine.submit(CONFIGS["default"], seqs), seqs, what="device results")
 
 
+def test_cuda_one_process_several_devices(engine, oracle):
+    """vce_init_devices: one process, every visible device, sequences spread by variant count (tests/multi_device_check.py,
+    in its own process because the device pool is process-wide).  Skipped on a one-GPU box."""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, os.path.join(here, "multi_device_check.py")], capture_output=True, text=True, timeout=1200)
+    if "SKIP:" in r.stdout:
+        pytest.skip(r.stdout.strip())
+    assert r.returncode == 0 and "OK:" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
 def test_cuda_genome_slice_all_modes(engine, oracle):
     """BASELINE.json configs[3] on a 10 % slice of the 24-chromosome genome: --squash-ploidy (haploid SQUASH_GT) and the
     two-pass mode of ga4gh / annotate / combine (diploid, then haploid allele matching on FN / FP)."""
