@@ -196,7 +196,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "vcfeval variants evaluated/sec", "value": v, "unit": "variants/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": workload_config(args, desc, nv_full, None),
+        "config": workload_config(args, desc, nv_full),
+        "sync_regions_per_step": int(regions),
         "cpu_baseline": {"value": v, "unit": "variants/s", "cores": threads, "kind": "port",
                          "sample": "%s (%d variants, %d sequences), %d worker threads of %d host cores" % (
                              sample, nv, len(seqs), threads, cores)},
@@ -213,10 +214,12 @@ def engine_config(name):
             "twopass": capi.Config(n_passes=2)}[name]
 
 
-def workload_config(args, desc, variants, regions):
-    """The `config` object: the same keys in both arms (the driver compares them)."""
+def workload_config(args, desc, variants):
+    """The `config` object: the same keys and values in both arms (the driver compares them)."""
     return {"workload": "%s: %s" % (args.workload, desc), "engine_config": args.config, "variants_per_step": int(variants),
-            "sync_regions_per_step": None if regions is None else int(regions)}
+            # timing rule: no L2 flush between steps -- the step's inputs are larger than the 126 MB L2 (or it is said otherwise)
+            "l2": ("inputs larger than L2 (per-variant arrays + reference windows > 126 MB)" if variants > 2_000_000
+                   else "inputs smaller than L2 (small workload)")}
 
 
 def main():
@@ -473,11 +476,11 @@ def main():
         "metric": "vcfeval variants evaluated/sec", "value": value, "unit": "variants/s", "n_gpus": world, "steps": args.steps,
         "warmup": n_warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": "%s: %s" % (args.workload, desc), "engine_config": args.config, "variants_per_step": int(total_variants),
-                   "sync_regions_per_step": int(total_regions), "sequences_per_rank": len(seqs),
-                   "l2": "inputs larger than L2 (per-variant arrays + reference windows > 126 MB)" if nv > 2_000_000 else "inputs smaller than L2 (small workload)",
-                   "sharding": "none (1 GPU)" if world == 1 else ("one sample pair per rank" if args.scaling == "weak" else "one sample pair, its sequences LPT-sharded over the ranks by variant count"),
-                   "host_threads_per_rank": int(os.environ.get("VCE_THREADS", "0"))},
+        "config": workload_config(args, desc, total_variants),
+        "sync_regions_per_step": int(total_regions),
+        "run": {"sequences_per_rank": len(seqs),
+                "sharding": "none (1 GPU)" if world == 1 else ("one sample pair per rank" if args.scaling == "weak" else "one sample pair, its sequences LPT-sharded over the ranks by variant count"),
+                "host_threads_per_rank": int(os.environ.get("VCE_THREADS", "0"))},
         "sync_regions_per_s": total_regions / (ms_per_step * 1e-3),
         "wall_ms_per_step": wall_per_step,
         "e2e": {"value": total_variants / (e2e_ms * 1e-3), "unit": "variants/s", "ms_per_step": e2e_ms,

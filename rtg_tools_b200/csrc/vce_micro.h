@@ -104,7 +104,10 @@ struct MicroTraits {
   static_assert(NSLOTS <= 32, "free list is one 32-bit mask");
 };
 
-typedef MicroTraits<1, 0, 3, 10> MicroA;   // one variant per side
+#ifndef VCE_MICROA_CAP
+#define VCE_MICROA_CAP 10
+#endif
+typedef MicroTraits<1, 0, 3, VCE_MICROA_CAP> MicroA;   // one variant per side
 typedef MicroTraits<4, 3, 6, 28> MicroB;   // up to four variants per side
 
 template <class T>

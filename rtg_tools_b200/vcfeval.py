@@ -18,7 +18,7 @@ import numpy as np
 from . import capi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libvce.so")
+LIB_PATH = os.environ.get("VCE_LIB") or os.path.join(_HERE, "csrc", "libvce.so")   # VCE_LIB: another build of the same sources (experiments)
 
 
 class EngineUnavailable(RuntimeError):
