@@ -217,9 +217,14 @@ def engine_config(name):
 def workload_config(args, desc, variants):
     """The `config` object: the same keys and values in both arms (the driver compares them)."""
     return {"workload": "%s: %s" % (args.workload, desc), "engine_config": args.config, "variants_per_step": int(variants),
-            # timing rule: no L2 flush between steps -- the step's inputs are larger than the 126 MB L2 (or it is said otherwise)
-            "l2": ("inputs larger than L2 (per-variant arrays + reference windows > 126 MB)" if variants > 2_000_000
-                   else "inputs smaller than L2 (small workload)")}
+            # timing rule: either the step's inputs are larger than the 126 MB L2, or L2 is flushed between the timed steps
+            "l2": ("inputs larger than L2 (per-variant arrays + reference windows > 126 MB per GPU)" if not l2_flush_needed(args, variants)
+                   else "L2 flushed between timed steps (256 MB written on the device; a rank's inputs are smaller than L2)")}
+
+
+def l2_flush_needed(args, variants):
+    per_gpu = variants / max(1, args.gpus) if args.scaling == "strong" else variants
+    return per_gpu < 2_000_000
 
 
 def main():
@@ -300,7 +305,13 @@ def main():
     launches = 0
     search_ms = 0.0
     t0 = time.perf_counter()
+    flush = None
+    if l2_flush_needed(args, nv * (world if args.scaling == "strong" else 1)):
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:%d" % local_rank)
     for _ in range(args.steps):
+        if flush is not None:   # outside the step's CUDA-event bracket (execute_ms is per step)
+            flush.zero_()
+            torch.cuda.synchronize()
         job.run()
         st = job.stats_ex()
         dev_ms += st["execute_ms"]

@@ -1990,9 +1990,9 @@ int Engine::settle(PassCtx& pc, WideBatch& early) {
       if (st == kRegionOverflow) {
         Rare& ra = pc.rare[key(k, j)];
         if (ra.tier >= kTierGeneral) { err_ = "search capacity exceeded in the large-capacity kernel"; return VCE_ERR_CAPACITY; }
-        int nt = ra.tier + 1;
-        const RegRange& g = pc.rr[k][j];
-        if (nt < kTierMid && std::max(g.cCount, g.bCount) > fastShape(nt).kv) nt = kTierMid;
+        // what outgrows a shared-memory tier goes straight to the arena tiers: every settle round is a launch plus a host
+        // round trip (~1 ms), and the follow-up rounds hold a handful of regions
+        const int nt = ra.tier < kTierMid ? kTierMid : ra.tier + 1;
         todo.push_back(std::make_pair(all[q].first, nt));
         ++be_->stats.escalated;
       } else if (st == kRegionWinMiss) {
@@ -2476,6 +2476,8 @@ int Engine::finishDevice(vce_sequence_result* results) {
   tm.lap("device results: final passes + copy back");
   // ---- per sequence: sync points, phasing counts, warnings, errors
   std::vector<uint8_t> live((size_t) nSeq_, 0);
+  struct SyncCopy { int32_t* dst; const int32_t* src; size_t n; };
+  std::vector<SyncCopy> syncCopies;
   for (int k = 0; k < nSeq_; ++k) {
     vce_sequence_result& res = results[k];
     const vce_sequence& sq = seqs_[k];
@@ -2511,7 +2513,7 @@ int Engine::finishDevice(vce_sequence_result* results) {
     const int s0 = out.seqSyncFirst[k], sn = out.seqSyncFirst[k + 1] - s0;
     res.n_sync[0] = sn;
     if (sn > res.sync_cap[0]) { res.error = VCE_ERR_CAPACITY; blank(0, 0); continue; }
-    std::memcpy(res.sync_points[0], out.syncPos + s0, (size_t) sn * sizeof(int32_t));
+    syncCopies.push_back(SyncCopy{res.sync_points[0], out.syncPos + s0, (size_t) sn});   // copied with the per-variant blocks below
     res.n_regions = sn;
     res.phasing[0] = (int32_t) out.counters[(size_t) k * 8 + 5];
     res.phasing[1] = (int32_t) out.counters[(size_t) k * 8 + 6];
@@ -2520,7 +2522,7 @@ int Engine::finishDevice(vce_sequence_result* results) {
   }
   tm.lap("device results: headers");
   // ---- per-variant records -> the caller's arrays (sorted inputs: sorted position == input index)
-  struct Task { int seq, side, lo, hi; };
+  struct Task { int seq, side, lo, hi; };   // side 2: a block of sync points (seq = index into syncCopies)
   std::vector<Task> tasks;
   const int block = 1 << 15;
   for (int k = 0; k < nSeq_; ++k) {
@@ -2530,8 +2532,18 @@ int Engine::finishDevice(vce_sequence_result* results) {
       for (int lo = 0; lo < n; lo += block) tasks.push_back(Task{k, side, lo, std::min(n, lo + block)});
     }
   }
+  const int syncBlock = 1 << 17;
+  for (size_t c = 0; c < syncCopies.size(); ++c) {
+    const int n = (int) syncCopies[c].n;
+    for (int lo = 0; lo < n; lo += syncBlock) tasks.push_back(Task{(int) c, 2, lo, std::min(n, lo + syncBlock)});
+  }
   pool_->parallelFor((int) tasks.size(), [&](int t, int) {
     const Task& tk = tasks[t];
+    if (tk.side == 2) {
+      const SyncCopy& sc = syncCopies[(size_t) tk.seq];
+      std::memcpy(sc.dst + tk.lo, sc.src + tk.lo, (size_t) (tk.hi - tk.lo) * sizeof(int32_t));
+      return;
+    }
     const vce_sequence& sq = seqs_[tk.seq];
     vce_side_result& o = tk.side == 0 ? results[tk.seq].calls : results[tk.seq].baseline;
     const vce_variants& in = tk.side == 0 ? sq.calls : sq.baseline;
