@@ -77,6 +77,7 @@ VCE_HD int ctaSmemWords(const CtaShape& s) {
   int wds = 0;
   wds += s.nb * kKeyW;                 // largest key of every block
   wds += (2 * s.nb + s.nb + 1) / 2 + 2;  // directory (deque of uint16) + free block stack (uint16)
+  wds = (wds + 3) & ~3;                // (carve() starts the cached blocks on a 16-byte boundary)
   wds += s.ncache * B_WORDS;           // cached blocks
   wds += (kMaxWork + 2) * kMaxW;       // work slots
   wds += kKeyW + kAuxW + 12;           // key of the path being inserted
