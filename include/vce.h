@@ -261,6 +261,38 @@ int vce_roc(const vce_roc_in* in, vce_roc_out* out);
 /* Same, also reporting host->device and kernel milliseconds (CUDA events) and the number of kernel launches. */
 int vce_roc_timed(const vce_roc_in* in, vce_roc_out* out, double* h2d_ms, double* kernel_ms, int32_t* launches);
 
+/*
+ * SURVEY.md 8(f) rank 3 -- variant loading on the device: the text of ONE sequence's VCF records (what
+ * VcfRecordTabixCallable.call reads for a sequence, VcfRecordTabixCallable.java:91-141; header lines and records of other
+ * sequences are passed over) becomes the vce_variants arrays vce_submit takes.  Restated: VcfSortRefiner.java:91-108
+ * (records sharing a start leave a java.util.PriorityQueue ordered by end), the loader filters (:103-118: longest allele
+ * over --Xmax-length, record beyond the template, factory says no / skips), the sample factory
+ * (VariantFactory.java:127-196: FILTER / FT unless --all-records, GT rules, haploid GT doubled, ploidy mismatch skipped),
+ * VcfUtils.getAlleleStrings / hasRedundantFirstNucleotide (:785-828), VariantType.getType (:107-190) and Allele.getAlleles
+ * (Allele.java:145-192).  --ref-overlap trimming (Variant.trimAlleles) and evaluation regions stay with the host.
+ * A record the reference would throw VcfFormatException for ends the call with VCE_ERR_BAD_ARGUMENT (vce_last_error names
+ * the line).  The result owns host copies of the arrays until vce_vcf_free.
+ */
+typedef struct vce_vcf_in {
+  const char* text;           /* uncompressed VCF text                            */
+  int64_t     text_len;       /* < 2 GB                                            */
+  const char* name;           /* CHROM to accept; NULL = every record              */
+  int32_t     template_len;   /* records ending beyond it are skipped; -1 = unknown */
+  int32_t     sample;         /* sample column, 0-based                            */
+  int32_t     ploidy;         /* --sample-ploidy (2)                               */
+  int32_t     pass_only;      /* 0 with --all-records                              */
+  int32_t     max_length;     /* --Xmax-length (1000), -1 = no limit               */
+} vce_vcf_in;
+typedef struct vce_vcf_stats {
+  int64_t lines, records, kept, skipped;   /* text lines, records of the sequence, variants, counted skips (:103-118) */
+  double  h2d_ms, kernel_ms, d2h_ms;       /* CUDA events on the loader's stream   */
+  int32_t launches;
+  int32_t reserved;
+} vce_vcf_stats;
+int  vce_vcf_parse(const vce_vcf_in* in, void** result);
+int  vce_vcf_variants(const void* result, vce_variants* out, vce_vcf_stats* stats);
+void vce_vcf_free(void* result);
+
 /* Formats the reference's warning text (PathFinder.java:163). Returns bytes written (excluding NUL). */
 int vce_format_warning(const vce_warning* w, const char* seq_name, char* buf, int32_t cap);
 

@@ -57,6 +57,21 @@ class CVariants(C.Structure):
     ]
 
 
+class CVcfIn(C.Structure):
+    _fields_ = [
+        ("text", C.c_char_p), ("text_len", C.c_int64), ("name", C.c_char_p), ("template_len", C.c_int32),
+        ("sample", C.c_int32), ("ploidy", C.c_int32), ("pass_only", C.c_int32), ("max_length", C.c_int32),
+    ]
+
+
+class CVcfStats(C.Structure):
+    _fields_ = [
+        ("lines", C.c_int64), ("records", C.c_int64), ("kept", C.c_int64), ("skipped", C.c_int64),
+        ("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("d2h_ms", C.c_double),
+        ("launches", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
 class CSequence(C.Structure):
     _fields_ = [
         ("name", C.c_char_p), ("template_bases", _u8p), ("template_len", C.c_int32),
@@ -382,6 +397,60 @@ class Library:
             f.argtypes = [C.POINTER(CConfig), C.c_int32, C.POINTER(CSequence), C.POINTER(CSequenceResult), C.c_int32]
             return f(C.byref(ccfg), len(results), cseqs, cres, threads)
         return self._submit(C.byref(ccfg), len(results), cseqs, cres)
+
+    def vcf_parse(self, text: bytes, name=None, template_len=-1, sample=0, ploidy=2, pass_only=True, max_length=1000):
+        """vce_vcf_parse: the records of sequence `name` in VCF `text` as a VariantSide (copies) plus the loader's counters
+        {"lines", "records", "kept", "skipped", "h2d_ms", "kernel_ms", "d2h_ms", "launches"}.  Raises ValueError on a record
+        the reference would throw VcfFormatException for."""
+        pre = "vce_" if self.prefix == "vce_" else self.prefix + "vce_"
+        f_parse = getattr(self.lib, pre + "vcf_parse")
+        f_get = getattr(self.lib, pre + "vcf_variants")
+        f_free = getattr(self.lib, pre + "vcf_free")
+        f_parse.restype = C.c_int
+        f_parse.argtypes = [C.POINTER(CVcfIn), C.POINTER(C.c_void_p)]
+        f_get.restype = C.c_int
+        f_get.argtypes = [C.c_void_p, C.POINTER(CVariants), C.POINTER(CVcfStats)]
+        f_free.restype = None
+        f_free.argtypes = [C.c_void_p]
+        cin = CVcfIn()
+        cin.text = text
+        cin.text_len = len(text)
+        cin.name = name.encode() if isinstance(name, str) else name
+        cin.template_len = int(template_len)
+        cin.sample, cin.ploidy, cin.pass_only, cin.max_length = int(sample), int(ploidy), int(bool(pass_only)), int(max_length)
+        handle = C.c_void_p()
+        rc = f_parse(C.byref(cin), C.byref(handle))
+        if rc != 0:
+            if self.prefix == "vce_":
+                msg = self.last_error()
+            else:
+                e = getattr(self.lib, pre + "vcf_error")
+                e.restype = C.c_char_p
+                msg = e().decode()
+            if rc == 2:   # VCE_ERR_BAD_ARGUMENT: a format error in the text
+                raise ValueError(msg)
+            raise RuntimeError("vcf_parse failed: %s %s" % (ERR_NAMES.get(rc, rc), msg))
+        try:
+            cv, st = CVariants(), CVcfStats()
+            rc = f_get(handle, C.byref(cv), C.byref(st))
+            if rc != 0:
+                raise RuntimeError("vcf_variants failed: %s" % ERR_NAMES.get(rc, rc))
+            n, ns = int(cv.n), int(cv.n_slots)
+
+            def arr(ptr, count, dtype):
+                if count <= 0:
+                    return np.zeros(0, dtype)
+                return np.ctypeslib.as_array(ptr, shape=(count,)).astype(dtype, copy=True)
+            off = arr(cv.allele_off, n + 1, np.int32) if n >= 0 else np.zeros(1, np.int32)
+            nt_off = arr(cv.allele_nt_off, ns + 1, np.int32)
+            side = VariantSide(arr(cv.id, n, np.int32), arr(cv.phased, n, np.uint8), arr(cv.status_in, n, np.uint8),
+                               arr(cv.gt, n * int(cv.gt_ploidy), np.int8).reshape(n, int(cv.gt_ploidy)), off,
+                               arr(cv.allele_start, ns, np.int32), arr(cv.allele_end, ns, np.int32), arr(cv.allele_null, ns, np.uint8),
+                               nt_off, arr(cv.nt, int(nt_off[-1]) if ns >= 0 and nt_off.size else 0, np.uint8))
+            stats = {k: getattr(st, k) for k in ("lines", "records", "kept", "skipped", "h2d_ms", "kernel_ms", "d2h_ms", "launches")}
+        finally:
+            f_free(handle)
+        return side, stats
 
     def roc(self, score, tp, fp, tp_raw, filter_mask=None, n_filters=1, ascending=False, timed=False):
         """Returns (rows per filter: list of (threshold, cum_tp, cum_fp, cum_tp_raw) arrays, no_score count).

@@ -18,6 +18,7 @@
 
 #include "../../include/vce.h"
 #include "vce_cuda.h"
+#include "vce_vcf.h"
 #include "vce_engine.h"
 
 namespace {
@@ -146,6 +147,7 @@ void vce_shutdown(void) {
   g_devPools.clear();
   g_devices.clear();
   vce::rocRelease();
+  vce::vcfShutdown();
   vce::templateRegistryRemove(-1, nullptr);
   vce::pinnedRegistryRemove(nullptr);
   g_device = -1;
@@ -441,6 +443,67 @@ int vce_roc_timed(const vce_roc_in* in, vce_roc_out* out, double* h2d_ms, double
   if (launches) *launches = t.launches;
   return VCE_OK;
 }
+
+// ------------------------------------------------------------------------------------------- VCF loader (vce_vcf.h)
+namespace {
+// shared by the CUDA library and nothing else: fills the C view of a result
+void vcfView(const vce::VcfResult& R, vce_variants* out) {
+  out->n = (int32_t) R.id.size();
+  out->gt_ploidy = R.ploidy;
+  out->id = R.id.data();
+  out->phased = R.phased.data();
+  out->status_in = R.statusIn.data();
+  out->gt = R.gt.data();
+  out->allele_off = R.alleleOff.data();
+  out->n_slots = R.alleleOff.empty() ? 0 : R.alleleOff.back();
+  out->allele_start = R.alleleStart.data();
+  out->allele_end = R.alleleEnd.data();
+  out->allele_null = R.alleleNull.data();
+  out->allele_nt_off = R.alleleNtOff.data();
+  out->nt = R.nt.data();
+}
+}  // namespace
+
+int vce_vcf_parse(const vce_vcf_in* in, void** result) {
+  if (!in || !result || (!in->text && in->text_len > 0)) return fail(VCE_ERR_BAD_ARGUMENT, "null argument");
+  *result = nullptr;
+  int dev;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    dev = g_device;
+  }
+  if (dev < 0) return fail(VCE_ERR_NOT_INITIALISED, "call vce_init first");
+  vce::VcfConfig cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.sample = in->sample; cfg.ploidy = in->ploidy; cfg.passOnly = in->pass_only; cfg.maxLength = in->max_length;
+  cfg.templateLen = in->template_len;
+  if (in->name) {
+    const size_t nl = std::strlen(in->name);
+    if (nl == 0 || nl >= sizeof(cfg.name)) return fail(VCE_ERR_BAD_ARGUMENT, "sequence name empty or too long");
+    std::memcpy(cfg.name, in->name, nl);
+    cfg.nameLen = (int32_t) nl;
+  }
+  std::unique_ptr<vce::VcfResult> R(new vce::VcfResult());
+  std::string err;
+  const int rc = vce::vcfParseOnDevice(dev, reinterpret_cast<const uint8_t*>(in->text), in->text_len, cfg, *R, err);
+  if (rc) return fail(rc, err);
+  *result = R.release();
+  return VCE_OK;
+}
+
+int vce_vcf_variants(const void* result, vce_variants* out, vce_vcf_stats* stats) {
+  if (!result || !out) return fail(VCE_ERR_BAD_ARGUMENT, "null argument");
+  const vce::VcfResult& R = *static_cast<const vce::VcfResult*>(result);
+  vcfView(R, out);
+  if (stats) {
+    stats->lines = R.stats.lines; stats->records = R.stats.records; stats->kept = R.stats.kept; stats->skipped = R.stats.skipped;
+    stats->h2d_ms = R.stats.h2dMs; stats->kernel_ms = R.stats.kernelMs; stats->d2h_ms = R.stats.d2hMs;
+    stats->launches = R.stats.launches; stats->reserved = 0;
+  }
+  return VCE_OK;
+}
+
+void vce_vcf_free(void* result) { delete static_cast<vce::VcfResult*>(result); }
 
 int vce_format_warning(const vce_warning* w, const char* seq_name, char* buf, int32_t cap) {
   // PathFinder.java:163

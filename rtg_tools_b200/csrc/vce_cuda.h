@@ -36,5 +36,11 @@ class WorkerPool;
 int rocRun(int device, const vce_roc_in* in, vce_roc_out* out, std::string& err, RocTiming* timing, WorkerPool* pool);
 void rocRelease();   // frees the per-device K4 contexts (vce_shutdown)
 
+// VCF loader (vce_vcf.cu / vce_vcf.h)
+struct VcfConfig;
+struct VcfResult;
+int vcfParseOnDevice(int device, const uint8_t* text, int64_t len, const VcfConfig& cfg, VcfResult& R, std::string& err);
+void vcfShutdown();
+
 }  // namespace vce
 #endif

@@ -1,0 +1,612 @@
+// vce_vcf.h -- SURVEY.md section 8(f) rank 3: VCF text -> the flat variant arrays of include/vce.h, on the device.
+//
+// Restates, per record of ONE sequence's stream (what VcfRecordTabixCallable reads for a sequence):
+//   the sort refinement of records that share a start      vcf/VcfSortRefiner.java:91-108 (java.util.PriorityQueue order)
+//   the loader filters, in order                            E/VcfRecordTabixCallable.java:91-141 (max length, beyond the
+//                                                           template, factory says no, factory skips)
+//   the sample factory                                      E/VariantFactory.java:127-196 (FILTER / FT, GT rules, ploidy)
+//   allele strings and types                                vcf/VcfUtils.java:785-828, vcf/VariantType.java:107-190
+//   the allele table                                        E/Allele.java:145-192 (only REF and the GT's alleles exist)
+// `--ref-overlap` trimming (Variant.trimAlleles) and evaluation regions stay with the host, as SURVEY 8(a3) says.
+//
+// Written once as pass bodies (VCE_LAMBDA) over an Ops policy, like vce_final.h: vce_vcf.cu runs them as kernels + CUB
+// scans, the test-only emulation as loops.  One thread per byte (line starts), per line (parse), per run of equal starts
+// (refinement), per kept variant (fill).
+#ifndef VCE_VCF_H_
+#define VCE_VCF_H_
+
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "vce_device.h"
+
+#if defined(__CUDACC__)
+#define VCE_VCF_LAMBDA [=] __host__ __device__
+#else
+#define VCE_VCF_LAMBDA [=]
+#endif
+
+namespace vce {
+
+enum : uint8_t { VK_KEPT = 0, VK_NOT_STREAM = 1, VK_IGNORED = 2, VK_SKIPPED = 3, VK_FATAL = 4 };
+// why a record is VK_FATAL (the reference throws VcfFormatException and the run ends)
+enum : uint8_t { VF_NONE = 0, VF_FIELDS = 1, VF_POS = 2, VF_SAMPLES = 3, VF_GT = 4, VF_GT_RANGE = 5, VF_ALT_IS_REF = 6, VF_GT_WIDE = 7 };
+
+struct VcfConfig {
+  int32_t sample;        // sample column (0-based)
+  int32_t ploidy;        // --sample-ploidy
+  int32_t passOnly;      // !--all-records
+  int32_t maxLength;     // --Xmax-length, -1 = no limit
+  int32_t templateLen;   // records that end beyond it are skipped, -1 = unknown
+  int32_t nameLen;       // CHROM to accept (a tabix query returns one sequence's records); 0 = accept every record
+  char name[232];
+};
+
+struct VcfLine {           // 40 bytes per line of text
+  int32_t start, end;      // POS - 1, start + len(REF)
+  int32_t nAlt;
+  int32_t ntBytes;         // bases of the materialised, non-null alleles
+  int8_t gt[4];
+  uint8_t kind, fatal, phased, pad;
+  int32_t refOff, altOff;  // offsets of REF / ALT within the line (the fill pass reads them again)
+  int32_t altLen, refLen;
+};
+
+struct VcfArrays {
+  // inputs
+  const uint8_t* text;
+  int32_t len;
+  VcfConfig cfg;
+  // pass scratch (device / host), sized by the caller: see vcfScratchInts()
+  int32_t* byteScan;       // [len + 1]
+  int32_t* lineStart;      // [nLines + 1]
+  VcfLine* lines;          // [nLines]
+  int32_t* streamScan;     // [nLines + 1]
+  int32_t* streamLine;     // [nStream]
+  int32_t* order;          // [nStream] refined position -> stream index
+  int32_t* heap;           // [nStream] scratch of the refinement
+  int32_t* keptScan;       // [nStream + 1]
+  int32_t* skipScan;       // [nStream + 1]
+  int32_t* keptPos;        // [n] kept variant -> refined position
+  int32_t* firstFatal;     // [1] smallest line index with a fatal record
+  // outputs (vce_variants layout), sized after the counting passes
+  int32_t* id;             // [n]
+  uint8_t* phased;         // [n]
+  uint8_t* statusIn;       // [n]
+  int8_t* gt;              // [n * ploidy]
+  int32_t* alleleOff;      // [n + 1]
+  int32_t* ntBase;         // [n + 1]
+  int32_t* alleleStart;    // [nSlots]
+  int32_t* alleleEnd;      // [nSlots]
+  uint8_t* alleleNull;     // [nSlots]
+  int32_t* alleleNtOff;    // [nSlots + 1]
+  uint8_t* nt;             // [nNt]
+  // counts
+  int32_t nLines, nStream, n, nSlots, nNt, nSkipped;
+};
+
+// ------------------------------------------------------------------------------------------------ small helpers
+VCE_HD bool vcfIsSym(const uint8_t* s, int n) {   // VariantType.getSymbolicAlleleType :107-122 != null
+  if (n <= 0) return false;
+  const uint8_t f = s[0], l = s[n - 1];
+  return f == '<' || l == '>' || f == '*' || l == '*' || f == '[' || f == ']' || l == '[' || l == ']';
+}
+VCE_HD int vcfBaseCode(uint8_t c) {   // DnaUtils.encodeString (upper-cased); -1 = illegal
+  switch (c) {
+    case 'N': case 'n': return 0;
+    case 'A': case 'a': return 1;
+    case 'C': case 'c': return 2;
+    case 'G': case 'g': return 3;
+    case 'T': case 't': return 4;
+    default: return -1;
+  }
+}
+VCE_HD bool vcfEq(const uint8_t* a, int na, const char* b, int nb) {
+  if (na != nb) return false;
+  for (int i = 0; i < na; ++i) if (a[i] != (uint8_t) b[i]) return false;
+  return true;
+}
+// one element of a ';'-separated list that is neither PASS nor "." -> filtered (VcfRecord.java:273-297)
+VCE_HD bool vcfListFails(const uint8_t* s, int n) {
+  int a = 0;
+  for (int i = 0; i <= n; ++i) {
+    if (i == n || s[i] == ';') {
+      const int m = i - a;
+      const bool ok = (m == 4 && s[a] == 'P' && s[a + 1] == 'A' && s[a + 2] == 'S' && s[a + 3] == 'S') || (m == 1 && s[a] == '.');
+      if (!ok) return true;
+      a = i + 1;
+    }
+  }
+  return false;
+}
+// k-th element of a separated list; returns false when there are fewer
+VCE_HD bool vcfNth(const uint8_t* s, int n, uint8_t sep, int k, int* off, int* len) {
+  int a = 0, idx = 0;
+  for (int i = 0; i <= n; ++i) {
+    if (i == n || s[i] == sep) {
+      if (idx == k) { *off = a; *len = i - a; return true; }
+      ++idx;
+      a = i + 1;
+    }
+  }
+  return false;
+}
+VCE_HD int vcfCount(const uint8_t* s, int n, uint8_t sep) {
+  int c = 1;
+  for (int i = 0; i < n; ++i) if (s[i] == sep) ++c;
+  return c;
+}
+
+// ------------------------------------------------------------------------------------------------ one record
+// Everything the loader decides about one line; the allele bytes themselves are written by vcfFillVariant.
+VCE_HDN VcfLine vcfParseLine(const uint8_t* t, int a, int b, const VcfConfig& cfg) {
+  VcfLine L;
+  L.start = L.end = 0; L.nAlt = 0; L.ntBytes = 0;
+  L.gt[0] = L.gt[1] = L.gt[2] = L.gt[3] = -2;
+  L.kind = VK_NOT_STREAM; L.fatal = VF_NONE; L.phased = 0; L.pad = 0;
+  L.refOff = L.altOff = L.altLen = L.refLen = 0;
+  if (b > a && t[b - 1] == '\r') --b;
+  bool blank = true;
+  for (int i = a; i < b; ++i) if (t[i] != ' ' && t[i] != '\t') { blank = false; break; }
+  if (blank || t[a] == '#') return L;
+  // fields: 0 CHROM 1 POS 3 REF 4 ALT 6 FILTER 8 FORMAT 9+sample
+  int fo[7], fl[7];
+  for (int q = 0; q < 7; ++q) { fo[q] = 0; fl[q] = -1; }
+  const int want[7] = {0, 1, 3, 4, 6, 8, 9 + cfg.sample};
+  int field = 0, fs = a;
+  for (int i = a; i <= b; ++i) {
+    if (i == b || t[i] == '\t') {
+      for (int q = 0; q < 7; ++q) if (want[q] == field) { fo[q] = fs; fl[q] = i - fs; }
+      ++field;
+      fs = i + 1;
+    }
+  }
+  const int nFields = field;
+  if (cfg.nameLen > 0 && !vcfEq(t + fo[0], fl[0] < 0 ? 0 : fl[0], cfg.name, cfg.nameLen)) return L;   // another sequence's record
+  L.kind = VK_IGNORED;
+  if (nFields < 8) { L.kind = VK_FATAL; L.fatal = VF_FIELDS; return L; }
+  // POS
+  {
+    long v = 0;
+    if (fl[1] <= 0 || fl[1] > 10) { L.kind = VK_FATAL; L.fatal = VF_POS; return L; }
+    for (int i = 0; i < fl[1]; ++i) {
+      const int c = t[fo[1] + i];
+      if (c < '0' || c > '9') { L.kind = VK_FATAL; L.fatal = VF_POS; return L; }
+      v = v * 10 + (c - '0');
+    }
+    if (v > 0x7fffffffL) { L.kind = VK_FATAL; L.fatal = VF_POS; return L; }
+    L.start = (int32_t) v - 1;
+  }
+  const uint8_t* ref = t + fo[2];
+  const int refLen = fl[2];
+  L.refOff = fo[2] - a; L.refLen = refLen;
+  L.end = L.start + refLen;
+  const uint8_t* alt = t + fo[3];
+  int altLen = fl[3];
+  int nAlt = 0;
+  if (!(altLen == 1 && alt[0] == '.')) nAlt = vcfCount(alt, altLen, ',');
+  else altLen = 0;
+  L.altOff = fo[3] - a; L.altLen = altLen; L.nAlt = nAlt;
+  // loader filter 1: longest allele string (VcfRecordTabixCallable.java:103-106)
+  int longest = refLen;
+  for (int k = 0; k < nAlt; ++k) {
+    int o = 0, l = 0;
+    vcfNth(alt, altLen, ',', k, &o, &l);
+    longest = l > longest ? l : longest;
+  }
+  if (cfg.maxLength > -1 && longest > cfg.maxLength) { L.kind = VK_SKIPPED; return L; }
+  // loader filter 2: beyond the template (:107-112)
+  if (cfg.templateLen >= 0 && L.end > cfg.templateLen) { L.kind = VK_SKIPPED; return L; }
+  // ---- SampleVariants.variant (VariantFactory.java:127-147)
+  const uint8_t* fmt = t + fo[5];
+  const int fmtLen = fl[5] < 0 ? 0 : fl[5];
+  const bool haveFmt = nFields > 8;
+  const int nSamples = nFields > 9 ? nFields - 9 : 0;
+  const uint8_t* smp = t + fo[6];
+  const int smpLen = fl[6] < 0 ? 0 : fl[6];
+  // key -> index within FORMAT
+  int gtKey = -1, ftKey = -1;
+  if (haveFmt) {
+    const int nk = vcfCount(fmt, fmtLen, ':');
+    for (int k = 0; k < nk; ++k) {
+      int o = 0, l = 0;
+      vcfNth(fmt, fmtLen, ':', k, &o, &l);
+      if (l == 2 && fmt[o] == 'G' && fmt[o + 1] == 'T' && gtKey < 0) gtKey = k;
+      if (l == 2 && fmt[o] == 'F' && fmt[o + 1] == 'T' && ftKey < 0) ftKey = k;
+    }
+  }
+  if (cfg.passOnly) {
+    const uint8_t* fil = t + fo[4];
+    const int filLen = fl[4];
+    if (!(filLen == 1 && fil[0] == '.') && vcfListFails(fil, filLen)) return L;     // FILTER not PASS
+    if (ftKey >= 0 && cfg.sample < nSamples) {                                       // sample FT
+      int o = 0, l = 0;
+      if (vcfNth(smp, smpLen, ':', ftKey, &o, &l) && vcfListFails(smp + o, l)) return L;
+    }
+  }
+  // getDefinedVariantGt :163-196
+  if (cfg.sample >= nSamples) { L.kind = VK_FATAL; L.fatal = VF_SAMPLES; return L; }
+  if (gtKey < 0) return L;
+  int go = 0, gl = 1;
+  const uint8_t dot = '.';   // a sample with fewer sub-fields than FORMAT has keys reads as missing
+  const uint8_t* gts = &dot;
+  if (vcfNth(smp, smpLen, ':', gtKey, &go, &gl)) gts = smp + go; else gl = 1;
+  int gt[4];
+  int ng = 0;
+  bool phased = false;
+  {
+    int x0 = 0;
+    for (int i = 0; i <= gl; ++i) {
+      if (i == gl || gts[i] == '/' || gts[i] == '|') {
+        if (i < gl && gts[i] == '|') phased = true;
+        const int m = i - x0;
+        int v = -1;
+        if (!(m == 1 && gts[x0] == '.')) {
+          if (m <= 0 || m > 6) { L.kind = VK_FATAL; L.fatal = VF_GT; return L; }
+          v = 0;
+          for (int q = 0; q < m; ++q) {
+            const int c = gts[x0 + q];
+            if (c < '0' || c > '9') { L.kind = VK_FATAL; L.fatal = VF_GT; return L; }
+            v = v * 10 + (c - '0');
+          }
+        }
+        if (ng < 4) gt[ng] = v;
+        ++ng;
+        x0 = i + 1;
+      }
+    }
+  }
+  for (int q = 0; q < ng && q < 4; ++q) if (gt[q] > nAlt) { L.kind = VK_FATAL; L.fatal = VF_GT_RANGE; return L; }
+  if (ng > 4) {   // more alleles than the ABI's gt[] holds: cannot be the expected ploidy (<= 4) either
+    L.kind = VK_SKIPPED;
+    return L;
+  }
+  if (cfg.ploidy == 2 && ng == 1) { gt[1] = gt[0]; ng = 2; }
+  if (ng != cfg.ploidy) { L.kind = VK_SKIPPED; return L; }   // SkippedVariantException: counted
+  // allele strings (VcfUtils.getAlleleStrings :806-828): padding base removed when every non-'*' ALT starts with REF's first base
+  bool pad = false;
+  {
+    const uint8_t c = refLen > 0 ? ref[0] : (uint8_t) '.';
+    bool hasAlt = false, same = true;
+    for (int k = 0; k < nAlt; ++k) {
+      int o = 0, l = 0;
+      vcfNth(alt, altLen, ',', k, &o, &l);
+      if (l > 0 && alt[o] != '*') {
+        hasAlt = true;
+        if (alt[o] != c) same = false;
+      } else if (l == 0) {
+        same = false;
+      }
+    }
+    pad = hasAlt && same;
+  }
+  L.pad = pad ? 1 : 0;
+  const uint8_t* r0 = ref + (pad ? 1 : 0);
+  const int r0n = refLen - (pad ? 1 : 0);
+  for (int k = 0; k < nAlt; ++k) {   // an ALT equal to REF is a format error, whatever the GT says
+    int o = 0, l = 0;
+    vcfNth(alt, altLen, ',', k, &o, &l);
+    const bool strip = pad && l > 0 && alt[o] != '*';
+    const uint8_t* s = alt + o + (strip ? 1 : 0);
+    const int sn = l - (strip ? 1 : 0);
+    bool eq = sn == r0n;
+    for (int q = 0; eq && q < sn; ++q) if (s[q] != r0[q]) eq = false;
+    if (eq) { L.kind = VK_FATAL; L.fatal = VF_ALT_IS_REF; return L; }
+  }
+  bool defined = false;   // some GT allele > 0 is a non-SV variant (VariantType.getType(String,String) :169-190)
+  for (int q = 0; q < ng && !defined; ++q) {
+    if (gt[q] <= 0) continue;
+    int o = 0, l = 0;
+    vcfNth(alt, altLen, ',', gt[q] - 1, &o, &l);
+    const bool strip = pad && l > 0 && alt[o] != '*';
+    const uint8_t* s = alt + o + (strip ? 1 : 0);
+    const int sn = l - (strip ? 1 : 0);
+    const bool snp = r0n == 1 && sn == 1 && s[0] != '*';
+    if (snp || !vcfIsSym(s, sn)) defined = true;
+  }
+  if (!defined) return L;
+  for (int q = 0; q < ng; ++q) if (gt[q] > 127) { L.kind = VK_FATAL; L.fatal = VF_GT_WIDE; return L; }
+  // Allele.getAlleles :145-192: REF and the GT's alleles; symbolic ones are null; an illegal base skips the record
+  int ntBytes = 0;
+  for (int id = 0; id <= nAlt; ++id) {
+    bool inGt = id == 0;
+    for (int q = 0; q < ng; ++q) if (gt[q] == id) inGt = true;
+    if (!inGt) continue;
+    const uint8_t* s;
+    int sn;
+    if (id == 0) { s = ref; sn = refLen; }
+    else {
+      int o = 0, l = 0;
+      vcfNth(alt, altLen, ',', id - 1, &o, &l);
+      s = alt + o; sn = l;
+    }
+    if (vcfIsSym(s, sn)) continue;
+    const int from = pad ? 1 : 0;
+    for (int q = from; q < sn; ++q) if (vcfBaseCode(s[q]) < 0) { L.kind = VK_SKIPPED; return L; }
+    ntBytes += sn > from ? sn - from : 0;
+  }
+  L.ntBytes = ntBytes;
+  for (int q = 0; q < ng; ++q) L.gt[q] = (int8_t) gt[q];
+  L.phased = phased ? 1 : 0;
+  L.kind = VK_KEPT;
+  return L;
+}
+
+// The allele table of one kept variant (slot 0 = the missing allele, slot 1 = REF, slot k + 1 = ALT k).
+VCE_HDN void vcfFillVariant(const uint8_t* line, const VcfLine& L, int ploidy, int32_t slot0, int32_t nt0, int32_t* aStart, int32_t* aEnd,
+                            uint8_t* aNull, int32_t* aNtOff, uint8_t* nt) {
+  const uint8_t* ref = line + L.refOff;
+  const uint8_t* alt = line + L.altOff;
+  int at = nt0;
+  for (int slot = 0; slot < L.nAlt + 2; ++slot) {
+    const int id = slot - 1;
+    bool have = id == 0;
+    for (int q = 0; q < ploidy && q < 4; ++q) if (id >= 0 && L.gt[q] == id) have = true;
+    const uint8_t* s = ref;
+    int sn = L.refLen;
+    if (id > 0) {
+      int o = 0, l = 0;
+      vcfNth(alt, L.altLen, ',', id - 1, &o, &l);
+      s = alt + o; sn = l;
+    }
+    aNtOff[slot0 + slot] = at;
+    if (id < 0 || !have || vcfIsSym(s, sn)) {
+      aStart[slot0 + slot] = 0; aEnd[slot0 + slot] = 0; aNull[slot0 + slot] = 1;
+      continue;
+    }
+    aStart[slot0 + slot] = L.start + (L.pad ? 1 : 0);
+    aEnd[slot0 + slot] = L.end;
+    aNull[slot0 + slot] = 0;
+    for (int q = L.pad ? 1 : 0; q < sn; ++q) nt[at++] = (uint8_t) vcfBaseCode(s[q]);
+  }
+}
+
+VCE_HD void vcfAtomicMin(int32_t* p, int32_t v) {
+#if defined(__CUDA_ARCH__)
+  atomicMin(p, v);
+#else
+  if (v < *p) *p = v;
+#endif
+}
+
+// Bytes of int32 scratch the counting passes need for `len` bytes of text holding at most `maxLines` lines.
+inline size_t vcfScratchBytes(int64_t len, int64_t maxLines) {
+  return (size_t) (len + 1) * 4 + (size_t) (maxLines + 1) * (4 * 8) + (size_t) maxLines * sizeof(VcfLine) + 64;
+}
+
+// ---- passes 1: line starts, parse, stream, refinement, kept / skipped counts.  Fills A.nLines, nStream, n, nSkipped, and
+// per kept variant the slot / base counts scanned into alleleOff / ntBase (both sized n + 1 by the caller AFTER
+// vcfCountLines; see vce_vcf.cu / the emulation for the calling order).
+template <class Ops>
+int vcfCountLines(Ops& ops, VcfArrays& A) {
+  const VcfArrays a = A;
+  ops.parFor(a.len + 1, VCE_VCF_LAMBDA(int i) {
+    a.byteScan[i] = (i < a.len && (i == 0 || a.text[i - 1] == '\n')) ? 1 : 0;
+  });
+  ops.exclusiveSum(a.byteScan, a.byteScan, a.len + 1);
+  A.nLines = ops.fetchInt(a.byteScan + a.len);
+  return A.nLines;
+}
+
+template <class Ops>
+void vcfParsePasses(Ops& ops, VcfArrays& A) {
+  const VcfArrays a = A;
+  const int nLines = A.nLines;
+  ops.parFor(a.len, VCE_VCF_LAMBDA(int i) {
+    if (i == 0 || a.text[i - 1] == '\n') a.lineStart[a.byteScan[i]] = i;
+  });
+  ops.parFor(1, VCE_VCF_LAMBDA(int) { a.lineStart[nLines] = a.len; *a.firstFatal = 0x7fffffff; });
+  ops.parFor(nLines + 1, VCE_VCF_LAMBDA(int l) {
+    if (l == nLines) { a.streamScan[l] = 0; return; }
+    int e = a.lineStart[l + 1];
+    if (e > a.lineStart[l] && a.text[e - 1] == '\n') --e;
+    const VcfLine L = vcfParseLine(a.text, a.lineStart[l], e, a.cfg);
+    a.lines[l] = L;
+    a.streamScan[l] = L.kind != VK_NOT_STREAM ? 1 : 0;
+    if (L.kind == VK_FATAL) vcfAtomicMin(a.firstFatal, l);
+  });
+  ops.exclusiveSum(a.streamScan, a.streamScan, nLines + 1);
+  A.nStream = ops.fetchInt(a.streamScan + nLines);
+  const int nStream = A.nStream;
+  ops.parFor(nLines, VCE_VCF_LAMBDA(int l) {
+    if (a.lines[l].kind != VK_NOT_STREAM) a.streamLine[a.streamScan[l]] = l;
+  });
+  // VcfSortRefiner: records that share a start leave a java.util.PriorityQueue ordered by end (ties are NOT stable: the
+  // binary heap's sift rules are replayed as they are).  One thread per run of equal starts; the run's slice of `heap`
+  // is its queue.
+  ops.parFor(nStream, VCE_VCF_LAMBDA(int s) {
+    const int st = a.lines[a.streamLine[s]].start;
+    if (s > 0 && a.lines[a.streamLine[s - 1]].start == st) return;
+    int e = s + 1;
+    while (e < nStream && a.lines[a.streamLine[e]].start == st) ++e;
+    if (e - s == 1) { a.order[s] = s; return; }
+    int32_t* q = a.heap + s;
+    int n = 0;
+    for (int x = s; x < e; ++x) {   // offer (siftUp)
+      const int kx = a.lines[a.streamLine[x]].end;
+      int k = n++;
+      while (k > 0) {
+        const int parent = (k - 1) >> 1;
+        const int pe = q[parent];
+        if (kx >= a.lines[a.streamLine[pe]].end) break;
+        q[k] = pe;
+        k = parent;
+      }
+      q[k] = x;
+    }
+    for (int out = s; out < e; ++out) {   // poll (siftDown)
+      a.order[out] = q[0];
+      const int x = q[--n];
+      if (n > 0) {
+        const int kx = a.lines[a.streamLine[x]].end;
+        int k = 0;
+        const int half = n >> 1;
+        while (k < half) {
+          int child = 2 * k + 1;
+          int c = q[child];
+          const int right = child + 1;
+          if (right < n && a.lines[a.streamLine[c]].end > a.lines[a.streamLine[q[right]]].end) { child = right; c = q[child]; }
+          if (kx <= a.lines[a.streamLine[c]].end) break;
+          q[k] = c;
+          k = child;
+        }
+        q[k] = x;
+      }
+    }
+  });
+  ops.parFor(nStream + 1, VCE_VCF_LAMBDA(int p) {
+    const int kind = p < nStream ? (int) a.lines[a.streamLine[a.order[p]]].kind : (int) VK_NOT_STREAM;
+    a.keptScan[p] = kind == VK_KEPT ? 1 : 0;
+    a.skipScan[p] = kind == VK_SKIPPED ? 1 : 0;
+  });
+  ops.exclusiveSum(a.keptScan, a.keptScan, nStream + 1);
+  ops.exclusiveSum(a.skipScan, a.skipScan, nStream + 1);
+  A.n = ops.fetchInt(a.keptScan + nStream);
+  A.nSkipped = ops.fetchInt(a.skipScan + nStream);
+}
+
+// ---- passes 2 (after the caller sized keptPos / alleleOff / ntBase by A.n): slot and base offsets
+template <class Ops>
+void vcfOffsetPasses(Ops& ops, VcfArrays& A) {
+  const VcfArrays a = A;
+  const int nStream = A.nStream, n = A.n;
+  ops.parFor(nStream, VCE_VCF_LAMBDA(int p) {
+    if (a.keptScan[p + 1] != a.keptScan[p]) a.keptPos[a.keptScan[p]] = p;
+  });
+  ops.parFor(n + 1, VCE_VCF_LAMBDA(int v) {
+    if (v == n) { a.alleleOff[v] = 0; a.ntBase[v] = 0; return; }
+    const VcfLine& L = a.lines[a.streamLine[a.order[a.keptPos[v]]]];
+    a.alleleOff[v] = L.nAlt + 2;
+    a.ntBase[v] = L.ntBytes;
+  });
+  ops.exclusiveSum(a.alleleOff, a.alleleOff, n + 1);
+  ops.exclusiveSum(a.ntBase, a.ntBase, n + 1);
+  A.nSlots = ops.fetchInt(a.alleleOff + n);
+  A.nNt = ops.fetchInt(a.ntBase + n);
+}
+
+// ---- passes 3 (after the caller sized the allele arrays by A.nSlots / A.nNt): the arrays of vce_variants
+template <class Ops>
+void vcfFillPasses(Ops& ops, VcfArrays& A) {
+  const VcfArrays a = A;
+  const int n = A.n, ploidy = A.cfg.ploidy;
+  const int nSlots = A.nSlots, nNt = A.nNt;
+  ops.parFor(n, VCE_VCF_LAMBDA(int v) {
+    const int p = a.keptPos[v];
+    const int l = a.streamLine[a.order[p]];
+    const VcfLine& L = a.lines[l];
+    a.id[v] = p + 1;   // 1-based ordinal of the record in the refined stream, counted before any filter (:100)
+    a.phased[v] = L.phased;
+    a.statusIn[v] = 0;
+    for (int q = 0; q < ploidy; ++q) a.gt[(size_t) v * ploidy + q] = q < 4 ? L.gt[q] : (int8_t) -2;
+    vcfFillVariant(a.text + a.lineStart[l], L, ploidy, a.alleleOff[v], a.ntBase[v], a.alleleStart, a.alleleEnd, a.alleleNull,
+                   a.alleleNtOff, a.nt);
+  });
+  ops.parFor(1, VCE_VCF_LAMBDA(int) { a.alleleNtOff[nSlots] = nNt; });
+}
+
+// ------------------------------------------------------------------------------------------------ driver (host code)
+struct VcfStats {
+  int64_t lines = 0, records = 0, kept = 0, skipped = 0;
+  double h2dMs = 0, kernelMs = 0, d2hMs = 0;
+  int32_t launches = 0, fatalLine = -1, fatalReason = 0;
+};
+struct VcfResult {   // what vce_vcf_variants hands out: host copies of the arrays, owned by the result
+  int32_t ploidy = 0;
+  std::vector<int32_t> id, alleleOff, alleleStart, alleleEnd, alleleNtOff;
+  std::vector<uint8_t> phased, statusIn, alleleNull, nt;
+  std::vector<int8_t> gt;
+  VcfStats stats;
+};
+
+// Ops: alloc<T>(n) / upload / download / parFor / exclusiveSum / fetchInt / mark(k) (timing marks: 0 before the upload,
+// 1 after it, 2 after the last kernel, 3 after the downloads).
+template <class Ops>
+int vcfDrive(Ops& ops, const uint8_t* text, int64_t len, const VcfConfig& cfg, VcfResult& R, std::string& err) {
+  if (len < 0 || len >= 0x7ffffff0LL) { err = "VCF text of 2 GB or more: hand it over in pieces (one sequence per call)"; return 1; }
+  if (cfg.ploidy < 1 || cfg.ploidy > 4 || cfg.sample < 0) { err = "sample / ploidy out of range"; return 1; }
+  R = VcfResult();
+  R.ploidy = cfg.ploidy;
+  VcfArrays A;
+  std::memset(&A, 0, sizeof(A));
+  A.len = (int32_t) len;
+  A.cfg = cfg;
+  ops.mark(0);
+  uint8_t* dText = ops.template alloc<uint8_t>((size_t) len + 16);
+  A.byteScan = ops.template alloc<int32_t>((size_t) len + 1);
+  A.firstFatal = ops.template alloc<int32_t>(4);
+  if (!dText || !A.byteScan || !A.firstFatal) { err = "out of device memory for the VCF text"; return 2; }
+  ops.upload(dText, text, (size_t) len);
+  A.text = dText;
+  ops.mark(1);
+  const int nLines = vcfCountLines(ops, A);
+  A.lineStart = ops.template alloc<int32_t>((size_t) nLines + 1);
+  A.lines = ops.template alloc<VcfLine>((size_t) nLines + 1);
+  A.streamScan = ops.template alloc<int32_t>((size_t) nLines + 1);
+  A.streamLine = ops.template alloc<int32_t>((size_t) nLines + 1);
+  A.order = ops.template alloc<int32_t>((size_t) nLines + 1);
+  A.heap = ops.template alloc<int32_t>((size_t) nLines + 1);
+  A.keptScan = ops.template alloc<int32_t>((size_t) nLines + 1);
+  A.skipScan = ops.template alloc<int32_t>((size_t) nLines + 1);
+  if (!A.lineStart || !A.lines || !A.streamScan || !A.streamLine || !A.order || !A.heap || !A.keptScan || !A.skipScan) {
+    err = "out of device memory for the VCF line tables";
+    return 2;
+  }
+  vcfParsePasses(ops, A);
+  R.stats.lines = nLines;
+  R.stats.records = A.nStream;
+  R.stats.skipped = A.nSkipped;
+  const int fatal = ops.fetchInt(A.firstFatal);
+  if (fatal != 0x7fffffff) {
+    VcfLine L;
+    ops.download(&L, A.lines + fatal, sizeof(L));
+    R.stats.fatalLine = fatal;
+    R.stats.fatalReason = L.fatal;
+    static const char* const why[] = {"", "fewer than 8 fields", "POS is not a number", "record does not contain enough samples",
+                                      "GT is not a list of allele ids", "GT contains an allele id out of range",
+                                      "an ALT allele is the same as REF", "allele id above 127"};
+    err = std::string("VCF format error in line ") + std::to_string(fatal + 1) + ": " + why[L.fatal < 8 ? L.fatal : 0];
+    return 3;
+  }
+  const int n = A.n;
+  A.keptPos = ops.template alloc<int32_t>((size_t) n + 1);
+  A.alleleOff = ops.template alloc<int32_t>((size_t) n + 1);
+  A.ntBase = ops.template alloc<int32_t>((size_t) n + 1);
+  A.id = ops.template alloc<int32_t>((size_t) n + 1);
+  A.phased = ops.template alloc<uint8_t>((size_t) n + 1);
+  A.statusIn = ops.template alloc<uint8_t>((size_t) n + 1);
+  A.gt = ops.template alloc<int8_t>((size_t) n * cfg.ploidy + 4);
+  if (!A.keptPos || !A.alleleOff || !A.ntBase || !A.id || !A.phased || !A.statusIn || !A.gt) { err = "out of device memory for the variants"; return 2; }
+  vcfOffsetPasses(ops, A);
+  A.alleleStart = ops.template alloc<int32_t>((size_t) A.nSlots + 1);
+  A.alleleEnd = ops.template alloc<int32_t>((size_t) A.nSlots + 1);
+  A.alleleNull = ops.template alloc<uint8_t>((size_t) A.nSlots + 1);
+  A.alleleNtOff = ops.template alloc<int32_t>((size_t) A.nSlots + 1);
+  A.nt = ops.template alloc<uint8_t>((size_t) A.nNt + 4);
+  if (!A.alleleStart || !A.alleleEnd || !A.alleleNull || !A.alleleNtOff || !A.nt) { err = "out of device memory for the allele tables"; return 2; }
+  vcfFillPasses(ops, A);
+  ops.mark(2);
+  R.id.resize((size_t) n); R.phased.resize((size_t) n); R.statusIn.resize((size_t) n); R.gt.resize((size_t) n * cfg.ploidy);
+  R.alleleOff.resize((size_t) n + 1);
+  R.alleleStart.resize((size_t) A.nSlots); R.alleleEnd.resize((size_t) A.nSlots); R.alleleNull.resize((size_t) A.nSlots);
+  R.alleleNtOff.resize((size_t) A.nSlots + 1);
+  R.nt.resize((size_t) A.nNt);
+  ops.download(R.id.data(), A.id, (size_t) n * 4);
+  ops.download(R.phased.data(), A.phased, (size_t) n);
+  ops.download(R.statusIn.data(), A.statusIn, (size_t) n);
+  ops.download(R.gt.data(), A.gt, (size_t) n * cfg.ploidy);
+  ops.download(R.alleleOff.data(), A.alleleOff, ((size_t) n + 1) * 4);
+  ops.download(R.alleleStart.data(), A.alleleStart, (size_t) A.nSlots * 4);
+  ops.download(R.alleleEnd.data(), A.alleleEnd, (size_t) A.nSlots * 4);
+  ops.download(R.alleleNull.data(), A.alleleNull, (size_t) A.nSlots);
+  ops.download(R.alleleNtOff.data(), A.alleleNtOff, ((size_t) A.nSlots + 1) * 4);
+  ops.download(R.nt.data(), A.nt, (size_t) A.nNt);
+  ops.mark(3);
+  R.stats.kept = n;
+  return 0;
+}
+
+}  // namespace vce
+#endif

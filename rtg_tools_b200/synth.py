@@ -378,3 +378,49 @@ def make_c3(n_clusters=2000, per_seq=50, seed=3, per_side=(12, 40), long_frac=0.
         out.append(seq)
         quals.append(q)
     return (out, quals) if return_qual else out
+
+
+def make_vcf_text(n_records, seed=7, name="chr1", mean_gap=700, samples=("s1", "s2")):
+    """A sorted single-sequence VCF (text, template_len) with the variant mix of `simulate_sample` (SNPs, MNPs, insertions and
+    deletions with their padding base, a few multi-allelic records, symbolic ALTs and filtered records): input of the VCF
+    loader (vce_vcf_parse), not tied to any template sequence."""
+    rng = np.random.default_rng(seed)
+    gaps = rng.geometric(1.0 / mean_gap, n_records).astype(np.int64)
+    pos = np.cumsum(gaps) + 1
+    kind = rng.choice(6, n_records, p=[0.72, 0.06, 0.08, 0.08, 0.04, 0.02])   # snp, mnp, ins, del, multi, symbolic
+    base = np.array(list("ACGT"))
+    r0 = rng.integers(0, 4, n_records)
+    a0 = (r0 + rng.integers(1, 4, n_records)) % 4
+    ln = rng.choice([1, 1, 2, 3, 5, 9], n_records)
+    tail = rng.integers(0, 4, (n_records, 9))
+    gt_het = rng.random(n_records) < 0.57
+    phased = rng.random(n_records) < 0.5
+    filt = rng.random(n_records) < 0.03
+    lines = ["##fileformat=VCFv4.2", "##contig=<ID=%s,length=%d>" % (name, int(pos[-1]) + 1000),
+             "##FORMAT=<ID=GT,Number=1,Type=String,Description=\"Genotype\">",
+             "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(samples)]
+    for i in range(n_records):
+        k = kind[i]
+        rb, ab = base[r0[i]], base[a0[i]]
+        t = "".join(base[tail[i, :ln[i]]])
+        if k == 0:
+            ref, alt = rb, ab
+        elif k == 1:
+            ref, alt = rb + t, ab + t[::-1] + ("" if len(t) == 0 else "")
+            if alt == ref:
+                alt = ab + t
+        elif k == 2:
+            ref, alt = rb, rb + t
+        elif k == 3:
+            ref, alt = rb + t, rb
+        elif k == 4:
+            ref, alt = rb, ab + "," + rb + t
+        else:
+            ref, alt = rb, "<DEL>"
+        sep = "|" if phased[i] else "/"
+        g1 = ("0" + sep + "1") if gt_het[i] else ("1" + sep + "1")
+        if k == 4:
+            g1 = "1" + sep + "2"
+        g2 = "0" + sep + "1" if (i & 3) else "."
+        lines.append("%s\t%d\t.\t%s\t%s\t%d\t%s\t.\tGT\t%s\t%s" % (name, pos[i], ref, alt, 10 + (i % 80), "q10" if filt[i] else "PASS", g1, g2))
+    return "\n".join(lines) + "\n", int(pos[-1]) + 1000

@@ -18,6 +18,7 @@
 #include "../../rtg_tools_b200/csrc/vce_engine.h"
 #include "../../rtg_tools_b200/csrc/vce_orient.h"
 #include "../../rtg_tools_b200/csrc/vce_pipeline.h"
+#include "../../rtg_tools_b200/csrc/vce_vcf.h"
 
 namespace {
 using namespace vce;
@@ -586,4 +587,62 @@ int emul_orientations(int32_t kind, int32_t H, int32_t gt_ploidy, const int8_t* 
   return cnt.n;
 }
 int emul_vce_roc(const vce_roc_in*, vce_roc_out*) { return VCE_ERR_UNSUPPORTED; }
+
+// ---- VCF loader (vce_vcf.h) with the passes run as loops
+}  // extern "C"
+namespace {
+struct HostVcfOps {
+  std::vector<std::unique_ptr<uint8_t[]>> blocks;
+  template <class T> T* alloc(size_t n) {
+    blocks.emplace_back(new uint8_t[n * sizeof(T) + 64]);
+    std::memset(blocks.back().get(), 0xcd, n * sizeof(T) + 64);   // poison: every entry read must have been written
+    return reinterpret_cast<T*>(blocks.back().get());
+  }
+  void upload(void* d, const void* h, size_t bytes) { if (bytes) std::memcpy(d, h, bytes); }
+  void download(void* h, const void* d, size_t bytes) { if (bytes) std::memcpy(h, d, bytes); }
+  template <class F> void parFor(int n, F f) { for (int i = 0; i < n; ++i) f(i); }
+  void exclusiveSum(int32_t* in, int32_t* out, int n) { int32_t acc = 0; for (int i = 0; i < n; ++i) { const int32_t v = in[i]; out[i] = acc; acc += v; } }
+  int fetchInt(const int32_t* p) { return *p; }
+  void mark(int) {}
+};
+std::string g_vcfErr;
+}  // namespace
+extern "C" {
+
+int emul_vce_vcf_parse(const vce_vcf_in* in, void** result) {
+  *result = nullptr;
+  vce::VcfConfig cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.sample = in->sample; cfg.ploidy = in->ploidy; cfg.passOnly = in->pass_only; cfg.maxLength = in->max_length;
+  cfg.templateLen = in->template_len;
+  if (in->name) {
+    const size_t nl = std::strlen(in->name);
+    if (nl == 0 || nl >= sizeof(cfg.name)) return VCE_ERR_BAD_ARGUMENT;
+    std::memcpy(cfg.name, in->name, nl);
+    cfg.nameLen = (int32_t) nl;
+  }
+  std::unique_ptr<vce::VcfResult> R(new vce::VcfResult());
+  HostVcfOps ops;
+  const int rc = vce::vcfDrive(ops, reinterpret_cast<const uint8_t*>(in->text), in->text_len, cfg, *R, g_vcfErr);
+  if (rc) return rc == 2 ? VCE_ERR_CUDA : VCE_ERR_BAD_ARGUMENT;
+  *result = R.release();
+  return VCE_OK;
+}
+const char* emul_vce_vcf_error() { return g_vcfErr.c_str(); }
+int emul_vce_vcf_variants(const void* result, vce_variants* out, vce_vcf_stats* stats) {
+  const vce::VcfResult& R = *static_cast<const vce::VcfResult*>(result);
+  out->n = (int32_t) R.id.size();
+  out->gt_ploidy = R.ploidy;
+  out->id = R.id.data(); out->phased = R.phased.data(); out->status_in = R.statusIn.data(); out->gt = R.gt.data();
+  out->allele_off = R.alleleOff.data();
+  out->n_slots = R.alleleOff.empty() ? 0 : R.alleleOff.back();
+  out->allele_start = R.alleleStart.data(); out->allele_end = R.alleleEnd.data(); out->allele_null = R.alleleNull.data();
+  out->allele_nt_off = R.alleleNtOff.data(); out->nt = R.nt.data();
+  if (stats) {
+    std::memset(stats, 0, sizeof(*stats));
+    stats->lines = R.stats.lines; stats->records = R.stats.records; stats->kept = R.stats.kept; stats->skipped = R.stats.skipped;
+  }
+  return VCE_OK;
+}
+void emul_vce_vcf_free(void* result) { delete static_cast<vce::VcfResult*>(result); }
 }

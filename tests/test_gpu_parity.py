@@ -323,3 +323,35 @@ def test_c_abi_from_plain_c_threads(tmp_path):
     print(out.stdout, out.stderr)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.startswith("OK")
+
+
+# ------------------------------------------------------------------------------------------- VCF loader
+def test_cuda_vcf_loader_fixtures(engine):
+    """vce_vcf_parse on every VCF the reference's vcfeval tests bundle (all samples, all sequences, with and without
+    --all-records) against the loader restated in oracle/ref_host.py."""
+    from test_vcf_loader import check_fixtures
+    assert check_fixtures(engine.lib) > 200
+
+
+def test_cuda_vcf_loader_fuzz(engine):
+    from test_vcf_loader import check_fuzz
+    out = check_fuzz(engine.lib, range(40))
+    assert out["ok"] == 40 * 8
+    out = check_fuzz(engine.lib, range(100, 140), bad=True)
+    assert out["format-error"] > 20 and out["ok"] > 20
+
+
+def test_cuda_vcf_loader_million_records(engine):
+    """A 1 M-record text (42 MB): the device arrays equal the emulation's (same sources as loops: scans, refinement, compaction
+    at scale) and, on the first 30 000 records, the reference loader's."""
+    import vcf_check
+    from helpers import emul_library
+    text, tl = synth.make_vcf_text(1_000_000, seed=11)
+    raw = text.encode()
+    got, st = engine.lib.vcf_parse(raw, "chr1", tl, 0)
+    want, _ = emul_library().vcf_parse(raw, "chr1", tl, 0)
+    vcf_check.assert_same_side(got, want, "1 M records, device vs emulation")
+    assert st["records"] == 1_000_000 and st["kept"] == got.n > 900_000 and st["launches"] > 10
+    head = "\n".join(text.split("\n", 30_004)[:30_004]) + "\n"
+    assert vcf_check.check_text(engine.lib, head, "chr1", tl, 0, what="first 30 000 records") == "ok"
+    assert vcf_check.check_text(engine.lib, head, "chr1", tl, 1, pass_only=False, what="second sample, all records") == "ok"
