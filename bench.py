@@ -28,6 +28,7 @@ the ranks by variant count (the reference arm evaluates the same pair); `--scali
 pair r of a cohort (same genome layout, different sample seeds).
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -249,6 +250,8 @@ def main():
                     help="do not page-lock the caller's input arrays (vce_host_register): the engine stages them through its own pinned slabs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roc", action="store_true")
+    ap.add_argument("--vcf-records", type=int, default=1_000_000,
+                    help="also time the VCF loader (SURVEY 8f rank 3, vce_vcf_parse) on a synthetic text of this many records; 0 = skip")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     C3_CLUSTERS[0] = args.c3_clusters
@@ -266,7 +269,7 @@ def main():
     # the ranks of one box share its host cores: give every rank's digest / assembly pool its share
     cores = os.cpu_count() or 1
     os.environ.setdefault("VCE_THREADS", str(max(1, cores // max(1, world))))
-    from rtg_tools_b200 import capi, multigpu, vcfeval
+    from rtg_tools_b200 import capi, multigpu, synth, vcfeval
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
@@ -482,6 +485,54 @@ def main():
                     assert np.array_equal(x.view(np.int64), y.view(np.int64)), "ROC rows differ from the oracle"
             roc_heavy["parity"] = "bit-exact vs oracle"
 
+    # ------------------------------------------------------------------ VCF loader, reported beside
+    vcf_load = None
+    if args.vcf_records > 0 and rank == 0:
+        text, vtl = synth.make_vcf_text(args.vcf_records, seed=11, mean_gap=100)
+        raw = np.frombuffer(text.encode(), np.uint8).copy()
+        if not args.no_pin:   # the caller's text buffer page-locked once, like the arrays of the matching path
+            eng.lib.lib.vce_host_register.restype = ctypes.c_int
+            eng.lib.lib.vce_host_register.argtypes = [ctypes.c_void_p, ctypes.c_uint64]
+            eng.lib.lib.vce_host_register(raw.ctypes.data, raw.nbytes)
+        for _ in range(3):
+            eng.lib.vcf_parse(raw, "chr1", vtl, 0)
+        vt = []
+        for _ in range(max(3, args.steps)):
+            t0 = time.perf_counter()
+            side, vst = eng.lib.vcf_parse(raw, "chr1", vtl, 0)
+            vt.append(time.perf_counter() - t0)
+        fields = ("id", "phased", "status_in", "gt", "allele_off", "allele_start", "allele_end", "allele_null", "allele_nt_off", "nt")
+        out_bytes = int(sum(getattr(side, f).nbytes for f in fields))
+        c_abi_ms = vst["h2d_ms"] + vst["kernel_ms"] + vst["d2h_ms"]
+        ach = (int(raw.nbytes) + out_bytes) / (vst["kernel_ms"] * 1e-3) / 1e9
+        vcf_load = {"records": int(vst["records"]), "variants": int(vst["kept"]), "text_bytes": int(raw.nbytes), "output_bytes": out_bytes,
+                    # host text in, host arrays out: H2D + kernels + D2H on the loader's stream (CUDA events); the Python wrapper's
+                    # own array copies are not part of the C-ABI call and are reported separately
+                    "e2e_records_per_s": vst["records"] / (c_abi_ms * 1e-3), "e2e_ms": c_abi_ms,
+                    "h2d_ms": vst["h2d_ms"], "kernel_ms": vst["kernel_ms"], "d2h_ms": vst["d2h_ms"], "gpu_launches": vst["launches"],
+                    "python_call_ms": float(np.mean(vt)) * 1e3,
+                    "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                                 "algorithmic_bytes": "text in + vce_variants arrays out", "peak_source": peak_src}}
+        if not args.no_cpu_baseline:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import vcf_check
+            n_cpu = min(100_000, args.vcf_records)
+            head = "\n".join(text.split("\n", n_cpu + 4)[:n_cpu + 4]) + "\n"
+            t0 = time.perf_counter()
+            want, _ = vcf_check.expected_side(head, "chr1", vtl, 0)
+            dt = time.perf_counter() - t0
+            got, _ = eng.lib.vcf_parse(head.encode(), "chr1", vtl, 0)
+            vcf_check.assert_same_side(got, want, "bench: VCF loader")
+            if not args.no_pin:
+                eng.lib.lib.vce_host_unregister.restype = ctypes.c_int
+                eng.lib.lib.vce_host_unregister.argtypes = [ctypes.c_void_p]
+                eng.lib.lib.vce_host_unregister(raw.ctypes.data)
+            vcf_load["cpu_baseline"] = {"value": n_cpu / dt, "unit": "records/s", "cores": 1, "kind": "port",
+                                        "sample": "the first %d records of the text through oracle/ref_host.py (Python restatement of "
+                                                  "VcfSortRefiner + VcfRecordTabixCallable + SampleVariants + Allele.getAlleles), %.1f s" % (n_cpu, dt),
+                                        "parity": "bit-exact on those records"}
+
     value = total_variants / (ms_per_step * 1e-3)
     out = {
         "metric": "vcfeval variants evaluated/sec", "value": value, "unit": "variants/s", "n_gpus": world, "steps": args.steps,
@@ -504,6 +555,7 @@ def main():
         "cpu_baseline": cpu,
         "roc": roc,
         "roc_heavy": roc_heavy,
+        "vcf_load": vcf_load,
         "summary_counts": [int(x) for x in counts] if counts is not None else None,
         "engine_stats": {k: st[k] for k in ("regions", "escalated", "spilled", "prefix_reruns", "iterations")},
     }

@@ -413,8 +413,13 @@ class Library:
         f_free.restype = None
         f_free.argtypes = [C.c_void_p]
         cin = CVcfIn()
-        cin.text = text
-        cin.text_len = len(text)
+        if isinstance(text, np.ndarray):   # a uint8 array (e.g. one the caller page-locked with vce_host_register)
+            text = np.ascontiguousarray(text, np.uint8)
+            cin.text = C.cast(text.ctypes.data, C.c_char_p)
+            cin.text_len = int(text.nbytes)
+        else:
+            cin.text = text
+            cin.text_len = len(text)
         cin.name = name.encode() if isinstance(name, str) else name
         cin.template_len = int(template_len)
         cin.sample, cin.ploidy, cin.pass_only, cin.max_length = int(sample), int(ploidy), int(bool(pass_only)), int(max_length)

@@ -448,19 +448,19 @@ int vce_roc_timed(const vce_roc_in* in, vce_roc_out* out, double* h2d_ms, double
 namespace {
 // shared by the CUDA library and nothing else: fills the C view of a result
 void vcfView(const vce::VcfResult& R, vce_variants* out) {
-  out->n = (int32_t) R.id.size();
+  out->n = R.n;
   out->gt_ploidy = R.ploidy;
-  out->id = R.id.data();
-  out->phased = R.phased.data();
-  out->status_in = R.statusIn.data();
-  out->gt = R.gt.data();
-  out->allele_off = R.alleleOff.data();
-  out->n_slots = R.alleleOff.empty() ? 0 : R.alleleOff.back();
-  out->allele_start = R.alleleStart.data();
-  out->allele_end = R.alleleEnd.data();
-  out->allele_null = R.alleleNull.data();
-  out->allele_nt_off = R.alleleNtOff.data();
-  out->nt = R.nt.data();
+  out->id = R.id;
+  out->phased = R.phased;
+  out->status_in = R.statusIn;
+  out->gt = R.gt;
+  out->allele_off = R.alleleOff;
+  out->n_slots = R.nSlots;
+  out->allele_start = R.alleleStart;
+  out->allele_end = R.alleleEnd;
+  out->allele_null = R.alleleNull;
+  out->allele_nt_off = R.alleleNtOff;
+  out->nt = R.nt;
 }
 }  // namespace
 

@@ -22,6 +22,41 @@ __global__ void __launch_bounds__(256) k_vcf_for(int n, F f) {
 }
 
 namespace {
+// page-locked result blocks are recycled: pinning memory costs more than the copy it speeds up
+std::mutex g_pinMu;
+std::vector<std::pair<uint8_t*, size_t>> g_pinFree;
+void pinRelease(uint8_t* p, size_t) {
+  std::lock_guard<std::mutex> lk(g_pinMu);
+  // the capacity travels in the 16 bytes before the block
+  const size_t cap = *reinterpret_cast<size_t*>(p - 16);
+  if (g_pinFree.size() < 6) g_pinFree.emplace_back(p, cap);
+  else cudaFreeHost(p - 16);
+}
+uint8_t* pinAcquire(size_t bytes) {
+  {
+    std::lock_guard<std::mutex> lk(g_pinMu);
+    size_t best = g_pinFree.size();
+    for (size_t i = 0; i < g_pinFree.size(); ++i) {
+      if (g_pinFree[i].second >= bytes && (best == g_pinFree.size() || g_pinFree[i].second < g_pinFree[best].second)) best = i;
+    }
+    if (best != g_pinFree.size()) {
+      uint8_t* p = g_pinFree[best].first;
+      g_pinFree.erase(g_pinFree.begin() + (long) best);
+      return p;
+    }
+  }
+  const size_t cap = bytes + bytes / 8 + 4096;
+  uint8_t* raw = nullptr;
+  if (cudaHostAlloc(reinterpret_cast<void**>(&raw), cap + 16, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  *reinterpret_cast<size_t*>(raw) = cap;
+  return raw + 16;
+}
+void pinDrain() {
+  std::lock_guard<std::mutex> lk(g_pinMu);
+  for (auto& e : g_pinFree) cudaFreeHost(e.first - 16);
+  g_pinFree.clear();
+}
+
 struct CudaVcfOps {
   cudaStream_t st = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -83,6 +118,10 @@ struct CudaVcfOps {
     return h;
   }
   void mark(int k) { if (ev[k]) note(cudaEventRecord(ev[k], st)); }
+  uint8_t* hostAlloc(size_t bytes, void (**release)(uint8_t*, size_t)) {
+    *release = &pinRelease;
+    return pinAcquire(bytes);
+  }
 };
 
 struct VcfCtx {
@@ -103,6 +142,7 @@ void vcfRelease() {
   if (o.st) cudaStreamDestroy(o.st);
   o = CudaVcfOps();
   g_vcf.device = -1;
+  pinDrain();
 }
 }  // namespace
 

@@ -59,8 +59,8 @@ struct VcfArrays {
   const uint8_t* text;
   int32_t len;
   VcfConfig cfg;
-  // pass scratch (device / host), sized by the caller: see vcfScratchInts()
-  int32_t* byteScan;       // [len + 1]
+  // pass scratch (device / host), sized by vcfDrive as the counts become known
+  int32_t* byteScan;       // [len / 32 + 2] line starts per 32-byte block, scanned
   int32_t* lineStart;      // [nLines + 1]
   VcfLine* lines;          // [nLines]
   int32_t* streamScan;     // [nLines + 1]
@@ -76,7 +76,8 @@ struct VcfArrays {
   uint8_t* phased;         // [n]
   uint8_t* statusIn;       // [n]
   int8_t* gt;              // [n * ploidy]
-  int32_t* alleleOff;      // [n + 1]
+  int32_t* alleleOff;      // [n + 1] (scan scratch)
+  int32_t* alleleOffOut;   // [n + 1] its copy inside the output block
   int32_t* ntBase;         // [n + 1]
   int32_t* alleleStart;    // [nSlots]
   int32_t* alleleEnd;      // [nSlots]
@@ -371,22 +372,26 @@ VCE_HD void vcfAtomicMin(int32_t* p, int32_t v) {
 #endif
 }
 
-// Bytes of int32 scratch the counting passes need for `len` bytes of text holding at most `maxLines` lines.
-inline size_t vcfScratchBytes(int64_t len, int64_t maxLines) {
-  return (size_t) (len + 1) * 4 + (size_t) (maxLines + 1) * (4 * 8) + (size_t) maxLines * sizeof(VcfLine) + 64;
-}
-
 // ---- passes 1: line starts, parse, stream, refinement, kept / skipped counts.  Fills A.nLines, nStream, n, nSkipped, and
 // per kept variant the slot / base counts scanned into alleleOff / ntBase (both sized n + 1 by the caller AFTER
 // vcfCountLines; see vce_vcf.cu / the emulation for the calling order).
+constexpr int kVcfBlock = 32;   // bytes of text per thread in the line-start passes
+
 template <class Ops>
 int vcfCountLines(Ops& ops, VcfArrays& A) {
   const VcfArrays a = A;
-  ops.parFor(a.len + 1, VCE_VCF_LAMBDA(int i) {
-    a.byteScan[i] = (i < a.len && (i == 0 || a.text[i - 1] == '\n')) ? 1 : 0;
+  const int nb = (a.len + kVcfBlock - 1) / kVcfBlock;
+  // a line starts at byte i when i == 0 or byte i - 1 is a newline: counted per block of 32 bytes, scanned over blocks
+  ops.parFor(nb + 1, VCE_VCF_LAMBDA(int b) {
+    int c = 0;
+    if (b < nb) {
+      const int lo = b * kVcfBlock, hi = lo + kVcfBlock < a.len ? lo + kVcfBlock : a.len;
+      for (int i = lo; i < hi; ++i) c += (i == 0 || a.text[i - 1] == '\n') ? 1 : 0;
+    }
+    a.byteScan[b] = c;
   });
-  ops.exclusiveSum(a.byteScan, a.byteScan, a.len + 1);
-  A.nLines = ops.fetchInt(a.byteScan + a.len);
+  ops.exclusiveSum(a.byteScan, a.byteScan, nb + 1);
+  A.nLines = ops.fetchInt(a.byteScan + nb);
   return A.nLines;
 }
 
@@ -394,8 +399,10 @@ template <class Ops>
 void vcfParsePasses(Ops& ops, VcfArrays& A) {
   const VcfArrays a = A;
   const int nLines = A.nLines;
-  ops.parFor(a.len, VCE_VCF_LAMBDA(int i) {
-    if (i == 0 || a.text[i - 1] == '\n') a.lineStart[a.byteScan[i]] = i;
+  ops.parFor((a.len + kVcfBlock - 1) / kVcfBlock, VCE_VCF_LAMBDA(int b) {
+    int at = a.byteScan[b];
+    const int lo = b * kVcfBlock, hi = lo + kVcfBlock < a.len ? lo + kVcfBlock : a.len;
+    for (int i = lo; i < hi; ++i) if (i == 0 || a.text[i - 1] == '\n') a.lineStart[at++] = i;
   });
   ops.parFor(1, VCE_VCF_LAMBDA(int) { a.lineStart[nLines] = a.len; *a.firstFatal = 0x7fffffff; });
   ops.parFor(nLines + 1, VCE_VCF_LAMBDA(int l) {
@@ -504,6 +511,7 @@ void vcfFillPasses(Ops& ops, VcfArrays& A) {
     vcfFillVariant(a.text + a.lineStart[l], L, ploidy, a.alleleOff[v], a.ntBase[v], a.alleleStart, a.alleleEnd, a.alleleNull,
                    a.alleleNtOff, a.nt);
   });
+  ops.parFor(n + 1, VCE_VCF_LAMBDA(int v) { a.alleleOffOut[v] = a.alleleOff[v]; });
   ops.parFor(1, VCE_VCF_LAMBDA(int) { a.alleleNtOff[nSlots] = nNt; });
 }
 
@@ -513,21 +521,40 @@ struct VcfStats {
   double h2dMs = 0, kernelMs = 0, d2hMs = 0;
   int32_t launches = 0, fatalLine = -1, fatalReason = 0;
 };
-struct VcfResult {   // what vce_vcf_variants hands out: host copies of the arrays, owned by the result
-  int32_t ploidy = 0;
-  std::vector<int32_t> id, alleleOff, alleleStart, alleleEnd, alleleNtOff;
-  std::vector<uint8_t> phased, statusIn, alleleNull, nt;
-  std::vector<int8_t> gt;
+struct VcfResult {   // what vce_vcf_variants hands out: ONE host block (page-locked in the CUDA library) laid out like the device's
+  int32_t ploidy = 0, n = 0, nSlots = 0, nNt = 0;
+  uint8_t* slab = nullptr;
+  size_t slabBytes = 0;
+  void (*release)(uint8_t*, size_t) = nullptr;
+  int32_t *id = nullptr, *alleleOff = nullptr, *alleleStart = nullptr, *alleleEnd = nullptr, *alleleNtOff = nullptr;
+  uint8_t *phased = nullptr, *statusIn = nullptr, *alleleNull = nullptr, *nt = nullptr;
+  int8_t* gt = nullptr;
   VcfStats stats;
+  VcfResult() = default;
+  VcfResult(const VcfResult&) = delete;
+  VcfResult& operator=(const VcfResult&) = delete;
+  ~VcfResult() { if (slab && release) release(slab, slabBytes); }
 };
 
-// Ops: alloc<T>(n) / upload / download / parFor / exclusiveSum / fetchInt / mark(k) (timing marks: 0 before the upload,
+// Offsets of the output arrays within one block (every array 16-byte aligned); the same layout on the device and on the host.
+struct VcfLayout {
+  size_t id, phased, statusIn, gt, alleleOff, alleleStart, alleleEnd, alleleNull, alleleNtOff, nt, total;
+  VcfLayout(size_t n, size_t ploidy, size_t nSlots, size_t nNt) {
+    size_t at = 0;
+    auto take = [&at](size_t bytes) { const size_t o = at; at += (bytes + 15) & ~(size_t) 15; return o; };
+    id = take(n * 4); phased = take(n); statusIn = take(n); gt = take(n * ploidy + 4); alleleOff = take((n + 1) * 4);
+    alleleStart = take(nSlots * 4); alleleEnd = take(nSlots * 4); alleleNull = take(nSlots); alleleNtOff = take((nSlots + 1) * 4);
+    nt = take(nNt + 4);
+    total = at;
+  }
+};
+
+// Ops: alloc<T>(n) / hostAlloc(bytes, &release) / upload / download / parFor / exclusiveSum / fetchInt / mark(k) (timing marks: 0 before the upload,
 // 1 after it, 2 after the last kernel, 3 after the downloads).
 template <class Ops>
 int vcfDrive(Ops& ops, const uint8_t* text, int64_t len, const VcfConfig& cfg, VcfResult& R, std::string& err) {
   if (len < 0 || len >= 0x7ffffff0LL) { err = "VCF text of 2 GB or more: hand it over in pieces (one sequence per call)"; return 1; }
   if (cfg.ploidy < 1 || cfg.ploidy > 4 || cfg.sample < 0) { err = "sample / ploidy out of range"; return 1; }
-  R = VcfResult();
   R.ploidy = cfg.ploidy;
   VcfArrays A;
   std::memset(&A, 0, sizeof(A));
@@ -535,7 +562,7 @@ int vcfDrive(Ops& ops, const uint8_t* text, int64_t len, const VcfConfig& cfg, V
   A.cfg = cfg;
   ops.mark(0);
   uint8_t* dText = ops.template alloc<uint8_t>((size_t) len + 16);
-  A.byteScan = ops.template alloc<int32_t>((size_t) len + 1);
+  A.byteScan = ops.template alloc<int32_t>((size_t) len / kVcfBlock + 4);
   A.firstFatal = ops.template alloc<int32_t>(4);
   if (!dText || !A.byteScan || !A.firstFatal) { err = "out of device memory for the VCF text"; return 2; }
   ops.upload(dText, text, (size_t) len);
@@ -572,38 +599,42 @@ int vcfDrive(Ops& ops, const uint8_t* text, int64_t len, const VcfConfig& cfg, V
   }
   const int n = A.n;
   A.keptPos = ops.template alloc<int32_t>((size_t) n + 1);
-  A.alleleOff = ops.template alloc<int32_t>((size_t) n + 1);
+  int32_t* offScan = ops.template alloc<int32_t>((size_t) n + 1);
   A.ntBase = ops.template alloc<int32_t>((size_t) n + 1);
-  A.id = ops.template alloc<int32_t>((size_t) n + 1);
-  A.phased = ops.template alloc<uint8_t>((size_t) n + 1);
-  A.statusIn = ops.template alloc<uint8_t>((size_t) n + 1);
-  A.gt = ops.template alloc<int8_t>((size_t) n * cfg.ploidy + 4);
-  if (!A.keptPos || !A.alleleOff || !A.ntBase || !A.id || !A.phased || !A.statusIn || !A.gt) { err = "out of device memory for the variants"; return 2; }
+  if (!A.keptPos || !offScan || !A.ntBase) { err = "out of device memory for the variants"; return 2; }
+  A.alleleOff = offScan;
   vcfOffsetPasses(ops, A);
-  A.alleleStart = ops.template alloc<int32_t>((size_t) A.nSlots + 1);
-  A.alleleEnd = ops.template alloc<int32_t>((size_t) A.nSlots + 1);
-  A.alleleNull = ops.template alloc<uint8_t>((size_t) A.nSlots + 1);
-  A.alleleNtOff = ops.template alloc<int32_t>((size_t) A.nSlots + 1);
-  A.nt = ops.template alloc<uint8_t>((size_t) A.nNt + 4);
-  if (!A.alleleStart || !A.alleleEnd || !A.alleleNull || !A.alleleNtOff || !A.nt) { err = "out of device memory for the allele tables"; return 2; }
+  const VcfLayout lay((size_t) n, (size_t) cfg.ploidy, (size_t) A.nSlots, (size_t) A.nNt);
+  uint8_t* dOut = ops.template alloc<uint8_t>(lay.total + 16);
+  if (!dOut) { err = "out of device memory for the allele tables"; return 2; }
+  A.id = reinterpret_cast<int32_t*>(dOut + lay.id);
+  A.phased = dOut + lay.phased;
+  A.statusIn = dOut + lay.statusIn;
+  A.gt = reinterpret_cast<int8_t*>(dOut + lay.gt);
+  A.alleleOffOut = reinterpret_cast<int32_t*>(dOut + lay.alleleOff);
+  A.alleleStart = reinterpret_cast<int32_t*>(dOut + lay.alleleStart);
+  A.alleleEnd = reinterpret_cast<int32_t*>(dOut + lay.alleleEnd);
+  A.alleleNull = dOut + lay.alleleNull;
+  A.alleleNtOff = reinterpret_cast<int32_t*>(dOut + lay.alleleNtOff);
+  A.nt = dOut + lay.nt;
   vcfFillPasses(ops, A);
   ops.mark(2);
-  R.id.resize((size_t) n); R.phased.resize((size_t) n); R.statusIn.resize((size_t) n); R.gt.resize((size_t) n * cfg.ploidy);
-  R.alleleOff.resize((size_t) n + 1);
-  R.alleleStart.resize((size_t) A.nSlots); R.alleleEnd.resize((size_t) A.nSlots); R.alleleNull.resize((size_t) A.nSlots);
-  R.alleleNtOff.resize((size_t) A.nSlots + 1);
-  R.nt.resize((size_t) A.nNt);
-  ops.download(R.id.data(), A.id, (size_t) n * 4);
-  ops.download(R.phased.data(), A.phased, (size_t) n);
-  ops.download(R.statusIn.data(), A.statusIn, (size_t) n);
-  ops.download(R.gt.data(), A.gt, (size_t) n * cfg.ploidy);
-  ops.download(R.alleleOff.data(), A.alleleOff, ((size_t) n + 1) * 4);
-  ops.download(R.alleleStart.data(), A.alleleStart, (size_t) A.nSlots * 4);
-  ops.download(R.alleleEnd.data(), A.alleleEnd, (size_t) A.nSlots * 4);
-  ops.download(R.alleleNull.data(), A.alleleNull, (size_t) A.nSlots);
-  ops.download(R.alleleNtOff.data(), A.alleleNtOff, ((size_t) A.nSlots + 1) * 4);
-  ops.download(R.nt.data(), A.nt, (size_t) A.nNt);
+  R.slab = ops.hostAlloc(lay.total + 16, &R.release);
+  R.slabBytes = lay.total + 16;
+  if (!R.slab) { err = "out of host memory for the result"; return 2; }
+  ops.download(R.slab, dOut, lay.total);
   ops.mark(3);
+  R.n = n; R.nSlots = A.nSlots; R.nNt = A.nNt;
+  R.id = reinterpret_cast<int32_t*>(R.slab + lay.id);
+  R.phased = R.slab + lay.phased;
+  R.statusIn = R.slab + lay.statusIn;
+  R.gt = reinterpret_cast<int8_t*>(R.slab + lay.gt);
+  R.alleleOff = reinterpret_cast<int32_t*>(R.slab + lay.alleleOff);
+  R.alleleStart = reinterpret_cast<int32_t*>(R.slab + lay.alleleStart);
+  R.alleleEnd = reinterpret_cast<int32_t*>(R.slab + lay.alleleEnd);
+  R.alleleNull = R.slab + lay.alleleNull;
+  R.alleleNtOff = reinterpret_cast<int32_t*>(R.slab + lay.alleleNtOff);
+  R.nt = R.slab + lay.nt;
   R.stats.kept = n;
   return 0;
 }

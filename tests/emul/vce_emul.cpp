@@ -604,6 +604,13 @@ struct HostVcfOps {
   void exclusiveSum(int32_t* in, int32_t* out, int n) { int32_t acc = 0; for (int i = 0; i < n; ++i) { const int32_t v = in[i]; out[i] = acc; acc += v; } }
   int fetchInt(const int32_t* p) { return *p; }
   void mark(int) {}
+  static void hostFree(uint8_t* p, size_t) { delete[] p; }
+  uint8_t* hostAlloc(size_t bytes, void (**release)(uint8_t*, size_t)) {
+    *release = &hostFree;
+    uint8_t* p = new uint8_t[bytes];
+    std::memset(p, 0xcd, bytes);
+    return p;
+  }
 };
 std::string g_vcfErr;
 }  // namespace
@@ -631,13 +638,13 @@ int emul_vce_vcf_parse(const vce_vcf_in* in, void** result) {
 const char* emul_vce_vcf_error() { return g_vcfErr.c_str(); }
 int emul_vce_vcf_variants(const void* result, vce_variants* out, vce_vcf_stats* stats) {
   const vce::VcfResult& R = *static_cast<const vce::VcfResult*>(result);
-  out->n = (int32_t) R.id.size();
+  out->n = R.n;
   out->gt_ploidy = R.ploidy;
-  out->id = R.id.data(); out->phased = R.phased.data(); out->status_in = R.statusIn.data(); out->gt = R.gt.data();
-  out->allele_off = R.alleleOff.data();
-  out->n_slots = R.alleleOff.empty() ? 0 : R.alleleOff.back();
-  out->allele_start = R.alleleStart.data(); out->allele_end = R.alleleEnd.data(); out->allele_null = R.alleleNull.data();
-  out->allele_nt_off = R.alleleNtOff.data(); out->nt = R.nt.data();
+  out->id = R.id; out->phased = R.phased; out->status_in = R.statusIn; out->gt = R.gt;
+  out->allele_off = R.alleleOff;
+  out->n_slots = R.nSlots;
+  out->allele_start = R.alleleStart; out->allele_end = R.alleleEnd; out->allele_null = R.alleleNull;
+  out->allele_nt_off = R.alleleNtOff; out->nt = R.nt;
   if (stats) {
     std::memset(stats, 0, sizeof(*stats));
     stats->lines = R.stats.lines; stats->records = R.stats.records; stats->kept = R.stats.kept; stats->skipped = R.stats.skipped;
