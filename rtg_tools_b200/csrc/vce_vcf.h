@@ -58,7 +58,8 @@ struct VcfArrays {
   // inputs
   const uint8_t* text;
   int32_t len;
-  VcfConfig cfg;
+  VcfConfig cfg;            // host copy
+  const VcfConfig* dCfg;    // the same where the passes run (read through a pointer: a by-value copy would sit on every thread's stack)
   // pass scratch (device / host), sized by vcfDrive as the counts become known
   int32_t* byteScan;       // [len / 32 + 2] line starts per 32-byte block, scanned
   int32_t* lineStart;      // [nLines + 1]
@@ -142,8 +143,7 @@ VCE_HD int vcfCount(const uint8_t* s, int n, uint8_t sep) {
 
 // ------------------------------------------------------------------------------------------------ one record
 // Everything the loader decides about one line; the allele bytes themselves are written by vcfFillVariant.
-VCE_HDN VcfLine vcfParseLine(const uint8_t* t, int a, int b, const VcfConfig& cfg) {
-  VcfLine L;
+VCE_HDN void vcfParseLine(const uint8_t* t, int a, int b, const VcfConfig& cfg, VcfLine& L) {
   L.start = L.end = 0; L.nAlt = 0; L.ntBytes = 0;
   L.gt[0] = L.gt[1] = L.gt[2] = L.gt[3] = -2;
   L.kind = VK_NOT_STREAM; L.fatal = VF_NONE; L.phased = 0; L.pad = 0;
@@ -151,7 +151,7 @@ VCE_HDN VcfLine vcfParseLine(const uint8_t* t, int a, int b, const VcfConfig& cf
   if (b > a && t[b - 1] == '\r') --b;
   bool blank = true;
   for (int i = a; i < b; ++i) if (t[i] != ' ' && t[i] != '\t') { blank = false; break; }
-  if (blank || t[a] == '#') return L;
+  if (blank || t[a] == '#') return;
   // fields: 0 CHROM 1 POS 3 REF 4 ALT 6 FILTER 8 FORMAT 9+sample
   int fo[7], fl[7];
   for (int q = 0; q < 7; ++q) { fo[q] = 0; fl[q] = -1; }
@@ -165,19 +165,19 @@ VCE_HDN VcfLine vcfParseLine(const uint8_t* t, int a, int b, const VcfConfig& cf
     }
   }
   const int nFields = field;
-  if (cfg.nameLen > 0 && !vcfEq(t + fo[0], fl[0] < 0 ? 0 : fl[0], cfg.name, cfg.nameLen)) return L;   // another sequence's record
+  if (cfg.nameLen > 0 && !vcfEq(t + fo[0], fl[0] < 0 ? 0 : fl[0], cfg.name, cfg.nameLen)) return;   // another sequence's record
   L.kind = VK_IGNORED;
-  if (nFields < 8) { L.kind = VK_FATAL; L.fatal = VF_FIELDS; return L; }
+  if (nFields < 8) { L.kind = VK_FATAL; L.fatal = VF_FIELDS; return; }
   // POS
   {
     long v = 0;
-    if (fl[1] <= 0 || fl[1] > 10) { L.kind = VK_FATAL; L.fatal = VF_POS; return L; }
+    if (fl[1] <= 0 || fl[1] > 10) { L.kind = VK_FATAL; L.fatal = VF_POS; return; }
     for (int i = 0; i < fl[1]; ++i) {
       const int c = t[fo[1] + i];
-      if (c < '0' || c > '9') { L.kind = VK_FATAL; L.fatal = VF_POS; return L; }
+      if (c < '0' || c > '9') { L.kind = VK_FATAL; L.fatal = VF_POS; return; }
       v = v * 10 + (c - '0');
     }
-    if (v > 0x7fffffffL) { L.kind = VK_FATAL; L.fatal = VF_POS; return L; }
+    if (v > 0x7fffffffL) { L.kind = VK_FATAL; L.fatal = VF_POS; return; }
     L.start = (int32_t) v - 1;
   }
   const uint8_t* ref = t + fo[2];
@@ -197,9 +197,9 @@ VCE_HDN VcfLine vcfParseLine(const uint8_t* t, int a, int b, const VcfConfig& cf
     vcfNth(alt, altLen, ',', k, &o, &l);
     longest = l > longest ? l : longest;
   }
-  if (cfg.maxLength > -1 && longest > cfg.maxLength) { L.kind = VK_SKIPPED; return L; }
+  if (cfg.maxLength > -1 && longest > cfg.maxLength) { L.kind = VK_SKIPPED; return; }
   // loader filter 2: beyond the template (:107-112)
-  if (cfg.templateLen >= 0 && L.end > cfg.templateLen) { L.kind = VK_SKIPPED; return L; }
+  if (cfg.templateLen >= 0 && L.end > cfg.templateLen) { L.kind = VK_SKIPPED; return; }
   // ---- SampleVariants.variant (VariantFactory.java:127-147)
   const uint8_t* fmt = t + fo[5];
   const int fmtLen = fl[5] < 0 ? 0 : fl[5];
@@ -221,15 +221,15 @@ VCE_HDN VcfLine vcfParseLine(const uint8_t* t, int a, int b, const VcfConfig& cf
   if (cfg.passOnly) {
     const uint8_t* fil = t + fo[4];
     const int filLen = fl[4];
-    if (!(filLen == 1 && fil[0] == '.') && vcfListFails(fil, filLen)) return L;     // FILTER not PASS
+    if (!(filLen == 1 && fil[0] == '.') && vcfListFails(fil, filLen)) return;     // FILTER not PASS
     if (ftKey >= 0 && cfg.sample < nSamples) {                                       // sample FT
       int o = 0, l = 0;
-      if (vcfNth(smp, smpLen, ':', ftKey, &o, &l) && vcfListFails(smp + o, l)) return L;
+      if (vcfNth(smp, smpLen, ':', ftKey, &o, &l) && vcfListFails(smp + o, l)) return;
     }
   }
   // getDefinedVariantGt :163-196
-  if (cfg.sample >= nSamples) { L.kind = VK_FATAL; L.fatal = VF_SAMPLES; return L; }
-  if (gtKey < 0) return L;
+  if (cfg.sample >= nSamples) { L.kind = VK_FATAL; L.fatal = VF_SAMPLES; return; }
+  if (gtKey < 0) return;
   int go = 0, gl = 1;
   const uint8_t dot = '.';   // a sample with fewer sub-fields than FORMAT has keys reads as missing
   const uint8_t* gts = &dot;
@@ -245,11 +245,11 @@ VCE_HDN VcfLine vcfParseLine(const uint8_t* t, int a, int b, const VcfConfig& cf
         const int m = i - x0;
         int v = -1;
         if (!(m == 1 && gts[x0] == '.')) {
-          if (m <= 0 || m > 6) { L.kind = VK_FATAL; L.fatal = VF_GT; return L; }
+          if (m <= 0 || m > 6) { L.kind = VK_FATAL; L.fatal = VF_GT; return; }
           v = 0;
           for (int q = 0; q < m; ++q) {
             const int c = gts[x0 + q];
-            if (c < '0' || c > '9') { L.kind = VK_FATAL; L.fatal = VF_GT; return L; }
+            if (c < '0' || c > '9') { L.kind = VK_FATAL; L.fatal = VF_GT; return; }
             v = v * 10 + (c - '0');
           }
         }
@@ -259,13 +259,13 @@ VCE_HDN VcfLine vcfParseLine(const uint8_t* t, int a, int b, const VcfConfig& cf
       }
     }
   }
-  for (int q = 0; q < ng && q < 4; ++q) if (gt[q] > nAlt) { L.kind = VK_FATAL; L.fatal = VF_GT_RANGE; return L; }
+  for (int q = 0; q < ng && q < 4; ++q) if (gt[q] > nAlt) { L.kind = VK_FATAL; L.fatal = VF_GT_RANGE; return; }
   if (ng > 4) {   // more alleles than the ABI's gt[] holds: cannot be the expected ploidy (<= 4) either
     L.kind = VK_SKIPPED;
-    return L;
+    return;
   }
   if (cfg.ploidy == 2 && ng == 1) { gt[1] = gt[0]; ng = 2; }
-  if (ng != cfg.ploidy) { L.kind = VK_SKIPPED; return L; }   // SkippedVariantException: counted
+  if (ng != cfg.ploidy) { L.kind = VK_SKIPPED; return; }   // SkippedVariantException: counted
   // allele strings (VcfUtils.getAlleleStrings :806-828): padding base removed when every non-'*' ALT starts with REF's first base
   bool pad = false;
   {
@@ -294,7 +294,7 @@ VCE_HDN VcfLine vcfParseLine(const uint8_t* t, int a, int b, const VcfConfig& cf
     const int sn = l - (strip ? 1 : 0);
     bool eq = sn == r0n;
     for (int q = 0; eq && q < sn; ++q) if (s[q] != r0[q]) eq = false;
-    if (eq) { L.kind = VK_FATAL; L.fatal = VF_ALT_IS_REF; return L; }
+    if (eq) { L.kind = VK_FATAL; L.fatal = VF_ALT_IS_REF; return; }
   }
   bool defined = false;   // some GT allele > 0 is a non-SV variant (VariantType.getType(String,String) :169-190)
   for (int q = 0; q < ng && !defined; ++q) {
@@ -307,8 +307,8 @@ VCE_HDN VcfLine vcfParseLine(const uint8_t* t, int a, int b, const VcfConfig& cf
     const bool snp = r0n == 1 && sn == 1 && s[0] != '*';
     if (snp || !vcfIsSym(s, sn)) defined = true;
   }
-  if (!defined) return L;
-  for (int q = 0; q < ng; ++q) if (gt[q] > 127) { L.kind = VK_FATAL; L.fatal = VF_GT_WIDE; return L; }
+  if (!defined) return;
+  for (int q = 0; q < ng; ++q) if (gt[q] > 127) { L.kind = VK_FATAL; L.fatal = VF_GT_WIDE; return; }
   // Allele.getAlleles :145-192: REF and the GT's alleles; symbolic ones are null; an illegal base skips the record
   int ntBytes = 0;
   for (int id = 0; id <= nAlt; ++id) {
@@ -325,14 +325,14 @@ VCE_HDN VcfLine vcfParseLine(const uint8_t* t, int a, int b, const VcfConfig& cf
     }
     if (vcfIsSym(s, sn)) continue;
     const int from = pad ? 1 : 0;
-    for (int q = from; q < sn; ++q) if (vcfBaseCode(s[q]) < 0) { L.kind = VK_SKIPPED; return L; }
+    for (int q = from; q < sn; ++q) if (vcfBaseCode(s[q]) < 0) { L.kind = VK_SKIPPED; return; }
     ntBytes += sn > from ? sn - from : 0;
   }
   L.ntBytes = ntBytes;
   for (int q = 0; q < ng; ++q) L.gt[q] = (int8_t) gt[q];
   L.phased = phased ? 1 : 0;
   L.kind = VK_KEPT;
-  return L;
+  return;
 }
 
 // The allele table of one kept variant (slot 0 = the missing allele, slot 1 = REF, slot k + 1 = ALT k).
@@ -409,8 +409,8 @@ void vcfParsePasses(Ops& ops, VcfArrays& A) {
     if (l == nLines) { a.streamScan[l] = 0; return; }
     int e = a.lineStart[l + 1];
     if (e > a.lineStart[l] && a.text[e - 1] == '\n') --e;
-    const VcfLine L = vcfParseLine(a.text, a.lineStart[l], e, a.cfg);
-    a.lines[l] = L;
+    VcfLine& L = a.lines[l];
+    vcfParseLine(a.text, a.lineStart[l], e, *a.dCfg, L);
     a.streamScan[l] = L.kind != VK_NOT_STREAM ? 1 : 0;
     if (L.kind == VK_FATAL) vcfAtomicMin(a.firstFatal, l);
   });
@@ -567,6 +567,10 @@ int vcfDrive(Ops& ops, const uint8_t* text, int64_t len, const VcfConfig& cfg, V
   if (!dText || !A.byteScan || !A.firstFatal) { err = "out of device memory for the VCF text"; return 2; }
   ops.upload(dText, text, (size_t) len);
   A.text = dText;
+  VcfConfig* dCfg = ops.template alloc<VcfConfig>(1);
+  if (!dCfg) { err = "out of device memory for the VCF text"; return 2; }
+  ops.upload(dCfg, &A.cfg, sizeof(VcfConfig));
+  A.dCfg = dCfg;
   ops.mark(1);
   const int nLines = vcfCountLines(ops, A);
   A.lineStart = ops.template alloc<int32_t>((size_t) nLines + 1);
