@@ -293,6 +293,58 @@ int  vce_vcf_parse(const vce_vcf_in* in, void** result);
 int  vce_vcf_variants(const void* result, vce_variants* out, vce_vcf_stats* stats);
 void vce_vcf_free(void* result);
 
+/*
+ * SURVEY.md 8(f) rank 4 -- the on-disk formats either side of the loader, decoded on the device.
+ *
+ * BGZF (`bgzip`ped VCF and its .tbi): the reference reads it through htsjdk's BlockCompressedInputStream (sam-rtg jar,
+ * third party) from TabixLineReader / BlockCompressedLineReader (src/com/rtg/tabix/TabixLineReader.java,
+ * BlockCompressedLineReader.java:58-133); restated from SAM spec 4.1, RFC 1952 and RFC 1951.  `data` holds the bytes of
+ * the file; a virtual offset is (offset of a BGZF member << 16) | offset within that member's text
+ * (src/com/rtg/tabix/VirtualOffsets.java); voffset_end < 0 = to the end of the file.  One BGZF member per warp.  A corrupt
+ * member ends the call with VCE_ERR_BAD_ARGUMENT (vce_last_error names its offset and what zlib would have said);
+ * check_crc != 0 also verifies every member's CRC32 on the device (htsjdk's default is not to).
+ */
+typedef struct vce_bgzf_stats {
+  int64_t blocks, compressed_bytes, text_bytes;
+  double  h2d_ms, kernel_ms, d2h_ms;          /* CUDA events on the loader's stream */
+  int32_t launches;
+  int32_t reserved;
+} vce_bgzf_stats;
+/* Host only: bytes of text between the two virtual offsets (sum of the members' ISIZE fields). */
+int vce_bgzf_text_size(const uint8_t* data, int64_t len, int64_t voffset_begin, int64_t voffset_end, int64_t* text_len);
+/* The text between the two virtual offsets into `text` (VCE_ERR_CAPACITY and *text_len = bytes needed when it is too small). */
+int vce_bgzf_inflate(const uint8_t* data, int64_t len, int64_t voffset_begin, int64_t voffset_end, int32_t check_crc,
+                     uint8_t* text, int64_t text_cap, int64_t* text_len, vce_bgzf_stats* stats);
+/* vce_vcf_parse on block-compressed input: in->text / in->text_len are the bytes of the .vcf.gz; the members are inflated and
+   the records parsed without the text leaving the device.  Results as for vce_vcf_parse; stats->kernel_ms covers both. */
+int vce_vcf_parse_bgzf(const vce_vcf_in* in, int64_t voffset_begin, int64_t voffset_end, int32_t check_crc, void** result,
+                       vce_bgzf_stats* stats);
+
+/*
+ * Tabix index (TabixIndexReader.java:63-146): the .tbi bytes are inflated on the device, the small tables stay with the host.
+ * vce_tabix_info: out = { sequences, format, seq column, begin column, end column (0-based, -1 = none), meta, skip }.
+ * vce_tabix_query = AbstractIndexReader.getFilePointers for one interval [begin0, end0) of `name` (0-based, end exclusive;
+ * -1 = open), AbstractIndexReader.java:102-205: the virtual offsets that bracket the region's records, or -1 / -1 when the
+ * index holds nothing for it (the reference returns null).
+ */
+int  vce_tabix_open(const uint8_t* tbi, int64_t len, void** index);
+int  vce_tabix_info(const void* index, int32_t out[7]);
+const char* vce_tabix_name(const void* index, int32_t i);
+int  vce_tabix_query(const void* index, const char* name, int32_t begin0, int32_t end0, int64_t* voffset_begin, int64_t* voffset_end);
+void vce_tabix_close(void* index);
+
+/*
+ * SDF sequence data straight into a resident template (replaces CompressedMemorySequencesReader's load of one sequence +
+ * vce_template_register): `seqdata` = the bytes of the SDF's seqdataN file written by BitwiseByteArray.dumpCompressedValues
+ * (src/com/rtg/util/bytecompression/BitwiseByteArray.java:426-439; read back by FileBitwiseInputStream.java:151-169): per
+ * 64 residues three big-endian 64-bit bit planes.  first_residue = the sequence's start within the file (seqpointerN),
+ * len = its length.  bases_out[len] receives the byte-per-base array (0 = N, 1..4 = A C G T) that vce_sequence.template_bases
+ * points at; the 2-bit copy stays on every device of the pool, registered under that pointer.  ms3 (optional): H2D, kernel,
+ * D2H milliseconds of the last device.
+ */
+int vce_template_register_sdf(const uint8_t* seqdata, int64_t seqdata_len, int64_t first_residue, int32_t len, uint8_t* bases_out,
+                              double* ms3);
+
 /* Formats the reference's warning text (PathFinder.java:163). Returns bytes written (excluding NUL). */
 int vce_format_warning(const vce_warning* w, const char* seq_name, char* buf, int32_t cap);
 

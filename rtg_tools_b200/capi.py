@@ -72,6 +72,14 @@ class CVcfStats(C.Structure):
     ]
 
 
+class CBgzfStats(C.Structure):
+    _fields_ = [
+        ("blocks", C.c_int64), ("compressed_bytes", C.c_int64), ("text_bytes", C.c_int64),
+        ("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("d2h_ms", C.c_double),
+        ("launches", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
 class CSequence(C.Structure):
     _fields_ = [
         ("name", C.c_char_p), ("template_bases", _u8p), ("template_len", C.c_int32),
@@ -398,43 +406,42 @@ class Library:
             return f(C.byref(ccfg), len(results), cseqs, cres, threads)
         return self._submit(C.byref(ccfg), len(results), cseqs, cres)
 
-    def vcf_parse(self, text: bytes, name=None, template_len=-1, sample=0, ploidy=2, pass_only=True, max_length=1000):
-        """vce_vcf_parse: the records of sequence `name` in VCF `text` as a VariantSide (copies) plus the loader's counters
-        {"lines", "records", "kept", "skipped", "h2d_ms", "kernel_ms", "d2h_ms", "launches"}.  Raises ValueError on a record
-        the reference would throw VcfFormatException for."""
+    def _loader_error(self, rc, what):
         pre = "vce_" if self.prefix == "vce_" else self.prefix + "vce_"
-        f_parse = getattr(self.lib, pre + "vcf_parse")
+        if self.prefix == "vce_":
+            msg = self.last_error()
+        else:
+            e = getattr(self.lib, pre + "vcf_error")
+            e.restype = C.c_char_p
+            msg = e().decode()
+        if rc == 2:   # VCE_ERR_BAD_ARGUMENT: a format error in the input
+            raise ValueError(msg)
+        raise RuntimeError("%s failed: %s %s" % (what, ERR_NAMES.get(rc, rc), msg))
+
+    @staticmethod
+    def _bytes_arg(data):
+        """(keep-alive object, char pointer, length) of bytes or a uint8 array (e.g. one page-locked with vce_host_register)."""
+        if isinstance(data, np.ndarray):
+            data = np.ascontiguousarray(data, np.uint8)
+            return data, C.cast(data.ctypes.data, C.c_char_p), int(data.nbytes)
+        return data, C.cast(C.c_char_p(data), C.c_char_p), len(data)
+
+    def _vcf_in(self, text, name, template_len, sample, ploidy, pass_only, max_length):
+        cin = CVcfIn()
+        keep, cin.text, cin.text_len = self._bytes_arg(text)
+        cin.name = name.encode() if isinstance(name, str) else name
+        cin.template_len = int(template_len)
+        cin.sample, cin.ploidy, cin.pass_only, cin.max_length = int(sample), int(ploidy), int(bool(pass_only)), int(max_length)
+        return cin, keep
+
+    def _vcf_result(self, handle):
+        pre = "vce_" if self.prefix == "vce_" else self.prefix + "vce_"
         f_get = getattr(self.lib, pre + "vcf_variants")
         f_free = getattr(self.lib, pre + "vcf_free")
-        f_parse.restype = C.c_int
-        f_parse.argtypes = [C.POINTER(CVcfIn), C.POINTER(C.c_void_p)]
         f_get.restype = C.c_int
         f_get.argtypes = [C.c_void_p, C.POINTER(CVariants), C.POINTER(CVcfStats)]
         f_free.restype = None
         f_free.argtypes = [C.c_void_p]
-        cin = CVcfIn()
-        if isinstance(text, np.ndarray):   # a uint8 array (e.g. one the caller page-locked with vce_host_register)
-            text = np.ascontiguousarray(text, np.uint8)
-            cin.text = C.cast(text.ctypes.data, C.c_char_p)
-            cin.text_len = int(text.nbytes)
-        else:
-            cin.text = text
-            cin.text_len = len(text)
-        cin.name = name.encode() if isinstance(name, str) else name
-        cin.template_len = int(template_len)
-        cin.sample, cin.ploidy, cin.pass_only, cin.max_length = int(sample), int(ploidy), int(bool(pass_only)), int(max_length)
-        handle = C.c_void_p()
-        rc = f_parse(C.byref(cin), C.byref(handle))
-        if rc != 0:
-            if self.prefix == "vce_":
-                msg = self.last_error()
-            else:
-                e = getattr(self.lib, pre + "vcf_error")
-                e.restype = C.c_char_p
-                msg = e().decode()
-            if rc == 2:   # VCE_ERR_BAD_ARGUMENT: a format error in the text
-                raise ValueError(msg)
-            raise RuntimeError("vcf_parse failed: %s %s" % (ERR_NAMES.get(rc, rc), msg))
         try:
             cv, st = CVariants(), CVcfStats()
             rc = f_get(handle, C.byref(cv), C.byref(st))
@@ -456,6 +463,118 @@ class Library:
         finally:
             f_free(handle)
         return side, stats
+
+    def vcf_parse(self, text: bytes, name=None, template_len=-1, sample=0, ploidy=2, pass_only=True, max_length=1000):
+        """vce_vcf_parse: the records of sequence `name` in VCF `text` as a VariantSide (copies) plus the loader's counters
+        {"lines", "records", "kept", "skipped", "h2d_ms", "kernel_ms", "d2h_ms", "launches"}.  Raises ValueError on a record
+        the reference would throw VcfFormatException for."""
+        pre = "vce_" if self.prefix == "vce_" else self.prefix + "vce_"
+        f_parse = getattr(self.lib, pre + "vcf_parse")
+        f_parse.restype = C.c_int
+        f_parse.argtypes = [C.POINTER(CVcfIn), C.POINTER(C.c_void_p)]
+        cin, keep = self._vcf_in(text, name, template_len, sample, ploidy, pass_only, max_length)
+        handle = C.c_void_p()
+        rc = f_parse(C.byref(cin), C.byref(handle))
+        del keep
+        if rc != 0:
+            self._loader_error(rc, "vcf_parse")
+        return self._vcf_result(handle)
+
+    # ---- on-disk formats (SURVEY 8f rank 4): BGZF members, tabix index, SDF sequence data
+    def bgzf_text_size(self, data, voffset_begin=0, voffset_end=-1):
+        pre = "vce_" if self.prefix == "vce_" else self.prefix + "vce_"
+        f = getattr(self.lib, pre + "bgzf_text_size")
+        f.restype = C.c_int
+        f.argtypes = [C.c_char_p, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_int64)]
+        keep, ptr, n = self._bytes_arg(data)
+        out = C.c_int64(0)
+        rc = f(ptr, n, int(voffset_begin), int(voffset_end), C.byref(out))
+        if rc != 0:
+            self._loader_error(rc, "bgzf_text_size")
+        return int(out.value)
+
+    def bgzf_inflate(self, data, voffset_begin=0, voffset_end=-1, check_crc=True):
+        """vce_bgzf_inflate: the text between two virtual offsets of a BGZF file (bytes), plus the decoder's counters."""
+        pre = "vce_" if self.prefix == "vce_" else self.prefix + "vce_"
+        size = self.bgzf_text_size(data, voffset_begin, voffset_end)
+        f = getattr(self.lib, pre + "bgzf_inflate")
+        f.restype = C.c_int
+        f.argtypes = [C.c_char_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, _u8p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(CBgzfStats)]
+        keep, ptr, n = self._bytes_arg(data)
+        out = np.zeros(max(size, 1), np.uint8)
+        got, st = C.c_int64(0), CBgzfStats()
+        rc = f(ptr, n, int(voffset_begin), int(voffset_end), int(bool(check_crc)), out.ctypes.data_as(_u8p), size, C.byref(got), C.byref(st))
+        if rc != 0:
+            self._loader_error(rc, "bgzf_inflate")
+        stats = {k: getattr(st, k) for k in ("blocks", "compressed_bytes", "text_bytes", "h2d_ms", "kernel_ms", "d2h_ms", "launches")}
+        return out[:int(got.value)].tobytes(), stats
+
+    def vcf_parse_bgzf(self, data, voffset_begin=0, voffset_end=-1, name=None, template_len=-1, sample=0, ploidy=2, pass_only=True,
+                       max_length=1000, check_crc=True):
+        """vce_vcf_parse_bgzf: vcf_parse on the bytes of a .vcf.gz, between two virtual offsets (e.g. from tabix_open(...).query)."""
+        pre = "vce_" if self.prefix == "vce_" else self.prefix + "vce_"
+        f = getattr(self.lib, pre + "vcf_parse_bgzf")
+        f.restype = C.c_int
+        f.argtypes = [C.POINTER(CVcfIn), C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(CBgzfStats)]
+        cin, keep = self._vcf_in(data, name, template_len, sample, ploidy, pass_only, max_length)
+        handle, st = C.c_void_p(), CBgzfStats()
+        rc = f(C.byref(cin), int(voffset_begin), int(voffset_end), int(bool(check_crc)), C.byref(handle), C.byref(st))
+        del keep
+        if rc != 0:
+            self._loader_error(rc, "vcf_parse_bgzf")
+        side, stats = self._vcf_result(handle)
+        for k in ("blocks", "compressed_bytes", "text_bytes"):
+            stats[k] = getattr(st, k)
+        if self.prefix == "vce_":
+            for k in ("h2d_ms", "kernel_ms", "d2h_ms", "launches"):
+                stats[k] = getattr(st, k)
+        return side, stats
+
+    def tabix_open(self, tbi: bytes):
+        """vce_tabix_open: a TabixIndex (names, options, query) over the bytes of a .tbi file."""
+        return TabixIndex(self, tbi)
+
+    def template_register_sdf(self, seqdata, first_residue, length):
+        """vce_template_register_sdf (product library): decodes one sequence of an SDF seqdata file on the device, keeps the 2-bit
+        copy resident and returns the byte-per-base array (the template_bases to hand to submit; keep it alive)."""
+        f = self._sym("template_register_sdf")
+        f.restype = C.c_int
+        f.argtypes = [C.c_char_p, C.c_int64, C.c_int64, C.c_int32, _u8p, C.POINTER(C.c_double)]
+        keep, ptr, n = self._bytes_arg(seqdata)
+        bases = np.zeros(int(length), np.uint8)
+        ms = (C.c_double * 3)()
+        rc = f(ptr, n, int(first_residue), int(length), bases.ctypes.data_as(_u8p), ms)
+        if rc != 0:
+            self._loader_error(rc, "template_register_sdf")
+        self.last_sdf_ms = tuple(ms)
+        return bases
+
+    def sdf_decode(self, seqdata, first_residue, length):
+        """Emulation only: (bases, packed words, N mask) made by the SDF granule / mask pass bodies."""
+        f = getattr(self.lib, self.prefix + "vce_sdf_decode")
+        f.restype = C.c_int
+        _u32p = C.POINTER(C.c_uint32)
+        f.argtypes = [C.c_char_p, C.c_int64, C.c_int64, C.c_int32, _u8p, _u32p, _u32p]
+        keep, ptr, n = self._bytes_arg(seqdata)
+        length = int(length)
+        words = (length + 15) // 16
+        bases, packed, nmask = np.zeros(length, np.uint8), np.zeros(words + 1, np.uint32), np.zeros((words + 31) // 32 + 1, np.uint32)
+        rc = f(ptr, n, int(first_residue), length, bases.ctypes.data_as(_u8p), packed.ctypes.data_as(_u32p), nmask.ctypes.data_as(_u32p))
+        if rc != 0:
+            raise ValueError("sdf_decode: %s" % ERR_NAMES.get(rc, rc))
+        return bases, packed[:words], nmask[:(words + 31) // 32]
+
+    def pack_template(self, bases):
+        """Emulation only: packTemplate (the host packing vce_template_register uses) for comparison with sdf_decode."""
+        f = getattr(self.lib, self.prefix + "vce_pack_template")
+        f.restype = C.c_int
+        _u32p = C.POINTER(C.c_uint32)
+        f.argtypes = [_u8p, C.c_int32, _u32p, _u32p]
+        bases = np.ascontiguousarray(bases, np.uint8)
+        words = (bases.size + 15) // 16
+        packed, nmask = np.zeros(words + 1, np.uint32), np.zeros((words + 31) // 32 + 1, np.uint32)
+        f(bases.ctypes.data_as(_u8p), int(bases.size), packed.ctypes.data_as(_u32p), nmask.ctypes.data_as(_u32p))
+        return packed[:words], nmask[:(words + 31) // 32]
 
     def roc(self, score, tp, fp, tp_raw, filter_mask=None, n_filters=1, ascending=False, timed=False):
         """Returns (rows per filter: list of (threshold, cum_tp, cum_fp, cum_tp_raw) arrays, no_score count).
@@ -506,3 +625,56 @@ class Library:
             s = f * cap
             rows.append((thr[s:s + k].copy(), ctp[s:s + k].copy(), cfp[s:s + k].copy(), craw[s:s + k].copy()))
         return rows, int(no_score[0])
+
+
+class TabixIndex:
+    """TabixIndexReader (src/com/rtg/tabix/TabixIndexReader.java) over vce_tabix_*: `.names`, `.options` (format, seq / begin / end
+    column 0-based, meta, skip) and `.query(name, begin0, end0)` -> (voffset_begin, voffset_end) or None."""
+
+    def __init__(self, library, tbi):
+        self._lib = library
+        pre = "vce_" if library.prefix == "vce_" else library.prefix + "vce_"
+        self._pre = pre
+        f = getattr(library.lib, pre + "tabix_open")
+        f.restype = C.c_int
+        f.argtypes = [C.c_char_p, C.c_int64, C.POINTER(C.c_void_p)]
+        self._h = C.c_void_p()
+        rc = f(tbi, len(tbi), C.byref(self._h))
+        if rc != 0:
+            self._h = None
+            library._loader_error(rc, "tabix_open")
+        info = (C.c_int32 * 7)()
+        g = getattr(library.lib, pre + "tabix_info")
+        g.restype = C.c_int
+        g.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
+        g(self._h, info)
+        self.options = {"format": info[1], "seq_col": info[2], "beg_col": info[3], "end_col": info[4], "meta": info[5], "skip": info[6]}
+        nm = getattr(library.lib, pre + "tabix_name")
+        nm.restype = C.c_char_p
+        nm.argtypes = [C.c_void_p, C.c_int32]
+        self.names = [nm(self._h, i).decode() for i in range(info[0])]
+
+    def query(self, name, begin0=-1, end0=-1):
+        q = getattr(self._lib.lib, self._pre + "tabix_query")
+        q.restype = C.c_int
+        q.argtypes = [C.c_void_p, C.c_char_p, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        vb, ve = C.c_int64(-1), C.c_int64(-1)
+        rc = q(self._h, name.encode(), int(begin0), int(end0), C.byref(vb), C.byref(ve))
+        if rc != 0:
+            self._lib._loader_error(rc, "tabix_query")
+        return None if vb.value < 0 else (int(vb.value), int(ve.value))
+
+    def close(self):
+        if self._h:
+            c = getattr(self._lib.lib, self._pre + "tabix_close")
+            c.restype = None
+            c.argtypes = [C.c_void_p]
+            c(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+

@@ -1,0 +1,606 @@
+// vce_bgzf.h -- SURVEY.md 8(f) rank 4: the on-disk formats either side of the VCF loader, decoded on the device.
+//
+//   BGZF   block-compressed VCF (`bgzip`): the reference reads it through htsjdk's BlockCompressedInputStream inside
+//          sam-rtg-2.23.0.1.jar (third party, not under /root/reference; call sites src/com/rtg/tabix/TabixLineReader.java,
+//          BlockCompressedLineReader.java:58-133, BlockCompressedPositionReader.java).  Restated from the published formats:
+//          SAM spec 4.1 (a BGZF file is a series of gzip members of at most 64 KiB with a "BC" extra field carrying the
+//          member size), RFC 1952 (member header / CRC32 / ISIZE trailer) and RFC 1951 (DEFLATE: stored, fixed and dynamic
+//          Huffman blocks).  One BGZF block per warp: every lane runs the same bit reader and Huffman decode (table reads
+//          are broadcasts, no divergence), literals are stored by lane 0, LZ77 matches are copied by all lanes.
+//   tabix  AbstractIndexReader.getFilePointers (src/com/rtg/tabix/AbstractIndexReader.java:102-205, reg2bins :238-262) and the
+//          TabixIndexReader constructor (TabixIndexReader.java:63-146) as plain host code over the inflated index: the virtual
+//          offsets [begin, end) that hold a region's records.  The index itself is BGZF and goes through the same kernel.
+//   SDF    sequence data of a formatted reference: BitwiseByteArray.dumpCompressedValues
+//          (src/com/rtg/util/bytecompression/BitwiseByteArray.java:426-439) writes, per 64 residues, three big-endian
+//          64-bit bit planes (most significant bit of the residue code first; residue i of the group is bit i);
+//          FileBitwiseInputStream.get (src/com/rtg/reader/FileBitwiseInputStream.java:151-169) reads them back.  The
+//          kernel turns the planes straight into the engine's resident template (2 bits per base + N mask per 16 bases)
+//          and the byte-per-base array the caller keeps.
+//
+// The pass bodies are shared by the CUDA instantiation (vce_vcf.cu) and the test-only host emulation (one lane).
+#ifndef VCE_BGZF_H_
+#define VCE_BGZF_H_
+
+#include <stdint.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "vce_device.h"
+
+namespace vce {
+
+// ------------------------------------------------------------------------------------------------ BGZF members
+struct BgzfBlock {
+  int64_t src;       // offset of the DEFLATE payload in the file
+  int64_t dst;       // offset of the block's text in the inflated output
+  int32_t srcLen;    // payload bytes
+  int32_t dstLen;    // ISIZE (RFC 1952): bytes of text
+  uint32_t crc;      // CRC32 of the text
+  int32_t hdrBack;   // src - hdrBack = offset of the member's header
+};
+
+enum : int32_t {
+  kInfOk = 0,
+  kInfBadType = 1,      // BTYPE 3
+  kInfBadStored = 2,    // LEN != ~NLEN
+  kInfBadLengths = 3,   // over-subscribed code, repeat without a previous length, too many lengths
+  kInfBadCode = 4,      // bit pattern that is no code / length symbol 286, 287 / distance symbol 30, 31
+  kInfTooFar = 5,       // distance reaches before the start of the block
+  kInfOverflow = 6,     // more text than ISIZE
+  kInfOverrun = 7,      // payload exhausted before the final block ended
+  kInfShort = 8,        // less text than ISIZE
+  kInfCrc = 9           // CRC32 mismatch (only when checked)
+};
+
+inline const char* bgzfStatusText(int s) {
+  static const char* const t[] = {"ok", "invalid block type", "invalid stored block lengths", "invalid code lengths set",
+                                  "invalid literal/length or distance code", "invalid distance too far back",
+                                  "more data than the block's ISIZE", "compressed data ends early",
+                                  "did not inflate the expected amount", "CRC32 mismatch"};
+  return s >= 0 && s <= 9 ? t[s] : "?";
+}
+
+// Host: walks the members of data[from, ...) up to (excluding) the member that starts at or after `toExcl`.
+// Returns "" or what is wrong with the file (BlockCompressedInputStream's "Invalid GZIP header" family).
+inline std::string bgzfWalk(const uint8_t* data, int64_t len, int64_t from, int64_t toExcl, std::vector<BgzfBlock>& out) {
+  auto le16 = [&](int64_t p) { return (uint32_t) data[p] | ((uint32_t) data[p + 1] << 8); };
+  auto le32 = [&](int64_t p) { return le16(p) | (le16(p + 2) << 16); };
+  int64_t pos = from, dst = out.empty() ? 0 : out.back().dst + out.back().dstLen;
+  while (pos < toExcl && pos < len) {
+    if (len - pos < 18) return "truncated BGZF block header at offset " + std::to_string(pos);
+    if (data[pos] != 0x1f || data[pos + 1] != 0x8b || data[pos + 2] != 8 || !(data[pos + 3] & 4))
+      return "not a block compressed (BGZF) file: invalid GZIP header at offset " + std::to_string(pos);
+    const int xlen = (int) le16(pos + 10);
+    if (len - pos < 12 + xlen) return "truncated BGZF extra field at offset " + std::to_string(pos);
+    int bsize = -1;
+    for (int64_t p = pos + 12; p + 4 <= pos + 12 + xlen;) {
+      const int slen = (int) le16(p + 2);
+      if (data[p] == 'B' && data[p + 1] == 'C' && slen == 2 && p + 6 <= pos + 12 + xlen) bsize = (int) le16(p + 4) + 1;
+      p += 4 + slen;
+    }
+    if (bsize < 0) return "not a block compressed (BGZF) file: no BC field at offset " + std::to_string(pos);
+    const int payload = bsize - xlen - 20;
+    if (payload < 0 || pos + bsize > len) return "truncated BGZF block at offset " + std::to_string(pos);
+    BgzfBlock b;
+    b.src = pos + 12 + xlen;
+    b.srcLen = payload;
+    b.crc = le32(pos + bsize - 8);
+    const uint32_t isize = le32(pos + bsize - 4);
+    if (isize > 65536u) return "BGZF block of more than 64 KiB at offset " + std::to_string(pos);
+    b.dstLen = (int32_t) isize;
+    b.dst = dst;
+    b.hdrBack = 12 + xlen;
+    dst += b.dstLen;
+    out.push_back(b);
+    pos += bsize;
+  }
+  return "";
+}
+
+// ------------------------------------------------------------------------------------------------ DEFLATE, one block per warp
+struct HostWarp {
+  static constexpr int W = 1;
+  static int lane() { return 0; }
+  static void sync() {}
+};
+#if defined(__CUDACC__)
+struct CudaWarp {
+  static constexpr int W = 32;
+  __device__ static int lane() { return (int) (threadIdx.x & 31u); }
+  __device__ static void sync() { __syncwarp(); }
+};
+#endif
+
+constexpr int kLitBits = 10;   // primary table of the literal/length code: codes of up to 10 bits in one lookup
+constexpr int kDistBits = 8;
+constexpr int kClBits = 7;     // the code-length code has at most 7 bits: always one lookup
+
+struct HuffMeta {            // canonical code description for the bit-by-bit walk (codes longer than the primary table)
+  uint16_t count[16];        // codes per length
+  uint16_t first[16];        // first canonical code of each length
+  uint16_t index[16];        // position of that code's symbol in `sym`
+};
+
+struct InflateWs {           // per-warp workspace (shared memory on the device): 3.9 KB
+  uint16_t litTab[1 << kLitBits];    // (symbol << 4) | length, 0 = not in the table
+  uint16_t distTab[1 << kDistBits];
+  uint16_t clTab[1 << kClBits];
+  uint16_t litSym[288];      // symbols ordered by (length, symbol)
+  uint16_t distSym[32];
+  HuffMeta lit, dist;
+  uint8_t lens[320];         // code lengths: literal/length then distance
+  int32_t scratch[4];
+};
+
+struct BitReader {           // LSB-first bit stream over aligned 32-bit words (little endian)
+  const uint32_t* wp;
+  const uint32_t* wStop;     // loading at or beyond this word means the payload was overrun by more than the slack
+  uint64_t bb;
+  int bc;
+  bool over;
+  VCE_HD void initAt(const uint8_t* p, const uint8_t* end) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t) 3);
+    wStop = reinterpret_cast<const uint32_t*>((reinterpret_cast<uintptr_t>(end) + 3) & ~(uintptr_t) 3) + 2;
+    const int skip = (int) (a & 3) * 8;
+    bb = (uint64_t) (*wp++) >> skip;
+    bc = 32 - skip;
+    over = false;
+  }
+  VCE_HD void refill() {     // afterwards at least 32 bits are available
+    if (bc < 32) {
+      uint32_t w = 0;
+      if (wp < wStop) w = *wp++; else over = true;
+      bb |= (uint64_t) w << bc;
+      bc += 32;
+    }
+  }
+  VCE_HD uint32_t peek(int n) const { return (uint32_t) bb & ((1u << n) - 1u); }
+  VCE_HD void drop(int n) { bb >>= n; bc -= n; }
+  VCE_HD uint32_t take(int n) { const uint32_t v = peek(n); drop(n); return v; }
+  // address of the first byte that no consumed bit belongs to
+  VCE_HD const uint8_t* bytePos() const { return reinterpret_cast<const uint8_t*>(wp) - (bc >> 3); }
+};
+
+VCE_HD uint32_t bitReverse(uint32_t v, int n) {
+  uint32_t r = 0;
+  for (int i = 0; i < n; ++i) { r = (r << 1) | (v & 1u); v >>= 1; }
+  return r;
+}
+
+// Builds the decoding structures of one canonical Huffman code from its code lengths (RFC 1951 3.2.2).
+// Returns false when the lengths over-subscribe the code space.
+template <class WP>
+VCE_HDN bool huffBuild(const uint8_t* lens, int n, uint16_t* tab, int tabBits, uint16_t* sym, HuffMeta* meta, int32_t* flag) {
+  const int lane = WP::lane();
+  WP::sync();   // `lens` written by lane 0
+  if (lane == 0) {
+    for (int l = 0; l < 16; ++l) meta->count[l] = 0;
+    for (int s = 0; s < n; ++s) ++meta->count[lens[s]];
+    int left = 1, ok = 1;
+    uint32_t code = 0, idx = 0;
+    for (int l = 1; l < 16; ++l) {
+      left = (left << 1) - (int) meta->count[l];
+      if (left < 0) ok = 0;
+      code = (code + (l > 1 ? meta->count[l - 1] : 0)) << 1;
+      meta->first[l] = (uint16_t) code;
+      meta->index[l] = (uint16_t) idx;
+      idx += meta->count[l];
+    }
+    *flag = ok;
+    if (ok) {
+      uint16_t next[16];
+      for (int l = 1; l < 16; ++l) next[l] = meta->index[l];
+      for (int s = 0; s < n; ++s) if (lens[s]) sym[next[lens[s]]++] = (uint16_t) s;
+    }
+  }
+  for (int i = lane; i < (1 << tabBits); i += WP::W) tab[i] = 0;
+  WP::sync();
+  if (!*flag) return false;
+  const int nCodes = (int) meta->index[15] + (int) meta->count[15];
+  for (int i = lane; i < nCodes; i += WP::W) {
+    const int s = sym[i];
+    const int l = lens[s];
+    if (l > tabBits) continue;
+    const uint32_t code = (uint32_t) meta->first[l] + (uint32_t) (i - (int) meta->index[l]);
+    const uint16_t e = (uint16_t) ((s << 4) | l);
+    for (uint32_t k = bitReverse(code, l); k < (1u << tabBits); k += 1u << l) tab[k] = e;
+  }
+  WP::sync();
+  return true;
+}
+
+// One symbol: primary table, else the canonical walk bit by bit.  -1 = no such code.
+VCE_HD int huffDecode(BitReader& br, const uint16_t* tab, int tabBits, const uint16_t* sym, const HuffMeta* meta) {
+  const uint32_t e = tab[br.peek(tabBits)];
+  if (e) { br.drop((int) (e & 15u)); return (int) (e >> 4); }
+  uint32_t code = 0;
+  uint64_t bits = br.bb;
+  for (int l = 1; l < 16; ++l) {
+    code = (code << 1) | (uint32_t) (bits & 1u);
+    bits >>= 1;
+    const uint32_t c = meta->count[l], f = meta->first[l];
+    if (code >= f && code - f < c) { br.drop(l); return sym[meta->index[l] + (code - f)]; }
+  }
+  return -1;
+}
+
+// Inflates one raw DEFLATE stream src[0, srcLen) into dst[0, dstLen); every lane of the warp calls it with the same
+// arguments and gets the same status.  No preset dictionary: a distance never reaches before dst[0].
+template <class WP>
+VCE_HDN int inflateBlock(const uint8_t* src, int srcLen, uint8_t* dst, int dstLen, InflateWs* ws) {
+  const int lane = WP::lane();
+  BitReader br;
+  br.initAt(src, src + srcLen);
+  int op = 0;
+  int status = kInfOk;
+  for (bool last = false; !last && status == kInfOk;) {
+    br.refill();
+    last = br.take(1) != 0;
+    const uint32_t type = br.take(2);
+    if (type == 3) { status = kInfBadType; break; }
+    if (type == 0) {
+      br.drop(br.bc & 7);
+      br.refill();
+      const uint32_t n = br.take(16), nn = br.take(16);
+      if ((n ^ nn) != 0xffffu) { status = kInfBadStored; break; }
+      const uint8_t* p = br.bytePos();
+      if (p + n > src + srcLen) { status = kInfOverrun; break; }
+      if (op + (int) n > dstLen) { status = kInfOverflow; break; }
+      for (int i = lane; i < (int) n; i += WP::W) dst[op + i] = p[i];
+      op += (int) n;
+      br.initAt(p + n, src + srcLen);
+      continue;
+    }
+    int nLit, nDist;
+    if (type == 1) {          // fixed code (RFC 1951 3.2.6)
+      WP::sync();
+      for (int s = lane; s < 320; s += WP::W) ws->lens[s] = (uint8_t) (s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : s < 288 ? 8 : 5);
+      nLit = 288;
+      nDist = 32;
+    } else {                  // dynamic code (3.2.7)
+      nLit = (int) br.take(5) + 257;
+      nDist = (int) br.take(5) + 1;
+      const int nCl = (int) br.take(4) + 4;
+      if (nLit > 286 || nDist > 30) { status = kInfBadLengths; break; }
+      WP::sync();
+      if (lane == 0) for (int i = 0; i < 19; ++i) ws->lens[i] = 0;
+      for (int i = 0; i < nCl; ++i) {
+        br.refill();
+        const uint32_t v = br.take(3);
+        // order of the code-length code lengths
+        // (16 17 18 0 8 7 9 6 10 5 11 4 12 3 13 2 14 1 15)
+        const int pos = i < 3 ? 16 + i : i == 3 ? 0 : (i & 1) ? 7 - ((i - 5) >> 1) : 6 + (i >> 1);
+        if (lane == 0) ws->lens[pos] = (uint8_t) v;
+      }
+      if (!huffBuild<WP>(ws->lens, 19, ws->clTab, kClBits, ws->distSym, &ws->dist, &ws->scratch[0])) { status = kInfBadLengths; break; }
+      // the lengths are decoded by every lane alike and land in registers first (the table above reads ws->lens)
+      int got = 0, prev = 0;
+      uint8_t* out = ws->lens;
+      // (clTab / dist meta stay valid while lens is rewritten: they were derived, not referenced)
+      WP::sync();
+      while (got < nLit + nDist && status == kInfOk) {
+        br.refill();
+        const int s = huffDecode(br, ws->clTab, kClBits, ws->distSym, &ws->dist);
+        if (s < 0) { status = kInfBadCode; break; }
+        int rep = 1, val = s;
+        if (s == 16) { if (got == 0) { status = kInfBadLengths; break; } val = prev; rep = 3 + (int) br.take(2); }
+        else if (s == 17) { val = 0; rep = 3 + (int) br.take(3); }
+        else if (s == 18) { val = 0; rep = 11 + (int) br.take(7); }
+        if (got + rep > nLit + nDist) { status = kInfBadLengths; break; }
+        if (lane == 0) for (int r = 0; r < rep; ++r) out[got + r] = (uint8_t) val;
+        got += rep;
+        prev = val;
+      }
+      if (status != kInfOk) break;
+      WP::sync();
+      if (ws->lens[256] == 0) { status = kInfBadLengths; break; }   // no end-of-block code
+    }
+    // the distance lengths sit right behind the literal/length lengths
+    if (!huffBuild<WP>(ws->lens, nLit, ws->litTab, kLitBits, ws->litSym, &ws->lit, &ws->scratch[0])) { status = kInfBadLengths; break; }
+    if (!huffBuild<WP>(ws->lens + nLit, nDist, ws->distTab, kDistBits, ws->distSym, &ws->dist, &ws->scratch[1])) { status = kInfBadLengths; break; }
+    for (;;) {
+      br.refill();
+      const int s = huffDecode(br, ws->litTab, kLitBits, ws->litSym, &ws->lit);
+      if (s < 256) {
+        if (s < 0) { status = kInfBadCode; break; }
+        if (op >= dstLen) { status = kInfOverflow; break; }
+        if (lane == 0) dst[op] = (uint8_t) s;
+        ++op;
+        continue;
+      }
+      if (s == 256) break;
+      const int li = s - 257;
+      if (li > 28) { status = kInfBadCode; break; }
+      int len;
+      if (li < 8) len = 3 + li;
+      else if (li == 28) len = 258;
+      else { const int x = (li - 4) >> 2; len = 3 + ((4 + (li & 3)) << x) + (int) br.take(x); }
+      br.refill();
+      const int ds = huffDecode(br, ws->distTab, kDistBits, ws->distSym, &ws->dist);
+      if (ds < 0 || ds > 29) { status = kInfBadCode; break; }
+      int dist;
+      if (ds < 4) dist = 1 + ds;
+      else { const int x = (ds >> 1) - 1; dist = 1 + ((2 + (ds & 1)) << x) + (int) br.take(x); }
+      if (dist > op) { status = kInfTooFar; break; }
+      if (op + len > dstLen) { status = kInfOverflow; break; }
+      if (br.over) { status = kInfOverrun; break; }
+      WP::sync();   // lane 0's literals and the previous copies are visible to every lane
+      const uint8_t* from = dst + op - dist;
+      if (dist >= len) {
+        for (int i = lane; i < len; i += WP::W) dst[op + i] = from[i];
+      } else {
+        for (int i = lane; i < len; i += WP::W) dst[op + i] = from[i % dist];
+      }
+      op += len;
+    }
+    if (br.over && status == kInfOk) status = kInfOverrun;
+  }
+  if (status == kInfOk) {
+    // bits consumed beyond the payload mean the stream was cut short
+    // (bytePos is the first byte no bit of which was consumed)
+    const uint8_t* p = br.bytePos();
+    if (p > src + srcLen) status = kInfOverrun;
+    else if (op != dstLen) status = kInfShort;
+  }
+  WP::sync();
+  return status;
+}
+
+// CRC32 (RFC 1952 8.1.1, polynomial 0xedb88320), one thread per block, byte by byte through a 256-entry table.
+VCE_HD uint32_t crc32TableEntry(uint32_t i) {
+  uint32_t c = i;
+  for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xedb88320u ^ (c >> 1) : c >> 1;
+  return c;
+}
+VCE_HD uint32_t crc32Bytes(const uint8_t* p, int n, const uint32_t* table) {
+  uint32_t c = 0xffffffffu;
+  for (int i = 0; i < n; ++i) c = table[(c ^ p[i]) & 0xffu] ^ (c >> 8);
+  return c ^ 0xffffffffu;
+}
+
+// Host: bytes of text between two virtual offsets, from the members' ISIZE fields alone.
+inline std::string bgzfTextSize(const uint8_t* data, int64_t len, int64_t vBeg, int64_t vEnd, int64_t* textLen) {
+  const int64_t cBeg = vBeg >> 16, uBeg = vBeg & 0xffff;
+  const int64_t cEnd = vEnd >= 0 ? vEnd >> 16 : len, uEnd = vEnd >= 0 ? vEnd & 0xffff : 0;
+  if (vBeg < 0 || cBeg > len || cEnd > len) return "BGZF: virtual offsets outside the file";
+  std::vector<BgzfBlock> blocks;
+  const std::string w = bgzfWalk(data, len, cBeg, uEnd > 0 ? cEnd + 1 : cEnd, blocks);
+  if (!w.empty()) return w;
+  int64_t end = blocks.empty() ? 0 : blocks.back().dst + blocks.back().dstLen;
+  if (uEnd > 0 && !blocks.empty()) end = blocks.back().dst + uEnd;
+  *textLen = end > uBeg ? end - uBeg : 0;
+  return "";
+}
+
+// ------------------------------------------------------------------------------------------------ driver
+struct BgzfStats {
+  int64_t blocks = 0, compressed = 0, text = 0;
+  double h2dMs = 0, kernelMs = 0, d2hMs = 0;
+  int launches = 0;
+};
+
+// The text between two virtual offsets (compressed offset << 16 | offset within the block's text), as TabixLineReader
+// walks it.  vEnd < 0: to the end of the file.  On success *dText / *textLen describe the slice in device memory
+// (owned by the ops' slab); `hostOut` (optional) receives a copy.
+template <class Ops>
+int bgzfDrive(Ops& ops, const uint8_t* data, int64_t len, int64_t vBeg, int64_t vEnd, bool checkCrc, const uint8_t** dText,
+              int64_t* textLen, std::vector<uint8_t>* hostOut, BgzfStats& st, std::string& err) {
+  *dText = nullptr;
+  *textLen = 0;
+  if (!data || len < 0 || vBeg < 0) { err = "BGZF: bad arguments"; return 1; }
+  const int64_t cBeg = vBeg >> 16, uBeg = vBeg & 0xffff;
+  int64_t cEnd = len, uEnd = 0;
+  if (vEnd >= 0) { cEnd = vEnd >> 16; uEnd = vEnd & 0xffff; }
+  if (cBeg > len || cEnd > len || (vEnd >= 0 && vEnd < vBeg)) { err = "BGZF: virtual offsets outside the file"; return 1; }
+  std::vector<BgzfBlock> blocks;
+  // the member that holds the end offset is needed when the end lies inside its text
+  std::string w = bgzfWalk(data, len, cBeg, uEnd > 0 ? cEnd + 1 : cEnd, blocks);
+  if (!w.empty()) { err = w; return 1; }
+  int64_t total = blocks.empty() ? 0 : blocks.back().dst + blocks.back().dstLen;
+  int64_t sliceEnd = total;
+  if (uEnd > 0) {
+    if (blocks.empty() || blocks.back().src - blocks.back().hdrBack != cEnd || uEnd > blocks.back().dstLen) { err = "BGZF: end offset beyond its block"; return 1; }
+    sliceEnd = blocks.back().dst + uEnd;
+  }
+  if (uBeg > 0 && (blocks.empty() || uBeg > blocks[0].dstLen)) { err = "BGZF: start offset beyond its block"; return 1; }
+  if (sliceEnd < uBeg) sliceEnd = uBeg;
+  if (total >= 0x7ffffff0LL) { err = "BGZF: 2 GB of text or more: hand it over in pieces (one sequence per call)"; return 1; }
+  const int nb = (int) blocks.size();
+  const int64_t span = nb ? blocks.back().src + blocks.back().srcLen + 8 - cBeg : 0;   // compressed bytes needed
+  for (BgzfBlock& b : blocks) b.src -= cBeg;
+  st.blocks = nb;
+  st.compressed = span;
+  st.text = sliceEnd - uBeg;
+  ops.mark(0);
+  uint8_t* dData = ops.template alloc<uint8_t>((size_t) span + 64);
+  BgzfBlock* dBlocks = ops.template alloc<BgzfBlock>((size_t) nb + 1);
+  int32_t* dStatus = ops.template alloc<int32_t>((size_t) nb + 1);
+  uint8_t* dOut = ops.template alloc<uint8_t>((size_t) total + 64);
+  if (!dData || !dBlocks || !dStatus || !dOut) { err = "out of device memory for the BGZF blocks"; return 2; }
+  ops.upload(dData, data + cBeg, (size_t) span);
+  ops.upload(dBlocks, blocks.data(), (size_t) nb * sizeof(BgzfBlock));
+  ops.mark(1);
+  ops.inflate(nb, dBlocks, dData, dOut, dStatus, checkCrc);
+  std::vector<int32_t> status((size_t) nb);
+  ops.download(status.data(), dStatus, (size_t) nb * sizeof(int32_t));
+  for (int b = 0; b < nb; ++b) {
+    if (status[(size_t) b] != kInfOk) {
+      err = "BGZF block at offset " + std::to_string(cBeg + blocks[(size_t) b].src - blocks[(size_t) b].hdrBack) + ": " + bgzfStatusText(status[(size_t) b]);
+      return 3;
+    }
+  }
+  *dText = dOut + uBeg;
+  *textLen = sliceEnd - uBeg;
+  if (hostOut) {
+    hostOut->resize((size_t) *textLen);
+    ops.download(hostOut->data(), *dText, (size_t) *textLen);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ tabix index (host)
+// The inflated index (TabixIndexReader.java:63-146).  Positions are byte offsets into `raw`.
+struct TabixIndex {
+  std::vector<uint8_t> raw;
+  int32_t format = 0, seqCol = 0, begCol = 0, endCol = 0, meta = 0, skip = 0;
+  std::vector<std::string> names;
+  std::vector<int64_t> binPos, linPos;
+};
+
+inline std::string tabixParse(TabixIndex& t) {
+  const std::vector<uint8_t>& b = t.raw;
+  auto le32 = [&](size_t p) { return (int32_t) ((uint32_t) b[p] | ((uint32_t) b[p + 1] << 8) | ((uint32_t) b[p + 2] << 16) | ((uint32_t) b[p + 3] << 24)); };
+  if (b.size() < 36) return "not a valid TABIX index. (index does not have a complete header)";
+  if (b[0] != 'T' || b[1] != 'B' || b[2] != 'I' || b[3] != 1) return "not a valid TABIX index. (index does not have a valid header)";
+  const int32_t nRef = le32(4);
+  t.format = le32(8);
+  t.seqCol = le32(12) - 1;
+  t.begCol = le32(16) - 1;
+  t.endCol = le32(20) - 1;
+  t.meta = le32(24);
+  t.skip = le32(28);
+  if (t.seqCol < 0) return "not a valid TABIX index. (invalid col_seq)";
+  if (t.begCol < 0) return "not a valid TABIX index. (invalid col_beg)";
+  const int32_t nameLen = le32(32);
+  if (nameLen < 0 || nRef < 0 || b.size() < (size_t) 36 + (size_t) nameLen) return "not a valid TABIX index. (sequence names truncated)";
+  size_t start = 36;
+  for (size_t i = 36; i < (size_t) 36 + (size_t) nameLen; ++i) {
+    if (b[i] == 0) {
+      if ((int32_t) t.names.size() >= nRef) return "not a valid TABIX index. (more sequence names provided than expected)";
+      t.names.emplace_back(reinterpret_cast<const char*>(b.data() + start), i - start);
+      start = i + 1;
+    }
+  }
+  if ((int32_t) t.names.size() != nRef) return "not a valid TABIX index. (insufficient number of sequence names provided)";
+  size_t pos = (size_t) 36 + (size_t) nameLen;
+  for (int32_t s = 0; s < nRef; ++s) {
+    t.binPos.push_back((int64_t) pos);
+    if (pos + 4 > b.size()) return "not a valid TABIX index. (truncated)";
+    const int32_t nBins = le32(pos);
+    pos += 4;
+    for (int32_t i = 0; i < nBins; ++i) {
+      if (pos + 8 > b.size()) return "not a valid TABIX index. (truncated)";
+      const int32_t nChunks = le32(pos + 4);
+      if (nChunks < 0) return "not a valid index. (numChunks = " + std::to_string(nChunks) + ")";
+      pos += 8 + (size_t) nChunks * 16;
+    }
+    t.linPos.push_back((int64_t) pos);
+    if (pos + 4 > b.size()) return "not a valid TABIX index. (truncated)";
+    const int32_t nLin = le32(pos);
+    if (nLin < 0) return "not a valid index. (linearIndexSize = " + std::to_string(nLin) + ")";
+    pos += 4 + (size_t) nLin * 8;
+    if (pos > b.size()) return "not a valid TABIX index. (truncated)";
+  }
+  return "";
+}
+
+// AbstractIndexReader.getFilePointers(seqName, intervals...) for ONE interval [beg, end) (0-based, end exclusive; end < 0 or
+// INT_MAX = to the end of the sequence): the smallest chunk begin / largest chunk end over the region's bins, linear-index
+// filtered (:170-199).  Returns 1 and the offsets, 0 when the index holds nothing for the region, -1 on a bad request.
+inline int tabixQuery(const TabixIndex& t, const std::string& name, int32_t beg0, int32_t end0, int64_t* vBeg, int64_t* vEnd, std::string& err) {
+  int seq = -1;
+  for (size_t i = 0; i < t.names.size(); ++i) if (t.names[i] == name) seq = (int) i;   // HashMap.put: the last one wins
+  if (seq < 0) return 0;
+  const std::vector<uint8_t>& b = t.raw;
+  auto le32 = [&](size_t p) { return (int32_t) ((uint32_t) b[p] | ((uint32_t) b[p + 1] << 8) | ((uint32_t) b[p + 2] << 16) | ((uint32_t) b[p + 3] << 24)); };
+  auto le64 = [&](size_t p) { return (uint64_t) (uint32_t) le32(p) | ((uint64_t) (uint32_t) le32(p + 4) << 32); };
+  constexpr int32_t kMaxCoord = 1 << 29;
+  const int32_t beg = (beg0 <= -1) ? 0 : beg0;
+  const int32_t end = (end0 <= -1 || end0 == 0x7fffffff) ? kMaxCoord : end0;
+  if (end > kMaxCoord || beg > kMaxCoord) { err = "The requested region contains coordinates greater than can be addressed by tabix/bam indexes"; return -1; }
+  const size_t linAt = (size_t) t.linPos[(size_t) seq];
+  const int32_t nLin = le32(linAt);
+  const int32_t linearBeg = beg >> 14;
+  // bins of the region (reg2bins :238-262)
+  std::vector<int32_t> bins;
+  const int32_t cEnd = end - 1;
+  bins.push_back(0);
+  for (int32_t k = 1 + (beg >> 26); k <= 1 + (cEnd >> 26); ++k) bins.push_back(k);
+  for (int32_t k = 9 + (beg >> 23); k <= 9 + (cEnd >> 23); ++k) bins.push_back(k);
+  for (int32_t k = 73 + (beg >> 20); k <= 73 + (cEnd >> 20); ++k) bins.push_back(k);
+  for (int32_t k = 585 + (beg >> 17); k <= 585 + (cEnd >> 17); ++k) bins.push_back(k);
+  for (int32_t k = 4681 + (beg >> 14); k <= 4681 + (cEnd >> 14); ++k) bins.push_back(k);
+  // bin id -> position of its chunk list (a later duplicate of a bin id replaces the earlier one, :154)
+  constexpr int32_t kNumBins = ((1 << 18) - 1) / 7 + 2;
+  std::vector<int64_t> where((size_t) kNumBins, -1);
+  size_t pos = (size_t) t.binPos[(size_t) seq];
+  const int32_t nBins = le32(pos);
+  pos += 4;
+  for (int32_t i = 0; i < nBins; ++i) {
+    const uint32_t id = (uint32_t) le32(pos);
+    const int32_t nChunks = le32(pos + 4);
+    if (id >= (uint32_t) kNumBins) { err = "not a valid index. (bin " + std::to_string(id) + ")"; return -1; }   // the reference: ArrayIndexOutOfBounds
+    where[id] = (int64_t) pos;
+    pos += 8 + (size_t) nChunks * 16;
+  }
+  bool have = false;
+  uint64_t lo = 0, hi = 0;
+  const uint64_t linMin = linearBeg < nLin ? le64(linAt + 4 + (size_t) linearBeg * 8) : 0;
+  for (int32_t bin : bins) {
+    if (bin >= kNumBins || where[(size_t) bin] < 0) continue;
+    const size_t at = (size_t) where[(size_t) bin];
+    const int32_t nChunks = le32(at + 4);
+    for (int32_t k = 0; k < nChunks; ++k) {
+      const uint64_t cb = le64(at + 8 + (size_t) k * 16), ce = le64(at + 16 + (size_t) k * 16);
+      if (bin >= 4681 || (linearBeg < nLin && linMin < ce)) {
+        if (!have || cb < lo) lo = cb;
+        if (!have || hi < ce) hi = ce;
+        have = true;
+      }
+    }
+  }
+  if (!have) return 0;
+  *vBeg = (int64_t) lo;
+  *vEnd = (int64_t) hi;
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------------ SDF sequence data
+// One 16-base granule of the resident template per call: residues [first + g * 16, ...) of the bit-plane file become
+// packed[g] (2 bits per base, base code - 1), the granule's N bit and 16 bytes of the byte-per-base array.
+// Codes: 0 = N, 1..4 = A C G T (DNA.ordinal()); codes 5..7 cannot be written by the formatter and are kept as they are
+// in the byte array (they count as "other" in the mask, like N).
+VCE_HD uint64_t sdfPlane(const uint8_t* file, int64_t longIdx) {   // big-endian 64-bit word (DataOutputStream.writeLong)
+  const uint8_t* p = file + longIdx * 8;
+  uint64_t v = 0;
+  for (int i = 0; i < 8; ++i) v = (v << 8) | p[i];
+  return v;
+}
+VCE_HD void sdfGranule(const uint8_t* file, int64_t first, int32_t len, int32_t g, uint32_t* packed, uint8_t* otherFlag, uint8_t* bases) {
+  uint32_t v = 0;
+  bool other = false;
+  const int32_t p0 = g * 16;
+  int64_t group = -1;
+  uint64_t b0 = 0, b1 = 0, b2 = 0;
+  for (int q = 0; q < 16 && p0 + q < len; ++q) {
+    const int64_t r = first + p0 + q;
+    if ((r >> 6) != group) {
+      group = r >> 6;
+      b0 = sdfPlane(file, group * 3);
+      b1 = sdfPlane(file, group * 3 + 1);
+      b2 = sdfPlane(file, group * 3 + 2);
+    }
+    const int bit = (int) (r & 63);
+    const uint32_t code = (uint32_t) (((b0 >> bit) & 1u) << 2 | ((b1 >> bit) & 1u) << 1 | ((b2 >> bit) & 1u));
+    if (code < 1 || code > 4) other = true;
+    v |= ((code - 1u) & 3u) << (2 * q);
+    if (bases) bases[p0 + q] = (uint8_t) code;
+  }
+  packed[g] = v;
+  otherFlag[g] = other ? 1 : 0;
+}
+// mask word m gathers the flags of granules [32 m, 32 m + 32)
+VCE_HD void sdfMaskWord(const uint8_t* otherFlag, int32_t granules, int32_t m, uint32_t* nmask) {
+  uint32_t mask = 0;
+  for (int gi = 0; gi < 32; ++gi) {
+    const int32_t g = m * 32 + gi;
+    if (g < granules && otherFlag[g]) mask |= 1u << gi;
+  }
+  nmask[m] = mask;
+}
+
+}  // namespace vce
+#endif

@@ -18,6 +18,7 @@
 
 #include "../../include/vce.h"
 #include "vce_cuda.h"
+#include "vce_bgzf.h"
 #include "vce_vcf.h"
 #include "vce_engine.h"
 
@@ -504,6 +505,142 @@ int vce_vcf_variants(const void* result, vce_variants* out, vce_vcf_stats* stats
 }
 
 void vce_vcf_free(void* result) { delete static_cast<vce::VcfResult*>(result); }
+
+// ------------------------------------------------------------------------------- on-disk formats (vce_bgzf.h)
+namespace {
+int currentDevice() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return g_device;
+}
+void bgzfStatsOut(const vce::BgzfStats& st, vce_bgzf_stats* out) {
+  if (!out) return;
+  out->blocks = st.blocks; out->compressed_bytes = st.compressed; out->text_bytes = st.text;
+  out->h2d_ms = st.h2dMs; out->kernel_ms = st.kernelMs; out->d2h_ms = st.d2hMs;
+  out->launches = st.launches; out->reserved = 0;
+}
+int vcfConfigFrom(const vce_vcf_in* in, vce::VcfConfig& cfg) {
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.sample = in->sample; cfg.ploidy = in->ploidy; cfg.passOnly = in->pass_only; cfg.maxLength = in->max_length;
+  cfg.templateLen = in->template_len;
+  if (in->name) {
+    const size_t nl = std::strlen(in->name);
+    if (nl == 0 || nl >= sizeof(cfg.name)) return fail(VCE_ERR_BAD_ARGUMENT, "sequence name empty or too long");
+    std::memcpy(cfg.name, in->name, nl);
+    cfg.nameLen = (int32_t) nl;
+  }
+  return VCE_OK;
+}
+}  // namespace
+
+int vce_bgzf_text_size(const uint8_t* data, int64_t len, int64_t voffset_begin, int64_t voffset_end, int64_t* text_len) {
+  if (!data || !text_len || len < 0 || voffset_begin < 0) return fail(VCE_ERR_BAD_ARGUMENT, "null argument");
+  const std::string w = vce::bgzfTextSize(data, len, voffset_begin, voffset_end, text_len);
+  if (!w.empty()) return fail(VCE_ERR_BAD_ARGUMENT, w);
+  return VCE_OK;
+}
+
+int vce_bgzf_inflate(const uint8_t* data, int64_t len, int64_t voffset_begin, int64_t voffset_end, int32_t check_crc, uint8_t* text,
+                     int64_t text_cap, int64_t* text_len, vce_bgzf_stats* stats) {
+  if (!data || !text_len || (!text && text_cap > 0)) return fail(VCE_ERR_BAD_ARGUMENT, "null argument");
+  const int dev = currentDevice();
+  if (dev < 0) return fail(VCE_ERR_NOT_INITIALISED, "call vce_init first");
+  std::vector<uint8_t> out;
+  vce::BgzfStats st;
+  std::string err;
+  const int rc = vce::bgzfInflateOnDevice(dev, data, len, voffset_begin, voffset_end, check_crc != 0, out, st, err);
+  if (rc) return fail(rc, err);
+  *text_len = (int64_t) out.size();
+  bgzfStatsOut(st, stats);
+  if ((int64_t) out.size() > text_cap) return fail(VCE_ERR_CAPACITY, "text buffer too small (vce_bgzf_text_size tells the size)");
+  if (!out.empty()) std::memcpy(text, out.data(), out.size());
+  return VCE_OK;
+}
+
+int vce_vcf_parse_bgzf(const vce_vcf_in* in, int64_t voffset_begin, int64_t voffset_end, int32_t check_crc, void** result,
+                       vce_bgzf_stats* stats) {
+  if (!in || !result || !in->text) return fail(VCE_ERR_BAD_ARGUMENT, "null argument");
+  *result = nullptr;
+  const int dev = currentDevice();
+  if (dev < 0) return fail(VCE_ERR_NOT_INITIALISED, "call vce_init first");
+  vce::VcfConfig cfg;
+  if (int rc = vcfConfigFrom(in, cfg)) return rc;
+  std::unique_ptr<vce::VcfResult> R(new vce::VcfResult());
+  vce::BgzfStats st;
+  std::string err;
+  const int rc = vce::vcfParseBgzfOnDevice(dev, reinterpret_cast<const uint8_t*>(in->text), in->text_len, voffset_begin, voffset_end,
+                                           check_crc != 0, cfg, *R, st, err);
+  if (rc) return fail(rc, err);
+  bgzfStatsOut(st, stats);
+  *result = R.release();
+  return VCE_OK;
+}
+
+int vce_tabix_open(const uint8_t* tbi, int64_t len, void** index) {
+  if (!tbi || !index || len < 0) return fail(VCE_ERR_BAD_ARGUMENT, "null argument");
+  *index = nullptr;
+  const int dev = currentDevice();
+  if (dev < 0) return fail(VCE_ERR_NOT_INITIALISED, "call vce_init first");
+  // TabixIndexReader.java:65-67
+  if (len < 18 || tbi[0] != 0x1f || tbi[1] != 0x8b) return fail(VCE_ERR_BAD_ARGUMENT, "not a valid TABIX index. (index file is not block compressed)");
+  std::unique_ptr<vce::TabixIndex> t(new vce::TabixIndex());
+  vce::BgzfStats st;
+  std::string err;
+  const int rc = vce::bgzfInflateOnDevice(dev, tbi, len, 0, -1, true, t->raw, st, err);
+  if (rc) return fail(rc, err.find("not a block compressed") != std::string::npos ? "not a valid TABIX index. (index file is not block compressed)" : err);
+  const std::string w = vce::tabixParse(*t);
+  if (!w.empty()) return fail(VCE_ERR_BAD_ARGUMENT, w);
+  *index = t.release();
+  return VCE_OK;
+}
+
+int vce_tabix_info(const void* index, int32_t out[7]) {
+  if (!index || !out) return fail(VCE_ERR_BAD_ARGUMENT, "null argument");
+  const vce::TabixIndex& t = *static_cast<const vce::TabixIndex*>(index);
+  out[0] = (int32_t) t.names.size(); out[1] = t.format; out[2] = t.seqCol; out[3] = t.begCol; out[4] = t.endCol; out[5] = t.meta; out[6] = t.skip;
+  return VCE_OK;
+}
+
+const char* vce_tabix_name(const void* index, int32_t i) {
+  if (!index) return nullptr;
+  const vce::TabixIndex& t = *static_cast<const vce::TabixIndex*>(index);
+  return i >= 0 && i < (int32_t) t.names.size() ? t.names[(size_t) i].c_str() : nullptr;
+}
+
+int vce_tabix_query(const void* index, const char* name, int32_t begin0, int32_t end0, int64_t* voffset_begin, int64_t* voffset_end) {
+  if (!index || !name || !voffset_begin || !voffset_end) return fail(VCE_ERR_BAD_ARGUMENT, "null argument");
+  std::string err;
+  *voffset_begin = *voffset_end = -1;
+  const int r = vce::tabixQuery(*static_cast<const vce::TabixIndex*>(index), name, begin0, end0, voffset_begin, voffset_end, err);
+  if (r < 0) return fail(VCE_ERR_BAD_ARGUMENT, err);
+  if (r == 0) *voffset_begin = *voffset_end = -1;
+  return VCE_OK;
+}
+
+void vce_tabix_close(void* index) { delete static_cast<vce::TabixIndex*>(index); }
+
+int vce_template_register_sdf(const uint8_t* seqdata, int64_t seqdata_len, int64_t first_residue, int32_t len, uint8_t* bases_out,
+                              double* ms3) {
+  if (!seqdata || !bases_out || len <= 0 || first_residue < 0) return fail(VCE_ERR_BAD_ARGUMENT, "null argument");
+  std::vector<int> devs;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_device < 0) return fail(VCE_ERR_NOT_INITIALISED, "call vce_init first");
+    devs = g_devices;
+  }
+  std::sort(devs.begin(), devs.end());
+  devs.erase(std::unique(devs.begin(), devs.end()), devs.end());
+  // only the longs that hold the sequence travel: groups of 64 residues, three big-endian longs each
+  const int64_t g0 = first_residue >> 6;
+  const int64_t rel = first_residue - (g0 << 6);
+  const int64_t need = ((rel + len + 63) >> 6) * 24;
+  if (g0 * 24 + need > seqdata_len) return fail(VCE_ERR_BAD_ARGUMENT, "SDF: the data does not cover the sequence");
+  for (int d : devs) {   // every device of the pool, like vce_template_register
+    std::string err;
+    const int rc = vce::sdfTemplateOnDevice(d, seqdata + g0 * 24, need, rel, len, bases_out, ms3, err);
+    if (rc) return fail(rc, err);
+  }
+  return VCE_OK;
+}
 
 int vce_format_warning(const vce_warning* w, const char* seq_name, char* buf, int32_t cap) {
   // PathFinder.java:163

@@ -1865,6 +1865,14 @@ int templateRegistryAdd(int device, const uint8_t* bases, int32_t len, const uin
   return VCE_OK;
 }
 
+// The arrays were made on the device (SDF decode, vce_vcf.cu) and now belong to the registry.
+int templateRegistryAdopt(int device, const uint8_t* bases, int32_t len, uint32_t* d2, uint32_t* dn, std::string&) {
+  templateRegistryRemove(device, bases);
+  std::lock_guard<std::mutex> lk(g_tmplMu);
+  g_templates.push_back(TemplateEntry{bases, len, device, d2, dn});
+  return VCE_OK;
+}
+
 void templateRegistryRemove(int device, const uint8_t* bases) {
   std::lock_guard<std::mutex> lk(g_tmplMu);
   for (size_t i = 0; i < g_templates.size();) {

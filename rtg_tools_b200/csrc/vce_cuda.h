@@ -3,6 +3,7 @@
 #define VCE_CUDA_H_
 
 #include <string>
+#include <vector>
 
 #include "../../include/vce.h"
 #include "vce_pipeline.h"
@@ -23,6 +24,7 @@ void cudaBackendMicroStats(Backend* b, double* ms, long long* regions);
 bool templateRegistryLookup(int device, const uint8_t* bases, int32_t len, const uint32_t** t2, const uint32_t** nmask);
 int templateRegistryAdd(int device, const uint8_t* bases, int32_t len, const uint32_t* packed, size_t words, const uint32_t* nmask,
                         size_t mwords, std::string& err);
+int templateRegistryAdopt(int device, const uint8_t* bases, int32_t len, uint32_t* d2, uint32_t* dn, std::string& err);
 void templateRegistryRemove(int device, const uint8_t* bases);   // device < 0: every device; bases == nullptr: every template
 
 // Caller memory page-locked through vce_host_register (one registry for the process; the ranges are portable across devices).
@@ -41,6 +43,16 @@ struct VcfConfig;
 struct VcfResult;
 int vcfParseOnDevice(int device, const uint8_t* text, int64_t len, const VcfConfig& cfg, VcfResult& R, std::string& err);
 void vcfShutdown();
+
+// On-disk formats either side of the loader (vce_bgzf.h): BGZF blocks inflated on the device, alone or chained into the VCF
+// parse without the text leaving the device; SDF bit planes decoded into a resident template.
+struct BgzfStats;
+int bgzfInflateOnDevice(int device, const uint8_t* data, int64_t len, int64_t vBeg, int64_t vEnd, bool checkCrc, std::vector<uint8_t>& text,
+                        BgzfStats& st, std::string& err);
+int vcfParseBgzfOnDevice(int device, const uint8_t* data, int64_t len, int64_t vBeg, int64_t vEnd, bool checkCrc, const VcfConfig& cfg,
+                         VcfResult& R, BgzfStats& st, std::string& err);
+int sdfTemplateOnDevice(int device, const uint8_t* file, int64_t fileLen, int64_t first, int32_t len, uint8_t* basesOut, double ms[3],
+                        std::string& err);
 
 }  // namespace vce
 #endif

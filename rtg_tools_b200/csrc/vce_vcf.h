@@ -552,7 +552,8 @@ struct VcfLayout {
 // Ops: alloc<T>(n) / hostAlloc(bytes, &release) / upload / download / parFor / exclusiveSum / fetchInt / mark(k) (timing marks: 0 before the upload,
 // 1 after it, 2 after the last kernel, 3 after the downloads).
 template <class Ops>
-int vcfDrive(Ops& ops, const uint8_t* text, int64_t len, const VcfConfig& cfg, VcfResult& R, std::string& err) {
+int vcfDrive(Ops& ops, const uint8_t* text, int64_t len, const VcfConfig& cfg, VcfResult& R, std::string& err,
+             const uint8_t* residentText = nullptr) {   // residentText: the text is in device memory already (vce_bgzf.h)
   if (len < 0 || len >= 0x7ffffff0LL) { err = "VCF text of 2 GB or more: hand it over in pieces (one sequence per call)"; return 1; }
   if (cfg.ploidy < 1 || cfg.ploidy > 4 || cfg.sample < 0) { err = "sample / ploidy out of range"; return 1; }
   R.ploidy = cfg.ploidy;
@@ -561,12 +562,12 @@ int vcfDrive(Ops& ops, const uint8_t* text, int64_t len, const VcfConfig& cfg, V
   A.len = (int32_t) len;
   A.cfg = cfg;
   ops.mark(0);
-  uint8_t* dText = ops.template alloc<uint8_t>((size_t) len + 16);
+  uint8_t* dText = residentText ? nullptr : ops.template alloc<uint8_t>((size_t) len + 16);
   A.byteScan = ops.template alloc<int32_t>((size_t) len / kVcfBlock + 4);
   A.firstFatal = ops.template alloc<int32_t>(4);
-  if (!dText || !A.byteScan || !A.firstFatal) { err = "out of device memory for the VCF text"; return 2; }
-  ops.upload(dText, text, (size_t) len);
-  A.text = dText;
+  if ((!dText && !residentText) || !A.byteScan || !A.firstFatal) { err = "out of device memory for the VCF text"; return 2; }
+  if (!residentText) ops.upload(dText, text, (size_t) len);
+  A.text = residentText ? residentText : dText;
   VcfConfig* dCfg = ops.template alloc<VcfConfig>(1);
   if (!dCfg) { err = "out of device memory for the VCF text"; return 2; }
   ops.upload(dCfg, &A.cfg, sizeof(VcfConfig));

@@ -18,6 +18,7 @@
 #include "../../rtg_tools_b200/csrc/vce_engine.h"
 #include "../../rtg_tools_b200/csrc/vce_orient.h"
 #include "../../rtg_tools_b200/csrc/vce_pipeline.h"
+#include "../../rtg_tools_b200/csrc/vce_bgzf.h"
 #include "../../rtg_tools_b200/csrc/vce_vcf.h"
 
 namespace {
@@ -604,6 +605,17 @@ struct HostVcfOps {
   void exclusiveSum(int32_t* in, int32_t* out, int n) { int32_t acc = 0; for (int i = 0; i < n; ++i) { const int32_t v = in[i]; out[i] = acc; acc += v; } }
   int fetchInt(const int32_t* p) { return *p; }
   void mark(int) {}
+  // one lane per "warp": the very same inflateBlock / CRC source as k_bgzf_inflate / k_bgzf_crc
+  void inflate(int nb, const vce::BgzfBlock* blocks, const uint8_t* data, uint8_t* out, int32_t* status, bool checkCrc) {
+    std::unique_ptr<vce::InflateWs> ws(new vce::InflateWs());
+    uint32_t table[256];
+    for (uint32_t i = 0; i < 256; ++i) table[i] = vce::crc32TableEntry(i);
+    for (int b = 0; b < nb; ++b) {
+      std::memset(ws.get(), 0xcd, sizeof(vce::InflateWs));
+      status[b] = vce::inflateBlock<vce::HostWarp>(data + blocks[b].src, blocks[b].srcLen, out + blocks[b].dst, blocks[b].dstLen, ws.get());
+      if (checkCrc && status[b] == vce::kInfOk && vce::crc32Bytes(out + blocks[b].dst, blocks[b].dstLen, table) != blocks[b].crc) status[b] = vce::kInfCrc;
+    }
+  }
   static void hostFree(uint8_t* p, size_t) { delete[] p; }
   uint8_t* hostAlloc(size_t bytes, void (**release)(uint8_t*, size_t)) {
     *release = &hostFree;
@@ -652,4 +664,101 @@ int emul_vce_vcf_variants(const void* result, vce_variants* out, vce_vcf_stats* 
   return VCE_OK;
 }
 void emul_vce_vcf_free(void* result) { delete static_cast<vce::VcfResult*>(result); }
+
+// ---- on-disk formats (vce_bgzf.h) through the host ops
+static int emulVcfConfig(const vce_vcf_in* in, vce::VcfConfig& cfg) {
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.sample = in->sample; cfg.ploidy = in->ploidy; cfg.passOnly = in->pass_only; cfg.maxLength = in->max_length;
+  cfg.templateLen = in->template_len;
+  if (in->name) {
+    const size_t nl = std::strlen(in->name);
+    if (nl == 0 || nl >= sizeof(cfg.name)) return VCE_ERR_BAD_ARGUMENT;
+    std::memcpy(cfg.name, in->name, nl);
+    cfg.nameLen = (int32_t) nl;
+  }
+  return VCE_OK;
+}
+int emul_vce_bgzf_text_size(const uint8_t* data, int64_t len, int64_t vb, int64_t ve, int64_t* text_len) {
+  g_vcfErr = vce::bgzfTextSize(data, len, vb, ve, text_len);
+  return g_vcfErr.empty() ? VCE_OK : VCE_ERR_BAD_ARGUMENT;
+}
+int emul_vce_bgzf_inflate(const uint8_t* data, int64_t len, int64_t vb, int64_t ve, int32_t check_crc, uint8_t* text, int64_t text_cap,
+                          int64_t* text_len, vce_bgzf_stats* stats) {
+  HostVcfOps ops;
+  const uint8_t* dText = nullptr;
+  std::vector<uint8_t> out;
+  vce::BgzfStats st;
+  const int rc = vce::bgzfDrive(ops, data, len, vb, ve, check_crc != 0, &dText, text_len, &out, st, g_vcfErr);
+  if (rc) return rc == 2 ? VCE_ERR_CUDA : VCE_ERR_BAD_ARGUMENT;
+  if (stats) { std::memset(stats, 0, sizeof(*stats)); stats->blocks = st.blocks; stats->compressed_bytes = st.compressed; stats->text_bytes = st.text; }
+  if ((int64_t) out.size() > text_cap) return VCE_ERR_CAPACITY;
+  if (!out.empty()) std::memcpy(text, out.data(), out.size());
+  return VCE_OK;
+}
+int emul_vce_vcf_parse_bgzf(const vce_vcf_in* in, int64_t vb, int64_t ve, int32_t check_crc, void** result, vce_bgzf_stats* stats) {
+  *result = nullptr;
+  vce::VcfConfig cfg;
+  if (emulVcfConfig(in, cfg)) return VCE_ERR_BAD_ARGUMENT;
+  std::unique_ptr<vce::VcfResult> R(new vce::VcfResult());
+  HostVcfOps ops;
+  const uint8_t* dText = nullptr;
+  int64_t textLen = 0;
+  vce::BgzfStats st;
+  int rc = vce::bgzfDrive(ops, reinterpret_cast<const uint8_t*>(in->text), in->text_len, vb, ve, check_crc != 0, &dText, &textLen, nullptr, st, g_vcfErr);
+  if (rc == 0) rc = vce::vcfDrive(ops, nullptr, textLen, cfg, *R, g_vcfErr, dText);
+  if (rc) return rc == 2 ? VCE_ERR_CUDA : VCE_ERR_BAD_ARGUMENT;
+  if (stats) { std::memset(stats, 0, sizeof(*stats)); stats->blocks = st.blocks; stats->compressed_bytes = st.compressed; stats->text_bytes = st.text; }
+  *result = R.release();
+  return VCE_OK;
+}
+int emul_vce_tabix_open(const uint8_t* tbi, int64_t len, void** index) {
+  *index = nullptr;
+  if (len < 18 || tbi[0] != 0x1f || tbi[1] != 0x8b) { g_vcfErr = "not a valid TABIX index. (index file is not block compressed)"; return VCE_ERR_BAD_ARGUMENT; }
+  std::unique_ptr<vce::TabixIndex> t(new vce::TabixIndex());
+  HostVcfOps ops;
+  const uint8_t* dText = nullptr;
+  int64_t textLen = 0;
+  vce::BgzfStats st;
+  if (vce::bgzfDrive(ops, tbi, len, 0, -1, true, &dText, &textLen, &t->raw, st, g_vcfErr)) return VCE_ERR_BAD_ARGUMENT;
+  g_vcfErr = vce::tabixParse(*t);
+  if (!g_vcfErr.empty()) return VCE_ERR_BAD_ARGUMENT;
+  *index = t.release();
+  return VCE_OK;
+}
+int emul_vce_tabix_info(const void* index, int32_t out[7]) {
+  const vce::TabixIndex& t = *static_cast<const vce::TabixIndex*>(index);
+  out[0] = (int32_t) t.names.size(); out[1] = t.format; out[2] = t.seqCol; out[3] = t.begCol; out[4] = t.endCol; out[5] = t.meta; out[6] = t.skip;
+  return VCE_OK;
+}
+const char* emul_vce_tabix_name(const void* index, int32_t i) {
+  const vce::TabixIndex& t = *static_cast<const vce::TabixIndex*>(index);
+  return i >= 0 && i < (int32_t) t.names.size() ? t.names[(size_t) i].c_str() : nullptr;
+}
+int emul_vce_tabix_query(const void* index, const char* name, int32_t b0, int32_t e0, int64_t* vb, int64_t* ve) {
+  *vb = *ve = -1;
+  const int r = vce::tabixQuery(*static_cast<const vce::TabixIndex*>(index), name, b0, e0, vb, ve, g_vcfErr);
+  if (r < 0) return VCE_ERR_BAD_ARGUMENT;
+  if (r == 0) *vb = *ve = -1;
+  return VCE_OK;
+}
+void emul_vce_tabix_close(void* index) { delete static_cast<vce::TabixIndex*>(index); }
+// SDF bit planes: the granule / mask bodies as loops; the packed words and the mask come back for comparison with packTemplate
+int emul_vce_sdf_decode(const uint8_t* seqdata, int64_t seqdata_len, int64_t first, int32_t len, uint8_t* bases_out, uint32_t* packed_out,
+                        uint32_t* nmask_out) {
+  const int64_t g0 = first >> 6, rel = first - (g0 << 6), need = ((rel + len + 63) >> 6) * 24;
+  if (len <= 0 || first < 0 || g0 * 24 + need > seqdata_len) return VCE_ERR_BAD_ARGUMENT;
+  const int32_t granules = (len + 15) / 16, mwords = (granules + 31) / 32;
+  std::vector<uint8_t> flag((size_t) granules);
+  for (int32_t g = 0; g < granules; ++g) vce::sdfGranule(seqdata + g0 * 24, rel, len, g, packed_out, flag.data(), bases_out);
+  for (int32_t m = 0; m < mwords; ++m) vce::sdfMaskWord(flag.data(), granules, m, nmask_out);
+  return VCE_OK;
+}
+// packTemplate (vce_engine.cpp) for the comparison above
+int emul_vce_pack_template(const uint8_t* bases, int32_t len, uint32_t* packed_out, uint32_t* nmask_out) {
+  std::vector<uint32_t> p, m;
+  vce::packTemplate(bases, len, nullptr, p, m);
+  std::memcpy(packed_out, p.data(), p.size() * 4);
+  std::memcpy(nmask_out, m.data(), m.size() * 4);
+  return VCE_OK;
+}
 }

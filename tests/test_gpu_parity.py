@@ -355,3 +355,86 @@ def test_cuda_vcf_loader_million_records(engine):
     head = "\n".join(text.split("\n", 30_004)[:30_004]) + "\n"
     assert vcf_check.check_text(engine.lib, head, "chr1", tl, 0, what="first 30 000 records") == "ok"
     assert vcf_check.check_text(engine.lib, head, "chr1", tl, 1, pass_only=False, what="second sample, all records") == "ok"
+
+
+# ------------------------------------------------------------------------------------------- on-disk formats
+def test_cuda_bgzf_reference_files(engine):
+    """vce_bgzf_inflate on every block-compressed file the reference's tests hold: the text zlib produces; plain gzip refused."""
+    import formats_check as fc
+    assert fc.check_reference_files(engine.lib) >= 25
+
+
+def test_cuda_tabix_known_answers_and_indexes(engine):
+    """TabixIndexReaderTest's known virtual offsets; every bundled .tbi against the restated index reader, and the text between
+    the offsets against zlib."""
+    import formats_check as fc
+    fc.check_tabix_known_answers(engine.lib)
+    assert fc.check_tabix_all_indexes(engine.lib) > 300
+
+
+def test_cuda_bgzf_synthetic_and_corrupt_streams(engine):
+    """Stored / fixed / dynamic members, long codes, overlapping and far matches, empty members, random slices; damaged members
+    accepted or refused exactly as zlib does."""
+    import formats_check as fc
+    assert fc.check_synthetic_streams(engine.lib, range(10)) > 100
+    rejected, _ = fc.check_corrupt_members(engine.lib)
+    assert rejected > 20
+
+
+def test_cuda_vcf_gz_chain(engine):
+    """.vcf.gz + .tbi -> variants of one sequence: tabix query, inflate and parse chained on the device."""
+    import formats_check as fc
+    assert fc.check_vcf_gz_chain(engine.lib) >= 24
+
+
+def test_cuda_bgzf_million_records(engine):
+    """The 1 M-record text as a 42 MB -> ~12 MB .vcf.gz of ~650 members: inflated text equal to zlib's, parsed arrays equal to
+    the plain-text loader's."""
+    import formats_oracle as fo
+    import vcf_check
+    text, tl = synth.make_vcf_text(1_000_000, seed=11)
+    raw = text.encode()
+    data, index = fo.bgzf_write(raw, level=6)
+    got_text, st = engine.lib.bgzf_inflate(data)
+    assert got_text == raw and st["blocks"] == len(index) + 1 and st["launches"] == 2
+    a, b = len(raw) // 3, 2 * len(raw) // 3
+    assert engine.lib.bgzf_inflate(data, fo.voffset(index, a), fo.voffset(index, b), check_crc=False)[0] == raw[a:b]
+    want, _ = engine.lib.vcf_parse(raw, "chr1", tl, 0)
+    got, st2 = engine.lib.vcf_parse_bgzf(data, 0, -1, "chr1", tl, 0)
+    vcf_check.assert_same_side(got, want, "1 M records through BGZF")
+    assert st2["records"] == 1_000_000 and st2["blocks"] == len(index) + 1
+
+
+def test_cuda_sdf_template(engine, oracle):
+    """vce_template_register_sdf: the byte-per-base array equals FileBitwiseInputStream's (restated), and a submit that finds the
+    template registered through the SDF path (2-bit copy made on the device from the bit planes) is bit-exact against the
+    oracle -- the same check as the registered pipeline test, with sequences that sit at odd offsets of one seqdata file."""
+    import formats_oracle as fo
+    seqs = synth.make_pair(12_000_000, n_chrom=3)
+    rng = np.random.default_rng(5)
+    for s in seqs:   # some N runs: the mask path
+        a = int(rng.integers(0, s.template.size - 500))
+        s.template[a:a + int(rng.integers(1, 300))] = 0
+    pad = [rng.integers(0, 5, int(n)).astype(np.uint8) for n in (37, 1, 64 * 5 + 3)]
+    parts, first = [], []
+    for p, s in zip(pad, seqs):
+        parts.append(p)
+        first.append(sum(x.size for x in parts))
+        parts.append(s.template)
+    file = fo.sdf_planes_write(np.concatenate(parts))
+    want = oracle.submit(CONFIGS["default"], seqs, threads=6)
+    keep = []
+    try:
+        for s, f in zip(seqs, first):
+            bases = engine.lib.template_register_sdf(file, f, s.template.size)
+            assert np.array_equal(bases, s.template) and np.array_equal(bases, fo.sdf_planes_read(file, f, s.template.size))
+            s.template = bases          # the registry recognises the sequence by this pointer
+            keep.append(bases)
+        got = engine.submit(CONFIGS["default"], seqs)
+        compare_results(want, got, seqs, what="templates registered from SDF bit planes")
+        st = engine.submit_stats()
+    finally:
+        engine.unregister_templates(seqs)
+    # the windows came from the resident copy: no window bytes were uploaded (compare with the unregistered run)
+    engine.submit(CONFIGS["default"], seqs)
+    assert st["h2d_bytes"] < engine.submit_stats()["h2d_bytes"]
