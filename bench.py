@@ -228,6 +228,96 @@ def l2_flush_needed(args, variants):
     return per_gpu < 2_000_000
 
 
+def formats_leg(eng, args, text, vtl, peak, peak_src):
+    """SURVEY 8f rank 4, reported beside: the VCF text of the loader leg as a bgzip file through vce_vcf_parse_bgzf (inflate on
+    the device, one BGZF member per warp, chained into the parse) and the inflate alone; a chromosome-sized sequence of SDF bit
+    planes through vce_template_register_sdf.  CPU beside it: zlib itself (what the JDK's Inflater wraps) on one core."""
+    import zlib
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import formats_oracle as fo
+    raw = text.encode()
+    data, index = fo.bgzf_write(raw, level=6)
+    data_np = np.frombuffer(data, np.uint8).copy()
+    if not args.no_pin:
+        eng.lib.lib.vce_host_register.restype = ctypes.c_int
+        eng.lib.lib.vce_host_register.argtypes = [ctypes.c_void_p, ctypes.c_uint64]
+        eng.lib.lib.vce_host_register(data_np.ctypes.data, data_np.nbytes)
+    for _ in range(3):
+        eng.lib.vcf_parse_bgzf(data_np, 0, -1, "chr1", vtl, 0, check_crc=False)
+    runs = []
+    for _ in range(max(3, args.steps)):
+        side, st = eng.lib.vcf_parse_bgzf(data_np, 0, -1, "chr1", vtl, 0, check_crc=False)
+        runs.append(st)
+    st = sorted(runs, key=lambda r: r["kernel_ms"])[len(runs) // 2]
+    # the inflate kernel alone (the same members; the text comes back to the host here, which the chained call avoids)
+    inf = []
+    for _ in range(4):
+        got_text, ist = eng.lib.bgzf_inflate(data_np, check_crc=False)
+        inf.append(ist)
+    ist = sorted(inf[1:], key=lambda r: r["kernel_ms"])[len(inf[1:]) // 2]
+    _, cst = eng.lib.bgzf_inflate(data_np, check_crc=True)
+    assert got_text == raw, "inflated text differs from the input text"
+    ach = (len(data) + len(raw)) / (ist["kernel_ms"] * 1e-3) / 1e9
+    c_abi_ms = st["h2d_ms"] + st["kernel_ms"] + st["d2h_ms"]
+    out = {"bgzf": {"members": int(ist["blocks"]), "compressed_bytes": len(data), "text_bytes": len(raw),
+                    "inflate_kernel_ms": ist["kernel_ms"], "inflate_plus_crc32_kernel_ms": cst["kernel_ms"],
+                    "inflate_text_GBps": len(raw) / (ist["kernel_ms"] * 1e-3) / 1e9,
+                    "chain": {"what": "vce_vcf_parse_bgzf: compressed host bytes in, vce_variants arrays out (CUDA events on the loader's stream)",
+                              "records": int(st["records"]), "variants": int(st["kept"]), "h2d_ms": st["h2d_ms"], "kernel_ms": st["kernel_ms"],
+                              "d2h_ms": st["d2h_ms"], "e2e_ms": c_abi_ms, "e2e_records_per_s": st["records"] / (c_abi_ms * 1e-3),
+                              "gpu_launches": int(st["launches"])},
+                    "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                                 "algorithmic_bytes": "compressed bytes in + text bytes out", "peak_source": peak_src}}}
+    if not args.no_cpu_baseline:
+        t0 = time.perf_counter()
+        want = fo.bgzf_read(data, check_crc=False)
+        dt = time.perf_counter() - t0
+        assert want == raw
+        plain, _ = eng.lib.vcf_parse(raw, "chr1", vtl, 0)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import vcf_check
+        vcf_check.assert_same_side(side, plain, "bench: BGZF chain vs plain-text loader")
+        out["bgzf"]["cpu_baseline"] = {"value": len(raw) / dt / 1e9, "unit": "GB/s of text", "cores": 1, "kind": "reference",
+                                       "sample": "all %d members through zlib (oracle/formats_oracle.bgzf_read: zlib.decompressobj(-15) per member, "
+                                                 "the library the JDK's Inflater wraps), %.2f s" % (ist["blocks"], dt),
+                                       "parity": "text byte-identical; parsed arrays identical to the plain-text loader's"}
+    if not args.no_pin:
+        eng.lib.lib.vce_host_unregister.restype = ctypes.c_int
+        eng.lib.lib.vce_host_unregister.argtypes = [ctypes.c_void_p]
+        eng.lib.lib.vce_host_unregister(data_np.ctypes.data)
+    # SDF: one chromosome-sized sequence (chr1 of the C2 genome: ~250 Mbp) of bit planes -> resident template
+    n_bases = 248_000_000
+    rng = np.random.default_rng(3)
+    codes = rng.integers(1, 5, n_bases, dtype=np.uint8)
+    codes[10_000_000:10_050_000] = 0
+    file = np.frombuffer(fo.sdf_planes_write(codes), np.uint8).copy()
+    ms = []
+    for _ in range(3):
+        bases = eng.lib.template_register_sdf(file, 0, n_bases)
+        ms.append(eng.lib.last_sdf_ms)
+    assert np.array_equal(bases, codes), "SDF decode differs from the codes written"
+    h2d, ker, d2h = sorted(ms, key=lambda r: r[1])[1]
+    lib = eng.lib.lib
+    lib.vce_template_unregister.restype = ctypes.c_int
+    lib.vce_template_unregister.argtypes = [ctypes.c_void_p]
+    lib.vce_template_unregister(bases.ctypes.data)
+    alg = file.nbytes + n_bases + n_bases // 4 + n_bases // 128
+    out["sdf"] = {"bases": n_bases, "seqdata_bytes": int(file.nbytes), "h2d_ms": h2d, "kernel_ms": ker, "d2h_ms": d2h,
+                  "roofline": {"bound": "hbm", "achieved": alg / (ker * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                               "frac": alg / (ker * 1e-3) / 1e9 / peak, "traffic": None,
+                               "algorithmic_bytes": "bit planes in + byte-per-base + 2-bit words + N mask out", "peak_source": peak_src},
+                  "parity": "byte-per-base array identical to the codes written (FileBitwiseInputStream restated)"}
+    if not args.no_cpu_baseline:
+        t0 = time.perf_counter()
+        want = fo.sdf_planes_read(file.tobytes(), 0, 20_000_000)
+        dt = time.perf_counter() - t0
+        assert np.array_equal(want, codes[:20_000_000])
+        out["sdf"]["cpu_baseline"] = {"value": 20_000_000 / dt, "unit": "bases/s", "cores": 1, "kind": "port",
+                                      "sample": "the first 20 M bases through oracle/formats_oracle.sdf_planes_read (numpy), %.2f s" % dt}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -252,6 +342,8 @@ def main():
     ap.add_argument("--no-roc", action="store_true")
     ap.add_argument("--vcf-records", type=int, default=1_000_000,
                     help="also time the VCF loader (SURVEY 8f rank 3, vce_vcf_parse) on a synthetic text of this many records; 0 = skip")
+    ap.add_argument("--no-formats", action="store_true", help="skip the BGZF / SDF decoders (SURVEY 8f rank 4) reported beside the VCF loader")
+    ap.add_argument("--formats-only", action="store_true", help="diagnostics: only the BGZF / SDF leg, printed as its own JSON line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     C3_CLUSTERS[0] = args.c3_clusters
@@ -291,6 +383,16 @@ def main():
                                                                                time.perf_counter() - t_gen))
     eng = vcfeval.Engine(local_rank)
     cfg = engine_config(args.config)
+    if args.formats_only:
+        peaks = {}
+        ppath = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(ppath):
+            with open(ppath) as f:
+                peaks = json.load(f)
+        pk = float(peaks.get("hbm_gbs", 6650.0))
+        text, vtl = synth.make_vcf_text(args.vcf_records, seed=11, mean_gap=100)
+        emit({"formats_load": formats_leg(eng, args, text, vtl, pk, "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s")})
+        return
 
     # ------------------------------------------------------------------ device-resident throughput (value)
     job = eng.job(cfg, seqs)
@@ -533,6 +635,10 @@ def main():
                                                   "VcfSortRefiner + VcfRecordTabixCallable + SampleVariants + Allele.getAlleles), %.1f s" % (n_cpu, dt),
                                         "parity": "bit-exact on those records"}
 
+    formats_load = None
+    if vcf_load is not None and not args.no_formats:
+        formats_load = formats_leg(eng, args, text, vtl, peak, peak_src)
+
     value = total_variants / (ms_per_step * 1e-3)
     out = {
         "metric": "vcfeval variants evaluated/sec", "value": value, "unit": "variants/s", "n_gpus": world, "steps": args.steps,
@@ -556,6 +662,7 @@ def main():
         "roc": roc,
         "roc_heavy": roc_heavy,
         "vcf_load": vcf_load,
+        "formats_load": formats_load,
         "summary_counts": [int(x) for x in counts] if counts is not None else None,
         "engine_stats": {k: st[k] for k in ("regions", "escalated", "spilled", "prefix_reruns", "iterations")},
     }

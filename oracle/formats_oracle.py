@@ -248,11 +248,9 @@ def sdf_planes_write(codes) -> bytes:
     padded = np.zeros(groups * 64, np.uint8)
     padded[:n] = codes
     out = np.zeros((groups, 3), np.uint64)
-    weights = (np.uint64(1) << np.arange(64, dtype=np.uint64))
-    g = padded.reshape(groups, 64)
-    for b in range(3):   # plane 0 = bit 2 of the code
-        bit = ((g >> (2 - b)) & 1).astype(np.uint64)
-        out[:, b] = (bit * weights).sum(axis=1, dtype=np.uint64)
+    for b in range(3):   # plane 0 = bit 2 of the code; residue i of a group is bit i of the long
+        bits = (padded >> (2 - b)) & 1
+        out[:, b] = np.packbits(bits, bitorder="little").view("<u8")
     return out.astype(">u8").tobytes()
 
 
