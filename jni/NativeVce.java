@@ -51,6 +51,40 @@ final class NativeVce {
                         boolean ascending, long[] nRows, double[] threshold, double[] cumTp, double[] cumFp, double[] cumTpRaw,
                         long[] noScore);
 
+  /**
+   * vce_tabix_open: the bytes of a .tbi file (TabixIndexReader.java:63-146); the index is inflated on the device.
+   * @return a handle for {@link #tabixQuery} / {@link #tabixClose}, 0 on failure ({@link #lastError} says why)
+   */
+  static native long tabixOpen(byte[] tbi);
+
+  /**
+   * vce_tabix_query: AbstractIndexReader.getFilePointers for one interval (AbstractIndexReader.java:102-205).
+   * @param begin0 0-based start, -1 = from the start of the sequence
+   * @param end0 0-based exclusive end, -1 = to the end of the sequence
+   * @return {virtual offset begin, virtual offset end}, or null when the index holds nothing for the region
+   */
+  static native long[] tabixQuery(long index, String sequenceName, int begin0, int end0);
+
+  /** vce_tabix_close. */
+  static native void tabixClose(long index);
+
+  /**
+   * vce_vcf_parse_bgzf: what VcfRecordTabixCallable.call (VcfRecordTabixCallable.java:91-141) produces for one sequence, from the
+   * bytes of the .vcf.gz between two virtual offsets: BGZF members inflated and records parsed on the device.
+   * @param out receives the arrays of the side (as SideArrays.flatten would have made them from the loaded variants)
+   * @param counters [4] out: text lines, records of the sequence, variants kept, counted skips
+   * @return 0, or a VCE_ERR_* code (2 = the reference would have thrown VcfFormatException / a corrupt BGZF member)
+   */
+  static native int loadVcfGz(byte[] file, long voffsetBegin, long voffsetEnd, String sequenceName, int templateLength, int sample,
+                              int ploidy, boolean passOnly, int maxLength, SideArrays out, long[] counters);
+
+  /**
+   * vce_template_register_sdf: one sequence of an SDF seqdata file (bit planes, FileBitwiseInputStream.java:151-169) becomes the
+   * resident template; replaces SequencesReader.read + registerTemplate.
+   * @return the byte-per-base array (0 = N, 1..4 = A C G T), or null on failure
+   */
+  static native byte[] registerTemplateSdf(byte[] seqdata, long firstResidue, int length);
+
   /** vce_format_warning: the text of PathFinder.java:163. */
   static native String formatWarning(int pass, int paths, int iterations, int start1, int end1, String sequenceName);
 }

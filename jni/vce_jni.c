@@ -249,6 +249,112 @@ JNIEXPORT jint JNICALL Java_com_rtg_vcf_eval_NativeVce_roc(JNIEnv* e, jclass c, 
   return rc;
 }
 
+/* ---- loaders: tabix index, .vcf.gz -> SideArrays, SDF seqdata -> resident template ---- */
+JNIEXPORT jlong JNICALL Java_com_rtg_vcf_eval_NativeVce_tabixOpen(JNIEnv* e, jclass c, jbyteArray jtbi) {
+  (void) c;
+  const jsize len = (*e)->GetArrayLength(e, jtbi);
+  void* p = (*e)->GetPrimitiveArrayCritical(e, jtbi, NULL);
+  void* index = NULL;
+  const int rc = vce_tabix_open((const uint8_t*) p, (int64_t) len, &index);
+  (*e)->ReleasePrimitiveArrayCritical(e, jtbi, p, JNI_ABORT);
+  return rc == 0 ? (jlong) (intptr_t) index : 0;
+}
+
+JNIEXPORT jlongArray JNICALL Java_com_rtg_vcf_eval_NativeVce_tabixQuery(JNIEnv* e, jclass c, jlong index, jstring jname, jint begin0, jint end0) {
+  (void) c;
+  const char* name = (*e)->GetStringUTFChars(e, jname, NULL);
+  int64_t v[2] = {-1, -1};
+  const int rc = vce_tabix_query((const void*) (intptr_t) index, name, begin0, end0, &v[0], &v[1]);
+  (*e)->ReleaseStringUTFChars(e, jname, name);
+  if (rc != 0 || v[0] < 0) return NULL;
+  jlongArray out = (*e)->NewLongArray(e, 2);
+  const jlong jv[2] = {(jlong) v[0], (jlong) v[1]};
+  (*e)->SetLongArrayRegion(e, out, 0, 2, jv);
+  return out;
+}
+
+JNIEXPORT void JNICALL Java_com_rtg_vcf_eval_NativeVce_tabixClose(JNIEnv* e, jclass c, jlong index) {
+  (void) e; (void) c;
+  vce_tabix_close((void*) (intptr_t) index);
+}
+
+static void set_int_field_array(JNIEnv* e, jobject o, const char* name, const int32_t* src, jsize n) {
+  jintArray a = (*e)->NewIntArray(e, n);
+  if (n > 0) (*e)->SetIntArrayRegion(e, a, 0, n, (const jint*) src);
+  (*e)->SetObjectField(e, o, fid(e, o, name, "[I"), a);
+}
+static void set_byte_field_array(JNIEnv* e, jobject o, const char* name, const void* src, jsize n) {
+  jbyteArray a = (*e)->NewByteArray(e, n);
+  if (n > 0) (*e)->SetByteArrayRegion(e, a, 0, n, (const jbyte*) src);
+  (*e)->SetObjectField(e, o, fid(e, o, name, "[B"), a);
+}
+
+JNIEXPORT jint JNICALL Java_com_rtg_vcf_eval_NativeVce_loadVcfGz(JNIEnv* e, jclass c, jbyteArray jfile, jlong vbeg, jlong vend, jstring jname,
+    jint templateLength, jint sample, jint ploidy, jboolean passOnly, jint maxLength, jobject jout, jlongArray jcounters) {
+  (void) c;
+  const char* name = (*e)->GetStringUTFChars(e, jname, NULL);
+  vce_vcf_in in;
+  memset(&in, 0, sizeof(in));
+  in.text_len = (int64_t) (*e)->GetArrayLength(e, jfile);
+  in.name = name;
+  in.template_len = templateLength;
+  in.sample = sample;
+  in.ploidy = ploidy;
+  in.pass_only = passOnly ? 1 : 0;
+  in.max_length = maxLength;
+  void* result = NULL;
+  /* the file bytes are pinned for the call only: the engine uploads them and keeps nothing */
+  void* p = (*e)->GetPrimitiveArrayCritical(e, jfile, NULL);
+  in.text = (const char*) p;
+  int rc = vce_vcf_parse_bgzf(&in, (int64_t) vbeg, (int64_t) vend, 0, &result, NULL);
+  (*e)->ReleasePrimitiveArrayCritical(e, jfile, p, JNI_ABORT);
+  (*e)->ReleaseStringUTFChars(e, jname, name);
+  if (rc != 0) return rc;
+  vce_variants v;
+  vce_vcf_stats st;
+  rc = vce_vcf_variants(result, &v, &st);
+  if (rc == 0) {
+    const jsize n = (jsize) v.n, slots = (jsize) v.n_slots;
+    (*e)->SetIntField(e, jout, fid(e, jout, "mN", "I"), n);
+    (*e)->SetIntField(e, jout, fid(e, jout, "mGtPloidy", "I"), v.gt_ploidy);
+    set_int_field_array(e, jout, "mId", v.id, n);
+    set_byte_field_array(e, jout, "mPhased", v.phased, n);
+    set_byte_field_array(e, jout, "mStatusIn", v.status_in, n);
+    set_byte_field_array(e, jout, "mGt", v.gt, n * v.gt_ploidy);
+    set_int_field_array(e, jout, "mAlleleOff", v.allele_off, n + 1);
+    set_int_field_array(e, jout, "mAlleleStart", v.allele_start, slots);
+    set_int_field_array(e, jout, "mAlleleEnd", v.allele_end, slots);
+    set_byte_field_array(e, jout, "mAlleleNull", v.allele_null, slots);
+    set_int_field_array(e, jout, "mAlleleNtOff", v.allele_nt_off, slots + 1);
+    set_byte_field_array(e, jout, "mNt", v.nt, slots > 0 ? (jsize) v.allele_nt_off[slots] : 0);
+    const jlong cnt[4] = {(jlong) st.lines, (jlong) st.records, (jlong) st.kept, (jlong) st.skipped};
+    (*e)->SetLongArrayRegion(e, jcounters, 0, 4, cnt);
+  }
+  vce_vcf_free(result);
+  return rc;
+}
+
+JNIEXPORT jbyteArray JNICALL Java_com_rtg_vcf_eval_NativeVce_registerTemplateSdf(JNIEnv* e, jclass c, jbyteArray jseqdata, jlong first, jint len) {
+  (void) c;
+  if (len <= 0) return NULL;
+  /* the registered bytes must not move: this stub owns them, as for registerTemplate */
+  tmpl_copy* t = (tmpl_copy*) malloc(sizeof(tmpl_copy));
+  if (!t) return NULL;
+  t->bytes = (uint8_t*) malloc((size_t) len + 1);
+  if (!t->bytes) { free(t); return NULL; }
+  t->len = len;
+  const jsize flen = (*e)->GetArrayLength(e, jseqdata);
+  void* p = (*e)->GetPrimitiveArrayCritical(e, jseqdata, NULL);
+  const int rc = vce_template_register_sdf((const uint8_t*) p, (int64_t) flen, (int64_t) first, (int32_t) len, t->bytes, NULL);
+  (*e)->ReleasePrimitiveArrayCritical(e, jseqdata, p, JNI_ABORT);
+  if (rc != 0) { free(t->bytes); free(t); return NULL; }
+  t->next = g_templates;
+  g_templates = t;
+  jbyteArray out = (*e)->NewByteArray(e, len);
+  (*e)->SetByteArrayRegion(e, out, 0, len, (const jbyte*) t->bytes);
+  return out;
+}
+
 JNIEXPORT jstring JNICALL Java_com_rtg_vcf_eval_NativeVce_formatWarning(JNIEnv* e, jclass c, jint pass, jint paths, jint iterations,
     jint start1, jint end1, jstring jname) {
   (void) c;

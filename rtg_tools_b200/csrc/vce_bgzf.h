@@ -134,34 +134,43 @@ struct InflateWs {           // per-warp workspace (shared memory on the device)
   int32_t scratch[4];
 };
 
-struct BitReader {           // LSB-first bit stream over aligned 32-bit words (little endian)
-  const uint32_t* wp;
+// LSB-first bit stream over aligned 32-bit words (little endian).  Two words are held in registers, `nxt` one word ahead of
+// what is being decoded (its load was issued a whole symbol earlier); a look at the next 32 bits is one funnel shift.
+struct BitReader {
+  const uint32_t* wp;        // word after `nxt`
   const uint32_t* wStop;     // loading at or beyond this word means the payload was overrun by more than the slack
-  uint64_t bb;
-  int bc;
+  uint32_t cur, nxt;
+  int off;                   // bits of `cur` already consumed, 0..31
   bool over;
+  VCE_HD uint32_t load() {
+    uint32_t w = 0;
+    if (wp < wStop) w = *wp; else over = true;
+    ++wp;
+    return w;
+  }
   VCE_HD void initAt(const uint8_t* p, const uint8_t* end) {
     const uintptr_t a = reinterpret_cast<uintptr_t>(p);
     wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t) 3);
     wStop = reinterpret_cast<const uint32_t*>((reinterpret_cast<uintptr_t>(end) + 3) & ~(uintptr_t) 3) + 2;
-    const int skip = (int) (a & 3) * 8;
-    bb = (uint64_t) (*wp++) >> skip;
-    bc = 32 - skip;
     over = false;
+    cur = load();
+    nxt = load();
+    off = (int) (a & 3) * 8;
   }
-  VCE_HD void refill() {     // afterwards at least 32 bits are available
-    if (bc < 32) {
-      uint32_t w = 0;
-      if (wp < wStop) w = *wp++; else over = true;
-      bb |= (uint64_t) w << bc;
-      bc += 32;
-    }
+  VCE_HD uint32_t peek() const {   // the next 32 bits
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(cur, nxt, (uint32_t) off);
+#else
+    return (uint32_t) ((((uint64_t) nxt << 32) | cur) >> off);
+#endif
   }
-  VCE_HD uint32_t peek(int n) const { return (uint32_t) bb & ((1u << n) - 1u); }
-  VCE_HD void drop(int n) { bb >>= n; bc -= n; }
-  VCE_HD uint32_t take(int n) { const uint32_t v = peek(n); drop(n); return v; }
+  VCE_HD void drop(int n) {        // n <= 32
+    off += n;
+    if (off >= 32) { cur = nxt; nxt = load(); off -= 32; }
+  }
+  VCE_HD uint32_t take(int n) { const uint32_t v = peek() & ((1u << n) - 1u); drop(n); return v; }
   // address of the first byte that no consumed bit belongs to
-  VCE_HD const uint8_t* bytePos() const { return reinterpret_cast<const uint8_t*>(wp) - (bc >> 3); }
+  VCE_HD const uint8_t* bytePos() const { return reinterpret_cast<const uint8_t*>(wp - 2) + ((off + 7) >> 3); }
 };
 
 VCE_HD uint32_t bitReverse(uint32_t v, int n) {
@@ -212,19 +221,25 @@ VCE_HDN bool huffBuild(const uint8_t* lens, int n, uint16_t* tab, int tabBits, u
   return true;
 }
 
-// One symbol: primary table, else the canonical walk bit by bit.  -1 = no such code.
-VCE_HD int huffDecode(BitReader& br, const uint16_t* tab, int tabBits, const uint16_t* sym, const HuffMeta* meta) {
-  const uint32_t e = tab[br.peek(tabBits)];
-  if (e) { br.drop((int) (e & 15u)); return (int) (e >> 4); }
+// The canonical walk bit by bit, for codes longer than the primary table (out of line: rare, and 15 unrolled steps at every
+// call site would crowd the instruction cache).  -1 = no such code.
+VCE_HDN int huffWalk(uint32_t v, const uint16_t* sym, const HuffMeta* meta, int* used) {
   uint32_t code = 0;
-  uint64_t bits = br.bb;
   for (int l = 1; l < 16; ++l) {
-    code = (code << 1) | (uint32_t) (bits & 1u);
-    bits >>= 1;
+    code = (code << 1) | (v & 1u);
+    v >>= 1;
     const uint32_t c = meta->count[l], f = meta->first[l];
-    if (code >= f && code - f < c) { br.drop(l); return sym[meta->index[l] + (code - f)]; }
+    if (code >= f && code - f < c) { *used = l; return sym[meta->index[l] + (code - f)]; }
   }
+  *used = 1;
   return -1;
+}
+// One symbol from the bits `v` (the reader's next 32 bits).  Returns the symbol and the code's length in *used; the caller
+// drops the bits together with the extra bits.
+VCE_HD int huffDecode(uint32_t v, const uint16_t* tab, int tabBits, const uint16_t* sym, const HuffMeta* meta, int* used) {
+  const uint32_t e = tab[v & ((1u << tabBits) - 1u)];
+  if (e) { *used = (int) (e & 15u); return (int) (e >> 4); }
+  return huffWalk(v, sym, meta, used);
 }
 
 // Inflates one raw DEFLATE stream src[0, srcLen) into dst[0, dstLen); every lane of the warp calls it with the same
@@ -237,14 +252,15 @@ VCE_HDN int inflateBlock(const uint8_t* src, int srcLen, uint8_t* dst, int dstLe
   int op = 0;
   int status = kInfOk;
   for (bool last = false; !last && status == kInfOk;) {
-    br.refill();
-    last = br.take(1) != 0;
-    const uint32_t type = br.take(2);
+    const uint32_t hdr = br.take(3);
+    last = (hdr & 1u) != 0;
+    const uint32_t type = hdr >> 1;
     if (type == 3) { status = kInfBadType; break; }
     if (type == 0) {
-      br.drop(br.bc & 7);
-      br.refill();
-      const uint32_t n = br.take(16), nn = br.take(16);
+      br.drop((8 - (br.off & 7)) & 7);
+      const uint32_t v = br.peek();
+      const uint32_t n = v & 0xffffu, nn = v >> 16;
+      br.drop(32);
       if ((n ^ nn) != 0xffffu) { status = kInfBadStored; break; }
       const uint8_t* p = br.bytePos();
       if (p + n > src + srcLen) { status = kInfOverrun; break; }
@@ -261,34 +277,36 @@ VCE_HDN int inflateBlock(const uint8_t* src, int srcLen, uint8_t* dst, int dstLe
       nLit = 288;
       nDist = 32;
     } else {                  // dynamic code (3.2.7)
-      nLit = (int) br.take(5) + 257;
-      nDist = (int) br.take(5) + 1;
-      const int nCl = (int) br.take(4) + 4;
+      const uint32_t h = br.take(14);
+      nLit = (int) (h & 31u) + 257;
+      nDist = (int) ((h >> 5) & 31u) + 1;
+      const int nCl = (int) (h >> 10) + 4;
       if (nLit > 286 || nDist > 30) { status = kInfBadLengths; break; }
       WP::sync();
       if (lane == 0) for (int i = 0; i < 19; ++i) ws->lens[i] = 0;
       for (int i = 0; i < nCl; ++i) {
-        br.refill();
         const uint32_t v = br.take(3);
-        // order of the code-length code lengths
-        // (16 17 18 0 8 7 9 6 10 5 11 4 12 3 13 2 14 1 15)
+        // order of the code-length code lengths (16 17 18 0 8 7 9 6 10 5 11 4 12 3 13 2 14 1 15)
         const int pos = i < 3 ? 16 + i : i == 3 ? 0 : (i & 1) ? 7 - ((i - 5) >> 1) : 6 + (i >> 1);
         if (lane == 0) ws->lens[pos] = (uint8_t) v;
       }
       if (!huffBuild<WP>(ws->lens, 19, ws->clTab, kClBits, ws->distSym, &ws->dist, &ws->scratch[0])) { status = kInfBadLengths; break; }
-      // the lengths are decoded by every lane alike and land in registers first (the table above reads ws->lens)
+      // the lengths are decoded by every lane alike; lane 0 writes them over the code-length lengths (the table above was
+      // derived from those, it does not refer to them)
       int got = 0, prev = 0;
       uint8_t* out = ws->lens;
-      // (clTab / dist meta stay valid while lens is rewritten: they were derived, not referenced)
       WP::sync();
       while (got < nLit + nDist && status == kInfOk) {
-        br.refill();
-        const int s = huffDecode(br, ws->clTab, kClBits, ws->distSym, &ws->dist);
+        const uint32_t v = br.peek();
+        int used;
+        const int s = huffDecode(v, ws->clTab, kClBits, ws->distSym, &ws->dist, &used);
         if (s < 0) { status = kInfBadCode; break; }
+        const uint32_t x = v >> used;
         int rep = 1, val = s;
-        if (s == 16) { if (got == 0) { status = kInfBadLengths; break; } val = prev; rep = 3 + (int) br.take(2); }
-        else if (s == 17) { val = 0; rep = 3 + (int) br.take(3); }
-        else if (s == 18) { val = 0; rep = 11 + (int) br.take(7); }
+        if (s == 16) { if (got == 0) { status = kInfBadLengths; break; } val = prev; rep = 3 + (int) (x & 3u); used += 2; }
+        else if (s == 17) { val = 0; rep = 3 + (int) (x & 7u); used += 3; }
+        else if (s == 18) { val = 0; rep = 11 + (int) (x & 127u); used += 7; }
+        br.drop(used);
         if (got + rep > nLit + nDist) { status = kInfBadLengths; break; }
         if (lane == 0) for (int r = 0; r < rep; ++r) out[got + r] = (uint8_t) val;
         got += rep;
@@ -302,34 +320,42 @@ VCE_HDN int inflateBlock(const uint8_t* src, int srcLen, uint8_t* dst, int dstLe
     if (!huffBuild<WP>(ws->lens, nLit, ws->litTab, kLitBits, ws->litSym, &ws->lit, &ws->scratch[0])) { status = kInfBadLengths; break; }
     if (!huffBuild<WP>(ws->lens + nLit, nDist, ws->distTab, kDistBits, ws->distSym, &ws->dist, &ws->scratch[1])) { status = kInfBadLengths; break; }
     for (;;) {
-      br.refill();
-      const int s = huffDecode(br, ws->litTab, kLitBits, ws->litSym, &ws->lit);
+      uint32_t v = br.peek();
+      int used;
+      const int s = huffDecode(v, ws->litTab, kLitBits, ws->litSym, &ws->lit, &used);
       if (s < 256) {
         if (s < 0) { status = kInfBadCode; break; }
         if (op >= dstLen) { status = kInfOverflow; break; }
+        br.drop(used);
         if (lane == 0) dst[op] = (uint8_t) s;
         ++op;
         continue;
       }
-      if (s == 256) break;
+      if (s == 256) { br.drop(used); break; }
       const int li = s - 257;
       if (li > 28) { status = kInfBadCode; break; }
+      v >>= used;
       int len;
       if (li < 8) len = 3 + li;
       else if (li == 28) len = 258;
-      else { const int x = (li - 4) >> 2; len = 3 + ((4 + (li & 3)) << x) + (int) br.take(x); }
-      br.refill();
-      const int ds = huffDecode(br, ws->distTab, kDistBits, ws->distSym, &ws->dist);
+      else { const int x = (li - 4) >> 2; len = 3 + ((4 + (li & 3)) << x) + (int) (v & ((1u << x) - 1u)); used += x; }
+      br.drop(used);        // at most 15 + 5 bits
+      v = br.peek();
+      const int ds = huffDecode(v, ws->distTab, kDistBits, ws->distSym, &ws->dist, &used);
       if (ds < 0 || ds > 29) { status = kInfBadCode; break; }
+      v >>= used;
       int dist;
       if (ds < 4) dist = 1 + ds;
-      else { const int x = (ds >> 1) - 1; dist = 1 + ((2 + (ds & 1)) << x) + (int) br.take(x); }
+      else { const int x = (ds >> 1) - 1; dist = 1 + ((2 + (ds & 1)) << x) + (int) (v & ((1u << x) - 1u)); used += x; }
+      br.drop(used);        // at most 15 + 13 bits
       if (dist > op) { status = kInfTooFar; break; }
       if (op + len > dstLen) { status = kInfOverflow; break; }
       if (br.over) { status = kInfOverrun; break; }
       WP::sync();   // lane 0's literals and the previous copies are visible to every lane
       const uint8_t* from = dst + op - dist;
-      if (dist >= len) {
+      if (len <= WP::W && dist >= len) {          // the common case: one load and one store per lane
+        if (lane < len) dst[op + lane] = from[lane];
+      } else if (dist >= len) {
         for (int i = lane; i < len; i += WP::W) dst[op + i] = from[i];
       } else {
         for (int i = lane; i < len; i += WP::W) dst[op + i] = from[i % dist];
@@ -339,10 +365,7 @@ VCE_HDN int inflateBlock(const uint8_t* src, int srcLen, uint8_t* dst, int dstLe
     if (br.over && status == kInfOk) status = kInfOverrun;
   }
   if (status == kInfOk) {
-    // bits consumed beyond the payload mean the stream was cut short
-    // (bytePos is the first byte no bit of which was consumed)
-    const uint8_t* p = br.bytePos();
-    if (p > src + srcLen) status = kInfOverrun;
+    if (br.bytePos() > src + srcLen) status = kInfOverrun;
     else if (op != dstLen) status = kInfShort;
   }
   WP::sync();

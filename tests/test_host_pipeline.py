@@ -352,3 +352,12 @@ def test_split_mnps_give_multi_variant_regions():
     c = seqs[0].calls
     starts = c.allele_start[1::3]
     assert (np.diff(starts) == 1).sum() > 5, "adjacent SNPs of split MNPs should survive the generator"
+
+
+def test_jni_binding_type_checks_against_the_header():
+    """jni/vce_jni.c (the binding a maintainer links into libvce_jni.so) type-checks against include/vce.h with a stand-in jni.h:
+    every vce_* call in it has the header's signature.  (No JDK in the image: jni/build.sh builds it where one exists.)"""
+    import subprocess
+    r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "tests", "c", "jni_stub"),
+                        os.path.join(ROOT, "jni", "vce_jni.c")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
