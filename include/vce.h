@@ -136,8 +136,9 @@ typedef struct vce_side_result {
                                    (valid when GT_MATCH or ALLELE_MATCH), unused entries = -2 */
   uint8_t* original;            /* [n] OrientedVariant.isOriginal()                */
   double*  weight;              /* [n] OrientedVariant.getWeight() (calls side; 0 on baseline) */
-  int32_t* sync_id;             /* [n] optional (may be NULL): index into sync_points[pass] of the sync
-                                   region holding the variant (InterleavingEvalSynchronizer.floorSyncPos :71-83),
+  int32_t* sync_id;             /* [n] optional (may be NULL): the SYNC annotation value = id of the sync region holding the
+                                   variant: the last sync point of sync_points[pass] at or before start - 1, plus 2
+                                   (InterleavingEvalSynchronizer.floorSyncPos :71-83), 0 for skipped variants;
                                    pass 0 for GT_MATCH, pass 1 when a pass-2 list exists and the variant was not GT-matched */
 } vce_side_result;
 
@@ -245,7 +246,9 @@ int  vce_job_stats(const vce_job* job, int64_t* n_launches, double* device_ms, d
 int  vce_job_stats_ex(const vce_job* job, double* out, int32_t n);
 
 /* Diagnostics of the calling thread's last vce_submit, out[0..n): kernel launches, H2D bytes, D2H bytes, regions,
-   regions settled by the warp-per-region kernels, best-first iterations. */
+   regions settled by the warp-per-region kernels, best-first iterations; with several devices also [6..9): sequences cut
+   into pieces to balance the devices, pieces made, sequences evaluated again in one piece because a cut could
+   not be verified. */
 int  vce_submit_stats(double* out, int32_t n);
 
 /*

@@ -395,6 +395,23 @@ class Library:
             raise RuntimeError("%ssubmit failed: %s %s" % (self.prefix, ERR_NAMES.get(rc, rc), self.last_error()))
         return results
 
+    def submit_split(self, cfg: Config, seqs: List[Sequence], n_dev: int, min_variants=100000, overlap=2048, gap=64, imbalance=1.1,
+                     pieces_per_device=4):
+        """Emulation only: vce_submit over `n_dev` emulated devices with the sequence splitting of vce_split.h.
+        Returns (results, {"split", "pieces", "redone"})."""
+        ccfg, cseqs, cres, results, keep = self.pack(cfg, seqs)
+        f = self._sym("vce_submit_split")
+        f.restype = C.c_int
+        f.argtypes = [C.POINTER(CConfig), C.c_int32, C.POINTER(CSequence), C.POINTER(CSequenceResult), C.c_int32,
+                      C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        opts = (C.c_int64 * 5)(int(min_variants), int(overlap), int(gap), int(round(imbalance * 100)), int(pieces_per_device))
+        st = (C.c_int64 * 3)()
+        rc = f(C.byref(ccfg), len(seqs), cseqs, cres, int(n_dev), opts, st)
+        self.unpack(cres, results, keep)
+        if rc != 0 and all(r.error == 0 for r in results):
+            raise RuntimeError("submit_split failed: %s" % ERR_NAMES.get(rc, rc))
+        return results, {"split": int(st[0]), "pieces": int(st[1]), "redone": int(st[2])}
+
     def submit_packed(self, packed, threads: int = 0) -> int:
         """vce_submit on buffers packed once with Library.pack (the caller owns and reuses every input / output array,
         as a JNI host would); returns the C return code.  Call Library.unpack(cres, results, keep) when done."""

@@ -19,6 +19,7 @@
 #include "../../include/vce.h"
 #include "vce_cuda.h"
 #include "vce_bgzf.h"
+#include "vce_split.h"
 #include "vce_vcf.h"
 #include "vce_engine.h"
 
@@ -278,6 +279,7 @@ int vce_job_stats_ex(const vce_job* job, double* out, int32_t n) {
 }
 
 static thread_local double t_submitStats[6] = {0, 0, 0, 0, 0, 0};
+static thread_local double t_splitStats[3] = {0, 0, 0};   // sequences cut, pieces, sequences evaluated again in one piece
 static thread_local std::vector<int64_t> t_summary;
 
 int vce_submit_summary(int64_t* out, int32_t n_seq) {
@@ -290,6 +292,7 @@ int vce_submit_summary(int64_t* out, int32_t n_seq) {
 int vce_submit_stats(double* out, int32_t n) {
   if (!out) return fail(VCE_ERR_BAD_ARGUMENT, "null argument");
   for (int i = 0; i < n && i < 6; ++i) out[i] = t_submitStats[i];
+  for (int i = 6; i < n && i < 9; ++i) out[i] = t_splitStats[i - 6];
   return VCE_OK;
 }
 
@@ -353,35 +356,82 @@ int vce_submit(const vce_config* cfg, int32_t n_seq, const vce_sequence* seqs, v
   }
   if (nDev > 1 && n_seq > 1) {
     // Sequences are independent (VcfEvalTask.java:131-135): longest-processing-time greedy by variant count over the devices,
-    // one host thread per device, each with its own context, streams and share of the host cores; no data-path exchange
-    std::vector<int32_t> order((size_t) n_seq);
-    for (int32_t k = 0; k < n_seq; ++k) order[(size_t) k] = k;
-    auto weight = [&](int32_t k) { return (int64_t) seqs[k].baseline.n + (int64_t) seqs[k].calls.n; };
-    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return weight(a) > weight(b); });
-    std::vector<std::vector<int32_t>> share(nDev);
-    std::vector<int64_t> load(nDev, 0);
-    for (int32_t k : order) {
-      size_t best = 0;
-      for (size_t d = 1; d < nDev; ++d) if (load[d] < load[best]) best = d;
-      share[best].push_back(k);
-      load[best] += weight(k) + 1;
-    }
-    for (auto& sh : share) std::sort(sh.begin(), sh.end());
-    std::vector<int> rcs(nDev, VCE_OK);
-    std::vector<std::string> msgs(nDev);
-    std::vector<std::array<double, 6>> stats(nDev);
+    // one host thread per device, each with its own context, streams and share of the host cores; no data-path exchange.
+    // When whole sequences do not balance (max / mean > 1.1) the long ones are cut into pieces at wide gaps,
+    // evaluated as sequences of their own and stitched back after verification (vce_split.h).
+    vce::SplitOptions so;
+    if (const char* e = std::getenv("VCE_SPLIT_MIN")) so.minVariants = std::atoll(e);
+    if (const char* e = std::getenv("VCE_SPLIT_OVERLAP")) so.overlap = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("VCE_SPLIT_IMBALANCE")) so.imbalance = std::atof(e);
+    vce::SplitPlan plan;
+    const char* se = std::getenv("VCE_SPLIT");
+    if (se && std::atoi(se) == 0) { for (int32_t k = 0; k < n_seq; ++k) plan.whole.push_back(k); }
+    else vce::splitPlan(*cfg, n_seq, seqs, results, (int) nDev, so, plan);
     std::vector<int64_t> summary((size_t) n_seq * 8, 0);
-    std::vector<std::thread> threads;
-    for (size_t d = 0; d < nDev; ++d) {
-      for (double& v : stats[d]) v = 0;
-      if (share[d].empty()) continue;
-      threads.emplace_back([&, d] { rcs[d] = submitOn((int) d, cfg, share[d], seqs, results, stats[d].data(), summary, msgs[d]); });
+    for (int i = 0; i < 6; ++i) t_submitStats[i] = 0;
+    int hardRc = VCE_OK;
+    std::string hardMsg;
+    // one round: items (whole sequences and pieces) over the devices
+    auto round = [&](const std::vector<vce_sequence>& xs, std::vector<vce_sequence_result>& xr, std::vector<int64_t>& xsum) {
+      std::vector<int64_t> w(xs.size());
+      for (size_t i = 0; i < xs.size(); ++i) w[i] = (int64_t) xs[i].baseline.n + (int64_t) xs[i].calls.n;
+      std::vector<int> dev;
+      vce::splitAssign(w, (int) nDev, dev);
+      std::vector<std::vector<int32_t>> share(nDev);
+      for (size_t i = 0; i < xs.size(); ++i) share[(size_t) dev[i]].push_back((int32_t) i);
+      std::vector<int> rcs(nDev, VCE_OK);
+      std::vector<std::string> msgs(nDev);
+      std::vector<std::array<double, 6>> stats(nDev);
+      xsum.assign(xs.size() * 8, 0);
+      std::vector<std::thread> threads;
+      for (size_t d = 0; d < nDev; ++d) {
+        for (double& v : stats[d]) v = 0;
+        if (share[d].empty()) continue;
+        threads.emplace_back([&, d] { rcs[d] = submitOn((int) d, cfg, share[d], xs.data(), xr.data(), stats[d].data(), xsum, msgs[d]); });
+      }
+      for (std::thread& t : threads) t.join();
+      for (int i = 0; i < 6; ++i) for (size_t d = 0; d < nDev; ++d) t_submitStats[i] += stats[d][(size_t) i];
+      for (size_t d = 0; d < nDev; ++d) {
+        if (!rcs[d]) continue;
+        bool perSequence = false;
+        for (int32_t i : share[d]) if (xr[(size_t) i].error == rcs[d]) perSequence = true;
+        if (!perSequence && !hardRc) { hardRc = rcs[d]; hardMsg = msgs[d]; }
+      }
+    };
+    std::vector<vce_sequence> xs;
+    std::vector<vce_sequence_result> xr;
+    for (int32_t k : plan.whole) { xs.push_back(seqs[k]); xr.push_back(results[k]); }
+    for (auto& p : plan.pieces) { xs.push_back(p->view); xr.push_back(p->res); }
+    std::vector<int64_t> xsum;
+    round(xs, xr, xsum);
+    if (hardRc) return fail(hardRc, hardMsg.empty() ? std::string("device failure") : hardMsg);
+    for (size_t i = 0; i < plan.whole.size(); ++i) {
+      const int32_t k = plan.whole[i];
+      results[k] = xr[i];
+      for (int q = 0; q < 8; ++q) summary[(size_t) k * 8 + q] = xsum[i * 8 + (size_t) q];
     }
-    for (std::thread& t : threads) t.join();
-    for (int i = 0; i < 6; ++i) { t_submitStats[i] = 0; for (size_t d = 0; d < nDev; ++d) t_submitStats[i] += stats[d][(size_t) i]; }
+    for (size_t i = 0; i < plan.pieces.size(); ++i) plan.pieces[i]->res = xr[plan.whole.size() + i];
+    std::vector<int32_t> redo;
+    for (const vce::SplitSeq& ss : plan.split) {
+      if (vce::splitMerge(plan, ss, seqs, results)) vce::splitSummary(seqs[ss.seq], results[ss.seq], summary.data() + (size_t) ss.seq * 8);
+      else redo.push_back(ss.seq);
+    }
+    t_splitStats[0] = (double) plan.split.size(); t_splitStats[1] = (double) plan.pieces.size(); t_splitStats[2] = (double) redo.size();
+    if (!redo.empty()) {   // a cut that could not be verified (or a piece with an error): those sequences in one piece
+      std::vector<vce_sequence> ys;
+      std::vector<vce_sequence_result> yr;
+      for (int32_t k : redo) { ys.push_back(seqs[k]); yr.push_back(results[k]); }
+      std::vector<int64_t> ysum;
+      round(ys, yr, ysum);
+      if (hardRc) return fail(hardRc, hardMsg.empty() ? std::string("device failure") : hardMsg);
+      for (size_t i = 0; i < redo.size(); ++i) {
+        results[redo[i]] = yr[i];
+        for (int q = 0; q < 8; ++q) summary[(size_t) redo[i] * 8 + q] = ysum[i * 8 + (size_t) q];
+      }
+    }
     t_summary = summary;
-    for (size_t d = 0; d < nDev; ++d) {
-      if (rcs[d]) return fail(rcs[d], msgs[d].empty() ? std::string("one or more sequences reported an error") : msgs[d]);
+    for (int32_t k = 0; k < n_seq; ++k) {
+      if (results[k].error) return fail(results[k].error, "one or more sequences reported an error");
     }
     return VCE_OK;
   }

@@ -19,6 +19,7 @@
 #include "../../rtg_tools_b200/csrc/vce_orient.h"
 #include "../../rtg_tools_b200/csrc/vce_pipeline.h"
 #include "../../rtg_tools_b200/csrc/vce_bgzf.h"
+#include "../../rtg_tools_b200/csrc/vce_split.h"
 #include "../../rtg_tools_b200/csrc/vce_vcf.h"
 
 namespace {
@@ -539,6 +540,76 @@ int emul_vce_submit(const vce_config* cfg, int32_t n_seq, const vce_sequence* se
   g_residentUploads = be.residentUploads.load();
   g_finalRuns = be.finalRuns.load();
   return rc;
+}
+
+// vce_submit over `n_dev` emulated devices with the sequence splitting of vce_split.h (what vce_capi.cpp does with real devices):
+// the items of every "device" go through an engine of their own, one after the other.  opts = {min variants, overlap, gap,
+// imbalance * 100, pieces per device}; out_stats = {sequences cut, pieces, sequences evaluated again in one piece}.
+int emul_vce_submit_split(const vce_config* cfg, int32_t n_seq, const vce_sequence* seqs, vce_sequence_result* results, int32_t n_dev,
+                          const int64_t* opts, int64_t* out_stats) {
+  vce::SplitOptions so;
+  so.minVariants = opts[0]; so.overlap = (int) opts[1]; so.gap = (int) opts[2]; so.imbalance = (double) opts[3] / 100.0;
+  so.piecesPerDevice = (int) opts[4];
+  vce::SplitPlan plan;
+  vce::splitPlan(*cfg, n_seq, seqs, results, n_dev, so, plan);
+  std::vector<int64_t> summary((size_t) n_seq * 8, 0);
+  int hard = 0;
+  auto round = [&](std::vector<vce_sequence>& xs, std::vector<vce_sequence_result>& xr, std::vector<int64_t>& xsum) {
+    std::vector<int64_t> w(xs.size());
+    for (size_t i = 0; i < xs.size(); ++i) w[i] = (int64_t) xs[i].baseline.n + xs[i].calls.n;
+    std::vector<int> dev;
+    vce::splitAssign(w, n_dev, dev);
+    xsum.assign(xs.size() * 8, 0);
+    for (int d = 0; d < n_dev; ++d) {
+      std::vector<int32_t> idx;
+      for (size_t i = 0; i < xs.size(); ++i) if (dev[i] == d) idx.push_back((int32_t) i);
+      if (idx.empty()) continue;
+      std::vector<vce_sequence> sub(idx.size());
+      std::vector<vce_sequence_result> res(idx.size());
+      for (size_t i = 0; i < idx.size(); ++i) { sub[i] = xs[(size_t) idx[i]]; res[i] = xr[(size_t) idx[i]]; }
+      const int rc = emul_vce_submit(cfg, (int32_t) idx.size(), sub.data(), res.data());
+      bool perSequence = false;
+      for (size_t i = 0; i < idx.size(); ++i) {
+        xr[(size_t) idx[i]] = res[i];
+        if (rc && res[i].error == rc) perSequence = true;
+        if (g_summary.size() >= (i + 1) * 8) for (int q = 0; q < 8; ++q) xsum[(size_t) idx[i] * 8 + (size_t) q] = g_summary[i * 8 + (size_t) q];
+      }
+      if (rc && !perSequence && !hard) hard = rc;
+    }
+  };
+  std::vector<vce_sequence> xs;
+  std::vector<vce_sequence_result> xr;
+  for (int32_t k : plan.whole) { xs.push_back(seqs[k]); xr.push_back(results[k]); }
+  for (auto& p : plan.pieces) { xs.push_back(p->view); xr.push_back(p->res); }
+  std::vector<int64_t> xsum;
+  round(xs, xr, xsum);
+  if (hard) return hard;
+  for (size_t i = 0; i < plan.whole.size(); ++i) {
+    results[plan.whole[i]] = xr[i];
+    for (int q = 0; q < 8; ++q) summary[(size_t) plan.whole[i] * 8 + (size_t) q] = xsum[i * 8 + (size_t) q];
+  }
+  for (size_t i = 0; i < plan.pieces.size(); ++i) plan.pieces[i]->res = xr[plan.whole.size() + i];
+  std::vector<int32_t> redo;
+  for (const vce::SplitSeq& ss : plan.split) {
+    if (vce::splitMerge(plan, ss, seqs, results)) vce::splitSummary(seqs[ss.seq], results[ss.seq], summary.data() + (size_t) ss.seq * 8);
+    else redo.push_back(ss.seq);
+  }
+  if (out_stats) { out_stats[0] = (int64_t) plan.split.size(); out_stats[1] = (int64_t) plan.pieces.size(); out_stats[2] = (int64_t) redo.size(); }
+  if (!redo.empty()) {
+    std::vector<vce_sequence> ys;
+    std::vector<vce_sequence_result> yr;
+    for (int32_t k : redo) { ys.push_back(seqs[k]); yr.push_back(results[k]); }
+    std::vector<int64_t> ysum;
+    round(ys, yr, ysum);
+    if (hard) return hard;
+    for (size_t i = 0; i < redo.size(); ++i) {
+      results[redo[i]] = yr[i];
+      for (int q = 0; q < 8; ++q) summary[(size_t) redo[i] * 8 + (size_t) q] = ysum[i * 8 + (size_t) q];
+    }
+  }
+  g_summary = summary;
+  for (int32_t k = 0; k < n_seq; ++k) if (results[k].error) return results[k].error;
+  return VCE_OK;
 }
 
 // staged job on the emulation: prepare once, execute `runs` times, finish (exercises the re-runnable path)

@@ -32,6 +32,24 @@ def main():
         compare_results(want, got, seqs, what="%d devices, %s" % (n, name))
         if name == "default":
             assert np.array_equal(eng.submit_summary(len(seqs)).sum(axis=0), multigpu.summary_counts(want))
+    # long sequences cut into pieces so that the devices balance (vce_split.h).  24 chromosomes balance on a few devices
+    # by themselves, so the thresholds are lowered to force the cuts; results must not change, and the counters must say that
+    # sequences were cut (and, with a one-variant overlap, that some were evaluated again in one piece)
+    import ctypes
+    lib = eng.lib.lib
+    lib.vce_submit_stats.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.c_int32]
+    want = oracle.submit(CONFIGS["default"], seqs, threads=8)
+    for overlap, imb in ((512, "1.0"), (1, "1.0")):
+        os.environ.update(VCE_SPLIT_IMBALANCE=imb, VCE_SPLIT_MIN="4000", VCE_SPLIT_OVERLAP=str(overlap))
+        got = eng.submit(CONFIGS["default"], seqs)
+        st = (ctypes.c_double * 9)()
+        lib.vce_submit_stats(st, 9)
+        compare_results(want, got, seqs, what="%d devices, sequences cut (overlap %d)" % (n, overlap))
+        assert np.array_equal(eng.submit_summary(len(seqs)).sum(axis=0), multigpu.summary_counts(want))
+        assert st[6] >= 10 and st[7] >= 2 * st[6], list(st)
+        print("split: %d sequences cut into %d pieces, %d evaluated again in one piece (overlap %d)" % (st[6], st[7], st[8], overlap))
+    for k in ("VCE_SPLIT_IMBALANCE", "VCE_SPLIT_MIN", "VCE_SPLIT_OVERLAP"):
+        os.environ.pop(k, None)
     # a single sequence takes the one-device path of the same pool
     one = [seqs[0]]
     compare_results(oracle.submit(CONFIGS["default"], one), eng.submit(CONFIGS["default"], one), one, what="one sequence")
