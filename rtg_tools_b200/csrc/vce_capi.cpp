@@ -6,9 +6,11 @@
 // so that a steady-state vce_submit() pays no allocation; concurrent callers each get their own context and share
 // the host worker pool.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -322,6 +324,8 @@ static int submitOn(int devIndex, const vce_config* cfg, const std::vector<int32
   return rc;
 }
 
+static vce::WorkerPool* rocPool();
+
 int vce_submit(const vce_config* cfg, int32_t n_seq, const vce_sequence* seqs, vce_sequence_result* results) {
   if (!cfg || !results || n_seq < 0 || (n_seq > 0 && !seqs)) return fail(VCE_ERR_BAD_ARGUMENT, "null argument");
   size_t nDev;
@@ -363,10 +367,18 @@ int vce_submit(const vce_config* cfg, int32_t n_seq, const vce_sequence* seqs, v
     if (const char* e = std::getenv("VCE_SPLIT_MIN")) so.minVariants = std::atoll(e);
     if (const char* e = std::getenv("VCE_SPLIT_OVERLAP")) so.overlap = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("VCE_SPLIT_IMBALANCE")) so.imbalance = std::atof(e);
+    if (const char* e = std::getenv("VCE_SPLIT_PIECES")) so.piecesPerDevice = std::max(1, std::atoi(e));
     vce::SplitPlan plan;
+    const auto tCall = std::chrono::steady_clock::now();
+    // planning and stitching are per-sequence tasks of the shared worker pool (no engine is running at those moments)
+    vce::WorkerPool* wp = rocPool();
+    auto par = [wp](int n, const std::function<void(int)>& fn) { if (n > 0) wp->parallelFor(n, [&](int t, int) { fn(t); }); };
     const char* se = std::getenv("VCE_SPLIT");
     if (se && std::atoi(se) == 0) { for (int32_t k = 0; k < n_seq; ++k) plan.whole.push_back(k); }
-    else vce::splitPlan(*cfg, n_seq, seqs, results, (int) nDev, so, plan);
+    else vce::splitPlan(*cfg, n_seq, seqs, results, (int) nDev, so, plan, par);
+    const bool timing = std::getenv("VCE_TIMING") != nullptr;
+    const auto tPlan = std::chrono::steady_clock::now();
+    if (timing && !plan.split.empty()) std::fprintf(stderr, "[vce] split: planning %.2f ms\n", std::chrono::duration<double, std::milli>(tPlan - tCall).count());
     std::vector<int64_t> summary((size_t) n_seq * 8, 0);
     for (int i = 0; i < 6; ++i) t_submitStats[i] = 0;
     int hardRc = VCE_OK;
@@ -412,9 +424,13 @@ int vce_submit(const vce_config* cfg, int32_t n_seq, const vce_sequence* seqs, v
     }
     for (size_t i = 0; i < plan.pieces.size(); ++i) plan.pieces[i]->res = xr[plan.whole.size() + i];
     std::vector<int32_t> redo;
-    for (const vce::SplitSeq& ss : plan.split) {
-      if (vce::splitMerge(plan, ss, seqs, results)) vce::splitSummary(seqs[ss.seq], results[ss.seq], summary.data() + (size_t) ss.seq * 8);
-      else redo.push_back(ss.seq);
+    const auto tRun = std::chrono::steady_clock::now();
+    vce::splitMergeAll(plan, seqs, results, summary.data(), redo, par);
+    if (timing && !plan.split.empty()) {
+      const auto tMerge = std::chrono::steady_clock::now();
+      std::fprintf(stderr, "[vce] split: %zu sequences cut into %zu pieces; devices %.2f ms, stitching %.2f ms, %zu to evaluate again\n",
+                   plan.split.size(), plan.pieces.size(), std::chrono::duration<double, std::milli>(tRun - tPlan).count(),
+                   std::chrono::duration<double, std::milli>(tMerge - tRun).count(), redo.size());
     }
     t_splitStats[0] = (double) plan.split.size(); t_splitStats[1] = (double) plan.pieces.size(); t_splitStats[2] = (double) redo.size();
     if (!redo.empty()) {   // a cut that could not be verified (or a piece with an error): those sequences in one piece

@@ -1830,7 +1830,9 @@ std::vector<TemplateEntry> g_templates;
 bool templateRegistryLookup(int device, const uint8_t* bases, int32_t len, const uint32_t** t2, const uint32_t** nmask) {
   std::lock_guard<std::mutex> lk(g_tmplMu);
   for (const TemplateEntry& e : g_templates) {
-    if (e.bases == bases && e.len == len && e.device == device) {
+    // (a shorter length is a prefix of the registered sequence: the pieces of a cut sequence end before the next piece's
+    // first variant, vce_split.h)
+    if (e.bases == bases && len <= e.len && e.device == device) {
       *t2 = e.t2;
       *nmask = e.nmask;
       return true;

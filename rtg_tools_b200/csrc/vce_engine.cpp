@@ -1642,7 +1642,11 @@ int Engine::widePack(PassCtx& pc, const std::vector<std::pair<RegKey, int>>& ite
         }
       }
       if (lo == INT_MAX) lo = 0;
-      const int ws = std::max(0, std::min(lo, d.startPos < 0 ? 0 : d.startPos) - 1);
+      // A sequence's first region starts its path at -1 and jumps to the base before its first variant without reading
+      // anything in between (PathFinder.skipToNextVariant :271-282 -> moveForward): its window starts where any other
+      // region's does.  (It used to start at 0: harmless for a chromosome, but a PIECE of a cut sequence, vce_split.h, starts
+      // tens of megabases in.)
+      const int ws = std::max(0, std::min(lo, d.startPos < 0 ? lo - 1 : d.startPos) - 1);
       // regions of the full-budget tiers sit in repeats more often than not: a wider window from the start (there are few of them)
       const int baseMargin = wb.tier[q] >= kTierCta ? std::max(opt_.margin, opt_.wideMargin) : opt_.margin;
       long we = extra < 0 ? (long) d.tmplLen : sz[q].hi + baseMargin + extra;

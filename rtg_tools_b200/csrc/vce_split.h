@@ -12,8 +12,9 @@
 //     before, and the allele id of the last one: MaxSumBoth.java:55,76).  The right piece sees the true carry at the cut when
 //     the overlap before the cut holds an included baseline variant and its results there equal the left piece's;
 //   * VERIFIED: the right piece must have included a baseline variant before the cut, and from that variant's start to the
-//     end of the overlap the two pieces must agree on every variant (status, orientation, weight bits) and on the sync points
-//     around the cut.  Otherwise the sequence is evaluated again in one piece -- exactness never depends on where the cuts fell;
+//     end of the overlap the two pieces must agree on every variant (status, orientation, weight bits, sync id) and on the
+//     sync points, at least one of which must lie before the cut.  Otherwise the sequence is evaluated again in one piece --
+//     exactness never depends on where the cuts fell;
 //   * sync points are joined in the middle of the gap before each cut (sync ids are position based: unchanged), warnings taken from the
 //     owning piece, and the phasing counts (PhasingEvaluator.java:55-142: a state machine over the whole sequence) and the
 //     split writers' counters are recomputed from the stitched per-variant results.
@@ -166,6 +167,11 @@ inline int splitSequence(const vce_sequence* seqs, const vce_sequence_result* re
     p->joinPos = j == 0 ? INT_MIN : own.pos - o.gap / 2;
     // the view: the caller's arrays from variant lo on, slot and base offsets rebased to the piece
     p->view = s;
+    // The piece's sequence ends right before the first variant it does not hold (a gap of `gap` bases or more lies before
+    // that variant): the search of its last region then finishes there instead of asking for the far end of the chromosome
+    // (Path.finished: the last base of the template is read, HaplotypePlayback.java:170-214).  A prefix of a registered
+    // template is recognised as registered.
+    if (j < m - 1) p->view.template_len = std::min(s.template_len, last.pos);
     memset(&p->res, 0, sizeof(p->res));
     for (int side = 0; side < 2; ++side) {
       const vce_variants& v = side == 0 ? s.calls : s.baseline;
@@ -235,22 +241,45 @@ inline double splitAssign(const std::vector<int64_t>& weight, int nDev, std::vec
   return sum > 0 ? (double) mx * nDev / (double) sum : 1.0;
 }
 
-// Decides which sequences to cut for `nDev` devices and cuts them.
+// Runs fn(0) .. fn(n - 1), possibly concurrently (the caller's worker pool; the emulation runs them in turn).
+struct SplitSerial {
+  template <class F> void operator()(int n, F fn) const { for (int i = 0; i < n; ++i) fn(i); }
+};
+
+// Decides which sequences to cut for `nDev` devices and cuts them (every sequence's scan is a task of `par`).
+template <class Par>
 inline void splitPlan(const vce_config& cfg, int32_t nSeq, const vce_sequence* seqs, const vce_sequence_result* results, int nDev,
-                      const SplitOptions& o, SplitPlan& plan) {
+                      const SplitOptions& o, SplitPlan& plan, const Par& par) {
   std::vector<int64_t> w((size_t) nSeq);
   int64_t total = 0;
   for (int32_t k = 0; k < nSeq; ++k) { w[(size_t) k] = (int64_t) seqs[k].calls.n + seqs[k].baseline.n; total += w[(size_t) k]; }
   std::vector<int> dev;
   const bool wanted = nDev > 1 && cfg.n_passes == 1 && cfg.flag_alternates == 0 && splitAssign(w, nDev, dev) > o.imbalance;
   const int64_t target = std::max<int64_t>(o.minVariants / 2, total / std::max(1, nDev) / std::max(1, o.piecesPerDevice));
-  for (int32_t k = 0; k < nSeq; ++k) {
-    int made = 0;
-    if (wanted && w[(size_t) k] >= o.minVariants && w[(size_t) k] > target + target / 2) {
-      made = splitSequence(seqs, results, k, (int) ((w[(size_t) k] + target - 1) / target), o, plan);
+  std::vector<int32_t> cand;
+  for (int32_t k = 0; k < nSeq; ++k) if (wanted && w[(size_t) k] >= o.minVariants && w[(size_t) k] > target + target / 2) cand.push_back(k);
+  std::vector<SplitPlan> local(cand.size());
+  std::vector<int> made(cand.size(), 0);
+  par((int) cand.size(), [&](int i) {
+    const int32_t k = cand[(size_t) i];
+    made[(size_t) i] = splitSequence(seqs, results, k, (int) ((w[(size_t) k] + target - 1) / target), o, local[(size_t) i]);
+  });
+  std::vector<uint8_t> cut((size_t) nSeq, 0);
+  for (size_t i = 0; i < cand.size(); ++i) {
+    if (made[i] < 2) continue;
+    cut[(size_t) cand[i]] = 1;
+    const int base = (int) plan.pieces.size();
+    for (auto& p : local[i].pieces) plan.pieces.push_back(std::move(p));
+    for (SplitSeq& ss : local[i].split) {
+      for (int& q : ss.pieces) q += base;
+      plan.split.push_back(std::move(ss));
     }
-    if (made < 2) plan.whole.push_back(k);
   }
+  for (int32_t k = 0; k < nSeq; ++k) if (!cut[(size_t) k]) plan.whole.push_back(k);
+}
+inline void splitPlan(const vce_config& cfg, int32_t nSeq, const vce_sequence* seqs, const vce_sequence_result* results, int nDev,
+                      const SplitOptions& o, SplitPlan& plan) {
+  splitPlan(cfg, nSeq, seqs, results, nDev, o, plan, SplitSerial());
 }
 
 // ---- stitching
@@ -394,21 +423,27 @@ inline bool splitMerge(const SplitPlan& plan, const SplitSeq& ss, const vce_sequ
           if (memcmp(&a.alleleIds[side][ia * VCE_MAX_PLOIDY], &b.alleleIds[side][ib * VCE_MAX_PLOIDY], VCE_MAX_PLOIDY) != 0) return false;
         }
         if (memcmp(&a.weight[side][ia], &b.weight[side][ib], sizeof(double)) != 0) return false;
+        if (a.syncId[side][ia] != b.syncId[side][ib]) return false;   // the same floor sync point in both pieces
       }
     }
-    // the sync points of the overlap, from the join position to the last variant both pieces hold
-    const int32_t from = b.joinPos;
+    // The sync points from that variant on, up to the last variant both pieces hold, must be the same -- and one of them must
+    // lie before the cut: there both searches stand in sync at the same position with the same carries, whatever the right
+    // piece assumed at its start (in a long tandem repeat the whole sequence's search may NOT be in sync where the piece began).
+    const int32_t from = fromPos;
     int32_t to = INT_MAX;
-    for (int side = 0; side < 2; ++side) if (a.hi[side] > 0 && a.hi[side] <= (int) ss.start[side].size() && a.hi[side] - 1 >= b.lo[side]) to = std::min(to, ss.start[side][(size_t) a.hi[side] - 1]);
+    for (int side = 0; side < 2; ++side) if (a.hi[side] > b.lo[side]) to = std::min(to, ss.start[side][(size_t) a.hi[side] - 1]);
     size_t qa = 0, qb = 0;
     const size_t na = (size_t) a.res.n_sync[0], nb = (size_t) b.res.n_sync[0];
     while (qa < na && a.sync[0][qa] < from) ++qa;
     while (qb < nb && b.sync[0][qb] < from) ++qb;
+    bool beforeCut = false;
     while (qa < na && qb < nb && a.sync[0][qa] < to && b.sync[0][qb] < to) {
       if (a.sync[0][qa] != b.sync[0][qb]) return false;
+      if (a.sync[0][qa] < b.joinPos) beforeCut = true;
       ++qa; ++qb;
     }
     if ((qa < na && a.sync[0][qa] < to) != (qb < nb && b.sync[0][qb] < to)) return false;
+    if (!beforeCut) return false;
   }
   // 2. sync points: piece j contributes the points in [joinPos(j), joinPos(j + 1))
   int nSync = 0;
@@ -463,6 +498,22 @@ inline bool splitMerge(const SplitPlan& plan, const SplitSeq& ss, const vce_sequ
   // 4. the whole-sequence state machine over the stitched results
   splitPhasing(s, out, ss.start, out.phasing);
   return true;
+}
+
+// Stitches every cut sequence (a task of `par` each); `summary` ([nSeq * 8]) receives the writers' counters of the stitched
+// ones, `redo` the sequences whose cuts could not be verified.
+template <class Par>
+inline void splitMergeAll(const SplitPlan& plan, const vce_sequence* seqs, vce_sequence_result* results, int64_t* summary,
+                          std::vector<int32_t>& redo, const Par& par) {
+  std::vector<uint8_t> ok(plan.split.size(), 0);
+  par((int) plan.split.size(), [&](int i) {
+    const SplitSeq& ss = plan.split[(size_t) i];
+    if (splitMerge(plan, ss, seqs, results)) {
+      splitSummary(seqs[ss.seq], results[ss.seq], summary + (size_t) ss.seq * 8);
+      ok[(size_t) i] = 1;
+    }
+  });
+  for (size_t i = 0; i < plan.split.size(); ++i) if (!ok[i]) redo.push_back(plan.split[i].seq);
 }
 
 }  // namespace vce

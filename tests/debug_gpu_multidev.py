@@ -28,8 +28,8 @@ def main():
     packed = eng.lib.pack(capi.Config(), seqs)
     ref = None
     for label, env in (("whole sequences (VCE_SPLIT=0)", {"VCE_SPLIT": "0"}), ("default rule (cut when max/mean > 1.1)", {}),
-                       ("forced cuts (VCE_SPLIT_IMBALANCE=1.0)", {"VCE_SPLIT_IMBALANCE": "1.0"})):
-        for k in ("VCE_SPLIT", "VCE_SPLIT_IMBALANCE"):
+                       ("forced cuts (VCE_SPLIT_IMBALANCE=1.0, VCE_SPLIT_PIECES=8 x devices)", {"VCE_SPLIT_IMBALANCE": "1.0", "VCE_SPLIT_PIECES": str(8 * n)})):
+        for k in ("VCE_SPLIT", "VCE_SPLIT_IMBALANCE", "VCE_SPLIT_PIECES"):
             os.environ.pop(k, None)
         os.environ.update(env)
         ts = []
@@ -38,6 +38,10 @@ def main():
             rc = eng.lib.submit_packed(packed)
             ts.append((time.perf_counter() - t0) * 1e3)
             assert rc == 0
+        if env.get("VCE_SPLIT_IMBALANCE"):      # one more call with the split path's own laps on stderr
+            os.environ["VCE_TIMING"] = "1"
+            eng.lib.submit_packed(packed)
+            os.environ.pop("VCE_TIMING")
         st = (ctypes.c_double * 9)()
         lib.vce_submit_stats(st, 9)
         import copy

@@ -197,7 +197,7 @@ class EmulBackend : public Backend {
   struct Tmpl { const uint8_t* bases; int32_t len; std::vector<uint32_t> t2, nmask; };
   static std::vector<Tmpl>& templates() { static std::vector<Tmpl> t; return t; }
   bool templateLookup(const uint8_t* bases, int32_t len, const uint32_t** t2, const uint32_t** nmask) override {
-    for (const Tmpl& t : templates()) if (t.bases == bases && t.len == len) { *t2 = t.t2.data(); *nmask = t.nmask.data(); return true; }
+    for (const Tmpl& t : templates()) if (t.bases == bases && len <= t.len) { *t2 = t.t2.data(); *nmask = t.nmask.data(); return true; }
     return false;
   }
   int residentUpload(const void* pinned, size_t, void** dev, int* eventId) override {
@@ -590,10 +590,7 @@ int emul_vce_submit_split(const vce_config* cfg, int32_t n_seq, const vce_sequen
   }
   for (size_t i = 0; i < plan.pieces.size(); ++i) plan.pieces[i]->res = xr[plan.whole.size() + i];
   std::vector<int32_t> redo;
-  for (const vce::SplitSeq& ss : plan.split) {
-    if (vce::splitMerge(plan, ss, seqs, results)) vce::splitSummary(seqs[ss.seq], results[ss.seq], summary.data() + (size_t) ss.seq * 8);
-    else redo.push_back(ss.seq);
-  }
+  vce::splitMergeAll(plan, seqs, results, summary.data(), redo, vce::SplitSerial());
   if (out_stats) { out_stats[0] = (int64_t) plan.split.size(); out_stats[1] = (int64_t) plan.pieces.size(); out_stats[2] = (int64_t) redo.size(); }
   if (!redo.empty()) {
     std::vector<vce_sequence> ys;

@@ -76,3 +76,22 @@ def test_split_dense_and_fuzz_sequences_fall_back_when_a_cut_cannot_be_verified(
         redone += st["redone"]
         split += st["split"]
     assert split >= 24 and redone >= 1      # the fall-back did run
+
+
+def test_split_pieces_of_registered_templates(emul, oracle):
+    """Pieces end right before the next piece's first variant (a shorter template length): a registered template is recognised
+    through its prefix, and the resident packet builder cuts the pieces' windows out of the same 2-bit copy."""
+    emul.lib.emul_template_register.argtypes = [ctypes.c_void_p, ctypes.c_int32]
+    emul.lib.emul_resident_uploads.restype = ctypes.c_int64
+    seqs = synth.make_pair(20_000_000, n_chrom=3)
+    want = oracle.submit(CONFIGS["default"], seqs, threads=6)
+    try:
+        for s in seqs:
+            s.template = np.ascontiguousarray(s.template, np.uint8)
+            emul.lib.emul_template_register(s.template.ctypes.data, int(s.template.shape[0]))
+        got, st = emul.submit_split(CONFIGS["default"], seqs, 6, min_variants=1000, overlap=32, imbalance=1.0, pieces_per_device=3)
+        assert st["split"] == 3 and st["redone"] == 0
+        assert emul.lib.emul_resident_uploads() > 0
+        compare_results(want, got, seqs, what="registered templates")
+    finally:
+        emul.lib.emul_template_register(None, 0)
