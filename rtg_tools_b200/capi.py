@@ -396,7 +396,7 @@ class Library:
         return results
 
     def submit_split(self, cfg: Config, seqs: List[Sequence], n_dev: int, min_variants=100000, overlap=2048, gap=64, imbalance=1.1,
-                     pieces_per_device=4):
+                     pieces_per_device=4, force=True):
         """Emulation only: vce_submit over `n_dev` emulated devices with the sequence splitting of vce_split.h.
         Returns (results, {"split", "pieces", "redone"})."""
         ccfg, cseqs, cres, results, keep = self.pack(cfg, seqs)
@@ -404,7 +404,7 @@ class Library:
         f.restype = C.c_int
         f.argtypes = [C.POINTER(CConfig), C.c_int32, C.POINTER(CSequence), C.POINTER(CSequenceResult), C.c_int32,
                       C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
-        opts = (C.c_int64 * 5)(int(min_variants), int(overlap), int(gap), int(round(imbalance * 100)), int(pieces_per_device))
+        opts = (C.c_int64 * 6)(int(min_variants), int(overlap), int(gap), int(round(imbalance * 100)), int(pieces_per_device), int(bool(force)))
         st = (C.c_int64 * 3)()
         rc = f(C.byref(ccfg), len(seqs), cseqs, cres, int(n_dev), opts, st)
         self.unpack(cres, results, keep)

@@ -374,6 +374,7 @@ int vce_submit(const vce_config* cfg, int32_t n_seq, const vce_sequence* seqs, v
     vce::WorkerPool* wp = rocPool();
     auto par = [wp](int n, const std::function<void(int)>& fn) { if (n > 0) wp->parallelFor(n, [&](int t, int) { fn(t); }); };
     const char* se = std::getenv("VCE_SPLIT");
+    so.force = se && std::atoi(se) == 1;   // 1: SURVEY 8e's rule alone (max / mean > 1.1), without the cost estimate
     if (se && std::atoi(se) == 0) { for (int32_t k = 0; k < n_seq; ++k) plan.whole.push_back(k); }
     else vce::splitPlan(*cfg, n_seq, seqs, results, (int) nDev, so, plan, par);
     const bool timing = std::getenv("VCE_TIMING") != nullptr;

@@ -1662,6 +1662,13 @@ int Engine::widePack(PassCtx& pc, const std::vector<std::pair<RegKey, int>>& ite
     for (int side = 0; side < 2; ++side) { vOff[side][n] = av[side]; sOff[side][n] = as[side]; nOff[side][n] = an[side]; }
   }
   wb.so = so;
+  if (tmw.on) {
+    long mx = 0;
+    size_t at = 0;
+    for (size_t q = 0; q < n; ++q) if (wb.descs[q].winLen > mx) { mx = wb.descs[q].winLen; at = q; }
+    if (n) std::fprintf(stderr, "[vce]   wide: %zu window bytes over %zu regions; longest window %ld (region %d of its sequence, start %d, tier %d)\n",
+                        winBytes, n, mx, wb.ids[at].j, wb.descs[at].winStart, wb.tier[at]);
+  }
   for (int side = 0; side < 2; ++side) {
     HostSide& hs = pd.side[side];
     hs.gtPloidy = pc.gtPloidy[side];

@@ -43,6 +43,22 @@ struct SplitOptions {
   int gap = 64;                   // bases without any variant before a cut
   double imbalance = 1.1;         // split only when the longest-processing-time assignment of whole sequences exceeds this
   int piecesPerDevice = 4;        // target piece size = mean device load / this
+  // Cutting costs host time (the scan for gaps, result buffers, verification, the phasing recount: measured ~5 ns per variant of
+  // a cut sequence on the B200 box's host, profiles/README.md) and saves device time (~10 ns per variant the longest device
+  // queue gets shorter).  Unless `force` is set, sequences are cut only when the saving is the larger of the two -- which
+  // is the case when a few long sequences dominate a batch, and is NOT the case for 24 chromosomes on 8 devices.
+  bool force = false;
+  double hostNsPerVariant = 5.0, deviceNsPerVariant = 10.0;
+};
+
+template <class T>
+struct SplitRaw {               // an uninitialised array (no page is touched before the engine's workers write it)
+  std::unique_ptr<T[]> p;
+  void alloc(size_t n) { p.reset(new T[n > 0 ? n : 1]); }
+  T* data() { return p.get(); }
+  const T* data() const { return p.get(); }
+  T& operator[](size_t i) { return p[i]; }
+  const T& operator[](size_t i) const { return p[i]; }
 };
 
 // One piece of one sequence, with its own input view and result buffers.
@@ -55,11 +71,12 @@ struct SplitPiece {
   vce_sequence view;
   vce_sequence_result res;
   std::vector<int32_t> alleleOff[2], ntOff[2];
-  std::vector<uint8_t> status[2], original[2];
-  std::vector<int8_t> alleleIds[2];
-  std::vector<double> weight[2];
-  std::vector<int32_t> syncId[2];
-  std::vector<int32_t> sync[2];
+  // result buffers: NOT initialised -- the engine writes every entry of every per-variant array (checked with poisoned buffers)
+  SplitRaw<uint8_t> status[2], original[2];
+  SplitRaw<int8_t> alleleIds[2];
+  SplitRaw<double> weight[2];
+  SplitRaw<int32_t> syncId[2];
+  SplitRaw<int32_t> sync[2];
   std::vector<vce_warning> warn;
 };
 
@@ -78,27 +95,35 @@ struct SplitPlan {
 // ---- bounds (Allele.getAlleleBounds, Allele.java:195-206) and the wide gaps of one sequence
 struct SplitBoundary { int32_t c, b, pos; };   // first call / baseline variant after the gap, start of the earlier of the two
 
-inline bool splitScan(const vce_sequence& s, int gap, std::vector<int32_t> start[2], std::vector<SplitBoundary>& bounds) {
-  std::vector<int32_t> end[2];
-  for (int side = 0; side < 2; ++side) {
-    const vce_variants& v = side == 0 ? s.calls : s.baseline;
-    start[side].resize((size_t) v.n);
-    end[side].resize((size_t) v.n);
-    int32_t prev = INT_MIN;
-    for (int i = 0; i < v.n; ++i) {
-      int32_t a = INT_MAX, e = INT_MIN;
-      for (int q = v.allele_off[i]; q < v.allele_off[i + 1]; ++q) {
-        if (!v.allele_null[q]) { a = std::min(a, v.allele_start[q]); e = std::max(e, v.allele_end[q]); }
-      }
-      if (a == INT_MAX || a < prev) return false;   // no playable allele, or not sorted by start: not split
-      prev = a;
-      start[side][(size_t) i] = a;
-      end[side][(size_t) i] = e;
+// Allele bounds of the variants [lo, hi) of one side; false when a variant has no playable allele or the starts are not ascending
+// (such a sequence is not cut).  Chunks of one sequence run as separate tasks.
+inline bool splitBoundsChunk(const vce_variants& v, int lo, int hi, int32_t* start, int32_t* end) {
+  auto bounds = [&](int i, int32_t& a, int32_t& e) {
+    a = INT_MAX; e = INT_MIN;
+    for (int q = v.allele_off[i]; q < v.allele_off[i + 1]; ++q) {
+      if (!v.allele_null[q]) { a = std::min(a, v.allele_start[q]); e = std::max(e, v.allele_end[q]); }
     }
+  };
+  int32_t prev = INT_MIN, pe;
+  if (lo > 0) bounds(lo - 1, prev, pe);
+  for (int i = lo; i < hi; ++i) {
+    int32_t a, e;
+    bounds(i, a, e);
+    if (a == INT_MAX || a < prev) return false;
+    prev = a;
+    start[i] = a;
+    end[i] = e;
   }
+  return true;
+}
+
+// The wide gaps of one sequence from its variants' bounds.
+inline void splitScan(const vce_sequence& s, int gap, const std::vector<int32_t> start[2], const std::vector<int32_t> end[2],
+                      std::vector<SplitBoundary>& bounds) {
   const int nc = s.calls.n, nb = s.baseline.n;
   int c = 0, b = 0;
   int64_t maxEnd = INT_MIN;
+  bounds.reserve((size_t) (nc + nb) / 2 + 16);
   while (c < nc || b < nb) {
     const bool takeC = b >= nb || (c < nc && start[0][(size_t) c] <= start[1][(size_t) b]);
     const int32_t st = takeC ? start[0][(size_t) c] : start[1][(size_t) b];
@@ -107,19 +132,21 @@ inline bool splitScan(const vce_sequence& s, int gap, std::vector<int32_t> start
     maxEnd = std::max<int64_t>(maxEnd, st);
     if (takeC) ++c; else ++b;
   }
-  return true;
 }
 
 // Cuts sequence `k` into about `nPieces` pieces; appends them to the plan.  Returns the number of pieces made (0 or 1 = not split).
 inline int splitSequence(const vce_sequence* seqs, const vce_sequence_result* results, int k, int nPieces, const SplitOptions& o,
-                         SplitPlan& plan) {
+                         std::vector<int32_t> start[2], const std::vector<int32_t> end[2], SplitPlan& plan) {
   const vce_sequence& s = seqs[k];
   const int64_t total = (int64_t) s.calls.n + s.baseline.n;
   if (nPieces < 2 || s.calls.n == 0 || s.baseline.n == 0) return 0;
   SplitSeq ss;
   ss.seq = k;
   std::vector<SplitBoundary> bd;
-  if (!splitScan(s, o.gap, ss.start, bd) || bd.empty()) return 0;
+  splitScan(s, o.gap, start, end, bd);
+  if (bd.empty()) return 0;
+  ss.start[0].swap(start[0]);
+  ss.start[1].swap(start[1]);
   auto count = [&](const SplitBoundary& x) { return (int64_t) x.c + x.b; };
   auto nearest = [&](int64_t target) {   // boundary whose variant count is closest to target
     size_t lo = 0, hi = bd.size();
@@ -196,11 +223,11 @@ inline int splitSequence(const vce_sequence* seqs, const vce_sequence_result* re
       w.allele_nt_off = p->ntOff[side].data();
       w.nt = v.nt + nt0;
       vce_side_result& r = side == 0 ? p->res.calls : p->res.baseline;
-      p->status[side].assign((size_t) n, 0);
-      p->original[side].assign((size_t) n, 0);
-      p->alleleIds[side].assign((size_t) n * VCE_MAX_PLOIDY, -2);
-      p->weight[side].assign((size_t) n, 0.0);
-      p->syncId[side].assign((size_t) n, 0);
+      p->status[side].alloc((size_t) n);
+      p->original[side].alloc((size_t) n);
+      p->alleleIds[side].alloc((size_t) n * VCE_MAX_PLOIDY);
+      p->weight[side].alloc((size_t) n);
+      p->syncId[side].alloc((size_t) n);
       r.status = p->status[side].data();
       r.original = p->original[side].data();
       r.allele_ids = p->alleleIds[side].data();
@@ -208,10 +235,11 @@ inline int splitSequence(const vce_sequence* seqs, const vce_sequence_result* re
       r.sync_id = p->syncId[side].data();
     }
     const int cap = p->view.calls.n + p->view.baseline.n + 2;
-    for (int pass = 0; pass < 2; ++pass) {
-      p->sync[pass].assign((size_t) cap, 0);
+    for (int pass = 0; pass < 2; ++pass) {   // (single-pass configurations only: the second list stays empty)
+      const int c = pass == 0 ? cap : 2;
+      p->sync[pass].alloc((size_t) c);
       p->res.sync_points[pass] = p->sync[pass].data();
-      p->res.sync_cap[pass] = cap;
+      p->res.sync_cap[pass] = c;
     }
     p->warn.resize((size_t) std::max(1, results[k].warn_cap));
     p->res.warnings = p->warn.data();
@@ -224,7 +252,7 @@ inline int splitSequence(const vce_sequence* seqs, const vce_sequence_result* re
 }
 
 // Longest-processing-time greedy: item weights -> device of every item; returns max load / mean load.
-inline double splitAssign(const std::vector<int64_t>& weight, int nDev, std::vector<int>& device) {
+inline double splitAssign(const std::vector<int64_t>& weight, int nDev, std::vector<int>& device, int64_t* maxLoad = nullptr) {
   std::vector<int> order(weight.size());
   for (size_t i = 0; i < order.size(); ++i) order[i] = (int) i;
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return weight[(size_t) a] > weight[(size_t) b]; });
@@ -238,6 +266,7 @@ inline double splitAssign(const std::vector<int64_t>& weight, int nDev, std::vec
   }
   int64_t sum = 0, mx = 0;
   for (int64_t l : load) { sum += l; mx = std::max(mx, l); }
+  if (maxLoad) *maxLoad = mx;
   return sum > 0 ? (double) mx * nDev / (double) sum : 1.0;
 }
 
@@ -254,15 +283,46 @@ inline void splitPlan(const vce_config& cfg, int32_t nSeq, const vce_sequence* s
   int64_t total = 0;
   for (int32_t k = 0; k < nSeq; ++k) { w[(size_t) k] = (int64_t) seqs[k].calls.n + seqs[k].baseline.n; total += w[(size_t) k]; }
   std::vector<int> dev;
-  const bool wanted = nDev > 1 && cfg.n_passes == 1 && cfg.flag_alternates == 0 && splitAssign(w, nDev, dev) > o.imbalance;
+  int64_t maxWhole = 0;
+  const bool wanted = nDev > 1 && cfg.n_passes == 1 && cfg.flag_alternates == 0 && splitAssign(w, nDev, dev, &maxWhole) > o.imbalance;
   const int64_t target = std::max<int64_t>(o.minVariants / 2, total / std::max(1, nDev) / std::max(1, o.piecesPerDevice));
   std::vector<int32_t> cand;
-  for (int32_t k = 0; k < nSeq; ++k) if (wanted && w[(size_t) k] >= o.minVariants && w[(size_t) k] > target + target / 2) cand.push_back(k);
+  int64_t cutVariants = 0;
+  for (int32_t k = 0; k < nSeq; ++k) {
+    if (wanted && w[(size_t) k] >= o.minVariants && w[(size_t) k] > target + target / 2) { cand.push_back(k); cutVariants += w[(size_t) k]; }
+  }
+  if (!o.force && !cand.empty()) {
+    const double saved = ((double) maxWhole - 1.03 * (double) total / nDev) * o.deviceNsPerVariant;
+    if (saved <= (double) cutVariants * o.hostNsPerVariant) cand.clear();
+  }
   std::vector<SplitPlan> local(cand.size());
   std::vector<int> made(cand.size(), 0);
+  // 1. allele bounds, in chunks of 64 Ki variants (a long chromosome is many tasks)
+  struct Bounds { std::vector<int32_t> start[2], end[2]; };
+  std::vector<Bounds> bounds(cand.size());
+  struct Chunk { int i, side, lo, hi; };
+  std::vector<Chunk> chunks;
+  for (size_t i = 0; i < cand.size(); ++i) {
+    for (int side = 0; side < 2; ++side) {
+      const int n = side == 0 ? seqs[cand[i]].calls.n : seqs[cand[i]].baseline.n;
+      bounds[i].start[side].resize((size_t) n);
+      bounds[i].end[side].resize((size_t) n);
+      for (int lo = 0; lo < n; lo += 1 << 16) chunks.push_back(Chunk{(int) i, side, lo, std::min(n, lo + (1 << 16))});
+    }
+  }
+  std::vector<uint8_t> bad(cand.size(), 0);
+  par((int) chunks.size(), [&](int t) {
+    const Chunk& ch = chunks[(size_t) t];
+    const vce_sequence& sq = seqs[cand[(size_t) ch.i]];
+    Bounds& bo = bounds[(size_t) ch.i];
+    if (!splitBoundsChunk(ch.side == 0 ? sq.calls : sq.baseline, ch.lo, ch.hi, bo.start[ch.side].data(), bo.end[ch.side].data())) bad[(size_t) ch.i] = 1;
+  });
+  // 2. gaps, cuts, views and result buffers, one task per sequence
   par((int) cand.size(), [&](int i) {
     const int32_t k = cand[(size_t) i];
-    made[(size_t) i] = splitSequence(seqs, results, k, (int) ((w[(size_t) k] + target - 1) / target), o, local[(size_t) i]);
+    if (bad[(size_t) i]) return;
+    made[(size_t) i] = splitSequence(seqs, results, k, (int) ((w[(size_t) k] + target - 1) / target), o, bounds[(size_t) i].start,
+                                     bounds[(size_t) i].end, local[(size_t) i]);
   });
   std::vector<uint8_t> cut((size_t) nSeq, 0);
   for (size_t i = 0; i < cand.size(); ++i) {

@@ -27,8 +27,8 @@ def main():
     lib.vce_submit_stats.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.c_int32]
     packed = eng.lib.pack(capi.Config(), seqs)
     ref = None
-    for label, env in (("whole sequences (VCE_SPLIT=0)", {"VCE_SPLIT": "0"}), ("default rule (cut when max/mean > 1.1)", {}),
-                       ("forced cuts (VCE_SPLIT_IMBALANCE=1.0, VCE_SPLIT_PIECES=8 x devices)", {"VCE_SPLIT_IMBALANCE": "1.0", "VCE_SPLIT_PIECES": str(8 * n)})):
+    for label, env in (("whole sequences (VCE_SPLIT=0)", {"VCE_SPLIT": "0"}), ("default rule (max/mean > 1.1 and the saving estimate)", {}),
+                       ("forced cuts (VCE_SPLIT=1, VCE_SPLIT_IMBALANCE=1.0, VCE_SPLIT_PIECES=8 x devices)", {"VCE_SPLIT": "1", "VCE_SPLIT_IMBALANCE": "1.0", "VCE_SPLIT_PIECES": str(8 * n)})):
         for k in ("VCE_SPLIT", "VCE_SPLIT_IMBALANCE", "VCE_SPLIT_PIECES"):
             os.environ.pop(k, None)
         os.environ.update(env)
@@ -38,7 +38,8 @@ def main():
             rc = eng.lib.submit_packed(packed)
             ts.append((time.perf_counter() - t0) * 1e3)
             assert rc == 0
-        if env.get("VCE_SPLIT_IMBALANCE"):      # one more call with the split path's own laps on stderr
+        if label.startswith("whole") or env.get("VCE_SPLIT_IMBALANCE"):      # one more call with the stage laps on stderr
+            print("==== laps: %s" % label, file=sys.stderr, flush=True)
             os.environ["VCE_TIMING"] = "1"
             eng.lib.submit_packed(packed)
             os.environ.pop("VCE_TIMING")

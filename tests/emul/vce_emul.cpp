@@ -7,6 +7,7 @@
 // `emul_` prefix, and is never linked into or loaded by the product library (rtg_tools_b200/csrc/libvce.so),
 // which fails loudly without a CUDA device.
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -544,14 +545,17 @@ int emul_vce_submit(const vce_config* cfg, int32_t n_seq, const vce_sequence* se
 
 // vce_submit over `n_dev` emulated devices with the sequence splitting of vce_split.h (what vce_capi.cpp does with real devices):
 // the items of every "device" go through an engine of their own, one after the other.  opts = {min variants, overlap, gap,
-// imbalance * 100, pieces per device}; out_stats = {sequences cut, pieces, sequences evaluated again in one piece}.
+// imbalance * 100, pieces per device, force (no cost estimate)}; out_stats = {sequences cut, pieces, sequences evaluated again in one piece}.
 int emul_vce_submit_split(const vce_config* cfg, int32_t n_seq, const vce_sequence* seqs, vce_sequence_result* results, int32_t n_dev,
                           const int64_t* opts, int64_t* out_stats) {
   vce::SplitOptions so;
   so.minVariants = opts[0]; so.overlap = (int) opts[1]; so.gap = (int) opts[2]; so.imbalance = (double) opts[3] / 100.0;
   so.piecesPerDevice = (int) opts[4];
+  so.force = opts[5] != 0;
   vce::SplitPlan plan;
+  const auto t0 = std::chrono::steady_clock::now();
   vce::splitPlan(*cfg, n_seq, seqs, results, n_dev, so, plan);
+  if (std::getenv("VCE_TIMING")) fprintf(stderr, "[emul] split planning (serial) %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
   std::vector<int64_t> summary((size_t) n_seq * 8, 0);
   int hard = 0;
   auto round = [&](std::vector<vce_sequence>& xs, std::vector<vce_sequence_result>& xr, std::vector<int64_t>& xsum) {
@@ -590,7 +594,9 @@ int emul_vce_submit_split(const vce_config* cfg, int32_t n_seq, const vce_sequen
   }
   for (size_t i = 0; i < plan.pieces.size(); ++i) plan.pieces[i]->res = xr[plan.whole.size() + i];
   std::vector<int32_t> redo;
+  const auto t1 = std::chrono::steady_clock::now();
   vce::splitMergeAll(plan, seqs, results, summary.data(), redo, vce::SplitSerial());
+  if (std::getenv("VCE_TIMING")) fprintf(stderr, "[emul] split stitching (serial) %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
   if (out_stats) { out_stats[0] = (int64_t) plan.split.size(); out_stats[1] = (int64_t) plan.pieces.size(); out_stats[2] = (int64_t) redo.size(); }
   if (!redo.empty()) {
     std::vector<vce_sequence> ys;

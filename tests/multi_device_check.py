@@ -40,7 +40,7 @@ def main():
     lib.vce_submit_stats.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.c_int32]
     want = oracle.submit(CONFIGS["default"], seqs, threads=8)
     for overlap, imb in ((512, "1.0"), (1, "1.0")):
-        os.environ.update(VCE_SPLIT_IMBALANCE=imb, VCE_SPLIT_MIN="4000", VCE_SPLIT_OVERLAP=str(overlap), VCE_SPLIT_PIECES="64")
+        os.environ.update(VCE_SPLIT="1", VCE_SPLIT_IMBALANCE=imb, VCE_SPLIT_MIN="4000", VCE_SPLIT_OVERLAP=str(overlap), VCE_SPLIT_PIECES="64")
         got = eng.submit(CONFIGS["default"], seqs)
         st = (ctypes.c_double * 9)()
         lib.vce_submit_stats(st, 9)
@@ -48,7 +48,7 @@ def main():
         assert np.array_equal(eng.submit_summary(len(seqs)).sum(axis=0), multigpu.summary_counts(want))
         assert st[6] >= 10 and st[7] >= 2 * st[6], list(st)
         print("split: %d sequences cut into %d pieces, %d evaluated again in one piece (overlap %d)" % (st[6], st[7], st[8], overlap))
-    for k in ("VCE_SPLIT_IMBALANCE", "VCE_SPLIT_MIN", "VCE_SPLIT_OVERLAP", "VCE_SPLIT_PIECES"):
+    for k in ("VCE_SPLIT", "VCE_SPLIT_IMBALANCE", "VCE_SPLIT_MIN", "VCE_SPLIT_OVERLAP", "VCE_SPLIT_PIECES"):
         os.environ.pop(k, None)
     # a single sequence takes the one-device path of the same pool
     one = [seqs[0]]

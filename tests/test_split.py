@@ -95,3 +95,16 @@ def test_split_pieces_of_registered_templates(emul, oracle):
         compare_results(want, got, seqs, what="registered templates")
     finally:
         emul.lib.emul_template_register(None, 0)
+
+
+def test_split_cost_estimate_keeps_balanced_genomes_whole(emul, oracle):
+    """Without `force` a cut must pay for itself: 24 chromosomes on 8 emulated devices (max / mean ~1.1) stay whole, one long
+    sequence next to two short ones is cut."""
+    seqs = synth.make_pair(60_000_000, n_chrom=24)
+    got, st = emul.submit_split(CONFIGS["default"], seqs, 8, min_variants=2000, overlap=64, force=False)
+    assert st["split"] == 0
+    seqs = synth.make_pair(12_000_000, n_chrom=1) + synth.make_pair(1_000_000, n_chrom=2, genome_seed=7)
+    want = oracle.submit(CONFIGS["default"], seqs, threads=6)
+    got, st = emul.submit_split(CONFIGS["default"], seqs, 8, min_variants=2000, overlap=64, force=False)
+    assert st["split"] == 1 and st["pieces"] >= 8
+    compare_results(want, got, seqs, what="one dominant sequence")
