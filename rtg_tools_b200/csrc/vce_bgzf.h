@@ -6,7 +6,8 @@
 //          SAM spec 4.1 (a BGZF file is a series of gzip members of at most 64 KiB with a "BC" extra field carrying the
 //          member size), RFC 1952 (member header / CRC32 / ISIZE trailer) and RFC 1951 (DEFLATE: stored, fixed and dynamic
 //          Huffman blocks).  One BGZF block per warp: every lane runs the same bit reader and Huffman decode (table reads
-//          are broadcasts, no divergence), literals are stored by lane 0, LZ77 matches are copied by all lanes.
+//          are broadcasts, no divergence), literals are stored by lane 0, LZ77 matches are copied by all lanes.  Table entries are
+//          pre-decoded (base value, number of extra bits, kind), so that a symbol costs one look-up and one bit-field extract.
 //   tabix  AbstractIndexReader.getFilePointers (src/com/rtg/tabix/AbstractIndexReader.java:102-205, reg2bins :238-262) and the
 //          TabixIndexReader constructor (TabixIndexReader.java:63-146) as plain host code over the inflated index: the virtual
 //          offsets [begin, end) that hold a region's records.  The index itself is BGZF and goes through the same kernel.
@@ -123,16 +124,48 @@ struct HuffMeta {            // canonical code description for the bit-by-bit wa
   uint16_t index[16];        // position of that code's symbol in `sym`
 };
 
-struct InflateWs {           // per-warp workspace (shared memory on the device): 3.9 KB
-  uint16_t litTab[1 << kLitBits];    // (symbol << 4) | length, 0 = not in the table
-  uint16_t distTab[1 << kDistBits];
-  uint16_t clTab[1 << kClBits];
+// Pre-decoded table entry of the literal/length and distance codes: what the inner loop needs, without arithmetic on the symbol.
+//   bits 0-3  code length (0 = the code is longer than the primary table: canonical walk)
+//   bits 4-7  number of extra bits
+//   bits 8-23 value: the literal, or the base of the length / distance (RFC 1951 3.2.5)
+//   bits 24-25 kind
+enum : uint32_t { kEntLiteral = 0, kEntBase = 1, kEntEnd = 2, kEntInvalid = 3 };
+VCE_HD uint32_t litEntry(int s, int codeLen) {          // literal/length symbol s
+  uint32_t kind, val = 0, x = 0;
+  if (s < 256) { kind = kEntLiteral; val = (uint32_t) s; }
+  else if (s == 256) kind = kEntEnd;
+  else if (s > 285) kind = kEntInvalid;
+  else {
+    kind = kEntBase;
+    const int li = s - 257;
+    if (li < 8) val = 3 + (uint32_t) li;
+    else if (li == 28) val = 258;
+    else { x = (uint32_t) (li - 4) >> 2; val = 3 + ((4 + ((uint32_t) li & 3u)) << x); }
+  }
+  return (uint32_t) codeLen | (x << 4) | (val << 8) | (kind << 24);
+}
+VCE_HD uint32_t distEntry(int s, int codeLen) {         // distance symbol s
+  uint32_t kind = kEntBase, val = 0, x = 0;
+  if (s > 29) kind = kEntInvalid;
+  else if (s < 4) val = 1 + (uint32_t) s;
+  else { x = ((uint32_t) s >> 1) - 1; val = 1 + ((2 + ((uint32_t) s & 1u)) << x); }
+  return (uint32_t) codeLen | (x << 4) | (val << 8) | (kind << 24);
+}
+
+struct InflateWs {           // per-warp workspace (shared memory on the device): 10.4 KB
+  uint32_t litTab[1 << kLitBits];    // pre-decoded entries, 0 = not in the table
+  uint32_t distTab[1 << kDistBits];
+  uint16_t clTab[1 << kClBits];      // code-length code: (symbol << 4) | length
   uint16_t litSym[288];      // symbols ordered by (length, symbol)
   uint16_t distSym[32];
   HuffMeta lit, dist;
   uint8_t lens[320];         // code lengths: literal/length then distance
   int32_t scratch[4];
+  // the last kRing bytes of text: a match whose distance reaches no further back is copied out of shared memory (text this
+  // warp wrote a moment ago comes back from L2 otherwise: that wait was 30 % of the kernel's stall samples)
+  uint8_t ring[4096];
 };
+constexpr int kRing = 4096;
 
 // LSB-first bit stream over aligned 32-bit words (little endian).  Two words are held in registers, `nxt` one word ahead of
 // what is being decoded (its load was issued a whole symbol earlier); a look at the next 32 bits is one funnel shift.
@@ -180,9 +213,10 @@ VCE_HD uint32_t bitReverse(uint32_t v, int n) {
 }
 
 // Builds the decoding structures of one canonical Huffman code from its code lengths (RFC 1951 3.2.2).
-// Returns false when the lengths over-subscribe the code space.
-template <class WP>
-VCE_HDN bool huffBuild(const uint8_t* lens, int n, uint16_t* tab, int tabBits, uint16_t* sym, HuffMeta* meta, int32_t* flag) {
+// KIND 0: code-length code (16-bit entries (symbol << 4) | length), 1: literal/length code, 2: distance code (pre-decoded
+// 32-bit entries).  Returns false when the lengths over-subscribe the code space.
+template <class WP, int KIND, class E>
+VCE_HDN bool huffBuild(const uint8_t* lens, int n, E* tab, int tabBits, uint16_t* sym, HuffMeta* meta, int32_t* flag) {
   const int lane = WP::lane();
   WP::sync();   // `lens` written by lane 0
   if (lane == 0) {
@@ -214,7 +248,7 @@ VCE_HDN bool huffBuild(const uint8_t* lens, int n, uint16_t* tab, int tabBits, u
     const int l = lens[s];
     if (l > tabBits) continue;
     const uint32_t code = (uint32_t) meta->first[l] + (uint32_t) (i - (int) meta->index[l]);
-    const uint16_t e = (uint16_t) ((s << 4) | l);
+    const E e = KIND == 0 ? (E) ((s << 4) | l) : KIND == 1 ? (E) litEntry(s, l) : (E) distEntry(s, l);
     for (uint32_t k = bitReverse(code, l); k < (1u << tabBits); k += 1u << l) tab[k] = e;
   }
   WP::sync();
@@ -234,12 +268,28 @@ VCE_HDN int huffWalk(uint32_t v, const uint16_t* sym, const HuffMeta* meta, int*
   *used = 1;
   return -1;
 }
-// One symbol from the bits `v` (the reader's next 32 bits).  Returns the symbol and the code's length in *used; the caller
-// drops the bits together with the extra bits.
+// One symbol of the code-length code from the bits `v` (the reader's next 32 bits); the code's length goes to *used.
 VCE_HD int huffDecode(uint32_t v, const uint16_t* tab, int tabBits, const uint16_t* sym, const HuffMeta* meta, int* used) {
   const uint32_t e = tab[v & ((1u << tabBits) - 1u)];
   if (e) { *used = (int) (e & 15u); return (int) (e >> 4); }
   return huffWalk(v, sym, meta, used);
+}
+// Pre-decoded entry for a code longer than the primary table (or for no code at all: kEntInvalid).
+template <int KIND>
+VCE_HDN uint32_t huffLong(uint32_t v, const uint16_t* sym, const HuffMeta* meta) {
+  int used;
+  const int s = huffWalk(v, sym, meta, &used);
+  if (s < 0) return 1u | (kEntInvalid << 24);
+  return KIND == 1 ? litEntry(s, used) : distEntry(s, used);
+}
+VCE_HD uint32_t bitField(uint32_t v, uint32_t pos, uint32_t n) {   // n bits of v from bit pos (n may be 0)
+#if defined(__CUDA_ARCH__)
+  uint32_t r;
+  asm("bfe.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(v), "r"(pos), "r"(n));
+  return r;
+#else
+  return (v >> pos) & ((1u << n) - 1u);
+#endif
 }
 
 // Inflates one raw DEFLATE stream src[0, srcLen) into dst[0, dstLen); every lane of the warp calls it with the same
@@ -251,6 +301,13 @@ VCE_HDN int inflateBlock(const uint8_t* src, int srcLen, uint8_t* dst, int dstLe
   br.initAt(src, src + srcLen);
   int op = 0;
   int status = kInfOk;
+  // A short match's byte is loaded when the match is decoded and stored when the NEXT match is (or at the end): the load's
+  // latency -- shared memory, or L2 for a source further back than the ring -- passes while the next symbol is decoded.
+  int pendPos = -1;
+  uint8_t pendC = 0;
+  auto flush = [&]() {
+    if (pendPos >= 0) { dst[pendPos] = pendC; ws->ring[pendPos & (kRing - 1)] = pendC; pendPos = -1; }
+  };
   for (bool last = false; !last && status == kInfOk;) {
     const uint32_t hdr = br.take(3);
     last = (hdr & 1u) != 0;
@@ -265,7 +322,7 @@ VCE_HDN int inflateBlock(const uint8_t* src, int srcLen, uint8_t* dst, int dstLe
       const uint8_t* p = br.bytePos();
       if (p + n > src + srcLen) { status = kInfOverrun; break; }
       if (op + (int) n > dstLen) { status = kInfOverflow; break; }
-      for (int i = lane; i < (int) n; i += WP::W) dst[op + i] = p[i];
+      for (int i = lane; i < (int) n; i += WP::W) { const uint8_t c = p[i]; dst[op + i] = c; ws->ring[(op + i) & (kRing - 1)] = c; }
       op += (int) n;
       br.initAt(p + n, src + srcLen);
       continue;
@@ -290,7 +347,7 @@ VCE_HDN int inflateBlock(const uint8_t* src, int srcLen, uint8_t* dst, int dstLe
         const int pos = i < 3 ? 16 + i : i == 3 ? 0 : (i & 1) ? 7 - ((i - 5) >> 1) : 6 + (i >> 1);
         if (lane == 0) ws->lens[pos] = (uint8_t) v;
       }
-      if (!huffBuild<WP>(ws->lens, 19, ws->clTab, kClBits, ws->distSym, &ws->dist, &ws->scratch[0])) { status = kInfBadLengths; break; }
+      if (!huffBuild<WP, 0>(ws->lens, 19, ws->clTab, kClBits, ws->distSym, &ws->dist, &ws->scratch[0])) { status = kInfBadLengths; break; }
       // the lengths are decoded by every lane alike; lane 0 writes them over the code-length lengths (the table above was
       // derived from those, it does not refer to them)
       int got = 0, prev = 0;
@@ -317,53 +374,70 @@ VCE_HDN int inflateBlock(const uint8_t* src, int srcLen, uint8_t* dst, int dstLe
       if (ws->lens[256] == 0) { status = kInfBadLengths; break; }   // no end-of-block code
     }
     // the distance lengths sit right behind the literal/length lengths
-    if (!huffBuild<WP>(ws->lens, nLit, ws->litTab, kLitBits, ws->litSym, &ws->lit, &ws->scratch[0])) { status = kInfBadLengths; break; }
-    if (!huffBuild<WP>(ws->lens + nLit, nDist, ws->distTab, kDistBits, ws->distSym, &ws->dist, &ws->scratch[1])) { status = kInfBadLengths; break; }
+    if (!huffBuild<WP, 1>(ws->lens, nLit, ws->litTab, kLitBits, ws->litSym, &ws->lit, &ws->scratch[0])) { status = kInfBadLengths; break; }
+    if (!huffBuild<WP, 2>(ws->lens + nLit, nDist, ws->distTab, kDistBits, ws->distSym, &ws->dist, &ws->scratch[1])) { status = kInfBadLengths; break; }
     for (;;) {
       uint32_t v = br.peek();
-      int used;
-      const int s = huffDecode(v, ws->litTab, kLitBits, ws->litSym, &ws->lit, &used);
-      if (s < 256) {
-        if (s < 0) { status = kInfBadCode; break; }
+      uint32_t e = ws->litTab[v & ((1u << kLitBits) - 1u)];
+      if (!e) e = huffLong<1>(v, ws->litSym, &ws->lit);
+      uint32_t n = e & 15u;
+      const uint32_t kind = e >> 24;
+      if (kind == kEntLiteral) {
         if (op >= dstLen) { status = kInfOverflow; break; }
-        br.drop(used);
-        if (lane == 0) dst[op] = (uint8_t) s;
+        br.drop((int) n);
+        if (lane == 0) { dst[op] = (uint8_t) (e >> 8); ws->ring[op & (kRing - 1)] = (uint8_t) (e >> 8); }
         ++op;
         continue;
       }
-      if (s == 256) { br.drop(used); break; }
-      const int li = s - 257;
-      if (li > 28) { status = kInfBadCode; break; }
-      v >>= used;
-      int len;
-      if (li < 8) len = 3 + li;
-      else if (li == 28) len = 258;
-      else { const int x = (li - 4) >> 2; len = 3 + ((4 + (li & 3)) << x) + (int) (v & ((1u << x) - 1u)); used += x; }
-      br.drop(used);        // at most 15 + 5 bits
+      if (kind != kEntBase) {
+        if (kind == kEntEnd) br.drop((int) n); else status = kInfBadCode;
+        break;
+      }
+      uint32_t x = (e >> 4) & 15u;
+      const int len = (int) (((e >> 8) & 0xffffu) + bitField(v, n, x));
+      br.drop((int) (n + x));        // at most 15 + 5 bits
       v = br.peek();
-      const int ds = huffDecode(v, ws->distTab, kDistBits, ws->distSym, &ws->dist, &used);
-      if (ds < 0 || ds > 29) { status = kInfBadCode; break; }
-      v >>= used;
-      int dist;
-      if (ds < 4) dist = 1 + ds;
-      else { const int x = (ds >> 1) - 1; dist = 1 + ((2 + (ds & 1)) << x) + (int) (v & ((1u << x) - 1u)); used += x; }
-      br.drop(used);        // at most 15 + 13 bits
-      if (dist > op) { status = kInfTooFar; break; }
-      if (op + len > dstLen) { status = kInfOverflow; break; }
-      if (br.over) { status = kInfOverrun; break; }
+      uint32_t d = ws->distTab[v & ((1u << kDistBits) - 1u)];
+      if (!d) d = huffLong<2>(v, ws->distSym, &ws->dist);
+      n = d & 15u;
+      x = (d >> 4) & 15u;
+      const int dist = (int) (((d >> 8) & 0xffffu) + bitField(v, n, x));
+      br.drop((int) (n + x));        // at most 15 + 13 bits
+      // one test for everything that can be wrong with a match; which one it was is sorted out on the way out
+      if (((d >> 24) != kEntBase) | (dist > op) | (op + len > dstLen) | br.over) {
+        status = (d >> 24) != kEntBase ? kInfBadCode : dist > op ? kInfTooFar : op + len > dstLen ? kInfOverflow : kInfOverrun;
+        break;
+      }
+      flush();
       WP::sync();   // lane 0's literals and the previous copies are visible to every lane
-      const uint8_t* from = dst + op - dist;
-      if (len <= WP::W && dist >= len) {          // the common case: one load and one store per lane
-        if (lane < len) dst[op + lane] = from[lane];
-      } else if (dist >= len) {
-        for (int i = lane; i < len; i += WP::W) dst[op + i] = from[i];
+      if (len <= WP::W && dist >= len) {            // the common case: one load per lane now, its two stores later
+        if (lane < len) {
+          pendC = dist <= kRing ? ws->ring[(op - dist + lane) & (kRing - 1)] : dst[op - dist + lane];
+          pendPos = op + lane;
+        }
+      } else if (dist <= kRing) {                   // the source is in the ring (every byte of text goes through it)
+        const int src0 = op - dist;
+        {
+          // longer than a warp, or overlapping itself (bytes [op - dist, op) repeat with period dist).  The ring holds kRing
+          // bytes and dist + len may exceed that: a round's reads are finished before its writes start.
+          for (int i0 = 0; i0 < len; i0 += WP::W) {
+            const int i = i0 + lane;
+            uint8_t c = 0;
+            if (i < len) c = ws->ring[(src0 + (dist >= len ? i : i % dist)) & (kRing - 1)];
+            WP::sync();
+            if (i < len) { dst[op + i] = c; ws->ring[(op + i) & (kRing - 1)] = c; }
+            WP::sync();
+          }
+        }
       } else {
-        for (int i = lane; i < len; i += WP::W) dst[op + i] = from[i % dist];
+        const uint8_t* from = dst + op - dist;      // further back than the ring: from the text in global memory (dist > len)
+        for (int i = lane; i < len; i += WP::W) { const uint8_t c = from[i]; dst[op + i] = c; ws->ring[(op + i) & (kRing - 1)] = c; }
       }
       op += len;
     }
     if (br.over && status == kInfOk) status = kInfOverrun;
   }
+  flush();
   if (status == kInfOk) {
     if (br.bytePos() > src + srcLen) status = kInfOverrun;
     else if (op != dstLen) status = kInfShort;

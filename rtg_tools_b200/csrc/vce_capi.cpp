@@ -456,7 +456,8 @@ int vce_submit(const vce_config* cfg, int32_t n_seq, const vce_sequence* seqs, v
   Context* c = acquire(rc);
   if (!c) return rc;
   c->backend->stats = vce::SearchStats();
-  if (const char* e = std::getenv("VCE_DEVICE_BUILD")) c->engine->options().deviceBuild = std::atoi(e) != 0;   // contexts are pooled
+  // (contexts are pooled: the switch is applied on every call, so that a context does not keep the mode of an earlier call)
+  { const char* e = std::getenv("VCE_DEVICE_BUILD"); c->engine->options().deviceBuild = e ? std::atoi(e) != 0 : true; }
   rc = c->engine->run(*cfg, n_seq, seqs, results);
   const std::string msg = rc ? c->engine->error() : std::string();
   t_summary = c->engine->summary();

@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(256) k_vcf_for(int n, F f) {
   if (i < n) f(i);
 }
 
-constexpr int kInflateWarps = 8;   // BGZF blocks per CTA: 8 x 3.9 KB of tables
+constexpr int kInflateWarps = 4;   // BGZF blocks per CTA: 4 x 10.4 KB of tables + text ring (static shared memory)
 
 __global__ void __launch_bounds__(kInflateWarps * 32) k_bgzf_inflate(int nBlocks, const BgzfBlock* blocks, const uint8_t* data,
                                                                    uint8_t* out, int32_t* status) {
