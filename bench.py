@@ -435,6 +435,7 @@ def main():
         dev_ms += st["execute_ms"]
         launches += int(st["launches"])
         search_ms += st["search_ms"]
+    own_wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps   # this rank's own time, before it waits for the others
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     results = job.fetch()
@@ -464,6 +465,7 @@ def main():
             raise RuntimeError("vce_submit failed: %s" % eng.lib.last_error())
         # the summary merge, the only collective of the path; the counters come from the device with the results
         counts = multigpu.merge_counts(eng.submit_summary(len(seqs)).sum(axis=0))
+    own_e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     clocks = sampler.stop()
@@ -485,6 +487,18 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    # every rank's own share and times (the step is as slow as the slowest rank: this names it)
+    mine = [float(rank), float(nv), float(regions), float(len(seqs)), dev_ms / args.steps, own_wall_ms, own_e2e_ms,
+            float(sub_stats["h2d_bytes"]), search_ms / args.steps]
+    if world > 1:
+        tm = torch.tensor(mine, dtype=torch.float64, device="cuda")
+        allr = torch.empty(world * len(mine), dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(allr, tm)
+        allr = allr.cpu().reshape(world, len(mine)).tolist()
+    else:
+        allr = [mine]
+    per_rank = [{"rank": int(r[0]), "variants": int(r[1]), "sync_regions": int(r[2]), "sequences": int(r[3]), "staged_device_ms": r[4],
+                 "staged_wall_ms": r[5], "e2e_ms_before_the_barrier": r[6], "e2e_h2d_bytes": int(r[7]), "search_kernels_ms": r[8]} for r in allr]
     ms_per_step = reduce_max(dev_ms / args.steps)
     wall_per_step = reduce_max(wall_ms / args.steps)
     e2e_ms = reduce_max(e2e_ms)
@@ -661,7 +675,8 @@ def main():
         "sync_regions_per_step": int(total_regions),
         "run": {"sequences_per_rank": len(seqs),
                 "sharding": "none (1 GPU)" if world == 1 else ("one sample pair per rank" if args.scaling == "weak" else "one sample pair, its sequences LPT-sharded over the ranks by variant count"),
-                "host_threads_per_rank": int(os.environ.get("VCE_THREADS", "0"))},
+                "host_threads_per_rank": int(os.environ.get("VCE_THREADS", "0")),
+                "per_rank": per_rank},
         "sync_regions_per_s": total_regions / (ms_per_step * 1e-3),
         "wall_ms_per_step": wall_per_step,
         "e2e": {"value": total_variants / (e2e_ms * 1e-3), "unit": "variants/s", "ms_per_step": e2e_ms,
