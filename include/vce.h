@@ -295,6 +295,18 @@ typedef struct vce_vcf_stats {
 int  vce_vcf_parse(const vce_vcf_in* in, void** result);
 int  vce_vcf_variants(const void* result, vce_variants* out, vce_vcf_stats* stats);
 void vce_vcf_free(void* result);
+/*
+ * The ROC inputs of the variants of a result, made by the same device passes ("RocFilter classification"):
+ * what RocContainer.addRocLine derives from a call's record (RocContainer.java:225-248) -- qual[i] = the QUAL column as
+ * Double.parseDouble reads it (RocScoreField.java:50-80; NaN when missing) and filter_mask[i] = the RocFilters that accept the
+ * record, one bit per filter in declaration order (RocFilter.java:48-137): 0 ALL, 1 HOM, 2 HET, 3 SNP, 4 NON_SNP, 5 MNP, 6 INDEL,
+ * 7 XRX, 8 NON_XRX (VariantType.getType(rec, gt) :130-160 on the padding-stripped alleles, VcfUtils.isHomozygousAlt /
+ * isHeterozygous, INFO key XRX).  Bit 31 (VCE_ROC_SCORE_UNPARSED): the QUAL text is none of the plain decimal forms the device
+ * parses exactly (more than 15 significant digits, hex floats, "NaN" ...): parse it yourself.  Select the bits of the filters
+ * in use and hand (qual, tp, fp, tp_raw, mask) to vce_roc.  The arrays live as long as the result.
+ */
+#define VCE_ROC_SCORE_UNPARSED 0x80000000u
+int vce_vcf_roc_fields(const void* result, const uint32_t** filter_mask, const double** qual);
 
 /*
  * SURVEY.md 8(f) rank 4 -- the on-disk formats either side of the loader, decoded on the device.

@@ -477,6 +477,15 @@ class Library:
                                arr(cv.allele_start, ns, np.int32), arr(cv.allele_end, ns, np.int32), arr(cv.allele_null, ns, np.uint8),
                                nt_off, arr(cv.nt, int(nt_off[-1]) if ns >= 0 and nt_off.size else 0, np.uint8))
             stats = {k: getattr(st, k) for k in ("lines", "records", "kept", "skipped", "h2d_ms", "kernel_ms", "d2h_ms", "launches")}
+            # the ROC inputs of the same variants (vce_vcf_roc_fields): RocFilter bits and QUAL
+            f_roc = getattr(self.lib, pre + "vcf_roc_fields", None)
+            if f_roc is not None:
+                f_roc.restype = C.c_int
+                f_roc.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.POINTER(C.c_double))]
+                pm, pq = C.POINTER(C.c_uint32)(), C.POINTER(C.c_double)()
+                if f_roc(handle, C.byref(pm), C.byref(pq)) == 0:
+                    stats["roc_mask"] = arr(pm, n, np.uint32)
+                    stats["qual"] = arr(pq, n, np.float64)
         finally:
             f_free(handle)
         return side, stats

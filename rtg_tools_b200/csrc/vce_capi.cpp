@@ -574,6 +574,14 @@ int vce_vcf_variants(const void* result, vce_variants* out, vce_vcf_stats* stats
 
 void vce_vcf_free(void* result) { delete static_cast<vce::VcfResult*>(result); }
 
+int vce_vcf_roc_fields(const void* result, const uint32_t** filter_mask, const double** qual) {
+  if (!result || !filter_mask || !qual) return fail(VCE_ERR_BAD_ARGUMENT, "null argument");
+  const vce::VcfResult& R = *static_cast<const vce::VcfResult*>(result);
+  *filter_mask = R.rocMask;
+  *qual = R.qual;
+  return VCE_OK;
+}
+
 // ------------------------------------------------------------------------------- on-disk formats (vce_bgzf.h)
 namespace {
 int currentDevice() {

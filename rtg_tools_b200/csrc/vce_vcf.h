@@ -17,6 +17,7 @@
 
 #include <cstdint>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -85,6 +86,8 @@ struct VcfArrays {
   uint8_t* alleleNull;     // [nSlots]
   int32_t* alleleNtOff;    // [nSlots + 1]
   uint8_t* nt;             // [nNt]
+  uint32_t* rocMask;       // [n] RocFilter bits of the variant's record (vcfRocFields)
+  double* qual;            // [n] QUAL as a double, NaN when missing
   // counts
   int32_t nLines, nStream, n, nSlots, nNt, nSkipped;
 };
@@ -335,6 +338,172 @@ VCE_HDN void vcfParseLine(const uint8_t* t, int a, int b, const VcfConfig& cfg, 
   return;
 }
 
+// ---- ROC inputs of one kept variant: what RocContainer.addRocLine (RocContainer.java:225-248) derives from the record
+// VariantType of one ALT against REF, both with the padding base removed (VariantType.getType(String,String) :169-190,
+// isInsertionOrDeletion :193-219).  Ordinals: 0 NO_CALL 1 UNCHANGED 2 SNP 3 MNP 4 DELETION 5 INSERTION 6 INDEL 7 SV_BREAKEND
+// 8 SV_SYMBOLIC 9 SV_MISSING.
+VCE_HD int vcfAlleleType(const uint8_t* r, int rn, const uint8_t* s, int sn) {
+  bool eq = rn == sn;
+  for (int i = 0; eq && i < rn; ++i) if (r[i] != s[i]) eq = false;
+  if (eq) return 1;
+  if (rn == 1 && sn == 1 && s[0] != '*') return 2;
+  if (sn > 0) {
+    const uint8_t f = s[0], l = s[sn - 1];
+    if (f == '<' || l == '>') return 8;
+    if (f == '*' || l == '*') return 9;
+    if (f == '[' || f == ']' || l == '[' || l == ']') return 7;
+  }
+  if (rn == sn) return 3;
+  bool insDel = rn == 0 || sn == 0;
+  if (!insDel) {
+    const bool ins = rn < sn;
+    const uint8_t* s1 = ins ? r : s;   // the shorter one
+    const uint8_t* s2 = ins ? s : r;
+    const int n1 = ins ? rn : sn, n2 = ins ? sn : rn;
+    int left = 0;
+    while (left < n1 && s1[left] == s2[left]) ++left;
+    if (left == n1) insDel = true;
+    else {
+      int right = 0;
+      while (right < n1 && s1[n1 - right - 1] == s2[n2 - right - 1]) ++right;
+      insDel = left + right >= n1;
+    }
+  }
+  if (insDel) return rn < sn ? 5 : 4;
+  return 6;
+}
+VCE_HD int vcfTypePrecedence(int a, int b) {   // VariantType.getPrecedence :85-98
+  const bool ia = a >= 4 && a <= 6, ib = b >= 4 && b <= 6;
+  if (a != b && ia && ib) return 6;
+  return a > b ? a : b;
+}
+// Double.parseDouble for the decimal forms a QUAL column holds: [sign] digits [. digits] [e [sign] digits] with at most 15
+// significant digits and a decimal exponent within +-22 is exact in one multiplication or division of exact doubles (both
+// correctly rounded, like the JDK's result).  Anything else (hex floats, "NaN", "Infinity", more digits) is left to the
+// caller's parser: *ok = false.
+VCE_HD double vcfParseDecimal(const uint8_t* s, int n, bool* ok) {
+  *ok = false;
+  int i = 0;
+  bool neg = false;
+  if (i < n && (s[i] == '+' || s[i] == '-')) { neg = s[i] == '-'; ++i; }
+  uint64_t m = 0;
+  int digits = 0, sig = 0, frac = 0;
+  bool dot = false;
+  for (; i < n; ++i) {
+    const uint8_t c = s[i];
+    if (c == '.' && !dot) { dot = true; continue; }
+    if (c < '0' || c > '9') break;
+    ++digits;
+    if (sig > 0 || c != '0') { if (++sig > 15) return 0.0; m = m * 10 + (uint64_t) (c - '0'); }
+    if (dot) ++frac;
+  }
+  if (digits == 0) return 0.0;
+  int e10 = 0;
+  if (i < n && (s[i] == 'e' || s[i] == 'E')) {
+    ++i;
+    bool eneg = false;
+    if (i < n && (s[i] == '+' || s[i] == '-')) { eneg = s[i] == '-'; ++i; }
+    int ed = 0;
+    for (; i < n && s[i] >= '0' && s[i] <= '9'; ++i) { if (++ed > 4) return 0.0; e10 = e10 * 10 + (s[i] - '0'); }
+    if (ed == 0) return 0.0;
+    if (eneg) e10 = -e10;
+  }
+  if (i != n) return 0.0;
+  e10 -= frac;
+  double v = (double) m;
+  if (m != 0) {
+    if (e10 > 22 || e10 < -22) return 0.0;
+    double p = 1.0;
+    for (int k = e10 < 0 ? -e10 : e10; k > 0; --k) p *= 10.0;   // exact up to 10^22
+    v = e10 < 0 ? v / p : v * p;
+  }
+  *ok = true;
+  return neg ? -v : v;
+}
+// Filter bits in RocFilter's declaration order (RocFilter.java:48-137): ALL HOM HET SNP NON_SNP MNP INDEL XRX NON_XRX; bit 31:
+// the QUAL text needs the caller's own parser (qual is NaN then).  `line` is the record's text, L what vcfParseLine kept.
+constexpr uint32_t kRocScoreUnparsed = 0x80000000u;
+VCE_HDN void vcfRocFields(const uint8_t* line, int lineLen, const VcfLine& L, int ploidy, uint32_t* maskOut, double* qualOut) {
+  // QUAL = field 5, INFO = field 7
+  int fo[2] = {0, 0}, fl[2] = {-1, -1};
+  int field = 0, fs = 0;
+  for (int i = 0; i <= lineLen && field <= 7; ++i) {
+    if (i == lineLen || line[i] == '\t') {
+      if (field == 5) { fo[0] = fs; fl[0] = i - fs; }
+      if (field == 7) { fo[1] = fs; fl[1] = i - fs; }
+      ++field;
+      fs = i + 1;
+    }
+  }
+  uint32_t mask = 1u;   // ALL
+  // zygosity (VcfUtils.isHomozygousAlt :692-694, isHeterozygous :708-710) on the sample's GT
+  const bool hom = ploidy == 1 || L.gt[0] == L.gt[1];
+  bool homRef = true;
+  for (int q = 0; q < ploidy && q < 4; ++q) if (L.gt[q] != 0) homRef = false;
+  if (hom && !homRef) mask |= 1u << 1;
+  if (ploidy == 2 && L.gt[0] != L.gt[1]) mask |= 1u << 2;
+  // VariantType.getType(VcfRecord, int[]) :130-160
+  int type = 0, altId = 0, q = 0;
+  bool allMissing = true;
+  for (; q < ploidy && q < 4; ++q) {
+    const int a = L.gt[q];
+    if (a != -1) {
+      allMissing = false;
+      if (a != 0) { altId = a; ++q; break; }
+    }
+  }
+  if (allMissing) type = 0;
+  else if (altId == 0) type = 1;
+  else {
+    const int pad = L.pad ? 1 : 0;
+    const uint8_t* ref = line + L.refOff + pad;
+    const int rn = L.refLen - pad;
+    const uint8_t* alt = line + L.altOff;
+    auto typeOf = [&](int id) {
+      int o = 0, l = 0;
+      vcfNth(alt, L.altLen, ',', id - 1, &o, &l);
+      const bool strip = pad && l > 0 && alt[o] != '*';
+      return vcfAlleleType(ref, rn, alt + o + (strip ? 1 : 0), l - (strip ? 1 : 0));
+    };
+    type = typeOf(altId);
+    for (; q < ploidy && q < 4; ++q) {
+      const int a = L.gt[q];
+      if (a > 0 && a != altId) type = vcfTypePrecedence(type, typeOf(a));
+    }
+  }
+  mask |= type == 2 ? 1u << 3 : 1u << 4;
+  if (type == 3) mask |= 1u << 5;
+  if (type >= 4 && type <= 6) mask |= 1u << 6;
+  // VcfUtils.isComplexScored :529-531: INFO holds the key XRX
+  bool xrx = false;
+  if (fl[1] > 0) {
+    const uint8_t* info = line + fo[1];
+    int a = 0;
+    for (int i = 0; i <= fl[1]; ++i) {
+      if (i == fl[1] || info[i] == ';') {
+        int k = a;
+        while (k < i && info[k] != '=') ++k;
+        if (k - a == 3 && info[a] == 'X' && info[a + 1] == 'R' && info[a + 2] == 'X') xrx = true;
+        a = i + 1;
+      }
+    }
+  }
+  mask |= xrx ? 1u << 7 : 1u << 8;
+  // RocScoreField.QUAL :50-80
+#if defined(__CUDA_ARCH__)
+  double qual = __longlong_as_double(0x7ff8000000000000LL);   // Double.NaN
+#else
+  double qual = std::numeric_limits<double>::quiet_NaN();
+#endif
+  if (fl[0] > 0 && !(fl[0] == 1 && line[fo[0]] == '.')) {
+    bool ok = false;
+    const double v = vcfParseDecimal(line + fo[0], fl[0], &ok);
+    if (ok) qual = v; else mask |= kRocScoreUnparsed;
+  }
+  *maskOut = mask;
+  *qualOut = qual;
+}
+
 // The allele table of one kept variant (slot 0 = the missing allele, slot 1 = REF, slot k + 1 = ALT k).
 VCE_HDN void vcfFillVariant(const uint8_t* line, const VcfLine& L, int ploidy, int32_t slot0, int32_t nt0, int32_t* aStart, int32_t* aEnd,
                             uint8_t* aNull, int32_t* aNtOff, uint8_t* nt) {
@@ -510,6 +679,10 @@ void vcfFillPasses(Ops& ops, VcfArrays& A) {
     for (int q = 0; q < ploidy; ++q) a.gt[(size_t) v * ploidy + q] = q < 4 ? L.gt[q] : (int8_t) -2;
     vcfFillVariant(a.text + a.lineStart[l], L, ploidy, a.alleleOff[v], a.ntBase[v], a.alleleStart, a.alleleEnd, a.alleleNull,
                    a.alleleNtOff, a.nt);
+    int e = a.lineStart[l + 1];
+    if (e > a.lineStart[l] && a.text[e - 1] == '\n') --e;
+    if (e > a.lineStart[l] && a.text[e - 1] == '\r') --e;
+    vcfRocFields(a.text + a.lineStart[l], e - a.lineStart[l], L, ploidy, a.rocMask + v, a.qual + v);
   });
   ops.parFor(n + 1, VCE_VCF_LAMBDA(int v) { a.alleleOffOut[v] = a.alleleOff[v]; });
   ops.parFor(1, VCE_VCF_LAMBDA(int) { a.alleleNtOff[nSlots] = nNt; });
@@ -529,6 +702,8 @@ struct VcfResult {   // what vce_vcf_variants hands out: ONE host block (page-lo
   int32_t *id = nullptr, *alleleOff = nullptr, *alleleStart = nullptr, *alleleEnd = nullptr, *alleleNtOff = nullptr;
   uint8_t *phased = nullptr, *statusIn = nullptr, *alleleNull = nullptr, *nt = nullptr;
   int8_t* gt = nullptr;
+  uint32_t* rocMask = nullptr;
+  double* qual = nullptr;
   VcfStats stats;
   VcfResult() = default;
   VcfResult(const VcfResult&) = delete;
@@ -538,13 +713,14 @@ struct VcfResult {   // what vce_vcf_variants hands out: ONE host block (page-lo
 
 // Offsets of the output arrays within one block (every array 16-byte aligned); the same layout on the device and on the host.
 struct VcfLayout {
-  size_t id, phased, statusIn, gt, alleleOff, alleleStart, alleleEnd, alleleNull, alleleNtOff, nt, total;
+  size_t id, phased, statusIn, gt, alleleOff, alleleStart, alleleEnd, alleleNull, alleleNtOff, nt, rocMask, qual, total;
   VcfLayout(size_t n, size_t ploidy, size_t nSlots, size_t nNt) {
     size_t at = 0;
     auto take = [&at](size_t bytes) { const size_t o = at; at += (bytes + 15) & ~(size_t) 15; return o; };
     id = take(n * 4); phased = take(n); statusIn = take(n); gt = take(n * ploidy + 4); alleleOff = take((n + 1) * 4);
     alleleStart = take(nSlots * 4); alleleEnd = take(nSlots * 4); alleleNull = take(nSlots); alleleNtOff = take((nSlots + 1) * 4);
     nt = take(nNt + 4);
+    rocMask = take(n * 4); qual = take(n * 8);
     total = at;
   }
 };
@@ -622,6 +798,8 @@ int vcfDrive(Ops& ops, const uint8_t* text, int64_t len, const VcfConfig& cfg, V
   A.alleleNull = dOut + lay.alleleNull;
   A.alleleNtOff = reinterpret_cast<int32_t*>(dOut + lay.alleleNtOff);
   A.nt = dOut + lay.nt;
+  A.rocMask = reinterpret_cast<uint32_t*>(dOut + lay.rocMask);
+  A.qual = reinterpret_cast<double*>(dOut + lay.qual);
   vcfFillPasses(ops, A);
   ops.mark(2);
   R.slab = ops.hostAlloc(lay.total + 16, &R.release);
@@ -640,6 +818,8 @@ int vcfDrive(Ops& ops, const uint8_t* text, int64_t len, const VcfConfig& cfg, V
   R.alleleNull = R.slab + lay.alleleNull;
   R.alleleNtOff = reinterpret_cast<int32_t*>(R.slab + lay.alleleNtOff);
   R.nt = R.slab + lay.nt;
+  R.rocMask = reinterpret_cast<uint32_t*>(R.slab + lay.rocMask);
+  R.qual = reinterpret_cast<double*>(R.slab + lay.qual);
   R.stats.kept = n;
   return 0;
 }

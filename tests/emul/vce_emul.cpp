@@ -738,6 +738,12 @@ int emul_vce_vcf_variants(const void* result, vce_variants* out, vce_vcf_stats* 
   return VCE_OK;
 }
 void emul_vce_vcf_free(void* result) { delete static_cast<vce::VcfResult*>(result); }
+int emul_vce_vcf_roc_fields(const void* result, const uint32_t** filter_mask, const double** qual) {
+  const vce::VcfResult& R = *static_cast<const vce::VcfResult*>(result);
+  *filter_mask = R.rocMask;
+  *qual = R.qual;
+  return VCE_OK;
+}
 
 // ---- on-disk formats (vce_bgzf.h) through the host ops
 static int emulVcfConfig(const vce_vcf_in* in, vce::VcfConfig& cfg) {

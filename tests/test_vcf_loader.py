@@ -106,7 +106,10 @@ def fuzz_vcf(rng, n_records=250, template_len=3000, bad=False):
             if rng.random() < 0.1:
                 keys = keys[:1]                    # trailing sub-fields dropped
             return ":".join(vals[k] for k in keys)
-        line = "\t".join([chrom, str(pos), ".", ref, ",".join(alts) if alts else ".", "50", filt, ".", fmt, sample(), sample()])
+        qual = rng.choice(["50", ".", "37.5", "0", "1e3", "0.001", "123456.789", "99.99", "4.9e-3", "1234567890123456789", "-3", "+7.25", "1E2",
+                           "3.", ".5", "12345678901234.5", "2.5e22", "1e-22"])
+        info = rng.choice([".", "XRX", "DP=10;XRX", "XRX=1;AC=2", "XRXX;DP=3", "AN=2;AC=1"])
+        line = "\t".join([chrom, str(pos), ".", ref, ",".join(alts) if alts else ".", qual, filt, info, fmt, sample(), sample()])
         if rng.random() < 0.03:
             line += "\r"
         lines.append(line)

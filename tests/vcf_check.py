@@ -15,7 +15,38 @@ def expected_side(text, name, template_len, sample, ploidy=2, pass_only=True, ma
     def factory(rec, vid):
         return ref_host.sample_variant(rec, vid, sample, ploidy, pass_only)
     out, skipped = ref_host.load_side(recs, template_len, factory, max_length, False)
-    return capi.VariantSide.from_variants(out, ploidy), skipped
+    side = capi.VariantSide.from_variants(out, ploidy)
+    side.roc_expect = expected_roc_fields(out, sample)
+    return side, skipped
+
+
+ROC_BITS = {"ALL": 1, "HOM": 2, "HET": 4, "SNP": 8, "NON_SNP": 16, "MNP": 32, "INDEL": 64, "XRX": 128, "NON_XRX": 256}
+
+
+def expected_roc_fields(variants, sample):
+    """What RocContainer.addRocLine (RocContainer.java:225-248) derives from each kept variant's record: the RocFilters that
+    accept it (RocFilter.java:48-137, on the RAW sample GT as VcfUtils.getValidGt returns it) and the QUAL score
+    (RocScoreField.java:50-80)."""
+    masks, quals = [], []
+    for v in variants:
+        rec = v["rec"]
+        raw = [(-1 if x == "." else int(x)) for x in rec.sample_field(sample, "GT").replace("|", "/").split("/")]
+        m = ROC_BITS["ALL"]
+        hom = len(raw) == 1 or raw[0] == raw[1]
+        if hom and not all(g == 0 for g in raw):
+            m |= ROC_BITS["HOM"]
+        if len(raw) == 2 and raw[0] != raw[1]:
+            m |= ROC_BITS["HET"]
+        t = ref_host.record_type(rec, raw)
+        m |= ROC_BITS["SNP"] if t == "SNP" else ROC_BITS["NON_SNP"]
+        if t == "MNP":
+            m |= ROC_BITS["MNP"]
+        if t in ("INSERTION", "DELETION", "INDEL"):
+            m |= ROC_BITS["INDEL"]
+        m |= ROC_BITS["XRX"] if rec.has_info("XRX") else ROC_BITS["NON_XRX"]
+        masks.append(m)
+        quals.append(float("nan") if rec.qual == "." else float(rec.qual))
+    return np.array(masks, np.uint32), np.array(quals, np.float64)
 
 
 FIELDS = ("id", "phased", "status_in", "gt", "allele_off", "allele_start", "allele_end", "allele_null", "allele_nt_off", "nt")
@@ -40,5 +71,13 @@ def check_text(engine, text, name, template_len, sample, ploidy=2, pass_only=Tru
     got, stats = engine.vcf_parse(text.encode(), name, template_len, sample, ploidy, pass_only, max_length)
     assert_same_side(got, want, what)
     assert stats["skipped"] == skipped, "%s: skipped %d vs %d" % (what, stats["skipped"], skipped)
+    if "roc_mask" in stats:
+        wm, wq = want.roc_expect
+        gm, gq = stats["roc_mask"], stats["qual"]
+        assert np.array_equal(gm & 0x7fffffff, wm), "%s: RocFilter bits differ at %s\n got %s\nwant %s" % (
+            what, np.nonzero((gm & 0x7fffffff) != wm)[0][:5], gm[:20], wm[:20])
+        parsed = (gm >> 31) == 0     # the others are left to the caller's parser (bit 31)
+        assert np.array_equal(gq[parsed].view(np.int64), wq[parsed].view(np.int64)), "%s: QUAL differs" % what
+        assert np.isnan(gq[~parsed]).all()
     assert stats["kept"] == want.n
     return "ok"
