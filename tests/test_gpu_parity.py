@@ -349,8 +349,9 @@ def test_cuda_vcf_loader_million_records(engine):
     text, tl = synth.make_vcf_text(1_000_000, seed=11)
     raw = text.encode()
     got, st = engine.lib.vcf_parse(raw, "chr1", tl, 0)
-    want, _ = emul_library().vcf_parse(raw, "chr1", tl, 0)
+    want, st_e = emul_library().vcf_parse(raw, "chr1", tl, 0)
     vcf_check.assert_same_side(got, want, "1 M records, device vs emulation")
+    assert np.array_equal(st["roc_mask"], st_e["roc_mask"]) and np.array_equal(st["qual"].view(np.int64), st_e["qual"].view(np.int64))
     assert st["records"] == 1_000_000 and st["kept"] == got.n > 900_000 and st["launches"] > 10
     head = "\n".join(text.split("\n", 30_004)[:30_004]) + "\n"
     assert vcf_check.check_text(engine.lib, head, "chr1", tl, 0, what="first 30 000 records") == "ok"
