@@ -272,7 +272,9 @@ int vce_roc_timed(const vce_roc_in* in, vce_roc_out* out, double* h2d_ms, double
  * over --Xmax-length, record beyond the template, factory says no / skips), the sample factory
  * (VariantFactory.java:127-196: FILTER / FT unless --all-records, GT rules, haploid GT doubled, ploidy mismatch skipped),
  * VcfUtils.getAlleleStrings / hasRedundantFirstNucleotide (:785-828), VariantType.getType (:107-190) and Allele.getAlleles
- * (Allele.java:145-192).  --ref-overlap trimming (Variant.trimAlleles) and evaluation regions stay with the host.
+ * (Allele.java:145-192) and, with ref_overlap, Variant.trimAlleles (Variant.java:93-190: REF nulled, ALTs stripped of what they
+ * share with REF, the side decided by the overlapping neighbours; clusters of overlapping variants one thread each).
+ * Evaluation regions stay with the host.
  * A record the reference would throw VcfFormatException for ends the call with VCE_ERR_BAD_ARGUMENT (vce_last_error names
  * the line).  The result owns host copies of the arrays until vce_vcf_free.
  */
@@ -285,6 +287,8 @@ typedef struct vce_vcf_in {
   int32_t     ploidy;         /* --sample-ploidy (2)                               */
   int32_t     pass_only;      /* 0 with --all-records                              */
   int32_t     max_length;     /* --Xmax-length (1000), -1 = no limit               */
+  int32_t     ref_overlap;    /* --ref-overlap: Variant.trimAlleles (Variant.java:93-190) on the loaded variants */
+  int32_t     reserved;
 } vce_vcf_in;
 typedef struct vce_vcf_stats {
   int64_t lines, records, kept, skipped;   /* text lines, records of the sequence, variants, counted skips (:103-118) */

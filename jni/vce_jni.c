@@ -290,7 +290,7 @@ static void set_byte_field_array(JNIEnv* e, jobject o, const char* name, const v
 }
 
 JNIEXPORT jint JNICALL Java_com_rtg_vcf_eval_NativeVce_loadVcfGz(JNIEnv* e, jclass c, jbyteArray jfile, jlong vbeg, jlong vend, jstring jname,
-    jint templateLength, jint sample, jint ploidy, jboolean passOnly, jint maxLength, jobject jout, jlongArray jcounters) {
+    jint templateLength, jint sample, jint ploidy, jboolean passOnly, jint maxLength, jboolean refOverlap, jobject jout, jlongArray jcounters) {
   (void) c;
   const char* name = (*e)->GetStringUTFChars(e, jname, NULL);
   vce_vcf_in in;
@@ -302,6 +302,7 @@ JNIEXPORT jint JNICALL Java_com_rtg_vcf_eval_NativeVce_loadVcfGz(JNIEnv* e, jcla
   in.ploidy = ploidy;
   in.pass_only = passOnly ? 1 : 0;
   in.max_length = maxLength;
+  in.ref_overlap = refOverlap ? 1 : 0;
   void* result = NULL;
   /* the file bytes are pinned for the call only: the engine uploads them and keeps nothing */
   void* p = (*e)->GetPrimitiveArrayCritical(e, jfile, NULL);

@@ -42,6 +42,7 @@ struct VcfConfig {
   int32_t maxLength;     // --Xmax-length, -1 = no limit
   int32_t templateLen;   // records that end beyond it are skipped, -1 = unknown
   int32_t nameLen;       // CHROM to accept (a tabix query returns one sequence's records); 0 = accept every record
+  int32_t refOverlap;    // --ref-overlap: Variant.trimAlleles (Variant.java:93-190) on the loaded variants
   char name[232];
 };
 
@@ -87,6 +88,12 @@ struct VcfArrays {
   int32_t* alleleNtOff;    // [nSlots + 1]
   uint8_t* nt;             // [nNt]
   uint32_t* rocMask;       // [n] RocFilter bits of the variant's record (vcfRocFields)
+  // --ref-overlap (sized n + 1 when on): current locus of every kept variant, trim mode, cluster heads, prefix maxima
+  int32_t* locS;
+  int32_t* locE;
+  uint8_t* trim;           // 0 = untrimmed, 1 = prefix first, 2 = suffix first (Variant.trimAlleles(boolean) :97-122)
+  uint8_t* head;           // 1 = no earlier variant's locus reaches this one's start: a new cluster begins
+  int32_t* blockMax;       // [n / 1024 + 2]
   double* qual;            // [n] QUAL as a double, NaN when missing
   // counts
   int32_t nLines, nStream, n, nSlots, nNt, nSkipped;
@@ -504,12 +511,130 @@ VCE_HDN void vcfRocFields(const uint8_t* line, int lineLen, const VcfLine& L, in
   *qualOut = qual;
 }
 
+// ---- --ref-overlap: Variant.trimAlleles (Variant.java:93-190)
+// ALT `id` of a kept variant as the allele table holds it (padding base removed); false when the slot is null (not in the GT, or
+// symbolic).  REF: id 0.
+VCE_HD bool vcfAlleleText(const uint8_t* line, const VcfLine& L, int ploidy, int id, const uint8_t** s, int* sn) {
+  const int pad = L.pad ? 1 : 0;
+  if (id == 0) { *s = line + L.refOff + pad; *sn = L.refLen - pad; return true; }
+  bool have = false;
+  for (int q = 0; q < ploidy && q < 4; ++q) if (L.gt[q] == id) have = true;
+  if (!have) return false;
+  int o = 0, l = 0;
+  vcfNth(line + L.altOff, L.altLen, ',', id - 1, &o, &l);
+  const uint8_t* a = line + L.altOff + o;
+  if (vcfIsSym(a, l)) return false;
+  *s = a + pad;
+  *sn = l - pad;
+  return true;
+}
+VCE_HD int vcfCommonPrefix(int offset, const uint8_t* a, int an, const uint8_t* b, int bn) {   // ByteUtils.longestPrefix on base codes
+  const int n = (an < bn ? an : bn) - offset;
+  int i = 0;
+  while (i < n && vcfBaseCode(a[i]) == vcfBaseCode(b[i])) ++i;
+  return i;
+}
+VCE_HD int vcfCommonSuffix(int offset, const uint8_t* a, int an, const uint8_t* b, int bn) {   // ByteUtils.longestSuffix
+  const int n = (an < bn ? an : bn) - offset;
+  int i = 0;
+  while (i < n && vcfBaseCode(a[an - 1 - i]) == vcfBaseCode(b[bn - 1 - i])) ++i;
+  return i;
+}
+// Bases trimmed off one ALT (Variant.trimAlleles(boolean) :97-122): prefix first, then the suffix of what is left -- or the other way
+VCE_HD void vcfTrimOf(const uint8_t* ref, int rn, const uint8_t* alt, int an, bool leftFirst, int* lead, int* trail) {
+  if (leftFirst) { *lead = vcfCommonPrefix(0, ref, rn, alt, an); *trail = vcfCommonSuffix(*lead, ref, rn, alt, an); }
+  else { *trail = vcfCommonSuffix(0, ref, rn, alt, an); *lead = vcfCommonPrefix(*trail, ref, rn, alt, an); }
+}
+// Locus of a variant after trimming in the given mode: the bounds of its non-null ALTs (REF is null afterwards); also the bases left.
+VCE_HD void vcfTrimmedLocus(const uint8_t* line, const VcfLine& L, int ploidy, bool leftFirst, int32_t* ls, int32_t* le, int32_t* ntBytes) {
+  const uint8_t* ref; int rn;
+  vcfAlleleText(line, L, ploidy, 0, &ref, &rn);
+  const int32_t s0 = L.start + (L.pad ? 1 : 0), e0 = L.end;
+  int32_t lo = 0x7fffffff, hi = -0x7fffffff - 1, bytes = 0;
+  for (int id = 1; id <= L.nAlt; ++id) {
+    const uint8_t* alt; int an;
+    if (!vcfAlleleText(line, L, ploidy, id, &alt, &an)) continue;
+    int lead, trail;
+    vcfTrimOf(ref, rn, alt, an, leftFirst, &lead, &trail);
+    lo = s0 + lead < lo ? s0 + lead : lo;
+    hi = e0 - trail > hi ? e0 - trail : hi;
+    bytes += an - lead - trail;
+  }
+  *ls = lo; *le = hi; *ntBytes = bytes;
+}
+// Variant.trimAlleles(List) :124-190 over one cluster [v0, v1) of kept variants (no variant outside it overlaps one inside).
+// a.locS / a.locE hold the current loci (untrimmed at the start), a.trim receives every variant's mode.
+VCE_HD const VcfLine& vcfKeptLine(const VcfArrays& a, int v, const uint8_t** line) {
+  const int l = a.streamLine[a.order[a.keptPos[v]]];
+  *line = a.text + a.lineStart[l];
+  return a.lines[l];
+}
+VCE_HD bool vcfLociOverlap(int32_t as, int32_t ae, int32_t bs, int32_t be) { return bs < ae && be > as; }   // Range.overlaps
+VCE_HDN void vcfTrimCluster(const VcfArrays& a, int ploidy, int v0, int v1) {
+  int first = v0, last = v0;
+  for (int vi = v0; vi < v1; ++vi) {
+    const uint8_t* line;
+    const VcfLine& L = vcfKeptLine(a, vi, &line);
+    while (last < v1 && (last <= vi || vcfLociOverlap(a.locS[vi], a.locE[vi], a.locS[last], a.locE[last]))) ++last;
+    while (first < vi && !vcfLociOverlap(a.locS[vi], a.locE[vi], a.locS[first], a.locE[first])) ++first;
+    bool leftFirst = true;
+    if (!(first == vi && last == vi + 1)) {
+      // the longest prefix / suffix any ALT shares with REF: only when both exist does the neighbourhood decide (:141-186)
+      const uint8_t* ref; int rn;
+      vcfAlleleText(line, L, ploidy, 0, &ref, &rn);
+      int lead = 0, trail = 0;
+      for (int id = 1; id <= L.nAlt; ++id) {
+        const uint8_t* alt; int an;
+        if (!vcfAlleleText(line, L, ploidy, id, &alt, &an)) continue;
+        const int p = vcfCommonPrefix(0, ref, rn, alt, an), q = vcfCommonSuffix(0, ref, rn, alt, an);
+        lead = p > lead ? p : lead;
+        trail = q > trail ? q : trail;
+      }
+      if (lead != 0 && trail != 0) {
+        int lc = 0, rc = 0;
+        for (int i = first; i < last; ++i) {
+          if (i == vi) continue;
+          const int lo = a.locE[i] - a.locS[vi], ro = a.locE[vi] - a.locS[i];
+          if (lo <= 0 && ro <= 0) continue;
+          if (lo > 0 && lo <= lead) ++lc;
+          if (ro > 0 && ro < trail) ++rc;
+        }
+        leftFirst = lc > rc;
+      }
+    }
+    a.trim[vi] = leftFirst ? 1 : 2;
+    int32_t ls, le, bytes;
+    vcfTrimmedLocus(line, L, ploidy, leftFirst, &ls, &le, &bytes);
+    a.locS[vi] = ls;
+    a.locE[vi] = le;
+  }
+}
+
 // The allele table of one kept variant (slot 0 = the missing allele, slot 1 = REF, slot k + 1 = ALT k).
 VCE_HDN void vcfFillVariant(const uint8_t* line, const VcfLine& L, int ploidy, int32_t slot0, int32_t nt0, int32_t* aStart, int32_t* aEnd,
-                            uint8_t* aNull, int32_t* aNtOff, uint8_t* nt) {
+                            uint8_t* aNull, int32_t* aNtOff, uint8_t* nt, int trim = 0) {
   const uint8_t* ref = line + L.refOff;
   const uint8_t* alt = line + L.altOff;
   int at = nt0;
+  if (trim) {   // --ref-overlap: REF becomes null, every ALT loses what it shares with REF (Variant.trimAlleles(boolean) :97-122)
+    const uint8_t* r0; int rn;
+    vcfAlleleText(line, L, ploidy, 0, &r0, &rn);
+    for (int slot = 0; slot < L.nAlt + 2; ++slot) {
+      const uint8_t* s; int sn;
+      aNtOff[slot0 + slot] = at;
+      if (slot < 2 || !vcfAlleleText(line, L, ploidy, slot - 1, &s, &sn)) {
+        aStart[slot0 + slot] = 0; aEnd[slot0 + slot] = 0; aNull[slot0 + slot] = 1;
+        continue;
+      }
+      int lead, trail;
+      vcfTrimOf(r0, rn, s, sn, trim == 1, &lead, &trail);
+      aStart[slot0 + slot] = L.start + (L.pad ? 1 : 0) + lead;
+      aEnd[slot0 + slot] = L.end - trail;
+      aNull[slot0 + slot] = 0;
+      for (int q = lead; q < sn - trail; ++q) nt[at++] = (uint8_t) vcfBaseCode(s[q]);
+    }
+    return;
+  }
   for (int slot = 0; slot < L.nAlt + 2; ++slot) {
     const int id = slot - 1;
     bool have = id == 0;
@@ -651,11 +776,53 @@ void vcfOffsetPasses(Ops& ops, VcfArrays& A) {
   ops.parFor(nStream, VCE_VCF_LAMBDA(int p) {
     if (a.keptScan[p + 1] != a.keptScan[p]) a.keptPos[a.keptScan[p]] = p;
   });
+  const int ploidy = A.cfg.ploidy;
+  if (A.cfg.refOverlap && n > 0) {
+    // Variant.trimAlleles(List) :124-190 looks at a variant's overlapping neighbours, earlier ones already trimmed: clusters of
+    // transitively overlapping variants are independent of each other and are walked by one thread each.  Cluster heads: a
+    // variant that starts at or after the largest end seen so far (prefix maximum in blocks of 1024).
+    const int nb = (n + 1023) / 1024;
+    ops.parFor(n, VCE_VCF_LAMBDA(int v) {
+      const uint8_t* line;
+      const VcfLine& L = vcfKeptLine(a, v, &line);
+      a.locS[v] = L.start + (L.pad ? 1 : 0);
+      a.locE[v] = L.end;
+      a.trim[v] = 0;
+    });
+    ops.parFor(nb, VCE_VCF_LAMBDA(int b) {
+      int32_t m = -0x7fffffff - 1;
+      const int hi = (b + 1) * 1024 < n ? (b + 1) * 1024 : n;
+      for (int v = b * 1024; v < hi; ++v) m = a.locE[v] > m ? a.locE[v] : m;
+      a.blockMax[b] = m;
+    });
+    ops.parFor(1, VCE_VCF_LAMBDA(int) {   // exclusive prefix maximum over the blocks
+      int32_t m = -0x7fffffff - 1;
+      for (int b = 0; b < nb; ++b) { const int32_t x = a.blockMax[b]; a.blockMax[b] = m; m = x > m ? x : m; }
+    });
+    ops.parFor(nb, VCE_VCF_LAMBDA(int b) {
+      int32_t m = a.blockMax[b];
+      const int hi = (b + 1) * 1024 < n ? (b + 1) * 1024 : n;
+      for (int v = b * 1024; v < hi; ++v) {
+        a.head[v] = (v == 0 || a.locS[v] >= m) ? 1 : 0;
+        m = a.locE[v] > m ? a.locE[v] : m;
+      }
+    });
+    ops.parFor(n, VCE_VCF_LAMBDA(int v) {
+      if (!a.head[v]) return;
+      int e = v + 1;
+      while (e < n && !a.head[e]) ++e;
+      vcfTrimCluster(a, ploidy, v, e);
+    });
+  }
+  const bool trimmed = A.cfg.refOverlap != 0;
   ops.parFor(n + 1, VCE_VCF_LAMBDA(int v) {
     if (v == n) { a.alleleOff[v] = 0; a.ntBase[v] = 0; return; }
-    const VcfLine& L = a.lines[a.streamLine[a.order[a.keptPos[v]]]];
+    const uint8_t* line;
+    const VcfLine& L = vcfKeptLine(a, v, &line);
     a.alleleOff[v] = L.nAlt + 2;
-    a.ntBase[v] = L.ntBytes;
+    int32_t bytes = L.ntBytes;
+    if (trimmed) { int32_t ls, le; vcfTrimmedLocus(line, L, ploidy, a.trim[v] == 1, &ls, &le, &bytes); }
+    a.ntBase[v] = bytes;
   });
   ops.exclusiveSum(a.alleleOff, a.alleleOff, n + 1);
   ops.exclusiveSum(a.ntBase, a.ntBase, n + 1);
@@ -669,6 +836,7 @@ void vcfFillPasses(Ops& ops, VcfArrays& A) {
   const VcfArrays a = A;
   const int n = A.n, ploidy = A.cfg.ploidy;
   const int nSlots = A.nSlots, nNt = A.nNt;
+  const bool trimmed = A.cfg.refOverlap != 0;
   ops.parFor(n, VCE_VCF_LAMBDA(int v) {
     const int p = a.keptPos[v];
     const int l = a.streamLine[a.order[p]];
@@ -678,7 +846,7 @@ void vcfFillPasses(Ops& ops, VcfArrays& A) {
     a.statusIn[v] = 0;
     for (int q = 0; q < ploidy; ++q) a.gt[(size_t) v * ploidy + q] = q < 4 ? L.gt[q] : (int8_t) -2;
     vcfFillVariant(a.text + a.lineStart[l], L, ploidy, a.alleleOff[v], a.ntBase[v], a.alleleStart, a.alleleEnd, a.alleleNull,
-                   a.alleleNtOff, a.nt);
+                   a.alleleNtOff, a.nt, trimmed ? a.trim[v] : 0);
     int e = a.lineStart[l + 1];
     if (e > a.lineStart[l] && a.text[e - 1] == '\n') --e;
     if (e > a.lineStart[l] && a.text[e - 1] == '\r') --e;
@@ -783,6 +951,14 @@ int vcfDrive(Ops& ops, const uint8_t* text, int64_t len, const VcfConfig& cfg, V
   int32_t* offScan = ops.template alloc<int32_t>((size_t) n + 1);
   A.ntBase = ops.template alloc<int32_t>((size_t) n + 1);
   if (!A.keptPos || !offScan || !A.ntBase) { err = "out of device memory for the variants"; return 2; }
+  if (cfg.refOverlap) {
+    A.locS = ops.template alloc<int32_t>((size_t) n + 1);
+    A.locE = ops.template alloc<int32_t>((size_t) n + 1);
+    A.trim = ops.template alloc<uint8_t>((size_t) n + 1);
+    A.head = ops.template alloc<uint8_t>((size_t) n + 1);
+    A.blockMax = ops.template alloc<int32_t>((size_t) n / 1024 + 2);
+    if (!A.locS || !A.locE || !A.trim || !A.head || !A.blockMax) { err = "out of device memory for the variants"; return 2; }
+  }
   A.alleleOff = offScan;
   vcfOffsetPasses(ops, A);
   const VcfLayout lay((size_t) n, (size_t) cfg.ploidy, (size_t) A.nSlots, (size_t) A.nNt);

@@ -708,6 +708,7 @@ int emul_vce_vcf_parse(const vce_vcf_in* in, void** result) {
   std::memset(&cfg, 0, sizeof(cfg));
   cfg.sample = in->sample; cfg.ploidy = in->ploidy; cfg.passOnly = in->pass_only; cfg.maxLength = in->max_length;
   cfg.templateLen = in->template_len;
+  cfg.refOverlap = in->ref_overlap;
   if (in->name) {
     const size_t nl = std::strlen(in->name);
     if (nl == 0 || nl >= sizeof(cfg.name)) return VCE_ERR_BAD_ARGUMENT;
@@ -750,6 +751,7 @@ static int emulVcfConfig(const vce_vcf_in* in, vce::VcfConfig& cfg) {
   std::memset(&cfg, 0, sizeof(cfg));
   cfg.sample = in->sample; cfg.ploidy = in->ploidy; cfg.passOnly = in->pass_only; cfg.maxLength = in->max_length;
   cfg.templateLen = in->template_len;
+  cfg.refOverlap = in->ref_overlap;
   if (in->name) {
     const size_t nl = std::strlen(in->name);
     if (nl == 0 || nl >= sizeof(cfg.name)) return VCE_ERR_BAD_ARGUMENT;

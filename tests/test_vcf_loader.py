@@ -36,8 +36,11 @@ def check_fixtures(engine):
     for name, side, si, text, seqs, p in fixture_cases():
         for nm, tmpl in seqs:
             for pass_only in (True, False):
-                vcf_check.check_text(engine, text, nm, len(tmpl), si, p.sample_ploidy, pass_only, p.max_length,
-                                     what="%s %s sample %d sequence %s pass_only %s" % (name, side, si, nm, pass_only))
+                # (every fixture also with --ref-overlap trimming, whether its own command line has it or not)
+                for ref_overlap in (p.ref_overlap, not p.ref_overlap):
+                    vcf_check.check_text(engine, text, nm, len(tmpl), si, p.sample_ploidy, pass_only, p.max_length,
+                                         what="%s %s sample %d sequence %s pass_only %s ref_overlap %s" % (name, side, si, nm, pass_only, ref_overlap),
+                                         ref_overlap=ref_overlap)
                 n += 1
     return n
 
@@ -129,6 +132,9 @@ def check_fuzz(engine, seeds, bad=False):
                 r = vcf_check.check_text(engine, text, "chr1", tl, sample, ploidy, pass_only, max_length,
                                          what="fuzz seed %d sample %d ploidy %d pass_only %s max_length %d" % (seed, sample, ploidy, pass_only, max_length))
                 outcomes[r] += 1
+                r2 = vcf_check.check_text(engine, text, "chr1", tl, sample, ploidy, pass_only, max_length, ref_overlap=True,
+                                          what="fuzz seed %d sample %d ploidy %d pass_only %s max_length %d --ref-overlap" % (seed, sample, ploidy, pass_only, max_length))
+                assert r2 == r
     return outcomes
 
 

@@ -1,20 +1,20 @@
 """Shared checker of the VCF loader (vce_vcf_parse): the arrays an engine returns for (text, sequence, sample) against the
 loader restated in oracle/ref_host.py (VcfSortRefiner + VcfRecordTabixCallable filters + SampleVariants factory +
-Allele.getAlleles), without --ref-overlap trimming and evaluation regions, which stay on the host."""
+Allele.getAlleles, Variant.trimAlleles with --ref-overlap), without evaluation regions, which stay on the host."""
 import numpy as np
 
 import ref_host
 from rtg_tools_b200 import capi
 
 
-def expected_side(text, name, template_len, sample, ploidy=2, pass_only=True, max_length=1000):
+def expected_side(text, name, template_len, sample, ploidy=2, pass_only=True, max_length=1000, ref_overlap=False):
     """(VariantSide, skipped count) or the exception class the loader ends with."""
     _, recs = ref_host.parse_vcf(text)
     recs = [r for r in recs if r.chrom == name]
 
     def factory(rec, vid):
         return ref_host.sample_variant(rec, vid, sample, ploidy, pass_only)
-    out, skipped = ref_host.load_side(recs, template_len, factory, max_length, False)
+    out, skipped = ref_host.load_side(recs, template_len, factory, max_length, ref_overlap)
     side = capi.VariantSide.from_variants(out, ploidy)
     side.roc_expect = expected_roc_fields(out, sample)
     return side, skipped
@@ -58,17 +58,17 @@ def assert_same_side(got, want, what):
         assert a.shape == b.shape and np.array_equal(a, b), "%s: %s differs\n got %s\nwant %s" % (what, f, a[:40], b[:40])
 
 
-def check_text(engine, text, name, template_len, sample, ploidy=2, pass_only=True, max_length=1000, what=""):
+def check_text(engine, text, name, template_len, sample, ploidy=2, pass_only=True, max_length=1000, what="", ref_overlap=False):
     """Compares one (text, sequence, sample); returns 'ok' or 'format-error' (both sides agree the text is invalid)."""
     try:
-        want, skipped = expected_side(text, name, template_len, sample, ploidy, pass_only, max_length)
+        want, skipped = expected_side(text, name, template_len, sample, ploidy, pass_only, max_length, ref_overlap)
     except (ref_host.VcfFormatError, ValueError, IndexError):
         try:
-            engine.vcf_parse(text.encode(), name, template_len, sample, ploidy, pass_only, max_length)
+            engine.vcf_parse(text.encode(), name, template_len, sample, ploidy, pass_only, max_length, ref_overlap)
         except ValueError:
             return "format-error"
         raise AssertionError("%s: the reference loader rejects this text, the engine accepted it" % what)
-    got, stats = engine.vcf_parse(text.encode(), name, template_len, sample, ploidy, pass_only, max_length)
+    got, stats = engine.vcf_parse(text.encode(), name, template_len, sample, ploidy, pass_only, max_length, ref_overlap)
     assert_same_side(got, want, what)
     assert stats["skipped"] == skipped, "%s: skipped %d vs %d" % (what, stats["skipped"], skipped)
     if "roc_mask" in stats:
