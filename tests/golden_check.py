@@ -24,9 +24,47 @@ def _weight_str(w):
     return None if abs(w - 1.0) <= 0.001 else format(w, "#.3g")
 
 
-def check_scenario(engine, sc, cfg_over=None):
+def bgzf_side_loader(library):
+    """A side loader for run_vcfeval that goes the whole way of the device loaders: the VCF text is bgzipped and indexed here
+    (oracle/formats_oracle.py), then the sequence's records are found through vce_tabix_query and read through
+    vce_vcf_parse_bgzf (inflate + parse + --ref-overlap trimming on the engine under test)."""
+    import formats_oracle as fo
+    cache = {}
+
+    def load(text, name, template_len, sample, ploidy, pass_only, max_length, ref_overlap):
+        if id(text) not in cache:
+            raw = text.encode()
+            lines = text.split("\n")
+            header_len = 0
+            recs = []
+            names = []
+            pos = 0
+            data, index = fo.bgzf_write(raw, 777)     # small members: records straddle them
+            for ln in lines:
+                nxt = pos + len(ln) + 1
+                if ln and not ln.startswith("#"):
+                    f = ln.split("\t")
+                    if f[0] not in names:
+                        names.append(f[0])
+                    beg = int(f[1]) - 1
+                    recs.append((names.index(f[0]), beg, beg + max(1, len(f[3])), fo.voffset(index, pos), fo.voffset(index, min(nxt, len(raw)))))
+                pos = nxt
+            # tabix needs the records of a sequence to be contiguous; the fixtures are sorted by sequence
+            cache[id(text)] = (data, library.tabix_open(fo.tabix_build(recs, names)) if recs else None)
+        data, idx = cache[id(text)]
+        q = idx.query(name) if idx is not None else None
+        if q is None:      # nothing indexed for the sequence: what TabixLineReader would read is empty
+            side, _ = library.vcf_parse(b"", name, template_len, sample, ploidy, pass_only, max_length, ref_overlap)
+            return side
+        side, _ = library.vcf_parse_bgzf(data, q[0], q[1], name, template_len, sample, ploidy, pass_only, max_length, True, ref_overlap)
+        return side
+    return load
+
+
+def check_scenario(engine, sc, cfg_over=None, side_loader=None):
     """Returns the list of output names that were compared."""
-    rr = ref_host.run_vcfeval(engine, sc["template_fa"], sc["baseline_vcf"], sc["calls_vcf"], sc["args"], cfg_over)
+    rr = ref_host.run_vcfeval(engine, sc["template_fa"], sc["baseline_vcf"], sc["calls_vcf"], sc["args"], cfg_over, side_loader)
+    check_scenario.device_loaded = getattr(check_scenario, "device_loaded", 0) + getattr(rr, "device_loaded", 0)
     exp = sc["expected"]
     checked = []
     p = rr.params

@@ -69,3 +69,25 @@ def test_sdf_planes_layout():
     f = fo.sdf_planes_write(np.array([4, 1, 2, 3, 0], np.uint8))
     longs = np.frombuffer(f, ">u8")
     assert longs.tolist() == [0b00001, 0b01100, 0b01010]
+
+
+def test_emul_golden_fixtures_from_vcf_gz(emul):
+    """The reference's own vcfeval fixtures end to end with the device loaders in the way: every VCF is bgzipped and tabix-indexed,
+    each sequence's records are found through the index, inflated, parsed and (with --ref-overlap) trimmed by the engine under
+    test, the matching runs on those arrays, and the outputs must be the files the reference's tests expect."""
+    import json
+    import os
+    from golden_check import bgzf_side_loader, check_scenario
+    from helpers import Hybrid
+    from rtg_tools_b200 import capi
+    from test_oracle_golden import SCENARIOS
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "tests", "golden", "vcfeval_fixtures.json")) as f:
+        fx = json.load(f)["scenarios"]
+    oracle = capi.Library(os.path.join(root, "oracle", "liboracle.so"), prefix="oracle_")
+    loader = bgzf_side_loader(emul)
+    check_scenario.device_loaded = 0
+    for name in SCENARIOS:
+        assert check_scenario(Hybrid(emul, oracle), fx[name], side_loader=loader), name
+    # 26 of the 29 scenarios load sample columns without a region restriction: 83 sides came through the chain
+    assert check_scenario.device_loaded >= 80

@@ -443,3 +443,16 @@ def test_cuda_sdf_template(engine, oracle):
         assert st["h2d_bytes"] == engine.submit_stats()["h2d_bytes"]
     finally:
         engine.unregister_templates(seqs)
+
+
+def test_cuda_golden_fixtures_from_vcf_gz(engine, fixtures):
+    """The reference's vcfeval fixtures end to end on the device: .vcf.gz + .tbi -> tabix query -> BGZF inflate -> VCF parse (+
+    --ref-overlap trimming) -> matching -> the output files the reference's tests expect (83 sides of 26 scenarios go through the
+    loader chain; the arrays are also compared with the restated host loader's)."""
+    from golden_check import bgzf_side_loader
+    loader = bgzf_side_loader(engine.lib)
+    check_scenario.device_loaded = 0
+    for name in SCENARIOS:
+        assert check_scenario(engine, fixtures[name], side_loader=loader), name
+    assert check_scenario.device_loaded >= 80
+
