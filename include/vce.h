@@ -274,7 +274,7 @@ int vce_roc_timed(const vce_roc_in* in, vce_roc_out* out, double* h2d_ms, double
  * VcfUtils.getAlleleStrings / hasRedundantFirstNucleotide (:785-828), VariantType.getType (:107-190) and Allele.getAlleles
  * (Allele.java:145-192) and, with ref_overlap, Variant.trimAlleles (Variant.java:93-190: REF nulled, ALTs stripped of what they
  * share with REF, the side decided by the overlapping neighbours; clusters of overlapping variants one thread each).
- * Evaluation regions stay with the host.
+ * With eval_regions, the OUTSIDE_EVAL status bit of VcfRecordTabixCallable.java:125-127 (MergedIntervals.overlapped :172-179).
  * A record the reference would throw VcfFormatException for ends the call with VCE_ERR_BAD_ARGUMENT (vce_last_error names
  * the line).  The result owns host copies of the arrays until vce_vcf_free.
  */
@@ -288,7 +288,10 @@ typedef struct vce_vcf_in {
   int32_t     pass_only;      /* 0 with --all-records                              */
   int32_t     max_length;     /* --Xmax-length (1000), -1 = no limit               */
   int32_t     ref_overlap;    /* --ref-overlap: Variant.trimAlleles (Variant.java:93-190) on the loaded variants */
-  int32_t     reserved;
+  int32_t     n_eval_regions; /* --evaluation-regions of this sequence; ignored when eval_regions is NULL */
+  const int32_t* eval_regions;/* [n_eval_regions * 2] merged intervals [start, end), ascending (ReferenceRegions / MergedIntervals):
+                                 variants whose locus overlaps none get VCE_STATUS_OUTSIDE_EVAL in status_in
+                                 (VcfRecordTabixCallable.java:125-127); NULL = no regions given */
 } vce_vcf_in;
 typedef struct vce_vcf_stats {
   int64_t lines, records, kept, skipped;   /* text lines, records of the sequence, variants, counted skips (:103-118) */

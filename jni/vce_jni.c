@@ -290,7 +290,8 @@ static void set_byte_field_array(JNIEnv* e, jobject o, const char* name, const v
 }
 
 JNIEXPORT jint JNICALL Java_com_rtg_vcf_eval_NativeVce_loadVcfGz(JNIEnv* e, jclass c, jbyteArray jfile, jlong vbeg, jlong vend, jstring jname,
-    jint templateLength, jint sample, jint ploidy, jboolean passOnly, jint maxLength, jboolean refOverlap, jobject jout, jlongArray jcounters) {
+    jint templateLength, jint sample, jint ploidy, jboolean passOnly, jint maxLength, jboolean refOverlap, jintArray jregions, jobject jout,
+    jlongArray jcounters) {
   (void) c;
   const char* name = (*e)->GetStringUTFChars(e, jname, NULL);
   vce_vcf_in in;
@@ -305,9 +306,14 @@ JNIEXPORT jint JNICALL Java_com_rtg_vcf_eval_NativeVce_loadVcfGz(JNIEnv* e, jcla
   in.ref_overlap = refOverlap ? 1 : 0;
   void* result = NULL;
   /* the file bytes are pinned for the call only: the engine uploads them and keeps nothing */
+  const jsize nreg = jregions ? (*e)->GetArrayLength(e, jregions) / 2 : 0;
   void* p = (*e)->GetPrimitiveArrayCritical(e, jfile, NULL);
+  void* reg = jregions ? (*e)->GetPrimitiveArrayCritical(e, jregions, NULL) : NULL;
   in.text = (const char*) p;
+  in.eval_regions = (const int32_t*) reg;
+  in.n_eval_regions = (int32_t) nreg;
   int rc = vce_vcf_parse_bgzf(&in, (int64_t) vbeg, (int64_t) vend, 0, &result, NULL);
+  if (reg) (*e)->ReleasePrimitiveArrayCritical(e, jregions, reg, JNI_ABORT);
   (*e)->ReleasePrimitiveArrayCritical(e, jfile, p, JNI_ABORT);
   (*e)->ReleaseStringUTFChars(e, jname, name);
   if (rc != 0) return rc;

@@ -547,6 +547,8 @@ int vce_vcf_parse(const vce_vcf_in* in, void** result) {
   cfg.sample = in->sample; cfg.ploidy = in->ploidy; cfg.passOnly = in->pass_only; cfg.maxLength = in->max_length;
   cfg.templateLen = in->template_len;
   cfg.refOverlap = in->ref_overlap;
+  cfg.evalRegions = in->eval_regions;
+  cfg.nEvalRegions = in->eval_regions ? in->n_eval_regions : -1;
   if (in->name) {
     const size_t nl = std::strlen(in->name);
     if (nl == 0 || nl >= sizeof(cfg.name)) return fail(VCE_ERR_BAD_ARGUMENT, "sequence name empty or too long");
@@ -600,6 +602,8 @@ int vcfConfigFrom(const vce_vcf_in* in, vce::VcfConfig& cfg) {
   cfg.sample = in->sample; cfg.ploidy = in->ploidy; cfg.passOnly = in->pass_only; cfg.maxLength = in->max_length;
   cfg.templateLen = in->template_len;
   cfg.refOverlap = in->ref_overlap;
+  cfg.evalRegions = in->eval_regions;
+  cfg.nEvalRegions = in->eval_regions ? in->n_eval_regions : -1;
   if (in->name) {
     const size_t nl = std::strlen(in->name);
     if (nl == 0 || nl >= sizeof(cfg.name)) return fail(VCE_ERR_BAD_ARGUMENT, "sequence name empty or too long");

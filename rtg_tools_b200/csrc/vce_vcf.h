@@ -21,6 +21,7 @@
 #include <string>
 #include <vector>
 
+#include "../../include/vce.h"
 #include "vce_device.h"
 
 #if defined(__CUDACC__)
@@ -43,6 +44,8 @@ struct VcfConfig {
   int32_t templateLen;   // records that end beyond it are skipped, -1 = unknown
   int32_t nameLen;       // CHROM to accept (a tabix query returns one sequence's records); 0 = accept every record
   int32_t refOverlap;    // --ref-overlap: Variant.trimAlleles (Variant.java:93-190) on the loaded variants
+  int32_t nEvalRegions;  // --evaluation-regions of this sequence: merged intervals, ascending; -1 = none
+  const int32_t* evalRegions;   // HOST pointer to [start, end) pairs (vcfDrive makes the device copy: VcfArrays::evalRegions)
   char name[232];
 };
 
@@ -88,6 +91,8 @@ struct VcfArrays {
   int32_t* alleleNtOff;    // [nSlots + 1]
   uint8_t* nt;             // [nNt]
   uint32_t* rocMask;       // [n] RocFilter bits of the variant's record (vcfRocFields)
+  const int32_t* evalRegions;   // device copy of the evaluation regions (pairs), nullptr = none
+  int32_t nEvalRegions;
   // --ref-overlap (sized n + 1 when on): current locus of every kept variant, trim mode, cluster heads, prefix maxima
   int32_t* locS;
   int32_t* locE;
@@ -843,7 +848,17 @@ void vcfFillPasses(Ops& ops, VcfArrays& A) {
     const VcfLine& L = a.lines[l];
     a.id[v] = p + 1;   // 1-based ordinal of the record in the refined stream, counted before any filter (:100)
     a.phased[v] = L.phased;
-    a.statusIn[v] = 0;
+    // VcfRecordTabixCallable.java:125-127: outside the evaluation regions (MergedIntervals.overlapped :172-179 on the variant's
+    // untrimmed locus: the interval with the greatest start below the locus' end must reach beyond its start)
+    uint8_t status = 0;
+    if (a.evalRegions) {
+      const int32_t vs = L.start + (L.pad ? 1 : 0), ve = L.end;
+      int lo = 0, hi = a.nEvalRegions;          // first interval whose start is >= ve
+      while (lo < hi) { const int m = (lo + hi) / 2; if (a.evalRegions[2 * m] < ve) lo = m + 1; else hi = m; }
+      const bool over = lo > 0 && vs < a.evalRegions[2 * (lo - 1) + 1];
+      if (!over) status = VCE_STATUS_OUTSIDE_EVAL;
+    }
+    a.statusIn[v] = status;
     for (int q = 0; q < ploidy; ++q) a.gt[(size_t) v * ploidy + q] = q < 4 ? L.gt[q] : (int8_t) -2;
     vcfFillVariant(a.text + a.lineStart[l], L, ploidy, a.alleleOff[v], a.ntBase[v], a.alleleStart, a.alleleEnd, a.alleleNull,
                    a.alleleNtOff, a.nt, trimmed ? a.trim[v] : 0);
@@ -951,6 +966,13 @@ int vcfDrive(Ops& ops, const uint8_t* text, int64_t len, const VcfConfig& cfg, V
   int32_t* offScan = ops.template alloc<int32_t>((size_t) n + 1);
   A.ntBase = ops.template alloc<int32_t>((size_t) n + 1);
   if (!A.keptPos || !offScan || !A.ntBase) { err = "out of device memory for the variants"; return 2; }
+  if (cfg.nEvalRegions >= 0 && cfg.evalRegions) {
+    int32_t* dReg = ops.template alloc<int32_t>((size_t) cfg.nEvalRegions * 2 + 2);
+    if (!dReg) { err = "out of device memory for the evaluation regions"; return 2; }
+    ops.upload(dReg, cfg.evalRegions, (size_t) cfg.nEvalRegions * 2 * sizeof(int32_t));
+    A.evalRegions = dReg;
+    A.nEvalRegions = cfg.nEvalRegions;
+  }
   if (cfg.refOverlap) {
     A.locS = ops.template alloc<int32_t>((size_t) n + 1);
     A.locE = ops.template alloc<int32_t>((size_t) n + 1);

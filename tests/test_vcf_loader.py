@@ -132,8 +132,12 @@ def check_fuzz(engine, seeds, bad=False):
                 r = vcf_check.check_text(engine, text, "chr1", tl, sample, ploidy, pass_only, max_length,
                                          what="fuzz seed %d sample %d ploidy %d pass_only %s max_length %d" % (seed, sample, ploidy, pass_only, max_length))
                 outcomes[r] += 1
-                r2 = vcf_check.check_text(engine, text, "chr1", tl, sample, ploidy, pass_only, max_length, ref_overlap=True,
-                                          what="fuzz seed %d sample %d ploidy %d pass_only %s max_length %d --ref-overlap" % (seed, sample, ploidy, pass_only, max_length))
+                # --evaluation-regions: random merged intervals (some empty gaps, some covering everything nearby)
+                cuts = np.sort(rng.choice(np.arange(1, tl + 50), size=int(rng.integers(0, 12)) * 2, replace=False))
+                regions = [(int(cuts[i]), int(cuts[i + 1])) for i in range(0, len(cuts), 2)]
+                r2 = vcf_check.check_text(engine, text, "chr1", tl, sample, ploidy, pass_only, max_length, ref_overlap=True, eval_regions=regions,
+                                          what="fuzz seed %d sample %d ploidy %d pass_only %s max_length %d --ref-overlap, %d regions" % (
+                                              seed, sample, ploidy, pass_only, max_length, len(regions)))
                 assert r2 == r
     return outcomes
 

@@ -7,14 +7,14 @@ import ref_host
 from rtg_tools_b200 import capi
 
 
-def expected_side(text, name, template_len, sample, ploidy=2, pass_only=True, max_length=1000, ref_overlap=False):
+def expected_side(text, name, template_len, sample, ploidy=2, pass_only=True, max_length=1000, ref_overlap=False, eval_regions=None):
     """(VariantSide, skipped count) or the exception class the loader ends with."""
     _, recs = ref_host.parse_vcf(text)
     recs = [r for r in recs if r.chrom == name]
 
     def factory(rec, vid):
         return ref_host.sample_variant(rec, vid, sample, ploidy, pass_only)
-    out, skipped = ref_host.load_side(recs, template_len, factory, max_length, ref_overlap)
+    out, skipped = ref_host.load_side(recs, template_len, factory, max_length, ref_overlap, eval_regions)
     side = capi.VariantSide.from_variants(out, ploidy)
     side.roc_expect = expected_roc_fields(out, sample)
     return side, skipped
@@ -58,17 +58,18 @@ def assert_same_side(got, want, what):
         assert a.shape == b.shape and np.array_equal(a, b), "%s: %s differs\n got %s\nwant %s" % (what, f, a[:40], b[:40])
 
 
-def check_text(engine, text, name, template_len, sample, ploidy=2, pass_only=True, max_length=1000, what="", ref_overlap=False):
+def check_text(engine, text, name, template_len, sample, ploidy=2, pass_only=True, max_length=1000, what="", ref_overlap=False,
+               eval_regions=None):
     """Compares one (text, sequence, sample); returns 'ok' or 'format-error' (both sides agree the text is invalid)."""
     try:
-        want, skipped = expected_side(text, name, template_len, sample, ploidy, pass_only, max_length, ref_overlap)
+        want, skipped = expected_side(text, name, template_len, sample, ploidy, pass_only, max_length, ref_overlap, eval_regions)
     except (ref_host.VcfFormatError, ValueError, IndexError):
         try:
-            engine.vcf_parse(text.encode(), name, template_len, sample, ploidy, pass_only, max_length, ref_overlap)
+            engine.vcf_parse(text.encode(), name, template_len, sample, ploidy, pass_only, max_length, ref_overlap, eval_regions)
         except ValueError:
             return "format-error"
         raise AssertionError("%s: the reference loader rejects this text, the engine accepted it" % what)
-    got, stats = engine.vcf_parse(text.encode(), name, template_len, sample, ploidy, pass_only, max_length, ref_overlap)
+    got, stats = engine.vcf_parse(text.encode(), name, template_len, sample, ploidy, pass_only, max_length, ref_overlap, eval_regions)
     assert_same_side(got, want, what)
     assert stats["skipped"] == skipped, "%s: skipped %d vs %d" % (what, stats["skipped"], skipped)
     if "roc_mask" in stats:
