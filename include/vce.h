@@ -283,7 +283,8 @@ typedef struct vce_vcf_in {
   int64_t     text_len;       /* < 2 GB                                            */
   const char* name;           /* CHROM to accept; NULL = every record              */
   int32_t     template_len;   /* records ending beyond it are skipped; -1 = unknown */
-  int32_t     sample;         /* sample column, 0-based                            */
+  int32_t     sample;         /* sample column, 0-based; -1 = `--sample ALT` (VariantFactory.AllAlts :195-239: every
+                                 ALT that is a sequence, no genotypes: gt_ploidy 0) */
   int32_t     ploidy;         /* --sample-ploidy (2)                               */
   int32_t     pass_only;      /* 0 with --all-records                              */
   int32_t     max_length;     /* --Xmax-length (1000), -1 = no limit               */

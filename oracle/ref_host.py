@@ -760,7 +760,7 @@ def run_vcfeval(engine, template_fa, baseline_vcf, calls_vcf, args, cfg_over=Non
     """Replays `rtg vcfeval` on in-memory text inputs.  Returns a RunResult with per-record outcomes and the
     regenerated output files the fixtures check.  `side_loader(vcf_text, name, template_len, sample, ploidy, pass_only, max_length,
     ref_overlap) -> VariantSide` (optional): the arrays handed to the engine come from it (the device loaders under test) instead
-    of from this module's own loader, wherever a sample column is loaded without a region restriction; the arrays of both loaders
+    of from this module's own loader, wherever the run has no region restriction; the arrays of both loaders
     must agree, and everything downstream then runs on the loader's output."""
     p = Params(args)
     seqs = parse_fasta(template_fa)
@@ -813,15 +813,14 @@ def run_vcfeval(engine, template_fa, baseline_vcf, calls_vcf, args, cfg_over=Non
         cside = capi.VariantSide.from_variants(cl, gp if cfac == "sample" else 0)
         if side_loader is not None and p.region is None:
             fields = ("id", "phased", "status_in", "gt", "allele_off", "allele_start", "allele_end", "allele_null", "allele_nt_off", "nt")
-            if bfac == "sample":
-                got = side_loader(baseline_vcf, name, len(tmpl), bsample, gp, pass_only, p.max_length, p.ref_overlap)
-                assert all(np.array_equal(np.asarray(getattr(got, f)), np.asarray(getattr(bside, f))) for f in fields), "baseline arrays of %s differ" % name
-                bside = got
-            if cfac == "sample":
-                got = side_loader(calls_vcf, name, len(tmpl), csample, gp, pass_only, p.max_length, p.ref_overlap)
-                assert all(np.array_equal(np.asarray(getattr(got, f)), np.asarray(getattr(cside, f))) for f in fields), "call arrays of %s differ" % name
-                cside = got
-            rr.device_loaded = getattr(rr, "device_loaded", 0) + (bfac == "sample") + (cfac == "sample")
+            # (sample -1 = the all-alts factory of `--sample ALT`)
+            got = side_loader(baseline_vcf, name, len(tmpl), bsample, gp, pass_only, p.max_length, p.ref_overlap)
+            assert all(np.array_equal(np.asarray(getattr(got, f)), np.asarray(getattr(bside, f))) for f in fields), "baseline arrays of %s differ" % name
+            bside = got
+            got = side_loader(calls_vcf, name, len(tmpl), csample, gp, pass_only, p.max_length, p.ref_overlap)
+            assert all(np.array_equal(np.asarray(getattr(got, f)), np.asarray(getattr(cside, f))) for f in fields), "call arrays of %s differ" % name
+            cside = got
+            rr.device_loaded = getattr(rr, "device_loaded", 0) + 2
         batch.append(capi.Sequence(name, tmpl, bside, cside))
         loaded.append((bl, cl))
     results = engine.submit(cfg, batch)

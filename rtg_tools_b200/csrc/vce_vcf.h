@@ -49,7 +49,7 @@ struct VcfConfig {
   char name[232];
 };
 
-struct VcfLine {           // 40 bytes per line of text
+struct VcfLine {           // 44 bytes per line of text
   int32_t start, end;      // POS - 1, start + len(REF)
   int32_t nAlt;
   int32_t ntBytes;         // bases of the materialised, non-null alleles
@@ -57,6 +57,7 @@ struct VcfLine {           // 40 bytes per line of text
   uint8_t kind, fatal, phased, pad;
   int32_t refOff, altOff;  // offsets of REF / ALT within the line (the fill pass reads them again)
   int32_t altLen, refLen;
+  int32_t nSlots;          // allele slots of the variant: nAlt + 2, or 2 + the non-symbolic ALTs in all-alts mode (gt[0] == -3)
 };
 
 struct VcfArrays {
@@ -163,6 +164,7 @@ VCE_HDN void vcfParseLine(const uint8_t* t, int a, int b, const VcfConfig& cfg, 
   L.gt[0] = L.gt[1] = L.gt[2] = L.gt[3] = -2;
   L.kind = VK_NOT_STREAM; L.fatal = VF_NONE; L.phased = 0; L.pad = 0;
   L.refOff = L.altOff = L.altLen = L.refLen = 0;
+  L.nSlots = 0;
   if (b > a && t[b - 1] == '\r') --b;
   bool blank = true;
   for (int i = a; i < b; ++i) if (t[i] != ' ' && t[i] != '\t') { blank = false; break; }
@@ -215,6 +217,50 @@ VCE_HDN void vcfParseLine(const uint8_t* t, int a, int b, const VcfConfig& cfg, 
   if (cfg.maxLength > -1 && longest > cfg.maxLength) { L.kind = VK_SKIPPED; return; }
   // loader filter 2: beyond the template (:107-112)
   if (cfg.templateLen >= 0 && L.end > cfg.templateLen) { L.kind = VK_SKIPPED; return; }
+  if (cfg.sample < 0) {
+    // ---- AllAlts.variant (VariantFactory.java:223-239): no sample column; every ALT that is a sequence becomes an allele
+    // (pruneEmptyAlts :211-221 drops the symbolic ones from the table), no genotype
+    if (cfg.passOnly) {
+      const uint8_t* fil = t + fo[4];
+      const int filLen = fl[4];
+      if (!(filLen == 1 && fil[0] == '.') && vcfListFails(fil, filLen)) return;
+    }
+    if (nAlt == 0) return;
+    bool pad = false;
+    {
+      const uint8_t c = refLen > 0 ? ref[0] : (uint8_t) '.';
+      bool hasAlt = false, same = true;
+      for (int k = 0; k < nAlt; ++k) {
+        int o = 0, l = 0;
+        vcfNth(alt, altLen, ',', k, &o, &l);
+        if (l > 0 && alt[o] != '*') { hasAlt = true; if (alt[o] != c) same = false; }
+        else if (l == 0) same = false;
+      }
+      pad = hasAlt && same;
+    }
+    L.pad = pad ? 1 : 0;
+    const int from = pad ? 1 : 0;
+    int ntBytes = 0, real = 0;
+    for (int id = 0; id <= nAlt; ++id) {
+      const uint8_t* sq = ref;
+      int sn = refLen;
+      if (id > 0) {
+        int o = 0, l = 0;
+        vcfNth(alt, altLen, ',', id - 1, &o, &l);
+        sq = alt + o; sn = l;
+      }
+      if (vcfIsSym(sq, sn)) continue;
+      for (int q = from; q < sn; ++q) if (vcfBaseCode(sq[q]) < 0) { L.kind = VK_SKIPPED; return; }
+      ntBytes += sn > from ? sn - from : 0;
+      if (id > 0) ++real;
+    }
+    if (real == 0) return;
+    L.ntBytes = ntBytes;
+    L.nSlots = 2 + real;
+    L.gt[0] = -3;   // all-alts marker
+    L.kind = VK_KEPT;
+    return;
+  }
   // ---- SampleVariants.variant (VariantFactory.java:127-147)
   const uint8_t* fmt = t + fo[5];
   const int fmtLen = fl[5] < 0 ? 0 : fl[5];
@@ -346,6 +392,7 @@ VCE_HDN void vcfParseLine(const uint8_t* t, int a, int b, const VcfConfig& cfg, 
   L.ntBytes = ntBytes;
   for (int q = 0; q < ng; ++q) L.gt[q] = (int8_t) gt[q];
   L.phased = phased ? 1 : 0;
+  L.nSlots = nAlt + 2;
   L.kind = VK_KEPT;
   return;
 }
@@ -522,7 +569,7 @@ VCE_HDN void vcfRocFields(const uint8_t* line, int lineLen, const VcfLine& L, in
 VCE_HD bool vcfAlleleText(const uint8_t* line, const VcfLine& L, int ploidy, int id, const uint8_t** s, int* sn) {
   const int pad = L.pad ? 1 : 0;
   if (id == 0) { *s = line + L.refOff + pad; *sn = L.refLen - pad; return true; }
-  bool have = false;
+  bool have = L.gt[0] == -3;   // all-alts mode: every ALT
   for (int q = 0; q < ploidy && q < 4; ++q) if (L.gt[q] == id) have = true;
   if (!have) return false;
   int o = 0, l = 0;
@@ -621,6 +668,33 @@ VCE_HDN void vcfFillVariant(const uint8_t* line, const VcfLine& L, int ploidy, i
   const uint8_t* ref = line + L.refOff;
   const uint8_t* alt = line + L.altOff;
   int at = nt0;
+  if (L.gt[0] == -3) {   // all-alts mode: slot 0 missing, slot 1 REF, then the ALTs that are sequences, closed up (pruneEmptyAlts)
+    const uint8_t* r0; int rn;
+    vcfAlleleText(line, L, ploidy, 0, &r0, &rn);
+    int slot = 0;
+    aNtOff[slot0] = at; aStart[slot0] = 0; aEnd[slot0] = 0; aNull[slot0] = 1;
+    ++slot;
+    aNtOff[slot0 + slot] = at;
+    if (trim) { aStart[slot0 + slot] = 0; aEnd[slot0 + slot] = 0; aNull[slot0 + slot] = 1; }
+    else {
+      aStart[slot0 + slot] = L.start + (L.pad ? 1 : 0); aEnd[slot0 + slot] = L.end; aNull[slot0 + slot] = 0;
+      for (int q = 0; q < rn; ++q) nt[at++] = (uint8_t) vcfBaseCode(r0[q]);
+    }
+    ++slot;
+    for (int id = 1; id <= L.nAlt; ++id) {
+      const uint8_t* s; int sn;
+      if (!vcfAlleleText(line, L, ploidy, id, &s, &sn)) continue;
+      int lead = 0, trail = 0;
+      if (trim) vcfTrimOf(r0, rn, s, sn, trim == 1, &lead, &trail);
+      aNtOff[slot0 + slot] = at;
+      aStart[slot0 + slot] = L.start + (L.pad ? 1 : 0) + lead;
+      aEnd[slot0 + slot] = L.end - trail;
+      aNull[slot0 + slot] = 0;
+      for (int q = lead; q < sn - trail; ++q) nt[at++] = (uint8_t) vcfBaseCode(s[q]);
+      ++slot;
+    }
+    return;
+  }
   if (trim) {   // --ref-overlap: REF becomes null, every ALT loses what it shares with REF (Variant.trimAlleles(boolean) :97-122)
     const uint8_t* r0; int rn;
     vcfAlleleText(line, L, ploidy, 0, &r0, &rn);
@@ -824,7 +898,7 @@ void vcfOffsetPasses(Ops& ops, VcfArrays& A) {
     if (v == n) { a.alleleOff[v] = 0; a.ntBase[v] = 0; return; }
     const uint8_t* line;
     const VcfLine& L = vcfKeptLine(a, v, &line);
-    a.alleleOff[v] = L.nAlt + 2;
+    a.alleleOff[v] = L.nSlots;
     int32_t bytes = L.ntBytes;
     if (trimmed) { int32_t ls, le; vcfTrimmedLocus(line, L, ploidy, a.trim[v] == 1, &ls, &le, &bytes); }
     a.ntBase[v] = bytes;
@@ -859,13 +933,14 @@ void vcfFillPasses(Ops& ops, VcfArrays& A) {
       if (!over) status = VCE_STATUS_OUTSIDE_EVAL;
     }
     a.statusIn[v] = status;
-    for (int q = 0; q < ploidy; ++q) a.gt[(size_t) v * ploidy + q] = q < 4 ? L.gt[q] : (int8_t) -2;
+    if (a.cfg.sample >= 0) for (int q = 0; q < ploidy; ++q) a.gt[(size_t) v * ploidy + q] = q < 4 ? L.gt[q] : (int8_t) -2;
     vcfFillVariant(a.text + a.lineStart[l], L, ploidy, a.alleleOff[v], a.ntBase[v], a.alleleStart, a.alleleEnd, a.alleleNull,
                    a.alleleNtOff, a.nt, trimmed ? a.trim[v] : 0);
     int e = a.lineStart[l + 1];
     if (e > a.lineStart[l] && a.text[e - 1] == '\n') --e;
     if (e > a.lineStart[l] && a.text[e - 1] == '\r') --e;
-    vcfRocFields(a.text + a.lineStart[l], e - a.lineStart[l], L, ploidy, a.rocMask + v, a.qual + v);
+    if (a.cfg.sample >= 0) vcfRocFields(a.text + a.lineStart[l], e - a.lineStart[l], L, ploidy, a.rocMask + v, a.qual + v);
+    else { a.rocMask[v] = 0; a.qual[v] = 0.0; }   // all-alts mode has no sample to classify: the ROC inputs are the caller's
   });
   ops.parFor(n + 1, VCE_VCF_LAMBDA(int v) { a.alleleOffOut[v] = a.alleleOff[v]; });
   ops.parFor(1, VCE_VCF_LAMBDA(int) { a.alleleNtOff[nSlots] = nNt; });
@@ -914,8 +989,8 @@ template <class Ops>
 int vcfDrive(Ops& ops, const uint8_t* text, int64_t len, const VcfConfig& cfg, VcfResult& R, std::string& err,
              const uint8_t* residentText = nullptr) {   // residentText: the text is in device memory already (vce_bgzf.h)
   if (len < 0 || len >= 0x7ffffff0LL) { err = "VCF text of 2 GB or more: hand it over in pieces (one sequence per call)"; return 1; }
-  if (cfg.ploidy < 1 || cfg.ploidy > 4 || cfg.sample < 0) { err = "sample / ploidy out of range"; return 1; }
-  R.ploidy = cfg.ploidy;
+  if (cfg.ploidy < 1 || cfg.ploidy > 4 || cfg.sample < -1) { err = "sample / ploidy out of range"; return 1; }
+  R.ploidy = cfg.sample < 0 ? 0 : cfg.ploidy;   // all-alts mode (sample -1, VariantFactory.AllAlts): no genotypes
   VcfArrays A;
   std::memset(&A, 0, sizeof(A));
   A.len = (int32_t) len;

@@ -27,7 +27,7 @@ def fixture_cases():
         p = ref_host.Params(sc["args"])
         for side in ("baseline_vcf", "calls_vcf"):
             samples, _ = ref_host.parse_vcf(sc[side])
-            for si in range(len(samples)):
+            for si in [-1] + list(range(len(samples))):     # -1 = --sample ALT (all-alts factory)
                 yield name, side, si, sc[side], seqs, p
 
 
@@ -127,7 +127,7 @@ def check_fuzz(engine, seeds, bad=False):
         rng = np.random.default_rng(seed)
         tl = 2000
         text = fuzz_vcf(rng, template_len=tl, bad=bad)
-        for sample in (0, 1):
+        for sample in (0, 1, -1):
             for ploidy, pass_only, max_length in ((2, True, 1000), (2, False, 20), (1, True, 1000), (3, False, 1000)):
                 r = vcf_check.check_text(engine, text, "chr1", tl, sample, ploidy, pass_only, max_length,
                                          what="fuzz seed %d sample %d ploidy %d pass_only %s max_length %d" % (seed, sample, ploidy, pass_only, max_length))
@@ -150,7 +150,7 @@ def test_emul_vcf_loader_matches_reference_on_fixtures(emul):
 
 def test_emul_vcf_loader_fuzz(emul):
     out = check_fuzz(emul, range(40))
-    assert out["ok"] == 40 * 8
+    assert out["ok"] == 40 * 12
 
 
 def test_emul_vcf_loader_format_errors(emul):
