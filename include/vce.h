@@ -290,6 +290,8 @@ typedef struct vce_vcf_in {
   int32_t     max_length;     /* --Xmax-length (1000), -1 = no limit               */
   int32_t     ref_overlap;    /* --ref-overlap: Variant.trimAlleles (Variant.java:93-190) on the loaded variants */
   int32_t     n_eval_regions; /* --evaluation-regions of this sequence; ignored when eval_regions is NULL */
+  int32_t     region_begin;   /* --region within the sequence: only records overlapping [region_begin, region_end) belong to the */
+  int32_t     region_end;     /* stream (0-based, end exclusive; what TabixLineReader hands on); region_end < 0 = whole sequence */
   const int32_t* eval_regions;/* [n_eval_regions * 2] merged intervals [start, end), ascending (ReferenceRegions / MergedIntervals):
                                  variants whose locus overlaps none get VCE_STATUS_OUTSIDE_EVAL in status_in
                                  (VcfRecordTabixCallable.java:125-127); NULL = no regions given */

@@ -304,6 +304,8 @@ JNIEXPORT jint JNICALL Java_com_rtg_vcf_eval_NativeVce_loadVcfGz(JNIEnv* e, jcla
   in.pass_only = passOnly ? 1 : 0;
   in.max_length = maxLength;
   in.ref_overlap = refOverlap ? 1 : 0;
+  in.region_begin = 0;
+  in.region_end = -1;   /* the whole sequence (a finer --region: set both from the RegionRestriction) */
   void* result = NULL;
   /* the file bytes are pinned for the call only: the engine uploads them and keeps nothing */
   const jsize nreg = jregions ? (*e)->GetArrayLength(e, jregions) / 2 : 0;

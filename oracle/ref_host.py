@@ -759,8 +759,8 @@ class RunResult:
 def run_vcfeval(engine, template_fa, baseline_vcf, calls_vcf, args, cfg_over=None, side_loader=None):
     """Replays `rtg vcfeval` on in-memory text inputs.  Returns a RunResult with per-record outcomes and the
     regenerated output files the fixtures check.  `side_loader(vcf_text, name, template_len, sample, ploidy, pass_only, max_length,
-    ref_overlap) -> VariantSide` (optional): the arrays handed to the engine come from it (the device loaders under test) instead
-    of from this module's own loader, wherever the run has no region restriction; the arrays of both loaders
+    ref_overlap, region) -> VariantSide` (optional): the arrays handed to the engine come from it (the device loaders under test) instead
+    of from this module's own loader; the arrays of both loaders
     must agree, and everything downstream then runs on the loader's output."""
     p = Params(args)
     seqs = parse_fasta(template_fa)
@@ -811,13 +811,17 @@ def run_vcfeval(engine, template_fa, baseline_vcf, calls_vcf, args, cfg_over=Non
         gp = p.sample_ploidy
         bside = capi.VariantSide.from_variants(bl, gp if bfac == "sample" else 0)
         cside = capi.VariantSide.from_variants(cl, gp if cfac == "sample" else 0)
-        if side_loader is not None and p.region is None:
+        if side_loader is not None:
             fields = ("id", "phased", "status_in", "gt", "allele_off", "allele_start", "allele_end", "allele_null", "allele_nt_off", "nt")
             # (sample -1 = the all-alts factory of `--sample ALT`)
-            got = side_loader(baseline_vcf, name, len(tmpl), bsample, gp, pass_only, p.max_length, p.ref_overlap)
+            reg = None
+            if p.region is not None:   # --region chr:start-end (1-based inclusive): (sequence, 0-based begin, end exclusive)
+                rc, rrng = p.region.split(":")
+                reg = (rc, int(rrng.split("-")[0]) - 1, int(rrng.split("-")[1]))
+            got = side_loader(baseline_vcf, name, len(tmpl), bsample, gp, pass_only, p.max_length, p.ref_overlap, reg)
             assert all(np.array_equal(np.asarray(getattr(got, f)), np.asarray(getattr(bside, f))) for f in fields), "baseline arrays of %s differ" % name
             bside = got
-            got = side_loader(calls_vcf, name, len(tmpl), csample, gp, pass_only, p.max_length, p.ref_overlap)
+            got = side_loader(calls_vcf, name, len(tmpl), csample, gp, pass_only, p.max_length, p.ref_overlap, reg)
             assert all(np.array_equal(np.asarray(getattr(got, f)), np.asarray(getattr(cside, f))) for f in fields), "call arrays of %s differ" % name
             cside = got
             rr.device_loaded = getattr(rr, "device_loaded", 0) + 2

@@ -549,6 +549,8 @@ int vce_vcf_parse(const vce_vcf_in* in, void** result) {
   cfg.refOverlap = in->ref_overlap;
   cfg.evalRegions = in->eval_regions;
   cfg.nEvalRegions = in->eval_regions ? in->n_eval_regions : -1;
+  cfg.regionBeg = in->region_begin;
+  cfg.regionEnd = in->region_end;
   if (in->name) {
     const size_t nl = std::strlen(in->name);
     if (nl == 0 || nl >= sizeof(cfg.name)) return fail(VCE_ERR_BAD_ARGUMENT, "sequence name empty or too long");
@@ -604,6 +606,8 @@ int vcfConfigFrom(const vce_vcf_in* in, vce::VcfConfig& cfg) {
   cfg.refOverlap = in->ref_overlap;
   cfg.evalRegions = in->eval_regions;
   cfg.nEvalRegions = in->eval_regions ? in->n_eval_regions : -1;
+  cfg.regionBeg = in->region_begin;
+  cfg.regionEnd = in->region_end;
   if (in->name) {
     const size_t nl = std::strlen(in->name);
     if (nl == 0 || nl >= sizeof(cfg.name)) return fail(VCE_ERR_BAD_ARGUMENT, "sequence name empty or too long");

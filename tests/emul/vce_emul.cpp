@@ -711,6 +711,8 @@ int emul_vce_vcf_parse(const vce_vcf_in* in, void** result) {
   cfg.refOverlap = in->ref_overlap;
   cfg.evalRegions = in->eval_regions;
   cfg.nEvalRegions = in->eval_regions ? in->n_eval_regions : -1;
+  cfg.regionBeg = in->region_begin;
+  cfg.regionEnd = in->region_end;
   if (in->name) {
     const size_t nl = std::strlen(in->name);
     if (nl == 0 || nl >= sizeof(cfg.name)) return VCE_ERR_BAD_ARGUMENT;
@@ -756,6 +758,8 @@ static int emulVcfConfig(const vce_vcf_in* in, vce::VcfConfig& cfg) {
   cfg.refOverlap = in->ref_overlap;
   cfg.evalRegions = in->eval_regions;
   cfg.nEvalRegions = in->eval_regions ? in->n_eval_regions : -1;
+  cfg.regionBeg = in->region_begin;
+  cfg.regionEnd = in->region_end;
   if (in->name) {
     const size_t nl = std::strlen(in->name);
     if (nl == 0 || nl >= sizeof(cfg.name)) return VCE_ERR_BAD_ARGUMENT;

@@ -31,7 +31,7 @@ def bgzf_side_loader(library):
     import formats_oracle as fo
     cache = {}
 
-    def load(text, name, template_len, sample, ploidy, pass_only, max_length, ref_overlap):
+    def load(text, name, template_len, sample, ploidy, pass_only, max_length, ref_overlap, region=None):
         if id(text) not in cache:
             raw = text.encode()
             lines = text.split("\n")
@@ -52,11 +52,17 @@ def bgzf_side_loader(library):
             # tabix needs the records of a sequence to be contiguous; the fixtures are sorted by sequence
             cache[id(text)] = (data, library.tabix_open(fo.tabix_build(recs, names)) if recs else None)
         data, idx = cache[id(text)]
-        q = idx.query(name) if idx is not None else None
-        if q is None:      # nothing indexed for the sequence: what TabixLineReader would read is empty
+        rng = None
+        if region is not None:      # --region: another sequence reads nothing; this one is queried and filtered by position
+            rng = (region[1], region[2]) if region[0] == name else (0, 0)
+        q = None
+        if idx is not None and rng != (0, 0):
+            q = idx.query(name) if rng is None else idx.query(name, rng[0], rng[1])
+        if q is None:      # nothing indexed for the sequence / region: what TabixLineReader would read is empty
             side, _ = library.vcf_parse(b"", name, template_len, sample, ploidy, pass_only, max_length, ref_overlap)
             return side
-        side, _ = library.vcf_parse_bgzf(data, q[0], q[1], name, template_len, sample, ploidy, pass_only, max_length, True, ref_overlap)
+        side, _ = library.vcf_parse_bgzf(data, q[0], q[1], name, template_len, sample, ploidy, pass_only, max_length, True, ref_overlap,
+                                         None, rng)
         return side
     return load
 

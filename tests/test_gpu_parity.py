@@ -447,12 +447,12 @@ def test_cuda_sdf_template(engine, oracle):
 
 def test_cuda_golden_fixtures_from_vcf_gz(engine, fixtures):
     """The reference's vcfeval fixtures end to end on the device: .vcf.gz + .tbi -> tabix query -> BGZF inflate -> VCF parse (+
-    --ref-overlap trimming) -> matching -> the output files the reference's tests expect (the sides of 27 scenarios go through the
-    loader chain, `--sample ALT` ones included; the arrays are also compared with the restated host loader's)."""
+    --ref-overlap trimming) -> matching -> the output files the reference's tests expect (every side of all 29 scenarios goes through the
+    loader chain: sample columns, `--sample ALT`, a `--region` window; the arrays are also compared with the restated host loader's)."""
     from golden_check import bgzf_side_loader
     loader = bgzf_side_loader(engine.lib)
     check_scenario.device_loaded = 0
     for name in SCENARIOS:
         assert check_scenario(engine, fixtures[name], side_loader=loader), name
-    assert check_scenario.device_loaded >= 84
+    assert check_scenario.device_loaded >= 96
 

@@ -139,6 +139,10 @@ def check_fuzz(engine, seeds, bad=False):
                                           what="fuzz seed %d sample %d ploidy %d pass_only %s max_length %d --ref-overlap, %d regions" % (
                                               seed, sample, ploidy, pass_only, max_length, len(regions)))
                 assert r2 == r
+                if r == "ok":     # --region: a window of the sequence (a format error outside the window is none of its business)
+                    lo = int(rng.integers(0, tl))
+                    assert vcf_check.check_text(engine, text, "chr1", tl, sample, ploidy, pass_only, max_length, ref_overlap=bool(seed & 1),
+                                                region=(lo, lo + int(rng.integers(1, 600))), what="fuzz seed %d --region" % seed) == "ok"
     return outcomes
 
 

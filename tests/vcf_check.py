@@ -7,10 +7,13 @@ import ref_host
 from rtg_tools_b200 import capi
 
 
-def expected_side(text, name, template_len, sample, ploidy=2, pass_only=True, max_length=1000, ref_overlap=False, eval_regions=None):
+def expected_side(text, name, template_len, sample, ploidy=2, pass_only=True, max_length=1000, ref_overlap=False, eval_regions=None,
+                  region=None):
     """(VariantSide, skipped count) or the exception class the loader ends with."""
     _, recs = ref_host.parse_vcf(text)
     recs = [r for r in recs if r.chrom == name]
+    if region is not None:      # --region: the records TabixLineReader hands on (ref_host._restrict)
+        recs = [r for r in recs if r.start < region[1] and max(r.end, r.start + 1) > region[0]]
 
     def factory(rec, vid):
         if sample < 0:     # --sample ALT: VariantFactory.AllAlts
@@ -61,17 +64,17 @@ def assert_same_side(got, want, what):
 
 
 def check_text(engine, text, name, template_len, sample, ploidy=2, pass_only=True, max_length=1000, what="", ref_overlap=False,
-               eval_regions=None):
+               eval_regions=None, region=None):
     """Compares one (text, sequence, sample); returns 'ok' or 'format-error' (both sides agree the text is invalid)."""
     try:
-        want, skipped = expected_side(text, name, template_len, sample, ploidy, pass_only, max_length, ref_overlap, eval_regions)
+        want, skipped = expected_side(text, name, template_len, sample, ploidy, pass_only, max_length, ref_overlap, eval_regions, region)
     except (ref_host.VcfFormatError, ValueError, IndexError):
         try:
-            engine.vcf_parse(text.encode(), name, template_len, sample, ploidy, pass_only, max_length, ref_overlap, eval_regions)
+            engine.vcf_parse(text.encode(), name, template_len, sample, ploidy, pass_only, max_length, ref_overlap, eval_regions, region)
         except ValueError:
             return "format-error"
         raise AssertionError("%s: the reference loader rejects this text, the engine accepted it" % what)
-    got, stats = engine.vcf_parse(text.encode(), name, template_len, sample, ploidy, pass_only, max_length, ref_overlap, eval_regions)
+    got, stats = engine.vcf_parse(text.encode(), name, template_len, sample, ploidy, pass_only, max_length, ref_overlap, eval_regions, region)
     assert_same_side(got, want, what)
     assert stats["skipped"] == skipped, "%s: skipped %d vs %d" % (what, stats["skipped"], skipped)
     if "roc_mask" in stats and want.roc_expect is not None:
