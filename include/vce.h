@@ -274,7 +274,9 @@ int vce_roc_timed(const vce_roc_in* in, vce_roc_out* out, double* h2d_ms, double
  * VcfUtils.getAlleleStrings / hasRedundantFirstNucleotide (:785-828), VariantType.getType (:107-190) and Allele.getAlleles
  * (Allele.java:145-192) and, with ref_overlap, Variant.trimAlleles (Variant.java:93-190: REF nulled, ALTs stripped of what they
  * share with REF, the side decided by the overlapping neighbours; clusters of overlapping variants one thread each).
- * With eval_regions, the OUTSIDE_EVAL status bit of VcfRecordTabixCallable.java:125-127 (MergedIntervals.overlapped :172-179).
+ * With eval_regions, the OUTSIDE_EVAL status bit of VcfRecordTabixCallable.java:125-127 (MergedIntervals.overlapped :172-179);
+ * with sample -1 the all-alts factory of `--sample ALT` (VariantFactory.java:195-239); with a region, only the records
+ * TabixLineReader hands on for it.  vce_vcf_roc_fields adds the ROC inputs of the same variants.
  * A record the reference would throw VcfFormatException for ends the call with VCE_ERR_BAD_ARGUMENT (vce_last_error names
  * the line).  The result owns host copies of the arrays until vce_vcf_free.
  */
@@ -291,7 +293,8 @@ typedef struct vce_vcf_in {
   int32_t     ref_overlap;    /* --ref-overlap: Variant.trimAlleles (Variant.java:93-190) on the loaded variants */
   int32_t     n_eval_regions; /* --evaluation-regions of this sequence; ignored when eval_regions is NULL */
   int32_t     region_begin;   /* --region within the sequence: only records overlapping [region_begin, region_end) belong to the */
-  int32_t     region_end;     /* stream (0-based, end exclusive; what TabixLineReader hands on); region_end < 0 = whole sequence */
+  int32_t     region_end;     /* stream (0-based, end exclusive; what TabixLineReader hands on); region_end <= region_begin (a
+                                 zeroed struct) = the whole sequence */
   const int32_t* eval_regions;/* [n_eval_regions * 2] merged intervals [start, end), ascending (ReferenceRegions / MergedIntervals):
                                  variants whose locus overlaps none get VCE_STATUS_OUTSIDE_EVAL in status_in
                                  (VcfRecordTabixCallable.java:125-127); NULL = no regions given */

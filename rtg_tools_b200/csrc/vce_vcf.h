@@ -45,7 +45,7 @@ struct VcfConfig {
   int32_t nameLen;       // CHROM to accept (a tabix query returns one sequence's records); 0 = accept every record
   int32_t refOverlap;    // --ref-overlap: Variant.trimAlleles (Variant.java:93-190) on the loaded variants
   int32_t nEvalRegions;  // --evaluation-regions of this sequence: merged intervals, ascending; -1 = none
-  int32_t regionBeg, regionEnd;   // --region within the sequence, 0-based, end exclusive; regionEnd < 0 = the whole sequence
+  int32_t regionBeg, regionEnd;   // --region within the sequence, 0-based, end exclusive; regionEnd <= regionBeg = the whole sequence
   const int32_t* evalRegions;   // HOST pointer to [start, end) pairs (vcfDrive makes the device copy: VcfArrays::evalRegions)
   char name[232];
 };
@@ -204,7 +204,7 @@ VCE_HDN void vcfParseLine(const uint8_t* t, int a, int b, const VcfConfig& cfg, 
   L.end = L.start + refLen;
   // --region: TabixLineReader hands on only the records that overlap it (an empty REF still covers its position); the others
   // are not part of the stream (they take no ordinal)
-  if (cfg.regionEnd >= 0) {
+  if (cfg.regionEnd > cfg.regionBeg) {
     const int32_t e1 = L.end > L.start + 1 ? L.end : L.start + 1;
     if (!(L.start < cfg.regionEnd && e1 > cfg.regionBeg)) { L.kind = VK_NOT_STREAM; return; }
   }

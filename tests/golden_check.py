@@ -54,9 +54,9 @@ def bgzf_side_loader(library):
         data, idx = cache[id(text)]
         rng = None
         if region is not None:      # --region: another sequence reads nothing; this one is queried and filtered by position
-            rng = (region[1], region[2]) if region[0] == name else (0, 0)
+            rng = (region[1], region[2]) if region[0] == name else "other sequence"
         q = None
-        if idx is not None and rng != (0, 0):
+        if idx is not None and rng != "other sequence":
             q = idx.query(name) if rng is None else idx.query(name, rng[0], rng[1])
         if q is None:      # nothing indexed for the sequence / region: what TabixLineReader would read is empty
             side, _ = library.vcf_parse(b"", name, template_len, sample, ploidy, pass_only, max_length, ref_overlap)
