@@ -298,6 +298,8 @@ typedef struct vce_vcf_in {
   const int32_t* eval_regions;/* [n_eval_regions * 2] merged intervals [start, end), ascending (ReferenceRegions / MergedIntervals):
                                  variants whose locus overlaps none get VCE_STATUS_OUTSIDE_EVAL in status_in
                                  (VcfRecordTabixCallable.java:125-127); NULL = no regions given */
+  const char* score_field;    /* --vcf-score-field for vce_vcf_roc_fields: NULL or "QUAL" = the QUAL column, else a FORMAT key of the
+                                 sample (vcfeval's default is "GQ"; RocScoreField.java:50-80,120-140) */
 } vce_vcf_in;
 typedef struct vce_vcf_stats {
   int64_t lines, records, kept, skipped;   /* text lines, records of the sequence, variants, counted skips (:103-118) */

@@ -62,7 +62,7 @@ class CVcfIn(C.Structure):
         ("text", C.c_char_p), ("text_len", C.c_int64), ("name", C.c_char_p), ("template_len", C.c_int32),
         ("sample", C.c_int32), ("ploidy", C.c_int32), ("pass_only", C.c_int32), ("max_length", C.c_int32),
         ("ref_overlap", C.c_int32), ("n_eval_regions", C.c_int32), ("region_begin", C.c_int32), ("region_end", C.c_int32),
-        ("eval_regions", C.POINTER(C.c_int32)),
+        ("eval_regions", C.POINTER(C.c_int32)), ("score_field", C.c_char_p),
     ]
 
 
@@ -445,13 +445,14 @@ class Library:
             return data, C.cast(data.ctypes.data, C.c_char_p), int(data.nbytes)
         return data, C.cast(C.c_char_p(data), C.c_char_p), len(data)
 
-    def _vcf_in(self, text, name, template_len, sample, ploidy, pass_only, max_length, ref_overlap=False, eval_regions=None, region=None):
+    def _vcf_in(self, text, name, template_len, sample, ploidy, pass_only, max_length, ref_overlap=False, eval_regions=None, region=None, score_field=None):
         cin = CVcfIn()
         keep, cin.text, cin.text_len = self._bytes_arg(text)
         cin.name = name.encode() if isinstance(name, str) else name
         cin.template_len = int(template_len)
         cin.sample, cin.ploidy, cin.pass_only, cin.max_length = int(sample), int(ploidy), int(bool(pass_only)), int(max_length)
         cin.ref_overlap = int(bool(ref_overlap))
+        cin.score_field = score_field.encode() if isinstance(score_field, str) else score_field
         cin.region_begin, cin.region_end = (0, -1) if region is None else (int(region[0]), int(region[1]))
         if eval_regions is not None:   # merged, ascending [start, end) pairs of this sequence
             reg = np.ascontiguousarray(np.asarray(eval_regions, np.int32).reshape(-1, 2))
@@ -500,7 +501,7 @@ class Library:
         return side, stats
 
     def vcf_parse(self, text: bytes, name=None, template_len=-1, sample=0, ploidy=2, pass_only=True, max_length=1000, ref_overlap=False,
-                  eval_regions=None, region=None):
+                  eval_regions=None, region=None, score_field=None):
         """vce_vcf_parse: the records of sequence `name` in VCF `text` as a VariantSide (copies) plus the loader's counters
         {"lines", "records", "kept", "skipped", "h2d_ms", "kernel_ms", "d2h_ms", "launches"}.  Raises ValueError on a record
         the reference would throw VcfFormatException for."""
@@ -508,7 +509,7 @@ class Library:
         f_parse = getattr(self.lib, pre + "vcf_parse")
         f_parse.restype = C.c_int
         f_parse.argtypes = [C.POINTER(CVcfIn), C.POINTER(C.c_void_p)]
-        cin, keep = self._vcf_in(text, name, template_len, sample, ploidy, pass_only, max_length, ref_overlap, eval_regions, region)
+        cin, keep = self._vcf_in(text, name, template_len, sample, ploidy, pass_only, max_length, ref_overlap, eval_regions, region, score_field)
         handle = C.c_void_p()
         rc = f_parse(C.byref(cin), C.byref(handle))
         del keep
@@ -546,13 +547,13 @@ class Library:
         return out[:int(got.value)].tobytes(), stats
 
     def vcf_parse_bgzf(self, data, voffset_begin=0, voffset_end=-1, name=None, template_len=-1, sample=0, ploidy=2, pass_only=True,
-                       max_length=1000, check_crc=True, ref_overlap=False, eval_regions=None, region=None):
+                       max_length=1000, check_crc=True, ref_overlap=False, eval_regions=None, region=None, score_field=None):
         """vce_vcf_parse_bgzf: vcf_parse on the bytes of a .vcf.gz, between two virtual offsets (e.g. from tabix_open(...).query)."""
         pre = "vce_" if self.prefix == "vce_" else self.prefix + "vce_"
         f = getattr(self.lib, pre + "vcf_parse_bgzf")
         f.restype = C.c_int
         f.argtypes = [C.POINTER(CVcfIn), C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(CBgzfStats)]
-        cin, keep = self._vcf_in(data, name, template_len, sample, ploidy, pass_only, max_length, ref_overlap, eval_regions, region)
+        cin, keep = self._vcf_in(data, name, template_len, sample, ploidy, pass_only, max_length, ref_overlap, eval_regions, region, score_field)
         handle, st = C.c_void_p(), CBgzfStats()
         rc = f(C.byref(cin), int(voffset_begin), int(voffset_end), int(bool(check_crc)), C.byref(handle), C.byref(st))
         del keep

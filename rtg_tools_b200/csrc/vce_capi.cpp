@@ -551,6 +551,12 @@ int vce_vcf_parse(const vce_vcf_in* in, void** result) {
   cfg.nEvalRegions = in->eval_regions ? in->n_eval_regions : -1;
   cfg.regionBeg = in->region_begin;
   cfg.regionEnd = in->region_end;
+  if (in->score_field && std::strcmp(in->score_field, "QUAL") != 0) {
+    const size_t sl = std::strlen(in->score_field);
+    if (sl == 0 || sl >= sizeof(cfg.scoreField)) return fail(VCE_ERR_BAD_ARGUMENT, "score field name too long");
+    std::memcpy(cfg.scoreField, in->score_field, sl);
+    cfg.scoreLen = (int32_t) sl;
+  }
   if (in->name) {
     const size_t nl = std::strlen(in->name);
     if (nl == 0 || nl >= sizeof(cfg.name)) return fail(VCE_ERR_BAD_ARGUMENT, "sequence name empty or too long");
@@ -608,6 +614,12 @@ int vcfConfigFrom(const vce_vcf_in* in, vce::VcfConfig& cfg) {
   cfg.nEvalRegions = in->eval_regions ? in->n_eval_regions : -1;
   cfg.regionBeg = in->region_begin;
   cfg.regionEnd = in->region_end;
+  if (in->score_field && std::strcmp(in->score_field, "QUAL") != 0) {
+    const size_t sl = std::strlen(in->score_field);
+    if (sl == 0 || sl >= sizeof(cfg.scoreField)) return fail(VCE_ERR_BAD_ARGUMENT, "score field name too long");
+    std::memcpy(cfg.scoreField, in->score_field, sl);
+    cfg.scoreLen = (int32_t) sl;
+  }
   if (in->name) {
     const size_t nl = std::strlen(in->name);
     if (nl == 0 || nl >= sizeof(cfg.name)) return fail(VCE_ERR_BAD_ARGUMENT, "sequence name empty or too long");

@@ -45,6 +45,8 @@ struct VcfConfig {
   int32_t nameLen;       // CHROM to accept (a tabix query returns one sequence's records); 0 = accept every record
   int32_t refOverlap;    // --ref-overlap: Variant.trimAlleles (Variant.java:93-190) on the loaded variants
   int32_t nEvalRegions;  // --evaluation-regions of this sequence: merged intervals, ascending; -1 = none
+  int32_t scoreLen;      // --vcf-score-field: 0 = QUAL, else the length of scoreField, a FORMAT key of the sample (GQ by default in vcfeval)
+  char scoreField[20];
   int32_t regionBeg, regionEnd;   // --region within the sequence, 0-based, end exclusive; regionEnd <= regionBeg = the whole sequence
   const int32_t* evalRegions;   // HOST pointer to [start, end) pairs (vcfDrive makes the device copy: VcfArrays::evalRegions)
   char name[232];
@@ -489,14 +491,18 @@ VCE_HD double vcfParseDecimal(const uint8_t* s, int n, bool* ok) {
 // Filter bits in RocFilter's declaration order (RocFilter.java:48-137): ALL HOM HET SNP NON_SNP MNP INDEL XRX NON_XRX; bit 31:
 // the QUAL text needs the caller's own parser (qual is NaN then).  `line` is the record's text, L what vcfParseLine kept.
 constexpr uint32_t kRocScoreUnparsed = 0x80000000u;
-VCE_HDN void vcfRocFields(const uint8_t* line, int lineLen, const VcfLine& L, int ploidy, uint32_t* maskOut, double* qualOut) {
-  // QUAL = field 5, INFO = field 7
-  int fo[2] = {0, 0}, fl[2] = {-1, -1};
+VCE_HDN void vcfRocFields(const uint8_t* line, int lineLen, const VcfLine& L, const VcfConfig& cfg, uint32_t* maskOut, double* qualOut) {
+  const int ploidy = cfg.ploidy;
+  // QUAL = field 5, INFO = field 7, FORMAT = field 8, the sample = field 9 + cfg.sample
+  int fo[4] = {0, 0, 0, 0}, fl[4] = {-1, -1, -1, -1};
   int field = 0, fs = 0;
-  for (int i = 0; i <= lineLen && field <= 7; ++i) {
+  const int last = cfg.scoreLen > 0 ? 9 + cfg.sample : 7;
+  for (int i = 0; i <= lineLen && field <= last; ++i) {
     if (i == lineLen || line[i] == '\t') {
       if (field == 5) { fo[0] = fs; fl[0] = i - fs; }
       if (field == 7) { fo[1] = fs; fl[1] = i - fs; }
+      if (field == 8) { fo[2] = fs; fl[2] = i - fs; }
+      if (field == 9 + cfg.sample) { fo[3] = fs; fl[3] = i - fs; }
       ++field;
       fs = i + 1;
     }
@@ -561,10 +567,29 @@ VCE_HDN void vcfRocFields(const uint8_t* line, int lineLen, const VcfLine& L, in
 #else
   double qual = std::numeric_limits<double>::quiet_NaN();
 #endif
-  if (fl[0] > 0 && !(fl[0] == 1 && line[fo[0]] == '.')) {
-    bool ok = false;
-    const double v = vcfParseDecimal(line + fo[0], fl[0], &ok);
-    if (ok) qual = v; else mask |= kRocScoreUnparsed;
+  if (cfg.scoreLen == 0) {
+    if (fl[0] > 0 && !(fl[0] == 1 && line[fo[0]] == '.')) {
+      bool ok = false;
+      const double v = vcfParseDecimal(line + fo[0], fl[0], &ok);
+      if (ok) qual = v; else mask |= kRocScoreUnparsed;
+    }
+  } else if (fl[2] > 0 && fl[3] >= 0) {
+    // RocScoreField.FORMAT :120-140 over VcfUtils.getDoubleFormatFieldFromRecord :550-566: the sample's value of the key, NaN when
+    // the key or the value is missing, values within 1e-8 of zero become 0
+    const uint8_t* fmt = line + fo[2];
+    const int nk = vcfCount(fmt, fl[2], ':');
+    int key = -1;
+    for (int k = 0; k < nk && key < 0; ++k) {
+      int o = 0, l = 0;
+      vcfNth(fmt, fl[2], ':', k, &o, &l);
+      if (vcfEq(fmt + o, l, cfg.scoreField, cfg.scoreLen)) key = k;
+    }
+    int o = 0, l = 0;
+    if (key >= 0 && vcfNth(line + fo[3], fl[3], ':', key, &o, &l) && !(l == 1 && line[fo[3] + o] == '.') && l > 0) {
+      bool ok = false;
+      const double v = vcfParseDecimal(line + fo[3] + o, l, &ok);
+      if (ok) qual = (v >= -0.00000001 && v <= 0.00000001) ? 0.0 : v; else mask |= kRocScoreUnparsed;
+    }
   }
   *maskOut = mask;
   *qualOut = qual;
@@ -946,7 +971,7 @@ void vcfFillPasses(Ops& ops, VcfArrays& A) {
     int e = a.lineStart[l + 1];
     if (e > a.lineStart[l] && a.text[e - 1] == '\n') --e;
     if (e > a.lineStart[l] && a.text[e - 1] == '\r') --e;
-    if (a.cfg.sample >= 0) vcfRocFields(a.text + a.lineStart[l], e - a.lineStart[l], L, ploidy, a.rocMask + v, a.qual + v);
+    if (a.cfg.sample >= 0) vcfRocFields(a.text + a.lineStart[l], e - a.lineStart[l], L, *a.dCfg, a.rocMask + v, a.qual + v);
     else { a.rocMask[v] = 0; a.qual[v] = 0.0; }   // all-alts mode has no sample to classify: the ROC inputs are the caller's
   });
   ops.parFor(n + 1, VCE_VCF_LAMBDA(int v) { a.alleleOffOut[v] = a.alleleOff[v]; });

@@ -104,7 +104,8 @@ def fuzz_vcf(rng, n_records=250, template_len=3000, bad=False):
             g = rng.choice(gts)
             if na == 0:
                 g = rng.choice(["0/0", ".", "0"])
-            vals = {"GT": g, "GQ": str(int(rng.integers(1, 99))), "FT": rng.choice(["PASS", ".", "lowq", "PASS;lowq"])}
+            vals = {"GT": g, "GQ": rng.choice([str(int(rng.integers(1, 99))), ".", "0", "12.5", "1e-9", "-0.000000001", "3e1", "0.00000002"]),
+                    "FT": rng.choice(["PASS", ".", "lowq", "PASS;lowq"])}
             keys = fmt.split(":")
             if rng.random() < 0.1:
                 keys = keys[:1]                    # trailing sub-fields dropped
@@ -139,6 +140,9 @@ def check_fuzz(engine, seeds, bad=False):
                                           what="fuzz seed %d sample %d ploidy %d pass_only %s max_length %d --ref-overlap, %d regions" % (
                                               seed, sample, ploidy, pass_only, max_length, len(regions)))
                 assert r2 == r
+                if r == "ok" and sample >= 0:   # --vcf-score-field GQ (vcfeval's default): the sample's FORMAT value as the score
+                    assert vcf_check.check_text(engine, text, "chr1", tl, sample, ploidy, pass_only, max_length, score_field="GQ",
+                                                what="fuzz seed %d score field GQ" % seed) == "ok"
                 if r == "ok":     # --region: a window of the sequence (a format error outside the window is none of its business)
                     lo = int(rng.integers(0, tl))
                     assert vcf_check.check_text(engine, text, "chr1", tl, sample, ploidy, pass_only, max_length, ref_overlap=bool(seed & 1),

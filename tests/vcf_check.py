@@ -8,7 +8,7 @@ from rtg_tools_b200 import capi
 
 
 def expected_side(text, name, template_len, sample, ploidy=2, pass_only=True, max_length=1000, ref_overlap=False, eval_regions=None,
-                  region=None):
+                  region=None, score_field=None):
     """(VariantSide, skipped count) or the exception class the loader ends with."""
     _, recs = ref_host.parse_vcf(text)
     recs = [r for r in recs if r.chrom == name]
@@ -21,14 +21,14 @@ def expected_side(text, name, template_len, sample, ploidy=2, pass_only=True, ma
         return ref_host.sample_variant(rec, vid, sample, ploidy, pass_only)
     out, skipped = ref_host.load_side(recs, template_len, factory, max_length, ref_overlap, eval_regions)
     side = capi.VariantSide.from_variants(out, ploidy if sample >= 0 else 0)
-    side.roc_expect = expected_roc_fields(out, sample) if sample >= 0 else None
+    side.roc_expect = expected_roc_fields(out, sample, score_field) if sample >= 0 else None
     return side, skipped
 
 
 ROC_BITS = {"ALL": 1, "HOM": 2, "HET": 4, "SNP": 8, "NON_SNP": 16, "MNP": 32, "INDEL": 64, "XRX": 128, "NON_XRX": 256}
 
 
-def expected_roc_fields(variants, sample):
+def expected_roc_fields(variants, sample, score_field=None):
     """What RocContainer.addRocLine (RocContainer.java:225-248) derives from each kept variant's record: the RocFilters that
     accept it (RocFilter.java:48-137, on the RAW sample GT as VcfUtils.getValidGt returns it) and the QUAL score
     (RocScoreField.java:50-80)."""
@@ -50,7 +50,12 @@ def expected_roc_fields(variants, sample):
             m |= ROC_BITS["INDEL"]
         m |= ROC_BITS["XRX"] if rec.has_info("XRX") else ROC_BITS["NON_XRX"]
         masks.append(m)
-        quals.append(float("nan") if rec.qual == "." else float(rec.qual))
+        if score_field in (None, "QUAL"):
+            quals.append(float("nan") if rec.qual == "." else float(rec.qual))
+        else:      # RocScoreField.FORMAT :120-140 (MathUtils.approxEquals(val, 0, 1e-8) is inclusive)
+            fv = rec.sample_field(sample, score_field)
+            x = float("nan") if fv is None or fv == "." else float(fv)
+            quals.append(0.0 if -1e-8 <= x <= 1e-8 else x)
     return np.array(masks, np.uint32), np.array(quals, np.float64)
 
 
@@ -64,17 +69,17 @@ def assert_same_side(got, want, what):
 
 
 def check_text(engine, text, name, template_len, sample, ploidy=2, pass_only=True, max_length=1000, what="", ref_overlap=False,
-               eval_regions=None, region=None):
+               eval_regions=None, region=None, score_field=None):
     """Compares one (text, sequence, sample); returns 'ok' or 'format-error' (both sides agree the text is invalid)."""
     try:
-        want, skipped = expected_side(text, name, template_len, sample, ploidy, pass_only, max_length, ref_overlap, eval_regions, region)
+        want, skipped = expected_side(text, name, template_len, sample, ploidy, pass_only, max_length, ref_overlap, eval_regions, region, score_field)
     except (ref_host.VcfFormatError, ValueError, IndexError):
         try:
-            engine.vcf_parse(text.encode(), name, template_len, sample, ploidy, pass_only, max_length, ref_overlap, eval_regions, region)
+            engine.vcf_parse(text.encode(), name, template_len, sample, ploidy, pass_only, max_length, ref_overlap, eval_regions, region, score_field)
         except ValueError:
             return "format-error"
         raise AssertionError("%s: the reference loader rejects this text, the engine accepted it" % what)
-    got, stats = engine.vcf_parse(text.encode(), name, template_len, sample, ploidy, pass_only, max_length, ref_overlap, eval_regions, region)
+    got, stats = engine.vcf_parse(text.encode(), name, template_len, sample, ploidy, pass_only, max_length, ref_overlap, eval_regions, region, score_field)
     assert_same_side(got, want, what)
     assert stats["skipped"] == skipped, "%s: skipped %d vs %d" % (what, stats["skipped"], skipped)
     if "roc_mask" in stats and want.roc_expect is not None:
