@@ -73,12 +73,14 @@ final class NativeVce {
    * bytes of the .vcf.gz between two virtual offsets: BGZF members inflated and records parsed on the device.
    * @param refOverlap --ref-overlap: Variant.trimAlleles (Variant.java:93-190) applied on the device
    * @param evalRegions null, or the sequence's merged --evaluation-regions as [start, end) pairs (MergedIntervals): variants outside get STATUS_OUTSIDE_EVAL
+   * @param scoreField --vcf-score-field: null or "QUAL", else a FORMAT key of the sample ("GQ"); out.mScore / out.mRocMask receive the ROC inputs
    * @param out receives the arrays of the side (as SideArrays.flatten would have made them from the loaded variants)
    * @param counters [4] out: text lines, records of the sequence, variants kept, counted skips
    * @return 0, or a VCE_ERR_* code (2 = the reference would have thrown VcfFormatException / a corrupt BGZF member)
    */
   static native int loadVcfGz(byte[] file, long voffsetBegin, long voffsetEnd, String sequenceName, int templateLength, int sample,
-                              int ploidy, boolean passOnly, int maxLength, boolean refOverlap, int[] evalRegions, SideArrays out, long[] counters);
+                              int ploidy, boolean passOnly, int maxLength, boolean refOverlap, int[] evalRegions, String scoreField, SideArrays out,
+                              long[] counters);
 
   /**
    * vce_template_register_sdf: one sequence of an SDF seqdata file (bit planes, FileBitwiseInputStream.java:151-169) becomes the

@@ -21,6 +21,9 @@ final class SideArrays {
   byte[] mAlleleNull;      // 1 = Java null Allele ("play nothing on this haplotype")
   int[] mAlleleNtOff;      // [slots + 1]
   byte[] mNt;              // concatenated Allele.nt() (0..4, DnaUtils encoding; 5 = explicit unknown)
+  // filled by NativeVce.loadVcfGz only: what RocContainer.addRocLine derives from each variant's record (vce_vcf_roc_fields)
+  double[] mScore;         // RocSortValueExtractor.getSortValue: QUAL or the sample's FORMAT field; NaN = missing
+  int[] mRocMask;          // bit per RocFilter in declaration order (ALL HOM HET SNP NON_SNP MNP INDEL XRX NON_XRX); bit 31: parse mScore in Java
 
   /** Flattens {@code variants}; {@code gtPloidy} is the width of {@code GtIdVariant.alleleIds()} (0 for plain Variants). */
   static SideArrays flatten(List<? extends Variant> variants, int gtPloidy) {

@@ -290,8 +290,8 @@ static void set_byte_field_array(JNIEnv* e, jobject o, const char* name, const v
 }
 
 JNIEXPORT jint JNICALL Java_com_rtg_vcf_eval_NativeVce_loadVcfGz(JNIEnv* e, jclass c, jbyteArray jfile, jlong vbeg, jlong vend, jstring jname,
-    jint templateLength, jint sample, jint ploidy, jboolean passOnly, jint maxLength, jboolean refOverlap, jintArray jregions, jobject jout,
-    jlongArray jcounters) {
+    jint templateLength, jint sample, jint ploidy, jboolean passOnly, jint maxLength, jboolean refOverlap, jintArray jregions, jstring jscore,
+    jobject jout, jlongArray jcounters) {
   (void) c;
   const char* name = (*e)->GetStringUTFChars(e, jname, NULL);
   vce_vcf_in in;
@@ -308,6 +308,8 @@ JNIEXPORT jint JNICALL Java_com_rtg_vcf_eval_NativeVce_loadVcfGz(JNIEnv* e, jcla
   in.region_end = -1;   /* the whole sequence (a finer --region: set both from the RegionRestriction) */
   void* result = NULL;
   /* the file bytes are pinned for the call only: the engine uploads them and keeps nothing */
+  const char* score = jscore ? (*e)->GetStringUTFChars(e, jscore, NULL) : NULL;
+  in.score_field = score;
   const jsize nreg = jregions ? (*e)->GetArrayLength(e, jregions) / 2 : 0;
   void* p = (*e)->GetPrimitiveArrayCritical(e, jfile, NULL);
   void* reg = jregions ? (*e)->GetPrimitiveArrayCritical(e, jregions, NULL) : NULL;
@@ -318,6 +320,7 @@ JNIEXPORT jint JNICALL Java_com_rtg_vcf_eval_NativeVce_loadVcfGz(JNIEnv* e, jcla
   if (reg) (*e)->ReleasePrimitiveArrayCritical(e, jregions, reg, JNI_ABORT);
   (*e)->ReleasePrimitiveArrayCritical(e, jfile, p, JNI_ABORT);
   (*e)->ReleaseStringUTFChars(e, jname, name);
+  if (score) (*e)->ReleaseStringUTFChars(e, jscore, score);
   if (rc != 0) return rc;
   vce_variants v;
   vce_vcf_stats st;
@@ -336,6 +339,14 @@ JNIEXPORT jint JNICALL Java_com_rtg_vcf_eval_NativeVce_loadVcfGz(JNIEnv* e, jcla
     set_byte_field_array(e, jout, "mAlleleNull", v.allele_null, slots);
     set_int_field_array(e, jout, "mAlleleNtOff", v.allele_nt_off, slots + 1);
     set_byte_field_array(e, jout, "mNt", v.nt, slots > 0 ? (jsize) v.allele_nt_off[slots] : 0);
+    const uint32_t* mask = NULL;
+    const double* qual = NULL;
+    if (vce_vcf_roc_fields(result, &mask, &qual) == 0) {
+      set_int_field_array(e, jout, "mRocMask", (const int32_t*) mask, n);
+      jdoubleArray sc = (*e)->NewDoubleArray(e, n);
+      if (n > 0) (*e)->SetDoubleArrayRegion(e, sc, 0, n, (const jdouble*) qual);
+      (*e)->SetObjectField(e, jout, fid(e, jout, "mScore", "[D"), sc);
+    }
     const jlong cnt[4] = {(jlong) st.lines, (jlong) st.records, (jlong) st.kept, (jlong) st.skipped};
     (*e)->SetLongArrayRegion(e, jcounters, 0, 4, cnt);
   }

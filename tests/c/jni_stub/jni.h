@@ -50,6 +50,8 @@ struct JNINativeInterface_ {
   jintArray (*NewIntArray)(JNIEnv*, jsize);
   jlongArray (*NewLongArray)(JNIEnv*, jsize);
   jbyteArray (*NewByteArray)(JNIEnv*, jsize);
+  jdoubleArray (*NewDoubleArray)(JNIEnv*, jsize);
+  void (*SetDoubleArrayRegion)(JNIEnv*, jdoubleArray, jsize, jsize, const jdouble*);
   jint* (*GetIntArrayElements)(JNIEnv*, jintArray, jboolean*);
   void (*ReleaseIntArrayElements)(JNIEnv*, jintArray, jint*, jint);
   void (*GetIntArrayRegion)(JNIEnv*, jintArray, jsize, jsize, jint*);
