@@ -661,33 +661,53 @@ inline int tabixQuery(const TabixIndex& t, const std::string& name, int32_t beg0
 // Codes: 0 = N, 1..4 = A C G T (DNA.ordinal()); codes 5..7 cannot be written by the formatter and are kept as they are
 // in the byte array (they count as "other" in the mask, like N).
 VCE_HD uint64_t sdfPlane(const uint8_t* file, int64_t longIdx) {   // big-endian 64-bit word (DataOutputStream.writeLong)
+#if defined(__CUDA_ARCH__)
+  // (the planes sit at multiples of 8 bytes of a 256-byte aligned buffer)
+  const uint2 w = *reinterpret_cast<const uint2*>(file + longIdx * 8);
+  return ((uint64_t) __byte_perm(w.x, 0, 0x0123) << 32) | (uint64_t) __byte_perm(w.y, 0, 0x0123);
+#else
   const uint8_t* p = file + longIdx * 8;
   uint64_t v = 0;
   for (int i = 0; i < 8; ++i) v = (v << 8) | p[i];
   return v;
+#endif
 }
+VCE_HD uint32_t sdfSpread16(uint32_t x) {   // bit i -> bit 2 i
+  x = (x | (x << 8)) & 0x00ff00ffu;
+  x = (x | (x << 4)) & 0x0f0f0f0fu;
+  x = (x | (x << 2)) & 0x33333333u;
+  x = (x | (x << 1)) & 0x55555555u;
+  return x;
+}
+// The granule's 16 residues as three 16-bit masks (bit q = residue q), straight out of the planes: the packed word and the N flag
+// are bit logic on the masks -- with x = 2 * plane1 + plane2, (code - 1) & 3 = (x - 1) & 3 whatever plane0 says, i.e. low bit =
+// ~plane2, high bit = ~(plane1 ^ plane2) -- and the byte-per-base array takes the masks four residues at a time.
 VCE_HD void sdfGranule(const uint8_t* file, int64_t first, int32_t len, int32_t g, uint32_t* packed, uint8_t* otherFlag, uint8_t* bases) {
-  uint32_t v = 0;
-  bool other = false;
   const int32_t p0 = g * 16;
-  int64_t group = -1;
-  uint64_t b0 = 0, b1 = 0, b2 = 0;
-  for (int q = 0; q < 16 && p0 + q < len; ++q) {
-    const int64_t r = first + p0 + q;
-    if ((r >> 6) != group) {
-      group = r >> 6;
-      b0 = sdfPlane(file, group * 3);
-      b1 = sdfPlane(file, group * 3 + 1);
-      b2 = sdfPlane(file, group * 3 + 2);
-    }
-    const int bit = (int) (r & 63);
-    const uint32_t code = (uint32_t) (((b0 >> bit) & 1u) << 2 | ((b1 >> bit) & 1u) << 1 | ((b2 >> bit) & 1u));
-    if (code < 1 || code > 4) other = true;
-    v |= ((code - 1u) & 3u) << (2 * q);
-    if (bases) bases[p0 + q] = (uint8_t) code;
+  const int valid = len - p0 < 16 ? len - p0 : 16;
+  const int64_t r = first + p0;
+  const int64_t group = r >> 6;
+  const int bit = (int) (r & 63);
+  uint64_t a = sdfPlane(file, group * 3) >> bit, b = sdfPlane(file, group * 3 + 1) >> bit, c = sdfPlane(file, group * 3 + 2) >> bit;
+  if (bit + valid > 64) {   // the granule runs on into the next group of 64 residues
+    a |= sdfPlane(file, group * 3 + 3) << (64 - bit);
+    b |= sdfPlane(file, group * 3 + 4) << (64 - bit);
+    c |= sdfPlane(file, group * 3 + 5) << (64 - bit);
   }
-  packed[g] = v;
-  otherFlag[g] = other ? 1 : 0;
+  const uint32_t m = valid == 16 ? 0xffffu : (1u << valid) - 1u;
+  const uint32_t A = (uint32_t) a & m, B = (uint32_t) b & m, C = (uint32_t) c & m;
+  packed[g] = sdfSpread16(~C & m) | (sdfSpread16(~(B ^ C) & m) << 1);
+  otherFlag[g] = (((~A & ~B & ~C) | (A & (B | C))) & m) ? 1 : 0;
+  if (!bases) return;
+  uint32_t w[4];
+  for (int k = 0; k < 4; ++k) {   // four residues per word: bit j of the nibble -> byte j
+    const uint32_t na = (A >> (4 * k)) & 15u, nb = (B >> (4 * k)) & 15u, nc = (C >> (4 * k)) & 15u;
+    w[k] = (((na * 0x00204081u) & 0x01010101u) << 2) | (((nb * 0x00204081u) & 0x01010101u) << 1) | ((nc * 0x00204081u) & 0x01010101u);
+  }
+#if defined(__CUDA_ARCH__)
+  if (valid == 16) { *reinterpret_cast<uint4*>(bases + p0) = make_uint4(w[0], w[1], w[2], w[3]); return; }
+#endif
+  for (int q = 0; q < valid; ++q) bases[p0 + q] = (uint8_t) (w[q >> 2] >> (8 * (q & 3)));
 }
 // mask word m gathers the flags of granules [32 m, 32 m + 32)
 VCE_HD void sdfMaskWord(const uint8_t* otherFlag, int32_t granules, int32_t m, uint32_t* nmask) {

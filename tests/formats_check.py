@@ -271,6 +271,7 @@ def check_sdf_decode(engine, seeds=range(8)):
         rng = np.random.default_rng(seed)
         lens = [int(x) for x in rng.integers(1, 5000, 4)] + [1, 15, 16, 17, 63, 64, 65, 511, 512, 513]
         seqs = [random_codes(rng, n) for n in lens]
+        seqs.append(rng.integers(0, 8, 777).astype(np.uint8))   # codes 5..7 cannot come from the formatter; they must still round-trip
         allc = np.concatenate(seqs)
         file = fo.sdf_planes_write(allc)
         assert np.array_equal(fo.sdf_planes_read(file, 0, allc.size), allc)
